@@ -1,0 +1,75 @@
+"""Independent pure-Python restatement of ksw_extend2, used ONLY to
+differential-test oracle/qmo_ksw.c (two restatements written separately from the same spec, as
+SURVEY.md section 7 'hard part 6' asks).  Test infrastructure; small cases only."""
+
+
+def score(a, b, t, q):
+    if t > 3 or q > 3:
+        return -1
+    return a if t == q else -b
+
+
+def ksw_extend2(query, target, h0, w, end_bonus, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100):
+    qlen, tlen = len(query), len(target)
+    H = [0] * (qlen + 1)
+    E = [0] * (qlen + 1)
+    H[0] = h0
+    if qlen >= 1:
+        H[1] = h0 - (o_ins + e_ins) if h0 > o_ins + e_ins else 0
+    j = 2
+    while j <= qlen and H[j - 1] > e_ins:
+        H[j] = H[j - 1] - e_ins
+        j += 1
+    maxsc = max(a, -b, -1)
+    w = min(w, max(1, int((qlen * maxsc + end_bonus - o_ins) / e_ins + 1.0)),
+            max(1, int((qlen * maxsc + end_bonus - o_del) / e_del + 1.0)))
+    mx, mx_i, mx_j, mx_ie, gscore, max_off = h0, -1, -1, -1, -1, 0
+    beg, end = 0, qlen
+    cells = 0
+    for i in range(tlen):
+        f, m, mj = 0, 0, -1
+        beg = max(beg, i - w)
+        end = min(end, i + w + 1, qlen)
+        h1 = max(0, h0 - (o_del + e_del * (i + 1))) if beg == 0 else 0
+        j = beg
+        while j < end:
+            M, e = H[j], E[j]
+            H[j] = h1
+            M = M + score(a, b, target[i], query[j]) if M else 0
+            h = max(M, e, f)
+            h1 = h
+            if not (m > h):
+                mj = j
+            m = max(m, h)
+            e = max(e - e_del, max(M - (o_del + e_del), 0))
+            E[j] = e
+            f = max(f - e_ins, max(M - (o_ins + e_ins), 0))
+            j += 1
+        cells += max(0, end - beg)
+        H[end] = h1
+        E[end] = 0
+        if j == qlen:
+            if not (gscore > h1):
+                mx_ie = i
+            gscore = max(gscore, h1)
+        if m == 0:
+            break
+        if m > mx:
+            mx, mx_i, mx_j = m, i, mj
+            max_off = max(max_off, abs(mj - i))
+        elif zdrop > 0:
+            if i - mx_i > mj - mx_j:
+                if mx - m - ((i - mx_i) - (mj - mx_j)) * e_del > zdrop:
+                    break
+            else:
+                if mx - m - ((mj - mx_j) - (i - mx_i)) * e_ins > zdrop:
+                    break
+        j = beg
+        while j < end and H[j] == 0 and E[j] == 0:
+            j += 1
+        beg = j
+        j = end
+        while j >= beg and H[j] == 0 and E[j] == 0:
+            j -= 1
+        end = min(j + 2, qlen)
+    return (mx, mx_j + 1, mx_i + 1, mx_ie + 1, gscore, max_off), cells

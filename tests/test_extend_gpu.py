@@ -1,0 +1,82 @@
+"""GPU parity (bit-exact): the CUDA batched extension kernel, called through the C-ABI, against the CPU
+oracle's ksw_extend2 on the same tasks.  Integer work => every field must be identical."""
+import numpy as np
+import pytest
+
+from tests import extgen
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("score", "qle", "tle", "gtle", "gscore", "max_off")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from quasimodo_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def oracle_results(pairs, h0s, ws, eb, retry=False, prev_h0=False):
+    from oracle import qmo_py
+    out = []
+    for (q, t), h0, w in zip(pairs, h0s, ws):
+        cells, prev, res, wu = 0, (int(h0) if prev_h0 else -1), None, int(w)
+        for a in range(2 if retry else 1):
+            wu = int(w) << a
+            res, c = qmo_py.ksw_extend2(q, t, int(h0), wu, eb)
+            cells += c
+            if res[0] == prev or res[5] < (wu >> 1) + (wu >> 2):
+                break
+            prev = res[0]
+        out.append(res + (wu, cells))
+    return out
+
+
+def check(ctx, pairs, h0s, ws, eb, flags=0):
+    from quasimodo_b200.api import pack_ext_tasks
+    seq, tasks = pack_ext_tasks(pairs, h0s, ws, eb, flags)
+    got = ctx.extend_batch_host(seq, tasks)
+    want = oracle_results(pairs, h0s, ws, eb, retry=bool(flags & 1), prev_h0=bool(flags & 2))
+    bad = []
+    for i, wnt in enumerate(want):
+        g = tuple(int(got[i][f]) for f in FIELDS) + (int(got[i]["w_used"]), int(got[i]["cells"]))
+        if g != wnt:
+            bad.append((i, g, wnt, len(pairs[i][0]), len(pairs[i][1]), int(h0s[i]), int(ws[i])))
+    assert not bad, f"{len(bad)} of {len(want)} tasks differ; first: {bad[:3]}"
+
+
+@pytest.mark.parametrize("eb", [0, 5])
+def test_extend_random(ctx, eb):
+    rng = np.random.default_rng(1234 + eb)
+    pairs, h0s, ws = extgen.random_tasks(rng, 4000)
+    check(ctx, pairs, h0s, ws, eb)
+
+
+def test_extend_adversarial(ctx):
+    pairs, h0s, ws = extgen.adversarial_tasks()
+    check(ctx, pairs, h0s, ws, 5)
+    check(ctx, pairs, h0s, ws, 0)
+
+
+def test_extend_long_queries(ctx):
+    rng = np.random.default_rng(77)
+    pairs, h0s, ws = extgen.random_tasks(rng, 600, max_qlen=500)
+    check(ctx, pairs, h0s, ws, 5)
+
+
+@pytest.mark.parametrize("flags", [1, 3])
+def test_extend_band_retry(ctx, flags):
+    rng = np.random.default_rng(4321)
+    pairs, h0s, ws = extgen.random_tasks(rng, 2000)
+    ws = np.where(ws > 50, 10, ws)        # small bands so that the 2w retry actually triggers
+    check(ctx, pairs, h0s, ws, 5, flags=flags)
+
+
+def test_extend_rejects_bad_task(ctx):
+    from quasimodo_b200 import QmError
+    from quasimodo_b200.api import pack_ext_tasks
+    seq, tasks = pack_ext_tasks([(np.zeros(600, np.uint8), np.zeros(10, np.uint8))], [31], [100], 5)
+    with pytest.raises(QmError):
+        ctx.extend_batch_host(seq, tasks)

@@ -1,0 +1,78 @@
+"""Oracle self-checks (CPU): the C restatement of ksw_extend2 against the independent Python
+restatement of SURVEY.md Appendix A.3, on random and adversarial tasks."""
+import numpy as np
+import pytest
+
+from oracle import ksw_py, qmo_py
+
+
+def mutate(rng, seq, sub=0.05, indel=0.02):
+    out = []
+    for b in seq:
+        r = rng.random()
+        if r < indel / 2:
+            continue
+        if r < indel:
+            out.append(int(rng.integers(0, 4)))
+        if rng.random() < sub:
+            out.append(int(rng.integers(0, 4)))
+        else:
+            out.append(int(b))
+    return np.array(out, dtype=np.uint8)
+
+
+def random_task(rng):
+    qlen = int(rng.integers(1, 130))
+    q = rng.integers(0, 4, qlen).astype(np.uint8)
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        t = rng.integers(0, 4, int(rng.integers(0, 2 * qlen + 10))).astype(np.uint8)
+    else:
+        t = mutate(rng, q, sub=[0.0, 0.03, 0.12][kind - 1], indel=[0.0, 0.01, 0.05][kind - 1])
+        t = np.concatenate([t, rng.integers(0, 4, int(rng.integers(0, qlen + 10))).astype(np.uint8)])
+    if rng.random() < 0.1 and qlen > 2:
+        q[rng.integers(0, qlen)] = 4
+    if rng.random() < 0.05 and len(t) > 2:
+        t[rng.integers(0, len(t))] = 4
+    h0 = int(rng.integers(1, 160))
+    w = int(rng.choice([1, 3, 5, 20, 100, 200]))
+    eb = int(rng.choice([0, 5]))
+    return q, t, h0, w, eb
+
+
+def test_extend_c_vs_python_random():
+    rng = np.random.default_rng(7)
+    n_gs = 0
+    for _ in range(1500):
+        q, t, h0, w, eb = random_task(rng)
+        c_res, c_cells = qmo_py.ksw_extend2(q, t, h0, w, eb)
+        p_res, p_cells = ksw_py.ksw_extend2(list(q), list(t), h0, w, eb)
+        assert c_res == p_res, (list(q), list(t), h0, w, eb)
+        assert c_cells == p_cells
+        n_gs += c_res[4] > 0
+    assert n_gs > 100  # the to-end path is exercised
+
+
+@pytest.mark.parametrize("q,t,h0,w,eb,expect", [
+    # perfect 10-mer extension from h0=31: score 41 at (10,10); to-end score 41 at row 10
+    ([0, 1, 2, 3, 0, 1, 2, 3, 0, 1], [0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 2], 31, 100, 5, (41, 10, 10, 10, 41, 0)),
+    # empty target: nothing extends
+    ([0, 1, 2], [], 31, 100, 5, (31, 0, 0, 0, -1, 0)),
+    # all-N query: every cell scores -1, best stays h0
+    ([4, 4, 4], [0, 1, 2, 3], 10, 100, 5, (10, 0, 0, 3, 7, 0)),
+])
+def test_extend_known_answers(q, t, h0, w, eb, expect):
+    res, _ = qmo_py.ksw_extend2(q, t, h0, w, eb)
+    py, _ = ksw_py.ksw_extend2(q, t, h0, w, eb)
+    assert res == py
+    assert res == expect
+
+
+def test_global_simple():
+    q = [0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3]
+    s, cig = qmo_py.ksw_global2(q, q, 5)
+    assert s == 12 and cig == [(0, 12)]
+    t = q[:6] + [2, 2] + q[6:]           # 2-base deletion from the read's view
+    s, cig = qmo_py.ksw_global2(q, t, 5)
+    assert s == 12 - 8 and sum(l for op, l in cig if op in (0, 1)) == 12 and sum(l for op, l in cig if op in (0, 2)) == 14
+    assert [op for op, _ in cig] == [0, 2, 0]
