@@ -96,6 +96,33 @@ int qm_extend_batch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const 
 int qm_extend_batch_host(qm_ctx *ctx, const qm_opt *opt, const uint8_t *h_seq, size_t seq_bytes,
                          const qm_ext_task *h_tasks, int64_t n_tasks, qm_ext_result *h_out);
 
+/* ---- synthetic inputs: deterministic, index-addressable read-pair simulator ----
+ * The reference ships no reads (data/PRJEB32127.txt lists ENA URLs; no network), so benchmark and
+ * parity inputs are simulated from the bundled genomes.  Pair i is a pure function of (seed, i):
+ * any shard can be generated independently, on the host or on the device, with identical bytes.
+ * genome: base codes 0..3 of all source genomes, source s at [src_off[s], src_off[s]+src_len[s]);
+ * src_cum[s] = floor(2^32 * cumulative weight share) (last = 2^32-1), weight = copies x length.
+ * Output layout ("read batch", used by every later stage): reads 2i / 2i+1 are the mates of pair i,
+ * codes[r*stride + j] in 0..4 (4 = N), quals[r*stride + j] = phred, stride >= read_len. */
+typedef struct {
+    uint64_t seed;
+    int32_t  read_len;
+    int32_t  ins_mean, ins_sd, ins_max;   /* insert size model N(mean, sd) clipped to [read_len, max] */
+    int32_t  n_sources;
+    int32_t  indel_ppm;                   /* indel events per 1e6 bases (cfg 5: 200)                  */
+    int32_t  n_ppm;                       /* bases forced to N per 1e6 (1000)                         */
+    int32_t  lowq_ppm;                    /* bases with Q2..Q12 per 1e6 (20000)                       */
+    int32_t  reserved[3];
+} qm_sim_params;
+
+int qm_simulate_pairs_host(const qm_sim_params *p, const uint8_t *h_genome, const int64_t *src_off,
+                           const int64_t *src_len, const uint32_t *src_cum, int64_t pair0, int64_t n_pairs,
+                           int32_t stride, uint8_t *h_codes, uint8_t *h_quals, int32_t *h_src /* may be NULL */,
+                           int64_t *h_pos /* may be NULL */);
+int qm_simulate_pairs(qm_ctx *ctx, const qm_sim_params *p, const uint8_t *d_genome, const int64_t *h_src_off,
+                      const int64_t *h_src_len, const uint32_t *h_src_cum, int64_t pair0, int64_t n_pairs,
+                      int32_t stride, uint8_t *d_codes, uint8_t *d_quals, void *stream);
+
 /* ---- measurement helper: whole-GPU issue rate of the DPX instruction the extension kernel leans on
  * (register-resident dependent chains of __viaddmax_s16x2_relu / __viaddmax_s32_relu on every SM).
  * Returns giga warp-lane instructions per second in *out_gops (packed: per 32-bit lane op).

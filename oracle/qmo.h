@@ -59,6 +59,63 @@ int64_t qmo_ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t 
 int qmo_ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                     const qmo_opt_t *o, int w, int *n_cigar, uint32_t *cigar, int max_cigar);
 
+/* ---- reference + k-mer index (replaces `bwa index`, rules/index.smk:13) ---- */
+#define QMO_MAX_SEEDS 64
+#define QMO_MAX_REGS  16
+#define QMO_MAX_CIGAR 21
+#define QMO_OCC_CAP   32
+
+typedef struct qmo_ref qmo_ref_t;
+/* codes: concatenated forward strands (0..3), contig i has lens[i] bases */
+qmo_ref_t *qmo_ref_create(const uint8_t *codes, int n_contigs, const int64_t *lens, int k);
+void qmo_ref_destroy(qmo_ref_t *r);
+int64_t qmo_ref_lpac(const qmo_ref_t *r);
+
+typedef struct { int64_t rbeg; int32_t qbeg, len; } qmo_seed_t;              /* 16 B */
+typedef struct {
+    int64_t rb, re;               /* [rb,re) in bwa's doubled coordinates (>= l_pac: reverse strand) */
+    int32_t qb, qe;
+    int32_t rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0;
+} qmo_reg_t;                                                                   /* 64 B */
+typedef struct {
+    int32_t rid, pos;             /* 0-based leftmost position on contig rid                         */
+    uint16_t flag; uint8_t mapq; uint8_t n_cigar;
+    int32_t score, sub, nm;
+    int32_t mate_rid, mate_pos, tlen;
+    int32_t qb, qe;               /* aligned interval of the read as sequenced                        */
+    uint32_t cigar[QMO_MAX_CIGAR];/* BAM encoding len<<4|op, ops M=0 I=1 D=2 S=4                       */
+} qmo_aln_t;                                                                   /* 128 B */
+typedef struct { int32_t low, high, failed, pad; double avg, std; } qmo_pestat_t;   /* x4: FF FR RF RR */
+
+/* log of every ksw_extend2 call made while aligning (stage-local parity: "same seeds => same tuples") */
+typedef struct {
+    uint32_t q_off, t_off; int32_t qlen, tlen, h0, w, end_bonus; uint32_t flags;   /* = qm_ext_task */
+} qmo_ext_task_t;
+typedef struct {
+    uint8_t *seq; int64_t seq_len, seq_cap;
+    qmo_ext_task_t *tasks; qmo_ext_t *results; int32_t *w_used; int64_t *cells; int64_t n, cap;
+} qmo_ext_log_t;
+
+/* MEM seeds of one read (codes 0..4), sorted by (qbeg, rbeg); returns count */
+int qmo_collect_seeds(const qmo_ref_t *R, const qmo_opt_t *o, const uint8_t *read, int len, qmo_seed_t *out);
+
+/* single-end stage for reads [0,n): seeds -> chains -> extension -> sorted, de-duplicated regions
+ * (bwamem.c mem_align1_core).  reads: n x stride codes.  Any of the outputs may be NULL. */
+void qmo_align_se(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n, const uint8_t *reads, int stride,
+                  const int32_t *lens, qmo_seed_t *seeds, int32_t *n_seeds, qmo_reg_t *regs, int32_t *n_regs,
+                  qmo_ext_log_t *log, int64_t *cells_total);
+
+/* insert-size model from the first n_pairs pairs' regions (bwamem_pair.c mem_pestat) */
+void qmo_pestat(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, const qmo_reg_t *regs,
+                const int32_t *n_regs, qmo_pestat_t pes[4]);
+
+/* paired-end stage (bwamem_pair.c mem_sam_pe without mate rescue) + CIGAR generation
+ * (bwamem.c mem_reg2aln / bwa.c bwa_gen_cigar2).  pair_id0 = global index of pair 0 (tie-break hash).
+ * regs/n_regs are modified in place (primary marking re-sorts them). */
+void qmo_pair_and_finish(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, int64_t pair_id0,
+                         const uint8_t *reads, int stride, const int32_t *lens,
+                         qmo_reg_t *regs, int32_t *n_regs, const qmo_pestat_t pes[4], qmo_aln_t *alns);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,3 +74,108 @@ def ksw_global2(query, target, w, opt=None, max_cigar=64):
     if n.value < 0:
         raise OverflowError("cigar overflow")
     return int(s), [(int(c & 0xf), int(c >> 4)) for c in cig[:n.value]]
+
+
+# ---------------------------------------------------------------------------------------------
+# pipeline stages
+MAX_SEEDS, MAX_REGS, MAX_CIGAR = 64, 16, 21
+SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])
+REG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"),
+                      ("truesc", "<i4"), ("sub", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"),
+                      ("seedcov", "<i4"), ("secondary", "<i4"), ("seedlen0", "<i4")])
+ALN_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("flag", "<u2"), ("mapq", "u1"), ("n_cigar", "u1"),
+                      ("score", "<i4"), ("sub", "<i4"), ("nm", "<i4"), ("mate_rid", "<i4"), ("mate_pos", "<i4"),
+                      ("tlen", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("cigar", "<u4", (MAX_CIGAR,))])
+PESTAT_DTYPE = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+EXT_TASK_DTYPE = np.dtype([("q_off", "<u4"), ("t_off", "<u4"), ("qlen", "<i4"), ("tlen", "<i4"),
+                           ("h0", "<i4"), ("w", "<i4"), ("end_bonus", "<i4"), ("flags", "<u4")])
+assert REG_DTYPE.itemsize == 64 and ALN_DTYPE.itemsize == 128 and SEED_DTYPE.itemsize == 16
+
+
+class ExtLog(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("seq_len", C.c_int64), ("seq_cap", C.c_int64),
+                ("tasks", C.c_void_p), ("results", C.c_void_p), ("w_used", C.c_void_p), ("cells", C.c_void_p),
+                ("n", C.c_int64), ("cap", C.c_int64)]
+
+
+class Ref:
+    def __init__(self, codes, lens, k=31):
+        L = lib()
+        L.qmo_ref_create.restype = C.c_void_p
+        L.qmo_ref_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.qmo_ref_destroy.argtypes = [C.c_void_p]
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        self.l_pac = int(lens.sum())
+        self.lens = lens
+        self.k = k
+        self._h = L.qmo_ref_create(codes.ctypes.data, len(lens), lens.ctypes.data, k)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qmo_ref_destroy(self._h)
+            self._h = None
+
+
+def _libc_free(ptr):
+    C.CDLL(None).free(C.c_void_p(ptr))
+
+
+def align_se(ref, reads, lens, opt=None, want_log=False):
+    """-> dict(seeds, n_seeds, regs, n_regs, cells[, log])"""
+    opt = opt or default_opt()
+    L = lib()
+    L.qmo_align_se.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    seeds = np.zeros((n, MAX_SEEDS), dtype=SEED_DTYPE)
+    n_seeds = np.zeros(n, dtype=np.int32)
+    regs = np.zeros((n, MAX_REGS), dtype=REG_DTYPE)
+    n_regs = np.zeros(n, dtype=np.int32)
+    cells = C.c_int64(0)
+    log = ExtLog()
+    L.qmo_align_se(ref._h, C.byref(opt), n, reads.ctypes.data, stride, lens.ctypes.data, seeds.ctypes.data,
+                   n_seeds.ctypes.data, regs.ctypes.data, n_regs.ctypes.data, C.byref(log) if want_log else None,
+                   C.byref(cells))
+    out = dict(seeds=seeds, n_seeds=n_seeds, regs=regs, n_regs=n_regs, cells=cells.value)
+    if want_log:
+        m = log.n
+        if m:
+            out["log"] = dict(
+                seq=np.ctypeslib.as_array(C.cast(log.seq, C.POINTER(C.c_uint8)), (log.seq_len,)).copy(),
+                tasks=np.frombuffer(C.string_at(log.tasks, m * 32), dtype=EXT_TASK_DTYPE).copy(),
+                results=np.frombuffer(C.string_at(log.results, m * 24), dtype=EXT_DTYPE).copy(),
+                w_used=np.frombuffer(C.string_at(log.w_used, m * 4), dtype="<i4").copy(),
+                cells=np.frombuffer(C.string_at(log.cells, m * 8), dtype="<i8").copy())
+            for p in (log.seq, log.tasks, log.results, log.w_used, log.cells):
+                _libc_free(p)
+        else:
+            out["log"] = dict(seq=np.zeros(1, np.uint8), tasks=np.zeros(0, EXT_TASK_DTYPE), results=np.zeros(0, EXT_DTYPE),
+                              w_used=np.zeros(0, "<i4"), cells=np.zeros(0, "<i8"))
+    return out
+
+
+def pestat(ref, regs, n_regs, opt=None):
+    opt = opt or default_opt()
+    L = lib()
+    L.qmo_pestat.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    pes = np.zeros(4, dtype=PESTAT_DTYPE)
+    L.qmo_pestat(ref._h, C.byref(opt), len(n_regs) // 2, regs.ctypes.data, n_regs.ctypes.data, pes.ctypes.data)
+    return pes
+
+
+def pair_and_finish(ref, reads, lens, regs, n_regs, pes, pair_id0=0, opt=None):
+    """regs / n_regs are modified in place (primary marking re-sorts them)"""
+    opt = opt or default_opt()
+    L = lib()
+    L.qmo_pair_and_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    alns = np.zeros(n, dtype=ALN_DTYPE)
+    L.qmo_pair_and_finish(ref._h, C.byref(opt), n // 2, int(pair_id0), reads.ctypes.data, stride, lens.ctypes.data,
+                          regs.ctypes.data, n_regs.ctypes.data, pes.ctypes.data, alns.ctypes.data)
+    return alns

@@ -25,6 +25,12 @@ class Opt(C.Structure):
                 ("min_chain_weight", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class SimParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("read_len", C.c_int32), ("ins_mean", C.c_int32), ("ins_sd", C.c_int32),
+                ("ins_max", C.c_int32), ("n_sources", C.c_int32), ("indel_ppm", C.c_int32), ("n_ppm", C.c_int32),
+                ("lowq_ppm", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
 EXT_TASK_DTYPE = np.dtype([("q_off", "<u4"), ("t_off", "<u4"), ("qlen", "<i4"), ("tlen", "<i4"),
                            ("h0", "<i4"), ("w", "<i4"), ("end_bonus", "<i4"), ("flags", "<u4")])
 EXT_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
@@ -36,6 +42,7 @@ QM_EXT_PREV_H0 = 2
 EXPORTS = [
     "qm_opt_default", "qm_ctx_create", "qm_ctx_destroy", "qm_last_error", "qm_version",
     "qm_device_sm_count", "qm_extend_batch", "qm_extend_batch_host", "qm_dpx_peak_sync",
+    "qm_simulate_pairs_host", "qm_simulate_pairs",
 ]
 
 
@@ -56,6 +63,10 @@ def lib():
         L.qm_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.qm_extend_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p]
         L.qm_dpx_peak_sync.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.qm_simulate_pairs_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qm_simulate_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
