@@ -96,6 +96,88 @@ int qm_extend_batch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const 
 int qm_extend_batch_host(qm_ctx *ctx, const qm_opt *opt, const uint8_t *h_seq, size_t seq_bytes,
                          const qm_ext_task *h_tasks, int64_t n_tasks, qm_ext_result *h_out);
 
+/* ---- reference index (replaces `bwa index`, rules/index.smk:13) ----
+ * k-mer hash index (k = opt->min_seed_len <= 32) over the forward strands of the concatenated contigs
+ * plus the 2-bit packed reference; both live in device memory owned by the index object. */
+typedef struct qm_index qm_index;
+#define QM_MAX_CONTIGS 16
+int     qm_index_build(qm_ctx *ctx, const uint8_t *h_codes /* 0..3 */, int n_contigs, const int64_t *h_lens,
+                       int k, qm_index **out);
+void    qm_index_destroy(qm_ctx *ctx, qm_index *idx);
+int64_t qm_index_lpac(const qm_index *idx);
+
+/* ---- alignment of read pairs (replaces `bwa mem -k 31 ref r1 r2`, rules/bwa.smk:15) ----
+ * Read batch layout: see the simulator below (codes/quals, reads 2i and 2i+1 are mates).
+ * Stage 1  qm_align_se      : seeding (all MEMs >= k via the hash index), chaining (bwamem.c mem_chain,
+ *                             mem_chain_flt), extension (mem_chain2aln -> the batched ksw_extend2 kernel),
+ *                             redundancy removal (mem_sort_dedup_patch) -> per-read region lists.
+ * Stage 2  qm_pestat_sync   : insert-size model of the batch (bwamem_pair.c mem_pestat).
+ * Stage 3  qm_pair_finish   : primary marking, pairing, MAPQ (mem_sam_pe without mate rescue), CIGAR/NM
+ *                             (mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2), SAM flags -> qm_aln records.
+ * Hard limits (shared with the oracle): QM_MAX_SEEDS seeds and QM_MAX_REGS regions per read, k-mers with
+ * more than min(max_occ, QM_OCC_CAP) occurrences are ignored, QM_MAX_CIGAR operations per alignment. */
+#define QM_MAX_SEEDS 64
+#define QM_MAX_REGS  16
+#define QM_MAX_CIGAR 21
+#define QM_OCC_CAP   32
+
+typedef struct { int64_t rbeg; int32_t qbeg, len; } qm_seed;                 /* 16 B */
+typedef struct {
+    int64_t rb, re;               /* [rb,re) in bwa's doubled coordinates (>= l_pac: reverse strand) */
+    int32_t qb, qe;
+    int32_t rid, score, truesc, sub, csub, sub_n, w, seedcov, secondary, seedlen0;
+} qm_reg;                                                                     /* 64 B */
+typedef struct {
+    int32_t  rid, pos;            /* 0-based leftmost position on contig rid; -1 when unplaced        */
+    uint16_t flag; uint8_t mapq; uint8_t n_cigar;   /* n_cigar = 255: CIGAR overflow (read unmapped)  */
+    int32_t  score, sub, nm;
+    int32_t  mate_rid, mate_pos, tlen;
+    int32_t  qb, qe;              /* aligned interval of the read as sequenced                        */
+    uint32_t cigar[QM_MAX_CIGAR]; /* BAM encoding len<<4|op, ops M=0 I=1 D=2 S=4                       */
+} qm_aln;                                                                     /* 128 B */
+typedef struct { int32_t low, high, failed, pad; double avg, std; } qm_pestat;  /* x4: FF FR RF RR */
+
+/* diagnostic / parity entry: seeds of every read, sorted by (qbeg, rbeg) */
+int qm_collect_seeds(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
+                     const int32_t *d_lens, int64_t n_reads, qm_seed *d_seeds /* [n][QM_MAX_SEEDS] */,
+                     int32_t *d_n_seeds, void *stream);
+/* d_cells (may be NULL): one int64, += executed extension cells (GCUPS work unit) */
+int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
+                const int32_t *d_lens, int64_t n_reads, qm_reg *d_regs /* [n][QM_MAX_REGS] */, int32_t *d_n_regs,
+                int64_t *d_cells, void *stream);
+int qm_pestat_sync(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm_reg *d_regs, const int32_t *d_n_regs,
+                   int64_t n_pairs, qm_pestat h_pes[4], void *stream);
+int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
+                   const int32_t *d_lens, int64_t n_pairs, int64_t pair_id0, qm_reg *d_regs, int32_t *d_n_regs,
+                   const qm_pestat h_pes[4], qm_aln *d_alns, void *stream);
+
+/* ---- pileup counting (replaces the counting of `bcftools mpileup`, rules/vcfcall.smk:115, and of
+ * `samtools mpileup`, rules/vcfcall.smk:39; upstream mplp_func / bam_plp_push / overlap_push /
+ * bcf_call_glfgen) ----
+ * Count tensor: int32 [QM_NCH][l_pac], CHANNEL-MAJOR planes (plane c at d_counts + c*l_pac), position =
+ * forward coordinate on the concatenated contigs.  Channels:
+ *   0-3 A,C,G,T forward strand, BQ >= min_bq      4 N forward        5 deleted base, forward read
+ *   6-9 A,C,G,T reverse strand                   10 N reverse       11 deleted base, reverse read
+ *  12 an insertion follows this base             13 a deletion follows this base
+ *  14 raw depth (every aligned base of every admitted read, before the BQ filter = bcftools ori_depth)
+ *  15 admitted reads whose leftmost aligned base is here
+ * Admission as bcftools mpileup: skip UNMAP|SECONDARY|QCFAIL|DUP, MAPQ < min_mapq, and paired reads that
+ * are not proper pairs unless count_orphans; mate-overlap quality rewrite unless ignore_overlaps; BAQ off
+ * (-B) and no depth cap (deliberate).  Accumulates (+=) into d_counts. */
+#define QM_NCH 16
+typedef struct {
+    int32_t min_mapq;        /* -q (0)   */
+    int32_t min_bq;          /* -Q (13)  */
+    int32_t count_orphans;   /* -A       */
+    int32_t ignore_overlaps; /* -x       */
+} qm_pileup_opt;
+void qm_pileup_opt_default(qm_pileup_opt *p);
+int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
+                         const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                         int64_t n_pairs, int32_t *d_counts, void *stream);
+/* planes [QM_NCH][l_pac] -> rows [l_pac][QM_NCH] (row order of the count TSV) */
+int qm_counts_to_rows(qm_ctx *ctx, const qm_index *idx, const int32_t *d_planes, int32_t *d_rows, void *stream);
+
 /* ---- synthetic inputs: deterministic, index-addressable read-pair simulator ----
  * The reference ships no reads (data/PRJEB32127.txt lists ENA URLs; no network), so benchmark and
  * parity inputs are simulated from the bundled genomes.  Pair i is a pure function of (seed, i):

@@ -116,6 +116,24 @@ void qmo_pair_and_finish(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs
                          const uint8_t *reads, int stride, const int32_t *lens,
                          qmo_reg_t *regs, int32_t *n_regs, const qmo_pestat_t pes[4], qmo_aln_t *alns);
 
+/* ---- pileup counting (bcftools mpileup -B semantics, rules/vcfcall.smk:115) ----
+ * counts: int32 [l_pac][16], row = forward reference position (contigs concatenated), channels:
+ *  0-3 A,C,G,T forward (BQ >= min_bq)   4 N forward   5 deleted forward
+ *  6-9 A,C,G,T reverse                 10 N reverse  11 deleted reverse
+ *  12 insertion follows this base  13 deletion follows this base
+ *  14 raw depth (every non-deleted base of every admitted read, before the BQ filter = bcftools ori_depth)
+ *  15 admitted reads whose leftmost aligned base is here */
+#define QMO_NCH 16
+typedef struct {
+    int32_t min_mapq;        /* -q (0)   */
+    int32_t min_bq;          /* -Q (13)  */
+    int32_t count_orphans;   /* -A       */
+    int32_t ignore_overlaps; /* -x       */
+} qmo_pileup_opt_t;
+void qmo_pileup_opt_default(qmo_pileup_opt_t *p);
+void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs, const qmo_aln_t *alns,
+                const uint8_t *reads, const uint8_t *quals, int stride, const int32_t *lens, int32_t *counts);
+
 #ifdef __cplusplus
 }
 #endif

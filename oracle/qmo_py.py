@@ -179,3 +179,30 @@ def pair_and_finish(ref, reads, lens, regs, n_regs, pes, pair_id0=0, opt=None):
     L.qmo_pair_and_finish(ref._h, C.byref(opt), n // 2, int(pair_id0), reads.ctypes.data, stride, lens.ctypes.data,
                           regs.ctypes.data, n_regs.ctypes.data, pes.ctypes.data, alns.ctypes.data)
     return alns
+
+
+NCH = 16
+
+
+class PileupOpt(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("min_bq", C.c_int32), ("count_orphans", C.c_int32),
+                ("ignore_overlaps", C.c_int32)]
+
+
+def pileup(ref, alns, reads, quals, lens, popt=None):
+    """-> int32 counts [l_pac, 16] (rows = forward reference positions, contigs concatenated)"""
+    L = lib()
+    L.qmo_pileup.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                             C.c_void_p, C.c_void_p]
+    if popt is None:
+        popt = PileupOpt()
+        L.qmo_pileup_opt_default(C.byref(popt))
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    alns = np.ascontiguousarray(alns, dtype=ALN_DTYPE)
+    counts = np.zeros((ref.l_pac, NCH), dtype=np.int32)
+    L.qmo_pileup(ref._h, C.byref(popt), n // 2, alns.ctypes.data, reads.ctypes.data, quals.ctypes.data, stride,
+                 lens.ctypes.data, counts.ctypes.data)
+    return counts

@@ -31,19 +31,55 @@ class SimParams(C.Structure):
                 ("lowq_ppm", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class PileupOpt(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("min_bq", C.c_int32), ("count_orphans", C.c_int32),
+                ("ignore_overlaps", C.c_int32)]
+
+
+MAX_SEEDS, MAX_REGS, MAX_CIGAR, NCH = 64, 16, 21, 16
 EXT_TASK_DTYPE = np.dtype([("q_off", "<u4"), ("t_off", "<u4"), ("qlen", "<i4"), ("tlen", "<i4"),
                            ("h0", "<i4"), ("w", "<i4"), ("end_bonus", "<i4"), ("flags", "<u4")])
 EXT_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
                              ("gscore", "<i4"), ("max_off", "<i4"), ("w_used", "<i4"), ("cells", "<i4")])
+SEED_DTYPE = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])
+REG_DTYPE = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("rid", "<i4"), ("score", "<i4"),
+                      ("truesc", "<i4"), ("sub", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"),
+                      ("seedcov", "<i4"), ("secondary", "<i4"), ("seedlen0", "<i4")])
+ALN_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("flag", "<u2"), ("mapq", "u1"), ("n_cigar", "u1"),
+                      ("score", "<i4"), ("sub", "<i4"), ("nm", "<i4"), ("mate_rid", "<i4"), ("mate_pos", "<i4"),
+                      ("tlen", "<i4"), ("qb", "<i4"), ("qe", "<i4"), ("cigar", "<u4", (MAX_CIGAR,))])
+PESTAT_DTYPE = np.dtype([("low", "<i4"), ("high", "<i4"), ("failed", "<i4"), ("pad", "<i4"), ("avg", "<f8"), ("std", "<f8")])
+assert REG_DTYPE.itemsize == 64 and ALN_DTYPE.itemsize == 128 and SEED_DTYPE.itemsize == 16 and PESTAT_DTYPE.itemsize == 32
 QM_EXT_BAND_RETRY = 1
 QM_EXT_PREV_H0 = 2
 
-# every symbol include/quasimodo_b200.h declares (checked by tests/test_cabi.py)
-EXPORTS = [
-    "qm_opt_default", "qm_ctx_create", "qm_ctx_destroy", "qm_last_error", "qm_version",
-    "qm_device_sm_count", "qm_extend_batch", "qm_extend_batch_host", "qm_dpx_peak_sync",
-    "qm_simulate_pairs_host", "qm_simulate_pairs",
-]
+_P, _I, _L = C.c_void_p, C.c_int32, C.c_int64
+
+# every symbol include/quasimodo_b200.h declares (checked by tests/test_cabi.py): name -> (restype, argtypes)
+SIGNATURES = {
+    "qm_opt_default": (None, [_P]),
+    "qm_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "qm_ctx_destroy": (None, [_P]),
+    "qm_last_error": (C.c_char_p, [_P]),
+    "qm_version": (C.c_char_p, []),
+    "qm_device_sm_count": (C.c_int, [_P]),
+    "qm_extend_batch": (C.c_int, [_P, _P, _P, _P, _L, _P, _P]),
+    "qm_extend_batch_host": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _L, _P]),
+    "qm_index_build": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_void_p)]),
+    "qm_index_destroy": (None, [_P, _P]),
+    "qm_index_lpac": (_L, [_P]),
+    "qm_collect_seeds": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P]),
+    "qm_align_se": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
+    "qm_pestat_sync": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P]),
+    "qm_pair_finish": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "qm_pileup_opt_default": (None, [_P]),
+    "qm_pileup_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P]),
+    "qm_counts_to_rows": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
+    "qm_simulate_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P]),
+    "qm_dpx_peak_sync": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+EXPORTS = sorted(SIGNATURES)
 
 
 def lib():
@@ -53,20 +89,10 @@ def lib():
             raise QmError(f"{SO_PATH} is missing: build it with `python -m quasimodo_b200.build` "
                           "(there is no CPU fallback)")
         L = C.CDLL(SO_PATH)
-        L.qm_version.restype = C.c_char_p
-        L.qm_last_error.restype = C.c_char_p
-        L.qm_last_error.argtypes = [C.c_void_p]
-        L.qm_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
-        L.qm_ctx_destroy.argtypes = [C.c_void_p]
-        L.qm_ctx_destroy.restype = None
-        L.qm_device_sm_count.argtypes = [C.c_void_p]
-        L.qm_extend_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-        L.qm_extend_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p]
-        L.qm_dpx_peak_sync.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        L.qm_simulate_pairs_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                             C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.qm_simulate_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                        C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
         _LIB = L
     return _LIB
 
@@ -74,4 +100,10 @@ def lib():
 def default_opt():
     o = Opt()
     lib().qm_opt_default(C.byref(o))
+    return o
+
+
+def default_pileup_opt():
+    o = PileupOpt()
+    lib().qm_pileup_opt_default(C.byref(o))
     return o

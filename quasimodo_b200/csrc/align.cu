@@ -1,0 +1,562 @@
+// align.cu -- single-end alignment stage: seeding, chaining, the per-read extension state machine and
+// redundancy removal.  Replaces the compute of `bwa mem -k 31` worker1 (bwamem.c mem_align1_core:
+// mem_chain -> mem_chain_flt -> mem_chain2aln -> mem_sort_dedup_patch; reference call site
+// rules/bwa.smk:15; semantics SURVEY.md A.2, A.5).
+//
+// Layout of the work on the GPU:
+//   seed_chain_kernel   one thread per read: rolling 2-bit k-mers of both strands probe the L2-resident
+//                       hash index; consecutive hits on one diagonal are merged into maximal exact
+//                       matches; seeds are chained and chains filtered exactly as bwa does; the result
+//                       is a per-read "plan" = the order in which mem_chain2aln visits the seeds.
+//   advance_kernel      one thread per read: a small state machine that walks the plan, applies
+//                       mem_chain2aln's "already covered" test against the read's regions so far and
+//                       emits at most one extension task (left or right) per round; it consumes the
+//                       previous task's result first (right depends on left).
+//   ext_kernel<C>       extend.cu: all tasks of a round, one warp per task, DPX cell updates.
+//   The host loops advance -> extend until no read emits a task (one 24-byte read-back per round).
+// Tasks reference the read batch and the reference in place (ExtTaskI, QM_EXTI_INDIRECT); no sequence
+// bytes are materialised.
+#include "pipeline.cuh"
+
+namespace {
+
+enum { PH_NEXT = 0, PH_WAIT_LEFT = 1, PH_WAIT_RIGHT = 2, PH_RIGHT = 3, PH_DONE = 4 };
+
+struct ReadState {
+    int16_t cursor;
+    uint8_t phase, n_av;
+    int32_t task;
+};
+
+constexpr int kPlanSkipped = 0x8000;
+
+__device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
+{
+    const int l_del = (int)((double)(qlen * o.a - o.o_del) / o.e_del + 1.);
+    const int l_ins = (int)((double)(qlen * o.a - o.o_ins) / o.e_ins + 1.);
+    int l = l_del > l_ins ? l_del : l_ins;
+    l = l > 1 ? l : 1;
+    return l < o.w << 1 ? l : o.w << 1;
+}
+
+// ---- seeding: all maximal exact matches of length >= k on both strands ----
+__device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S)
+{
+    const int k = V.k;
+    const uint32_t occ_cap = (uint32_t)(o.max_occ < QM_OCC_CAP ? o.max_occ : QM_OCC_CAP);
+    const uint64_t mask = k < 32 ? ((1ull << (2 * k)) - 1) : ~0ull;
+    const int top = 2 * (k - 1);
+    uint64_t fw = 0, rc = 0;
+    int valid = 0, n = 0;
+    int hint[2] = {-1, -1};
+    for (int i = 0; i < len; ++i) {
+        const int c = rd[i];
+        if (c > 3) { valid = 0; fw = rc = 0; continue; }
+        fw = ((fw << 2) | (uint64_t)c) & mask;
+        rc = (rc >> 2) | ((uint64_t)(3 - c) << top);
+        if (++valid < k) continue;
+        const int q = i - k + 1;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            uint32_t first, cnt;
+            if (!qm_idx_lookup(V, pass ? rc : fw, first, cnt)) continue;
+            if (cnt > occ_cap) continue;
+            for (uint32_t t = 0; t < cnt; ++t) {
+                const int64_t p = V.pos[first + t];
+                const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
+                const int64_t diag = rpos - q;
+                int m = hint[pass];
+                bool found = false;
+                if (cnt == 1 && m >= 0 && S[m].rbeg - S[m].qbeg == diag && S[m].qbeg + S[m].len - k + 1 == q) found = true;
+                else
+                    for (m = 0; m < n; ++m)
+                        if (S[m].rbeg - S[m].qbeg == diag && S[m].qbeg + S[m].len - k + 1 == q) { found = true; break; }
+                if (found) { ++S[m].len; hint[pass] = m; }
+                else if (n < QM_MAX_SEEDS) {
+                    S[n].rbeg = rpos; S[n].qbeg = q; S[n].len = k;
+                    hint[pass] = n++;
+                }
+            }
+        }
+    }
+    for (int i = 1; i < n; ++i) {       // order: (qbeg, rbeg)
+        const qm_seed x = S[i];
+        int j = i - 1;
+        while (j >= 0 && (S[j].qbeg > x.qbeg || (S[j].qbeg == x.qbeg && S[j].rbeg > x.rbeg))) { S[j + 1] = S[j]; --j; }
+        S[j + 1] = x;
+    }
+    return n;
+}
+
+__device__ __forceinline__ int seed_rid(const IndexView &V, const qm_seed &s)
+{
+    const int64_t f = s.rbeg >= V.l_pac ? 2 * V.l_pac - 1 - s.rbeg : s.rbeg;
+    return qm_pos2rid(V, f);
+}
+
+// chains + filter -> plan (bwamem.c mem_chain, mem_chain_weight, mem_chain_flt, and the visiting order of
+// mem_chain2aln).  Returns the number of plan entries.
+__device__ int build_plan(const IndexView &V, const qm_opt &o, const qm_seed *S, int ns, uint16_t *plan)
+{
+    int64_t cpos[QM_MAX_SEEDS];
+    uint8_t cfirst[QM_MAX_SEEDS], clast[QM_MAX_SEEDS], order[QM_MAX_SEEDS];
+    int8_t crid[QM_MAX_SEEDS], chain_of[QM_MAX_SEEDS];
+    int nc = 0;
+    for (int i = 0; i < ns; ++i) {
+        const qm_seed p = S[i];
+        const int rid = seed_rid(V, p);
+        int lower = -1;
+        for (int kk = 0; kk < nc; ++kk) { if (cpos[order[kk]] <= p.rbeg) lower = kk; else break; }
+        int res = 0;      // 0: new chain, 1: contained, 2: appended
+        if (lower >= 0) {
+            const int c = order[lower];
+            const qm_seed first = S[cfirst[c]], last = S[clast[c]];
+            const int64_t qend = last.qbeg + last.len, rend = last.rbeg + last.len;
+            if (rid == crid[c]) {
+                if (p.qbeg >= first.qbeg && p.qbeg + p.len <= qend && p.rbeg >= first.rbeg && p.rbeg + p.len <= rend) res = 1;
+                else if ((last.rbeg < V.l_pac || first.rbeg < V.l_pac) && p.rbeg >= V.l_pac) res = 0;
+                else {
+                    const int64_t x = p.qbeg - last.qbeg, y = p.rbeg - last.rbeg;
+                    if (y >= 0 && x - y <= o.w && y - x <= o.w && x - last.len < o.max_chain_gap && y - last.len < o.max_chain_gap) res = 2;
+                }
+            }
+            if (res == 1) { chain_of[i] = -1; continue; }
+            if (res == 2) { chain_of[i] = (int8_t)c; clast[c] = (uint8_t)i; continue; }
+        }
+        cpos[nc] = p.rbeg; crid[nc] = (int8_t)rid; cfirst[nc] = clast[nc] = (uint8_t)i; chain_of[i] = (int8_t)nc;
+        const int at = lower + 1;
+        for (int kk = nc; kk > at; --kk) order[kk] = order[kk - 1];
+        order[at] = (uint8_t)nc++;
+    }
+    if (nc == 0) return 0;
+    // weights (per chain, seeds in seed order)
+    int cw[QM_MAX_SEEDS];
+    for (int c = 0; c < nc; ++c) {
+        int64_t end = 0;
+        int w = 0, w2 = 0;
+        for (int i = 0; i < ns; ++i) {
+            if (chain_of[i] != c) continue;
+            const qm_seed s = S[i];
+            if (s.qbeg >= end) w += s.len; else if (s.qbeg + s.len > end) w += (int)(s.qbeg + s.len - end);
+            if (s.qbeg + s.len > end) end = s.qbeg + s.len;
+        }
+        end = 0;
+        for (int i = 0; i < ns; ++i) {
+            if (chain_of[i] != c) continue;
+            const qm_seed s = S[i];
+            if (s.rbeg >= end) w2 += s.len; else if (s.rbeg + s.len > end) w2 += (int)(s.rbeg + s.len - end);
+            if (s.rbeg + s.len > end) end = s.rbeg + s.len;
+        }
+        cw[c] = w2 < w ? w2 : w;
+    }
+    // B-tree order, weight filter, stable sort by weight descending
+    uint8_t srt[QM_MAX_SEEDS];
+    int m = 0;
+    for (int kk = 0; kk < nc; ++kk) if (cw[order[kk]] >= o.min_chain_weight) srt[m++] = order[kk];
+    for (int i = 1; i < m; ++i) {
+        const uint8_t x = srt[i];
+        int j = i - 1;
+        while (j >= 0 && cw[srt[j]] < cw[x]) { srt[j + 1] = srt[j]; --j; }
+        srt[j + 1] = x;
+    }
+    if (m == 0) return 0;
+    uint8_t kept[QM_MAX_SEEDS], kept_idx[QM_MAX_SEEDS];
+    int8_t firstsh[QM_MAX_SEEDS];
+    for (int i = 0; i < m; ++i) { kept[i] = 0; firstsh[i] = -1; }
+    int n_kept = 0;
+    kept[0] = 3; kept_idx[n_kept++] = 0;
+#define CBEG(i_) (S[cfirst[srt[i_]]].qbeg)
+#define CEND(i_) (S[clast[srt[i_]]].qbeg + S[clast[srt[i_]]].len)
+    for (int i = 1; i < m; ++i) {
+        int large_ovlp = 0, kk;
+        for (kk = 0; kk < n_kept; ++kk) {
+            const int j = kept_idx[kk];
+            const int b_max = CBEG(j) > CBEG(i) ? CBEG(j) : CBEG(i);
+            const int e_min = CEND(j) < CEND(i) ? CEND(j) : CEND(i);
+            if (e_min > b_max) {
+                const int li = CEND(i) - CBEG(i), lj = CEND(j) - CBEG(j);
+                const int min_l = li < lj ? li : lj;
+                if (e_min - b_max >= min_l * o.mask_level && min_l < o.max_chain_gap) {
+                    large_ovlp = 1;
+                    if (firstsh[j] < 0) firstsh[j] = (int8_t)i;
+                    if (cw[srt[i]] < cw[srt[j]] * o.drop_ratio && cw[srt[j]] - cw[srt[i]] >= o.min_seed_len << 1) break;
+                }
+            }
+        }
+        if (kk == n_kept) { kept_idx[n_kept++] = (uint8_t)i; kept[i] = large_ovlp ? 2 : 3; }
+    }
+#undef CBEG
+#undef CEND
+    for (int i = 0; i < n_kept; ++i) { const int j = kept_idx[i]; if (firstsh[j] >= 0) kept[firstsh[j]] = 1; }
+    // plan: kept chains in sorted order; inside a chain seeds by descending (len, index in chain)
+    int np = 0, ord = 0;
+    for (int i = 0; i < m; ++i) {
+        if (!kept[i]) continue;
+        const int c = srt[i];
+        const int base = np;
+        for (int s = 0; s < ns; ++s) {
+            if (chain_of[s] != c) continue;
+            // insertion into descending order by (len, within)
+            const int len = S[s].len;
+            int j = np - 1;
+            while (j >= base) {
+                const int sj = plan[j] & 63;
+                if (S[sj].len > len) break;         // equal length: the later seed (larger index) goes first
+                plan[j + 1] = plan[j];
+                --j;
+            }
+            plan[j + 1] = (uint16_t)(s | (ord << 6));
+            ++np;
+        }
+        ++ord;
+    }
+    return np;
+}
+
+__global__ void __launch_bounds__(128)
+seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                  int64_t n, qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds, uint16_t *__restrict__ plan,
+                  uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    qm_seed *S = seeds + r * QM_MAX_SEEDS;
+    const int ns = collect_seeds(V, o, codes + r * stride, lens[r], S);
+    n_seeds[r] = ns;
+    if (seeds_only) return;
+    const int np = build_plan(V, o, S, ns, plan + r * QM_MAX_SEEDS);
+    n_plan[r] = (uint8_t)np;
+    ReadState s;
+    s.cursor = 0; s.phase = PH_NEXT; s.n_av = 0; s.task = -1;
+    st[r] = s;
+}
+
+// ---- mem_sort_dedup_patch without mem_patch_reg (stable sorts) ----
+__device__ int sort_dedup(const qm_opt &o, int n, qm_reg *a)
+{
+    if (n <= 1) return n;
+    for (int i = 1; i < n; ++i) { const qm_reg x = a[i]; int j = i - 1; while (j >= 0 && a[j].re > x.re) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
+    for (int i = 1; i < n; ++i) {
+        qm_reg *p = &a[i];
+        if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + o.max_chain_gap) continue;
+        for (int j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + o.max_chain_gap; --j) {
+            qm_reg *q = &a[j];
+            if (q->qe == q->qb) continue;
+            const int64_t orr = q->re - p->rb;
+            const int64_t oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
+            const int64_t mr = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
+            const int64_t mq = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
+            if (orr > o.mask_level_redun * mr && oq > o.mask_level_redun * mq) {
+                if (p->score < q->score) { p->qe = p->qb; break; }
+                else q->qe = q->qb;
+            }
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+    n = m;
+    for (int i = 1; i < n; ++i) {
+        const qm_reg x = a[i];
+        int j = i - 1;
+        while (j >= 0 && !(a[j].score > x.score || (a[j].score == x.score && (a[j].rb < x.rb || (a[j].rb == x.rb && a[j].qb <= x.qb))))) { a[j + 1] = a[j]; --j; }
+        a[j + 1] = x;
+    }
+    for (int i = 1; i < n; ++i)
+        if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+    m = n ? 1 : 0;
+    for (int i = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+    return m;
+}
+
+struct RoundCounters {        // zeroed before every advance round
+    int class_count[8];       // [0..4] tasks per striping class
+    int class_cursor[8];      // work cursors of the extension kernels
+    int n_tasks;
+    int pad[7];
+};
+
+// ---- mem_chain2aln as a per-read state machine ----
+__global__ void __launch_bounds__(128)
+advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+               int64_t n, const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
+               ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
+               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks, int *__restrict__ lists,
+               int64_t list_stride, RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    ReadState s = st[r];
+    if (s.phase == PH_DONE) return;
+    const qm_seed *S = seeds + r * QM_MAX_SEEDS;
+    uint16_t *PL = plan + r * QM_MAX_SEEDS;
+    qm_reg *av = regs + r * QM_MAX_REGS;
+    const int lq = lens[r], np = n_plan[r];
+    const uint8_t *query = codes + r * stride;
+    const int64_t l_pac = V.l_pac;
+
+    if (s.phase == PH_WAIT_LEFT) {
+        const qm_ext_result x = res[s.task];
+        const qm_seed sd = S[PL[s.cursor] & 63];
+        qm_reg *a = &av[s.n_av];
+        if (cells) atomicAdd(cells, (unsigned long long)x.cells);
+        a->score = x.score; a->w = x.w_used;
+        if (x.gscore <= 0 || x.gscore <= x.score - o.pen_clip5) { a->qb = sd.qbeg - x.qle; a->rb = sd.rbeg - x.tle; a->truesc = x.score; }
+        else { a->qb = 0; a->rb = sd.rbeg - x.gtle; a->truesc = x.gscore; }
+        s.phase = PH_RIGHT;
+    } else if (s.phase == PH_WAIT_RIGHT) {
+        const qm_ext_result x = res[s.task];
+        const qm_seed sd = S[PL[s.cursor] & 63];
+        qm_reg *a = &av[s.n_av];
+        const int sc0 = a->score;        // score before the right extension (= the task's h0)
+        if (cells) atomicAdd(cells, (unsigned long long)x.cells);
+        const int qe = sd.qbeg + sd.len;
+        const int64_t re = sd.rbeg + sd.len;
+        a->score = x.score;
+        if (x.gscore <= 0 || x.gscore <= x.score - o.pen_clip3) { a->qe = qe + x.qle; a->re = re + x.tle; a->truesc += x.score - sc0; }
+        else { a->qe = lq; a->re = re + x.gtle; a->truesc += x.gscore - sc0; }
+        if (x.w_used > a->w) a->w = x.w_used;
+        s.phase = PH_NEXT + 100;       // finalize marker
+    }
+
+    for (;;) {
+        if (s.phase == PH_NEXT + 100) {
+            // finalize the region in av[n_av]: seed coverage over the chain's seeds
+            const int ent = PL[s.cursor];
+            const int chain = (ent >> 6) & 63;
+            qm_reg *a = &av[s.n_av];
+            int cov = 0;
+            for (int i = 0; i < np; ++i) {
+                if (((PL[i] >> 6) & 63) != chain) continue;
+                const qm_seed t = S[PL[i] & 63];
+                if (t.qbeg >= a->qb && t.qbeg + t.len <= a->qe && t.rbeg >= a->rb && t.rbeg + t.len <= a->re) cov += t.len;
+            }
+            a->seedcov = cov;
+            a->seedlen0 = S[ent & 63].len;
+            ++s.n_av; ++s.cursor;
+            s.phase = PH_NEXT;
+        }
+        if (s.phase == PH_NEXT) {
+            // next seed of the plan that is not already explained by an existing region
+            bool have = false;
+            while (s.cursor < np) {
+                const int ent = PL[s.cursor];
+                const int chain = (ent >> 6) & 63;
+                const qm_seed sd = S[ent & 63];
+                int i;
+                for (i = 0; i < s.n_av; ++i) {
+                    const qm_reg *p = &av[i];
+                    if (sd.rbeg < p->rb || sd.rbeg + sd.len > p->re || sd.qbeg < p->qb || sd.qbeg + sd.len > p->qe) continue;
+                    if (sd.len - p->seedlen0 > .1 * lq) continue;
+                    int qd = sd.qbeg - p->qb;
+                    int64_t rd = sd.rbeg - p->rb;
+                    int mg = max_gap_for(o, qd < rd ? qd : (int)rd);
+                    int w = mg < p->w ? mg : p->w;
+                    if (qd - rd < w && rd - qd < w) break;
+                    qd = p->qe - (sd.qbeg + sd.len); rd = p->re - (sd.rbeg + sd.len);
+                    mg = max_gap_for(o, qd < rd ? qd : (int)rd);
+                    w = mg < p->w ? mg : p->w;
+                    if (qd - rd < w && rd - qd < w) break;
+                }
+                bool skip = false;
+                if (i < s.n_av) {
+                    // covered: extend anyway only if an earlier-visited, extended seed of this chain overlaps it on
+                    // a different diagonal
+                    int j;
+                    for (j = s.cursor - 1; j >= 0; --j) {
+                        const int ej = PL[j];
+                        if (((ej >> 6) & 63) != chain) break;       // plan entries of one chain are contiguous
+                        if (ej & kPlanSkipped) continue;
+                        const qm_seed t = S[ej & 63];
+                        if (t.len < sd.len * .95) continue;
+                        if (sd.qbeg <= t.qbeg && sd.qbeg + sd.len - t.qbeg >= sd.len >> 2 && t.qbeg - sd.qbeg != t.rbeg - sd.rbeg) break;
+                        if (t.qbeg <= sd.qbeg && t.qbeg + t.len - sd.qbeg >= sd.len >> 2 && sd.qbeg - t.qbeg != sd.rbeg - t.rbeg) break;
+                    }
+                    if (j < 0 || ((PL[j] >> 6) & 63) != chain) skip = true;
+                }
+                if (!skip && s.n_av >= QM_MAX_REGS) skip = true;       // documented hard cap
+                if (skip) { PL[s.cursor] = (uint16_t)(ent | kPlanSkipped); ++s.cursor; continue; }
+                have = true;
+                break;
+            }
+            if (!have) {
+                n_regs[r] = sort_dedup(o, s.n_av, av);
+                s.phase = PH_DONE;
+                st[r] = s;
+                return;
+            }
+        }
+        // the chain's reference window (mem_chain2aln rmax[], clamped to the contig as bns_fetch_seq does)
+        const int ent = PL[s.cursor];
+        const int chain = (ent >> 6) & 63;
+        const qm_seed sd = S[ent & 63];
+        int64_t rmax0 = l_pac << 1, rmax1 = 0;
+        qm_seed first_seed = sd;
+        int first_idx = 1 << 30;
+        for (int i = 0; i < np; ++i) {
+            if (((PL[i] >> 6) & 63) != chain) continue;
+            const int si = PL[i] & 63;
+            const qm_seed t = S[si];
+            const int64_t b = t.rbeg - (t.qbeg + max_gap_for(o, t.qbeg));
+            const int tail = lq - t.qbeg - t.len;
+            const int64_t e = t.rbeg + t.len + (tail + max_gap_for(o, tail));
+            rmax0 = b < rmax0 ? b : rmax0;
+            rmax1 = e > rmax1 ? e : rmax1;
+            if (si < first_idx) { first_idx = si; first_seed = t; }     // seed 0 of the chain = lowest seed index
+        }
+        rmax0 = rmax0 > 0 ? rmax0 : 0;
+        rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+        if (rmax0 < l_pac && l_pac < rmax1) { if (first_seed.rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+        int rid;
+        {
+            const bool rev = first_seed.rbeg >= l_pac;
+            const int64_t f = rev ? 2 * l_pac - 1 - first_seed.rbeg : first_seed.rbeg;
+            rid = qm_pos2rid(V, f);
+            int64_t far_beg = V.off[rid], far_end = V.off[rid] + V.len[rid];
+            if (rev) { const int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+            rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
+            rmax1 = rmax1 < far_end ? rmax1 : far_end;
+        }
+        ExtTaskI t;
+        bool emit = false;
+        if (s.phase == PH_NEXT) {
+            qm_reg *a = &av[s.n_av];
+            qm_reg z = {};
+            z.w = o.w; z.score = z.truesc = -1; z.rid = rid; z.secondary = -1;
+            *a = z;
+            if (sd.qbeg) {
+                t.q = query + sd.qbeg - 1; t.qstep = -1; t.qlen = sd.qbeg;
+                t.t = nullptr; t.t0 = sd.rbeg - 1; t.tstep = -1; t.tlen = (int)(sd.rbeg - rmax0);
+                t.h0 = sd.len * o.a; t.w = o.w; t.end_bonus = o.pen_clip5;
+                t.flags = QM_EXT_BAND_RETRY | QM_EXTI_INDIRECT;
+                emit = true;
+                s.phase = PH_WAIT_LEFT;
+            } else {
+                a->score = a->truesc = sd.len * o.a; a->qb = 0; a->rb = sd.rbeg;
+                s.phase = PH_RIGHT;
+            }
+        }
+        if (s.phase == PH_RIGHT) {
+            qm_reg *a = &av[s.n_av];
+            if (sd.qbeg + sd.len != lq) {
+                const int qe = sd.qbeg + sd.len;
+                const int64_t re = sd.rbeg + sd.len;
+                t.q = query + qe; t.qstep = 1; t.qlen = lq - qe;
+                t.t = nullptr; t.t0 = re; t.tstep = 1; t.tlen = (int)(rmax1 - re);
+                t.h0 = a->score; t.w = o.w; t.end_bonus = o.pen_clip3;
+                t.flags = QM_EXT_BAND_RETRY | QM_EXT_PREV_H0 | QM_EXTI_INDIRECT;
+                emit = true;
+                s.phase = PH_WAIT_RIGHT;
+            } else {
+                a->qe = lq; a->re = sd.rbeg + sd.len;
+                s.phase = PH_NEXT + 100;
+                continue;
+            }
+        }
+        if (emit) {
+            t.pad[0] = (int)r; t.pad[1] = 0;
+            const int slot = atomicAdd(&ctr->n_tasks, 1);
+            tasks[slot] = t;
+            const int c = qm_ext_class(t.qlen);
+            const int ls = atomicAdd(&ctr->class_count[c], 1);
+            lists[(int64_t)c * list_stride + ls] = slot;
+            s.task = slot;
+            st[r] = s;
+            return;
+        }
+    }
+}
+
+constexpr int64_t kSeBatch = 1 << 19;       // reads per internal round-trip (bounds scratch memory)
+
+struct SeScratch {
+    qm_seed *seeds; int32_t *n_seeds; uint16_t *plan; uint8_t *n_plan; ReadState *st;
+    ExtTaskI *tasks; qm_ext_result *res; int *lists; RoundCounters *ctr; RoundCounters *h_ctr;
+};
+
+int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_seeds = take((size_t)nb * QM_MAX_SEEDS * sizeof(qm_seed));
+    const size_t o_ns = take((size_t)nb * 4);
+    const size_t o_plan = take((size_t)nb * QM_MAX_SEEDS * 2);
+    const size_t o_np = take((size_t)nb);
+    const size_t o_st = take((size_t)nb * sizeof(ReadState));
+    const size_t o_tasks = take((size_t)nb * sizeof(ExtTaskI));
+    const size_t o_res = take((size_t)nb * sizeof(qm_ext_result));
+    const size_t o_lists = take((size_t)nb * kExtClasses * 4);
+    const size_t o_ctr = take(sizeof(RoundCounters));
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 3, off, &p);
+    if (rc) return rc;
+    char *b = (char *)p;
+    sc->seeds = (qm_seed *)(b + o_seeds); sc->n_seeds = (int32_t *)(b + o_ns); sc->plan = (uint16_t *)(b + o_plan);
+    sc->n_plan = (uint8_t *)(b + o_np); sc->st = (ReadState *)(b + o_st); sc->tasks = (ExtTaskI *)(b + o_tasks);
+    sc->res = (qm_ext_result *)(b + o_res); sc->lists = (int *)(b + o_lists); sc->ctr = (RoundCounters *)(b + o_ctr);
+    return QM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qm_collect_seeds(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
+                     const int32_t *d_lens, int64_t n_reads, qm_seed *d_seeds, int32_t *d_n_seeds, void *stream)
+{
+    if (!ctx || !idx || !opt || n_reads < 0 || (n_reads > 0 && (!d_codes || !d_lens || !d_seeds || !d_n_seeds)))
+        return QM_EINVAL;
+    if (opt->min_seed_len != idx->v.k) return qm_fail(ctx, QM_EINVAL, "index built with k=%d but min_seed_len=%d", idx->v.k, opt->min_seed_len);
+    if (n_reads == 0) return QM_OK;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int tpb = 128;
+    seed_chain_kernel<<<(unsigned)((n_reads + tpb - 1) / tpb), tpb, 0, (cudaStream_t)stream>>>(
+        idx->v, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true);
+    QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}
+
+int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
+                const int32_t *d_lens, int64_t n_reads, qm_reg *d_regs, int32_t *d_n_regs, int64_t *d_cells, void *stream)
+{
+    if (!ctx || !idx || !opt || n_reads < 0 || (n_reads > 0 && (!d_codes || !d_lens || !d_regs || !d_n_regs)))
+        return QM_EINVAL;
+    if (opt->min_seed_len != idx->v.k) return qm_fail(ctx, QM_EINVAL, "index built with k=%d but min_seed_len=%d", idx->v.k, opt->min_seed_len);
+    if (opt->e_ins <= 0 || opt->e_del <= 0) return qm_fail(ctx, QM_EINVAL, "gap extension penalties must be > 0");
+    if (n_reads == 0) return QM_OK;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nbmax = n_reads < kSeBatch ? n_reads : kSeBatch;
+    SeScratch sc;
+    int rc = se_scratch(ctx, nbmax, &sc);
+    if (rc) return rc;
+    RoundCounters *h_ctr = nullptr;
+    QM_CUDA(ctx, cudaMallocHost(&h_ctr, sizeof(RoundCounters)));
+    const ExtParams P = qm_ext_params(opt);
+    const int tpb = 128;
+    for (int64_t b0 = 0; b0 < n_reads; b0 += kSeBatch) {
+        const int64_t nb = n_reads - b0 < kSeBatch ? n_reads - b0 : kSeBatch;
+        const unsigned grid = (unsigned)((nb + tpb - 1) / tpb);
+        const uint8_t *codes = d_codes + b0 * stride;
+        const int32_t *lens = d_lens + b0;
+        seed_chain_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan,
+                                                sc.n_plan, sc.st, false);
+        for (int round = 0; round < 4 * QM_MAX_REGS + 8; ++round) {
+            cudaMemsetAsync(sc.ctr, 0, sizeof(RoundCounters), st);
+            advance_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.plan, sc.n_plan, sc.st,
+                                                 d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.res, sc.tasks, sc.lists, nb,
+                                                 sc.ctr, (unsigned long long *)d_cells);
+            cudaMemcpyAsync(h_ctr, sc.ctr, sizeof(RoundCounters), cudaMemcpyDeviceToHost, st);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFreeHost(h_ctr); return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
+            if (h_ctr->n_tasks == 0) break;
+            rc = qm_ext_launch_classes(ctx, P, idx->v, sc.tasks, sc.lists, nb, sc.ctr->class_count, sc.ctr->class_cursor,
+                                       h_ctr->class_count, sc.res, st);
+            if (rc) { cudaFreeHost(h_ctr); return rc; }
+        }
+    }
+    cudaFreeHost(h_ctr);
+    QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}
+
+}  // extern "C"

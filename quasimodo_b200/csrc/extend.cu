@@ -10,25 +10,26 @@
 // (band, (m,mj), z-drop, to-end score, zero-span trimming) are warp-uniform, computed from three
 // REDUX reductions.  Cell arithmetic uses the Blackwell DPX instructions
 // (__viaddmax_s32_relu / __vimax3_s32 / __viaddmax_s32); no tensor cores: this is not a contraction.
-#include "common.cuh"
+#include "pipeline.cuh"
 
 namespace {
 
-struct ExtParams {
-    int a, b, o_del, e_del, o_ins, e_ins, zdrop;
-};
+constexpr int kNumClasses = kExtClasses;
 
-// classes of column striping: C = 1,2,4,8,16 columns per lane <=> qlen+1 <= 32*C
-constexpr int kNumClasses = 5;
-__host__ __device__ inline int class_of_qlen(int qlen)
-{
-    int need = qlen + 1;
-    if (need <= 32) return 0;
-    if (need <= 64) return 1;
-    if (need <= 128) return 2;
-    if (need <= 256) return 3;
-    return 4;
-}
+// where a task's bases come from: explicit byte strings (public C-ABI tasks) or the read batch /
+// reference index in place (pipeline tasks; nothing is materialised in HBM)
+struct SeqFetch {
+    const uint8_t *q, *t;
+    int64_t t0;
+    int qstep, tstep;
+    bool indirect;
+    const IndexView *V;
+    __device__ __forceinline__ int qbase(int j) const { return q[(int64_t)j * qstep]; }
+    __device__ __forceinline__ int tbase(int i) const
+    {
+        return indirect ? qm_ref_base(*V, t0 + (int64_t)i * tstep) : t[i];
+    }
+};
 
 struct ExtState {
     int score, qle, tle, gtle, gscore, max_off, cells;
@@ -36,8 +37,7 @@ struct ExtState {
 
 // One ksw_extend2 call executed by one warp.  All lanes return the same ExtState.
 template <int C>
-__device__ __forceinline__ ExtState ext_run(const ExtParams &P, const uint8_t *__restrict__ query, int qlen,
-                                            const uint8_t *__restrict__ target, int tlen, int h0, int w,
+__device__ __forceinline__ ExtState ext_run(const ExtParams &P, const SeqFetch &S, int qlen, int tlen, int h0, int w,
                                             int end_bonus, int lane)
 {
     const unsigned FULL = 0xffffffffu;
@@ -58,7 +58,7 @@ __device__ __forceinline__ ExtState ext_run(const ExtParams &P, const uint8_t *_
         }
         h[k] = v;
         e[k] = 0;
-        const int c = (j < qlen) ? query[j] : 4;
+        const int c = (j < qlen) ? S.qbase(j) : 4;
         qc[k] = c;
         mis[k] = (c > 3) ? -1 : -P.b;
     }
@@ -77,10 +77,10 @@ __device__ __forceinline__ ExtState ext_run(const ExtParams &P, const uint8_t *_
     int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
     int beg = 0, end = qlen, cells = 0;
 
-    int tb_next = tlen > 0 ? target[0] : 0;
+    int tb_next = tlen > 0 ? S.tbase(0) : 0;
     for (int i = 0; i < tlen; ++i) {
         const int tb = tb_next;
-        if (i + 1 < tlen) tb_next = target[i + 1];
+        if (i + 1 < tlen) tb_next = S.tbase(i + 1);
 
         if (beg < i - w) {
             // columns that fall out of the band are never read again by the reference; zero them so
@@ -186,9 +186,10 @@ __device__ __forceinline__ ExtState ext_run(const ExtParams &P, const uint8_t *_
     return r;
 }
 
-// ---- binning of tasks by striping class (device side, no host sync) ----
-__global__ void ext_classify_kernel(const qm_ext_task *__restrict__ tasks, int64_t n, int *__restrict__ lists,
-                                    int *__restrict__ counts, qm_ext_result *__restrict__ out, int *__restrict__ err)
+// ---- public tasks -> internal tasks, binned by striping class (device side, no host sync) ----
+__global__ void ext_classify_kernel(const qm_ext_task *__restrict__ tasks, const uint8_t *__restrict__ seq, int64_t n,
+                                    ExtTaskI *__restrict__ itasks, int *__restrict__ lists, int *__restrict__ counts,
+                                    qm_ext_result *__restrict__ out, int *__restrict__ err)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -200,16 +201,21 @@ __global__ void ext_classify_kernel(const qm_ext_task *__restrict__ tasks, int64
         atomicExch(err, 1);
         return;
     }
-    const int c = class_of_qlen(t.qlen);
+    ExtTaskI it;
+    it.q = seq + t.q_off; it.t = seq + t.t_off; it.t0 = 0; it.qstep = 1; it.tstep = 1;
+    it.qlen = t.qlen; it.tlen = t.tlen; it.h0 = t.h0; it.w = t.w; it.end_bonus = t.end_bonus;
+    it.flags = t.flags & (QM_EXT_BAND_RETRY | QM_EXT_PREV_H0);
+    it.pad[0] = it.pad[1] = 0;
+    itasks[i] = it;
+    const int c = qm_ext_class(t.qlen);
     const int slot = atomicAdd(&counts[c], 1);
     lists[(int64_t)c * n + slot] = (int)i;
 }
 
 template <int C>
 __global__ void __launch_bounds__(128)
-ext_kernel(ExtParams P, const uint8_t *__restrict__ seq, const qm_ext_task *__restrict__ tasks,
-           const int *__restrict__ list, const int *__restrict__ count, int *__restrict__ cursor,
-           qm_ext_result *__restrict__ out)
+ext_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const int *__restrict__ list,
+           const int *__restrict__ count, int *__restrict__ cursor, qm_ext_result *__restrict__ out)
 {
     const int lane = qm_lane();
     const int n = *count;
@@ -219,14 +225,16 @@ ext_kernel(ExtParams P, const uint8_t *__restrict__ seq, const qm_ext_task *__re
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= n) break;
         const int tid = list[idx];
-        const qm_ext_task t = tasks[tid];
-        const uint8_t *q = seq + t.q_off, *tg = seq + t.t_off;
+        const ExtTaskI t = tasks[tid];
+        SeqFetch S;
+        S.q = t.q; S.t = t.t; S.t0 = t.t0; S.qstep = t.qstep; S.tstep = t.tstep;
+        S.indirect = (t.flags & QM_EXTI_INDIRECT) != 0; S.V = &V;
         ExtState r;
         int w_used = t.w, cells = 0, prev = (t.flags & QM_EXT_PREV_H0) ? t.h0 : -1;
         const int tries = (t.flags & QM_EXT_BAND_RETRY) ? 2 : 1;
         for (int a = 0; a < tries; ++a) {
             w_used = t.w << a;
-            r = ext_run<C>(P, q, t.qlen, tg, t.tlen, t.h0, w_used, t.end_bonus, lane);
+            r = ext_run<C>(P, S, t.qlen, t.tlen, t.h0, w_used, t.end_bonus, lane);
             cells += r.cells;
             if (r.score == prev || r.max_off < (w_used >> 1) + (w_used >> 2)) break;
             prev = r.score;
@@ -240,9 +248,37 @@ ext_kernel(ExtParams P, const uint8_t *__restrict__ seq, const qm_ext_task *__re
     }
 }
 
+template <int C>
+void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
+                  int64_t list_stride, const int *d_counts, int *d_cursors, const int *h_counts, qm_ext_result *d_out,
+                  cudaStream_t st)
+{
+    int64_t warps = (int64_t)ctx->sm_count * 64;          // persistent: up to 16 blocks of 4 warps per SM
+    if (h_counts) {
+        if (h_counts[cls] == 0) return;
+        if (h_counts[cls] < warps) warps = h_counts[cls];
+    }
+    unsigned blocks = (unsigned)((warps + 3) / 4);
+    if (blocks > (unsigned)ctx->sm_count) blocks = ((blocks + ctx->sm_count - 1) / ctx->sm_count) * ctx->sm_count;
+    ext_kernel<C><<<blocks, 128, 0, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
+}
+
 }  // namespace
 
-// Launch the whole batch on `stream`.  Scratch: lists (5*n ints) + counters.
+int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                          const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
+                          const int *h_counts, qm_ext_result *d_out, cudaStream_t st)
+{
+    launch_class<1>(ctx, 0, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    launch_class<2>(ctx, 1, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    launch_class<4>(ctx, 2, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    launch_class<8>(ctx, 3, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    launch_class<16>(ctx, 4, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}
+
+// Launch a batch of public tasks on `stream`.  Scratch 0: internal tasks + lists + counters.
 int qm_extend_launch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const qm_ext_task *d_tasks,
                      int64_t n, qm_ext_result *d_out, cudaStream_t st)
 {
@@ -250,28 +286,18 @@ int qm_extend_launch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const
     if (n < 0 || n > 0x7fffffff / kNumClasses) return qm_fail(ctx, QM_ELIMIT, "qm_extend_batch: n_tasks=%lld out of range", (long long)n);
     if (opt->e_ins <= 0 || opt->e_del <= 0) return qm_fail(ctx, QM_EINVAL, "gap extension penalties must be > 0");
     void *p = nullptr;
+    const size_t task_bytes = (size_t)n * sizeof(ExtTaskI);
     const size_t list_bytes = (size_t)kNumClasses * n * sizeof(int);
-    int rc = qm_scratch_reserve(ctx, 0, list_bytes + 64 * sizeof(int), &p);
+    int rc = qm_scratch_reserve(ctx, 0, task_bytes + list_bytes + 64 * sizeof(int), &p);
     if (rc) return rc;
-    int *lists = (int *)p;
-    int *ctrs = (int *)((char *)p + list_bytes);     // [0..4] counts, [8..12] cursors, [16] err
+    ExtTaskI *itasks = (ExtTaskI *)p;
+    int *lists = (int *)((char *)p + task_bytes);
+    int *ctrs = (int *)((char *)p + task_bytes + list_bytes);     // [0..4] counts, [8..12] cursors, [16] err
     QM_CUDA(ctx, cudaMemsetAsync(ctrs, 0, 64 * sizeof(int), st));
-    ExtParams P = {opt->a, opt->b, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->zdrop};
     const int tpb = 256;
-    ext_classify_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_tasks, n, lists, ctrs, d_out, ctrs + 16);
-    // persistent grids: enough warps to fill every SM; work is fetched with an atomic cursor
-    const int64_t warps_wanted = (n + 0) < (int64_t)ctx->sm_count * 64 ? n : (int64_t)ctx->sm_count * 64;
-    unsigned blocks = (unsigned)((warps_wanted + 3) / 4);
-    if (blocks < 1) blocks = 1;
-    // round up to a multiple of the SM count once the batch is large enough
-    if (blocks > (unsigned)ctx->sm_count) blocks = ((blocks + ctx->sm_count - 1) / ctx->sm_count) * ctx->sm_count;
-    ext_kernel<1><<<blocks, 128, 0, st>>>(P, d_seq, d_tasks, lists + 0 * n, ctrs + 0, ctrs + 8, d_out);
-    ext_kernel<2><<<blocks, 128, 0, st>>>(P, d_seq, d_tasks, lists + 1 * n, ctrs + 1, ctrs + 9, d_out);
-    ext_kernel<4><<<blocks, 128, 0, st>>>(P, d_seq, d_tasks, lists + 2 * n, ctrs + 2, ctrs + 10, d_out);
-    ext_kernel<8><<<blocks, 128, 0, st>>>(P, d_seq, d_tasks, lists + 3 * n, ctrs + 3, ctrs + 11, d_out);
-    ext_kernel<16><<<blocks, 128, 0, st>>>(P, d_seq, d_tasks, lists + 4 * n, ctrs + 4, ctrs + 12, d_out);
-    QM_CUDA(ctx, cudaGetLastError());
-    return QM_OK;
+    ext_classify_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_tasks, d_seq, n, itasks, lists, ctrs, d_out, ctrs + 16);
+    IndexView V = {};
+    return qm_ext_launch_classes(ctx, qm_ext_params(opt), V, itasks, lists, n, ctrs, ctrs + 8, nullptr, d_out, st);
 }
 
 extern "C" {

@@ -1,0 +1,93 @@
+// index.cu -- k-mer hash index of the reference (replaces `bwa index`, rules/index.smk:13).
+// One-off host build (the genomes are 0.24-4.9 Mb; SURVEY.md 8a1 "negligible"), device-resident tables:
+// 16-byte open-addressing entries {k-mer, first, count} + ascending occurrence lists.  For the HCMV
+// genomes the table is ~8 MB and stays in the 126 MB L2.
+#include <algorithm>
+#include <vector>
+#include "pipeline.cuh"
+
+extern "C" {
+
+int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int64_t *h_lens, int k, qm_index **out)
+{
+    if (!ctx || !out) return QM_EINVAL;
+    *out = nullptr;
+    if (!h_codes || !h_lens || n_contigs <= 0 || n_contigs > QM_MAX_CONTIGS || k < 8 || k > 32)
+        return qm_fail(ctx, QM_EINVAL, "qm_index_build: need 1..%d contigs and 8 <= k <= 32", QM_MAX_CONTIGS);
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    qm_index *ix = new qm_index();
+    IndexView &v = ix->v;
+    v.k = k; v.n_contigs = n_contigs;
+    int64_t total = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        if (h_lens[c] <= 0) { delete ix; return qm_fail(ctx, QM_EINVAL, "contig %d has no bases", c); }
+        v.off[c] = total; v.len[c] = h_lens[c]; total += h_lens[c];
+    }
+    if (total >= (1ll << 31)) { delete ix; return qm_fail(ctx, QM_ELIMIT, "reference too long for 32-bit positions"); }
+    v.l_pac = total;
+    for (int64_t i = 0; i < total; ++i)
+        if (h_codes[i] > 3) { delete ix; return qm_fail(ctx, QM_EINVAL, "reference base %lld is not A/C/G/T", (long long)i); }
+
+    // all k-mers that do not straddle a contig boundary
+    std::vector<std::pair<uint64_t, uint32_t>> km;
+    km.reserve((size_t)total);
+    const uint64_t mask = k < 32 ? ((1ull << (2 * k)) - 1) : ~0ull;
+    for (int c = 0; c < n_contigs; ++c) {
+        uint64_t key = 0;
+        for (int64_t p = 0; p < h_lens[c]; ++p) {
+            key = ((key << 2) | h_codes[v.off[c] + p]) & mask;
+            if (p >= k - 1) km.emplace_back(key, (uint32_t)(v.off[c] + p - (k - 1)));
+        }
+    }
+    std::sort(km.begin(), km.end());
+    ix->n_kmers = (int64_t)km.size();
+    std::vector<uint32_t> pos(km.size() + 1);
+    int64_t n_unique = 0;
+    for (size_t i = 0; i < km.size(); ++i) {
+        pos[i] = km[i].second;
+        if (i == 0 || km[i].first != km[i - 1].first) ++n_unique;
+    }
+    ix->n_unique = n_unique;
+    int bits = 4;
+    while ((1ll << bits) < 2 * n_unique) ++bits;
+    const int64_t tsize = 1ll << bits;
+    ix->table_size = tsize;
+    std::vector<uint4> table((size_t)tsize, make_uint4(0xffffffffu, 0xffffffffu, 0, 0));
+    v.mask = (uint64_t)tsize - 1; v.shift = 64 - bits;
+    for (size_t i = 0; i < km.size();) {
+        size_t j = i;
+        while (j < km.size() && km[j].first == km[i].first) ++j;
+        const uint64_t key = km[i].first;
+        uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> v.shift;
+        while (table[h].x != 0xffffffffu || table[h].y != 0xffffffffu) h = (h + 1) & v.mask;
+        table[h] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)i, (uint32_t)(j - i));
+        i = j;
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
+        (e = cudaMalloc(&ix->d_table, (size_t)tsize * sizeof(uint4))) != cudaSuccess ||
+        (e = cudaMalloc(&ix->d_pos, pos.size() * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_refb, h_codes, (size_t)total, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_table, table.data(), (size_t)tsize * sizeof(uint4), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_pos, pos.data(), pos.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        qm_index_destroy(ctx, ix);
+        return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
+    }
+    v.refb = (const uint8_t *)ix->d_refb; v.table = (const uint4 *)ix->d_table; v.pos = (const uint32_t *)ix->d_pos;
+    *out = ix;
+    return QM_OK;
+}
+
+void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
+{
+    if (!ix) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (ix->d_refb) cudaFree(ix->d_refb);
+    if (ix->d_table) cudaFree(ix->d_table);
+    if (ix->d_pos) cudaFree(ix->d_pos);
+    delete ix;
+}
+
+int64_t qm_index_lpac(const qm_index *ix) { return ix ? ix->v.l_pac : 0; }
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// pipeline.cuh -- device-side views and internal task formats shared by the alignment kernels.
+#pragma once
+#include "common.cuh"
+
+// ---- reference index as kernels see it (passed by value) ----
+struct IndexView {
+    const uint8_t *refb;      // forward strand, one base code (0..3) per byte, contigs concatenated
+    const uint4 *table;       // open addressing: {key lo, key hi, first, count}; empty = key all-ones
+    const uint32_t *pos;      // occurrence lists (ascending forward positions)
+    uint64_t mask;            // table size - 1
+    int shift;                // 64 - log2(table size)
+    int k, n_contigs;
+    int64_t l_pac;
+    int64_t off[QM_MAX_CONTIGS], len[QM_MAX_CONTIGS];
+};
+
+struct qm_index {
+    IndexView v;
+    void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr;
+    int64_t n_kmers = 0, n_unique = 0, table_size = 0;
+};
+
+static __device__ __forceinline__ int qm_ref_base(const IndexView &V, int64_t x)
+{   // bwa's doubled coordinates: [l_pac, 2 l_pac) is the reverse complement strand
+    return x < V.l_pac ? V.refb[x] : 3 - V.refb[2 * V.l_pac - 1 - x];
+}
+static __device__ __forceinline__ int qm_pos2rid(const IndexView &V, int64_t fpos)
+{
+    int r = -1;
+    for (int c = 0; c < V.n_contigs; ++c)
+        if (fpos >= V.off[c] && fpos < V.off[c] + V.len[c]) r = c;
+    return r;
+}
+static __device__ __forceinline__ bool qm_idx_lookup(const IndexView &V, uint64_t key, uint32_t &first, uint32_t &cnt)
+{
+    uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> V.shift;
+    for (;;) {
+        const uint4 e = __ldg(&V.table[h]);
+        const uint64_t kk = (uint64_t)e.x | ((uint64_t)e.y << 32);
+        if (kk == key) { first = e.z; cnt = e.w; return true; }
+        if (kk == ~0ull) return false;
+        h = (h + 1) & V.mask;
+    }
+}
+
+// ---- internal extension task (superset of qm_ext_task) ----
+#define QM_EXTI_INDIRECT 0x100u   // target = reference bases at doubled coordinate t0 + i*tstep
+struct ExtTaskI {
+    const uint8_t *q;             // query base j = q[j*qstep]
+    const uint8_t *t;             // direct target bytes (when !INDIRECT)
+    int64_t t0;
+    int32_t qstep, tstep;
+    int32_t qlen, tlen, h0, w, end_bonus;
+    uint32_t flags;
+    int32_t pad[2];
+};                                // 64 B
+
+struct ExtParams {
+    int a, b, o_del, e_del, o_ins, e_ins, zdrop;
+};
+static inline ExtParams qm_ext_params(const qm_opt *o)
+{
+    ExtParams P = {o->a, o->b, o->o_del, o->e_del, o->o_ins, o->e_ins, o->zdrop};
+    return P;
+}
+
+constexpr int kExtClasses = 5;    // C = 1,2,4,8,16 columns per lane <=> qlen+1 <= 32*C
+static __host__ __device__ __forceinline__ int qm_ext_class(int qlen)
+{
+    const int need = qlen + 1;
+    return need <= 32 ? 0 : need <= 64 ? 1 : need <= 128 ? 2 : need <= 256 ? 3 : 4;
+}
+
+// Launch the per-class extension kernels.  lists: [kExtClasses][list_stride] task indices; h_counts may be
+// NULL (unknown on the host: persistent grids sized for the SM count) or the 5 class counts.
+int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                          const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
+                          const int *h_counts, qm_ext_result *d_out, cudaStream_t st);

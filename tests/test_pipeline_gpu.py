@@ -1,0 +1,123 @@
+"""GPU parity (bit-exact) of the whole read-level path, stage by stage, through the C-ABI against the CPU
+oracle on the same simulated read pairs: seeds -> regions (+ executed extension cells) -> insert-size
+model -> alignment records (pos, flag, MAPQ, CIGAR, NM, mate fields) -> pileup count tensor.
+Integer / index work => every field must be identical; the insert-size moments are doubles computed by
+the same host code path (libm) and are compared exactly as well."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from quasimodo_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _workload(name, n):
+    from quasimodo_b200 import workloads
+    if name == "cfg1":
+        return workloads.config1(n)
+    if name == "cfg2":
+        return workloads.config2(6, n)
+    if name == "cfg3":
+        return workloads.config3(n)
+    if name == "cfg4":
+        return workloads.config4(n)
+    if name == "cfg5":
+        return workloads.config5(n)
+    raise KeyError(name)
+
+
+def run_both(ctx, W, n_pairs, pair0=0):
+    import torch
+    from quasimodo_b200 import _lib
+    from oracle import qmo_py
+    codes, quals, _, _ = W.simulate_host(pair0, n_pairs)
+    lens = np.full(2 * n_pairs, W.params.read_len, np.int32)
+    opt_o = qmo_py.default_opt()
+    opt_o.w = W.w
+    opt_g = _lib.default_opt()
+    opt_g.w = W.w
+    # ---- oracle ----
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    o = qmo_py.align_se(ref, codes, lens, opt=opt_o)
+    o_regs_se = o["regs"].copy()
+    o_pes = qmo_py.pestat(ref, o["regs"], o["n_regs"], opt=opt_o)
+    o_alns = qmo_py.pair_and_finish(ref, codes, lens, o["regs"], o["n_regs"], o_pes, pair_id0=pair0, opt=opt_o)
+    o_counts = qmo_py.pileup(ref, o_alns, codes, quals, lens)
+    # ---- device ----
+    dev = torch.device("cuda:0")
+    idx = ctx.index(W.ref, 31)
+    d_codes = torch.from_numpy(codes).to(dev)
+    d_quals = torch.from_numpy(quals).to(dev)
+    d_lens = torch.from_numpy(lens).to(dev)
+    d_seeds, d_ns = ctx.collect_seeds(idx, d_codes, d_lens, opt=opt_g)
+    d_cells = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_regs, d_nr = ctx.align_se(idx, d_codes, d_lens, d_cells=d_cells, opt=opt_g)
+    torch.cuda.synchronize()
+    g_regs_se = d_regs.cpu().numpy().view(_lib.REG_DTYPE).reshape(-1, _lib.MAX_REGS)
+    g_pes = ctx.pestat(idx, d_regs, d_nr, n_pairs, opt=opt_g)
+    d_alns = ctx.pair_finish(idx, d_codes, d_lens, d_regs, d_nr, g_pes, pair_id0=pair0, opt=opt_g)
+    d_counts = torch.zeros(_lib.NCH * idx.l_pac, dtype=torch.int32, device=dev)
+    ctx.pileup_accumulate(idx, d_alns, d_codes, d_quals, d_lens, d_counts)
+    rows = ctx.counts_to_rows(idx, d_counts)
+    torch.cuda.synchronize()
+    g = dict(seeds=d_seeds.cpu().numpy().view(_lib.SEED_DTYPE).reshape(-1, _lib.MAX_SEEDS), n_seeds=d_ns.cpu().numpy(),
+             regs_se=g_regs_se, n_regs=d_nr.cpu().numpy(), cells=int(d_cells.item()), pes=g_pes,
+             alns=d_alns.cpu().numpy().view(_lib.ALN_DTYPE), counts=rows.cpu().numpy(),
+             planes=d_counts.cpu().numpy().reshape(_lib.NCH, idx.l_pac))
+    oo = dict(seeds=o["seeds"], n_seeds=o["n_seeds"], regs_se=o_regs_se, n_regs=o["n_regs"], cells=o["cells"], pes=o_pes,
+              alns=o_alns, counts=o_counts)
+    idx.close()
+    return g, oo
+
+
+def compare(g, o):
+    assert np.array_equal(g["n_seeds"], o["n_seeds"])
+    for r in range(len(o["n_seeds"])):
+        n = o["n_seeds"][r]
+        assert np.array_equal(g["seeds"][r, :n], o["seeds"][r, :n]), f"seeds of read {r}"
+    assert np.array_equal(g["n_regs"], o["n_regs"])
+    bad = [r for r in range(len(o["n_regs"])) if not np.array_equal(g["regs_se"][r, :o["n_regs"][r]], o["regs_se"][r, :o["n_regs"][r]])]
+    assert not bad, f"{len(bad)} reads with different regions, first {bad[:5]}"
+    assert g["cells"] == o["cells"]
+    assert g["pes"].tobytes() == o["pes"].tobytes(), (g["pes"], o["pes"])
+    # alignment records: compare field by field; cigar only up to n_cigar
+    for f in ("rid", "pos", "flag", "mapq", "n_cigar", "score", "sub", "nm", "mate_rid", "mate_pos", "tlen", "qb", "qe"):
+        d = np.nonzero(g["alns"][f] != o["alns"][f])[0]
+        assert d.size == 0, f"field {f}: {d.size} records differ, first {d[:5]}: {g['alns'][f][d[:5]]} vs {o['alns'][f][d[:5]]}"
+    nc = np.where(o["alns"]["n_cigar"] == 255, 0, o["alns"]["n_cigar"])
+    mask = np.arange(g["alns"]["cigar"].shape[1])[None, :] < nc[:, None]
+    assert np.array_equal(np.where(mask, g["alns"]["cigar"], 0), np.where(mask, o["alns"]["cigar"], 0))
+    assert np.array_equal(g["counts"], o["counts"])
+    assert np.array_equal(g["planes"].T, o["counts"])
+
+
+@pytest.mark.parametrize("name,n", [("cfg1", 3000), ("cfg2", 3000), ("cfg4", 3000), ("cfg5", 2000), ("cfg3", 3000)])
+def test_pipeline_parity(ctx, name, n):
+    W = _workload(name, n)
+    g, o = run_both(ctx, W, n)
+    compare(g, o)
+    mapped = (o["alns"]["flag"] & 4) == 0
+    assert mapped.mean() > 0.8
+    assert o["counts"][:, 14].sum() > 0
+
+
+def test_pipeline_pair_offset(ctx):
+    """a shard starting at pair 5000 gives the records the full run gives for those pairs (index-addressable input)"""
+    W = _workload("cfg1", 8000)
+    g, o = run_both(ctx, W, 1500, pair0=5000)
+    compare(g, o)
+
+
+def test_pileup_start_channel_counts_admitted_reads(ctx):
+    """channel 15 sums to the number of admitted reads (mapped, primary, proper pair)"""
+    W = _workload("cfg1", 2000)
+    g, o = run_both(ctx, W, 2000)
+    a = o["alns"]
+    admitted = ((a["flag"] & 4) == 0) & ((a["flag"] & 2) != 0) & (a["n_cigar"] != 0) & (a["n_cigar"] != 255)
+    assert int(g["counts"][:, 15].sum()) == int(admitted.sum())
