@@ -178,6 +178,68 @@ int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *
 /* planes [QM_NCH][l_pac] -> rows [l_pac][QM_NCH] (row order of the count TSV) */
 int qm_counts_to_rows(qm_ctx *ctx, const qm_index *idx, const int32_t *d_planes, int32_t *d_rows, void *stream);
 
+/* ---- one sample end to end: the rule-level entry (replaces the compute of rule `bwa`, rules/bwa.smk:15-18,
+ * and the counting of rules `mpileup` / `bcftools`, rules/vcfcall.smk:39,115, for one {sample}.{ref_name}) ----
+ * A qm_sample owns the sample's count tensor (device, planes [QM_NCH][l_pac]).  Read pairs are handed in
+ * batch by batch, from device memory (qm_sample_add_pairs, asynchronous on `stream` except for the small
+ * per-round read-backs) or from host memory (qm_sample_add_pairs_host: chunked, the next chunk's copy overlaps
+ * the current chunk's kernels when the host buffers are page-locked; synchronous).
+ * bwa estimates its insert-size model per input chunk (mem_pestat); here it is fixed ONCE per sample, from
+ * the first min(n, QM_PESTAT_PAIRS) pairs handed in, or from that prefix of the sample given explicitly
+ * (qm_sample_estimate_pestat: a shard that does not start at pair 0 passes the sample's first pairs; every
+ * GPU derives the same model, no collective), or set directly, so that the records do not depend on batching
+ * or sharding. */
+#define QM_PESTAT_PAIRS 65536
+typedef struct qm_sample qm_sample;
+int  qm_sample_begin(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm_pileup_opt *popt, qm_sample **out);
+void qm_sample_destroy(qm_sample *s);
+int  qm_sample_reset(qm_sample *s, void *stream);                 /* zero counts, forget the insert-size model */
+int  qm_sample_set_pestat(qm_sample *s, const qm_pestat pes[4]);
+int  qm_sample_get_pestat(const qm_sample *s, qm_pestat pes[4]);
+int  qm_sample_estimate_pestat(qm_sample *s, const uint8_t *d_codes, int32_t stride, const int32_t *d_lens, int64_t n_pairs,
+                               void *stream);
+int  qm_sample_add_pairs(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride,
+                         const int32_t *d_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *d_alns /* may be NULL */,
+                         void *stream);
+int  qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t *h_quals, int32_t stride,
+                              const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns /* may be NULL */);
+int32_t *qm_sample_counts(qm_sample *s);                          /* device pointer, planes [QM_NCH][l_pac] */
+int  qm_sample_stats_sync(qm_sample *s, int64_t *n_pairs, int64_t *cells, void *stream);
+int  qm_sample_counts_host(qm_sample *s, int32_t *h_rows /* [l_pac][QM_NCH] */);
+
+/* ---- SNP calls from the count tensor (stands in for `bcftools call -p 0.01 --ploidy 1 -mv | bcftools view
+ * -i 'INFO/DP>=10'`, rules/vcfcall.smk:116-117).  A threshold caller: a non-reference base b is called at a
+ * position when raw depth (channel 14) >= min_dp, AD[b] >= min_alt and AD[b] >= min_af * sum(AD).  bcftools'
+ * likelihood model and QUAL are outside the parity contract; QUAL here is a phred-scaled
+ * Chernoff bound of the binomial error tail.  Output sorted by (position, alt).  Synchronous. */
+typedef struct { int32_t min_dp, min_alt; float min_af; int32_t reserved; } qm_call_opt;
+typedef struct {
+    int32_t rid, pos;             /* 0-based position on contig rid */
+    uint8_t ref, alt, pad[2];     /* base codes 0..3 */
+    int32_t dp, ad_ref_f, ad_ref_r, ad_alt_f, ad_alt_r;
+    float   qual, af;
+} qm_call;                        /* 40 B */
+void qm_call_opt_default(qm_call_opt *o);
+int  qm_call_snps(qm_ctx *ctx, const qm_index *idx, const qm_call_opt *copt, const int32_t *d_counts, qm_call *d_calls,
+                  int64_t max_calls, int64_t *h_n_calls, void *stream);
+
+/* ---- TP/FP/FN matcher (replaces the `fgrep -wf` / `fgrep -wvf` pipelines of
+ * program/extract_TP_FP_SNPs.py:47-57 and the set arithmetic of scripts/caller_performance_compare.R:93-99) ----
+ * key = pos << 8 | ref << 4 | alt (1-based VCF POS, base codes 0..3); CHROM is not part of the key, exactly
+ * like the script's pattern "POS\t.\tREF\tALT".  call_flags[i] = 1 iff call key i occurs among the truth keys
+ * (TP, else FP); truth_flags[j] = 1 iff truth key j occurs among the call keys (else FN).  d_truth_flags may be
+ * NULL.  Asynchronous on `stream`. */
+int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, const uint64_t *d_truth_keys, int64_t n_truth,
+                  uint8_t *d_call_flags, uint8_t *d_truth_flags, void *stream);
+
+/* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
+ * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,
+ * 4 pileup, 5 h2d, 6 d2h, 7 other.  qm_profile_collect synchronises the device and returns + clears the totals;
+ * launch counts are kept even when timing is disabled. */
+#define QM_N_STAGES 8
+int qm_profile_enable(qm_ctx *ctx, int on);
+int qm_profile_collect(qm_ctx *ctx, double ms_out[QM_N_STAGES], int64_t launches_out[QM_N_STAGES]);
+
 /* ---- synthetic inputs: deterministic, index-addressable read-pair simulator ----
  * The reference ships no reads (data/PRJEB32127.txt lists ENA URLs; no network), so benchmark and
  * parity inputs are simulated from the bundled genomes.  Pair i is a pure function of (seed, i):

@@ -13,6 +13,8 @@ struct qmo_ref { int n_contigs, k; int64_t l_pac, *off, *len; uint8_t *fwd; int6
 
 void qmo_pileup_opt_default(qmo_pileup_opt_t *p) { p->min_mapq = 0; p->min_bq = 13; p->count_orphans = 0; p->ignore_overlaps = 0; }
 
+#define INC(x) do { _Pragma("omp atomic") (x)++; } while (0)
+
 static int admitted(const qmo_pileup_opt_t *po, const qmo_aln_t *a)
 {
     if (a->flag & (0x4 | 0x100 | 0x200 | 0x400)) return 0;
@@ -38,12 +40,16 @@ static void expand(const qmo_aln_t *a, int l_seq, int32_t *rpos)
 void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs, const qmo_aln_t *alns,
                 const uint8_t *reads, const uint8_t *quals, int stride, const int32_t *lens, int32_t *counts)
 {
+    /* pairs are independent and the counts are integer sums: parallel over pairs with atomic increments */
+#pragma omp parallel
+    {
     int64_t pi;
     int32_t *rp[2];
     uint8_t *sq[2], *ql[2];
     rp[0] = (int32_t *)malloc(4 * stride); rp[1] = (int32_t *)malloc(4 * stride);
     sq[0] = (uint8_t *)malloc(stride); sq[1] = (uint8_t *)malloc(stride);
     ql[0] = (uint8_t *)malloc(stride); ql[1] = (uint8_t *)malloc(stride);
+#pragma omp for schedule(dynamic, 1024)
     for (pi = 0; pi < n_pairs; ++pi) {
         const qmo_aln_t *a[2] = { &alns[2 * pi], &alns[2 * pi + 1] };
         int ok[2], e, i, L[2] = { lens[2 * pi], lens[2 * pi + 1] };
@@ -89,22 +95,23 @@ void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs,
             for (k = 0; k < a[e]->n_cigar; ++k) {
                 int op = a[e]->cigar[k] & 0xf, len = (int)(a[e]->cigar[k] >> 4);
                 if (op == 0) {
-                    if (!started) { base[(int64_t)p * QMO_NCH + 15]++; started = 1; }
+                    if (!started) { INC(base[(int64_t)p * QMO_NCH + 15]); started = 1; }
                     for (i = 0; i < len; ++i) {
                         int32_t *row = base + (int64_t)(p + i) * QMO_NCH;
-                        row[14]++;
-                        if (ql[e][x + i] >= po->min_bq) row[(rev ? 6 : 0) + sq[e][x + i]]++;
+                        INC(row[14]);
+                        if (ql[e][x + i] >= po->min_bq) INC(row[(rev ? 6 : 0) + sq[e][x + i]]);
                     }
                     x += len; p += len; last_m = p - 1;
-                } else if (op == 1) { if (last_m >= 0) base[(int64_t)last_m * QMO_NCH + 12]++; x += len; }
+                } else if (op == 1) { if (last_m >= 0) INC(base[(int64_t)last_m * QMO_NCH + 12]); x += len; }
                 else if (op == 4) x += len;
                 else if (op == 2) {
-                    if (last_m >= 0) base[(int64_t)last_m * QMO_NCH + 13]++;
-                    for (i = 0; i < len; ++i) base[(int64_t)(p + i) * QMO_NCH + (rev ? 11 : 5)]++;
+                    if (last_m >= 0) INC(base[(int64_t)last_m * QMO_NCH + 13]);
+                    for (i = 0; i < len; ++i) INC(base[(int64_t)(p + i) * QMO_NCH + (rev ? 11 : 5)]);
                     p += len;
                 }
             }
         }
     }
     free(rp[0]); free(rp[1]); free(sq[0]); free(sq[1]); free(ql[0]); free(ql[1]);
+    }
 }

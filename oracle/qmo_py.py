@@ -206,3 +206,35 @@ def pileup(ref, alns, reads, quals, lens, popt=None):
     L.qmo_pileup(ref._h, C.byref(popt), n // 2, alns.ctypes.data, reads.ctypes.data, quals.ctypes.data, stride,
                  lens.ctypes.data, counts.ctypes.data)
     return counts
+
+
+PESTAT_PAIRS = 65536
+
+
+def run_sample(ref, codes, quals, lens, pair_id0=0, opt=None, popt=None, prefix=None):
+    """The whole read-level path for one batch of a sample, as the product's qm_sample does it: single-end
+    alignment, insert-size model from the sample's first min(n, PESTAT_PAIRS) pairs (`prefix` = (codes, lens) of
+    those pairs when this batch is a later shard), pairing + CIGAR, pileup.  -> (alns, counts, cells, pes)"""
+    opt = opt or default_opt()
+    o = align_se(ref, codes, lens, opt=opt)
+    n_pairs = len(lens) // 2
+    if prefix is None:
+        m = min(n_pairs, PESTAT_PAIRS)
+        pes = pestat(ref, o["regs"][:2 * m], o["n_regs"][:2 * m], opt=opt)
+    else:
+        pc, pl = prefix
+        m = min(len(pl) // 2, PESTAT_PAIRS)
+        po = align_se(ref, pc[:2 * m], pl[:2 * m], opt=opt)
+        pes = pestat(ref, po["regs"], po["n_regs"], opt=opt)
+    alns = pair_and_finish(ref, codes, lens, o["regs"], o["n_regs"], pes, pair_id0=pair_id0, opt=opt)
+    counts = pileup(ref, alns, codes, quals, lens, popt)
+    return alns, counts, o["cells"], pes
+
+
+def n_threads():
+    L = lib()
+    try:
+        omp = C.CDLL("libgomp.so.1")
+        return int(omp.omp_get_max_threads())
+    except OSError:
+        return 1

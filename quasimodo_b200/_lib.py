@@ -36,7 +36,16 @@ class PileupOpt(C.Structure):
                 ("ignore_overlaps", C.c_int32)]
 
 
-MAX_SEEDS, MAX_REGS, MAX_CIGAR, NCH = 64, 16, 21, 16
+class CallOpt(C.Structure):
+    _fields_ = [("min_dp", C.c_int32), ("min_alt", C.c_int32), ("min_af", C.c_float), ("reserved", C.c_int32)]
+
+
+MAX_SEEDS, MAX_REGS, MAX_CIGAR, NCH, N_STAGES, PESTAT_PAIRS = 64, 16, 21, 16, 8, 65536
+STAGES = ("seed_chain", "advance", "extend", "pair_cigar", "pileup", "h2d", "d2h", "other")
+CALL_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("ref", "u1"), ("alt", "u1"), ("pad", "u1", (2,)), ("dp", "<i4"),
+                       ("ad_ref_f", "<i4"), ("ad_ref_r", "<i4"), ("ad_alt_f", "<i4"), ("ad_alt_r", "<i4"),
+                       ("qual", "<f4"), ("af", "<f4")])
+assert CALL_DTYPE.itemsize == 40
 EXT_TASK_DTYPE = np.dtype([("q_off", "<u4"), ("t_off", "<u4"), ("qlen", "<i4"), ("tlen", "<i4"),
                            ("h0", "<i4"), ("w", "<i4"), ("end_bonus", "<i4"), ("flags", "<u4")])
 EXT_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
@@ -75,6 +84,22 @@ SIGNATURES = {
     "qm_pileup_opt_default": (None, [_P]),
     "qm_pileup_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P]),
     "qm_counts_to_rows": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qm_sample_begin": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_void_p)]),
+    "qm_sample_destroy": (None, [_P]),
+    "qm_sample_reset": (C.c_int, [_P, _P]),
+    "qm_sample_set_pestat": (C.c_int, [_P, _P]),
+    "qm_sample_get_pestat": (C.c_int, [_P, _P]),
+    "qm_sample_estimate_pestat": (C.c_int, [_P, _P, _I, _P, _L, _P]),
+    "qm_sample_add_pairs": (C.c_int, [_P, _P, _P, _I, _P, _L, _L, _P, _P]),
+    "qm_sample_add_pairs_host": (C.c_int, [_P, _P, _P, _I, _P, _L, _L, _P]),
+    "qm_sample_counts": (_P, [_P]),
+    "qm_sample_stats_sync": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
+    "qm_sample_counts_host": (C.c_int, [_P, _P]),
+    "qm_call_opt_default": (None, [_P]),
+    "qm_call_snps": (C.c_int, [_P, _P, _P, _P, _P, _L, C.POINTER(C.c_int64), _P]),
+    "qm_eval_match": (C.c_int, [_P, _P, _L, _P, _L, _P, _P, _P]),
+    "qm_profile_enable": (C.c_int, [_P, C.c_int]),
+    "qm_profile_collect": (C.c_int, [_P, _P, _P]),
     "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
     "qm_simulate_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P]),
     "qm_dpx_peak_sync": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -100,6 +125,12 @@ def lib():
 def default_opt():
     o = Opt()
     lib().qm_opt_default(C.byref(o))
+    return o
+
+
+def default_call_opt():
+    o = CallOpt()
+    lib().qm_call_opt_default(C.byref(o))
     return o
 
 

@@ -44,6 +44,99 @@ class Index:
             pass
 
 
+class Sample:
+    """One {sample}.{ref_name}: owns the count tensor; pairs are added batch by batch (qm_sample_*)."""
+
+    def __init__(self, ctx, idx, opt=None, popt=None):
+        self.ctx, self.idx = ctx, idx
+        self.opt = opt or ctx.opt
+        self.popt = popt or ctx.pileup_opt
+        self._h = C.c_void_p()
+        rc = _lib.lib().qm_sample_begin(ctx._h, idx._h, C.byref(self.opt), C.byref(self.popt), C.byref(self._h))
+        _check(ctx._h, rc, "qm_sample_begin")
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            _lib.lib().qm_sample_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, stream=0):
+        _check(self.ctx._h, _lib.lib().qm_sample_reset(self._h, C.c_void_p(stream)), "qm_sample_reset")
+
+    def set_pestat(self, pes):
+        pes = np.ascontiguousarray(pes, dtype=_lib.PESTAT_DTYPE)
+        _check(self.ctx._h, _lib.lib().qm_sample_set_pestat(self._h, pes.ctypes.data), "qm_sample_set_pestat")
+
+    def get_pestat(self):
+        pes = np.zeros(4, dtype=_lib.PESTAT_DTYPE)
+        _check(self.ctx._h, _lib.lib().qm_sample_get_pestat(self._h, pes.ctypes.data), "qm_sample_get_pestat")
+        return pes
+
+    def estimate_pestat(self, d_codes, d_lens, stream=0):
+        """insert-size model from the sample's first pairs (device tensors); see qm_sample_estimate_pestat"""
+        n, stride = d_codes.shape
+        rc = _lib.lib().qm_sample_estimate_pestat(self._h, _ptr(d_codes), stride, _ptr(d_lens), n // 2, C.c_void_p(stream))
+        _check(self.ctx._h, rc, "qm_sample_estimate_pestat")
+
+    def add_pairs(self, d_codes, d_quals, d_lens, pair_id0=0, d_alns=None, stream=0):
+        """device-resident batch: torch uint8 [2n, stride] codes / quals, int32 [2n] lens"""
+        n, stride = d_codes.shape
+        rc = _lib.lib().qm_sample_add_pairs(self._h, _ptr(d_codes), _ptr(d_quals), stride, _ptr(d_lens), n // 2,
+                                            int(pair_id0), _ptr(d_alns), C.c_void_p(stream))
+        _check(self.ctx._h, rc, "qm_sample_add_pairs")
+
+    def add_pairs_host(self, h_codes, h_quals, h_lens, pair_id0=0, h_alns=None):
+        """host batch (numpy arrays or pinned torch CPU tensors); copies happen inside"""
+        def hp(a):
+            return C.c_void_p(0) if a is None else C.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+        n, stride = h_codes.shape
+        rc = _lib.lib().qm_sample_add_pairs_host(self._h, hp(h_codes), hp(h_quals), int(stride), hp(h_lens), n // 2,
+                                                 int(pair_id0), hp(h_alns))
+        _check(self.ctx._h, rc, "qm_sample_add_pairs_host")
+
+    def counts_ptr(self):
+        return _lib.lib().qm_sample_counts(self._h)
+
+    def counts_tensor(self):
+        """torch int32 view [NCH, l_pac] of the device count tensor (no copy)"""
+        import torch
+        n = _lib.NCH * self.idx.l_pac
+
+        class _Holder:
+            pass
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (self.counts_ptr(), False), "version": 3}
+        return torch.as_tensor(h, device=f"cuda:{self.ctx.device}").view(_lib.NCH, self.idx.l_pac)
+
+    def stats(self, stream=0):
+        n, c = C.c_int64(), C.c_int64()
+        rc = _lib.lib().qm_sample_stats_sync(self._h, C.byref(n), C.byref(c), C.c_void_p(stream))
+        _check(self.ctx._h, rc, "qm_sample_stats_sync")
+        return n.value, c.value
+
+    def counts_host(self):
+        rows = np.empty((self.idx.l_pac, _lib.NCH), dtype=np.int32)
+        _check(self.ctx._h, _lib.lib().qm_sample_counts_host(self._h, rows.ctypes.data), "qm_sample_counts_host")
+        return rows
+
+    def call_snps(self, copt=None, max_calls=1 << 20, stream=0):
+        """-> structured array CALL_DTYPE, sorted by (position, alt)"""
+        import torch
+        copt = copt or _lib.default_call_opt()
+        d_calls = torch.empty(max_calls * 40, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
+        n = C.c_int64()
+        rc = _lib.lib().qm_call_snps(self.ctx._h, self.idx._h, C.byref(copt), C.c_void_p(self.counts_ptr()), _ptr(d_calls),
+                                     max_calls, C.byref(n), C.c_void_p(stream))
+        _check(self.ctx._h, rc, "qm_call_snps")
+        return d_calls[:n.value * 40].cpu().numpy().view(_lib.CALL_DTYPE)
+
+
 class Context:
     """One per (process, device).  Raises if no B200-class device is usable (no CPU fallback)."""
 
@@ -97,6 +190,19 @@ class Context:
         rc = _lib.lib().qm_dpx_peak_sync(self._h, kind, iters, C.byref(g), C.byref(ms))
         _check(self._h, rc, "qm_dpx_peak_sync")
         return g.value, ms.value
+
+    def sample(self, idx, opt=None, popt=None):
+        return Sample(self, idx, opt, popt)
+
+    def profile_enable(self, on=True):
+        _check(self._h, _lib.lib().qm_profile_enable(self._h, 1 if on else 0), "qm_profile_enable")
+
+    def profile_collect(self):
+        """-> ({stage: ms}, {stage: launches}); synchronises the device and clears the totals"""
+        ms = (C.c_double * _lib.N_STAGES)()
+        ln = (C.c_int64 * _lib.N_STAGES)()
+        _check(self._h, _lib.lib().qm_profile_collect(self._h, ms, ln), "qm_profile_collect")
+        return dict(zip(_lib.STAGES, list(ms))), dict(zip(_lib.STAGES, list(ln)))
 
     # ---- alignment pipeline on a device-resident read batch (torch uint8 tensors [2*n_pairs, stride]) ----
     def index(self, genome, k=None):

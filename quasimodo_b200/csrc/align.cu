@@ -538,19 +538,27 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
         const unsigned grid = (unsigned)((nb + tpb - 1) / tpb);
         const uint8_t *codes = d_codes + b0 * stride;
         const int32_t *lens = d_lens + b0;
+        int sp = qm_prof_begin(ctx, QM_ST_SEED, st);
         seed_chain_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan,
                                                 sc.n_plan, sc.st, false);
+        qm_prof_end(ctx, QM_ST_SEED, sp, st, 1);
         for (int round = 0; round < 4 * QM_MAX_REGS + 8; ++round) {
+            sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
             cudaMemsetAsync(sc.ctr, 0, sizeof(RoundCounters), st);
             advance_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.plan, sc.n_plan, sc.st,
                                                  d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.res, sc.tasks, sc.lists, nb,
                                                  sc.ctr, (unsigned long long *)d_cells);
+            qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
             cudaMemcpyAsync(h_ctr, sc.ctr, sizeof(RoundCounters), cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { cudaFreeHost(h_ctr); return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
             if (h_ctr->n_tasks == 0) break;
+            sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
+            int n_launch = 0;
+            for (int c = 0; c < kExtClasses; ++c) n_launch += h_ctr->class_count[c] > 0;
             rc = qm_ext_launch_classes(ctx, P, idx->v, sc.tasks, sc.lists, nb, sc.ctr->class_count, sc.ctr->class_cursor,
                                        h_ctr->class_count, sc.res, st);
+            qm_prof_end(ctx, QM_ST_EXTEND, sp, st, n_launch);
             if (rc) { cudaFreeHost(h_ctr); return rc; }
         }
     }

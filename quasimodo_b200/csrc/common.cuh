@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include "../../include/quasimodo_b200.h"
 
 #define QM_WARP 32
@@ -13,14 +14,27 @@ struct qm_scratch {
     size_t cap = 0;
 };
 
+// stage timers (CUDA events on the launching stream; enabled by qm_profile_enable)
+enum { QM_ST_SEED = 0, QM_ST_ADVANCE, QM_ST_EXTEND, QM_ST_PAIR, QM_ST_PILEUP, QM_ST_H2D, QM_ST_D2H, QM_ST_OTHER, QM_ST_N };
+struct qm_prof_span { int stage; cudaEvent_t e0, e1; };
+
 struct qm_ctx {
     int device = -1;
     int sm_count = 0;
     std::string err;
     // scratch arenas grown on demand (never shrunk); index = purpose
-    qm_scratch scratch[8];
-    cudaStream_t own_stream = nullptr;
+    qm_scratch scratch[12];
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    bool prof_on = false;
+    std::vector<qm_prof_span> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[QM_ST_N] = {};
+    long long prof_launches[QM_ST_N] = {};
 };
+
+// open / close a timed span on stream st (no-ops unless profiling is enabled)
+int qm_prof_begin(qm_ctx *ctx, int stage, cudaStream_t st);
+void qm_prof_end(qm_ctx *ctx, int stage, int span, cudaStream_t st, int launches);
 
 // grow-only scratch; contents are NOT preserved across a growth
 int qm_scratch_reserve(qm_ctx *ctx, int which, size_t bytes, void **out);

@@ -28,7 +28,58 @@ int qm_scratch_reserve(qm_ctx *ctx, int which, size_t bytes, void **out)
     return QM_OK;
 }
 
+static cudaEvent_t prof_event(qm_ctx *ctx)
+{
+    cudaEvent_t e = nullptr;
+    if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+int qm_prof_begin(qm_ctx *ctx, int stage, cudaStream_t st)
+{
+    if (!ctx->prof_on) return -1;
+    qm_prof_span sp;
+    sp.stage = stage; sp.e0 = prof_event(ctx); sp.e1 = prof_event(ctx);
+    cudaEventRecord(sp.e0, st);
+    ctx->prof_spans.push_back(sp);
+    return (int)ctx->prof_spans.size() - 1;
+}
+
+void qm_prof_end(qm_ctx *ctx, int stage, int span, cudaStream_t st, int launches)
+{
+    ctx->prof_launches[stage] += launches;          // launch counts are kept even when timing is off
+    if (span >= 0) cudaEventRecord(ctx->prof_spans[span].e1, st);
+}
+
 extern "C" {
+
+int qm_profile_enable(qm_ctx *ctx, int on)
+{
+    if (!ctx) return QM_EINVAL;
+    ctx->prof_on = on != 0;
+    return QM_OK;
+}
+
+// synchronises the device, adds every finished span to the per-stage totals, returns and clears them
+int qm_profile_collect(qm_ctx *ctx, double *ms_out, int64_t *launches_out)
+{
+    if (!ctx) return QM_EINVAL;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    QM_CUDA(ctx, cudaDeviceSynchronize());
+    for (auto &sp : ctx->prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) ctx->prof_ms[sp.stage] += ms;
+        ctx->prof_pool.push_back(sp.e0); ctx->prof_pool.push_back(sp.e1);
+    }
+    ctx->prof_spans.clear();
+    for (int i = 0; i < QM_ST_N; ++i) {
+        if (ms_out) ms_out[i] = ctx->prof_ms[i];
+        if (launches_out) launches_out[i] = ctx->prof_launches[i];
+        ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0;
+    }
+    return QM_OK;
+}
 
 void qm_opt_default(qm_opt *o)
 {
@@ -63,7 +114,8 @@ int qm_ctx_create(int device, qm_ctx **out)
     qm_ctx *c = new qm_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return QM_ECUDA; }
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return QM_ECUDA; }
     *out = c;
     return QM_OK;
 }
@@ -74,6 +126,9 @@ void qm_ctx_destroy(qm_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (auto &s : ctx->scratch) if (s.ptr) cudaFree(s.ptr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     delete ctx;
 }
 

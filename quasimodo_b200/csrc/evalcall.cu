@@ -1,0 +1,205 @@
+// evalcall.cu -- (1) SNP calls from the count tensor, (2) the TP/FP/FN matcher.
+//
+// (1) stands in for `bcftools call -p 0.01 --ploidy 1 -mv | bcftools view -i 'INFO/DP>=10'`
+//     (rules/vcfcall.smk:116-117).  bcftools' multiallelic likelihood model and its QUAL are NOT reproduced
+//     (outside the parity contract); this is a threshold caller whose records carry what the
+//     downstream consumers read: POS, single-base REF/ALT, QUAL, DP, AF.
+// (2) replaces the three bash pipelines of program/extract_TP_FP_SNPs.py:24-57 -- `fgrep -wf` of
+//     "POS\t.\tREF\tALT" patterns against the caller's SNP lines -- by a sorted-key membership test:
+//     key = pos << 8 | ref << 4 | alt (CHROM is not compared, exactly like the script; B.5).
+#include <math.h>
+#include "pipeline.cuh"
+
+namespace {
+
+__device__ __forceinline__ bool call_test(const qm_call_opt &o, int dp_raw, int tot, int ad)
+{
+    return dp_raw >= o.min_dp && ad >= o.min_alt && tot > 0 && (double)ad >= (double)o.min_af * (double)tot;
+}
+
+// pass 0: number of calls per position; pass 1: write them at offs[pos]
+template <int PASS>
+__global__ void call_kernel(IndexView V, qm_call_opt o, const int32_t *__restrict__ counts, int *__restrict__ n_at,
+                            const int64_t *__restrict__ offs, qm_call *__restrict__ out, int64_t max_calls)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= V.l_pac) return;
+    const int64_t L = V.l_pac;
+    int ad[4], adf[4], tot = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { adf[b] = counts[b * L + p]; ad[b] = adf[b] + counts[(6 + b) * L + p]; tot += ad[b]; }
+    const int dp_raw = counts[14 * L + p];
+    const int ref = V.refb[p];
+    int n = 0;
+    int64_t at = PASS ? offs[p] : 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (b == ref || !call_test(o, dp_raw, tot, ad[b])) continue;
+        if (PASS) {
+            if (at < max_calls) {
+                qm_call c;
+                const int rid = qm_pos2rid(V, p);
+                c.rid = rid; c.pos = (int32_t)(p - V.off[rid]);
+                c.ref = (uint8_t)ref; c.alt = (uint8_t)b; c.pad[0] = c.pad[1] = 0;
+                c.dp = dp_raw;
+                c.ad_ref_f = adf[ref]; c.ad_ref_r = ad[ref] - adf[ref];
+                c.ad_alt_f = adf[b]; c.ad_alt_r = ad[b] - adf[b];
+                // QUAL: Chernoff bound on the binomial tail P(X >= ad | tot, e = 0.002), phred scaled, capped at 999
+                const double f = (double)ad[b] / tot, e = 0.002;
+                double kl = f * log(f / e);
+                if (f < 1.0) kl += (1.0 - f) * log((1.0 - f) / (1.0 - e));
+                double q = f > e ? 4.342944819032518 * tot * kl : 0.0;
+                c.qual = (float)(q > 999.0 ? 999.0 : q);
+                c.af = (float)f;
+                out[at] = c;
+            }
+            ++at;
+        }
+        ++n;
+    }
+    if (!PASS) n_at[p] = n;
+}
+
+// single-block exclusive scan of n ints into int64 offsets; total to offs[n]
+__global__ void scan_kernel(const int *__restrict__ in, int64_t n, int64_t *__restrict__ offs)
+{
+    __shared__ int64_t warp_sum[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        int64_t v = i < n ? in[i] : 0, x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int64_t s = lane < (int)(blockDim.x >> 5) ? warp_sum[lane] : 0, t = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
+            warp_sum[lane] = t - s;         // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        const int64_t excl = carry + warp_sum[w] + x - v;
+        if (i < n) offs[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offs[n] = carry;
+}
+
+// ---- matcher ----
+__global__ void pad_copy_kernel(const uint64_t *__restrict__ in, int64_t n, int64_t n_pad, uint64_t *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_pad) out[i] = i < n ? in[i] : ~0ull;
+}
+
+// one block sorts n_pad (power of two) keys in global memory: bitonic network, __syncthreads between passes
+__global__ void __launch_bounds__(1024) bitonic_kernel(uint64_t *__restrict__ a, int64_t n_pad)
+{
+    for (int64_t k = 2; k <= n_pad; k <<= 1)
+        for (int64_t j = k >> 1; j > 0; j >>= 1) {
+            for (int64_t t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                const bool up = (lo & k) == 0;
+                const uint64_t x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void member_kernel(const uint64_t *__restrict__ q, int64_t nq, const uint64_t *__restrict__ sorted, int64_t ns,
+                              uint8_t *__restrict__ flags)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const uint64_t key = q[i];
+    int64_t lo = 0, hi = ns;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < key) lo = mid + 1; else hi = mid; }
+    flags[i] = (lo < ns && sorted[lo] == key) ? 1 : 0;
+}
+
+int sorted_copy(qm_ctx *ctx, int which, const uint64_t *d_keys, int64_t n, uint64_t **out, cudaStream_t st)
+{
+    int64_t n_pad = 2;
+    while (n_pad < n) n_pad <<= 1;
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, which, (size_t)n_pad * 8, &p);
+    if (rc) return rc;
+    pad_copy_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(d_keys, n, n_pad, (uint64_t *)p);
+    bitonic_kernel<<<1, 1024, 0, st>>>((uint64_t *)p, n_pad);
+    *out = (uint64_t *)p;
+    return QM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void qm_call_opt_default(qm_call_opt *o) { o->min_dp = 10; o->min_alt = 2; o->min_af = 0.01f; o->reserved = 0; }
+
+int qm_call_snps(qm_ctx *ctx, const qm_index *idx, const qm_call_opt *copt, const int32_t *d_counts, qm_call *d_calls,
+                 int64_t max_calls, int64_t *h_n_calls, void *stream)
+{
+    if (!ctx || !idx || !copt || !d_counts || !h_n_calls || max_calls < 0 || (max_calls > 0 && !d_calls)) return QM_EINVAL;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t L = idx->v.l_pac;
+    void *p = nullptr;
+    const size_t n_bytes = ((size_t)L * 4 + 255) & ~(size_t)255;
+    int rc = qm_scratch_reserve(ctx, 7, n_bytes + (size_t)(L + 1) * 8, &p);
+    if (rc) return rc;
+    int *n_at = (int *)p;
+    int64_t *offs = (int64_t *)((char *)p + n_bytes);
+    const unsigned grid = (unsigned)((L + 127) / 128);
+    const int sp = qm_prof_begin(ctx, QM_ST_OTHER, st);
+    call_kernel<0><<<grid, 128, 0, st>>>(idx->v, *copt, d_counts, n_at, nullptr, nullptr, 0);
+    scan_kernel<<<1, 1024, 0, st>>>(n_at, L, offs);
+    call_kernel<1><<<grid, 128, 0, st>>>(idx->v, *copt, d_counts, nullptr, offs, d_calls, max_calls);
+    qm_prof_end(ctx, QM_ST_OTHER, sp, st, 3);
+    QM_CUDA(ctx, cudaGetLastError());
+    QM_CUDA(ctx, cudaMemcpyAsync(h_n_calls, offs + L, 8, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    if (*h_n_calls > max_calls) return qm_fail(ctx, QM_ELIMIT, "qm_call_snps: %lld calls exceed max_calls=%lld", (long long)*h_n_calls, (long long)max_calls);
+    return QM_OK;
+}
+
+int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, const uint64_t *d_truth_keys, int64_t n_truth,
+                  uint8_t *d_call_flags, uint8_t *d_truth_flags, void *stream)
+{
+    if (!ctx || n_call < 0 || n_truth < 0 || (n_call > 0 && (!d_call_keys || !d_call_flags)) || (n_truth > 0 && !d_truth_keys))
+        return QM_EINVAL;
+    if (n_call > (1ll << 26) || n_truth > (1ll << 26)) return qm_fail(ctx, QM_ELIMIT, "qm_eval_match: more than 2^26 keys");
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sp = qm_prof_begin(ctx, QM_ST_OTHER, st);
+    int launches = 0;
+    if (n_call > 0) {
+        if (n_truth > 0) {
+            uint64_t *sorted = nullptr;
+            int rc = sorted_copy(ctx, 8, d_truth_keys, n_truth, &sorted, st);
+            if (rc) return rc;
+            member_kernel<<<(unsigned)((n_call + 255) / 256), 256, 0, st>>>(d_call_keys, n_call, sorted, n_truth, d_call_flags);
+            launches += 3;
+        } else QM_CUDA(ctx, cudaMemsetAsync(d_call_flags, 0, (size_t)n_call, st));
+    }
+    if (n_truth > 0 && d_truth_flags) {
+        if (n_call > 0) {
+            uint64_t *sorted = nullptr;
+            int rc = sorted_copy(ctx, 9, d_call_keys, n_call, &sorted, st);
+            if (rc) return rc;
+            member_kernel<<<(unsigned)((n_truth + 255) / 256), 256, 0, st>>>(d_truth_keys, n_truth, sorted, n_call, d_truth_flags);
+            launches += 3;
+        } else QM_CUDA(ctx, cudaMemsetAsync(d_truth_flags, 0, (size_t)n_truth, st));
+    }
+    qm_prof_end(ctx, QM_ST_OTHER, sp, st, launches);
+    QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}
+
+}  // extern "C"

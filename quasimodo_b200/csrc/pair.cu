@@ -62,22 +62,20 @@ __device__ int cal_sub(const qm_opt &o, const qm_reg *a, int n)
     return j < n ? a[j].score : o.min_seed_len * o.a;
 }
 
-// candidate insert sizes for mem_pestat: out[i] = dir<<32 | isize, or 0 when the pair does not qualify
-__global__ void pestat_collect_kernel(IndexView V, qm_opt o, const qm_reg *__restrict__ regs, const int32_t *__restrict__ n_regs,
-                                      int64_t n_pairs, uint64_t *__restrict__ out)
+// insert-size histogram for mem_pestat: hist[dir][isize] += 1 for every qualifying pair
+__global__ void pestat_hist_kernel(IndexView V, qm_opt o, const qm_reg *__restrict__ regs, const int32_t *__restrict__ n_regs,
+                                   int64_t n_pairs, unsigned *__restrict__ hist)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const qm_reg *r0 = regs + (2 * i) * QM_MAX_REGS, *r1 = regs + (2 * i + 1) * QM_MAX_REGS;
     const int n0 = n_regs[2 * i], n1 = n_regs[2 * i + 1];
-    uint64_t v = 0;
     if (n0 && n1 && !(cal_sub(o, r0, n0) > 0.8 * r0[0].score) && !(cal_sub(o, r1, n1) > 0.8 * r1[0].score) &&
         r0[0].rid == r1[0].rid) {
         int64_t is;
         const int dir = infer_dir(V.l_pac, r0[0].rb, r1[0].rb, &is);
-        if (is && is <= o.max_ins) v = (uint64_t)dir << 32 | (uint64_t)is | (1ull << 40);
+        if (is && is <= o.max_ins) atomicAdd(&hist[(int64_t)dir * (o.max_ins + 1) + is], 1u);
     }
-    out[i] = v;
 }
 
 // mem_mark_primary_se: sort by (score desc, hash asc), mark secondaries, fill sub / sub_n
@@ -503,38 +501,51 @@ int qm_pestat_sync(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm
                    int64_t n_pairs, qm_pestat pes[4], void *stream)
 {
     if (!ctx || !idx || !opt || !pes || n_pairs < 0 || (n_pairs > 0 && (!d_regs || !d_n_regs))) return QM_EINVAL;
+    if (opt->max_ins < 1 || opt->max_ins > (1 << 20)) return qm_fail(ctx, QM_ELIMIT, "qm_pestat_sync: max_ins must be in [1, 2^20]");
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<uint64_t> h((size_t)n_pairs);
+    // device: one histogram of insert sizes per orientation; host: the percentile / moment arithmetic of
+    // mem_pestat replayed over the histogram in ascending order (same operation order as over the sorted list)
+    const size_t bins = (size_t)opt->max_ins + 1;
+    std::vector<unsigned> h(4 * bins, 0u);
     if (n_pairs > 0) {
         void *p = nullptr;
-        int rc = qm_scratch_reserve(ctx, 4, (size_t)n_pairs * 8, &p);
+        int rc = qm_scratch_reserve(ctx, 4, 4 * bins * sizeof(unsigned), &p);
         if (rc) return rc;
+        QM_CUDA(ctx, cudaMemsetAsync(p, 0, 4 * bins * sizeof(unsigned), st));
         const int tpb = 128;
-        pestat_collect_kernel<<<(unsigned)((n_pairs + tpb - 1) / tpb), tpb, 0, st>>>(idx->v, *opt, d_regs, d_n_regs, n_pairs, (uint64_t *)p);
-        QM_CUDA(ctx, cudaMemcpyAsync(h.data(), p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
+        const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
+        pestat_hist_kernel<<<(unsigned)((n_pairs + tpb - 1) / tpb), tpb, 0, st>>>(idx->v, *opt, d_regs, d_n_regs, n_pairs, (unsigned *)p);
+        qm_prof_end(ctx, QM_ST_PAIR, sp, st, 1);
+        QM_CUDA(ctx, cudaMemcpyAsync(h.data(), p, 4 * bins * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         QM_CUDA(ctx, cudaStreamSynchronize(st));
     }
-    // host part of mem_pestat: percentiles and moments per orientation
-    std::vector<uint64_t> isz[4];
-    for (uint64_t v : h) if (v) isz[(v >> 32) & 3].push_back(v & 0xffffffffu);
-    size_t max = 0;
+    int64_t cnt[4], max = 0;
     for (int d = 0; d < 4; ++d) {
         qm_pestat *r = &pes[d];
         r->low = r->high = r->failed = r->pad = 0; r->avg = r->std = 0;
-        std::vector<uint64_t> &q = isz[d];
-        const int64_t n = (int64_t)q.size();
-        if (q.size() > max) max = q.size();
+        const unsigned *q = h.data() + (size_t)d * bins;
+        int64_t n = 0;
+        for (size_t v = 0; v < bins; ++v) n += q[v];
+        cnt[d] = n;
+        if (n > max) max = n;
         if (n < 10) { r->failed = 1; continue; }
-        std::sort(q.begin(), q.end());
-        const int p25 = (int)q[(int)(.25 * n + .499)], p75 = (int)q[(int)(.75 * n + .499)];
+        auto nth = [&](int64_t k) {       // value at rank k of the ascending list
+            int64_t c = 0;
+            for (size_t v = 0; v < bins; ++v) { c += q[v]; if (c > k) return (int)v; }
+            return (int)bins - 1;
+        };
+        const int p25 = nth((int)(.25 * n + .499)), p75 = nth((int)(.75 * n + .499));
         r->low = (int)(p25 - 2.0 * (p75 - p25) + .499);
         if (r->low < 1) r->low = 1;
         r->high = (int)(p75 + 2.0 * (p75 - p25) + .499);
         int64_t x = 0;
-        for (int64_t i = 0; i < n; ++i) if ((int64_t)q[i] >= r->low && (int64_t)q[i] <= r->high) { r->avg += q[i]; ++x; }
+        for (int64_t v = r->low; v <= r->high && v < (int64_t)bins; ++v) for (unsigned c = 0; c < q[v]; ++c) { r->avg += (double)v; ++x; }
         r->avg /= x;
-        for (int64_t i = 0; i < n; ++i) if ((int64_t)q[i] >= r->low && (int64_t)q[i] <= r->high) r->std += (q[i] - r->avg) * (q[i] - r->avg);
+        for (int64_t v = r->low; v <= r->high && v < (int64_t)bins; ++v) {
+            const double dlt = ((double)v - r->avg) * ((double)v - r->avg);
+            for (unsigned c = 0; c < q[v]; ++c) r->std += dlt;
+        }
         r->std = sqrt(r->std / x);
         r->low = (int)(p25 - 3.0 * (p75 - p25) + .499);
         r->high = (int)(p75 + 3.0 * (p75 - p25) + .499);
@@ -542,7 +553,7 @@ int qm_pestat_sync(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm
         if (r->high < r->avg + 4.0 * r->std) r->high = (int)(r->avg + 4.0 * r->std + .499);
         if (r->low < 1) r->low = 1;
     }
-    for (int d = 0; d < 4; ++d) if (!pes[d].failed && isz[d].size() < max * 0.05) pes[d].failed = 1;
+    for (int d = 0; d < 4; ++d) if (!pes[d].failed && cnt[d] < max * 0.05) pes[d].failed = 1;
     return QM_OK;
 }
 
@@ -596,7 +607,9 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     PS.overflow_used = (unsigned long long *)(b + o_misc); PS.err = (int *)(b + o_misc + 16);
     int64_t blocks = (n_pairs + 127) / 128;
     if (blocks > threads_total / 128) blocks = threads_total / 128;
+    const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
     pair_kernel<<<(unsigned)blocks, 128, 0, st>>>(idx->v, *opt, T, PS, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns);
+    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 1);
     QM_CUDA(ctx, cudaGetLastError());
     int h_err = 0;
     QM_CUDA(ctx, cudaMemcpyAsync(&h_err, PS.err, 4, cudaMemcpyDeviceToHost, st));

@@ -177,8 +177,10 @@ int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *
     int64_t blocks = (n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int64_t cap = (int64_t)ctx->sm_count * 16;       // persistent: 16 blocks x 4 warps per SM
     if (blocks > cap) blocks = cap;
+    const int sp = qm_prof_begin(ctx, QM_ST_PILEUP, (cudaStream_t)stream);
     pileup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr);
+    qm_prof_end(ctx, QM_ST_PILEUP, sp, (cudaStream_t)stream, 1);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }

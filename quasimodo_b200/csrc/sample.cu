@@ -1,0 +1,246 @@
+// sample.cu -- one sample end to end on one device: the compute of the reference's `bwa` rule
+// (rules/bwa.smk:15 `bwa mem -k 31 ref r1 r2`) followed by the counting of its `bcftools` / `mpileup`
+// rules (rules/vcfcall.smk:39,115) for one {sample}.{ref_name}, fed batch by batch.
+//
+// A qm_sample owns the int32 count tensor [QM_NCH][l_pac] of the sample and chunk-sized scratch (regions,
+// alignment records).  Pairs are processed in chunks of kChunkPairs: seeding/chaining -> extension rounds ->
+// pairing/CIGAR -> pileup, all on the caller's stream (device entry) or on the context's compute stream with
+// the next chunk's host->device copy running on the copy stream (host entry).  The insert-size model
+// (bwa's per-chunk mem_pestat) is fixed ONCE per sample from the first min(n, 2^18) pairs handed in -- or
+// set by the caller (multi-GPU: rank 0's model is broadcast) -- so that results do not depend on how the
+// pair stream is split into batches or across GPUs.
+#include "pipeline.cuh"
+
+namespace {
+constexpr int64_t kChunkPairs = 1 << 18;
+constexpr int64_t kPestatPairs = QM_PESTAT_PAIRS;
+}
+
+struct qm_sample {
+    qm_ctx *ctx = nullptr;
+    const qm_index *idx = nullptr;
+    qm_opt opt;
+    qm_pileup_opt popt;
+    int32_t *d_counts = nullptr;
+    int64_t *d_cells = nullptr;
+    qm_reg *d_regs = nullptr;
+    int32_t *d_n_regs = nullptr;
+    qm_aln *d_alns = nullptr;
+    uint8_t *d_stage[2] = {nullptr, nullptr};     // host-entry staging: codes | quals | lens, double buffered
+    size_t stage_cap = 0;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool have_pes = false;
+    qm_pestat pes[4];
+    int64_t n_pairs = 0;
+};
+
+namespace {
+
+int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                 int64_t n, int64_t pair_id0, qm_aln *d_alns_out, cudaStream_t st)
+{
+    qm_ctx *ctx = s->ctx;
+    int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, s->d_cells, st);
+    if (rc) return rc;
+    if (!s->have_pes) {
+        rc = qm_pestat_sync(ctx, s->idx, &s->opt, s->d_regs, s->d_n_regs, n < kPestatPairs ? n : kPestatPairs, s->pes, st);
+        if (rc) return rc;
+        s->have_pes = true;
+    }
+    qm_aln *alns = d_alns_out ? d_alns_out : s->d_alns;
+    rc = qm_pair_finish(ctx, s->idx, &s->opt, d_codes, stride, d_lens, n, pair_id0, s->d_regs, s->d_n_regs, s->pes, alns, st);
+    if (rc) return rc;
+    rc = qm_pileup_accumulate(ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n, s->d_counts, st);
+    if (rc) return rc;
+    s->n_pairs += n;
+    return QM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qm_sample_begin(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm_pileup_opt *popt, qm_sample **out)
+{
+    if (!ctx || !idx || !opt || !popt || !out) return QM_EINVAL;
+    *out = nullptr;
+    if (opt->min_seed_len != idx->v.k) return qm_fail(ctx, QM_EINVAL, "index built with k=%d but min_seed_len=%d", idx->v.k, opt->min_seed_len);
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    qm_sample *s = new qm_sample();
+    s->ctx = ctx; s->idx = idx; s->opt = *opt; s->popt = *popt;
+    cudaError_t e;
+    if ((e = cudaMalloc(&s->d_counts, (size_t)QM_NCH * idx->v.l_pac * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_cells, 8)) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_regs, (size_t)2 * kChunkPairs * QM_MAX_REGS * sizeof(qm_reg))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_n_regs, (size_t)2 * kChunkPairs * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_alns, (size_t)2 * kChunkPairs * sizeof(qm_aln))) != cudaSuccess ||
+        (e = cudaMemset(s->d_counts, 0, (size_t)QM_NCH * idx->v.l_pac * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMemset(s->d_cells, 0, 8)) != cudaSuccess) {
+        qm_sample_destroy(s);
+        return qm_fail(ctx, QM_ENOMEM, "qm_sample_begin: %s", cudaGetErrorString(e));
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_consumed[i], cudaEventDisableTiming);
+    }
+    *out = s;
+    return QM_OK;
+}
+
+void qm_sample_destroy(qm_sample *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(s->d_counts); cudaFree(s->d_cells); cudaFree(s->d_regs); cudaFree(s->d_n_regs); cudaFree(s->d_alns);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->d_stage[i]);
+        if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+        if (s->ev_consumed[i]) cudaEventDestroy(s->ev_consumed[i]);
+    }
+    delete s;
+}
+
+// zero the counts and forget the insert-size model: the object can be reused for the next sample
+int qm_sample_reset(qm_sample *s, void *stream)
+{
+    if (!s) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    QM_CUDA(ctx, cudaMemsetAsync(s->d_counts, 0, (size_t)QM_NCH * s->idx->v.l_pac * sizeof(int32_t), (cudaStream_t)stream));
+    QM_CUDA(ctx, cudaMemsetAsync(s->d_cells, 0, 8, (cudaStream_t)stream));
+    s->have_pes = false; s->n_pairs = 0;
+    return QM_OK;
+}
+
+int qm_sample_set_pestat(qm_sample *s, const qm_pestat pes[4])
+{
+    if (!s || !pes) return QM_EINVAL;
+    for (int d = 0; d < 4; ++d) s->pes[d] = pes[d];
+    s->have_pes = true;
+    return QM_OK;
+}
+
+int qm_sample_get_pestat(const qm_sample *s, qm_pestat pes[4])
+{
+    if (!s || !pes) return QM_EINVAL;
+    if (!s->have_pes) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_get_pestat: no pairs added yet and no model set");
+    for (int d = 0; d < 4; ++d) pes[d] = s->pes[d];
+    return QM_OK;
+}
+
+// insert-size model from a designated prefix of the sample (the first min(n, QM_PESTAT_PAIRS) pairs given):
+// single-end alignment of the prefix + mem_pestat, nothing is counted.  A shard that does not start at pair 0
+// calls this with the sample's first pairs before adding its own (every rank gets the same model, no collective).
+int qm_sample_estimate_pestat(qm_sample *s, const uint8_t *d_codes, int32_t stride, const int32_t *d_lens, int64_t n_pairs,
+                              void *stream)
+{
+    if (!s || n_pairs <= 0 || !d_codes || !d_lens || stride <= 0) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = n_pairs < kPestatPairs ? n_pairs : kPestatPairs;
+    int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = qm_pestat_sync(ctx, s->idx, &s->opt, s->d_regs, s->d_n_regs, n, s->pes, (cudaStream_t)stream);
+    if (rc) return rc;
+    s->have_pes = true;
+    return QM_OK;
+}
+
+int qm_sample_add_pairs(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                        int64_t n_pairs, int64_t pair_id0, qm_aln *d_alns, void *stream)
+{
+    if (!s || n_pairs < 0 || (n_pairs > 0 && (!d_codes || !d_quals || !d_lens)) || stride <= 0) return QM_EINVAL;
+    QM_CUDA(s->ctx, cudaSetDevice(s->ctx->device));
+    for (int64_t p0 = 0; p0 < n_pairs; p0 += kChunkPairs) {
+        const int64_t n = n_pairs - p0 < kChunkPairs ? n_pairs - p0 : kChunkPairs;
+        int rc = sample_chunk(s, d_codes + 2 * p0 * stride, d_quals + 2 * p0 * stride, stride, d_lens + 2 * p0, n, pair_id0 + p0,
+                              d_alns ? d_alns + 2 * p0 : nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return QM_OK;
+}
+
+// Host entry: h_* should be page-locked for the copies to overlap the previous chunk's kernels.
+// h_alns (may be NULL) receives the alignment records, 2 per pair, in input order.  Synchronous.
+int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t *h_quals, int32_t stride,
+                             const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns)
+{
+    if (!s || n_pairs < 0 || (n_pairs > 0 && (!h_codes || !h_quals || !h_lens)) || stride <= 0) return QM_EINVAL;
+    if (n_pairs == 0) return QM_OK;
+    qm_ctx *ctx = s->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t seq_bytes = (size_t)2 * kChunkPairs * stride;
+    const size_t seq_al = (seq_bytes + 255) & ~(size_t)255;
+    const size_t need = 2 * seq_al + (size_t)2 * kChunkPairs * sizeof(int32_t);
+    if (need > s->stage_cap) {
+        for (int i = 0; i < 2; ++i) {
+            if (s->d_stage[i]) QM_CUDA(ctx, cudaFree(s->d_stage[i]));
+            s->d_stage[i] = nullptr;
+            QM_CUDA(ctx, cudaMalloc(&s->d_stage[i], need));
+        }
+        s->stage_cap = need;
+    }
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->own_stream;
+    const int64_t n_chunks = (n_pairs + kChunkPairs - 1) / kChunkPairs;
+    auto enqueue_copy = [&](int64_t c) -> cudaError_t {
+        const int b = (int)(c & 1);
+        const int64_t p0 = c * kChunkPairs, n = n_pairs - p0 < kChunkPairs ? n_pairs - p0 : kChunkPairs;
+        cudaError_t e;
+        if ((e = cudaStreamWaitEvent(cs, s->ev_consumed[b], 0)) != cudaSuccess) return e;     // buffer b free again
+        if ((e = cudaMemcpyAsync(s->d_stage[b], h_codes + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(s->d_stage[b] + seq_al, h_quals + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(s->d_stage[b] + 2 * seq_al, h_lens + 2 * p0, (size_t)2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+        return cudaEventRecord(s->ev_copied[b], cs);
+    };
+    // a fresh event counts as completed, so the first two waits on ev_consumed pass immediately
+    QM_CUDA(ctx, enqueue_copy(0));
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t p0 = c * kChunkPairs, n = n_pairs - p0 < kChunkPairs ? n_pairs - p0 : kChunkPairs;
+        if (c + 1 < n_chunks) QM_CUDA(ctx, enqueue_copy(c + 1));
+        QM_CUDA(ctx, cudaStreamWaitEvent(ks, s->ev_copied[b], 0));
+        int rc = sample_chunk(s, s->d_stage[b], s->d_stage[b] + seq_al, stride, (const int32_t *)(s->d_stage[b] + 2 * seq_al), n,
+                              pair_id0 + p0, nullptr, ks);
+        if (rc) return rc;
+        if (h_alns) QM_CUDA(ctx, cudaMemcpyAsync(h_alns + 2 * p0, s->d_alns, (size_t)2 * n * sizeof(qm_aln), cudaMemcpyDeviceToHost, ks));
+        QM_CUDA(ctx, cudaEventRecord(s->ev_consumed[b], ks));
+    }
+    QM_CUDA(ctx, cudaStreamSynchronize(ks));
+    return QM_OK;
+}
+
+int32_t *qm_sample_counts(qm_sample *s) { return s ? s->d_counts : nullptr; }
+
+// executed extension cells and pairs so far (synchronises `stream`)
+int qm_sample_stats_sync(qm_sample *s, int64_t *n_pairs, int64_t *cells, void *stream)
+{
+    if (!s) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    int64_t c = 0;
+    QM_CUDA(ctx, cudaMemcpyAsync(&c, s->d_cells, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    if (n_pairs) *n_pairs = s->n_pairs;
+    if (cells) *cells = c;
+    return QM_OK;
+}
+
+// count tensor to the host as rows [l_pac][QM_NCH] (count-TSV order); synchronous
+int qm_sample_counts_host(qm_sample *s, int32_t *h_rows)
+{
+    if (!s || !h_rows) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    QM_CUDA(ctx, cudaDeviceSynchronize());          // counts may have been accumulated on any stream
+    void *p = nullptr;
+    const size_t bytes = (size_t)QM_NCH * s->idx->v.l_pac * sizeof(int32_t);
+    int rc = qm_scratch_reserve(ctx, 6, bytes, &p);
+    if (rc) return rc;
+    rc = qm_counts_to_rows(ctx, s->idx, s->d_counts, (int32_t *)p, ctx->own_stream);
+    if (rc) return rc;
+    QM_CUDA(ctx, cudaMemcpyAsync(h_rows, p, bytes, cudaMemcpyDeviceToHost, ctx->own_stream));
+    QM_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+    return QM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+"""CPU: the evaluation oracle (oracle/eval_py.py) against the golden outputs of the reference's own
+program/extract_TP_FP_SNPs.py (tests/golden/eval, made by tests/golden/make_eval_golden.py), byte for byte;
+plus the caller_performance table restatement on the same files."""
+import filecmp
+import os
+import shutil
+
+import pytest
+
+from oracle import eval_py
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval")
+
+
+@pytest.mark.parametrize("sample", ["TM-1-1", "TA-1-0"])
+def test_extract_matches_reference_script(tmp_path, sample):
+    src = os.path.join(GOLD, sample)
+    d = tmp_path / sample
+    os.makedirs(d / "fp")
+    name = f"{sample}.Merlin.bcftools"
+    shutil.copy(os.path.join(src, name + ".vcf"), d)
+    eval_py.extract_tp_fp_snp(str(d / (name + ".vcf")), os.path.join(src, "truth.vcf"))
+    assert filecmp.cmp(d / (name + ".filtered.vcf"), os.path.join(src, name + ".filtered.vcf"), shallow=False)
+    assert filecmp.cmp(d / "fp" / (name + ".fp.vcf"), os.path.join(src, "fp", name + ".fp.vcf"), shallow=False)
+    if sample == "TM-1-1":
+        assert filecmp.cmp(d / "tp" / (name + ".tp.vcf"), os.path.join(src, "tp", name + ".tp.vcf"), shallow=False)
+    else:
+        assert not (d / "tp").exists()
+
+
+def test_quirks_present_in_golden():
+    """the golden TP file holds the hits the script's word matching implies"""
+    tp = open(os.path.join(GOLD, "TM-1-1", "tp", "TM-1-1.Merlin.bcftools.tp.vcf")).read()
+    fp = open(os.path.join(GOLD, "TM-1-1", "fp", "TM-1-1.Merlin.bcftools.fp.vcf")).read()
+    assert "\t11100\t.\tA\tC\t" in fp and "\t11100\t" not in tp          # 1100 is not a word inside 11100
+    assert "\t1100\trs1\tA\tC\t" in fp                                    # ID must be "."
+    assert tp.count("\t1100\t.\tA\tC\t") >= 2                            # duplicates both kept
+    assert "OtherChrom\t7000\t.\tG\tT\t" in tp                            # CHROM is not compared
+    assert "\t7000\t.\tG\tC\t" in fp and "\t6000\t.\tA\tC\t" in fp
+
+
+def test_performance_row():
+    src = os.path.join(GOLD, "TM-1-1")
+    truth = {"TM": eval_py.make_snp_vector(os.path.join(src, "truth.vcf"))}
+    row = eval_py.performance_row(os.path.join(src, "TM-1-1.Merlin.bcftools.filtered.vcf"), truth, ["TM-1-1"])
+    snp = eval_py.make_snp_vector(os.path.join(src, "TM-1-1.Merlin.bcftools.filtered.vcf"))
+    tp = len(set(snp) & set(truth["TM"]))
+    assert row[:2] == ["BCFtools", "TM-1-1"] and int(row[3]) == len(snp) and int(row[4]) == tp
+    assert int(row[5]) == len(set(snp) - set(truth["TM"]))
+    assert row[6] == eval_py.r_num(round(tp / len(snp), 3))
+    pure = eval_py.performance_row(os.path.join(GOLD, "TA-1-0", "TA-1-0.Merlin.bcftools.filtered.vcf"), truth, ["TM-1-1"])
+    assert pure[2] == "0" and pure[4] == "0" and pure[5] == pure[3] and pure[6:] == ["0", "NA", "NA"]
