@@ -1,0 +1,83 @@
+"""Oracle sanity (CPU): the bwa-mem restatement must put simulated reads back where the simulator drew them from,
+produce self-consistent records, and its pileup must count what the records say.  These are the checks that stand
+in for golden vectors the reference does not have for its third-party aligner."""
+import numpy as np
+import pytest
+
+from oracle import qmo_py
+from quasimodo_b200 import workloads
+
+
+@pytest.fixture(scope="module")
+def run():
+    n = 3000
+    W = workloads.config1(n)
+    codes, quals, src, pos = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns, counts, cells, pes = qmo_py.run_sample(ref, codes, quals, lens)
+    return dict(W=W, n=n, codes=codes, quals=quals, src=src, pos=pos, alns=alns, counts=counts, cells=cells, pes=pes)
+
+
+def test_reference_strain_reads_map_to_origin(run):
+    s, strand = run["src"] & 0xffff, run["src"] >> 16
+    start, ins = run["pos"] & ((1 << 40) - 1), run["pos"] >> 40
+    merlin = s == 1                                    # source 1 = Merlin = the alignment reference
+    a0, a1 = run["alns"][0::2], run["alns"][1::2]
+    left = np.where(strand == 0, a0["pos"], a1["pos"])
+    both = ((a0["flag"] & 4) == 0) & ((a1["flag"] & 4) == 0)
+    ok = (left == start) & both
+    assert ok[merlin].mean() > 0.97
+    # proper pairs with TLEN = insert size
+    tl = np.abs(a0["tlen"])
+    assert (tl[merlin & ok] == ins[merlin & ok]).mean() > 0.97
+    assert ((a0["flag"] & 2) != 0)[merlin].mean() > 0.97
+
+
+def test_insert_size_model(run):
+    fr = run["pes"][1]
+    assert not fr["failed"] and abs(fr["avg"] - 350) < 3 and abs(fr["std"] - 35) < 3
+    assert all(run["pes"][d]["failed"] for d in (0, 2, 3))
+
+
+def test_records_self_consistent(run):
+    a = run["alns"]
+    mapped = (a["flag"] & 4) == 0
+    assert mapped.mean() > 0.9
+    for r in a[mapped][:500]:
+        ql = sum(c >> 4 for c in r["cigar"][:r["n_cigar"]] if (c & 0xf) in (0, 1, 4))
+        assert ql == 150
+        assert r["qe"] - r["qb"] == sum(c >> 4 for c in r["cigar"][:r["n_cigar"]] if (c & 0xf) in (0, 1))
+        assert 0 <= r["mapq"] <= 60 and r["pos"] >= 0
+    # mates point at each other
+    a0, a1 = a[0::2], a[1::2]
+    both = ((a0["flag"] & 4) == 0) & ((a1["flag"] & 4) == 0)
+    assert np.array_equal(a0["mate_pos"][both], a1["pos"][both]) and np.array_equal(a1["mate_pos"][both], a0["pos"][both])
+    assert np.array_equal(a0["tlen"][both], -a1["tlen"][both])
+
+
+def test_pileup_totals(run):
+    a, cnt = run["alns"], run["counts"]
+    admitted = ((a["flag"] & 4) == 0) & ((a["flag"] & 2) != 0) & (a["n_cigar"] != 0) & (a["n_cigar"] != 255)
+    m_bases = sum(int(sum(c >> 4 for c in r["cigar"][:r["n_cigar"]] if (c & 0xf) == 0)) for r in a[admitted])
+    assert int(cnt[:, 14].sum()) == m_bases
+    assert int(cnt[:, 15].sum()) == int(admitted.sum())
+    assert (cnt[:, :5].sum() + cnt[:, 6:11].sum()) <= m_bases          # BQ filter and overlap zeroing only remove
+    assert (cnt >= 0).all()
+
+
+def test_shards_sum_to_whole(run):
+    """oracle statement of the multi-GPU decomposition: shard counts (each with the sample's prefix) add up"""
+    from quasimodo_b200 import sharding
+    W, n = run["W"], run["n"]
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    lens = np.full(2 * n, 150, np.int32)
+    total = np.zeros_like(run["counts"])
+    for r in range(3):
+        lo, hi = sharding.shard_range(n, r, 3)
+        pre = None if r == 0 and not sharding.needs_prefix(lo, hi, n, qmo_py.PESTAT_PAIRS) else (run["codes"], lens)
+        _, c, _, pes = qmo_py.run_sample(ref, run["codes"][2 * lo:2 * hi], run["quals"][2 * lo:2 * hi], lens[2 * lo:2 * hi],
+                                         pair_id0=lo, prefix=pre)
+        assert pes.tobytes() == run["pes"].tobytes()
+        total += c
+    assert np.array_equal(total, run["counts"])
