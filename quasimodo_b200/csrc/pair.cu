@@ -14,9 +14,6 @@ namespace {
 
 constexpr int kMapqTabLen = 1024;
 constexpr int kSubnTabLen = 256;
-constexpr int kSliceBytes = 24 * 1024;       // per-thread DP scratch: eh[] (4 KB) + direction matrix
-constexpr int kEhBytes = 4 * 1024;
-constexpr size_t kOverflowBytes = 256u << 20;
 
 struct PairTables {
     const double *mapq_l;        // [kMapqTabLen]: l < coef_len ? 1 : log(coef_len)/log(l)
@@ -25,12 +22,6 @@ struct PairTables {
     qm_pestat pes[4];
 };
 
-struct PairScratch {
-    uint8_t *slices;             // [threads][kSliceBytes]
-    uint8_t *overflow;           // bump pool for large direction matrices
-    unsigned long long *overflow_used;
-    int *err;
-};
 
 __device__ __forceinline__ uint64_t hash64(uint64_t key)
 {
@@ -216,6 +207,7 @@ __device__ __forceinline__ int infer_bw(int l1, int l2, int score, int a, int q,
 }
 
 #define QM_NEG_INF (-0x40000000)
+#define QM_NEVER   (-0x7ff00000)           // below every value the DP can produce, still safe to subtract from
 
 struct SeqPair {            // query / reference bases of one CIGAR task, reversed on the reverse strand
     const uint8_t *q;
@@ -227,158 +219,213 @@ struct SeqPair {            // query / reference bases of one CIGAR task, revers
     __device__ __forceinline__ int tb(int i) const { return qm_ref_base(*V, rev ? rb + rlen - 1 - i : rb + i); }
 };
 
-// ksw_global2; cigar in forward order M/I/D; returns score, *n_cigar = -1 on overflow
-__device__ int global_align(const qm_opt &o, const SeqPair &S, int w, int2 *eh, uint8_t *dir, int *n_cigar, uint32_t *cigar, int max_cigar)
+// a read whose CIGAR needs the banded global DP (everything else is finished by pair_decide_kernel)
+struct CigTask {
+    int64_t rb, re;
+    int32_t read, w2, truesc, regw;
+};
+
+constexpr int kCigWarps = 4;                  // warps per block of the CIGAR kernel
+constexpr int kDirBytes = 14 * 1024;          // shared-memory direction matrix per warp; larger ones go to global memory
+constexpr size_t kOverflowPerWarp = 1u << 20; // global fallback per warp: covers tlen x ncol up to 1 MiB
+
+// ksw_global2 by one warp: column j lives in lane j%32, slot j/32.  E is column-local; the F
+// recurrence opens from m only, so inside a 32-column slot it is a max-plus prefix scan with a carry between slots.
+// dir: one byte per (row, column - beg(row)), exactly the reference's z[] (bits 0-1 H source, bit 2 E extends,
+// bits 4-5 F extends).  Returns H(tlen-1, qlen-1).
+template <int C>
+__device__ int global_dp_warp(const qm_opt &o, const SeqPair &S, int w, uint8_t *dir, int n_col, int lane)
 {
+    const unsigned FULL = 0xffffffffu;
     const int qlen = S.lq, tlen = S.rlen;
-    const int gapo_d = o.o_del + o.e_del, gapo_i = o.o_ins + o.e_ins;
-    const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
-    eh[0] = make_int2(0, QM_NEG_INF);
-    int col;
-    for (col = 1; col <= qlen && col <= w; ++col) eh[col] = make_int2(-(o.o_ins + o.e_ins * col), QM_NEG_INF);
-    for (; col <= qlen; ++col) eh[col] = make_int2(QM_NEG_INF, QM_NEG_INF);
-    for (int row = 0; row < tlen; ++row) {
-        int f = QM_NEG_INF;
-        uint8_t *drow = dir + (size_t)row * n_col;
-        const int tb = S.tb(row);
-        const int lo = row > w ? row - w : 0;
-        const int hi = row + w + 1 < qlen ? row + w + 1 : qlen;
-        int left = lo == 0 ? -(o.o_del + o.e_del * (row + 1)) : QM_NEG_INF;
-        for (col = lo; col < hi; ++col) {
-            const int2 c = eh[col];
-            int m = c.x, e = c.y, h, t;
-            const int qb = S.qb(col);
-            m += (tb > 3 || qb > 3) ? -1 : (tb == qb ? o.a : -o.b);
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
+    int Hp[C], E[C], qc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int j = c * 32 + lane;
+        Hp[c] = (j < w && j < qlen) ? -(o.o_ins + o.e_ins * (j + 1)) : QM_NEG_INF;      // H(-1, j) = eh[j+1].h
+        E[c] = QM_NEG_INF;
+        qc[c] = j < qlen ? S.qb(j) : 4;
+    }
+    int tb_next = tlen > 0 ? S.tb(0) : 0;
+    for (int i = 0; i < tlen; ++i) {
+        const int tb = tb_next;
+        if (i + 1 < tlen) tb_next = S.tb(i + 1);
+        const int beg = i > w ? i - w : 0;
+        const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+        uint8_t *drow = dir + (size_t)i * n_col - beg;
+        int carry = QM_NEG_INF;                      // F at the first cell of the row
+        int prev31 = i == 0 ? 0 : -(o.o_del + o.e_del * i);     // H(i-1, -1); only read when beg == 0
+        if (beg > 0) prev31 = QM_NEG_INF;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int o31 = __shfl_sync(FULL, Hp[c], 31);        // H(i-1, 32c+31) before this row overwrites it
+            const int lo = c * 32;
+            if (lo + 32 <= beg || lo >= end) { prev31 = o31; continue; }       // warp-uniform
+            const int j = lo + lane;
+            const bool act = j >= beg && j < end;
+            int diag = __shfl_up_sync(FULL, Hp[c], 1);
+            if (lane == 0) diag = prev31;
+            prev31 = o31;
+            const int s = (tb > 3 || qc[c] > 3) ? -1 : (tb == qc[c] ? o.a : -o.b);
+            const int m = diag + s;
+            // F: inclusive max-plus scan of the openings g = m - oe_ins over the active lanes
+            int x = act ? m - oe_ins : QM_NEVER;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, x, d);
+                if (lane >= d) x = max(x, y - d * o.e_ins);
+            }
+            int sprev = __shfl_up_sync(FULL, x, 1);              // scan value of the lane to the left
+            const int la = beg > lo ? beg - lo : 0;              // first active lane of this slot
+            if (lane <= la) sprev = QM_NEVER;
+            const int f = max(carry - (lane - la) * o.e_ins, sprev);
+            // the cell, in the reference's operation order
+            int e = E[c];
             uint8_t d = m >= e ? 0 : 1;
-            h = m >= e ? m : e;
+            int h = m >= e ? m : e;
             d = h >= f ? d : 2;
             h = h >= f ? h : f;
-            t = m - gapo_d;
+            int t = m - oe_del;
             e -= o.e_del;
             if (e > t) d |= 1 << 2; else e = t;
-            eh[col] = make_int2(left, e);
-            left = h;
-            t = m - gapo_i;
-            f -= o.e_ins;
-            if (f > t) d |= 2 << 4; else f = t;
-            drow[col - lo] = d;
+            t = m - oe_ins;
+            const int f2 = f - o.e_ins;
+            if (f2 > t) d |= 2 << 4;
+            if (act) { E[c] = e; Hp[c] = h; drow[j] = d; }
+            // F entering the next slot = f after the last cell of this one
+            carry = __shfl_sync(FULL, f2 > t ? f2 : t, 31);
         }
-        eh[hi] = make_int2(left, QM_NEG_INF);
     }
-    const int score = eh[qlen].x;
-    int n = 0, state = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
-    bool overflow = false;
-#define PUSH(op_, len_) do { \
-        if (n > 0 && (int)(cigar[n - 1] & 0xf) == (op_)) cigar[n - 1] += (uint32_t)(len_) << 4; \
-        else if (n < max_cigar) cigar[n++] = (uint32_t)(len_) << 4 | (op_); \
-        else overflow = true; } while (0)
-    while (i >= 0 && k >= 0) {
-        const int lo = i > w ? i - w : 0;
-        state = dir[(size_t)i * n_col + (k - lo)] >> (state << 1) & 3;
-        if (state == 0)      { PUSH(0, 1); --i; --k; }
-        else if (state == 1) { PUSH(2, 1); --i; }
-        else                 { PUSH(1, 1); --k; }
-    }
-    if (i >= 0) PUSH(2, i + 1);
-    if (k >= 0) PUSH(1, k + 1);
-#undef PUSH
-    for (i = 0; i < n >> 1; ++i) { const uint32_t t = cigar[i]; cigar[i] = cigar[n - 1 - i]; cigar[n - 1 - i] = t; }
-    *n_cigar = overflow ? -1 : n;
+    const int jl = qlen - 1;
+    int score = QM_NEG_INF;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        if ((jl >> 5) == c) score = __shfl_sync(FULL, Hp[c], jl & 31);
     return score;
 }
 
-// bwa_gen_cigar2: returns score; NM via *nm
-__device__ int gen_cigar(const IndexView &V, const qm_opt &o, int w_, int l_query, const uint8_t *query, int64_t rb, int64_t re,
-                         uint8_t *slice, const PairScratch &PS, int *n_cigar, uint32_t *cigar, int *nm)
+// bwa_gen_cigar2's DP branch + traceback + NM for one task; all lanes return the same values
+__device__ int gen_cigar_warp(const IndexView &V, const qm_opt &o, int w_, int l_query, const uint8_t *query, int64_t rb, int64_t re,
+                              uint8_t *dir_smem, uint8_t *dir_glob, int lane, int *n_cigar_out, uint32_t *cigar /* shared, per warp */,
+                              int *nm_out, int *err)
 {
-    const int64_t l_pac = V.l_pac;
+    const unsigned FULL = 0xffffffffu;
     const int rlen = (int)(re - rb);
-    int score = 0;
-    *n_cigar = 0; *nm = -1;
-    if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return 0;
     SeqPair S;
-    S.q = query; S.lq = l_query; S.rlen = rlen; S.rb = rb; S.rev = rb >= l_pac; S.V = &V;
-    if (l_query == rlen && w_ == 0) {
-        cigar[0] = (uint32_t)l_query << 4; *n_cigar = 1;
-        for (int i = 0; i < l_query; ++i) { const int r = S.tb(i), q = S.qb(i); score += (r > 3 || q > 3) ? -1 : (r == q ? o.a : -o.b); }
-    } else {
-        int max_ins = (int)((double)(((l_query + 1) >> 1) * o.a - o.o_ins) / o.e_ins + 1.);
-        int max_del = (int)((double)(((l_query + 1) >> 1) * o.a - o.o_del) / o.e_del + 1.);
-        int max_gap = max_ins > max_del ? max_ins : max_del;
-        if (max_gap < 1) max_gap = 1;
-        int w = (max_gap + abs(rlen - l_query) + 1) >> 1;
-        if (w > w_) w = w_;
-        const int min_w = abs(rlen - l_query) + 3;
-        if (w < min_w) w = min_w;
-        const int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
-        const size_t need = (size_t)n_col * rlen;
-        uint8_t *dir = slice + kEhBytes;
-        if ((size_t)(l_query + 1) * sizeof(int2) > (size_t)kEhBytes) { atomicExch(PS.err, 2); *n_cigar = -1; return 0; }
-        if (need > (size_t)(kSliceBytes - kEhBytes)) {
-            const unsigned long long at = atomicAdd(PS.overflow_used, (unsigned long long)((need + 15) & ~(size_t)15));
-            if (at + need > kOverflowBytes) { atomicExch(PS.err, 3); *n_cigar = -1; return 0; }
-            dir = PS.overflow + at;
-        }
-        score = global_align(o, S, w, (int2 *)slice, dir, n_cigar, cigar, QM_MAX_CIGAR - 2);
+    S.q = query; S.lq = l_query; S.rlen = rlen; S.rb = rb; S.rev = rb >= V.l_pac; S.V = &V;
+    int max_ins = (int)((double)(((l_query + 1) >> 1) * o.a - o.o_ins) / o.e_ins + 1.);
+    int max_del = (int)((double)(((l_query + 1) >> 1) * o.a - o.o_del) / o.e_del + 1.);
+    int max_gap = max_ins > max_del ? max_ins : max_del;
+    if (max_gap < 1) max_gap = 1;
+    int w = (max_gap + abs(rlen - l_query) + 1) >> 1;
+    if (w > w_) w = w_;
+    const int min_w = abs(rlen - l_query) + 3;
+    if (w < min_w) w = min_w;
+    const int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
+    const size_t need = (size_t)n_col * rlen;
+    uint8_t *dir = dir_smem;
+    if (need > (size_t)kDirBytes) {
+        if (need > kOverflowPerWarp) { if (lane == 0) atomicExch(err, 3); *n_cigar_out = -1; *nm_out = -1; return 0; }
+        dir = dir_glob;
     }
-    if (*n_cigar > 0) {
+    int score;
+    if (l_query <= 160) score = global_dp_warp<5>(o, S, w, dir, n_col, lane);
+    else if (l_query <= 256) score = global_dp_warp<8>(o, S, w, dir, n_col, lane);
+    else if (l_query <= 512) score = global_dp_warp<16>(o, S, w, dir, n_col, lane);
+    else { if (lane == 0) atomicExch(err, 2); *n_cigar_out = -1; *nm_out = -1; return 0; }
+    __syncwarp();
+    // traceback (lane 0), CIGAR built back to front then reversed
+    int n = 0;
+    if (lane == 0) {
+        const int max_cigar = QM_MAX_CIGAR - 2;
+        int state = 0, i = rlen - 1, k = (i + w + 1 < l_query ? i + w + 1 : l_query) - 1;
+        bool overflow = false;
+        uint32_t cur = 0;                            // run being built: len << 4 | op ; 0 = none
+        while (i >= 0 && k >= 0) {
+            const int lo = i > w ? i - w : 0;
+            state = dir[(size_t)i * n_col + (k - lo)] >> (state << 1) & 3;
+            const uint32_t op = state == 0 ? 0u : (state == 1 ? 2u : 1u);
+            if (cur && (cur & 0xf) == op) cur += 1u << 4;
+            else {
+                if (cur) { if (n < max_cigar) cigar[n++] = cur; else overflow = true; }
+                cur = 1u << 4 | op;
+            }
+            if (state == 0) { --i; --k; } else if (state == 1) --i; else --k;
+        }
+        auto push = [&](uint32_t op, int len) {
+            if (cur && (cur & 0xf) == op) cur += (uint32_t)len << 4;
+            else {
+                if (cur) { if (n < max_cigar) cigar[n++] = cur; else overflow = true; }
+                cur = (uint32_t)len << 4 | op;
+            }
+        };
+        if (i >= 0) push(2, i + 1);
+        if (k >= 0) push(1, k + 1);
+        if (cur) { if (n < max_cigar) cigar[n++] = cur; else overflow = true; }
+        for (int a = 0; a < n >> 1; ++a) { const uint32_t t = cigar[a]; cigar[a] = cigar[n - 1 - a]; cigar[n - 1 - a] = t; }
+        if (overflow) n = -1;
+    }
+    n = __shfl_sync(FULL, n, 0);
+    __syncwarp();
+    *n_cigar_out = n;
+    int nm = -1;
+    if (n > 0) {
         int x = 0, y = 0, n_mm = 0, n_gap = 0;
-        for (int k = 0; k < *n_cigar; ++k) {
+        for (int k = 0; k < n; ++k) {
             const int op = cigar[k] & 0xf, len = (int)(cigar[k] >> 4);
-            if (op == 0) { for (int i = 0; i < len; ++i) if (S.qb(x + i) != S.tb(y + i)) ++n_mm; x += len; y += len; }
-            else if (op == 2) { if (k > 0 && k < *n_cigar - 1) n_gap += len; y += len; }
+            if (op == 0) { for (int a = lane; a < len; a += 32) if (S.qb(x + a) != S.tb(y + a)) ++n_mm; x += len; y += len; }
+            else if (op == 2) { if (k > 0 && k < n - 1) n_gap += len; y += len; }
             else if (op == 1) { x += len; n_gap += len; }
         }
-        *nm = n_mm + n_gap;
+        nm = __reduce_add_sync(FULL, n_mm) + n_gap;
     }
+    *nm_out = nm;
     return score;
 }
 
-// mem_reg2aln
-__device__ void reg_to_aln(const IndexView &V, const qm_opt &o, const PairTables &T, int l_query, const uint8_t *query,
-                           const qm_reg *ar, uint8_t *slice, const PairScratch &PS, qm_aln *a)
+// mem_reg2aln, first half: MAPQ / flags / band inference; reads on the no-DP path (equal lengths, w2 == 0) are
+// completed here, the others become CigTasks.  Returns true when a task is needed.
+__device__ bool reg_to_aln_prepare(const IndexView &V, const qm_opt &o, const PairTables &T, int l_query, const uint8_t *query,
+                                   const qm_reg *ar, qm_aln *a, int *w2_out)
 {
     qm_aln r = {};
-    if (ar == nullptr || ar->rb < 0 || ar->re < 0) { r.rid = -1; r.pos = -1; r.flag |= 0x4; *a = r; return; }
+    if (ar == nullptr || ar->rb < 0 || ar->re < 0) { r.rid = -1; r.pos = -1; r.flag |= 0x4; *a = r; return false; }
     const int qb = ar->qb, qe = ar->qe;
     const int64_t rb = ar->rb, re = ar->re;
-    int nm = -1, score = 0, last_sc = -(1 << 30), n_cigar = 0;
-    uint32_t cig[QM_MAX_CIGAR];
     r.mapq = ar->secondary < 0 ? (uint8_t)approx_mapq(o, T, *ar) : 0;
     if (ar->secondary >= 0) r.flag |= 0x100;
     int tmp = infer_bw(qe - qb, (int)(re - rb), ar->truesc, o.a, o.o_del, o.e_del);
     int w2 = infer_bw(qe - qb, (int)(re - rb), ar->truesc, o.a, o.o_ins, o.e_ins);
     if (tmp > w2) w2 = tmp;
     if (w2 > o.w) w2 = w2 < ar->w ? w2 : ar->w;
-    int i = 0;
-    do {
-        if (w2 > o.w << 2) w2 = o.w << 2;
-        score = gen_cigar(V, o, w2, qe - qb, query + qb, rb, re, slice, PS, &n_cigar, cig, &nm);
-        if (score == last_sc || w2 == o.w << 2) break;
-        last_sc = score;
-        w2 <<= 1;
-    } while (++i < 3 && score < ar->truesc - o.a);
-    r.nm = nm;
-    const bool is_rev = (rb < V.l_pac ? rb : re - 1) >= V.l_pac;
-    int64_t pos = rb < V.l_pac ? rb : 2 * V.l_pac - 1 - (re - 1);
-    if (n_cigar < 0) { r.rid = -1; r.pos = -1; r.flag |= 0x4; r.n_cigar = 255; *a = r; return; }
-    int c0 = 0;
-    if (n_cigar > 0) {
-        if ((cig[0] & 0xf) == 2) { pos += cig[0] >> 4; c0 = 1; --n_cigar; }
-        else if ((cig[c0 + n_cigar - 1] & 0xf) == 2) --n_cigar;
-    }
-    int m = 0;
-    const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
-    if (clip5) r.cigar[m++] = (uint32_t)clip5 << 4 | 4;
-    for (i = 0; i < n_cigar; ++i) r.cigar[m++] = cig[c0 + i];
-    if (clip3) r.cigar[m++] = (uint32_t)clip3 << 4 | 4;
-    r.n_cigar = (uint8_t)m;
-    r.rid = qm_pos2rid(V, pos);
-    r.pos = (int32_t)(pos - V.off[r.rid]);
-    if (is_rev) r.flag |= 0x10;
     r.score = ar->score; r.sub = ar->sub > ar->csub ? ar->sub : ar->csub;
     r.qb = qb; r.qe = qe;
+    const bool is_rev = rb >= V.l_pac;            // a region never straddles l_pac
+    if (is_rev) r.flag |= 0x10;
+    if (qe - qb == (int)(re - rb) && w2 == 0 && !(rb < V.l_pac && re > V.l_pac)) {
+        // bwa_gen_cigar2's shortcut: <len>M, NM = mismatches
+        SeqPair S;
+        S.q = query + qb; S.lq = qe - qb; S.rlen = qe - qb; S.rb = rb; S.rev = is_rev; S.V = &V;
+        int n_mm = 0;
+        for (int i = 0; i < S.lq; ++i) n_mm += S.qb(i) != S.tb(i);
+        r.nm = n_mm;
+        const int64_t pos = rb < V.l_pac ? rb : 2 * V.l_pac - 1 - (re - 1);
+        int m = 0;
+        const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+        if (clip5) r.cigar[m++] = (uint32_t)clip5 << 4 | 4;
+        r.cigar[m++] = (uint32_t)(qe - qb) << 4;
+        if (clip3) r.cigar[m++] = (uint32_t)clip3 << 4 | 4;
+        r.n_cigar = (uint8_t)m;
+        r.rid = qm_pos2rid(V, pos);
+        r.pos = (int32_t)(pos - V.off[r.rid]);
+        *a = r;
+        return false;
+    }
+    r.rid = ar->rid; r.pos = -1; r.n_cigar = 0;
     *a = r;
+    *w2_out = w2;
+    return true;
 }
 
 __device__ __forceinline__ int cigar_rlen(const qm_aln &a)
@@ -416,81 +463,162 @@ __device__ void finish_pair(qm_aln h[2], int extra_flag)
     }
 }
 
+// ---- kernel 1 (one thread per pair): primary marking, pairing, MAPQ, no-DP CIGARs, task list ----
+// The proper-pair bit (2) and "pairing decided" (4) travel to kernel 3 in the not yet final tlen field of mate 1.
 __global__ void __launch_bounds__(128)
-pair_kernel(IndexView V, qm_opt o, PairTables T, PairScratch PS, const uint8_t *__restrict__ codes, int stride,
-            const int32_t *__restrict__ lens, int64_t n_pairs, int64_t pair_id0, qm_reg *__restrict__ regs,
-            int32_t *__restrict__ n_regs, qm_aln *__restrict__ alns)
+pair_decide_kernel(IndexView V, qm_opt o, PairTables T, const uint8_t *__restrict__ codes, int stride,
+                   const int32_t *__restrict__ lens, int64_t n_pairs, int64_t pair_id0, qm_reg *__restrict__ regs,
+                   int32_t *__restrict__ n_regs, qm_aln *__restrict__ alns, CigTask *__restrict__ tasks, int *__restrict__ n_tasks)
 {
-    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    uint8_t *slice = PS.slices + tid * kSliceBytes;
-    for (int64_t pi = tid; pi < n_pairs; pi += nthreads) {
-        qm_reg *a[2] = { regs + (2 * pi) * QM_MAX_REGS, regs + (2 * pi + 1) * QM_MAX_REGS };
-        const int n[2] = { n_regs[2 * pi], n_regs[2 * pi + 1] };
-        int n_pri[2], z[2] = {0, 0};
-        const uint8_t *seq[2] = { codes + (2 * pi) * stride, codes + (2 * pi + 1) * stride };
-        const int l_seq[2] = { lens[2 * pi], lens[2 * pi + 1] };
-        const uint64_t id = (uint64_t)(pair_id0 + pi);
-        qm_aln h[2];
-        int extra_flag = 0, o_sc = 0, subo = 0, n_sub = 0;
-        bool paired_done = false;
-        mark_primary(o, n[0], a[0], id << 1 | 0);
-        mark_primary(o, n[1], a[1], id << 1 | 1);
-        n_pri[0] = n[0]; n_pri[1] = n[1];
-        if (n_pri[0] && n_pri[1] && (o_sc = pair_up(V, o, T, a, n_pri, id, &subo, &n_sub, z)) > 0) {
-            bool is_multi[2];
-            for (int i = 0; i < 2; ++i) {
-                int j;
-                for (j = 1; j < n_pri[i]; ++j) if (a[i][j].secondary < 0 && a[i][j].score >= o.T) break;
-                is_multi[i] = j < n_pri[i];
-            }
-            if (!(is_multi[0] || is_multi[1])) {
-                int q_se[2];
-                const int score_un = a[0][0].score + a[1][0].score - o.pen_unpaired;
-                if (score_un > subo) subo = score_un;
-                int q_pe = raw_mapq(o_sc - subo, o.a);
-                if (n_sub > 0) q_pe -= T.subn[n_sub < kSubnTabLen ? n_sub : kSubnTabLen - 1];
-                if (q_pe < 0) q_pe = 0;
-                if (q_pe > 60) q_pe = 60;
-                if (o_sc > score_un) {
-                    qm_reg *c[2] = { &a[0][z[0]], &a[1][z[1]] };
-                    for (int i = 0; i < 2; ++i) {
-                        if (c[i]->secondary >= 0) { c[i]->sub = a[i][c[i]->secondary].score; c[i]->secondary = -2; }
-                        q_se[i] = approx_mapq(o, T, *c[i]);
-                    }
-                    for (int i = 0; i < 2; ++i) {
-                        q_se[i] = q_se[i] > q_pe ? q_se[i] : q_pe < q_se[i] + 40 ? q_pe : q_se[i] + 40;
-                        const int cap = raw_mapq(c[i]->score - c[i]->csub, o.a);
-                        if (q_se[i] > cap) q_se[i] = cap;
-                    }
-                    extra_flag |= 2;
-                } else {
-                    z[0] = z[1] = 0;
-                    q_se[0] = approx_mapq(o, T, a[0][0]);
-                    q_se[1] = approx_mapq(o, T, a[1][0]);
+    const int64_t pi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (pi >= n_pairs) return;
+    qm_reg *a[2] = { regs + (2 * pi) * QM_MAX_REGS, regs + (2 * pi + 1) * QM_MAX_REGS };
+    const int n[2] = { n_regs[2 * pi], n_regs[2 * pi + 1] };
+    int n_pri[2], z[2] = {0, 0};
+    const uint8_t *seq[2] = { codes + (2 * pi) * stride, codes + (2 * pi + 1) * stride };
+    const int l_seq[2] = { lens[2 * pi], lens[2 * pi + 1] };
+    const uint64_t id = (uint64_t)(pair_id0 + pi);
+    int extra_flag = 0, o_sc = 0, subo = 0, n_sub = 0;
+    bool paired_done = false;
+    const qm_reg *chosen[2] = { nullptr, nullptr };
+    int q_se[2] = {0, 0};
+    mark_primary(o, n[0], a[0], id << 1 | 0);
+    mark_primary(o, n[1], a[1], id << 1 | 1);
+    n_pri[0] = n[0]; n_pri[1] = n[1];
+    if (n_pri[0] && n_pri[1] && (o_sc = pair_up(V, o, T, a, n_pri, id, &subo, &n_sub, z)) > 0) {
+        bool is_multi[2];
+        for (int i = 0; i < 2; ++i) {
+            int j;
+            for (j = 1; j < n_pri[i]; ++j) if (a[i][j].secondary < 0 && a[i][j].score >= o.T) break;
+            is_multi[i] = j < n_pri[i];
+        }
+        if (!(is_multi[0] || is_multi[1])) {
+            const int score_un = a[0][0].score + a[1][0].score - o.pen_unpaired;
+            if (score_un > subo) subo = score_un;
+            int q_pe = raw_mapq(o_sc - subo, o.a);
+            if (n_sub > 0) q_pe -= T.subn[n_sub < kSubnTabLen ? n_sub : kSubnTabLen - 1];
+            if (q_pe < 0) q_pe = 0;
+            if (q_pe > 60) q_pe = 60;
+            if (o_sc > score_un) {
+                qm_reg *c[2] = { &a[0][z[0]], &a[1][z[1]] };
+                for (int i = 0; i < 2; ++i) {
+                    if (c[i]->secondary >= 0) { c[i]->sub = a[i][c[i]->secondary].score; c[i]->secondary = -2; }
+                    q_se[i] = approx_mapq(o, T, *c[i]);
                 }
                 for (int i = 0; i < 2; ++i) {
-                    reg_to_aln(V, o, T, l_seq[i], seq[i], &a[i][z[i]], slice, PS, &h[i]);
-                    h[i].mapq = (uint8_t)q_se[i];
-                    h[i].flag &= ~0x100;
+                    q_se[i] = q_se[i] > q_pe ? q_se[i] : q_pe < q_se[i] + 40 ? q_pe : q_se[i] + 40;
+                    const int cap = raw_mapq(c[i]->score - c[i]->csub, o.a);
+                    if (q_se[i] > cap) q_se[i] = cap;
                 }
-                paired_done = true;
+                extra_flag |= 2;
+            } else {
+                z[0] = z[1] = 0;
+                q_se[0] = approx_mapq(o, T, a[0][0]);
+                q_se[1] = approx_mapq(o, T, a[1][0]);
             }
+            chosen[0] = &a[0][z[0]]; chosen[1] = &a[1][z[1]];
+            paired_done = true;
         }
-        if (!paired_done) {
-            for (int i = 0; i < 2; ++i) {
-                if (n[i] && a[i][0].score >= o.T) reg_to_aln(V, o, T, l_seq[i], seq[i], &a[i][0], slice, PS, &h[i]);
-                else reg_to_aln(V, o, T, l_seq[i], seq[i], nullptr, slice, PS, &h[i]);
-            }
-            if (h[0].rid == h[1].rid && h[0].rid >= 0) {
-                int64_t dist;
-                const int d = infer_dir(V.l_pac, a[0][0].rb, a[1][0].rb, &dist);
-                if (!T.pes[d].failed && dist >= T.pes[d].low && dist <= T.pes[d].high) extra_flag |= 2;
-            }
-        }
-        finish_pair(h, extra_flag);
-        alns[2 * pi] = h[0]; alns[2 * pi + 1] = h[1];
     }
+    if (!paired_done) {
+        for (int i = 0; i < 2; ++i) chosen[i] = (n[i] && a[i][0].score >= o.T) ? &a[i][0] : nullptr;
+        // (the proper-pair test of this branch needs the final records: kernel 3)
+    }
+    for (int i = 0; i < 2; ++i) {
+        qm_aln h;
+        int w2 = 0;
+        const bool need = reg_to_aln_prepare(V, o, T, l_seq[i], seq[i], chosen[i], &h, &w2);
+        if (paired_done) { h.mapq = (uint8_t)q_se[i]; h.flag &= ~0x100; }
+        if (i == 0) h.tlen = extra_flag | (paired_done ? 4 : 0);
+        alns[2 * pi + i] = h;
+        if (need) {
+            CigTask t;
+            t.rb = chosen[i]->rb; t.re = chosen[i]->re; t.read = (int32_t)(2 * pi + i); t.w2 = w2;
+            t.truesc = chosen[i]->truesc; t.regw = chosen[i]->w;
+            tasks[atomicAdd(n_tasks, 1)] = t;
+        }
+    }
+}
+
+// ---- kernel 2 (one warp per task): banded global DP with traceback, bwa's band-doubling retry, NM, clips ----
+__global__ void __launch_bounds__(kCigWarps * 32)
+cigar_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+             const CigTask *__restrict__ tasks, const int *__restrict__ n_tasks, int *__restrict__ cursor,
+             uint8_t *__restrict__ overflow, qm_aln *__restrict__ alns, int *__restrict__ err)
+{
+    extern __shared__ uint8_t smem[];
+    __shared__ uint32_t s_cig[kCigWarps][QM_MAX_CIGAR];
+    const int lane = qm_lane(), wib = threadIdx.x >> 5;
+    uint8_t *dir_smem = smem + (size_t)wib * kDirBytes;
+    uint8_t *dir_glob = overflow + ((size_t)blockIdx.x * kCigWarps + wib) * kOverflowPerWarp;
+    const int n = *n_tasks;
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = atomicAdd(cursor, 1);
+        ti = __shfl_sync(0xffffffffu, ti, 0);
+        if (ti >= n) break;
+        const CigTask t = tasks[ti];
+        qm_aln *rec = alns + t.read;
+        const int l_query = lens[t.read];
+        const int qb = rec->qb, qe = rec->qe;
+        const uint8_t *query = codes + (int64_t)t.read * stride + qb;
+        int w2 = t.w2, nm = -1, score = 0, last_sc = -(1 << 30), n_cigar = 0;
+        int it = 0;
+        do {
+            if (w2 > o.w << 2) w2 = o.w << 2;
+            if (t.rb < V.l_pac && t.re > V.l_pac) { n_cigar = 0; nm = -1; score = 0; }
+            else score = gen_cigar_warp(V, o, w2, qe - qb, query, t.rb, t.re, dir_smem, dir_glob, lane, &n_cigar, s_cig[wib], &nm, err);
+            if (score == last_sc || w2 == o.w << 2) break;
+            last_sc = score;
+            w2 <<= 1;
+        } while (++it < 3 && score < t.truesc - o.a);
+        if (lane == 0) {
+            const uint32_t *cig = s_cig[wib];
+            if (n_cigar < 0) {       // CIGAR overflow: the read is reported unmapped (mem_reg2aln's fields stay unset)
+                rec->rid = -1; rec->pos = -1; rec->flag |= 0x4; rec->flag &= ~0x10; rec->n_cigar = 255; rec->nm = nm;
+                rec->score = 0; rec->sub = 0; rec->qb = 0; rec->qe = 0;
+            }
+            else {
+                const bool is_rev = t.rb >= V.l_pac;
+                int64_t pos = t.rb < V.l_pac ? t.rb : 2 * V.l_pac - 1 - (t.re - 1);
+                int c0 = 0;
+                if (n_cigar > 0) {
+                    if ((cig[0] & 0xf) == 2) { pos += cig[0] >> 4; c0 = 1; --n_cigar; }
+                    else if ((cig[n_cigar - 1] & 0xf) == 2) --n_cigar;
+                }
+                int m = 0;
+                const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+                if (clip5) rec->cigar[m++] = (uint32_t)clip5 << 4 | 4;
+                for (int k = 0; k < n_cigar; ++k) rec->cigar[m++] = cig[c0 + k];
+                if (clip3) rec->cigar[m++] = (uint32_t)clip3 << 4 | 4;
+                rec->n_cigar = (uint8_t)m;
+                const int rid = qm_pos2rid(V, pos);
+                rec->rid = rid;
+                rec->pos = (int32_t)(pos - V.off[rid]);
+                rec->nm = nm;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- kernel 3 (one thread per pair): proper-pair test of the unpaired branch, SAM flags, mate fields, TLEN ----
+__global__ void __launch_bounds__(128)
+pair_finish_kernel(IndexView V, PairTables T, int64_t n_pairs, const qm_reg *__restrict__ regs, qm_aln *__restrict__ alns)
+{
+    const int64_t pi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (pi >= n_pairs) return;
+    qm_aln h[2] = { alns[2 * pi], alns[2 * pi + 1] };
+    int extra_flag = h[0].tlen & 2;
+    const bool paired_done = (h[0].tlen & 4) != 0;
+    h[0].tlen = 0;
+    if (!paired_done && h[0].rid == h[1].rid && h[0].rid >= 0) {
+        int64_t dist;
+        const int d = infer_dir(V.l_pac, regs[(2 * pi) * QM_MAX_REGS].rb, regs[(2 * pi + 1) * QM_MAX_REGS].rb, &dist);
+        if (!T.pes[d].failed && dist >= T.pes[d].low && dist <= T.pes[d].high) extra_flag |= 2;
+    }
+    finish_pair(h, extra_flag);
+    alns[2 * pi] = h[0]; alns[2 * pi + 1] = h[1];
 }
 
 }  // namespace
@@ -585,13 +713,14 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
             term[term_off[d] + (size_t)(dist - pes[d].low)] = .721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt->a;
         }
     }
-    const int threads_total = ctx->sm_count * 256;
+    // scratch 5: tables | counters | task list | per-warp global fallback for oversized direction matrices
+    const int cig_blocks = ctx->sm_count * 3;                      // persistent: 3 blocks x 4 warps x 14 KB per SM
     const size_t o_tab = 0, o_subn = o_tab + kMapqTabLen * 8, o_term = o_subn + kSubnTabLen * 4;
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
-    const size_t o_slices = o_misc + 256;
-    const size_t o_over = o_slices + (size_t)threads_total * kSliceBytes;
+    const size_t o_tasks = o_misc + 256;
+    const size_t o_over = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
     void *p = nullptr;
-    int rc = qm_scratch_reserve(ctx, 5, o_over + kOverflowBytes, &p);
+    int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
     char *b = (char *)p;
     QM_CUDA(ctx, cudaMemcpyAsync(b + o_tab, tab.data(), kMapqTabLen * 8, cudaMemcpyHostToDevice, st));
@@ -602,17 +731,24 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     PairTables T;
     T.mapq_l = (const double *)(b + o_tab); T.subn = (const int *)(b + o_subn);
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
-    PairScratch PS;
-    PS.slices = (uint8_t *)(b + o_slices); PS.overflow = (uint8_t *)(b + o_over);
-    PS.overflow_used = (unsigned long long *)(b + o_misc); PS.err = (int *)(b + o_misc + 16);
-    int64_t blocks = (n_pairs + 127) / 128;
-    if (blocks > threads_total / 128) blocks = threads_total / 128;
+    int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
+    CigTask *tasks = (CigTask *)(b + o_tasks);
+    const unsigned grid = (unsigned)((n_pairs + 127) / 128);
+    static bool attr_set = false;
+    if (!attr_set) {
+        QM_CUDA(ctx, cudaFuncSetAttribute(cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCigWarps * kDirBytes));
+        attr_set = true;
+    }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
-    pair_kernel<<<(unsigned)blocks, 128, 0, st>>>(idx->v, *opt, T, PS, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns);
-    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 1);
+    pair_decide_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, T, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns,
+                                             tasks, n_tasks);
+    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, n_tasks,
+                                                                          cursor, (uint8_t *)(b + o_over), d_alns, err);
+    pair_finish_kernel<<<grid, 128, 0, st>>>(idx->v, T, n_pairs, d_regs, d_alns);
+    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 3);
     QM_CUDA(ctx, cudaGetLastError());
     int h_err = 0;
-    QM_CUDA(ctx, cudaMemcpyAsync(&h_err, PS.err, 4, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st));
     QM_CUDA(ctx, cudaStreamSynchronize(st));
     if (h_err) return qm_fail(ctx, QM_ELIMIT, "qm_pair_finish: traceback scratch exhausted (code %d)", h_err);
     return QM_OK;
