@@ -466,7 +466,7 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
     }
 }
 
-constexpr int64_t kSeBatch = 1 << 19;       // reads per internal round-trip (bounds scratch memory)
+constexpr int64_t kSeBatch = 1 << 20;       // reads per internal round-trip (bounds scratch memory)
 
 struct SeScratch {
     qm_seed *seeds; int32_t *n_seeds; uint16_t *plan; uint8_t *n_plan; ReadState *st;

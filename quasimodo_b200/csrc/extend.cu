@@ -15,6 +15,7 @@
 namespace {
 
 constexpr int kNumClasses = kExtClasses;
+constexpr int kThreadPerTaskMin = 16384;      // tasks in a class below which the warp-per-task kernel is used
 
 // where a task's bases come from: explicit byte strings (public C-ABI tasks) or the read batch /
 // reference index in place (pipeline tasks; nothing is materialised in HBM)
@@ -269,11 +270,23 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
                           const int *h_counts, qm_ext_result *d_out, cudaStream_t st)
 {
-    launch_class<1>(ctx, 0, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    launch_class<2>(ctx, 1, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    launch_class<4>(ctx, 2, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    launch_class<8>(ctx, 3, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    launch_class<16>(ctx, 4, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    // A class with many tasks goes to the thread-per-task kernel (extend2.cu: high throughput, but one task is a
+    // long serial chain, ~0.3 ms); a class with few tasks (the tail rounds of mem_chain2aln, where only reads with
+    // many chains are still active) goes to the warp-per-task kernel below (low latency).  Class 5 (qlen > 256)
+    // always does.  Without host-side counts (public qm_extend_batch) classes 0..4 use the thread-per-task kernel.
+    int big[kExtClasses] = {1, 1, 1, 1, 1, 0};
+    if (h_counts)
+        for (int c = 0; c < 5; ++c) big[c] = h_counts[c] >= kThreadPerTaskMin;
+    int hc2[kExtClasses];
+    for (int c = 0; c < kExtClasses; ++c) hc2[c] = big[c] ? (h_counts ? h_counts[c] : 1) : 0;
+    int rc = qm_ext2_launch_classes(ctx, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, hc2, h_counts != nullptr, d_out, st);
+    if (rc) return rc;
+    if (!big[0]) launch_class<2>(ctx, 0, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    if (!big[1]) launch_class<3>(ctx, 1, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    if (!big[2]) launch_class<4>(ctx, 2, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    if (!big[3]) launch_class<5>(ctx, 3, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    if (!big[4]) launch_class<9>(ctx, 4, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    launch_class<16>(ctx, 5, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }
@@ -292,7 +305,7 @@ int qm_extend_launch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const
     if (rc) return rc;
     ExtTaskI *itasks = (ExtTaskI *)p;
     int *lists = (int *)((char *)p + task_bytes);
-    int *ctrs = (int *)((char *)p + task_bytes + list_bytes);     // [0..4] counts, [8..12] cursors, [16] err
+    int *ctrs = (int *)((char *)p + task_bytes + list_bytes);     // [0..5] counts, [8..13] cursors, [16] err
     QM_CUDA(ctx, cudaMemsetAsync(ctrs, 0, 64 * sizeof(int), st));
     const int tpb = 256;
     ext_classify_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_tasks, d_seq, n, itasks, lists, ctrs, d_out, ctrs + 16);

@@ -209,6 +209,15 @@ __device__ __forceinline__ int infer_bw(int l1, int l2, int score, int a, int q,
 #define QM_NEG_INF (-0x40000000)
 #define QM_NEVER   (-0x7ff00000)           // below every value the DP can produce, still safe to subtract from
 
+struct Lut { unsigned lo, hi; };        // 8 score bytes: entries 0..3 = query A,C,G,T, entry 4 = query N
+// PTX prmt (default mode): selector nibble bit 3 replicates the sign of the selected byte -> sign-extended score
+__device__ __forceinline__ int lut_score(const Lut &L, unsigned sel)
+{
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(L.lo), "r"(L.hi), "r"(sel));
+    return r;
+}
+
 struct SeqPair {            // query / reference bases of one CIGAR task, reversed on the reverse strand
     const uint8_t *q;
     int lq, rlen;
@@ -540,24 +549,142 @@ pair_decide_kernel(IndexView V, qm_opt o, PairTables T, const uint8_t *__restric
     }
 }
 
+// ---- kernel 2a (one THREAD per task): score-only banded global DP for equal-length tasks ----
+// If ksw_global2's optimum equals the score of the ungapped alignment, its traceback is all-M (every cell on the
+// main diagonal then has m == H >= e, f, and ties choose M), so CIGAR = <len>M and NM = mismatches: no direction
+// matrix, no traceback.  This kernel runs the reference's row/column loop verbatim (no direction bits) with the
+// band of eh[] in a circular shared-memory buffer, one task per thread, and finishes every task whose first try
+// is final (score >= truesc - a, bwa's retry rule) and gap-free.  Everything else (length difference, wide band,
+// retry, real gaps) is left to the warp-per-task kernel with traceback.
+constexpr int kCsT = 128;              // threads per block
+
+template <int B>                       // circular slots per thread (power of two), needs 2w + 2 <= B
+__global__ void __launch_bounds__(kCsT)
+cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                 const CigTask *__restrict__ tasks, const int *__restrict__ n_tasks, int wmin, int wmax, int wtop,
+                 qm_aln *__restrict__ alns, int *__restrict__ left, int *__restrict__ n_left)
+{
+    extern __shared__ int cs_smem[];
+    int *HS = cs_smem + threadIdx.x;                           // HS[slot * kCsT]            eh[].h
+    int *ES = cs_smem + B * kCsT + threadIdx.x;                // ES[slot * kCsT]            eh[].e
+    unsigned short *SS = (unsigned short *)(cs_smem + 2 * B * kCsT) + threadIdx.x;   // PRMT selector of q[j]
+    const int n = *n_tasks;
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
+    for (int ti = blockIdx.x * kCsT + threadIdx.x; ti < n; ti += gridDim.x * kCsT) {
+        const CigTask t = tasks[ti];
+        qm_aln *rec = alns + t.read;
+        const int l_query = lens[t.read];
+        const int qb = rec->qb, qe = rec->qe;
+        const int lq = qe - qb, rlen = (int)(t.re - t.rb);
+        int w2 = t.w2;
+        if (w2 > o.w << 2) w2 = o.w << 2;
+        // band exactly as bwa_gen_cigar2 derives it
+        int max_ins = (int)((double)(((lq + 1) >> 1) * o.a - o.o_ins) / o.e_ins + 1.);
+        int max_del = (int)((double)(((lq + 1) >> 1) * o.a - o.o_del) / o.e_del + 1.);
+        int max_gap = max_ins > max_del ? max_ins : max_del;
+        if (max_gap < 1) max_gap = 1;
+        int w = (max_gap + abs(rlen - lq) + 1) >> 1;
+        if (w > w2) w = w2;
+        const int min_w = abs(rlen - lq) + 3;
+        if (w < min_w) w = min_w;
+        const bool mine = lq == rlen && w >= wmin && w <= wmax && !(t.rb < V.l_pac && t.re > V.l_pac);
+        if (!mine) {
+            if (wmin == 0 && !(lq == rlen && w <= wtop && !(t.rb < V.l_pac && t.re > V.l_pac)))
+                left[atomicAdd(n_left, 1)] = ti;          // the first (narrowest) instance hands over what no instance takes
+            continue;
+        }
+        SeqPair S;
+        S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
+        // first row of eh[] and the selectors of the columns row 0 can reach
+        HS[0] = 0; ES[0] = QM_NEG_INF;
+        for (int j = 1; j <= lq && j <= w; ++j) { HS[(j & (B - 1)) * kCsT] = -(o.o_ins + o.e_ins * j); ES[(j & (B - 1)) * kCsT] = QM_NEG_INF; }
+        if (w + 1 <= lq) { HS[((w + 1) & (B - 1)) * kCsT] = QM_NEG_INF; ES[((w + 1) & (B - 1)) * kCsT] = QM_NEG_INF; }
+        for (int j = 0; j < lq && j <= w; ++j) {
+            int c = S.qb(j);
+            c = c > 4 ? 4 : c;
+            SS[(j & (B - 1)) * kCsT] = (unsigned short)(c * 0x1111 + 0x8880);
+        }
+        int us = 0, n_mm = 0;                              // ungapped score and mismatches (the main diagonal)
+        for (int i = 0; i < rlen; ++i) {
+            const int tb = S.tb(i);
+            const int beg = i > w ? i - w : 0;
+            const int end = i + w + 1 < lq ? i + w + 1 : lq;
+            if (i > 0 && i + w < lq) {                     // the column entering the band on the right
+                int c = S.qb(i + w);
+                c = c > 4 ? 4 : c;
+                SS[((i + w) & (B - 1)) * kCsT] = (unsigned short)(c * 0x1111 + 0x8880);
+            }
+            Lut L;
+            if (tb > 3) { L.lo = 0xffffffffu; L.hi = 0xffffffffu; }
+            else {
+                const unsigned mis = (unsigned)(-o.b) & 0xffu, mat = (unsigned)o.a & 0xffu;
+                unsigned v = mis * 0x01010101u;
+                v = (v & ~(0xffu << (8 * tb))) | (mat << (8 * tb));
+                L.lo = v; L.hi = 0xffffffffu;
+            }
+            {   // main-diagonal cell: ungapped score / mismatch bookkeeping
+                const unsigned sel = SS[(i & (B - 1)) * kCsT];
+                us += lut_score(L, sel);
+                n_mm += (int)(sel & 7u) != tb;
+            }
+            int f = QM_NEG_INF;
+            int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : QM_NEG_INF;
+            for (int j = beg; j < end; ++j) {
+                const int sl = (j & (B - 1)) * kCsT;
+                int m = HS[sl], e = ES[sl];
+                HS[sl] = h1;
+                m += lut_score(L, SS[sl]);
+                int h = m >= e ? m : e;
+                h = h >= f ? h : f;
+                h1 = h;
+                int tt = m - oe_del;
+                e -= o.e_del;
+                e = e > tt ? e : tt;
+                ES[sl] = e;
+                tt = m - oe_ins;
+                f -= o.e_ins;
+                f = f > tt ? f : tt;
+            }
+            const int sl = (end & (B - 1)) * kCsT;
+            HS[sl] = h1; ES[sl] = QM_NEG_INF;
+        }
+        const int score = HS[(lq & (B - 1)) * kCsT];
+        if (score == us && !(score < t.truesc - o.a)) {
+            // final and gap-free: <lq>M with clips, exactly what mem_reg2aln writes
+            const bool is_rev = t.rb >= V.l_pac;
+            const int64_t pos = t.rb < V.l_pac ? t.rb : 2 * V.l_pac - 1 - (t.re - 1);
+            int m = 0;
+            const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+            if (clip5) rec->cigar[m++] = (uint32_t)clip5 << 4 | 4;
+            rec->cigar[m++] = (uint32_t)lq << 4;
+            if (clip3) rec->cigar[m++] = (uint32_t)clip3 << 4 | 4;
+            rec->n_cigar = (uint8_t)m;
+            const int rid = qm_pos2rid(V, pos);
+            rec->rid = rid;
+            rec->pos = (int32_t)(pos - V.off[rid]);
+            rec->nm = n_mm;
+        } else left[atomicAdd(n_left, 1)] = ti;
+    }
+}
+
 // ---- kernel 2 (one warp per task): banded global DP with traceback, bwa's band-doubling retry, NM, clips ----
 __global__ void __launch_bounds__(kCigWarps * 32)
 cigar_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
-             const CigTask *__restrict__ tasks, const int *__restrict__ n_tasks, int *__restrict__ cursor,
-             uint8_t *__restrict__ overflow, qm_aln *__restrict__ alns, int *__restrict__ err)
+             const CigTask *__restrict__ tasks, const int *__restrict__ left, const int *__restrict__ n_left,
+             int *__restrict__ cursor, uint8_t *__restrict__ overflow, qm_aln *__restrict__ alns, int *__restrict__ err)
 {
     extern __shared__ uint8_t smem[];
     __shared__ uint32_t s_cig[kCigWarps][QM_MAX_CIGAR];
     const int lane = qm_lane(), wib = threadIdx.x >> 5;
     uint8_t *dir_smem = smem + (size_t)wib * kDirBytes;
     uint8_t *dir_glob = overflow + ((size_t)blockIdx.x * kCigWarps + wib) * kOverflowPerWarp;
-    const int n = *n_tasks;
+    const int n = *n_left;
     for (;;) {
         int ti = 0;
         if (lane == 0) ti = atomicAdd(cursor, 1);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= n) break;
-        const CigTask t = tasks[ti];
+        const CigTask t = tasks[left[ti]];
         qm_aln *rec = alns + t.read;
         const int l_query = lens[t.read];
         const int qb = rec->qb, qe = rec->qe;
@@ -718,7 +845,8 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const size_t o_tab = 0, o_subn = o_tab + kMapqTabLen * 8, o_term = o_subn + kSubnTabLen * 4;
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
     const size_t o_tasks = o_misc + 256;
-    const size_t o_over = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
+    const size_t o_left = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
+    const size_t o_over = (o_left + (size_t)2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
@@ -732,20 +860,27 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     T.mapq_l = (const double *)(b + o_tab); T.subn = (const int *)(b + o_subn);
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
     int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
+    int *n_left = (int *)(b + o_misc + 24), *left = (int *)(b + o_left);
     CigTask *tasks = (CigTask *)(b + o_tasks);
     const unsigned grid = (unsigned)((n_pairs + 127) / 128);
     static bool attr_set = false;
     if (!attr_set) {
         QM_CUDA(ctx, cudaFuncSetAttribute(cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCigWarps * kDirBytes));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kCsT * 10));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kCsT * 10));
         attr_set = true;
     }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
     pair_decide_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, T, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns,
                                              tasks, n_tasks);
-    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, n_tasks,
+    // score-only thread-per-task pass (two band classes: w <= 15 and 16..31), then traceback only where needed
+    const unsigned cs_grid = (unsigned)(ctx->sm_count * 4);
+    cig_score_kernel<32><<<cs_grid, kCsT, 32 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, n_tasks, 0, 15, 31, d_alns, left, n_left);
+    cig_score_kernel<64><<<cs_grid, kCsT, 64 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, n_tasks, 16, 31, 31, d_alns, left, n_left);
+    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, left, n_left,
                                                                           cursor, (uint8_t *)(b + o_over), d_alns, err);
     pair_finish_kernel<<<grid, 128, 0, st>>>(idx->v, T, n_pairs, d_regs, d_alns);
-    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 3);
+    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 5);
     QM_CUDA(ctx, cudaGetLastError());
     int h_err = 0;
     QM_CUDA(ctx, cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st));

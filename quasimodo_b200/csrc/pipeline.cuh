@@ -64,15 +64,17 @@ static inline ExtParams qm_ext_params(const qm_opt *o)
     return P;
 }
 
-constexpr int kExtClasses = 5;    // C = 1,2,4,8,16 columns per lane <=> qlen+1 <= 32*C
+constexpr int kExtClasses = 6;    // query-length classes: <= 32, 64, 96, 128, 256 (thread-per-task kernel), <= 511 (warp-per-task)
 static __host__ __device__ __forceinline__ int qm_ext_class(int qlen)
 {
-    const int need = qlen + 1;
-    return need <= 32 ? 0 : need <= 64 ? 1 : need <= 128 ? 2 : need <= 256 ? 3 : 4;
+    return qlen <= 32 ? 0 : qlen <= 64 ? 1 : qlen <= 96 ? 2 : qlen <= 128 ? 3 : qlen <= 256 ? 4 : 5;
 }
 
 // Launch the per-class extension kernels.  lists: [kExtClasses][list_stride] task indices; h_counts may be
 // NULL (unknown on the host: persistent grids sized for the SM count) or the 5 class counts.
+int qm_ext2_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
+                           const int *h_counts, bool exact_counts, qm_ext_result *d_out, cudaStream_t st);
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
                           const int *h_counts, qm_ext_result *d_out, cudaStream_t st);

@@ -12,7 +12,7 @@
 #include "pipeline.cuh"
 
 namespace {
-constexpr int64_t kChunkPairs = 1 << 18;
+constexpr int64_t kChunkPairs = 1 << 19;
 constexpr int64_t kPestatPairs = QM_PESTAT_PAIRS;
 }
 

@@ -29,6 +29,8 @@ for _ in range(m):
 seq, tasks = pack_ext_tasks(base_pairs, h0s, ws, 5, 1)
 reps = (n + m - 1) // m
 tasks_big = np.tile(tasks, reps)[:n]
+if len(sys.argv) > 2 and sys.argv[2] == "sorted":      # warp-mates of similar shape: sensitivity of the thread-per-task kernel
+    tasks_big = tasks_big[np.lexsort((tasks_big["h0"], tasks_big["qlen"]))]
 d_seq = torch.from_numpy(seq).cuda()
 d_tasks = torch.from_numpy(tasks_big.view(np.uint8)).cuda()
 d_out = torch.zeros(n * 32, dtype=torch.uint8, device="cuda")
