@@ -17,6 +17,7 @@
 // Tasks reference the read batch and the reference in place (ExtTaskI, QM_EXTI_INDIRECT); no sequence
 // bytes are materialised.
 #include "pipeline.cuh"
+#include "ext_warp.cuh"
 
 namespace {
 
@@ -276,26 +277,17 @@ struct RoundCounters {        // zeroed before every advance round
 };
 
 // ---- mem_chain2aln as a per-read state machine ----
-__global__ void __launch_bounds__(128)
-advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
-               int64_t n, const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
-               ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
-               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks, int *__restrict__ lists,
-               int64_t list_stride, RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
+// Consumes the result of the read's pending extension (xres, when the state is a WAIT state), then walks the plan
+// until the next extension task is known (returns true, task in *t_out) or the read is finished (returns false,
+// regions sorted / de-duplicated, *n_regs_out set).
+__device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t *query, int lq, const qm_seed *S, uint16_t *PL,
+                             int np, ReadState &s, qm_reg *av, int32_t *n_regs_out, const qm_ext_result *xres, int64_t r,
+                             ExtTaskI *t_out, unsigned long long *cells)
 {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    ReadState s = st[r];
-    if (s.phase == PH_DONE) return;
-    const qm_seed *S = seeds + r * QM_MAX_SEEDS;
-    uint16_t *PL = plan + r * QM_MAX_SEEDS;
-    qm_reg *av = regs + r * QM_MAX_REGS;
-    const int lq = lens[r], np = n_plan[r];
-    const uint8_t *query = codes + r * stride;
     const int64_t l_pac = V.l_pac;
 
     if (s.phase == PH_WAIT_LEFT) {
-        const qm_ext_result x = res[s.task];
+        const qm_ext_result x = *xres;
         const qm_seed sd = S[PL[s.cursor] & 63];
         qm_reg *a = &av[s.n_av];
         if (cells) atomicAdd(cells, (unsigned long long)x.cells);
@@ -304,7 +296,7 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
         else { a->qb = 0; a->rb = sd.rbeg - x.gtle; a->truesc = x.gscore; }
         s.phase = PH_RIGHT;
     } else if (s.phase == PH_WAIT_RIGHT) {
-        const qm_ext_result x = res[s.task];
+        const qm_ext_result x = *xres;
         const qm_seed sd = S[PL[s.cursor] & 63];
         qm_reg *a = &av[s.n_av];
         const int sc0 = a->score;        // score before the right extension (= the task's h0)
@@ -379,10 +371,9 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
                 break;
             }
             if (!have) {
-                n_regs[r] = sort_dedup(o, s.n_av, av);
+                *n_regs_out = sort_dedup(o, s.n_av, av);
                 s.phase = PH_DONE;
-                st[r] = s;
-                return;
+                return false;
             }
         }
         // the chain's reference window (mem_chain2aln rmax[], clamped to the contig as bns_fetch_seq does)
@@ -454,19 +445,109 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
         }
         if (emit) {
             t.pad[0] = (int)r; t.pad[1] = 0;
-            const int slot = atomicAdd(&ctr->n_tasks, 1);
-            tasks[slot] = t;
-            const int c = qm_ext_class(t.qlen);
-            const int ls = atomicAdd(&ctr->class_count[c], 1);
-            lists[(int64_t)c * list_stride + ls] = slot;
-            s.task = slot;
-            st[r] = s;
-            return;
+            *t_out = t;
+            return true;
         }
     }
 }
 
-constexpr int64_t kSeBatch = 1 << 20;       // reads per internal round-trip (bounds scratch memory)
+__global__ void __launch_bounds__(128)
+advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+               int64_t n, const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
+               ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
+               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks, int *__restrict__ lists,
+               int64_t list_stride, RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    ReadState s = st[r];
+    if (s.phase == PH_DONE) return;
+    ExtTaskI t;
+    const bool emit = advance_read(V, o, codes + r * stride, lens[r], seeds + r * QM_MAX_SEEDS, plan + r * QM_MAX_SEEDS, n_plan[r], s,
+                                   regs + r * QM_MAX_REGS, n_regs + r, s.task >= 0 ? res + s.task : nullptr, r, &t, cells);
+    if (emit) {
+        const int slot = atomicAdd(&ctr->n_tasks, 1);
+        tasks[slot] = t;
+        const int c = qm_ext_class(t.qlen);
+        const int ls = atomicAdd(&ctr->class_count[c], 1);
+        lists[(int64_t)c * list_stride + ls] = slot;
+        s.task = slot;
+    }
+    st[r] = s;
+}
+
+// ---- tail: the reads still active after the bulk rounds (reads with many chains, up to 2 x QM_MAX_REGS dependent
+// extensions each) are finished by ONE WARP PER READ without further host round trips: the warp runs the pending
+// extension with the warp-wide kernel body (ext_warp.cuh), lane 0 feeds the result to the state machine, repeat. ----
+template <int C>
+__device__ __forceinline__ qm_ext_result tail_extend(const ExtParams &P, const IndexView &V, const ExtTaskI &t, int lane)
+{
+    SeqFetch F;
+    F.q = t.q; F.t = t.t; F.t0 = t.t0; F.qstep = t.qstep; F.tstep = t.tstep;
+    F.indirect = (t.flags & QM_EXTI_INDIRECT) != 0; F.V = &V;
+    ExtState r;
+    int w_used = t.w, cells = 0, prev = (t.flags & QM_EXT_PREV_H0) ? t.h0 : -1;
+    const int tries = (t.flags & QM_EXT_BAND_RETRY) ? 2 : 1;
+    for (int a = 0; a < tries; ++a) {
+        w_used = t.w << a;
+        r = ext_run<C>(P, F, t.qlen, t.tlen, t.h0, w_used, t.end_bonus, lane);
+        cells += r.cells;
+        if (r.score == prev || r.max_off < (w_used >> 1) + (w_used >> 2)) break;
+        prev = r.score;
+    }
+    qm_ext_result x;
+    x.score = r.score; x.qle = r.qle; x.tle = r.tle; x.gtle = r.gtle; x.gscore = r.gscore; x.max_off = r.max_off;
+    x.w_used = w_used; x.cells = cells;
+    return x;
+}
+
+constexpr int kTailWarps = 4;
+
+__global__ void __launch_bounds__(kTailWarps * 32)
+tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+            const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
+            ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
+            const ExtTaskI *__restrict__ tasks, int n_tasks, int *__restrict__ cursor, unsigned long long *__restrict__ cells)
+{
+    __shared__ ExtTaskI s_task[kTailWarps];
+    __shared__ qm_ext_result s_res[kTailWarps];
+    __shared__ int s_more[kTailWarps];
+    const int lane = qm_lane(), wib = threadIdx.x >> 5;
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(cursor, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= n_tasks) break;
+        if (lane == 0) s_task[wib] = tasks[slot];
+        __syncwarp();
+        const int64_t r = s_task[wib].pad[0];
+        ReadState s;
+        if (lane == 0) s = st[r];
+        for (;;) {
+            const ExtTaskI t = s_task[wib];
+            qm_ext_result x;
+            if (t.qlen <= 127) x = tail_extend<4>(P, V, t, lane);
+            else if (t.qlen <= 287) x = tail_extend<9>(P, V, t, lane);
+            else x = tail_extend<16>(P, V, t, lane);
+            __syncwarp();
+            if (lane == 0) {
+                s_res[wib] = x;
+                ExtTaskI nt;
+                const bool more = advance_read(V, o, codes + r * stride, lens[r], seeds + r * QM_MAX_SEEDS, plan + r * QM_MAX_SEEDS,
+                                               n_plan[r], s, regs + r * QM_MAX_REGS, n_regs + r, &s_res[wib], r, &nt, cells);
+                if (more) s_task[wib] = nt;
+                s_more[wib] = more ? 1 : 0;
+            }
+            __syncwarp();
+            if (!s_more[wib]) break;
+        }
+        if (lane == 0) { s.task = -1; st[r] = s; }
+        __syncwarp();
+    }
+}
+
+constexpr int64_t kSeBatch = 1 << 20;
+constexpr int kTailMinTasks = 8192;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
 
 struct SeScratch {
     qm_seed *seeds; int32_t *n_seeds; uint16_t *plan; uint8_t *n_plan; ReadState *st;
@@ -553,6 +634,17 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { cudaFreeHost(h_ctr); return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
             if (h_ctr->n_tasks == 0) break;
+            if (h_ctr->n_tasks < kTailMinTasks) {
+                // few reads left: finish them on the device, one warp per read, no more round trips
+                sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
+                int blocks = (h_ctr->n_tasks + kTailWarps - 1) / kTailWarps;
+                if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
+                tail_kernel<<<blocks, kTailWarps * 32, 0, st>>>(idx->v, *opt, P, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan,
+                                                                sc.st, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.tasks,
+                                                                h_ctr->n_tasks, &sc.ctr->class_cursor[7], (unsigned long long *)d_cells);
+                qm_prof_end(ctx, QM_ST_EXTEND, sp, st, 1);
+                break;
+            }
             sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
             int n_launch = 0;
             for (int c = 0; c < kExtClasses; ++c) n_launch += h_ctr->class_count[c] > 0;
