@@ -269,12 +269,16 @@ __device__ int sort_dedup(const qm_opt &o, int n, qm_reg *a)
     return m;
 }
 
-struct RoundCounters {        // zeroed before every advance round
-    int class_count[8];       // [0..4] tasks per striping class
-    int class_cursor[8];      // work cursors of the extension kernels
+struct RoundCounters {        // zeroed before every advance round; the host reads back the first kRoundHeader bytes
+    int class_count[kExtCtr];     // tasks per query-length class
+    int class_cursor[kExtCtr];    // work cursors of the extension kernels
     int n_tasks;
-    int pad[7];
+    int tail_cursor;
+    int pad[6];
+    int hist[512];            // tasks per query length (counting sort of the task lists by qlen)
+    int offs[512];            // running output offsets of the scatter pass, relative to the class's list
 };
+constexpr size_t kRoundHeader = (2 * kExtCtr + 8) * sizeof(int);
 
 // ---- mem_chain2aln as a per-read state machine ----
 // Consumes the result of the read's pending extension (xres, when the state is a WAIT state), then walks the plan
@@ -455,8 +459,8 @@ __global__ void __launch_bounds__(128)
 advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
                int64_t n, const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
                ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
-               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks, int *__restrict__ lists,
-               int64_t list_stride, RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
+               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks,
+               RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
 {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -468,12 +472,36 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
     if (emit) {
         const int slot = atomicAdd(&ctr->n_tasks, 1);
         tasks[slot] = t;
-        const int c = qm_ext_class(t.qlen);
-        const int ls = atomicAdd(&ctr->class_count[c], 1);
-        lists[(int64_t)c * list_stride + ls] = slot;
+        atomicAdd(&ctr->class_count[qm_ext_class(t.qlen)], 1);
+        atomicAdd(&ctr->hist[t.qlen], 1);
         s.task = slot;
     }
     st[r] = s;
+}
+
+// Counting sort of a round's tasks by query length into the per-class lists: warp-mates of the thread-per-task
+// extension kernel then run rows of similar length and finish at similar times.
+__global__ void __launch_bounds__(512) sort_offsets_kernel(RoundCounters *__restrict__ ctr)
+{
+    __shared__ int s_h[512];
+    const int q = threadIdx.x;
+    s_h[q] = ctr->hist[q];
+    __syncthreads();
+    // exclusive prefix of hist[] restricted to the query lengths of q's own class (classes are contiguous ranges)
+    const int c = qm_ext_class(q);
+    int acc = 0;
+    for (int k = q - 1; k >= 0 && qm_ext_class(k) == c; --k) acc += s_h[k];
+    ctr->offs[q] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+sort_scatter_kernel(const ExtTaskI *__restrict__ tasks, RoundCounters *__restrict__ ctr, int *__restrict__ lists, int64_t list_stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctr->n_tasks) return;
+    const int q = tasks[i].qlen;
+    const int pos = atomicAdd(&ctr->offs[q], 1);
+    lists[(int64_t)qm_ext_class(q) * list_stride + pos] = i;
 }
 
 // ---- tail: the reads still active after the bulk rounds (reads with many chains, up to 2 x QM_MAX_REGS dependent
@@ -627,10 +655,10 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
             cudaMemsetAsync(sc.ctr, 0, sizeof(RoundCounters), st);
             advance_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.plan, sc.n_plan, sc.st,
-                                                 d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.res, sc.tasks, sc.lists, nb,
+                                                 d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.res, sc.tasks,
                                                  sc.ctr, (unsigned long long *)d_cells);
             qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
-            cudaMemcpyAsync(h_ctr, sc.ctr, sizeof(RoundCounters), cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(h_ctr, sc.ctr, kRoundHeader, cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { cudaFreeHost(h_ctr); return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
             if (h_ctr->n_tasks == 0) break;
@@ -641,10 +669,14 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
                 tail_kernel<<<blocks, kTailWarps * 32, 0, st>>>(idx->v, *opt, P, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan,
                                                                 sc.st, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.tasks,
-                                                                h_ctr->n_tasks, &sc.ctr->class_cursor[7], (unsigned long long *)d_cells);
+                                                                h_ctr->n_tasks, &sc.ctr->tail_cursor, (unsigned long long *)d_cells);
                 qm_prof_end(ctx, QM_ST_EXTEND, sp, st, 1);
                 break;
             }
+            sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
+            sort_offsets_kernel<<<1, 512, 0, st>>>(sc.ctr);
+            sort_scatter_kernel<<<(unsigned)((h_ctr->n_tasks + 255) / 256), 256, 0, st>>>(sc.tasks, sc.ctr, sc.lists, nb);
+            qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 2);
             sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
             int n_launch = 0;
             for (int c = 0; c < kExtClasses; ++c) n_launch += h_ctr->class_count[c] > 0;

@@ -25,6 +25,9 @@ struct qm_ctx {
     // scratch arenas grown on demand (never shrunk); index = purpose
     qm_scratch scratch[12];
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    // side streams: the independent per-class extension kernels of one round run concurrently (fork/join by events)
+    cudaStream_t side[12] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
     bool prof_on = false;
     std::vector<qm_prof_span> prof_spans;
     std::vector<cudaEvent_t> prof_pool;

@@ -116,6 +116,11 @@ int qm_ctx_create(int device, qm_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return QM_ECUDA; }
+    for (int i = 0; i < 12; ++i) {
+        if (cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { qm_ctx_destroy(c); return QM_ECUDA; }
+    }
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { qm_ctx_destroy(c); return QM_ECUDA; }
     *out = c;
     return QM_OK;
 }
@@ -127,6 +132,11 @@ void qm_ctx_destroy(qm_ctx *ctx)
     for (auto &s : ctx->scratch) if (s.ptr) cudaFree(s.ptr);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 12; ++i) {
+        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     delete ctx;

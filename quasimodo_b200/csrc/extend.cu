@@ -103,21 +103,31 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
 {
     // A class with many tasks goes to the thread-per-task kernel (extend2.cu: high throughput, but one task is a
     // long serial chain, ~0.3 ms); a class with few tasks (the tail rounds of mem_chain2aln, where only reads with
-    // many chains are still active) goes to the warp-per-task kernel below (low latency).  Class 5 (qlen > 256)
-    // always does.  Without host-side counts (public qm_extend_batch) classes 0..4 use the thread-per-task kernel.
-    int big[kExtClasses] = {1, 1, 1, 1, 1, 0};
-    if (h_counts)
-        for (int c = 0; c < 5; ++c) big[c] = h_counts[c] >= kThreadPerTaskMin;
-    int hc2[kExtClasses];
-    for (int c = 0; c < kExtClasses; ++c) hc2[c] = big[c] ? (h_counts ? h_counts[c] : 1) : 0;
-    int rc = qm_ext2_launch_classes(ctx, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, hc2, h_counts != nullptr, d_out, st);
-    if (rc) return rc;
-    if (!big[0]) launch_class<2>(ctx, 0, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    if (!big[1]) launch_class<3>(ctx, 1, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    if (!big[2]) launch_class<4>(ctx, 2, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    if (!big[3]) launch_class<5>(ctx, 3, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    if (!big[4]) launch_class<9>(ctx, 4, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
-    launch_class<16>(ctx, 5, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, st);
+    // many chains are still active) goes to the warp-per-task kernel (low latency).  Class 9 (qlen > 256) always
+    // does.  Without host-side counts (public qm_extend_batch) classes 0..8 use the thread-per-task kernel.
+    // The classes of one round are independent: each runs on its own side stream, forked from / joined to `st`.
+    QM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    for (int c = 0; c < kExtClasses; ++c) {
+        if (h_counts && h_counts[c] == 0) continue;
+        cudaStream_t sc = ctx->side[c];
+        QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+        const bool big = c < 9 && (!h_counts || h_counts[c] >= kThreadPerTaskMin);
+        if (big) {
+            int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc);
+            if (rc) return rc;
+        } else {
+            switch (c) {
+            case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 6: case 7: launch_class<5>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 8: launch_class<9>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            default: launch_class<16>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            }
+        }
+        QM_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], sc));
+        QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+    }
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }
@@ -136,12 +146,12 @@ int qm_extend_launch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const
     if (rc) return rc;
     ExtTaskI *itasks = (ExtTaskI *)p;
     int *lists = (int *)((char *)p + task_bytes);
-    int *ctrs = (int *)((char *)p + task_bytes + list_bytes);     // [0..5] counts, [8..13] cursors, [16] err
+    int *ctrs = (int *)((char *)p + task_bytes + list_bytes);     // [0..9] counts, [16..25] cursors, [32] err
     QM_CUDA(ctx, cudaMemsetAsync(ctrs, 0, 64 * sizeof(int), st));
     const int tpb = 256;
-    ext_classify_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_tasks, d_seq, n, itasks, lists, ctrs, d_out, ctrs + 16);
+    ext_classify_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_tasks, d_seq, n, itasks, lists, ctrs, d_out, ctrs + 32);
     IndexView V = {};
-    return qm_ext_launch_classes(ctx, qm_ext_params(opt), V, itasks, lists, n, ctrs, ctrs + 8, nullptr, d_out, st);
+    return qm_ext_launch_classes(ctx, qm_ext_params(opt), V, itasks, lists, n, ctrs, ctrs + kExtCtr, nullptr, d_out, st);
 }
 
 extern "C" {

@@ -52,6 +52,7 @@ struct TState {                         // one in-flight task (registers)
     const uint8_t *q, *t;
     int64_t t0;
     int qstep, tstep;
+    int tb_next;                        // target base of the next row, fetched one row ahead
     bool indirect;
 };
 
@@ -70,30 +71,41 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
     TState S;
     S.tid_out = -1;
 
-    // Every thread is independent: no warp-collective operation anywhere below.  The lanes of a warp walk the
-    // same loop body (fetch / row / end-of-try) and reconverge once per row.
+    // The lanes of a warp walk the same loop body (refill / row / end-of-try) and reconverge once per row.  A lane
+    // whose task is finished does not fetch the next one at once: initialising a task is a serial loop over its
+    // query, and 32 lanes refilling one by one would stall the warp's row loop 32 times per task generation.
+    // Instead idle lanes wait until kRefill of them are idle (or nobody works) and then refill together.
+    constexpr int kRefill = 8;
+    bool exhausted = false;
     for (;;) {
+        const bool idle = S.tid_out < 0;
+        const unsigned idle_m = __ballot_sync(0xffffffffu, idle);
+        const unsigned want_m = __ballot_sync(0xffffffffu, idle && !exhausted);
+        if (idle_m == 0xffffffffu && want_m == 0u) break;                 // list drained and every lane finished
         // ---- fetch + initialise a task ----
-        if (S.tid_out < 0) {
+        if (idle && !exhausted && (__popc(want_m) >= kRefill || idle_m == 0xffffffffu)) {
             const int idx = atomicAdd(cursor, 1);
-            if (idx >= n) break;
-            const int tk = list[idx];
-            const ExtTaskI t = tasks[tk];
-            S.tid_out = tk;
-            S.qlen = t.qlen; S.tlen = t.tlen; S.h0 = t.h0; S.w0 = t.w; S.end_bonus = t.end_bonus;
-            S.tries_left = (t.flags & QM_EXT_BAND_RETRY) ? 2 : 1;
-            S.prev = (t.flags & QM_EXT_PREV_H0) ? t.h0 : -1;
-            S.cells = 0;
-            S.q = t.q; S.t = t.t; S.t0 = t.t0; S.qstep = t.qstep; S.tstep = t.tstep;
-            S.indirect = (t.flags & QM_EXTI_INDIRECT) != 0;
-            S.i = -1;                               // "needs row -1 initialisation"
-            S.w = S.w0;
-            for (int j = 0; j < S.qlen; ++j) {      // PRMT selectors: byte q of the row's score LUT, sign-extended
-                int c = S.q[(int64_t)j * S.qstep];
-                c = c > 4 ? 4 : c;
-                HP[2 * PL + IX(j)] = (unsigned short)(c * 0x1111 + 0x8880);
+            if (idx >= n) exhausted = true;
+            else {
+                const int tk = list[idx];
+                const ExtTaskI t = tasks[tk];
+                S.tid_out = tk;
+                S.qlen = t.qlen; S.tlen = t.tlen; S.h0 = t.h0; S.w0 = t.w; S.end_bonus = t.end_bonus;
+                S.tries_left = (t.flags & QM_EXT_BAND_RETRY) ? 2 : 1;
+                S.prev = (t.flags & QM_EXT_PREV_H0) ? t.h0 : -1;
+                S.cells = 0;
+                S.q = t.q; S.t = t.t; S.t0 = t.t0; S.qstep = t.qstep; S.tstep = t.tstep;
+                S.indirect = (t.flags & QM_EXTI_INDIRECT) != 0;
+                S.i = -1;                               // "needs row -1 initialisation"
+                S.w = S.w0;
+                for (int j = 0; j < S.qlen; ++j) {      // PRMT selectors: byte q of the row's score LUT, sign-extended
+                    int c = S.q[(int64_t)j * S.qstep];
+                    c = c > 4 ? 4 : c;
+                    HP[2 * PL + IX(j)] = (unsigned short)(c * 0x1111 + 0x8880);
+                }
             }
         }
+        if (S.tid_out < 0) continue;                    // waiting for a refill batch, or finished
         if (S.i < 0) {
             // row -1 of eh[] (SURVEY.md A.3 first lines) and the band clamp of this try
             const int qlen = S.qlen, h0 = S.h0;
@@ -115,6 +127,7 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
             S.w = w;                                   // clamped band of this try (w_used reports the unclamped one)
             S.mx = h0; S.mx_i = -1; S.mx_j = -1; S.mx_ie = -1; S.gscore = -1; S.max_off = 0;
             S.beg = 0; S.end = qlen; S.i = 0;
+            S.tb_next = S.tlen > 0 ? (S.indirect ? qm_ref_base(V, S.t0) : S.t[0]) : 0;
         }
         // ---- one row ----
         bool done = true;
@@ -122,7 +135,8 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
             done = false;
             const int i = S.i, qlen = S.qlen, w = S.w;
             int beg = S.beg, end = S.end;
-            const int tb = S.indirect ? qm_ref_base(V, S.t0 + (int64_t)i * S.tstep) : S.t[i];
+            const int tb = S.tb_next;
+            if (i + 1 < S.tlen) S.tb_next = S.indirect ? qm_ref_base(V, S.t0 + (int64_t)(i + 1) * S.tstep) : S.t[i + 1];
             const Lut L = make_lut(P, tb);
             if (beg < i - w) beg = i - w;
             if (end > i + w + 1) end = i + w + 1;
@@ -227,8 +241,7 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
 
 template <int CAP>
 void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
-             int64_t list_stride, const int *d_counts, int *d_cursors, const int *h_counts, bool exact_counts,
-             qm_ext_result *d_out, cudaStream_t st)
+             int64_t list_stride, const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, cudaStream_t st)
 {
     const size_t smem = (size_t)3 * (CAP / 2 + 1) * kT * 2 * 2;
     static bool attr_set = false;
@@ -239,13 +252,13 @@ void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
     }
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16) per_sm = 16;
+    if (per_sm > 12) per_sm = 12;
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
-    if (h_counts[cls] == 0) return;              // class not routed here (or known to be empty)
-    if (exact_counts) {
-        const int64_t need = (h_counts[cls] + kT - 1) / kT;
+    if (h_count >= 0) {
+        const int64_t need = (h_count + kT - 1) / kT;
         if (need < blocks) blocks = need;
     }
+    if (blocks < 1) return;
     const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins;
     if (sym) ext2_kernel<CAP, true><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
     else ext2_kernel<CAP, false><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
@@ -253,17 +266,22 @@ void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
 
 }  // namespace
 
-// classes 0..4 (qlen <= 32, 64, 96, 128, 256) with h_counts[c] != 0: thread-per-task kernel.  exact_counts: the
-// h_counts are the real class sizes (grids are trimmed to them); otherwise they only say "route this class here".
-int qm_ext2_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
-                           int64_t list_stride, const int *d_counts, int *d_cursors, const int *h_counts, bool exact_counts,
-                           qm_ext_result *d_out, cudaStream_t st)
+int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
+                         qm_ext_result *d_out, cudaStream_t st)
 {
-    launch2<32>(ctx, 0, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, exact_counts, d_out, st);
-    launch2<64>(ctx, 1, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, exact_counts, d_out, st);
-    launch2<96>(ctx, 2, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, exact_counts, d_out, st);
-    launch2<128>(ctx, 3, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, exact_counts, d_out, st);
-    launch2<256>(ctx, 4, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, exact_counts, d_out, st);
+    switch (cls) {
+    case 0: launch2<16>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 1: launch2<32>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 2: launch2<48>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 3: launch2<64>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 4: launch2<80>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 5: launch2<96>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 6: launch2<112>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 7: launch2<128>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 8: launch2<256>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    default: return qm_fail(ctx, QM_EINVAL, "qm_ext2_launch_class: class %d has no thread-per-task kernel", cls);
+    }
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }

@@ -64,17 +64,20 @@ static inline ExtParams qm_ext_params(const qm_opt *o)
     return P;
 }
 
-constexpr int kExtClasses = 6;    // query-length classes: <= 32, 64, 96, 128, 256 (thread-per-task kernel), <= 511 (warp-per-task)
+constexpr int kExtClasses = 10;   // query-length classes: 16-wide up to 128 (thread-per-task kernel, shared memory sized per
+                                  // class), <= 256 (thread-per-task), <= 511 (warp-per-task only)
+constexpr int kExtCtr = 16;       // slots per counter array (>= kExtClasses)
 static __host__ __device__ __forceinline__ int qm_ext_class(int qlen)
 {
-    return qlen <= 32 ? 0 : qlen <= 64 ? 1 : qlen <= 96 ? 2 : qlen <= 128 ? 3 : qlen <= 256 ? 4 : 5;
+    return qlen <= 128 ? (qlen <= 0 ? 0 : (qlen - 1) >> 4) : qlen <= 256 ? 8 : 9;
 }
 
 // Launch the per-class extension kernels.  lists: [kExtClasses][list_stride] task indices; h_counts may be
 // NULL (unknown on the host: persistent grids sized for the SM count) or the 5 class counts.
-int qm_ext2_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
-                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
-                           const int *h_counts, bool exact_counts, qm_ext_result *d_out, cudaStream_t st);
+// one class (0..8) on the thread-per-task kernel; h_count < 0: unknown on the host
+int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
+                         qm_ext_result *d_out, cudaStream_t st);
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
                           const int *h_counts, qm_ext_result *d_out, cudaStream_t st);
