@@ -41,6 +41,10 @@ __device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
 }
 
 // ---- seeding: all maximal exact matches of length >= k on both strands ----
+// Every k-mer of the read is looked up on both strands (oracle: qmo_collect_seeds).  Most look-ups are avoided
+// without changing the result: when the previous k-mer had exactly one hit, at forward reference position p, and the
+// new read base continues that match, the new k-mer EQUALS the reference k-mer next to p; if the index says that
+// k-mer is unique and its reverse complement absent (IndexView::uniq), both look-ups are known: one hit, there.
 __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S)
 {
     const int k = V.k;
@@ -49,37 +53,65 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
     const int top = 2 * (k - 1);
     uint64_t fw = 0, rc = 0;
     int valid = 0, n = 0;
-    int hint[2] = {-1, -1};
+    int64_t trk_p = -1;             // forward position of the previous k-mer's only hit, -1 = none / several
+    int trk_pass = 0;               // its strand: 0 = read k-mer as is, 1 = reverse complement
+    // the seed each strand is currently growing lives in registers (a clean read extends ONE seed ~120 times);
+    // S[] in global memory is only touched when a seed is created, looked for, or handed back
+    int64_t cur_diag[2] = {0, 0};
+    int cur_idx[2] = {-1, -1}, cur_len[2] = {0, 0}, cur_qnext[2] = {0, 0};
+    auto flush = [&]() {
+        if (cur_idx[0] >= 0) S[cur_idx[0]].len = cur_len[0];
+        if (cur_idx[1] >= 0) S[cur_idx[1]].len = cur_len[1];
+    };
+    auto add_hit = [&](int pass, int64_t p, int q, bool single) {
+        const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
+        const int64_t diag = rpos - q;
+        if (single && cur_idx[pass] >= 0 && cur_diag[pass] == diag && cur_qnext[pass] == q) {
+            ++cur_len[pass]; ++cur_qnext[pass];
+            return;
+        }
+        flush();
+        int m;
+        bool found = false;
+        for (m = 0; m < n; ++m)
+            if (S[m].rbeg - S[m].qbeg == diag && S[m].qbeg + S[m].len - k + 1 == q) { found = true; break; }
+        if (found) { cur_len[pass] = ++S[m].len; cur_idx[pass] = m; cur_diag[pass] = diag; cur_qnext[pass] = q + 1; }
+        else if (n < QM_MAX_SEEDS) {
+            S[n].rbeg = rpos; S[n].qbeg = q; S[n].len = k;
+            cur_len[pass] = k; cur_idx[pass] = n++; cur_diag[pass] = diag; cur_qnext[pass] = q + 1;
+        }
+    };
     for (int i = 0; i < len; ++i) {
         const int c = rd[i];
-        if (c > 3) { valid = 0; fw = rc = 0; continue; }
+        if (c > 3) { valid = 0; fw = rc = 0; trk_p = -1; continue; }
         fw = ((fw << 2) | (uint64_t)c) & mask;
         rc = (rc >> 2) | ((uint64_t)(3 - c) << top);
         if (++valid < k) continue;
         const int q = i - k + 1;
+        if (trk_p >= 0) {
+            const int64_t p2 = trk_pass ? trk_p - 1 : trk_p + 1;
+            if (p2 >= 0 && p2 + k <= V.l_pac && ((__ldg(&V.uniq[p2 >> 5]) >> (p2 & 31)) & 1u)) {
+                const int rb = trk_pass ? 3 - V.refb[p2] : V.refb[p2 + k - 1];
+                if (rb == c) { add_hit(trk_pass, p2, q, true); trk_p = p2; continue; }
+            }
+        }
+        int n_hits = 0, one_pass = 0;
+        int64_t one_p = -1;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             uint32_t first, cnt;
             if (!qm_idx_lookup(V, pass ? rc : fw, first, cnt)) continue;
-            if (cnt > occ_cap) continue;
+            if (cnt > occ_cap) { n_hits += 2; continue; }          // ignored k-mer: never a tracked single hit
             for (uint32_t t = 0; t < cnt; ++t) {
                 const int64_t p = V.pos[first + t];
-                const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
-                const int64_t diag = rpos - q;
-                int m = hint[pass];
-                bool found = false;
-                if (cnt == 1 && m >= 0 && S[m].rbeg - S[m].qbeg == diag && S[m].qbeg + S[m].len - k + 1 == q) found = true;
-                else
-                    for (m = 0; m < n; ++m)
-                        if (S[m].rbeg - S[m].qbeg == diag && S[m].qbeg + S[m].len - k + 1 == q) { found = true; break; }
-                if (found) { ++S[m].len; hint[pass] = m; }
-                else if (n < QM_MAX_SEEDS) {
-                    S[n].rbeg = rpos; S[n].qbeg = q; S[n].len = k;
-                    hint[pass] = n++;
-                }
+                add_hit(pass, p, q, cnt == 1);
+                one_p = p; one_pass = pass;
             }
+            n_hits += (int)cnt;
         }
+        if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; } else trk_p = -1;
     }
+    flush();
     for (int i = 1; i < n; ++i) {       // order: (qbeg, rbeg)
         const qm_seed x = S[i];
         int j = i - 1;

@@ -63,8 +63,36 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         table[h] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)i, (uint32_t)(j - i));
         i = j;
     }
+    // uniqueness bitmap: k-mer occurs once and its reverse complement never (see IndexView::uniq)
+    std::vector<uint32_t> uniq((size_t)(total + 31) / 32 + 1, 0u);
+    {
+        auto count_of = [&](uint64_t key) -> uint32_t {
+            uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> v.shift;
+            for (;;) {
+                const uint4 e4 = table[h];
+                const uint64_t kk = (uint64_t)e4.x | ((uint64_t)e4.y << 32);
+                if (kk == key) return e4.w;
+                if (e4.x == 0xffffffffu && e4.y == 0xffffffffu) return 0;
+                h = (h + 1) & v.mask;
+            }
+        };
+        for (size_t i = 0; i < km.size();) {
+            size_t j = i;
+            while (j < km.size() && km[j].first == km[i].first) ++j;
+            if (j - i == 1) {
+                const uint64_t key = km[i].first;
+                uint64_t rc = 0;
+                for (int b = 0; b < k; ++b) rc |= (uint64_t)(3 - ((key >> (2 * b)) & 3)) << (2 * (k - 1 - b));
+                // a palindromic k-mer (rc == key) is its own reverse complement: both look-ups hit, not unique
+                if (rc != key && count_of(rc) == 0) uniq[km[i].second >> 5] |= 1u << (km[i].second & 31);
+            }
+            i = j;
+        }
+    }
     cudaError_t e;
-    if ((e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
+    if ((e = cudaMalloc(&ix->d_uniq, uniq.size() * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_uniq, uniq.data(), uniq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_table, (size_t)tsize * sizeof(uint4))) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_pos, pos.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_refb, h_codes, (size_t)total, cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -74,6 +102,7 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
     }
     v.refb = (const uint8_t *)ix->d_refb; v.table = (const uint4 *)ix->d_table; v.pos = (const uint32_t *)ix->d_pos;
+    v.uniq = (const uint32_t *)ix->d_uniq;
     *out = ix;
     return QM_OK;
 }
@@ -85,6 +114,7 @@ void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
     if (ix->d_refb) cudaFree(ix->d_refb);
     if (ix->d_table) cudaFree(ix->d_table);
     if (ix->d_pos) cudaFree(ix->d_pos);
+    if (ix->d_uniq) cudaFree(ix->d_uniq);
     delete ix;
 }
 

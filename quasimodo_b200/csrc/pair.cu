@@ -234,6 +234,29 @@ struct CigTask {
     int32_t read, w2, truesc, regw;
 };
 
+// band of the first try, exactly as bwa_gen_cigar2 derives it from w2
+__device__ __forceinline__ int cig_band(const qm_opt &o, int w2, int lq, int rlen)
+{
+    if (w2 > o.w << 2) w2 = o.w << 2;
+    int max_ins = (int)((double)(((lq + 1) >> 1) * o.a - o.o_ins) / o.e_ins + 1.);
+    int max_del = (int)((double)(((lq + 1) >> 1) * o.a - o.o_del) / o.e_del + 1.);
+    int max_gap = max_ins > max_del ? max_ins : max_del;
+    if (max_gap < 1) max_gap = 1;
+    int w = (max_gap + abs(rlen - lq) + 1) >> 1;
+    if (w > w2) w = w2;
+    const int min_w = abs(rlen - lq) + 3;
+    return w < min_w ? min_w : w;
+}
+// which kernel takes a CIGAR task: 0 / 1 = score-only thread-per-task pass with 32 / 64 circular slots (equal
+// lengths, band <= 15 / <= 31), 2 = warp-per-task kernel with traceback
+__device__ __forceinline__ int cig_class(const IndexView &V, const qm_opt &o, const CigTask &t, int lq)
+{
+    const int rlen = (int)(t.re - t.rb);
+    if (lq != rlen || (t.rb < V.l_pac && t.re > V.l_pac)) return 2;
+    const int w = cig_band(o, t.w2, lq, rlen);
+    return w <= 15 ? 0 : w <= 31 ? 1 : 2;
+}
+
 constexpr int kCigWarps = 4;                  // warps per block of the CIGAR kernel
 constexpr int kDirBytes = 14 * 1024;          // shared-memory direction matrix per warp; larger ones go to global memory
 constexpr size_t kOverflowPerWarp = 1u << 20; // global fallback per warp: covers tlen x ncol up to 1 MiB
@@ -477,7 +500,8 @@ __device__ void finish_pair(qm_aln h[2], int extra_flag)
 __global__ void __launch_bounds__(128)
 pair_decide_kernel(IndexView V, qm_opt o, PairTables T, const uint8_t *__restrict__ codes, int stride,
                    const int32_t *__restrict__ lens, int64_t n_pairs, int64_t pair_id0, qm_reg *__restrict__ regs,
-                   int32_t *__restrict__ n_regs, qm_aln *__restrict__ alns, CigTask *__restrict__ tasks, int *__restrict__ n_tasks)
+                   int32_t *__restrict__ n_regs, qm_aln *__restrict__ alns, CigTask *__restrict__ tasks, int *__restrict__ n_tasks,
+                   int *__restrict__ lists /* [3][list_stride] */, int64_t list_stride, int *__restrict__ n_list /* [3] */)
 {
     const int64_t pi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (pi >= n_pairs) return;
@@ -544,7 +568,10 @@ pair_decide_kernel(IndexView V, qm_opt o, PairTables T, const uint8_t *__restric
             CigTask t;
             t.rb = chosen[i]->rb; t.re = chosen[i]->re; t.read = (int32_t)(2 * pi + i); t.w2 = w2;
             t.truesc = chosen[i]->truesc; t.regw = chosen[i]->w;
-            tasks[atomicAdd(n_tasks, 1)] = t;
+            const int slot = atomicAdd(n_tasks, 1);
+            tasks[slot] = t;
+            const int c = cig_class(V, o, t, h.qe - h.qb);
+            lists[c * list_stride + atomicAdd(&n_list[c], 1)] = slot;
         }
     }
 }
@@ -561,38 +588,23 @@ constexpr int kCsT = 128;              // threads per block
 template <int B>                       // circular slots per thread (power of two), needs 2w + 2 <= B
 __global__ void __launch_bounds__(kCsT)
 cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
-                 const CigTask *__restrict__ tasks, const int *__restrict__ n_tasks, int wmin, int wmax, int wtop,
+                 const CigTask *__restrict__ tasks, const int *__restrict__ mine, const int *__restrict__ n_mine,
                  qm_aln *__restrict__ alns, int *__restrict__ left, int *__restrict__ n_left)
 {
     extern __shared__ int cs_smem[];
     int *HS = cs_smem + threadIdx.x;                           // HS[slot * kCsT]            eh[].h
     int *ES = cs_smem + B * kCsT + threadIdx.x;                // ES[slot * kCsT]            eh[].e
     unsigned short *SS = (unsigned short *)(cs_smem + 2 * B * kCsT) + threadIdx.x;   // PRMT selector of q[j]
-    const int n = *n_tasks;
+    const int n = *n_mine;
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
-    for (int ti = blockIdx.x * kCsT + threadIdx.x; ti < n; ti += gridDim.x * kCsT) {
+    for (int li = blockIdx.x * kCsT + threadIdx.x; li < n; li += gridDim.x * kCsT) {
+        const int ti = mine[li];
         const CigTask t = tasks[ti];
         qm_aln *rec = alns + t.read;
         const int l_query = lens[t.read];
         const int qb = rec->qb, qe = rec->qe;
         const int lq = qe - qb, rlen = (int)(t.re - t.rb);
-        int w2 = t.w2;
-        if (w2 > o.w << 2) w2 = o.w << 2;
-        // band exactly as bwa_gen_cigar2 derives it
-        int max_ins = (int)((double)(((lq + 1) >> 1) * o.a - o.o_ins) / o.e_ins + 1.);
-        int max_del = (int)((double)(((lq + 1) >> 1) * o.a - o.o_del) / o.e_del + 1.);
-        int max_gap = max_ins > max_del ? max_ins : max_del;
-        if (max_gap < 1) max_gap = 1;
-        int w = (max_gap + abs(rlen - lq) + 1) >> 1;
-        if (w > w2) w = w2;
-        const int min_w = abs(rlen - lq) + 3;
-        if (w < min_w) w = min_w;
-        const bool mine = lq == rlen && w >= wmin && w <= wmax && !(t.rb < V.l_pac && t.re > V.l_pac);
-        if (!mine) {
-            if (wmin == 0 && !(lq == rlen && w <= wtop && !(t.rb < V.l_pac && t.re > V.l_pac)))
-                left[atomicAdd(n_left, 1)] = ti;          // the first (narrowest) instance hands over what no instance takes
-            continue;
-        }
+        const int w = cig_band(o, t.w2, lq, rlen);          // the band pair_decide_kernel classified this task by
         SeqPair S;
         S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
         // first row of eh[] and the selectors of the columns row 0 can reach
@@ -846,7 +858,7 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
     const size_t o_tasks = o_misc + 256;
     const size_t o_left = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
-    const size_t o_over = (o_left + (size_t)2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    const size_t o_over = (o_left + (size_t)3 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
@@ -860,7 +872,10 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     T.mapq_l = (const double *)(b + o_tab); T.subn = (const int *)(b + o_subn);
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
     int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
-    int *n_left = (int *)(b + o_misc + 24), *left = (int *)(b + o_left);
+    // three task lists of 2 n_pairs slots each: [0] band <= 15, [1] band <= 31, [2] traceback (filled by kernel 1 and
+    // appended to by the score-only kernels); counters n_list[0..2]
+    int *n_list = (int *)(b + o_misc + 32), *lists = (int *)(b + o_left);
+    const int64_t lstride = 2 * n_pairs;
     CigTask *tasks = (CigTask *)(b + o_tasks);
     const unsigned grid = (unsigned)((n_pairs + 127) / 128);
     static bool attr_set = false;
@@ -872,12 +887,14 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
     pair_decide_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, T, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns,
-                                             tasks, n_tasks);
+                                             tasks, n_tasks, lists, lstride, n_list);
     // score-only thread-per-task pass (two band classes: w <= 15 and 16..31), then traceback only where needed
     const unsigned cs_grid = (unsigned)(ctx->sm_count * 4);
-    cig_score_kernel<32><<<cs_grid, kCsT, 32 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, n_tasks, 0, 15, 31, d_alns, left, n_left);
-    cig_score_kernel<64><<<cs_grid, kCsT, 64 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, n_tasks, 16, 31, 31, d_alns, left, n_left);
-    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, left, n_left,
+    cig_score_kernel<32><<<cs_grid, kCsT, 32 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists, n_list,
+                                                                d_alns, lists + 2 * lstride, n_list + 2);
+    cig_score_kernel<64><<<cs_grid, kCsT, 64 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + lstride, n_list + 1,
+                                                                d_alns, lists + 2 * lstride, n_list + 2);
+    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 2 * lstride, n_list + 2,
                                                                           cursor, (uint8_t *)(b + o_over), d_alns, err);
     pair_finish_kernel<<<grid, 128, 0, st>>>(idx->v, T, n_pairs, d_regs, d_alns);
     qm_prof_end(ctx, QM_ST_PAIR, sp, st, 5);

@@ -7,6 +7,9 @@ struct IndexView {
     const uint8_t *refb;      // forward strand, one base code (0..3) per byte, contigs concatenated
     const uint4 *table;       // open addressing: {key lo, key hi, first, count}; empty = key all-ones
     const uint32_t *pos;      // occurrence lists (ascending forward positions)
+    const uint32_t *uniq;     // bit p: the k-mer starting at forward position p occurs exactly once in the reference
+                              // and its reverse complement does not occur at all (both look-ups of a read k-mer equal
+                              // to it are then known without touching the table)
     uint64_t mask;            // table size - 1
     int shift;                // 64 - log2(table size)
     int k, n_contigs;
@@ -16,7 +19,7 @@ struct IndexView {
 
 struct qm_index {
     IndexView v;
-    void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr;
+    void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr, *d_uniq = nullptr;
     int64_t n_kmers = 0, n_unique = 0, table_size = 0;
 };
 
