@@ -606,7 +606,7 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
     }
 }
 
-constexpr int64_t kSeBatch = 1 << 20;
+constexpr int64_t kSeBatch = 1 << 21;
 constexpr int kTailMinTasks = 8192;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
 
 struct SeScratch {

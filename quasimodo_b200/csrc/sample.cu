@@ -9,10 +9,11 @@
 // (bwa's per-chunk mem_pestat) is fixed ONCE per sample from the first min(n, 2^18) pairs handed in -- or
 // set by the caller (multi-GPU: rank 0's model is broadcast) -- so that results do not depend on how the
 // pair stream is split into batches or across GPUs.
+#include <vector>
 #include "pipeline.cuh"
 
 namespace {
-constexpr int64_t kChunkPairs = 1 << 19;
+constexpr int64_t kChunkPairs = 1 << 20;
 constexpr int64_t kPestatPairs = QM_PESTAT_PAIRS;
 }
 
@@ -182,10 +183,23 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
         s->stage_cap = need;
     }
     cudaStream_t cs = ctx->copy_stream, ks = ctx->own_stream;
-    const int64_t n_chunks = (n_pairs + kChunkPairs - 1) / kChunkPairs;
+    // chunk schedule: a small first chunk (its copy is the only one nothing can hide), then growing ones so that
+    // the kernels see large batches while every later copy runs under the previous chunk's kernels
+    std::vector<int64_t> starts, sizes;
+    {
+        const int64_t ramp[3] = { kChunkPairs / 4, kChunkPairs - kChunkPairs / 4, kChunkPairs };
+        int64_t p0 = 0;
+        for (int k = 0; p0 < n_pairs; ++k) {
+            int64_t n = ramp[k < 2 ? k : 2];
+            if (n > n_pairs - p0) n = n_pairs - p0;
+            starts.push_back(p0); sizes.push_back(n);
+            p0 += n;
+        }
+    }
+    const int64_t n_chunks = (int64_t)starts.size();
     auto enqueue_copy = [&](int64_t c) -> cudaError_t {
         const int b = (int)(c & 1);
-        const int64_t p0 = c * kChunkPairs, n = n_pairs - p0 < kChunkPairs ? n_pairs - p0 : kChunkPairs;
+        const int64_t p0 = starts[c], n = sizes[c];
         cudaError_t e;
         if ((e = cudaStreamWaitEvent(cs, s->ev_consumed[b], 0)) != cudaSuccess) return e;     // buffer b free again
         if ((e = cudaMemcpyAsync(s->d_stage[b], h_codes + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
@@ -197,7 +211,7 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
     QM_CUDA(ctx, enqueue_copy(0));
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
-        const int64_t p0 = c * kChunkPairs, n = n_pairs - p0 < kChunkPairs ? n_pairs - p0 : kChunkPairs;
+        const int64_t p0 = starts[c], n = sizes[c];
         if (c + 1 < n_chunks) QM_CUDA(ctx, enqueue_copy(c + 1));
         QM_CUDA(ctx, cudaStreamWaitEvent(ks, s->ev_copied[b], 0));
         int rc = sample_chunk(s, s->d_stage[b], s->d_stage[b] + seq_al, stride, (const int32_t *)(s->d_stage[b] + 2 * seq_al), n,
