@@ -681,167 +681,6 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
     }
 }
 
-// ---- kernel 2b (one THREAD per task): banded global DP WITH traceback for the tasks the score-only pass could not
-// finish (length difference, real gaps).  Same row/column loop plus the reference's direction byte per cell, written
-// to a global slab laid out [cell][thread] (a warp's stores for one cell are contiguous); the traceback walks the
-// thread's own bytes.  Only the first try is run here: if bwa's retry rule asks for a wider band, or the direction
-// matrix does not fit the slab, the task moves on to the warp-per-task kernel. ----
-constexpr size_t kTraceCellsPerThread = 16384;      // direction bytes per thread in the slab (rows x band columns)
-
-template <int B, int T>                // circular slots (power of two, 2w + 2 <= B), threads per block
-__global__ void __launch_bounds__(T)
-cig_trace_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
-                 const CigTask *__restrict__ tasks, const int *__restrict__ mine, const int *__restrict__ n_mine, int wmax,
-                 uint8_t *__restrict__ slab, qm_aln *__restrict__ alns, int *__restrict__ next, int *__restrict__ n_next)
-{
-    extern __shared__ int cs_smem[];
-    int *HS = cs_smem + threadIdx.x;
-    int *ES = cs_smem + B * T + threadIdx.x;
-    unsigned short *SS = (unsigned short *)(cs_smem + 2 * B * T) + threadIdx.x;
-    uint8_t *dir = slab + (size_t)blockIdx.x * T * kTraceCellsPerThread + threadIdx.x;      // dir[cell * T]
-    const int n = *n_mine;
-    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
-    for (int li = blockIdx.x * T + threadIdx.x; li < n; li += gridDim.x * T) {
-        const int ti = mine[li];
-        const CigTask t = tasks[ti];
-        qm_aln *rec = alns + t.read;
-        const int l_query = lens[t.read];
-        const int qb = rec->qb, qe = rec->qe;
-        const int lq = qe - qb, rlen = (int)(t.re - t.rb);
-        const int w = cig_band(o, t.w2, lq, rlen);
-        const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
-        if (w > wmax || (size_t)n_col * rlen > kTraceCellsPerThread || (t.rb < V.l_pac && t.re > V.l_pac) || lq <= 0 || rlen <= 0) {
-            next[atomicAdd(n_next, 1)] = ti;
-            continue;
-        }
-        SeqPair S;
-        S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
-        HS[0] = 0; ES[0] = QM_NEG_INF;
-        for (int j = 1; j <= lq && j <= w; ++j) { HS[(j & (B - 1)) * T] = -(o.o_ins + o.e_ins * j); ES[(j & (B - 1)) * T] = QM_NEG_INF; }
-        if (w + 1 <= lq) { HS[((w + 1) & (B - 1)) * T] = QM_NEG_INF; ES[((w + 1) & (B - 1)) * T] = QM_NEG_INF; }
-        for (int j = 0; j < lq && j <= w; ++j) {
-            int c = S.qb(j);
-            c = c > 4 ? 4 : c;
-            SS[(j & (B - 1)) * T] = (unsigned short)(c * 0x1111 + 0x8880);
-        }
-        for (int i = 0; i < rlen; ++i) {
-            const int tb = S.tb(i);
-            const int beg = i > w ? i - w : 0;
-            const int end = i + w + 1 < lq ? i + w + 1 : lq;
-            if (i > 0 && i + w < lq) {
-                int c = S.qb(i + w);
-                c = c > 4 ? 4 : c;
-                SS[((i + w) & (B - 1)) * T] = (unsigned short)(c * 0x1111 + 0x8880);
-            }
-            Lut L;
-            if (tb > 3) { L.lo = 0xffffffffu; L.hi = 0xffffffffu; }
-            else {
-                const unsigned mis = (unsigned)(-o.b) & 0xffu, mat = (unsigned)o.a & 0xffu;
-                unsigned v = mis * 0x01010101u;
-                v = (v & ~(0xffu << (8 * tb))) | (mat << (8 * tb));
-                L.lo = v; L.hi = 0xffffffffu;
-            }
-            int f = QM_NEG_INF;
-            int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : QM_NEG_INF;
-            uint8_t *drow = dir + ((size_t)i * n_col - beg) * T;
-            for (int j = beg; j < end; ++j) {
-                const int sl = (j & (B - 1)) * T;
-                int m = HS[sl], e = ES[sl];
-                HS[sl] = h1;
-                m += lut_score(L, SS[sl]);
-                uint8_t d = m >= e ? 0 : 1;
-                int h = m >= e ? m : e;
-                d = h >= f ? d : 2;
-                h = h >= f ? h : f;
-                h1 = h;
-                int tt = m - oe_del;
-                e -= o.e_del;
-                if (e > tt) d |= 1 << 2; else e = tt;
-                ES[sl] = e;
-                tt = m - oe_ins;
-                f -= o.e_ins;
-                if (f > tt) d |= 2 << 4; else f = tt;
-                drow[(size_t)j * T] = d;
-            }
-            const int sl = (end & (B - 1)) * T;
-            HS[sl] = h1; ES[sl] = QM_NEG_INF;
-        }
-        const int score = HS[(lq & (B - 1)) * T];
-        int w2c = t.w2;
-        if (w2c > o.w << 2) w2c = o.w << 2;
-        if (!(w2c == o.w << 2) && score < t.truesc - o.a) {      // bwa would retry with a doubled band
-            next[atomicAdd(n_next, 1)] = ti;
-            continue;
-        }
-        // traceback, CIGAR built back to front
-        uint32_t cig[QM_MAX_CIGAR];
-        int nc = 0;
-        bool overflow = false;
-        {
-            const int max_cigar = QM_MAX_CIGAR - 2;
-            int state = 0, i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1;
-            uint32_t cur = 0;
-            while (i >= 0 && k >= 0) {
-                const int lo = i > w ? i - w : 0;
-                state = dir[((size_t)i * n_col + (k - lo)) * T] >> (state << 1) & 3;
-                const uint32_t op = state == 0 ? 0u : (state == 1 ? 2u : 1u);
-                if (cur && (cur & 0xf) == op) cur += 1u << 4;
-                else {
-                    if (cur) { if (nc < max_cigar) cig[nc++] = cur; else overflow = true; }
-                    cur = 1u << 4 | op;
-                }
-                if (state == 0) { --i; --k; } else if (state == 1) --i; else --k;
-            }
-            for (int pass = 0; pass < 2; ++pass) {
-                const int len = pass == 0 ? i + 1 : k + 1;
-                const uint32_t op = pass == 0 ? 2u : 1u;
-                if (len <= 0) continue;
-                if (cur && (cur & 0xf) == op) cur += (uint32_t)len << 4;
-                else {
-                    if (cur) { if (nc < max_cigar) cig[nc++] = cur; else overflow = true; }
-                    cur = (uint32_t)len << 4 | op;
-                }
-            }
-            if (cur) { if (nc < max_cigar) cig[nc++] = cur; else overflow = true; }
-        }
-        if (overflow) {
-            rec->rid = -1; rec->pos = -1; rec->flag |= 0x4; rec->flag &= ~0x10; rec->n_cigar = 255; rec->nm = -1;
-            rec->score = 0; rec->sub = 0; rec->qb = 0; rec->qe = 0;
-            continue;
-        }
-        // cig[] is in reverse order: operation a of the forward CIGAR is cig[nc - 1 - a]
-        int nm = -1;
-        if (nc > 0) {
-            int x = 0, y = 0, n_mm = 0, n_gap = 0;
-            for (int a = 0; a < nc; ++a) {
-                const uint32_t c = cig[nc - 1 - a];
-                const int op = c & 0xf, len = (int)(c >> 4);
-                if (op == 0) { for (int u = 0; u < len; ++u) n_mm += S.qb(x + u) != S.tb(y + u); x += len; y += len; }
-                else if (op == 2) { if (a > 0 && a < nc - 1) n_gap += len; y += len; }
-                else if (op == 1) { x += len; n_gap += len; }
-            }
-            nm = n_mm + n_gap;
-        }
-        const bool is_rev = t.rb >= V.l_pac;
-        int64_t pos = t.rb < V.l_pac ? t.rb : 2 * V.l_pac - 1 - (t.re - 1);
-        int a0 = 0, a1 = nc;                        // forward-order slice [a0, a1) after squeezing a leading / trailing deletion
-        if (nc > 0) {
-            if ((cig[nc - 1] & 0xf) == 2) { pos += cig[nc - 1] >> 4; a0 = 1; }
-            else if ((cig[0] & 0xf) == 2) a1 = nc - 1;
-        }
-        int m = 0;
-        const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
-        if (clip5) rec->cigar[m++] = (uint32_t)clip5 << 4 | 4;
-        for (int a = a0; a < a1; ++a) rec->cigar[m++] = cig[nc - 1 - a];
-        if (clip3) rec->cigar[m++] = (uint32_t)clip3 << 4 | 4;
-        rec->n_cigar = (uint8_t)m;
-        const int rid = qm_pos2rid(V, pos);
-        rec->rid = rid;
-        rec->pos = (int32_t)(pos - V.off[rid]);
-        rec->nm = nm;
-    }
-}
-
 // ---- kernel 2 (one warp per task): banded global DP with traceback, bwa's band-doubling retry, NM, clips ----
 __global__ void __launch_bounds__(kCigWarps * 32)
 cigar_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
@@ -1021,12 +860,9 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
     const size_t o_tasks = o_misc + 256;
     const size_t o_left = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
-    const size_t o_over = (o_left + (size_t)6 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    const size_t o_over = (o_left + (size_t)4 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
     void *p = nullptr;
-    const int tr_blocks = ctx->sm_count * 2;                       // trace kernels: 2 blocks of 128 (band <= 31) / 64 threads per SM
-    const size_t slab_bytes = (size_t)tr_blocks * 128 * kTraceCellsPerThread;
-    const size_t o_slab = (o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp + 255) & ~(size_t)255;
-    int rc = qm_scratch_reserve(ctx, 5, o_slab + slab_bytes, &p);
+    int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
     char *b = (char *)p;
     QM_CUDA(ctx, cudaMemcpyAsync(b + o_tab, tab.data(), kMapqTabLen * 8, cudaMemcpyHostToDevice, st));
@@ -1039,7 +875,7 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
     int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
     // task lists of 2 n_pairs slots each: [0..2] score-only pass by band class, [3] needs traceback (filled by kernel 1,
-    // appended to by the score-only kernels), [4] what the trace kernel passes on; counters n_list[0..4]
+    // appended to by the score-only kernels); counters n_list[0..3]
     int *n_list = (int *)(b + o_misc + 32), *lists = (int *)(b + o_left);
     const int64_t lstride = 2 * n_pairs;
     CigTask *tasks = (CigTask *)(b + o_tasks);
@@ -1050,7 +886,6 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kCsT * 10));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * kCsT * 10));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * kCsT * 10));
-        QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 10));
         attr_set = true;
     }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
@@ -1065,14 +900,12 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
                                                                 d_alns, trace_list, n_trace);
     cig_score_kernel<72><<<cs_grid, kCsT, 72 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 2 * lstride, n_list + 2,
                                                                 d_alns, trace_list, n_trace);
-    // thread-per-task pass with traceback for narrow bands (<= 31); wider bands, retries and oversized direction
-    // matrices go to the warp-per-task kernel
-    cig_trace_kernel<64, 128><<<tr_blocks, 128, 64 * 128 * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, trace_list, n_trace,
-                                                                     31, (uint8_t *)(b + o_slab), d_alns, lists + 4 * lstride, n_list + 4);
-    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 4 * lstride, n_list + 4,
+    // everything that needs a traceback (length difference, real gaps, band-doubling retries): warp-per-task kernel.
+    // (A thread-per-task traceback variant was measured slower: too few such tasks to hide its per-task latency.)
+    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, trace_list, n_trace,
                                                                           cursor, (uint8_t *)(b + o_over), d_alns, err);
     pair_finish_kernel<<<grid, 128, 0, st>>>(idx->v, T, n_pairs, d_regs, d_alns);
-    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 7);
+    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 6);
     QM_CUDA(ctx, cudaGetLastError());
     int h_err = 0;
     QM_CUDA(ctx, cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st));
