@@ -171,6 +171,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     P, K, Wm = args.pairs, args.steps, args.warmup
     ctx = Context(local)                              # raises without the CUDA library / a B200: no CPU fallback

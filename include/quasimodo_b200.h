@@ -222,6 +222,7 @@ typedef struct {
 void qm_call_opt_default(qm_call_opt *o);
 int  qm_call_snps(qm_ctx *ctx, const qm_index *idx, const qm_call_opt *copt, const int32_t *d_counts, qm_call *d_calls,
                   int64_t max_calls, int64_t *h_n_calls, void *stream);
+int  qm_sample_call_snps_host(qm_sample *s, const qm_call_opt *copt, qm_call *h_calls, int64_t max_calls, int64_t *n_calls);
 
 /* ---- TP/FP/FN matcher (replaces the `fgrep -wf` / `fgrep -wvf` pipelines of
  * program/extract_TP_FP_SNPs.py:47-57 and the set arithmetic of scripts/caller_performance_compare.R:93-99) ----
@@ -231,6 +232,8 @@ int  qm_call_snps(qm_ctx *ctx, const qm_index *idx, const qm_call_opt *copt, con
  * NULL.  Asynchronous on `stream`. */
 int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, const uint64_t *d_truth_keys, int64_t n_truth,
                   uint8_t *d_call_flags, uint8_t *d_truth_flags, void *stream);
+int qm_eval_match_host(qm_ctx *ctx, const uint64_t *h_call_keys, int64_t n_call, const uint64_t *h_truth_keys, int64_t n_truth,
+                       uint8_t *h_call_flags, uint8_t *h_truth_flags /* may be NULL */);
 
 /* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
  * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,

@@ -98,6 +98,8 @@ SIGNATURES = {
     "qm_call_opt_default": (None, [_P]),
     "qm_call_snps": (C.c_int, [_P, _P, _P, _P, _P, _L, C.POINTER(C.c_int64), _P]),
     "qm_eval_match": (C.c_int, [_P, _P, _L, _P, _L, _P, _P, _P]),
+    "qm_eval_match_host": (C.c_int, [_P, _P, _L, _P, _L, _P, _P]),
+    "qm_sample_call_snps_host": (C.c_int, [_P, _P, _P, _L, C.POINTER(C.c_int64)]),
     "qm_profile_enable": (C.c_int, [_P, C.c_int]),
     "qm_profile_collect": (C.c_int, [_P, _P, _P]),
     "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),

@@ -202,4 +202,30 @@ int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, cons
     return QM_OK;
 }
 
+// same with host buffers: copies keys in, flags out; synchronous
+int qm_eval_match_host(qm_ctx *ctx, const uint64_t *h_call_keys, int64_t n_call, const uint64_t *h_truth_keys, int64_t n_truth,
+                       uint8_t *h_call_flags, uint8_t *h_truth_flags)
+{
+    if (!ctx || n_call < 0 || n_truth < 0 || (n_call > 0 && (!h_call_keys || !h_call_flags)) || (n_truth > 0 && !h_truth_keys))
+        return QM_EINVAL;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t kc = ((size_t)n_call * 8 + 255) & ~(size_t)255, kt = ((size_t)n_truth * 8 + 255) & ~(size_t)255;
+    const size_t fc = ((size_t)n_call + 255) & ~(size_t)255, ft = ((size_t)n_truth + 255) & ~(size_t)255;
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 11, kc + kt + fc + ft + 256, &p);
+    if (rc) return rc;
+    char *b = (char *)p;
+    uint64_t *dc = (uint64_t *)b, *dt = (uint64_t *)(b + kc);
+    uint8_t *dfc = (uint8_t *)(b + kc + kt), *dft = (uint8_t *)(b + kc + kt + fc);
+    cudaStream_t st = ctx->own_stream;
+    if (n_call) QM_CUDA(ctx, cudaMemcpyAsync(dc, h_call_keys, (size_t)n_call * 8, cudaMemcpyHostToDevice, st));
+    if (n_truth) QM_CUDA(ctx, cudaMemcpyAsync(dt, h_truth_keys, (size_t)n_truth * 8, cudaMemcpyHostToDevice, st));
+    rc = qm_eval_match(ctx, dc, n_call, dt, n_truth, dfc, h_truth_flags ? dft : nullptr, st);
+    if (rc) return rc;
+    if (n_call) QM_CUDA(ctx, cudaMemcpyAsync(h_call_flags, dfc, (size_t)n_call, cudaMemcpyDeviceToHost, st));
+    if (n_truth && h_truth_flags) QM_CUDA(ctx, cudaMemcpyAsync(h_truth_flags, dft, (size_t)n_truth, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    return QM_OK;
+}
+
 }  // extern "C"

@@ -257,4 +257,21 @@ int qm_sample_counts_host(qm_sample *s, int32_t *h_rows)
     return QM_OK;
 }
 
+// SNP calls of the sample to host memory (qm_call_snps on the sample's own tensor); synchronous
+int qm_sample_call_snps_host(qm_sample *s, const qm_call_opt *copt, qm_call *h_calls, int64_t max_calls, int64_t *n_calls)
+{
+    if (!s || !copt || !n_calls || max_calls < 0 || (max_calls > 0 && !h_calls)) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    QM_CUDA(ctx, cudaDeviceSynchronize());
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 10, (size_t)(max_calls > 0 ? max_calls : 1) * sizeof(qm_call), &p);
+    if (rc) return rc;
+    rc = qm_call_snps(ctx, s->idx, copt, s->d_counts, (qm_call *)p, max_calls, n_calls, ctx->own_stream);
+    if (rc) return rc;
+    QM_CUDA(ctx, cudaMemcpyAsync(h_calls, p, (size_t)*n_calls * sizeof(qm_call), cudaMemcpyDeviceToHost, ctx->own_stream));
+    QM_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+    return QM_OK;
+}
+
 }  // extern "C"
