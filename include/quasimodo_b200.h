@@ -235,6 +235,43 @@ int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, cons
 int qm_eval_match_host(qm_ctx *ctx, const uint64_t *h_call_keys, int64_t n_call, const uint64_t *h_truth_keys, int64_t n_truth,
                        uint8_t *h_call_flags, uint8_t *h_truth_flags /* may be NULL */);
 
+/* ---- coordinate sort (replaces the ordering of `samtools sort`, rules/bwa.smk:17; comparator bam1_lt of samtools
+ * bam_sort.c: (uint64)tid << 32 | (pos+1) << 1 | is_rev, unplaced (tid = -1) last, ties in input order) ----
+ * The key below orders records exactly like that comparator in as few bits as the reference needs: contig (unplaced
+ * = n_contigs) above pos+1 above the strand bit.  The sort is a stable LSD radix sort of (key, record index) pairs;
+ * records are not moved: the caller gathers through the permutation. */
+#ifdef __CUDACC__
+#define QM_INLINE_HD __host__ __device__
+#else
+#define QM_INLINE_HD
+#endif
+static inline QM_INLINE_HD int qm_sort_pos_bits(int64_t max_contig_len)
+{
+    int b = 1;
+    while (((int64_t)1 << b) <= max_contig_len + 1) ++b;         /* pos + 1 <= max_contig_len */
+    return b;
+}
+static inline QM_INLINE_HD int qm_sort_key_bits(int n_contigs, int pos_bits)
+{
+    int b = 1;
+    while ((1 << b) <= n_contigs) ++b;                            /* contig codes 0..n_contigs */
+    return b + pos_bits + 1;
+}
+static inline QM_INLINE_HD uint64_t qm_sort_key(int32_t rid, int32_t pos, int is_rev, int n_contigs, int pos_bits)
+{
+    return ((uint64_t)(uint32_t)(rid < 0 ? n_contigs : rid) << (pos_bits + 1)) | ((uint64_t)(uint32_t)(pos + 1) << 1) | (uint64_t)(is_rev != 0);
+}
+/* keys of device-resident records; *key_bits (may be NULL) receives the number of key bits in use */
+int qm_aln_sort_keys(qm_ctx *ctx, const qm_index *idx, const qm_aln *d_alns, int64_t n, uint64_t *d_keys, int *key_bits, void *stream);
+/* in place: d_keys sorted ascending (stable), d_vals[i] = input index of the record at sorted position i */
+int qm_sort_pairs(qm_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, int64_t n, int key_bits, void *stream);
+/* host keys in, permutation out; synchronous */
+int qm_sort_keys_host(qm_ctx *ctx, const uint64_t *h_keys, int64_t n, int key_bits, uint32_t *h_perm);
+
+/* page-locked host buffers for the driver (host<->device copies of qm_sample_add_pairs_host overlap the kernels) */
+int  qm_host_alloc(qm_ctx *ctx, size_t bytes, void **out);
+void qm_host_free(qm_ctx *ctx, void *p);
+
 /* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
  * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,
  * 4 pileup, 5 h2d, 6 d2h, 7 other.  qm_profile_collect synchronises the device and returns + clears the totals;

@@ -100,6 +100,11 @@ SIGNATURES = {
     "qm_eval_match": (C.c_int, [_P, _P, _L, _P, _L, _P, _P, _P]),
     "qm_eval_match_host": (C.c_int, [_P, _P, _L, _P, _L, _P, _P]),
     "qm_sample_call_snps_host": (C.c_int, [_P, _P, _P, _L, C.POINTER(C.c_int64)]),
+    "qm_aln_sort_keys": (C.c_int, [_P, _P, _P, _L, _P, C.POINTER(C.c_int), _P]),
+    "qm_sort_pairs": (C.c_int, [_P, _P, _P, _L, C.c_int, _P]),
+    "qm_sort_keys_host": (C.c_int, [_P, _P, _L, C.c_int, _P]),
+    "qm_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "qm_host_free": (None, [_P, _P]),
     "qm_profile_enable": (C.c_int, [_P, C.c_int]),
     "qm_profile_collect": (C.c_int, [_P, _P, _P]),
     "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),

@@ -1,0 +1,851 @@
+// qm_driver -- C++ host driver over the C-ABI (include/quasimodo_b200.h): the file-level drop-in for the
+// reference's read-level rules.  It owns no arithmetic of the hot path: alignment, counting, calling and the
+// coordinate sort all run in libquasimodo_b200.so on the B200; this file is file formats and plumbing.
+//
+//   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
+//                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf] [--gpu I] [-t THREADS] [-w BAND]
+//        = rules/bwa.smk:15-18 (bwa mem | samtools view | samtools sort | samtools index -> BAM + BAI),
+//          rules/vcfcall.smk:39 (pileup path: count TSV) and rules/vcfcall.smk:115-117 (VCF)
+//   qm_driver decontam --ref CONTAMINANT.fa[,MORE.fa] --r1 .. --r2 .. --out-r1 CLEAN1.fq --out-r2 CLEAN2.fq
+//                      [--keep-contigs N]
+//        = rules/decontamination.smk:15-17 / 43-48: keep the pairs whose BOTH records are unmapped
+//          ((flag & 12) == 12 && !(flag & 256)), re-emitted as FASTQ with /1 /2 names, as sequenced.
+//          With --keep-contigs N the first N contigs of the (concatenated) reference are the target genome and
+//          a pair is dropped iff a mate maps to a later (contaminant) contig: one pass instead of three.
+//   qm_driver bam-from-records --ref .. --r1 .. --r2 .. --alns ALNS.bin [--perm PERM.bin] --bam OUT.bam
+//        = the BAM/BAI writer alone on given qm_aln records (test entry; with --perm no GPU is touched)
+//
+// Exit status: 0 ok, 1 usage, 2 I/O or format error, 3 library/CUDA error (message on stderr), so a failing job
+// fails its Snakemake rule exactly like a failing `bwa`.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/quasimodo_b200.h"
+
+namespace {
+
+[[noreturn]] void die(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "qm_driver: ");
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    exit(code);
+}
+
+// ------------------------------------------------------------------------------------------------
+// line reader over zlib (reads plain and gzip files alike)
+struct LineReader {
+    gzFile f = nullptr;
+    std::string path;
+    std::vector<char> buf;
+    size_t pos = 0, len = 0;
+    explicit LineReader(const std::string &p) : path(p), buf(1 << 20)
+    {
+        f = gzopen(p.c_str(), "rb");
+        if (!f) die(2, "cannot open %s", p.c_str());
+        gzbuffer(f, 1 << 20);
+    }
+    ~LineReader() { if (f) gzclose(f); }
+    bool fill()
+    {
+        const int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n < 0) die(2, "read error in %s", path.c_str());
+        pos = 0; len = (size_t)n;
+        return n > 0;
+    }
+    // next line without the terminator; false at end of file
+    bool next(std::string &out)
+    {
+        out.clear();
+        bool got = false;
+        for (;;) {
+            if (pos == len && !fill()) return got;
+            got = true;
+            const char *s = buf.data() + pos;
+            const char *nl = (const char *)memchr(s, '\n', len - pos);
+            if (nl) {
+                out.append(s, nl - s);
+                pos += (size_t)(nl - s) + 1;
+                if (!out.empty() && out.back() == '\r') out.pop_back();
+                return true;
+            }
+            out.append(s, len - pos);
+            pos = len;
+        }
+    }
+};
+
+struct Genome {
+    std::vector<std::string> names;
+    std::vector<int64_t> lens, offs;
+    std::vector<uint8_t> codes;            // 0..3, contigs concatenated
+};
+
+void read_fasta(const std::string &path, Genome &g)
+{
+    LineReader rd(path);
+    std::string ln;
+    int8_t lut[256];
+    memset(lut, -1, sizeof lut);
+    lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+    bool open = false;
+    while (rd.next(ln)) {
+        if (ln.empty()) continue;
+        if (ln[0] == '>') {
+            if (open) g.lens.back() = (int64_t)g.codes.size() - g.offs.back();
+            size_t e = 1;
+            while (e < ln.size() && !isspace((unsigned char)ln[e])) ++e;
+            g.names.push_back(ln.substr(1, e - 1));      // bwa: name up to the first whitespace (.ann / .fai column 1)
+            g.offs.push_back((int64_t)g.codes.size());
+            g.lens.push_back(0);
+            open = true;
+        } else {
+            if (!open) die(2, "%s: sequence before the first '>' line", path.c_str());
+            for (char c : ln) {
+                const int8_t v = lut[(unsigned char)c];
+                if (v < 0) die(2, "%s: base '%c' in contig %s: only A/C/G/T references are supported (bwa would draw a random base)",
+                               path.c_str(), c, g.names.back().c_str());
+                g.codes.push_back((uint8_t)v);
+            }
+        }
+    }
+    if (open) g.lens.back() = (int64_t)g.codes.size() - g.offs.back();
+    if (g.names.empty()) die(2, "%s: no contigs", path.c_str());
+}
+
+// ------------------------------------------------------------------------------------------------
+// one batch of read pairs in the library's layout (reads 2i / 2i+1 are mates) + names
+struct Batch {
+    int64_t n_pairs = 0;
+    int32_t stride = 0;
+    uint8_t *codes = nullptr, *quals = nullptr;      // page-locked (qm_host_alloc)
+    int32_t *lens = nullptr;
+    qm_aln *alns = nullptr;
+    std::string names;                                // NUL-separated, one per pair
+    std::vector<uint32_t> name_off;
+};
+
+struct FastqPairReader {
+    LineReader r1, r2;
+    std::string h, s, p, q;
+    FastqPairReader(const std::string &a, const std::string &b) : r1(a), r2(b) {}
+    static bool record(LineReader &r, std::string &h, std::string &s, std::string &p, std::string &q)
+    {
+        if (!r.next(h)) return false;
+        while (h.empty()) if (!r.next(h)) return false;
+        if (h[0] != '@') die(2, "%s: FASTQ header expected, got '%.40s'", r.path.c_str(), h.c_str());
+        if (!r.next(s) || !r.next(p) || !r.next(q)) die(2, "%s: truncated FASTQ record", r.path.c_str());
+        if (p.empty() || p[0] != '+') die(2, "%s: '+' line expected", r.path.c_str());
+        if (s.size() != q.size()) die(2, "%s: sequence and quality lengths differ in %s", r.path.c_str(), h.c_str());
+        return true;
+    }
+    static std::string clean_name(const std::string &h)
+    {   // bwa: up to the first whitespace, a trailing /1 or /2 dropped
+        size_t e = 1;
+        while (e < h.size() && !isspace((unsigned char)h[e])) ++e;
+        std::string n = h.substr(1, e - 1);
+        if (n.size() > 2 && n[n.size() - 2] == '/' && (n.back() == '1' || n.back() == '2')) n.resize(n.size() - 2);
+        return n;
+    }
+};
+
+struct RawPair { std::string name, s[2], q[2]; };
+
+// reads up to max_pairs pairs; mates are matched by file order (bwa's rule), not by name
+bool read_batch(FastqPairReader &fr, int64_t max_pairs, std::vector<RawPair> &out)
+{
+    out.clear();
+    std::string h, s, p, q, h2;
+    while ((int64_t)out.size() < max_pairs) {
+        if (!FastqPairReader::record(fr.r1, h, s, p, q)) {
+            if (FastqPairReader::record(fr.r2, h2, s, p, q)) die(2, "%s has more records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
+            break;
+        }
+        RawPair rp;
+        rp.name = FastqPairReader::clean_name(h);
+        rp.s[0] = s; rp.q[0] = q;
+        if (!FastqPairReader::record(fr.r2, h2, s, p, q)) die(2, "%s has fewer records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
+        rp.s[1] = s; rp.q[1] = q;
+        out.push_back(std::move(rp));
+    }
+    return !out.empty();
+}
+
+struct Lib {
+    qm_ctx *ctx = nullptr;
+    void check(int rc, const char *what)
+    {
+        if (rc != QM_OK) die(3, "%s failed (%d): %s", what, rc, ctx ? qm_last_error(ctx) : "no context");
+    }
+};
+
+void pack_batch(Lib &L, const std::vector<RawPair> &raw, bool want_alns, Batch &b)
+{
+    static uint8_t lut[256];
+    static bool init = false;
+    if (!init) {
+        memset(lut, 4, sizeof lut);
+        lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+        init = true;
+    }
+    b.n_pairs = (int64_t)raw.size();
+    size_t mx = 1;
+    for (auto &r : raw) mx = std::max(mx, std::max(r.s[0].size(), r.s[1].size()));
+    if (mx > 500) die(2, "read of %zu bases: reads longer than 500 bp are not supported", mx);
+    b.stride = (int32_t)((mx + 15) & ~(size_t)15);
+    const size_t nb = (size_t)2 * b.n_pairs * b.stride;
+    void *p = nullptr;
+    L.check(qm_host_alloc(L.ctx, nb, &p), "qm_host_alloc"); b.codes = (uint8_t *)p;
+    L.check(qm_host_alloc(L.ctx, nb, &p), "qm_host_alloc"); b.quals = (uint8_t *)p;
+    L.check(qm_host_alloc(L.ctx, (size_t)2 * b.n_pairs * sizeof(int32_t), &p), "qm_host_alloc"); b.lens = (int32_t *)p;
+    if (want_alns) { L.check(qm_host_alloc(L.ctx, (size_t)2 * b.n_pairs * sizeof(qm_aln), &p), "qm_host_alloc"); b.alns = (qm_aln *)p; }
+    memset(b.codes, 4, nb);
+    memset(b.quals, 0, nb);
+    b.name_off.reserve(raw.size());
+    for (size_t i = 0; i < raw.size(); ++i) {
+        b.name_off.push_back((uint32_t)b.names.size());
+        b.names.append(raw[i].name);
+        b.names.push_back('\0');
+        for (int m = 0; m < 2; ++m) {
+            const std::string &s = raw[i].s[m], &q = raw[i].q[m];
+            uint8_t *c = b.codes + (2 * i + m) * b.stride, *qq = b.quals + (2 * i + m) * b.stride;
+            for (size_t j = 0; j < s.size(); ++j) {
+                c[j] = lut[(unsigned char)s[j]];
+                const int v = (int)(unsigned char)q[j] - 33;
+                qq[j] = (uint8_t)(v < 0 ? 0 : v > 93 ? 93 : v);
+            }
+            b.lens[2 * i + m] = (int32_t)s.size();
+        }
+    }
+}
+
+void free_batch(Lib &L, Batch &b)
+{
+    qm_host_free(L.ctx, b.codes); qm_host_free(L.ctx, b.quals); qm_host_free(L.ctx, b.lens); qm_host_free(L.ctx, b.alns);
+    b.codes = b.quals = nullptr; b.lens = nullptr; b.alns = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BGZF writer: blocks of <= 0xff00 bytes, raw deflate level 1, compressed by a thread team,
+// written in order; remembers each block's file offset so that virtual offsets can be resolved afterwards
+struct BgzfWriter {
+    static constexpr size_t kBlock = 0xff00;
+    FILE *fp = nullptr;
+    std::string path;
+    int threads = 1, level = 1;
+    std::vector<std::vector<uint8_t>> pending;
+    std::vector<uint8_t> cur;
+    std::vector<uint64_t> block_off;                  // file offset of every block written or pending
+    uint64_t file_off = 0;
+    size_t blocks_done = 0;
+    BgzfWriter(const std::string &p, int t, int lvl) : path(p), threads(t < 1 ? 1 : t), level(lvl)
+    {
+        fp = fopen(p.c_str(), "wb");
+        if (!fp) die(2, "cannot create %s", p.c_str());
+        cur.reserve(kBlock);
+    }
+    static void compress(const std::vector<uint8_t> &in, std::vector<uint8_t> &out, int level)
+    {
+        out.resize(18 + compressBound((uLong)in.size()) + 8 + 64);
+        static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        memcpy(out.data(), hdr, 16);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die(2, "deflateInit2 failed");
+        zs.next_in = (Bytef *)in.data(); zs.avail_in = (uInt)in.size();
+        zs.next_out = out.data() + 18; zs.avail_out = (uInt)(out.size() - 18 - 8);
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die(2, "deflate failed");
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const size_t total = 18 + clen + 8;
+        if (total > 65536) die(2, "BGZF block does not fit");
+        out[16] = (uint8_t)((total - 1) & 0xff); out[17] = (uint8_t)((total - 1) >> 8);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data(), (uInt)in.size()), isz = (uint32_t)in.size();
+        memcpy(out.data() + 18 + clen, &crc, 4);
+        memcpy(out.data() + 18 + clen + 4, &isz, 4);
+        out.resize(total);
+    }
+    void drain()
+    {
+        if (pending.empty()) return;
+        std::vector<std::vector<uint8_t>> outv(pending.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= pending.size()) break;
+                compress(pending[i], outv[i], level);
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, pending.size());
+        std::vector<std::thread> team;
+        for (int t = 1; t < nt; ++t) team.emplace_back(work);
+        work();
+        for (auto &t : team) t.join();
+        for (auto &o : outv) {
+            block_off.push_back(file_off);
+            if (fwrite(o.data(), 1, o.size(), fp) != o.size()) die(2, "write error on %s", path.c_str());
+            file_off += o.size();
+        }
+        blocks_done += pending.size();
+        pending.clear();
+    }
+    void close_block()
+    {
+        if (cur.empty()) return;
+        pending.push_back(cur);
+        cur.clear();
+        if (pending.size() >= (size_t)threads * 16) drain();
+    }
+    // index of the block the next byte goes to, and the offset inside it
+    void tell(uint64_t &block, uint32_t &off) const { block = blocks_done + pending.size(); off = (uint32_t)cur.size(); }
+    // keep a record inside one block when it fits in one (htslib's bgzf_flush_try)
+    void reserve(size_t n) { if (cur.size() + n > kBlock) close_block(); }
+    void write(const void *p, size_t n)
+    {
+        const uint8_t *s = (const uint8_t *)p;
+        while (n) {
+            const size_t k = std::min(n, kBlock - cur.size());
+            cur.insert(cur.end(), s, s + k);
+            s += k; n -= k;
+            if (cur.size() == kBlock) close_block();
+        }
+    }
+    void finish()
+    {
+        close_block();
+        drain();
+        static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        block_off.push_back(file_off);
+        if (fwrite(eof, 1, 28, fp) != 28 || fclose(fp) != 0) die(2, "write error on %s", path.c_str());
+        fp = nullptr;
+    }
+    uint64_t voffset(uint64_t block, uint32_t off) const { return (block_off[block] << 16) | off; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// BAM records + BAI
+inline int reg2bin(int64_t beg, int64_t end)
+{
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+struct RecRef {                       // one alignment record = (batch, read index inside the batch)
+    const Batch *b;
+    int64_t r;
+};
+
+struct BamIndexEntry { int32_t rid; int32_t beg, end; uint16_t bin; bool mapped; uint64_t blk0; uint32_t off0; uint64_t blk1; uint32_t off1; };
+
+inline void put32(std::vector<uint8_t> &v, uint32_t x) { uint8_t b[4]; memcpy(b, &x, 4); v.insert(v.end(), b, b + 4); }
+inline void put16(std::vector<uint8_t> &v, uint16_t x) { uint8_t b[2]; memcpy(b, &x, 2); v.insert(v.end(), b, b + 2); }
+
+void put_tag_int(std::vector<uint8_t> &v, const char *tag, int64_t x)
+{   // smallest fitting integer type, like htslib's bam_aux_append of SAM "i" values
+    v.push_back((uint8_t)tag[0]); v.push_back((uint8_t)tag[1]);
+    if (x >= 0) {
+        if (x <= 0xff) { v.push_back('C'); v.push_back((uint8_t)x); }
+        else if (x <= 0xffff) { v.push_back('S'); put16(v, (uint16_t)x); }
+        else { v.push_back('I'); put32(v, (uint32_t)x); }
+    } else {
+        if (x >= -128) { v.push_back('c'); v.push_back((uint8_t)(int8_t)x); }
+        else if (x >= -32768) { v.push_back('s'); put16(v, (uint16_t)(int16_t)x); }
+        else { v.push_back('i'); put32(v, (uint32_t)(int32_t)x); }
+    }
+}
+
+std::string cigar_string(const qm_aln &a)
+{
+    std::string s;
+    char tmp[16];
+    for (int k = 0; k < a.n_cigar; ++k) {
+        snprintf(tmp, sizeof tmp, "%u%c", a.cigar[k] >> 4, "MIDNSHP=X"[a.cigar[k] & 15]);
+        s += tmp;
+    }
+    return s;
+}
+
+int cigar_ref_len(const qm_aln &a)
+{
+    int n = 0;
+    for (int k = 0; k < a.n_cigar; ++k) { const int op = a.cigar[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) n += a.cigar[k] >> 4; }
+    return n;
+}
+
+// one BAM record into `out` (without the leading block_size); returns the reference span end for the index
+void encode_record(const Genome &g, const RecRef &rr, std::vector<uint8_t> &out, BamIndexEntry &ie)
+{
+    const Batch &b = *rr.b;
+    const int64_t r = rr.r;
+    const qm_aln &a = b.alns[r], &m = b.alns[r ^ 1];
+    const int l_seq = b.lens[r];
+    const uint8_t *codes = b.codes + r * b.stride, *quals = b.quals + r * b.stride;
+    const char *name = b.names.data() + b.name_off[r >> 1];
+    const size_t l_name = strlen(name) + 1;
+    const bool mapped = !(a.flag & 0x4);
+    const bool cig_ok = a.n_cigar != 255;
+    const int n_cig = mapped && cig_ok ? a.n_cigar : 0;
+    const int rlen = mapped ? cigar_ref_len(a) : 0;
+    const int64_t end = a.pos + (rlen > 0 ? rlen : 1);
+    const int bin = reg2bin(a.pos, end);
+    out.clear();
+    put32(out, (uint32_t)a.rid);
+    put32(out, (uint32_t)a.pos);
+    out.push_back((uint8_t)l_name);
+    out.push_back(a.mapq);
+    put16(out, (uint16_t)bin);
+    put16(out, (uint16_t)n_cig);
+    put16(out, a.flag);
+    put32(out, (uint32_t)l_seq);
+    put32(out, (uint32_t)a.mate_rid);
+    put32(out, (uint32_t)a.mate_pos);
+    put32(out, (uint32_t)a.tlen);
+    out.insert(out.end(), (const uint8_t *)name, (const uint8_t *)name + l_name);
+    for (int k = 0; k < n_cig; ++k) put32(out, a.cigar[k]);
+    // SEQ / QUAL as SAM stores them: reverse-complemented / reversed for reverse-strand records
+    const bool rev = (a.flag & 0x10) != 0 && mapped;
+    static const uint8_t nib[5] = {1, 2, 4, 8, 15};
+    std::vector<uint8_t> seq((size_t)l_seq);
+    for (int j = 0; j < l_seq; ++j) {
+        const uint8_t c = rev ? codes[l_seq - 1 - j] : codes[j];
+        seq[j] = rev ? (c < 4 ? (uint8_t)(3 - c) : 4) : c;
+    }
+    for (int j = 0; j < l_seq; j += 2) out.push_back((uint8_t)(nib[seq[j]] << 4 | (j + 1 < l_seq ? nib[seq[j + 1]] : 0)));
+    for (int j = 0; j < l_seq; ++j) out.push_back(rev ? quals[l_seq - 1 - j] : quals[j]);
+    // tags in bwa's order (mem_aln2sam): NM, MD (mapped), MC (mate mapped), AS, XS
+    if (n_cig > 0) {
+        put_tag_int(out, "NM", a.nm);
+        std::string md;
+        const uint8_t *ref = g.codes.data() + g.offs[a.rid] + a.pos;
+        int x = 0, y = 0, u = 0;
+        char tmp[16];
+        for (int k = 0; k < n_cig; ++k) {
+            const int op = a.cigar[k] & 15, len = (int)(a.cigar[k] >> 4);
+            if (op == 0) {
+                for (int i = 0; i < len; ++i) {
+                    if (seq[x + i] != ref[y + i]) { snprintf(tmp, sizeof tmp, "%d%c", u, "ACGTN"[ref[y + i]]); md += tmp; u = 0; }
+                    else ++u;
+                }
+                x += len; y += len;
+            } else if (op == 2) {
+                if (k > 0 && k < n_cig - 1) {                // bwa_gen_cigar2 ignores leading / trailing deletions
+                    snprintf(tmp, sizeof tmp, "%d^", u); md += tmp;
+                    for (int i = 0; i < len; ++i) md.push_back("ACGTN"[ref[y + i]]);
+                    u = 0;
+                }
+                y += len;
+            } else if (op == 1 || op == 4) x += len;
+        }
+        snprintf(tmp, sizeof tmp, "%d", u); md += tmp;
+        out.push_back('M'); out.push_back('D'); out.push_back('Z');
+        out.insert(out.end(), md.begin(), md.end()); out.push_back(0);
+    }
+    if (!(m.flag & 0x4) && m.n_cigar != 255 && m.n_cigar > 0) {
+        const std::string mc = cigar_string(m);
+        out.push_back('M'); out.push_back('C'); out.push_back('Z');
+        out.insert(out.end(), mc.begin(), mc.end()); out.push_back(0);
+    }
+    if (a.score >= 0) put_tag_int(out, "AS", a.score);
+    if (a.sub >= 0) put_tag_int(out, "XS", a.sub);
+    ie.rid = a.rid; ie.beg = a.pos; ie.end = (int32_t)end; ie.bin = (uint16_t)bin; ie.mapped = mapped;
+}
+
+void write_bai(const std::string &path, const Genome &g, const std::vector<BamIndexEntry> &ents, const BgzfWriter &bw)
+{
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) die(2, "cannot create %s", path.c_str());
+    auto w32 = [&](uint32_t x) { fwrite(&x, 4, 1, fp); };
+    auto w64 = [&](uint64_t x) { fwrite(&x, 8, 1, fp); };
+    fwrite("BAI\1", 1, 4, fp);
+    w32((uint32_t)g.names.size());
+    size_t e = 0;
+    uint64_t n_no_coor = 0;
+    for (size_t c = 0; c < g.names.size(); ++c) {
+        std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+        const size_t n_win = (size_t)((g.lens[c] + 16383) >> 14);
+        std::vector<uint64_t> lin(n_win, ~0ull);
+        uint64_t off_beg = ~0ull, off_end = 0, n_map = 0, n_unmap = 0;
+        int last_bin = -1;
+        for (; e < ents.size() && ents[e].rid == (int32_t)c; ++e) {
+            const BamIndexEntry &x = ents[e];
+            const uint64_t v0 = bw.voffset(x.blk0, x.off0), v1 = bw.voffset(x.blk1, x.off1);
+            auto &ch = bins[x.bin];
+            if (last_bin == (int)x.bin && !ch.empty()) ch.back().second = v1;       // consecutive records of one bin: one chunk
+            else ch.emplace_back(v0, v1);
+            last_bin = x.bin;
+            const size_t w0 = (size_t)(x.beg >> 14), w1 = (size_t)((x.end - 1) >> 14);
+            for (size_t w = w0; w <= w1 && w < n_win; ++w) if (lin[w] == ~0ull) lin[w] = v0;
+            if (off_beg == ~0ull) off_beg = v0;
+            off_end = v1;
+            if (x.mapped) ++n_map; else ++n_unmap;
+        }
+        size_t used = n_win;
+        while (used > 0 && lin[used - 1] == ~0ull) --used;
+        for (size_t w = 0; w < used; ++w) if (lin[w] == ~0ull) lin[w] = w ? lin[w - 1] : 0;
+        const bool any = off_beg != ~0ull;
+        w32((uint32_t)(bins.size() + (any ? 1 : 0)));
+        for (auto &kv : bins) {
+            w32(kv.first); w32((uint32_t)kv.second.size());
+            for (auto &ch : kv.second) { w64(ch.first); w64(ch.second); }
+        }
+        if (any) { w32(37450); w32(2); w64(off_beg); w64(off_end); w64(n_map); w64(n_unmap); }   // samtools' metadata pseudo-bin
+        w32((uint32_t)used);
+        for (size_t w = 0; w < used; ++w) w64(lin[w]);
+    }
+    for (; e < ents.size(); ++e) ++n_no_coor;
+    w64(n_no_coor);
+    if (fclose(fp) != 0) die(2, "write error on %s", path.c_str());
+}
+
+void write_bam(const std::string &path, const Genome &g, const std::vector<Batch> &batches, const std::vector<uint32_t> &perm,
+               const std::vector<int64_t> &batch_first_read, const std::string &cmdline, int threads)
+{
+    BgzfWriter bw(path, threads, 1);
+    std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
+    for (size_t c = 0; c < g.names.size(); ++c) text += "@SQ\tSN:" + g.names[c] + "\tLN:" + std::to_string(g.lens[c]) + "\n";
+    text += "@PG\tID:quasimodo_b200\tPN:quasimodo_b200\tVN:0.1\tCL:" + cmdline + "\n";
+    std::vector<uint8_t> hdr;
+    hdr.insert(hdr.end(), {'B', 'A', 'M', 1});
+    put32(hdr, (uint32_t)text.size());
+    hdr.insert(hdr.end(), text.begin(), text.end());
+    put32(hdr, (uint32_t)g.names.size());
+    for (size_t c = 0; c < g.names.size(); ++c) {
+        put32(hdr, (uint32_t)g.names[c].size() + 1);
+        hdr.insert(hdr.end(), g.names[c].begin(), g.names[c].end()); hdr.push_back(0);
+        put32(hdr, (uint32_t)g.lens[c]);
+    }
+    bw.write(hdr.data(), hdr.size());
+    bw.close_block();                                  // records start on a block boundary, as samtools writes them
+    std::vector<BamIndexEntry> ents(perm.size());
+    std::vector<uint8_t> rec;
+    for (size_t i = 0; i < perm.size(); ++i) {
+        const int64_t gr = perm[i];
+        const size_t bi = (size_t)(std::upper_bound(batch_first_read.begin(), batch_first_read.end(), gr) - batch_first_read.begin()) - 1;
+        RecRef rr{&batches[bi], gr - batch_first_read[bi]};
+        encode_record(g, rr, rec, ents[i]);
+        const uint32_t bs = (uint32_t)rec.size();
+        bw.reserve(rec.size() + 4);
+        bw.tell(ents[i].blk0, ents[i].off0);
+        bw.write(&bs, 4);
+        bw.write(rec.data(), rec.size());
+        bw.tell(ents[i].blk1, ents[i].off1);
+    }
+    bw.finish();
+    write_bai(path + ".bai", g, ents, bw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// text outputs: count TSV and caller VCF (B.4) -- same bytes as quasimodo_b200/formats.py
+void write_count_tsv(const std::string &path, const Genome &g, const std::vector<int32_t> &rows)
+{
+    FILE *fp = fopen(path.c_str(), "w");
+    if (!fp) die(2, "cannot create %s", path.c_str());
+    std::vector<char> buf(1 << 22);
+    setvbuf(fp, buf.data(), _IOFBF, buf.size());
+    fputs("chrom\tpos\tref\tdepth\tA_f\tC_f\tG_f\tT_f\tN_f\tdel_f\tA_r\tC_r\tG_r\tT_r\tN_r\tdel_r\tins_start\tdel_start\traw_depth\tread_starts\n", fp);
+    for (size_t c = 0; c < g.names.size(); ++c)
+        for (int64_t i = 0; i < g.lens[c]; ++i) {
+            const int32_t *r = rows.data() + (size_t)(g.offs[c] + i) * QM_NCH;
+            int64_t depth = 0;
+            for (int k = 0; k < 5; ++k) depth += r[k] + r[6 + k];
+            fprintf(fp, "%s\t%lld\t%c\t%lld", g.names[c].c_str(), (long long)(i + 1), "ACGT"[g.codes[g.offs[c] + i]], (long long)depth);
+            for (int k = 0; k < QM_NCH; ++k) fprintf(fp, "\t%d", r[k]);
+            fputc('\n', fp);
+        }
+    if (fclose(fp) != 0) die(2, "write error on %s", path.c_str());
+}
+
+std::string trim_float3(double x)
+{   // Python: f"{x:.3f}".rstrip("0").rstrip(".")
+    char tmp[64];
+    snprintf(tmp, sizeof tmp, "%.3f", x);
+    std::string s = tmp;
+    while (!s.empty() && s.back() == '0') s.pop_back();
+    if (!s.empty() && s.back() == '.') s.pop_back();
+    return s;
+}
+
+void write_vcf(const std::string &path, const Genome &g, const std::string &sample, const std::string &ref_path,
+               const std::vector<qm_call> &calls)
+{
+    FILE *fp = fopen(path.c_str(), "w");
+    if (!fp) die(2, "cannot create %s", path.c_str());
+    fprintf(fp, "##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n"
+                "##source=quasimodo_b200 (threshold caller on bcftools-mpileup-style counts; QUAL is not bcftools call QUAL)\n"
+                "##reference=file://%s\n", ref_path.c_str());
+    for (size_t c = 0; c < g.names.size(); ++c) fprintf(fp, "##contig=<ID=%s,length=%lld>\n", g.names[c].c_str(), (long long)g.lens[c]);
+    fprintf(fp, "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Raw read depth\">\n"
+                "##INFO=<ID=AF,Number=1,Type=Float,Description=\"Alternate allele fraction among bases passing the BQ filter\">\n"
+                "##INFO=<ID=DP4,Number=4,Type=Integer,Description=\"ref-forward, ref-reverse, alt-forward, alt-reverse bases\">\n"
+                "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+                "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n", sample.c_str());
+    for (const qm_call &c : calls)
+        fprintf(fp, "%s\t%d\t.\t%c\t%c\t%s\tPASS\tDP=%d;AF=%.3f;DP4=%d,%d,%d,%d\tGT\t1\n", g.names[c.rid].c_str(), c.pos + 1,
+                "ACGT"[c.ref], "ACGT"[c.alt], trim_float3((double)c.qual).c_str(), c.dp, (double)c.af, c.ad_ref_f, c.ad_ref_r, c.ad_alt_f, c.ad_alt_r);
+    if (fclose(fp) != 0) die(2, "write error on %s", path.c_str());
+}
+
+void write_fastq_pair(FILE *f1, FILE *f2, const Batch &b, int64_t pi)
+{
+    const char *name = b.names.data() + b.name_off[pi];
+    FILE *fs[2] = {f1, f2};
+    std::string s, q;
+    for (int m = 0; m < 2; ++m) {
+        const int64_t r = 2 * pi + m;
+        const int l = b.lens[r];
+        s.resize((size_t)l); q.resize((size_t)l);
+        for (int j = 0; j < l; ++j) { s[j] = "ACGTN"[b.codes[r * b.stride + j]]; q[j] = (char)(b.quals[r * b.stride + j] + 33); }
+        fprintf(fs[m], "@%s/%d\n%s\n+\n%s\n", name, m + 1, s.c_str(), q.c_str());   // bedtools bamtofastq: /1 /2 appended
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Args {
+    std::map<std::string, std::string> kv;
+    std::string get(const std::string &k, const std::string &d = "") const { auto it = kv.find(k); return it == kv.end() ? d : it->second; }
+    bool has(const std::string &k) const { return kv.count(k) != 0; }
+};
+
+Args parse_args(int argc, char **argv, int first)
+{
+    Args a;
+    for (int i = first; i < argc; ++i) {
+        std::string k = argv[i];
+        if (k.size() < 2 || k[0] != '-') die(1, "unexpected argument '%s'", k.c_str());
+        k = k.substr(k[1] == '-' ? 2 : 1);
+        if (i + 1 >= argc) die(1, "option --%s needs a value", k.c_str());
+        a.kv[k] = argv[++i];
+    }
+    return a;
+}
+
+std::vector<std::string> split(const std::string &s, char sep)
+{
+    std::vector<std::string> out;
+    size_t p = 0;
+    for (;;) {
+        const size_t q = s.find(sep, p);
+        out.push_back(s.substr(p, q == std::string::npos ? q : q - p));
+        if (q == std::string::npos) break;
+        p = q + 1;
+    }
+    return out;
+}
+
+void load_refs(const std::string &spec, Genome &g)
+{
+    for (auto &p : split(spec, ',')) read_fasta(p, g);
+    if (g.names.size() > QM_MAX_CONTIGS) die(2, "%zu contigs: at most %d are supported", g.names.size(), QM_MAX_CONTIGS);
+}
+
+int sort_key_bits(const Genome &g, int &pos_bits)
+{
+    int64_t mx = 0;
+    for (auto l : g.lens) mx = std::max(mx, l);
+    pos_bits = qm_sort_pos_bits(mx);
+    return qm_sort_key_bits((int)g.names.size(), pos_bits);
+}
+
+int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
+{
+    if (!a.has("ref") || !a.has("r1") || !a.has("r2")) die(1, "--ref, --r1 and --r2 are required");
+    const std::string bam = a.get("bam"), counts = a.get("counts"), vcf = a.get("vcf"), o1 = a.get("out-r1"), o2 = a.get("out-r2");
+    if (decontam && (o1.empty() || o2.empty())) die(1, "decontam needs --out-r1 and --out-r2");
+    const int threads = std::max(1, atoi(a.get("t", a.get("threads", "4")).c_str()));
+    // the insert-size model is fixed from the first QM_PESTAT_PAIRS pairs handed in: batches are never smaller than that,
+    // so the records do not depend on the batch size
+    const int64_t batch_pairs = std::max<int64_t>(QM_PESTAT_PAIRS, atoll(a.get("batch-pairs", "2000000").c_str()));
+    const int keep_contigs = atoi(a.get("keep-contigs", "0").c_str());
+    Genome g;
+    load_refs(a.get("ref"), g);
+    Lib L;
+    int rc = qm_ctx_create(atoi(a.get("gpu", "0").c_str()), &L.ctx);
+    if (rc != QM_OK) die(3, "qm_ctx_create failed (%d): no usable B200 (there is no CPU fallback)", rc);
+    qm_opt opt; qm_opt_default(&opt);
+    if (a.has("w")) opt.w = atoi(a.get("w").c_str());
+    if (a.has("k")) opt.min_seed_len = atoi(a.get("k").c_str());
+    qm_pileup_opt popt; qm_pileup_opt_default(&popt);
+    if (a.has("min-mapq")) popt.min_mapq = atoi(a.get("min-mapq").c_str());
+    if (a.has("min-bq")) popt.min_bq = atoi(a.get("min-bq").c_str());
+    qm_index *idx = nullptr;
+    L.check(qm_index_build(L.ctx, g.codes.data(), (int)g.names.size(), g.lens.data(), opt.min_seed_len, &idx), "qm_index_build");
+    qm_sample *smp = nullptr;
+    L.check(qm_sample_begin(L.ctx, idx, &opt, &popt, &smp), "qm_sample_begin");
+
+    const bool keep = !bam.empty() || decontam;       // records / reads needed after the batch loop
+    FastqPairReader fr(a.get("r1"), a.get("r2"));
+    std::vector<Batch> batches;
+    std::vector<int64_t> first_read;
+    std::vector<RawPair> raw;
+    int64_t n_pairs = 0, kept = 0;
+    FILE *f1 = nullptr, *f2 = nullptr;
+    if (decontam) {
+        f1 = fopen(o1.c_str(), "w"); f2 = fopen(o2.c_str(), "w");
+        if (!f1 || !f2) die(2, "cannot create %s / %s", o1.c_str(), o2.c_str());
+    }
+    while (read_batch(fr, batch_pairs, raw)) {
+        Batch b;
+        pack_batch(L, raw, keep, b);
+        raw.clear();
+        L.check(qm_sample_add_pairs_host(smp, b.codes, b.quals, b.stride, b.lens, b.n_pairs, n_pairs, b.alns), "qm_sample_add_pairs_host");
+        if (decontam) {
+            for (int64_t p = 0; p < b.n_pairs; ++p) {
+                const qm_aln &x = b.alns[2 * p], &y = b.alns[2 * p + 1];
+                bool ok;
+                if (keep_contigs > 0)      // fused pass: drop iff a mate sits on a contaminant contig
+                    ok = !(!(x.flag & 4) && x.rid >= keep_contigs) && !(!(y.flag & 4) && y.rid >= keep_contigs);
+                else                       // samtools view -f 12 -F 256 on each record
+                    ok = (x.flag & 12) == 12 && !(x.flag & 256) && (y.flag & 12) == 12 && !(y.flag & 256);
+                if (ok) { write_fastq_pair(f1, f2, b, p); ++kept; }
+            }
+        }
+        first_read.push_back(2 * n_pairs);
+        n_pairs += b.n_pairs;
+        if (!bam.empty()) batches.push_back(std::move(b));
+        else free_batch(L, b);
+    }
+    if (decontam) {
+        if (fclose(f1) != 0 || fclose(f2) != 0) die(2, "write error on the cleaned FASTQ files");
+        fprintf(stderr, "[qm_driver] decontam: %lld of %lld pairs kept\n", (long long)kept, (long long)n_pairs);
+    }
+    int64_t cells = 0;
+    L.check(qm_sample_stats_sync(smp, nullptr, &cells, nullptr), "qm_sample_stats_sync");
+    fprintf(stderr, "[qm_driver] %lld pairs aligned, %lld extension cells\n", (long long)n_pairs, (long long)cells);
+
+    if (!counts.empty()) {
+        std::vector<int32_t> rows(g.codes.size() * QM_NCH);
+        L.check(qm_sample_counts_host(smp, rows.data()), "qm_sample_counts_host");
+        write_count_tsv(counts, g, rows);
+    }
+    if (!vcf.empty()) {
+        qm_call_opt copt; qm_call_opt_default(&copt);
+        if (a.has("min-dp")) copt.min_dp = atoi(a.get("min-dp").c_str());
+        if (a.has("min-alt")) copt.min_alt = atoi(a.get("min-alt").c_str());
+        if (a.has("min-af")) copt.min_af = (float)atof(a.get("min-af").c_str());
+        std::vector<qm_call> calls(g.codes.size() * 3 + 16);                   // at most 3 alternative bases per position
+        int64_t nc = 0;
+        L.check(qm_sample_call_snps_host(smp, &copt, calls.data(), (int64_t)calls.size(), &nc), "qm_sample_call_snps_host");
+        calls.resize((size_t)nc);
+        write_vcf(vcf, g, a.get("sample", "sample"), split(a.get("ref"), ',')[0], calls);
+    }
+    if (!bam.empty()) {
+        // coordinate sort on the device: keys from the records, stable radix sort, gather through the permutation
+        int pos_bits = 0;
+        const int key_bits = sort_key_bits(g, pos_bits);
+        std::vector<uint64_t> keys((size_t)2 * n_pairs);
+        size_t k = 0;
+        for (auto &b : batches)
+            for (int64_t r = 0; r < 2 * b.n_pairs; ++r, ++k)
+                keys[k] = qm_sort_key(b.alns[r].rid, b.alns[r].pos, (b.alns[r].flag & 0x10) != 0, (int)g.names.size(), pos_bits);
+        std::vector<uint32_t> perm(keys.size());
+        L.check(qm_sort_keys_host(L.ctx, keys.data(), (int64_t)keys.size(), key_bits, perm.data()), "qm_sort_keys_host");
+        write_bam(bam, g, batches, perm, first_read, cmdline, threads);
+    }
+    for (auto &b : batches) free_batch(L, b);
+    qm_sample_destroy(smp);
+    qm_index_destroy(L.ctx, idx);
+    qm_ctx_destroy(L.ctx);
+    return 0;
+}
+
+template <class T> std::vector<T> read_binary(const std::string &path)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) die(2, "cannot open %s", path.c_str());
+    fseek(fp, 0, SEEK_END);
+    const long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (sz < 0 || (size_t)sz % sizeof(T)) die(2, "%s: size is not a multiple of %zu", path.c_str(), sizeof(T));
+    std::vector<T> v((size_t)sz / sizeof(T));
+    if (!v.empty() && fread(v.data(), sizeof(T), v.size(), fp) != v.size()) die(2, "read error in %s", path.c_str());
+    fclose(fp);
+    return v;
+}
+
+// the BAM/BAI writer alone: records given as a binary file of qm_aln (2 per pair, input order)
+int cmd_bam_from_records(const Args &a, const std::string &cmdline)
+{
+    if (!a.has("ref") || !a.has("r1") || !a.has("r2") || !a.has("alns") || !a.has("bam")) die(1, "--ref --r1 --r2 --alns --bam are required");
+    Genome g;
+    load_refs(a.get("ref"), g);
+    std::vector<qm_aln> alns = read_binary<qm_aln>(a.get("alns"));
+    FastqPairReader fr(a.get("r1"), a.get("r2"));
+    std::vector<RawPair> raw;
+    read_batch(fr, (int64_t)1 << 40, raw);
+    if (raw.size() * 2 != alns.size()) die(2, "%zu records for %zu pairs", alns.size(), raw.size());
+    // host-only path: plain memory instead of page-locked buffers, no context
+    Batch b;
+    b.n_pairs = (int64_t)raw.size();
+    size_t mx = 1;
+    for (auto &r : raw) mx = std::max(mx, std::max(r.s[0].size(), r.s[1].size()));
+    b.stride = (int32_t)mx;
+    std::vector<uint8_t> codes(2 * raw.size() * mx, 4), quals(2 * raw.size() * mx, 0);
+    std::vector<int32_t> lens(2 * raw.size());
+    static uint8_t lut[256];
+    memset(lut, 4, sizeof lut);
+    lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+    for (size_t i = 0; i < raw.size(); ++i) {
+        b.name_off.push_back((uint32_t)b.names.size());
+        b.names.append(raw[i].name); b.names.push_back('\0');
+        for (int m = 0; m < 2; ++m) {
+            const std::string &s = raw[i].s[m], &q = raw[i].q[m];
+            for (size_t j = 0; j < s.size(); ++j) { codes[(2 * i + m) * mx + j] = lut[(unsigned char)s[j]]; quals[(2 * i + m) * mx + j] = (uint8_t)(q[j] - 33); }
+            lens[2 * i + m] = (int32_t)s.size();
+        }
+    }
+    b.codes = codes.data(); b.quals = quals.data(); b.lens = lens.data(); b.alns = alns.data();
+    std::vector<uint32_t> perm;
+    if (a.has("perm")) perm = read_binary<uint32_t>(a.get("perm"));
+    else {
+        Lib L;
+        int rc = qm_ctx_create(atoi(a.get("gpu", "0").c_str()), &L.ctx);
+        if (rc != QM_OK) die(3, "qm_ctx_create failed (%d): no usable B200 (pass --perm to write a BAM without sorting)", rc);
+        int pos_bits = 0;
+        const int key_bits = sort_key_bits(g, pos_bits);
+        std::vector<uint64_t> keys(alns.size());
+        for (size_t r = 0; r < alns.size(); ++r) keys[r] = qm_sort_key(alns[r].rid, alns[r].pos, (alns[r].flag & 0x10) != 0, (int)g.names.size(), pos_bits);
+        perm.resize(keys.size());
+        L.check(qm_sort_keys_host(L.ctx, keys.data(), (int64_t)keys.size(), key_bits, perm.data()), "qm_sort_keys_host");
+        qm_ctx_destroy(L.ctx);
+    }
+    if (perm.size() != alns.size()) die(2, "permutation of %zu entries for %zu records", perm.size(), alns.size());
+    std::vector<Batch> batches;
+    batches.push_back(b);
+    write_bam(a.get("bam"), g, batches, perm, {0}, cmdline, std::max(1, atoi(a.get("t", "2").c_str())));
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records [options]   (%s)", qm_version());
+    std::string cmdline;
+    for (int i = 0; i < argc; ++i) { if (i) cmdline += ' '; cmdline += argv[i]; }
+    const std::string cmd = argv[1];
+    const Args a = parse_args(argc, argv, 2);
+    if (cmd == "sample") return cmd_sample(a, cmdline, false);
+    if (cmd == "decontam") return cmd_sample(a, cmdline, true);
+    if (cmd == "bam-from-records") return cmd_bam_from_records(a, cmdline);
+    die(1, "unknown command '%s'", cmd.c_str());
+}

@@ -19,6 +19,7 @@ def so():
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "quasimodo_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"static inline[^{]*\{.*?\n\}", "", text, flags=re.S)      # header-only helpers are not exports
     return sorted(set(re.findall(r"\b(qm_[a-z0-9_]+)\s*\(", text)))
 
 

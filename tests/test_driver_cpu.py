@@ -1,0 +1,135 @@
+"""CPU tests of the C++ host driver's file formats: the BAM + BAI writer is run on alignment
+records produced by the CPU oracle (`qm_driver bam-from-records --perm`, which touches no GPU) and read back with the
+test-side BAM reader; record order is checked against the restated samtools comparator (oracle/sort_py.py)."""
+import numpy as np
+import pytest
+
+from oracle import qmo_py, sort_py
+from quasimodo_b200 import workloads
+from tests import bamio, drvutil
+
+N_PAIRS = 500
+
+
+@pytest.fixture(scope="module")
+def case(tmp_path_factory):
+    d = tmp_path_factory.mktemp("drv")
+    ad, me = 229000, 235000
+    W = workloads.Workload("t", [("AD169", 1), ("Merlin", 10), ("Phix", 1), ("Ecoli", 1)], ["Merlin", "Phix"], N_PAIRS, 77,
+                           extra_weights=[40 * ad, 40 * me, 10 * me, 10 * me])
+    codes, quals, _, _ = W.simulate_host(0, N_PAIRS)
+    lens = np.full(2 * N_PAIRS, 150, np.int32)
+    lens[5] = 97                                    # ragged input
+    lens[10] = 60
+    codes[5, 97:] = 4
+    codes[10, 60:] = 4
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns, _, _, _ = qmo_py.run_sample(ref, codes, quals, lens)
+    names = drvutil.pair_names("sim.t", N_PAIRS)
+    fa, r1, r2 = str(d / "ref.fa"), str(d / "r1.fq.gz"), str(d / "r2.fq")
+    drvutil.write_fasta(W.ref, fa)
+    drvutil.write_fastq(codes, quals, lens, names, r1, str(d / "r2.tmp"), gz=True, comment=" 1:N:0")
+    drvutil.write_fastq(codes, quals, lens, names, str(d / "r1.tmp"), r2, gz=False)
+    perm = sort_py.sort_perm(alns)
+    alns.tofile(str(d / "alns.bin"))
+    perm.tofile(str(d / "perm.bin"))
+    bam = str(d / "out.bam")
+    drvutil.run_driver(["bam-from-records", "--ref", fa, "--r1", r1, "--r2", r2, "--alns", d / "alns.bin", "--perm", d / "perm.bin",
+                        "--bam", bam, "-t", 3])
+    return dict(W=W, codes=codes, quals=quals, lens=lens, alns=alns, names=names, perm=perm, bam=bamio.Bam(bam), bam_path=bam,
+                dir=d, fa=fa, r1=r1, r2=r2)
+
+
+def test_compact_key_orders_like_samtools():
+    """the library's compact sort key (include/quasimodo_b200.h: qm_sort_key) must order records exactly like the
+    literal samtools key, ties included"""
+    rng = np.random.default_rng(3)
+    n, n_contigs, max_len = 20000, 3, 5000
+    a = np.zeros(n, dtype=qmo_py.ALN_DTYPE)
+    a["rid"] = rng.integers(-1, n_contigs, n)
+    a["pos"] = np.where(a["rid"] >= 0, rng.integers(0, max_len, n), -1)
+    a["flag"] = rng.integers(0, 2, n) * 0x10
+    pos_bits = 1
+    while (1 << pos_bits) <= max_len + 1:
+        pos_bits += 1
+    rid = np.where(a["rid"] < 0, n_contigs, a["rid"]).astype(np.uint64)
+    compact = (rid << np.uint64(pos_bits + 1)) | ((a["pos"].astype(np.int64) + 1).astype(np.uint64) << np.uint64(1)) | \
+              ((a["flag"] & 0x10) != 0).astype(np.uint64)
+    assert np.array_equal(np.argsort(compact, kind="stable"), sort_py.sort_perm(a))
+    assert a["rid"][sort_py.sort_perm(a)][-1] == -1                  # unplaced records last
+
+
+def test_bam_header_and_order(case):
+    bam, W = case["bam"], case["W"]
+    assert bam.refs == list(zip(W.ref.names, W.ref.lens))
+    assert bam.text.startswith("@HD\tVN:1.6\tSO:coordinate\n")
+    assert [ln.split("\t")[1][3:] for ln in bam.text.split("\n") if ln.startswith("@SQ")] == W.ref.names
+    assert len(bam.records) == 2 * N_PAIRS
+    keys = [((r["rid"] & 0xffffffff) << 32) | ((r["pos"] + 1) << 1) | ((r["flag"] >> 4) & 1) for r in bam.records]
+    assert keys == sorted(keys)
+    assert any(r["rid"] == -1 for r in bam.records) and any(r["flag"] & 0x10 for r in bam.records)
+
+
+def test_bam_records_match_oracle(case):
+    assert drvutil.check_bam_records(case) > N_PAIRS
+
+
+def test_bai_finds_every_overlapping_record(case):
+    bam = case["bam"]
+    refs, n_no_coor = bamio.read_bai(case["bam_path"] + ".bai")
+    assert len(refs) == len(bam.refs)
+    assert n_no_coor == sum(1 for r in bam.records if r["rid"] == -1)
+    rng = np.random.default_rng(11)
+    spans = []
+    for r in bam.records:
+        rlen = sum(x >> 4 for x in r["cigar"] if (x & 15) in (0, 2))
+        spans.append((r["rid"], r["pos"], r["pos"] + max(rlen, 1)))
+    for rid, (name, ln) in enumerate(bam.refs):
+        bins, lin = refs[rid]
+        recs = [i for i, s in enumerate(spans) if s[0] == rid]
+        if not recs:
+            assert not bins
+            continue
+        meta = bins.pop(37450)
+        assert meta[1] == (sum(1 for i in recs if not bam.records[i]["flag"] & 4), sum(1 for i in recs if bam.records[i]["flag"] & 4))
+        # every record lies in exactly the chunk list of its own bin
+        for i in recs:
+            u = bam.records[i]["ustart"]
+            assert any(bam.voffset_to_u(b) <= u < bam.voffset_to_u(e) for b, e in bins[bam.records[i]["bin"]]), i
+        # linear index: the first record overlapping each 16 kb window
+        for w, v in enumerate(lin):
+            ov = [i for i in recs if spans[i][1] < (w + 1) << 14 and spans[i][2] > w << 14]
+            if ov:
+                assert bam.voffset_to_u(v) == bam.records[ov[0]]["ustart"], (rid, w)
+        # region queries through bins + linear index
+        for _ in range(20):
+            beg = int(rng.integers(0, ln))
+            end = min(ln, beg + int(rng.integers(1, 40000)))
+            want = {i for i in recs if spans[i][1] < end and spans[i][2] > beg}
+            lo = bam.voffset_to_u(lin[beg >> 14]) if (beg >> 14) < len(lin) else None
+            got = set()
+            for b in sort_py.reg2bins(beg, end):
+                for cb, ce in bins.get(b, []):
+                    ub, ue = bam.voffset_to_u(cb), bam.voffset_to_u(ce)
+                    got |= {i for i in recs if ub <= bam.records[i]["ustart"] < ue and (lo is None or bam.records[i]["uend"] > lo)}
+            assert want <= got, (rid, beg, end)
+
+
+def test_driver_rejects_bad_input(case):
+    d = case["dir"]
+    p = drvutil.run_driver(["bam-from-records", "--ref", case["fa"], "--r1", case["r1"], "--r2", str(d / "nope.fq"), "--alns", d / "alns.bin",
+                            "--perm", d / "perm.bin", "--bam", d / "x.bam"], check=False)
+    assert p.returncode == 2 and "cannot open" in p.stderr
+    short = str(d / "short.fq")
+    with open(case["r2"]) as fh, open(short, "w") as out:
+        out.writelines(fh.readlines()[:40])
+    p = drvutil.run_driver(["bam-from-records", "--ref", case["fa"], "--r1", case["r1"], "--r2", short, "--alns", d / "alns.bin",
+                            "--perm", d / "perm.bin", "--bam", d / "x.bam"], check=False)
+    assert p.returncode == 2 and "fewer records" in p.stderr
+    bad = str(d / "bad.fa")
+    open(bad, "w").write(">c1\nACGTNNACGT\n")
+    p = drvutil.run_driver(["bam-from-records", "--ref", bad, "--r1", case["r1"], "--r2", case["r2"], "--alns", d / "alns.bin",
+                            "--perm", d / "perm.bin", "--bam", d / "x.bam"], check=False)
+    assert p.returncode == 2 and "only A/C/G/T" in p.stderr
+    p = drvutil.run_driver(["frobnicate"], check=False)
+    assert p.returncode == 1

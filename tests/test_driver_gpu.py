@@ -1,0 +1,196 @@
+"""GPU tests of the file-level drop-in: the device radix sort against a stable argsort, and the C++
+driver end to end -- FASTQ in; sorted BAM + BAI, count TSV, VCF and cleaned FASTQ out -- against the CPU oracle's records
+ordered by the restated samtools comparator."""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from quasimodo_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n,bits", [(0, 24), (1, 24), (2, 8), (4095, 24), (4096, 13), (4097, 38), (100_003, 24), ((1 << 20) + 3, 64), (3_000_000, 30)])
+def test_radix_sort_is_a_stable_sort(ctx, n, bits):
+    from quasimodo_b200 import _lib
+    rng = np.random.default_rng(n + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, hi, n, dtype=np.uint64, endpoint=True)
+    if n > 10:                                       # long runs of equal keys: stability is the point
+        keys[rng.integers(0, n, n // 2)] = keys[0]
+        keys[: n // 4] = keys[: n // 4] & np.uint64(0xff)
+    perm = np.full(n, 0xffffffff, dtype=np.uint32)
+    rc = _lib.lib().qm_sort_keys_host(ctx._h, keys.ctypes.data, n, bits, perm.ctypes.data)
+    assert rc == 0, _lib.lib().qm_last_error(ctx._h)
+    assert np.array_equal(perm, np.argsort(keys, kind="stable").astype(np.uint32))
+
+
+def test_device_keys_match_header_formula(ctx):
+    import torch
+    from oracle import qmo_py, sort_py
+    from quasimodo_b200 import _lib, workloads
+    W = workloads.Workload("t", [("Merlin", 1), ("Phix", 1)], ["Merlin", "Phix"], 10, 1)
+    idx = ctx.index(W.ref, 31)
+    rng = np.random.default_rng(5)
+    n = 50_000
+    a = np.zeros(n, dtype=qmo_py.ALN_DTYPE)
+    a["rid"] = rng.integers(-1, 2, n)
+    a["pos"] = np.where(a["rid"] >= 0, rng.integers(0, 5000, n), -1)
+    a["flag"] = rng.integers(0, 2, n) * 0x10
+    d_alns = torch.from_numpy(a.view(np.uint8)).cuda()
+    d_keys = torch.empty(n, dtype=torch.int64, device="cuda")
+    d_perm = torch.empty(n, dtype=torch.int32, device="cuda")
+    bits = C.c_int()
+    L = _lib.lib()
+    assert L.qm_aln_sort_keys(ctx._h, idx._h, C.c_void_p(d_alns.data_ptr()), n, C.c_void_p(d_keys.data_ptr()), C.byref(bits), None) == 0
+    assert L.qm_sort_pairs(ctx._h, C.c_void_p(d_keys.data_ptr()), C.c_void_p(d_perm.data_ptr()), n, bits.value, None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_perm.cpu().numpy().view(np.uint32), sort_py.sort_perm(a))
+    k = d_keys.cpu().numpy()
+    assert (np.diff(k) >= 0).all()
+    idx.close()
+
+
+@pytest.fixture(scope="module")
+def sample_case(tmp_path_factory):
+    """3000 pairs of a 4-source mixture against Merlin|Phix (E. coli reads stay unmapped): oracle records + driver outputs"""
+    from oracle import qmo_py, sort_py
+    from quasimodo_b200 import workloads
+    from tests import bamio, drvutil
+    d = tmp_path_factory.mktemp("drvgpu")
+    n = 3000
+    me = 235000
+    W = workloads.Workload("t", [("AD169", 1), ("Merlin", 10), ("Phix", 1), ("Ecoli", 1)], ["Merlin", "Phix"], n, 78,
+                           extra_weights=[40 * me, 40 * me, 10 * me, 10 * me])
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    for r, l in ((3, 120), (8, 75), (2001, 149)):
+        lens[r] = l
+        codes[r, l:] = 4
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns, counts, cells, _ = qmo_py.run_sample(ref, codes, quals, lens)
+    names = drvutil.pair_names("sim.g", n)
+    fa, r1, r2 = str(d / "ref.fa"), str(d / "r1.fq.gz"), str(d / "r2.fq.gz")
+    drvutil.write_fasta(W.ref, fa)
+    drvutil.write_fastq(codes, quals, lens, names, r1, r2, gz=True)
+    bam, tsv, vcf = str(d / "s.bam"), str(d / "s.mpileup"), str(d / "s.vcf")
+    p = drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--bam", bam, "--counts", tsv, "--vcf", vcf, "--sample", "TM-1-1",
+                            "--min-dp", 3, "--min-alt", 2, "-t", 4])
+    return dict(W=W, n=n, codes=codes, quals=quals, lens=lens, alns=alns, counts=counts, cells=cells, names=names, perm=sort_py.sort_perm(alns),
+                bam=bamio.Bam(bam), bam_path=bam, tsv=tsv, vcf=vcf, fa=fa, r1=r1, r2=r2, dir=d, stderr=p.stderr)
+
+
+def test_driver_bam_matches_oracle_records_in_samtools_order(sample_case):
+    from tests import bamio, drvutil
+    assert f"{sample_case['n']} pairs aligned, {sample_case['cells']} extension cells" in sample_case["stderr"]
+    assert drvutil.check_bam_records(sample_case) > sample_case["n"]
+    refs, n_no_coor = bamio.read_bai(sample_case["bam_path"] + ".bai")
+    assert n_no_coor == int((sample_case["alns"]["rid"] < 0).sum()) > 0
+
+
+def test_driver_count_tsv_matches_oracle(sample_case):
+    W, counts = sample_case["W"], sample_case["counts"]
+    rows = [ln.rstrip("\n").split("\t") for ln in open(sample_case["tsv"])]
+    assert rows[0][:4] == ["chrom", "pos", "ref", "depth"] and len(rows) == 1 + W.ref.total
+    body = rows[1:]
+    got = np.array([[int(x) for x in r[4:]] for r in body], dtype=np.int32)
+    assert np.array_equal(got, counts)
+    assert [r[0] for r in body[:3]] == [W.ref.names[0]] * 3 and body[-1][0] == W.ref.names[-1]
+    assert body[0][1] == "1" and body[W.ref.lens[0]][1] == "1" and body[W.ref.lens[0] - 1][1] == str(W.ref.lens[0])
+    assert "".join(r[2] for r in body[:50]) == "".join("ACGT"[c] for c in W.ref.codes[:50])
+    depth = counts[:, 0:5].sum(1) + counts[:, 6:11].sum(1)
+    assert [int(r[3]) for r in body] == depth.tolist()
+
+
+def test_driver_vcf_matches_python_writer(ctx, sample_case, tmp_path):
+    from quasimodo_b200 import _lib, formats
+    W = sample_case["W"]
+    idx = ctx.index(W.ref, 31)
+    s = ctx.sample(idx)
+    s.add_pairs_host(sample_case["codes"], sample_case["quals"], sample_case["lens"])
+    copt = _lib.default_call_opt()
+    copt.min_dp, copt.min_alt = 3, 2
+    calls = s.call_snps(copt)
+    assert len(calls) > 20
+    want = str(tmp_path / "py.vcf")
+    formats.write_vcf(want, W.ref, "TM-1-1", calls)
+    a = [ln for ln in open(want) if not ln.startswith("##reference")]
+    b = [ln for ln in open(sample_case["vcf"]) if not ln.startswith("##reference")]
+    assert a == b
+    s.close()
+    idx.close()
+
+
+def test_driver_batches_do_not_change_the_outputs(tmp_path):
+    """70,000 pairs in batches of 65,536 (2 batches) and in one batch: identical records and counts"""
+    from quasimodo_b200 import workloads
+    from tests import bamio, drvutil
+    n = 70_000
+    W = workloads.config1(n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    fa, r1, r2 = str(tmp_path / "ref.fa"), str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    drvutil.write_fasta(W.ref, fa)
+    drvutil.write_fastq(codes, quals, lens, drvutil.pair_names("p", n), r1, r2)
+    outs = []
+    for tag, bp in (("a", 65536), ("b", 1 << 20)):
+        bam, tsv = str(tmp_path / f"{tag}.bam"), str(tmp_path / f"{tag}.tsv")
+        drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--bam", bam, "--counts", tsv, "--batch-pairs", bp])
+        data = b"".join(d for _, d in bamio.bgzf_blocks(bam))
+        l_text = int.from_bytes(data[4:8], "little")
+        outs.append((data[8 + l_text:], open(tsv, "rb").read()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert len(outs[0][0]) > 2 * n * 200
+
+
+def test_driver_decontam(sample_case):
+    """rules/decontamination.smk:15-17: pairs with both records unmapped against the contaminant survive, in input order"""
+    from oracle import qmo_py
+    from quasimodo_b200 import genomes
+    from tests import drvutil
+    d = sample_case["dir"]
+    phix = genomes.load("Phix")
+    pfa = str(d / "phix.fa")
+    drvutil.write_fasta(phix, pfa)
+    o1, o2 = str(d / "clean1.fq"), str(d / "clean2.fq")
+    drvutil.run_driver(["decontam", "--ref", pfa, "--r1", sample_case["r1"], "--r2", sample_case["r2"], "--out-r1", o1, "--out-r2", o2])
+    ref = qmo_py.Ref(phix.codes, phix.lens, k=31)
+    alns, _, _, _ = qmo_py.run_sample(ref, sample_case["codes"], sample_case["quals"], sample_case["lens"])
+    f = alns["flag"].reshape(-1, 2)
+    keep = np.flatnonzero((((f & 12) == 12) & ((f & 256) == 0)).all(1))
+    assert 0 < len(keep) < sample_case["n"]
+
+    def expect(m):
+        out = []
+        for p in keep:
+            r = 2 * p + m
+            L = sample_case["lens"][r]
+            out += [f"@{sample_case['names'][p]}/{m + 1}", "".join("ACGTN"[c] for c in sample_case["codes"][r, :L]), "+",
+                    "".join(chr(q + 33) for q in sample_case["quals"][r, :L])]
+        return out
+    assert open(o1).read().split("\n")[:-1] == expect(0)
+    assert open(o2).read().split("\n")[:-1] == expect(1)
+    # fused pass: Merlin is the target (first contig), PhiX the contaminant -> drop pairs with a mate mapped on PhiX
+    drvutil.run_driver(["decontam", "--ref", sample_case["fa"], "--keep-contigs", 1, "--r1", sample_case["r1"], "--r2", sample_case["r2"],
+                        "--out-r1", o1, "--out-r2", o2])
+    a = sample_case["alns"].reshape(-1, 2)
+    on_phix = (((a["flag"] & 4) == 0) & (a["rid"] >= 1)).any(1)
+    got = [ln[1:-3] for ln in open(o1) if ln.startswith("@sim.g.")]
+    assert got == [sample_case["names"][p] for p in np.flatnonzero(~on_phix)]
+
+
+def test_driver_fails_loudly_without_outputs(tmp_path, sample_case):
+    from tests import drvutil
+    p = drvutil.run_driver(["sample", "--ref", sample_case["fa"], "--r1", sample_case["r1"]], check=False)
+    assert p.returncode == 1
+    p = drvutil.run_driver(["sample", "--ref", sample_case["fa"], "--r1", sample_case["r1"], "--r2", sample_case["r2"], "--gpu", 99], check=False)
+    assert p.returncode == 3 and "no usable B200" in p.stderr
