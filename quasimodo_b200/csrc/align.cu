@@ -309,6 +309,7 @@ struct RoundCounters {        // zeroed before every advance round; the host rea
     int pad[6];
     int hist[512];            // tasks per query length (counting sort of the task lists by qlen)
     int offs[512];            // running output offsets of the scatter pass, relative to the class's list
+    int fb[2 * kExtCtr];      // fallback lists of the paired extension kernel: counts, then cursors
 };
 constexpr size_t kRoundHeader = (2 * kExtCtr + 8) * sizeof(int);
 
@@ -625,7 +626,7 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     const size_t o_st = take((size_t)nb * sizeof(ReadState));
     const size_t o_tasks = take((size_t)nb * sizeof(ExtTaskI));
     const size_t o_res = take((size_t)nb * sizeof(qm_ext_result));
-    const size_t o_lists = take((size_t)nb * kExtClasses * 4);
+    const size_t o_lists = take((size_t)nb * kExtClasses * 4 * 2);      // class lists, then the fallback lists
     const size_t o_ctr = take(sizeof(RoundCounters));
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 3, off, &p);
@@ -713,7 +714,7 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             int n_launch = 0;
             for (int c = 0; c < kExtClasses; ++c) n_launch += h_ctr->class_count[c] > 0;
             rc = qm_ext_launch_classes(ctx, P, idx->v, sc.tasks, sc.lists, nb, sc.ctr->class_count, sc.ctr->class_cursor,
-                                       h_ctr->class_count, sc.res, st);
+                                       h_ctr->class_count, sc.res, sc.lists + (int64_t)kExtClasses * nb, sc.ctr->fb, st);
             qm_prof_end(ctx, QM_ST_EXTEND, sp, st, n_launch);
             if (rc) { cudaFreeHost(h_ctr); return rc; }
         }

@@ -10,6 +10,7 @@
 // (band, (m,mj), z-drop, to-end score, zero-span trimming) are warp-uniform, computed from three
 // REDUX reductions.  Cell arithmetic uses the Blackwell DPX instructions
 // (__viaddmax_s32_relu / __vimax3_s32 / __viaddmax_s32); no tensor cores: this is not a contraction.
+#include <stdlib.h>
 #include "pipeline.cuh"
 #include "ext_warp.cuh"
 
@@ -99,7 +100,7 @@ void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, 
 
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
-                          const int *h_counts, qm_ext_result *d_out, cudaStream_t st)
+                          const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st)
 {
     // A class with many tasks goes to the thread-per-task kernel (extend2.cu: high throughput, but one task is a
     // long serial chain, ~0.3 ms); a class with few tasks (the tail rounds of mem_chain2aln, where only reads with
@@ -112,7 +113,24 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
         cudaStream_t sc = ctx->side[c];
         QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
         const bool big = c < 9 && (!h_counts || h_counts[c] >= kThreadPerTaskMin);
-        if (big) {
+        // The paired kernel (extend2p.cu) is bit-exact and 10 % faster than the scalar one on wide synthetic tasks, but on
+        // the pipeline's own tasks (rows of ~45 columns, ~85 rows) its per-row bookkeeping for two tasks eats the gain:
+        // measured 1.7x SLOWER per class launch (profiles/r01_v8_paired_vs_scalar.md).  Off unless QM_PAIRED is set.
+        static const bool paired = getenv("QM_PAIRED") != nullptr;
+        if (big && c < 8 && d_fb_lists && d_fb_ctr && paired) {
+            // two tasks per thread; what the packed arithmetic cannot hold (N in the query, scores above 255) comes back
+            // through the fallback list and runs on the scalar thread-per-task kernel right behind it
+            const int hc = h_counts ? h_counts[c] : -1;
+            int rc = qm_ext2p_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, hc, d_out, d_fb_lists, d_fb_ctr, sc);
+            if (rc) return rc;
+            // (few tasks, and a thread-per-task chain would add its full latency behind the paired kernel: warp per task)
+            switch (c) {
+            case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+            case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+            case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+            default: launch_class<5>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+            }
+        } else if (big) {
             int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc);
             if (rc) return rc;
         } else {
@@ -142,16 +160,17 @@ int qm_extend_launch(qm_ctx *ctx, const qm_opt *opt, const uint8_t *d_seq, const
     void *p = nullptr;
     const size_t task_bytes = (size_t)n * sizeof(ExtTaskI);
     const size_t list_bytes = (size_t)kNumClasses * n * sizeof(int);
-    int rc = qm_scratch_reserve(ctx, 0, task_bytes + list_bytes + 64 * sizeof(int), &p);
+    int rc = qm_scratch_reserve(ctx, 0, task_bytes + 2 * list_bytes + 128 * sizeof(int), &p);
     if (rc) return rc;
     ExtTaskI *itasks = (ExtTaskI *)p;
     int *lists = (int *)((char *)p + task_bytes);
-    int *ctrs = (int *)((char *)p + task_bytes + list_bytes);     // [0..9] counts, [16..25] cursors, [32] err
-    QM_CUDA(ctx, cudaMemsetAsync(ctrs, 0, 64 * sizeof(int), st));
+    int *fb_lists = (int *)((char *)p + task_bytes + list_bytes);
+    int *ctrs = (int *)((char *)p + task_bytes + 2 * list_bytes);     // [0..9] counts, [16..25] cursors, [32] err, [64..95] fallback
+    QM_CUDA(ctx, cudaMemsetAsync(ctrs, 0, 128 * sizeof(int), st));
     const int tpb = 256;
     ext_classify_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_tasks, d_seq, n, itasks, lists, ctrs, d_out, ctrs + 32);
     IndexView V = {};
-    return qm_ext_launch_classes(ctx, qm_ext_params(opt), V, itasks, lists, n, ctrs, ctrs + kExtCtr, nullptr, d_out, st);
+    return qm_ext_launch_classes(ctx, qm_ext_params(opt), V, itasks, lists, n, ctrs, ctrs + kExtCtr, nullptr, d_out, fb_lists, ctrs + 64, st);
 }
 
 extern "C" {
