@@ -45,7 +45,8 @@ __device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
 // without changing the result: when the previous k-mer had exactly one hit, at forward reference position p, and the
 // new read base continues that match, the new k-mer EQUALS the reference k-mer next to p; if the index says that
 // k-mer is unique and its reverse complement absent (IndexView::uniq), both look-ups are known: one hit, there.
-__device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S)
+__device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
+                             const uint32_t *__restrict__ sbloom /* V.bloom, or NULL */)
 {
     const int k = V.k;
     const uint32_t occ_cap = (uint32_t)(o.max_occ < QM_OCC_CAP ? o.max_occ : QM_OCC_CAP);
@@ -94,6 +95,15 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
                 const int rb = trk_pass ? 3 - V.refb[p2] : V.refb[p2 + k - 1];
                 if (rb == c) { add_hit(trk_pass, p2, q, true); trk_p = p2; continue; }
             }
+        }
+        if (sbloom) {
+            // a k-mer whose canonical form misses the filter occurs on neither strand: no table probe (the common case
+            // for the k - 1 k-mers that cover a mismatch)
+            uint32_t bp[3];
+            qm_bloom_pos(fw < rc ? fw : rc, V.bloom_bits, bp);
+            const uint32_t hit = (__ldg(&sbloom[bp[0] >> 5]) >> (bp[0] & 31)) & (__ldg(&sbloom[bp[1] >> 5]) >> (bp[1] & 31)) &
+                                 (__ldg(&sbloom[bp[2] >> 5]) >> (bp[2] & 31)) & 1u;
+            if (!hit) { trk_p = -1; continue; }
         }
         int n_hits = 0, one_pass = 0;
         int64_t one_p = -1;
@@ -246,7 +256,9 @@ __device__ int build_plan(const IndexView &V, const qm_opt &o, const qm_seed *S,
     return np;
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kSeedThreads = 128;
+
+__global__ void __launch_bounds__(kSeedThreads)
 seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
                   int64_t n, qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds, uint16_t *__restrict__ plan,
                   uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only)
@@ -254,7 +266,9 @@ seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int 
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n) return;
     qm_seed *S = seeds + r * QM_MAX_SEEDS;
-    const int ns = collect_seeds(V, o, codes + r * stride, lens[r], S);
+    // the filter is read through L1/L2 (a copy in shared memory was measured: the 208 KB carve-out shrinks L1 to the point
+    // where the byte-wise read loads and the chaining scratch thrash -- 16.3 -> 23.8 ms per 4 M reads)
+    const int ns = collect_seeds(V, o, codes + r * stride, lens[r], S, V.bloom_bits ? V.bloom : nullptr);
     n_seeds[r] = ns;
     if (seeds_only) return;
     const int np = build_plan(V, o, S, ns, plan + r * QM_MAX_SEEDS);
@@ -262,6 +276,16 @@ seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int 
     ReadState s;
     s.cursor = 0; s.phase = PH_NEXT; s.n_av = 0; s.task = -1;
     st[r] = s;
+}
+
+static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_opt &o, const uint8_t *codes, int stride, const int32_t *lens,
+                                     int64_t n, qm_seed *seeds, int32_t *n_seeds, uint16_t *plan, uint8_t *n_plan, ReadState *st,
+                                     bool seeds_only, cudaStream_t stream)
+{
+    (void)ctx;
+    seed_chain_kernel<<<(unsigned)((n + kSeedThreads - 1) / kSeedThreads), kSeedThreads, 0, stream>>>(V, o, codes, stride, lens, n, seeds, n_seeds,
+                                                                                                 plan, n_plan, st, seeds_only);
+    return cudaGetLastError();
 }
 
 // ---- mem_sort_dedup_patch without mem_patch_reg (stable sorts) ----
@@ -650,10 +674,8 @@ int qm_collect_seeds(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const 
     if (opt->min_seed_len != idx->v.k) return qm_fail(ctx, QM_EINVAL, "index built with k=%d but min_seed_len=%d", idx->v.k, opt->min_seed_len);
     if (n_reads == 0) return QM_OK;
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int tpb = 128;
-    seed_chain_kernel<<<(unsigned)((n_reads + tpb - 1) / tpb), tpb, 0, (cudaStream_t)stream>>>(
-        idx->v, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true);
-    QM_CUDA(ctx, cudaGetLastError());
+    QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true,
+                                   (cudaStream_t)stream));
     return QM_OK;
 }
 
@@ -681,8 +703,7 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
         const uint8_t *codes = d_codes + b0 * stride;
         const int32_t *lens = d_lens + b0;
         int sp = qm_prof_begin(ctx, QM_ST_SEED, st);
-        seed_chain_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan,
-                                                sc.n_plan, sc.st, false);
+        QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
         qm_prof_end(ctx, QM_ST_SEED, sp, st, 1);
         for (int round = 0; round < 4 * QM_MAX_REGS + 8; ++round) {
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);

@@ -48,8 +48,10 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         if (i == 0 || km[i].first != km[i - 1].first) ++n_unique;
     }
     ix->n_unique = n_unique;
+    // load factor <= 0.25 while the table stays L2-sized (a miss then ends after ~1.4 probes instead of ~2.5), else <= 0.5
     int bits = 4;
     while ((1ll << bits) < 2 * n_unique) ++bits;
+    if ((16ll << (bits + 1)) <= (64ll << 20)) ++bits;
     const int64_t tsize = 1ll << bits;
     ix->table_size = tsize;
     std::vector<uint4> table((size_t)tsize, make_uint4(0xffffffffu, 0xffffffffu, 0, 0));
@@ -89,7 +91,32 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
             i = j;
         }
     }
+    // Bloom filter over canonical k-mers: a read k-mer whose canonical form is not in the filter occurs on neither strand,
+    // and the seeding kernel answers that from shared memory instead of probing the table twice through L2.  Sized at
+    // >= 7 bits per distinct k-mer (3 hashes: ~4 % false positives) within the shared-memory budget, else no filter.
+    std::vector<uint32_t> bloom;
+    v.bloom_bits = 0;
+    if (n_unique * 7 <= (int64_t)kBloomMaxBytes * 8) {
+        const uint32_t bbits = kBloomMaxBytes * 8;
+        bloom.assign(bbits / 32, 0u);
+        for (size_t i = 0; i < km.size(); ++i) {
+            if (i && km[i].first == km[i - 1].first) continue;
+            const uint64_t key = km[i].first;
+            uint64_t rc = 0;
+            for (int b = 0; b < k; ++b) rc |= (uint64_t)(3 - ((key >> (2 * b)) & 3)) << (2 * (k - 1 - b));
+            uint32_t p[3];
+            qm_bloom_pos(key < rc ? key : rc, bbits, p);
+            for (int t = 0; t < 3; ++t) bloom[p[t] >> 5] |= 1u << (p[t] & 31);
+        }
+        v.bloom_bits = bbits;
+    }
     cudaError_t e;
+    if (!bloom.empty() && ((e = cudaMalloc(&ix->d_bloom, bloom.size() * 4)) != cudaSuccess ||
+                           (e = cudaMemcpy(ix->d_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)) {
+        qm_index_destroy(ctx, ix);
+        return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
+    }
+    v.bloom = (const uint32_t *)ix->d_bloom;
     if ((e = cudaMalloc(&ix->d_uniq, uniq.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_uniq, uniq.data(), uniq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
@@ -115,6 +142,7 @@ void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
     if (ix->d_table) cudaFree(ix->d_table);
     if (ix->d_pos) cudaFree(ix->d_pos);
     if (ix->d_uniq) cudaFree(ix->d_uniq);
+    if (ix->d_bloom) cudaFree(ix->d_bloom);
     delete ix;
 }
 

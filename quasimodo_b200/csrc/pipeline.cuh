@@ -10,6 +10,8 @@ struct IndexView {
     const uint32_t *uniq;     // bit p: the k-mer starting at forward position p occurs exactly once in the reference
                               // and its reverse complement does not occur at all (both look-ups of a read k-mer equal
                               // to it are then known without touching the table)
+    const uint32_t *bloom;    // Bloom filter over the canonical (min of k-mer and its reverse complement) reference k-mers,
+    uint32_t bloom_bits;      // 3 hash functions; 0 bits = no filter (reference too large for a shared-memory filter)
     uint64_t mask;            // table size - 1
     int shift;                // 64 - log2(table size)
     int k, n_contigs;
@@ -19,7 +21,7 @@ struct IndexView {
 
 struct qm_index {
     IndexView v;
-    void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr, *d_uniq = nullptr;
+    void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr, *d_uniq = nullptr, *d_bloom = nullptr;
     int64_t n_kmers = 0, n_unique = 0, table_size = 0;
 };
 
@@ -34,6 +36,16 @@ static __device__ __forceinline__ int qm_pos2rid(const IndexView &V, int64_t fpo
         if (fpos >= V.off[c] && fpos < V.off[c] + V.len[c]) r = c;
     return r;
 }
+// the three bit positions of a canonical k-mer in a filter of `bits` bits (same on host and device)
+static __host__ __device__ __forceinline__ void qm_bloom_pos(uint64_t canon, uint32_t bits, uint32_t p[3])
+{
+    const uint64_t h = canon * 0x9E3779B97F4A7C15ull;
+    const uint32_t a = (uint32_t)(h >> 32), b = (uint32_t)h, c = a ^ (b >> 9) ^ (b << 23);
+    p[0] = (uint32_t)(((uint64_t)a * bits) >> 32);
+    p[1] = (uint32_t)(((uint64_t)b * bits) >> 32);
+    p[2] = (uint32_t)(((uint64_t)c * bits) >> 32);
+}
+constexpr uint32_t kBloomMaxBytes = 208 * 1024;          // shared-memory budget of the seeding kernel's filter
 static __device__ __forceinline__ bool qm_idx_lookup(const IndexView &V, uint64_t key, uint32_t &first, uint32_t &cnt)
 {
     uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> V.shift;
