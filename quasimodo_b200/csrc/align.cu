@@ -42,18 +42,99 @@ __device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
 
 // ---- seeding: all maximal exact matches of length >= k on both strands ----
 // Every k-mer of the read is looked up on both strands (oracle: qmo_collect_seeds).  Most look-ups are avoided
-// without changing the result: when the previous k-mer had exactly one hit, at forward reference position p, and the
-// new read base continues that match, the new k-mer EQUALS the reference k-mer next to p; if the index says that
-// k-mer is unique and its reverse complement absent (IndexView::uniq), both look-ups are known: one hit, there.
+// without changing the result:
+//  * when the previous k-mer had exactly one hit, at forward reference position p, and the next read base continues
+//    that match, the next k-mer EQUALS the reference k-mer next to p; if the index says that k-mer is unique and its
+//    reverse complement absent (IndexView::uniqp), both look-ups are known: one hit, there.  This is decided for 32
+//    positions at a time: read, reference and bitmap are 2-bit / 1-bit packed, one XOR + count-trailing-zeros gives
+//    the length of the continuing run;
+//  * a k-mer whose canonical form misses the Bloom filter occurs on neither strand.
+// The read is packed once into shared memory (2 bits per base + an N bitmap); k-mers are cut out of the packed words,
+// so no rolling state ties one position to the next and whole runs can be skipped.
+constexpr int kSeedThreads = 128;
+
+struct PackedRead {                 // per-thread view of the block's shared arrays, [word][thread]
+    uint64_t *bits;                 // base j at bits 2*(j&31) of word j>>5
+    uint64_t *nmask;                // bit j&63 of word j>>6: base j is N
+    __device__ __forceinline__ uint64_t get2(int b) const
+    {   // 32 bases starting at base b (words past the read are zero)
+        const int w = b >> 5, sh = 2 * (b & 31);
+        const uint64_t lo = bits[w * kSeedThreads];
+        return sh ? (lo >> sh) | (bits[(w + 1) * kSeedThreads] << (64 - sh)) : lo;
+    }
+    __device__ __forceinline__ uint64_t getn(int b) const
+    {   // N flags of 64 bases starting at base b
+        const int w = b >> 6, sh = b & 63;
+        const uint64_t lo = nmask[w * kSeedThreads];
+        return sh ? (lo >> sh) | (nmask[(w + 1) * kSeedThreads] << (64 - sh)) : lo;
+    }
+};
+
+// reverse the order of the 32 two-bit groups of x
+__device__ __forceinline__ uint64_t grouprev(uint64_t x)
+{
+    const uint64_t y = __brevll(x);
+    return ((y >> 1) & 0x5555555555555555ull) | ((y & 0x5555555555555555ull) << 1);
+}
+
+__device__ __forceinline__ uint64_t ref_get2(const IndexView &V, int64_t b)
+{   // 32 reference bases starting at forward position b >= -32
+    const int64_t x = b + 32;
+    const uint64_t *w = V.ref2p + (x >> 5);
+    const int sh = 2 * (int)(x & 31);
+    const uint64_t lo = __ldg(w);
+    return sh ? (lo >> sh) | (__ldg(w + 1) << (64 - sh)) : lo;
+}
+__device__ __forceinline__ uint32_t uniq_get(const IndexView &V, int64_t b)
+{   // uniqueness flags of the 32 k-mers starting at forward positions b .. b+31, b >= -32
+    const int64_t x = b + 32;
+    const uint32_t *w = V.uniqp + (x >> 5);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (unsigned)(x & 31));
+}
+
+__device__ void pack_read(const uint8_t *__restrict__ rd, int len, int n_words, int n_nwords, PackedRead &R)
+{
+    for (int w = 0; w < n_words; ++w) R.bits[w * kSeedThreads] = 0;
+    for (int w = 0; w < n_nwords; ++w) R.nmask[w * kSeedThreads] = 0;
+    uint64_t acc = 0, nacc = 0;
+    int j = 0;
+    auto put = [&](unsigned c) {
+        acc |= (uint64_t)(c & 3u) << (2 * (j & 31));
+        nacc |= (uint64_t)(c >> 2) << (j & 63);
+        ++j;
+        if ((j & 31) == 0) { R.bits[((j >> 5) - 1) * kSeedThreads] = acc; acc = 0; }
+        if ((j & 63) == 0) { R.nmask[((j >> 6) - 1) * kSeedThreads] = nacc; nacc = 0; }
+    };
+    // head bytes up to 4-byte alignment, then whole words (4 bases per load), then the tail
+    while (j < len && ((uintptr_t)(rd + j) & 3u)) put(rd[j]);
+    while (j + 4 <= len) {
+        const uint32_t w4 = *(const uint32_t *)(rd + j);
+        // gather the four 2-bit codes / the four N flags (code 4) with one multiply each
+        const uint32_t c4 = ((w4 & 0x03030303u) * 0x01041040u) >> 24;
+        const uint32_t n4 = (((w4 >> 2) & 0x01010101u) * 0x10204080u) >> 28;
+        if ((j & 31) <= 28 && (j & 63) <= 60) {
+            acc |= (uint64_t)c4 << (2 * (j & 31));
+            nacc |= (uint64_t)n4 << (j & 63);
+            j += 4;
+            if ((j & 31) == 0) { R.bits[((j >> 5) - 1) * kSeedThreads] = acc; acc = 0; }
+            if ((j & 63) == 0) { R.nmask[((j >> 6) - 1) * kSeedThreads] = nacc; nacc = 0; }
+        } else {
+            put(w4 & 0xffu); put((w4 >> 8) & 0xffu); put((w4 >> 16) & 0xffu); put(w4 >> 24);
+        }
+    }
+    while (j < len) put(rd[j]);
+    if (j & 31) R.bits[(j >> 5) * kSeedThreads] = acc;
+    if (j & 63) R.nmask[(j >> 6) * kSeedThreads] = nacc;
+}
+
 __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
-                             const uint32_t *__restrict__ sbloom /* V.bloom, or NULL */)
+                             const uint32_t *__restrict__ bloom /* V.bloom, or NULL */, PackedRead &R, int n_words, int n_nwords)
 {
     const int k = V.k;
     const uint32_t occ_cap = (uint32_t)(o.max_occ < QM_OCC_CAP ? o.max_occ : QM_OCC_CAP);
     const uint64_t mask = k < 32 ? ((1ull << (2 * k)) - 1) : ~0ull;
-    const int top = 2 * (k - 1);
-    uint64_t fw = 0, rc = 0;
-    int valid = 0, n = 0;
+    const uint64_t kbits = k < 64 ? ((1ull << k) - 1) : ~0ull;
+    int n = 0;
     int64_t trk_p = -1;             // forward position of the previous k-mer's only hit, -1 = none / several
     int trk_pass = 0;               // its strand: 0 = read k-mer as is, 1 = reverse complement
     // the seed each strand is currently growing lives in registers (a clean read extends ONE seed ~120 times);
@@ -82,28 +163,65 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
             cur_len[pass] = k; cur_idx[pass] = n++; cur_diag[pass] = diag; cur_qnext[pass] = q + 1;
         }
     };
-    for (int i = 0; i < len; ++i) {
-        const int c = rd[i];
-        if (c > 3) { valid = 0; fw = rc = 0; trk_p = -1; continue; }
-        fw = ((fw << 2) | (uint64_t)c) & mask;
-        rc = (rc >> 2) | ((uint64_t)(3 - c) << top);
-        if (++valid < k) continue;
-        const int q = i - k + 1;
+    pack_read(rd, len, n_words, n_nwords, R);
+    const int q_last = len - k;                         // last k-mer start
+    int q = 0;
+    while (q <= q_last) {
         if (trk_p >= 0) {
-            const int64_t p2 = trk_pass ? trk_p - 1 : trk_p + 1;
-            if (p2 >= 0 && p2 + k <= V.l_pac && ((__ldg(&V.uniq[p2 >> 5]) >> (p2 & 31)) & 1u)) {
-                const int rb = trk_pass ? 3 - V.refb[p2] : V.refb[p2 + k - 1];
-                if (rb == c) { add_hit(trk_pass, p2, q, true); trk_p = p2; continue; }
+            // how many of the positions q, q+1, ... continue the unique match of position q-1 (at most 32 per step)
+            const int nb = q + k - 1;                   // index of the first new read base
+            const uint64_t rbits = R.get2(nb);
+            const uint32_t nbits = (uint32_t)R.getn(nb);
+            uint64_t refbits;
+            uint32_t ub;
+            int64_t lim;
+            if (!trk_pass) {
+                refbits = ref_get2(V, trk_p + k);
+                ub = uniq_get(V, trk_p + 1);
+                lim = V.l_pac - k - trk_p;              // positions p+1 .. l_pac-k
+            } else {
+                refbits = ~grouprev(ref_get2(V, trk_p - 32));
+                ub = __brev(uniq_get(V, trk_p - 32));
+                lim = trk_p;                            // positions p-1 .. 0
             }
+            const uint64_t x = rbits ^ refbits;
+            const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+            int m = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
+            const int m_n = nbits ? __ffs((int)nbits) - 1 : 32;
+            const int m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
+            m = m < m_n ? m : m_n;
+            m = m < m_u ? m : m_u;
+            if ((int64_t)m > lim) m = (int)lim;
+            if (m > q_last - q + 1) m = q_last - q + 1;
+            if (m > 0) {
+                const int64_t rpos = trk_pass ? 2 * V.l_pac - trk_p - k : trk_p;        // of the hit at q-1
+                if (cur_idx[trk_pass] >= 0 && cur_diag[trk_pass] == rpos - (q - 1) && cur_qnext[trk_pass] == q) {
+                    cur_len[trk_pass] += m; cur_qnext[trk_pass] += m;
+                }
+                trk_p = trk_pass ? trk_p - m : trk_p + m;
+                q += m;
+                if (m == 32) continue;
+                if (q > q_last) break;
+            }
+            // position q does not continue the match: the general path below decides
         }
-        if (sbloom) {
+        const uint64_t nm = R.getn(q) & kbits;
+        if (nm) {                                       // an N inside the k-mer: skip every k-mer that covers it
+            trk_p = -1;
+            q += 64 - __clzll((long long)nm);
+            continue;
+        }
+        const uint64_t v = R.get2(q) & mask;            // first base in the lowest bits
+        const uint64_t fw = grouprev(v) >> (64 - 2 * k);  // first base in the highest bits: the table's key order
+        const uint64_t rc = ~v & mask;                  // reverse complement in the same order
+        if (bloom) {
             // a k-mer whose canonical form misses the filter occurs on neither strand: no table probe (the common case
             // for the k - 1 k-mers that cover a mismatch)
             uint32_t bp[3];
             qm_bloom_pos(fw < rc ? fw : rc, V.bloom_bits, bp);
-            const uint32_t hit = (__ldg(&sbloom[bp[0] >> 5]) >> (bp[0] & 31)) & (__ldg(&sbloom[bp[1] >> 5]) >> (bp[1] & 31)) &
-                                 (__ldg(&sbloom[bp[2] >> 5]) >> (bp[2] & 31)) & 1u;
-            if (!hit) { trk_p = -1; continue; }
+            const uint32_t hit = (__ldg(&bloom[bp[0] >> 5]) >> (bp[0] & 31)) & (__ldg(&bloom[bp[1] >> 5]) >> (bp[1] & 31)) &
+                                 (__ldg(&bloom[bp[2] >> 5]) >> (bp[2] & 31)) & 1u;
+            if (!hit) { trk_p = -1; ++q; continue; }
         }
         int n_hits = 0, one_pass = 0;
         int64_t one_p = -1;
@@ -120,6 +238,7 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
             n_hits += (int)cnt;
         }
         if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; } else trk_p = -1;
+        ++q;
     }
     flush();
     for (int i = 1; i < n; ++i) {       // order: (qbeg, rbeg)
@@ -256,19 +375,21 @@ __device__ int build_plan(const IndexView &V, const qm_opt &o, const qm_seed *S,
     return np;
 }
 
-constexpr int kSeedThreads = 128;
-
 __global__ void __launch_bounds__(kSeedThreads)
 seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
                   int64_t n, qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds, uint16_t *__restrict__ plan,
-                  uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only)
+                  uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only, int n_words, int n_nwords)
 {
+    extern __shared__ uint64_t s_read[];            // [n_words][threads] packed bases, then [n_nwords][threads] N flags
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n) return;
+    PackedRead R;
+    R.bits = s_read + threadIdx.x;
+    R.nmask = s_read + (size_t)n_words * kSeedThreads + threadIdx.x;
     qm_seed *S = seeds + r * QM_MAX_SEEDS;
     // the filter is read through L1/L2 (a copy in shared memory was measured: the 208 KB carve-out shrinks L1 to the point
-    // where the byte-wise read loads and the chaining scratch thrash -- 16.3 -> 23.8 ms per 4 M reads)
-    const int ns = collect_seeds(V, o, codes + r * stride, lens[r], S, V.bloom_bits ? V.bloom : nullptr);
+    // where the chaining scratch thrashes -- 16.3 -> 23.8 ms per 4 M reads)
+    const int ns = collect_seeds(V, o, codes + r * stride, lens[r], S, V.bloom_bits ? V.bloom : nullptr, R, n_words, n_nwords);
     n_seeds[r] = ns;
     if (seeds_only) return;
     const int np = build_plan(V, o, S, ns, plan + r * QM_MAX_SEEDS);
@@ -283,8 +404,11 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
                                      bool seeds_only, cudaStream_t stream)
 {
     (void)ctx;
-    seed_chain_kernel<<<(unsigned)((n + kSeedThreads - 1) / kSeedThreads), kSeedThreads, 0, stream>>>(V, o, codes, stride, lens, n, seeds, n_seeds,
-                                                                                                 plan, n_plan, st, seeds_only);
+    // packed read: one word per 32 bases + one spare (windows may start at the last base), N flags per 64 bases + one spare
+    const int n_words = (stride + 31) / 32 + 2, n_nwords = (stride + 63) / 64 + 2;
+    const size_t smem = (size_t)(n_words + n_nwords) * kSeedThreads * sizeof(uint64_t);
+    seed_chain_kernel<<<(unsigned)((n + kSeedThreads - 1) / kSeedThreads), kSeedThreads, smem, stream>>>(
+        V, o, codes, stride, lens, n, seeds, n_seeds, plan, n_plan, st, seeds_only, n_words, n_nwords);
     return cudaGetLastError();
 }
 

@@ -91,6 +91,13 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
             i = j;
         }
     }
+    // padded 2-bit reference and padded uniqueness bitmap for the seeding kernel's 32-bases-at-a-time match extension
+    std::vector<uint64_t> ref2p((size_t)(total + 32 + 31) / 32 + 2, 0ull);
+    std::vector<uint32_t> uniqp((size_t)(total + 32 + 31) / 32 + 2, 0u);
+    for (int64_t x = 0; x < total; ++x) {
+        ref2p[(size_t)(x + 32) >> 5] |= (uint64_t)h_codes[x] << (2 * ((x + 32) & 31));
+        if ((uniq[x >> 5] >> (x & 31)) & 1u) uniqp[(size_t)(x + 32) >> 5] |= 1u << ((x + 32) & 31);
+    }
     // Bloom filter over canonical k-mers: a read k-mer whose canonical form is not in the filter occurs on neither strand,
     // and the seeding kernel answers that from shared memory instead of probing the table twice through L2.  Sized at
     // >= 7 bits per distinct k-mer (3 hashes: ~4 % false positives) within the shared-memory budget, else no filter.
@@ -117,6 +124,14 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
     }
     v.bloom = (const uint32_t *)ix->d_bloom;
+    if ((e = cudaMalloc(&ix->d_ref2p, ref2p.size() * 8)) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_ref2p, ref2p.data(), ref2p.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&ix->d_uniqp, uniqp.size() * 4)) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_uniqp, uniqp.data(), uniqp.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        qm_index_destroy(ctx, ix);
+        return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
+    }
+    v.ref2p = (const uint64_t *)ix->d_ref2p; v.uniqp = (const uint32_t *)ix->d_uniqp;
     if ((e = cudaMalloc(&ix->d_uniq, uniq.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_uniq, uniq.data(), uniq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
@@ -143,6 +158,8 @@ void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
     if (ix->d_pos) cudaFree(ix->d_pos);
     if (ix->d_uniq) cudaFree(ix->d_uniq);
     if (ix->d_bloom) cudaFree(ix->d_bloom);
+    if (ix->d_ref2p) cudaFree(ix->d_ref2p);
+    if (ix->d_uniqp) cudaFree(ix->d_uniqp);
     delete ix;
 }
 
