@@ -85,10 +85,10 @@ __device__ __forceinline__ uint64_t ref_get2(const IndexView &V, int64_t b)
     const uint64_t lo = __ldg(w);
     return sh ? (lo >> sh) | (__ldg(w + 1) << (64 - sh)) : lo;
 }
-__device__ __forceinline__ uint32_t uniq_get(const IndexView &V, int64_t b)
-{   // uniqueness flags of the 32 k-mers starting at forward positions b .. b+31, b >= -32
+__device__ __forceinline__ uint32_t uniq_get(const uint32_t *__restrict__ map, int64_t b)
+{   // flags of the 32 k-mers starting at forward positions b .. b+31, b >= -32 (map = V.uniqp or V.uniq2p)
     const int64_t x = b + 32;
-    const uint32_t *w = V.uniqp + (x >> 5);
+    const uint32_t *w = map + (x >> 5);
     return __funnelshift_r(__ldg(w), __ldg(w + 1), (unsigned)(x & 31));
 }
 
@@ -136,7 +136,8 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
     const uint64_t kbits = k < 64 ? ((1ull << k) - 1) : ~0ull;
     int n = 0;
     int64_t trk_p = -1;             // forward position of the previous k-mer's only hit, -1 = none / several
-    int trk_pass = 0;               // its strand: 0 = read k-mer as is, 1 = reverse complement
+    int64_t trk_p2 = -1;            // >= 0: the previous k-mer had one hit per strand, trk_p (as is) and trk_p2 (reverse complement)
+    int trk_pass = 0;               // strand of a lone hit: 0 = read k-mer as is, 1 = reverse complement
     // the seed each strand is currently growing lives in registers (a clean read extends ONE seed ~120 times);
     // S[] in global memory is only touched when a seed is created, looked for, or handed back
     int64_t cur_diag[2] = {0, 0};
@@ -168,37 +169,44 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
     int q = 0;
     while (q <= q_last) {
         if (trk_p >= 0) {
-            // how many of the positions q, q+1, ... continue the unique match of position q-1 (at most 32 per step)
+            // How many of the positions q, q+1, ... continue the match of position q-1 (at most 32 per step).  Tracked is
+            // either the ONLY hit of that k-mer (trk_p on strand trk_pass; trk_p2 < 0) or its only hit on EACH strand
+            // (forward-strand hit at trk_p, reverse-complement hit at trk_p2: inverted repeats).
             const int nb = q + k - 1;                   // index of the first new read base
             const uint64_t rbits = R.get2(nb);
             const uint32_t nbits = (uint32_t)R.getn(nb);
-            uint64_t refbits;
-            uint32_t ub;
-            int64_t lim;
-            if (!trk_pass) {
-                refbits = ref_get2(V, trk_p + k);
-                ub = uniq_get(V, trk_p + 1);
-                lim = V.l_pac - k - trk_p;              // positions p+1 .. l_pac-k
-            } else {
-                refbits = ~grouprev(ref_get2(V, trk_p - 32));
-                ub = __brev(uniq_get(V, trk_p - 32));
-                lim = trk_p;                            // positions p-1 .. 0
-            }
-            const uint64_t x = rbits ^ refbits;
-            const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
-            int m = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
-            const int m_n = nbits ? __ffs((int)nbits) - 1 : 32;
-            const int m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
-            m = m < m_n ? m : m_n;
-            m = m < m_u ? m : m_u;
-            if ((int64_t)m > lim) m = (int)lim;
+            int m = nbits ? __ffs((int)nbits) - 1 : 32;
             if (m > q_last - q + 1) m = q_last - q + 1;
-            if (m > 0) {
-                const int64_t rpos = trk_pass ? 2 * V.l_pac - trk_p - k : trk_p;        // of the hit at q-1
-                if (cur_idx[trk_pass] >= 0 && cur_diag[trk_pass] == rpos - (q - 1) && cur_qnext[trk_pass] == q) {
-                    cur_len[trk_pass] += m; cur_qnext[trk_pass] += m;
+            const bool two = trk_p2 >= 0;
+            if (two || !trk_pass) {                     // a forward-strand hit at trk_p: positions p+1 .. l_pac-k
+                const uint64_t x = rbits ^ ref_get2(V, trk_p + k);
+                const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+                const uint32_t ub = uniq_get(two ? V.uniq2p : V.uniqp, trk_p + 1);
+                const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32, m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
+                const int64_t lim = V.l_pac - k - trk_p;
+                m = m < m_b ? m : m_b; m = m < m_u ? m : m_u; m = (int64_t)m > lim ? (int)lim : m;
+            }
+            if (two || trk_pass) {                      // a reverse-complement hit at pr: positions pr-1 .. 0
+                const int64_t pr = two ? trk_p2 : trk_p;
+                const uint64_t x = rbits ^ ~grouprev(ref_get2(V, pr - 32));
+                const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+                const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
+                m = m < m_b ? m : m_b; m = (int64_t)m > pr ? (int)pr : m;
+                if (!two) {
+                    const uint32_t ub = __brev(uniq_get(V.uniqp, pr - 32));
+                    const int m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
+                    m = m < m_u ? m : m_u;
                 }
-                trk_p = trk_pass ? trk_p - m : trk_p + m;
+            }
+            if (m > 0) {
+                auto grow = [&](int pass, int64_t p) {
+                    const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;                 // of the hit at q-1
+                    if (cur_idx[pass] >= 0 && cur_diag[pass] == rpos - (q - 1) && cur_qnext[pass] == q) {
+                        cur_len[pass] += m; cur_qnext[pass] += m;
+                    }
+                };
+                if (two) { grow(0, trk_p); grow(1, trk_p2); trk_p += m; trk_p2 -= m; }
+                else { grow(trk_pass, trk_p); trk_p = trk_pass ? trk_p - m : trk_p + m; }
                 q += m;
                 if (m == 32) continue;
                 if (q > q_last) break;
@@ -207,7 +215,7 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
         }
         const uint64_t nm = R.getn(q) & kbits;
         if (nm) {                                       // an N inside the k-mer: skip every k-mer that covers it
-            trk_p = -1;
+            trk_p = -1; trk_p2 = -1;
             q += 64 - __clzll((long long)nm);
             continue;
         }
@@ -221,10 +229,10 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
             qm_bloom_pos(fw < rc ? fw : rc, V.bloom_bits, bp);
             const uint32_t hit = (__ldg(&bloom[bp[0] >> 5]) >> (bp[0] & 31)) & (__ldg(&bloom[bp[1] >> 5]) >> (bp[1] & 31)) &
                                  (__ldg(&bloom[bp[2] >> 5]) >> (bp[2] & 31)) & 1u;
-            if (!hit) { trk_p = -1; ++q; continue; }
+            if (!hit) { trk_p = -1; trk_p2 = -1; ++q; continue; }
         }
-        int n_hits = 0, one_pass = 0;
-        int64_t one_p = -1;
+        int n_hits = 0, one_pass = 0, n_pass[2] = {0, 0};
+        int64_t one_p = -1, p_of[2] = {-1, -1};
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             uint32_t first, cnt;
@@ -233,11 +241,13 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
             for (uint32_t t = 0; t < cnt; ++t) {
                 const int64_t p = V.pos[first + t];
                 add_hit(pass, p, q, cnt == 1);
-                one_p = p; one_pass = pass;
+                one_p = p; one_pass = pass; p_of[pass] = p;
             }
-            n_hits += (int)cnt;
+            n_hits += (int)cnt; n_pass[pass] = (int)cnt;
         }
-        if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; } else trk_p = -1;
+        trk_p = -1; trk_p2 = -1;
+        if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; }
+        else if (n_hits == 2 && n_pass[0] == 1 && n_pass[1] == 1) { trk_p = p_of[0]; trk_p2 = p_of[1]; trk_pass = 0; }
         ++q;
     }
     flush();

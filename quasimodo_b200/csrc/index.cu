@@ -66,7 +66,7 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         i = j;
     }
     // uniqueness bitmap: k-mer occurs once and its reverse complement never (see IndexView::uniq)
-    std::vector<uint32_t> uniq((size_t)(total + 31) / 32 + 1, 0u);
+    std::vector<uint32_t> uniq((size_t)(total + 31) / 32 + 1, 0u), uniq2((size_t)(total + 31) / 32 + 1, 0u);
     {
         auto count_of = [&](uint64_t key) -> uint32_t {
             uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> v.shift;
@@ -86,17 +86,22 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
                 uint64_t rc = 0;
                 for (int b = 0; b < k; ++b) rc |= (uint64_t)(3 - ((key >> (2 * b)) & 3)) << (2 * (k - 1 - b));
                 // a palindromic k-mer (rc == key) is its own reverse complement: both look-ups hit, not unique
-                if (rc != key && count_of(rc) == 0) uniq[km[i].second >> 5] |= 1u << (km[i].second & 31);
+                if (rc != key) {
+                    const uint32_t c_rc = count_of(rc);
+                    if (c_rc == 0) uniq[km[i].second >> 5] |= 1u << (km[i].second & 31);
+                    else if (c_rc == 1) uniq2[km[i].second >> 5] |= 1u << (km[i].second & 31);
+                }
             }
             i = j;
         }
     }
     // padded 2-bit reference and padded uniqueness bitmap for the seeding kernel's 32-bases-at-a-time match extension
     std::vector<uint64_t> ref2p((size_t)(total + 32 + 31) / 32 + 2, 0ull);
-    std::vector<uint32_t> uniqp((size_t)(total + 32 + 31) / 32 + 2, 0u);
+    std::vector<uint32_t> uniqp((size_t)(total + 32 + 31) / 32 + 2, 0u), uniq2p((size_t)(total + 32 + 31) / 32 + 2, 0u);
     for (int64_t x = 0; x < total; ++x) {
         ref2p[(size_t)(x + 32) >> 5] |= (uint64_t)h_codes[x] << (2 * ((x + 32) & 31));
         if ((uniq[x >> 5] >> (x & 31)) & 1u) uniqp[(size_t)(x + 32) >> 5] |= 1u << ((x + 32) & 31);
+        if ((uniq2[x >> 5] >> (x & 31)) & 1u) uniq2p[(size_t)(x + 32) >> 5] |= 1u << ((x + 32) & 31);
     }
     // Bloom filter over canonical k-mers: a read k-mer whose canonical form is not in the filter occurs on neither strand,
     // and the seeding kernel answers that from shared memory instead of probing the table twice through L2.  Sized at
@@ -127,11 +132,13 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
     if ((e = cudaMalloc(&ix->d_ref2p, ref2p.size() * 8)) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_ref2p, ref2p.data(), ref2p.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_uniqp, uniqp.size() * 4)) != cudaSuccess ||
-        (e = cudaMemcpy(ix->d_uniqp, uniqp.data(), uniqp.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        (e = cudaMemcpy(ix->d_uniqp, uniqp.data(), uniqp.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&ix->d_uniq2p, uniq2p.size() * 4)) != cudaSuccess ||
+        (e = cudaMemcpy(ix->d_uniq2p, uniq2p.data(), uniq2p.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
         qm_index_destroy(ctx, ix);
         return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
     }
-    v.ref2p = (const uint64_t *)ix->d_ref2p; v.uniqp = (const uint32_t *)ix->d_uniqp;
+    v.ref2p = (const uint64_t *)ix->d_ref2p; v.uniqp = (const uint32_t *)ix->d_uniqp; v.uniq2p = (const uint32_t *)ix->d_uniq2p;
     if ((e = cudaMalloc(&ix->d_uniq, uniq.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_uniq, uniq.data(), uniq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
@@ -160,6 +167,7 @@ void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
     if (ix->d_bloom) cudaFree(ix->d_bloom);
     if (ix->d_ref2p) cudaFree(ix->d_ref2p);
     if (ix->d_uniqp) cudaFree(ix->d_uniqp);
+    if (ix->d_uniq2p) cudaFree(ix->d_uniq2p);
     delete ix;
 }
 
