@@ -765,7 +765,7 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
     }
 }
 
-constexpr int64_t kSeBatch = 1 << 21;
+constexpr int64_t kSeBatch = 1 << 22;
 constexpr int kTailMinTasks = 8192;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
 
 struct SeScratch {
@@ -837,8 +837,27 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
         const uint8_t *codes = d_codes + b0 * stride;
         const int32_t *lens = d_lens + b0;
         int sp = qm_prof_begin(ctx, QM_ST_SEED, st);
-        QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
-        qm_prof_end(ctx, QM_ST_SEED, sp, st, 1);
+        int n_seed_launches = 0;
+        if (ctx->se_n_parts > 0 && b0 == 0 && n_reads <= kSeBatch) {
+            // the batch is still arriving piece by piece (host entry): seed each piece as soon as its copy has landed
+            int64_t r0 = 0;
+            for (int pt = 0; pt < ctx->se_n_parts; ++pt) {
+                const int64_t r1 = ctx->se_part_end[pt] < nb ? ctx->se_part_end[pt] : nb;
+                QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->se_part_ev[pt], 0));
+                if (r1 > r0) {
+                    QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes + r0 * stride, stride, lens + r0, r1 - r0, sc.seeds + r0 * QM_MAX_SEEDS,
+                                                   sc.n_seeds + r0, sc.plan + r0 * QM_MAX_SEEDS, sc.n_plan + r0, sc.st + r0, false, st));
+                    ++n_seed_launches;
+                    r0 = r1;
+                }
+            }
+            if (r0 < nb) return qm_fail(ctx, QM_EINVAL, "qm_align_se: the announced pieces cover %lld of %lld reads", (long long)r0, (long long)nb);
+        } else {
+            QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
+            n_seed_launches = 1;
+        }
+        ctx->se_n_parts = 0;
+        qm_prof_end(ctx, QM_ST_SEED, sp, st, n_seed_launches);
         for (int round = 0; round < 4 * QM_MAX_REGS + 8; ++round) {
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
             cudaMemsetAsync(sc.ctr, 0, sizeof(RoundCounters), st);

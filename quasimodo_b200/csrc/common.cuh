@@ -28,6 +28,12 @@ struct qm_ctx {
     // side streams: the independent per-class extension kernels of one round run concurrently (fork/join by events)
     cudaStream_t side[12] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[12] = {};
+    // host-entry hand-over to qm_align_se: the read batch arrives in se_n_parts pieces (reads [.., se_part_end[i]) are in
+    // device memory once se_part_ev[i] has fired), so seeding can start on the first piece while the rest is still
+    // being copied; consumed (reset to 0) by the next qm_align_se call
+    int se_n_parts = 0;
+    int64_t se_part_end[16] = {};
+    cudaEvent_t se_part_ev[16] = {};
     bool prof_on = false;
     std::vector<qm_prof_span> prof_spans;
     std::vector<cudaEvent_t> prof_pool;

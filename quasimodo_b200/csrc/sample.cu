@@ -9,12 +9,14 @@
 // (bwa's per-chunk mem_pestat) is fixed ONCE per sample from the first min(n, 2^18) pairs handed in -- or
 // set by the caller (multi-GPU: rank 0's model is broadcast) -- so that results do not depend on how the
 // pair stream is split into batches or across GPUs.
+#include <stdlib.h>
 #include <vector>
 #include "pipeline.cuh"
 
 namespace {
-constexpr int64_t kChunkPairs = 1 << 20;
+constexpr int64_t kChunkPairs = 1 << 21;
 constexpr int64_t kPestatPairs = QM_PESTAT_PAIRS;
+constexpr int kCopyParts = 8;
 }
 
 struct qm_sample {
@@ -29,7 +31,8 @@ struct qm_sample {
     qm_aln *d_alns = nullptr;
     uint8_t *d_stage[2] = {nullptr, nullptr};     // host-entry staging: codes | quals | lens, double buffered
     size_t stage_cap = 0;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_quals[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_part[2][kCopyParts] = {};      // pieces of a chunk's bases (see qm_ctx::se_part_ev)
     bool have_pes = false;
     qm_pestat pes[4];
     int64_t n_pairs = 0;
@@ -37,8 +40,10 @@ struct qm_sample {
 
 namespace {
 
+// quals_ready (may be NULL): event after which d_quals is valid; only the pileup reads the qualities, so their copy
+// may still be in flight while the reads are being aligned
 int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
-                 int64_t n, int64_t pair_id0, qm_aln *d_alns_out, cudaStream_t st)
+                 int64_t n, int64_t pair_id0, qm_aln *d_alns_out, cudaStream_t st, cudaEvent_t quals_ready = nullptr)
 {
     qm_ctx *ctx = s->ctx;
     int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, s->d_cells, st);
@@ -51,6 +56,7 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
     qm_aln *alns = d_alns_out ? d_alns_out : s->d_alns;
     rc = qm_pair_finish(ctx, s->idx, &s->opt, d_codes, stride, d_lens, n, pair_id0, s->d_regs, s->d_n_regs, s->pes, alns, st);
     if (rc) return rc;
+    if (quals_ready) QM_CUDA(ctx, cudaStreamWaitEvent(st, quals_ready, 0));
     rc = qm_pileup_accumulate(ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n, s->d_counts, st);
     if (rc) return rc;
     s->n_pairs += n;
@@ -82,6 +88,8 @@ int qm_sample_begin(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const q
     }
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_quals[i], cudaEventDisableTiming);
+        for (int p = 0; p < kCopyParts; ++p) cudaEventCreateWithFlags(&s->ev_part[i][p], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s->ev_consumed[i], cudaEventDisableTiming);
     }
     *out = s;
@@ -97,6 +105,8 @@ void qm_sample_destroy(qm_sample *s)
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->d_stage[i]);
         if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+        if (s->ev_quals[i]) cudaEventDestroy(s->ev_quals[i]);
+        for (int p = 0; p < kCopyParts; ++p) if (s->ev_part[i][p]) cudaEventDestroy(s->ev_part[i][p]);
         if (s->ev_consumed[i]) cudaEventDestroy(s->ev_consumed[i]);
     }
     delete s;
@@ -183,14 +193,27 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
         s->stage_cap = need;
     }
     cudaStream_t cs = ctx->copy_stream, ks = ctx->own_stream;
-    // chunk schedule: a small first chunk (its copy is the only one nothing can hide), then growing ones so that
-    // the kernels see large batches while every later copy runs under the previous chunk's kernels
+    // Full-size chunks (large batches: fewer extension rounds, shorter tails).  A chunk's bases are copied in kCopyParts
+    // pieces and seeded piece by piece, so only the first piece's copy is exposed; qualities travel behind the bases
+    // (only the pileup at the end of a chunk reads them); the next chunk's copies run under this chunk's kernels.
     std::vector<int64_t> starts, sizes;
     {
-        const int64_t ramp[3] = { kChunkPairs / 4, kChunkPairs - kChunkPairs / 4, kChunkPairs };
+        int64_t ramp[8] = { kChunkPairs };
+        int n_ramp = 1;
+        if (const char *e = getenv("QM_HOST_CHUNKS")) {             // measurement knob: comma-separated chunk sizes
+            n_ramp = 0;
+            for (const char *q = e; *q && n_ramp < 8;) {
+                char *end = nullptr;
+                const long long v = strtoll(q, &end, 10);
+                if (end == q) break;
+                if (v > 0) ramp[n_ramp++] = v < kChunkPairs ? v : kChunkPairs;
+                q = *end ? end + 1 : end;
+            }
+            if (n_ramp == 0) { ramp[0] = kChunkPairs; n_ramp = 1; }
+        }
         int64_t p0 = 0;
         for (int k = 0; p0 < n_pairs; ++k) {
-            int64_t n = ramp[k < 2 ? k : 2];
+            int64_t n = k < n_ramp ? ramp[k] : kChunkPairs;
             if (n > n_pairs - p0) n = n_pairs - p0;
             starts.push_back(p0); sizes.push_back(n);
             p0 += n;
@@ -202,10 +225,17 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
         const int64_t p0 = starts[c], n = sizes[c];
         cudaError_t e;
         if ((e = cudaStreamWaitEvent(cs, s->ev_consumed[b], 0)) != cudaSuccess) return e;     // buffer b free again
-        if ((e = cudaMemcpyAsync(s->d_stage[b], h_codes + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(s->d_stage[b] + seq_al, h_quals + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(s->d_stage[b] + 2 * seq_al, h_lens + 2 * p0, (size_t)2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
-        return cudaEventRecord(s->ev_copied[b], cs);
+        if ((e = cudaEventRecord(s->ev_copied[b], cs)) != cudaSuccess) return e;
+        // the bases in kCopyParts pieces, an event behind each: seeding starts on piece 0 while the others are in flight
+        for (int pt = 0; pt < kCopyParts; ++pt) {
+            const int64_t r0 = 2 * n * pt / kCopyParts, r1 = 2 * n * (pt + 1) / kCopyParts;
+            if (r1 > r0 && (e = cudaMemcpyAsync(s->d_stage[b] + r0 * stride, h_codes + (2 * p0 + r0) * stride, (size_t)(r1 - r0) * stride,
+                                                cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(s->ev_part[b][pt], cs)) != cudaSuccess) return e;
+        }
+        if ((e = cudaMemcpyAsync(s->d_stage[b] + seq_al, h_quals + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+        return cudaEventRecord(s->ev_quals[b], cs);
     };
     // a fresh event counts as completed, so the first two waits on ev_consumed pass immediately
     QM_CUDA(ctx, enqueue_copy(0));
@@ -214,8 +244,11 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
         const int64_t p0 = starts[c], n = sizes[c];
         if (c + 1 < n_chunks) QM_CUDA(ctx, enqueue_copy(c + 1));
         QM_CUDA(ctx, cudaStreamWaitEvent(ks, s->ev_copied[b], 0));
+        ctx->se_n_parts = kCopyParts;
+        for (int pt = 0; pt < kCopyParts; ++pt) { ctx->se_part_end[pt] = 2 * n * (pt + 1) / kCopyParts; ctx->se_part_ev[pt] = s->ev_part[b][pt]; }
         int rc = sample_chunk(s, s->d_stage[b], s->d_stage[b] + seq_al, stride, (const int32_t *)(s->d_stage[b] + 2 * seq_al), n,
-                              pair_id0 + p0, nullptr, ks);
+                              pair_id0 + p0, nullptr, ks, s->ev_quals[b]);
+        ctx->se_n_parts = 0;
         if (rc) return rc;
         if (h_alns) QM_CUDA(ctx, cudaMemcpyAsync(h_alns + 2 * p0, s->d_alns, (size_t)2 * n * sizeof(qm_aln), cudaMemcpyDeviceToHost, ks));
         QM_CUDA(ctx, cudaEventRecord(s->ev_consumed[b], ks));
