@@ -464,7 +464,8 @@ struct RoundCounters {        // zeroed before every advance round; the host rea
     int class_cursor[kExtCtr];    // work cursors of the extension kernels
     int n_tasks;
     int tail_cursor;
-    int pad[6];
+    int max_score;            // max over the round's tasks of h0 + qlen * a: <= 255 lets the extension kernel hold eh[] in bytes
+    int pad[5];
     int hist[512];            // tasks per query length (counting sort of the task lists by qlen)
     int offs[512];            // running output offsets of the scatter pass, relative to the class's list
     int fb[2 * kExtCtr];      // fallback lists of the paired extension kernel: counts, then cursors
@@ -665,6 +666,7 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
         tasks[slot] = t;
         atomicAdd(&ctr->class_count[qm_ext_class(t.qlen)], 1);
         atomicAdd(&ctr->hist[t.qlen], 1);
+        atomicMax(&ctr->max_score, t.h0 + t.qlen * o.a);
         s.task = slot;
     }
     st[r] = s;
@@ -888,7 +890,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             int n_launch = 0;
             for (int c = 0; c < kExtClasses; ++c) n_launch += h_ctr->class_count[c] > 0;
             rc = qm_ext_launch_classes(ctx, P, idx->v, sc.tasks, sc.lists, nb, sc.ctr->class_count, sc.ctr->class_cursor,
-                                       h_ctr->class_count, sc.res, sc.lists + (int64_t)kExtClasses * nb, sc.ctr->fb, st);
+                                       h_ctr->class_count, sc.res, sc.lists + (int64_t)kExtClasses * nb, sc.ctr->fb, st,
+                                       h_ctr->max_score <= 255);
             qm_prof_end(ctx, QM_ST_EXTEND, sp, st, n_launch);
             if (rc) { cudaFreeHost(h_ctr); return rc; }
         }

@@ -100,7 +100,8 @@ void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, 
 
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
-                          const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st)
+                          const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st,
+                          bool scores_fit_bytes)
 {
     // A class with many tasks goes to the thread-per-task kernel (extend2.cu: high throughput, but one task is a
     // long serial chain, ~0.3 ms); a class with few tasks (the tail rounds of mem_chain2aln, where only reads with
@@ -131,7 +132,8 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
             default: launch_class<5>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
             }
         } else if (big) {
-            int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc);
+            int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc,
+                                          scores_fit_bytes);
             if (rc) return rc;
         } else {
             switch (c) {

@@ -56,7 +56,10 @@ struct TState {                         // one in-flight task (registers)
     bool indirect;
 };
 
-template <int CAP, bool SYM>
+// BYTES: every score of the batch fits a byte (h0 + qlen*a <= 255, known on the host from the round's counters): eh[j] is
+// then ONE 16-bit word h | e << 8 -- 4 instead of 6 bytes of shared memory per column (1.5x the resident warps) and 3
+// instead of 5 shared accesses per cell, for 3 more ALU instructions (unpack, pack).
+template <int CAP, bool SYM, bool BYTES>
 __global__ void __launch_bounds__(kT)
 ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const int *__restrict__ list,
             const int *__restrict__ count, int *__restrict__ cursor, qm_ext_result *__restrict__ out)
@@ -65,6 +68,10 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
     constexpr int PL = (CAP / 2 + 1) * kT * 2;             // halfwords per plane
     unsigned short *HP = smem_u16 + 2 * threadIdx.x;       // HP[IX(j)] = eh[j].h, HP[PL + IX(j)] = eh[j].e,
                                                            // HP[2 PL + IX(j)] = PRMT selector of q[j]
+                                                           // (BYTES: HP[IX(j)] = h | e << 8, HP[PL + IX(j)] = selector)
+    constexpr int SEL = BYTES ? PL : 2 * PL;
+#define EH_SET(j, h) { HP[IX(j)] = (unsigned short)(h); if (!BYTES) HP[PL + IX(j)] = 0; }       /* eh[j] = {h, 0} */
+#define EH_ZERO(j) (BYTES ? HP[IX(j)] == 0 : (HP[IX(j)] | HP[PL + IX(j)]) == 0)
 #define IX(j) ((((j) >> 1) * (2 * kT)) + ((j) & 1))
     const int n = *count;
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
@@ -101,7 +108,7 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
                 for (int j = 0; j < S.qlen; ++j) {      // PRMT selectors: byte q of the row's score LUT, sign-extended
                     int c = S.q[(int64_t)j * S.qstep];
                     c = c > 4 ? 4 : c;
-                    HP[2 * PL + IX(j)] = (unsigned short)(c * 0x1111 + 0x8880);
+                    HP[SEL + IX(j)] = (unsigned short)(c * 0x1111 + 0x8880);
                 }
             }
         }
@@ -109,12 +116,12 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
         if (S.i < 0) {
             // row -1 of eh[] (SURVEY.md A.3 first lines) and the band clamp of this try
             const int qlen = S.qlen, h0 = S.h0;
-            HP[0] = (unsigned short)h0; HP[PL] = 0;
+            EH_SET(0, h0)
             int v = h0 > oe_ins ? h0 - oe_ins : 0;
-            if (qlen >= 1) { HP[IX(1)] = (unsigned short)v; HP[PL + IX(1)] = 0; }
+            if (qlen >= 1) EH_SET(1, v)
             int j = 2;
-            for (; j <= qlen && v > P.e_ins; ++j) { v -= P.e_ins; HP[IX(j)] = (unsigned short)v; HP[PL + IX(j)] = 0; }
-            for (; j <= qlen; ++j) { HP[IX(j)] = 0; HP[PL + IX(j)] = 0; }
+            for (; j <= qlen && v > P.e_ins; ++j) { v -= P.e_ins; EH_SET(j, v) }
+            for (; j <= qlen; ++j) EH_SET(j, 0)
             int best = P.a > -1 ? P.a : -1;
             if (-P.b > best) best = -P.b;
             int w = S.w;
@@ -150,15 +157,17 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
             // one cell of the reference's inner loop at halfword offset O from p; K receives H << 18 | U
 #define QM_CELL(O, U, K)                                                                         \
             {                                                                                    \
-                const int hh = p[O], e = p[PL + (O)];                                            \
-                const int s = lut_score(L, p[2 * PL + (O)]);                                     \
+                int hh, e;                                                                       \
+                if (BYTES) { const int he = p[O]; hh = he & 0xff; e = he >> 8; }                 \
+                else { hh = p[O]; e = p[PL + (O)]; }                                             \
+                const int s = lut_score(L, p[SEL + (O)]);                                        \
                 const int M = hh + min(s, hh);              /* h ? h + s : <= 0 */               \
                 const int H = __vimax3_s32(M, e, f);                                             \
                 const int td = M - oe_del;                                                       \
                 const int en = __viaddmax_s32_relu(e, -P.e_del, td);                             \
                 f = __viaddmax_s32_relu(f, -P.e_ins, SYM ? td : M - oe_ins);                     \
-                p[O] = (unsigned short)h1;                                                       \
-                p[PL + (O)] = (unsigned short)en;                                                \
+                if (BYTES) p[O] = (unsigned short)(en * 256 + h1);                               \
+                else { p[O] = (unsigned short)h1; p[PL + (O)] = (unsigned short)en; }            \
                 h1 = H;                                                                          \
                 K = H * 262144 + (U);                                                            \
             }
@@ -189,7 +198,7 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
 #undef IX_UNUSED
             // eh[end] = {h1, 0}; the reference's j is max(beg, end) here
             const int jstop = end > beg ? end : beg;
-            HP[IX(jstop)] = (unsigned short)h1; HP[PL + IX(jstop)] = 0;
+            EH_SET(jstop, h1)
             if (end > beg) S.cells += end - beg;
             int m = 0, mj = -1;
             if (bkey >= 0) { m = bkey >> 18; mj = beg + (bkey & 0x3ffff); }
@@ -213,9 +222,9 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
             else {
                 // trim to the non-zero span of eh[beg..end]
                 int a = beg;
-                while (a < end && (HP[IX(a)] | HP[PL + IX(a)]) == 0) ++a;
+                while (a < end && EH_ZERO(a)) ++a;
                 int b = end;
-                while (b >= a && (HP[IX(b)] | HP[PL + IX(b)]) == 0) --b;
+                while (b >= a && EH_ZERO(b)) --b;
                 S.beg = a;
                 S.end = b + 2 < qlen ? b + 2 : qlen;
                 S.i = i + 1;
@@ -239,20 +248,20 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
     }
 }
 
-template <int CAP>
+template <int CAP, bool BYTES>
 void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
              int64_t list_stride, const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, cudaStream_t st)
 {
-    const size_t smem = (size_t)3 * (CAP / 2 + 1) * kT * 2 * 2;
+    const size_t smem = (size_t)(BYTES ? 2 : 3) * (CAP / 2 + 1) * kT * 2 * 2;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(ext2_kernel<CAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(ext2_kernel<CAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ext2_kernel<CAP, true, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ext2_kernel<CAP, false, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 12) per_sm = 12;
+    if (per_sm > 16) per_sm = 16;
     int64_t blocks = (int64_t)ctx->sm_count * per_sm;
     if (h_count >= 0) {
         const int64_t need = (h_count + kT - 1) / kT;
@@ -260,28 +269,31 @@ void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
     }
     if (blocks < 1) return;
     const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins;
-    if (sym) ext2_kernel<CAP, true><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
-    else ext2_kernel<CAP, false><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
+    if (sym) ext2_kernel<CAP, true, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
+    else ext2_kernel<CAP, false, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
 }
 
 }  // namespace
 
 int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                          const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
-                         qm_ext_result *d_out, cudaStream_t st)
+                         qm_ext_result *d_out, cudaStream_t st, bool bytes)
 {
+#define QM_L2(CAPV) { if (bytes) launch2<CAPV, true>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); \
+                      else launch2<CAPV, false>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); }
     switch (cls) {
-    case 0: launch2<16>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 1: launch2<32>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 2: launch2<48>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 3: launch2<64>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 4: launch2<80>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 5: launch2<96>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 6: launch2<112>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 7: launch2<128>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
-    case 8: launch2<256>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); break;
+    case 0: QM_L2(16) break;
+    case 1: QM_L2(32) break;
+    case 2: QM_L2(48) break;
+    case 3: QM_L2(64) break;
+    case 4: QM_L2(80) break;
+    case 5: QM_L2(96) break;
+    case 6: QM_L2(112) break;
+    case 7: QM_L2(128) break;
+    case 8: QM_L2(256) break;
     default: return qm_fail(ctx, QM_EINVAL, "qm_ext2_launch_class: class %d has no thread-per-task kernel", cls);
     }
+#undef QM_L2
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }

@@ -96,9 +96,10 @@ static __host__ __device__ __forceinline__ int qm_ext_class(int qlen)
 // Launch the per-class extension kernels.  lists: [kExtClasses][list_stride] task indices; h_counts may be
 // NULL (unknown on the host: persistent grids sized for the SM count) or the 5 class counts.
 // one class (0..8) on the thread-per-task kernel; h_count < 0: unknown on the host
+// bytes: the caller guarantees h0 + qlen*a <= 255 for every task of the list (eh[] held in bytes, see extend2.cu)
 int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                          const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
-                         qm_ext_result *d_out, cudaStream_t st);
+                         qm_ext_result *d_out, cudaStream_t st, bool bytes = false);
 // two tasks per thread in one s16x2 word (extend2p.cu), classes 0..7; tasks it cannot hold are appended to the
 // class's fallback list d_fb_lists[cls][.] (count d_fb_ctr[cls]) for the scalar kernel
 int qm_ext2p_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
@@ -108,4 +109,5 @@ int qm_ext2p_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexV
 // then fallback cursors); both NULL: the paired kernel is not used
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
-                          const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st);
+                          const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st,
+                          bool scores_fit_bytes = false);
