@@ -362,12 +362,19 @@ def run_ours(args):
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     dpx_gops, _ = ctx.dpx_peak(1, 4096)                 # measured now: G lane-instr/s of __viaddmax_s16x2_relu
     gcups_peak = dpx_gops * 2.0 / 9.0                   # 2 packed cells per lane-instr, 9 DPX-class instr per cell
+    traffic = None
+    try:                                                   # per-launch DRAM bytes of the extension kernel from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ext2_traffic.json")))["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     ext_ms = stage_ms["extend"]
     dom = max(("seed_chain", "advance", "extend", "pair_cigar", "pileup"), key=lambda k: stage_ms[k])
     gcups = cells_total / ext_ms / 1e6 if ext_ms > 0 else 0.0
-    roofline = {"kernel": "ext_kernel<C> (batched ksw_extend2)", "bound": "int-issue (DPX), not hbm/tensor",
+    roofline = {"kernel": "ext2_kernel<CAP> + ext_kernel<C> (batched ksw_extend2)", "bound": "int-issue (DPX), not hbm/tensor",
                 "achieved": gcups, "peak": gcups_peak, "unit": "GCUPS", "frac": gcups / gcups_peak if gcups_peak else None,
-                "traffic": None, "avg_launch_ms": ext_ms / max(1, stage_launch["extend"]),
+                "traffic": traffic, "traffic_how": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per ext2_kernel launch "
+                                               "(profiles/ext2_traffic.json); the kernel is issue-bound, not DRAM-bound",
+                "avg_launch_ms": ext_ms / max(1, stage_launch["extend"]),
                 "work": f"{cells_total} executed ksw_extend2 cells in {K} steps ({cells_total / (P * K):.0f} cells/pair)",
                 "peak_how": f"measured in this run: {dpx_gops:.0f} G lane-instr/s of viaddmax_s16x2_relu x 2 cells / 9 instr",
                 "dominant_stage": dom}
