@@ -1,0 +1,151 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot run 2 M pairs in seconds):
+conservation laws that tie the count tensor to the alignment records, shard additivity (the multi-GPU decomposition),
+run-to-run determinism, and the device coordinate sort on millions of records.  Every law is first checked on the CPU
+oracle's own records and counts at a size the oracle handles, so the law itself is pinned before it is trusted."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+FULL = 2_000_000            # BASELINE configs[1]: 2 M pairs per sample
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from quasimodo_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def conservation(alns, counts_rows):
+    """(admitted reads, aligned M bases of admitted reads) from the records vs (sum of channel 15, sum of channel 14)"""
+    f = alns["flag"].astype(np.int64)
+    nc = alns["n_cigar"].astype(np.int64)
+    ok = ((f & (0x4 | 0x100 | 0x200 | 0x400)) == 0) & (nc != 0) & (nc != 255) & ~(((f & 1) != 0) & ((f & 2) == 0))
+    cig = alns["cigar"].astype(np.int64)
+    k = np.arange(cig.shape[1])[None, :]
+    is_m = ((cig & 0xf) == 0) & (k < nc[:, None])
+    m_bases = ((cig >> 4) * is_m).sum(1)
+    return (int(ok.sum()), int(m_bases[ok].sum())), (int(counts_rows[:, 15].sum()), int(counts_rows[:, 14].sum()))
+
+
+def test_conservation_law_holds_on_the_oracle():
+    from oracle import qmo_py
+    from quasimodo_b200 import workloads
+    W = workloads.config2(4, 5000)
+    codes, quals, _, _ = W.simulate_host(0, 5000)
+    lens = np.full(10000, 150, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns, counts, _, _ = qmo_py.run_sample(ref, codes, quals, lens)
+    a, b = conservation(alns, counts)
+    assert a == b and a[0] > 5000
+
+
+@pytest.fixture(scope="module")
+def full(ctx):
+    """sample TA-1-1 at full size, reads simulated on the device; whole-sample run with records"""
+    import torch
+    from quasimodo_b200 import _lib, workloads
+    W = workloads.config2(4, FULL)
+    idx = ctx.index(W.ref, 31)
+    dev = torch.device("cuda:0")
+    g = torch.from_numpy(W.src_codes).to(dev)
+    c = torch.empty((2 * FULL, 150), dtype=torch.uint8, device=dev)
+    q = torch.empty_like(c)
+    ctx.simulate_pairs(W, 0, FULL, g, c, q, 0)
+    lens = torch.full((2 * FULL,), 150, dtype=torch.int32, device=dev)
+    d_alns = torch.zeros(2 * FULL * 128, dtype=torch.uint8, device=dev)
+    s = ctx.sample(idx)
+    s.add_pairs(c, q, lens, d_alns=d_alns)
+    counts = s.counts_host()
+    pes = s.get_pestat()
+    stats = s.stats()
+    s.close()
+    yield dict(W=W, idx=idx, c=c, q=q, lens=lens, d_alns=d_alns, counts=counts, pes=pes, stats=stats)
+    idx.close()
+
+
+def test_full_size_conservation(full):
+    from quasimodo_b200 import _lib
+    alns = full["d_alns"].cpu().numpy().view(_lib.ALN_DTYPE)
+    a, b = conservation(alns, full["counts"])
+    assert a == b
+    assert a[0] > 3_000_000                       # most of the 4 M reads are admitted
+    assert full["stats"][0] == FULL and full["stats"][1] > 5_000_000_000      # executed extension cells of the sample
+    # mates point at each other
+    x, y = alns[0::2], alns[1::2]
+    both = ((x["flag"] & 4) == 0) & ((y["flag"] & 4) == 0)
+    assert np.array_equal(x["mate_pos"][both], y["pos"][both]) and np.array_equal(y["mate_pos"][both], x["pos"][both])
+    assert np.array_equal(x["tlen"][both], -y["tlen"][both])
+    # every mapped record lies inside its contig
+    m = (alns["flag"] & 4) == 0
+    assert (alns["pos"][m] >= 0).all() and (alns["pos"][m] < np.array(full["W"].ref.lens)[alns["rid"][m]]).all()
+
+
+def test_full_size_shards_add_up_and_runs_repeat(ctx, full):
+    """four shards of 500 k pairs, each primed with the sample's insert-size prefix, sum to the whole-sample tensor
+    (what the NCCL all-reduce adds up); a second whole-sample run reproduces the tensor bit for bit"""
+    idx, c, q, lens = full["idx"], full["c"], full["q"], full["lens"]
+    from quasimodo_b200 import _lib
+    npre = _lib.PESTAT_PAIRS
+    total = np.zeros_like(full["counts"])
+    for k in range(4):
+        s = ctx.sample(idx)
+        lo, hi = k * FULL // 4, (k + 1) * FULL // 4
+        if k:
+            s.estimate_pestat(c[:2 * npre], lens[:2 * npre])
+        s.add_pairs(c[2 * lo:2 * hi], q[2 * lo:2 * hi], lens[2 * lo:2 * hi], pair_id0=lo)
+        assert s.get_pestat().tobytes() == full["pes"].tobytes()
+        total += s.counts_host()
+        s.close()
+    assert np.array_equal(total, full["counts"])
+    s = ctx.sample(idx)
+    s.add_pairs(c, q, lens)
+    assert np.array_equal(s.counts_host(), full["counts"])
+    s.close()
+
+
+def test_full_size_host_entry_equals_device_entry(ctx, full):
+    """the host-buffer entry (chunked copies, piecewise seeding) gives the same tensor and records as the resident one"""
+    import torch
+    from quasimodo_b200 import _lib
+    n = 600_000
+    hc, hq = full["c"][:2 * n].cpu().pin_memory(), full["q"][:2 * n].cpu().pin_memory()
+    hl = full["lens"][:2 * n].cpu().pin_memory()
+    h_alns = np.zeros(2 * n, dtype=_lib.ALN_DTYPE)
+    a = ctx.sample(full["idx"])
+    a.add_pairs_host(hc, hq, hl, h_alns=h_alns)
+    b = ctx.sample(full["idx"])
+    d_alns = torch.zeros(2 * n * 128, dtype=torch.uint8, device="cuda")
+    b.add_pairs(full["c"][:2 * n], full["q"][:2 * n], full["lens"][:2 * n], d_alns=d_alns)
+    assert np.array_equal(a.counts_host(), b.counts_host())
+    assert h_alns.tobytes() == d_alns.cpu().numpy().tobytes()
+    a.close()
+    b.close()
+
+
+def test_full_size_sort_is_stable_and_ordered(ctx, full):
+    import torch
+    from oracle import sort_py
+    from quasimodo_b200 import _lib
+    n = 2 * FULL
+    d_keys = torch.empty(n, dtype=torch.int64, device="cuda")
+    d_perm = torch.empty(n, dtype=torch.int32, device="cuda")
+    bits = C.c_int()
+    L = _lib.lib()
+    assert L.qm_aln_sort_keys(ctx._h, full["idx"]._h, C.c_void_p(full["d_alns"].data_ptr()), n, C.c_void_p(d_keys.data_ptr()), C.byref(bits), None) == 0
+    keys_in = d_keys.clone()
+    assert L.qm_sort_pairs(ctx._h, C.c_void_p(d_keys.data_ptr()), C.c_void_p(d_perm.data_ptr()), n, bits.value, None) == 0
+    torch.cuda.synchronize()
+    perm = d_perm.to(torch.int64)
+    assert bool((d_keys[1:] >= d_keys[:-1]).all())                                   # ordered
+    assert bool((keys_in[perm] == d_keys).all())                                      # a gather of the input
+    assert int(torch.bincount(perm, minlength=n).max()) == 1                          # a permutation
+    tie = d_keys[1:] == d_keys[:-1]
+    assert bool((perm[1:][tie] > perm[:-1][tie]).all())                               # ties in input order
+    # and the order is samtools' order of the records themselves
+    alns = full["d_alns"].cpu().numpy().view(_lib.ALN_DTYPE)
+    sk = sort_py.samtools_keys(alns)[d_perm.cpu().numpy().view(np.uint32)]
+    assert (sk[1:] >= sk[:-1]).all()
