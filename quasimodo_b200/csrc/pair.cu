@@ -891,15 +891,30 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
     pair_decide_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, T, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns,
                                              tasks, n_tasks, lists, lstride, n_list);
-    // score-only thread-per-task pass (two band classes: w <= 15 and 16..31), then traceback only where needed
-    const unsigned cs_grid = (unsigned)(ctx->sm_count * 4);
+    // score-only thread-per-task pass (three band classes), then traceback only where needed.  The three classes are
+    // independent and none of them fills the GPU alone (shared memory caps the resident warps): side streams, as the
+    // extension classes do.
     int *trace_list = lists + 3 * lstride, *n_trace = n_list + 3;
-    cig_score_kernel<32><<<cs_grid, kCsT, 32 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists, n_list,
-                                                                d_alns, trace_list, n_trace);
-    cig_score_kernel<48><<<cs_grid, kCsT, 48 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + lstride, n_list + 1,
-                                                                d_alns, trace_list, n_trace);
-    cig_score_kernel<72><<<cs_grid, kCsT, 72 * kCsT * 10, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 2 * lstride, n_list + 2,
-                                                                d_alns, trace_list, n_trace);
+    QM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    for (int c = 0; c < 3; ++c) {
+        cudaStream_t sc = ctx->side[c];
+        QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+        if (c == 0) {
+            const size_t sm = 32 * kCsT * 10;
+            const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
+            cig_score_kernel<32><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists, n_list, d_alns, trace_list, n_trace);
+        } else if (c == 1) {
+            const size_t sm = 48 * kCsT * 10;
+            const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
+            cig_score_kernel<48><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + lstride, n_list + 1, d_alns, trace_list, n_trace);
+        } else {
+            const size_t sm = 72 * kCsT * 10;
+            const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
+            cig_score_kernel<72><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 2 * lstride, n_list + 2, d_alns, trace_list, n_trace);
+        }
+        QM_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], sc));
+        QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+    }
     // everything that needs a traceback (length difference, real gaps, band-doubling retries): warp-per-task kernel.
     // (A thread-per-task traceback variant was measured slower: too few such tasks to hide its per-task latency.)
     cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, trace_list, n_trace,
