@@ -860,7 +860,7 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
     const size_t o_tasks = o_misc + 256;
     const size_t o_left = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
-    const size_t o_over = (o_left + (size_t)4 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    const size_t o_over = (o_left + (size_t)5 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
@@ -874,8 +874,8 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     T.mapq_l = (const double *)(b + o_tab); T.subn = (const int *)(b + o_subn);
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
     int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
-    // task lists of 2 n_pairs slots each: [0..2] score-only pass by band class, [3] needs traceback (filled by kernel 1,
-    // appended to by the score-only kernels); counters n_list[0..3]
+    // task lists of 2 n_pairs slots each: [0..2] score-only pass by band class, [3] needs traceback (filled by kernel 1),
+    // [4] needs traceback after all (filled by the score-only kernels); counters n_list[0..4]
     int *n_list = (int *)(b + o_misc + 32), *lists = (int *)(b + o_left);
     const int64_t lstride = 2 * n_pairs;
     CigTask *tasks = (CigTask *)(b + o_tasks);
@@ -894,12 +894,18 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     // score-only thread-per-task pass (three band classes), then traceback only where needed.  The three classes are
     // independent and none of them fills the GPU alone (shared memory caps the resident warps): side streams, as the
     // extension classes do.
-    int *trace_list = lists + 3 * lstride, *n_trace = n_list + 3;
+    int *trace_list = lists + 4 * lstride, *n_trace = n_list + 4;
+    int *cursor2 = (int *)(b + o_misc + 12);
     QM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < 4; ++c) {
         cudaStream_t sc = ctx->side[c];
         QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
-        if (c == 0) {
+        if (c == 3) {
+            // the tasks kernel 1 already knows to need a traceback (length difference, wide band) start right away, next to
+            // the score-only classes
+            cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 3 * lstride,
+                                                                                  n_list + 3, cursor2, (uint8_t *)(b + o_over), d_alns, err);
+        } else if (c == 0) {
             const size_t sm = 32 * kCsT * 10;
             const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
             cig_score_kernel<32><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists, n_list, d_alns, trace_list, n_trace);
