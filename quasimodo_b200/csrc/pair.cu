@@ -681,6 +681,182 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
     }
 }
 
+// ---- kernel 2b (one THREAD per task): banded global DP WITH traceback for the tasks the score-only pass could not
+// finish (length difference, real gaps).  Same row/column loop plus the reference's direction byte per cell, written
+// to a global slab laid out [cell][thread] (a warp's stores for one cell are contiguous); the traceback walks the
+// thread's own bytes.  Only the first try is run here: if bwa's retry rule asks for a wider band, or the direction
+// matrix does not fit the slab, the task moves on to the warp-per-task kernel. ----
+constexpr size_t kTraceCellsPerThread = 32768;      // direction nibbles per thread in the slab (rows x band columns rounded up to 8)
+
+template <int B, int T>                // circular slots (power of two, 2w + 2 <= B), threads per block
+__global__ void __launch_bounds__(T)
+cig_trace_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                 const CigTask *__restrict__ tasks, const int *__restrict__ mine, const int *__restrict__ n_mine, int wmax,
+                 uint8_t *__restrict__ slab, qm_aln *__restrict__ alns, int *__restrict__ next, int *__restrict__ n_next)
+{
+    // eh[] in 16 bits: every real score of a <= 500-base global alignment is above -4000 and the "minus infinity" of
+    // cells outside the band only ever loses a few hundred more, so -20000 orders exactly like the reference's
+    // -2^30 in every comparison.  Slots (2s, 2s+1) of a thread share one 32-bit word: lane t always hits bank t.
+    extern __shared__ short ct_smem[];
+    constexpr int NEG16 = -20000;
+    short *HS = ct_smem + 2 * threadIdx.x;
+    short *ES = HS + B * T;
+    unsigned short *SS = (unsigned short *)(HS + 2 * B * T);
+#define SX(sl) ((((sl) >> 1) * (2 * T)) + ((sl) & 1))
+    // direction nibbles (bits 0-1 source of H, bit 2 E extends, bit 3 F extends), 8 cells per word, each row starting a
+    // fresh word, in a slab region of the thread's own: consecutive words of one thread fill whole 32-byte sectors in L2
+    // before they are written back (one byte per cell scattered [cell][thread] cost 12 GB of DRAM writes per 2 M pairs)
+    uint32_t *dirw = (uint32_t *)slab + ((size_t)blockIdx.x * T + threadIdx.x) * (kTraceCellsPerThread / 8);
+    const int n = *n_mine;
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
+    for (int li = blockIdx.x * T + threadIdx.x; li < n; li += gridDim.x * T) {
+        const int ti = mine[li];
+        const CigTask t = tasks[ti];
+        qm_aln *rec = alns + t.read;
+        const int l_query = lens[t.read];
+        const int qb = rec->qb, qe = rec->qe;
+        const int lq = qe - qb, rlen = (int)(t.re - t.rb);
+        const int w = cig_band(o, t.w2, lq, rlen);
+        const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
+        const int row_words = (n_col + 7) >> 3;
+        if (w > wmax || (size_t)row_words * rlen > kTraceCellsPerThread / 8 || lq > 500 || rlen > 1000 || (t.rb < V.l_pac && t.re > V.l_pac) || lq <= 0 || rlen <= 0) {
+            next[atomicAdd(n_next, 1)] = ti;
+            continue;
+        }
+        SeqPair S;
+        S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
+        HS[0] = 0; ES[0] = NEG16;
+        for (int j = 1; j <= lq && j <= w; ++j) { HS[SX(j & (B - 1))] = (short)-(o.o_ins + o.e_ins * j); ES[SX(j & (B - 1))] = NEG16; }
+        if (w + 1 <= lq) { HS[SX((w + 1) & (B - 1))] = NEG16; ES[SX((w + 1) & (B - 1))] = NEG16; }
+        for (int j = 0; j < lq && j <= w; ++j) {
+            int c = S.qb(j);
+            c = c > 4 ? 4 : c;
+            SS[SX(j & (B - 1))] = (unsigned short)(c * 0x1111 + 0x8880);
+        }
+        for (int i = 0; i < rlen; ++i) {
+            const int tb = S.tb(i);
+            const int beg = i > w ? i - w : 0;
+            const int end = i + w + 1 < lq ? i + w + 1 : lq;
+            if (i > 0 && i + w < lq) {
+                int c = S.qb(i + w);
+                c = c > 4 ? 4 : c;
+                SS[SX((i + w) & (B - 1))] = (unsigned short)(c * 0x1111 + 0x8880);
+            }
+            Lut L;
+            if (tb > 3) { L.lo = 0xffffffffu; L.hi = 0xffffffffu; }
+            else {
+                const unsigned mis = (unsigned)(-o.b) & 0xffu, mat = (unsigned)o.a & 0xffu;
+                unsigned v = mis * 0x01010101u;
+                v = (v & ~(0xffu << (8 * tb))) | (mat << (8 * tb));
+                L.lo = v; L.hi = 0xffffffffu;
+            }
+            int f = NEG16;
+            int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : NEG16;
+            uint32_t *drow = dirw + (size_t)i * row_words;
+            uint32_t acc = 0;
+            int cn = 0;                                     // cells of this row so far
+            for (int j = beg; j < end; ++j) {
+                const int sl = SX(j & (B - 1));
+                int m = HS[sl], e = ES[sl];
+                HS[sl] = (short)h1;
+                m += lut_score(L, SS[sl]);
+                uint32_t d = m >= e ? 0u : 1u;
+                int h = m >= e ? m : e;
+                d = h >= f ? d : 2u;
+                h = h >= f ? h : f;
+                h1 = h;
+                int tt = m - oe_del;
+                e -= o.e_del;
+                if (e > tt) d |= 4u; else e = tt;
+                ES[sl] = (short)e;
+                tt = m - oe_ins;
+                f -= o.e_ins;
+                if (f > tt) d |= 8u; else f = tt;
+                acc |= d << (4 * (cn & 7));
+                if ((++cn & 7) == 0) { drow[(cn >> 3) - 1] = acc; acc = 0; }
+            }
+            if (cn & 7) drow[cn >> 3] = acc;
+            const int sl = SX(end & (B - 1));
+            HS[sl] = (short)h1; ES[sl] = NEG16;
+        }
+        const int score = HS[SX(lq & (B - 1))];
+        int w2c = t.w2;
+        if (w2c > o.w << 2) w2c = o.w << 2;
+        if (!(w2c == o.w << 2) && score < t.truesc - o.a) {      // bwa would retry with a doubled band
+            next[atomicAdd(n_next, 1)] = ti;
+            continue;
+        }
+        // traceback, CIGAR built back to front
+        uint32_t cig[QM_MAX_CIGAR];
+        int nc = 0;
+        bool overflow = false;
+        {
+            const int max_cigar = QM_MAX_CIGAR - 2;
+            int state = 0, i = rlen - 1, k = (i + w + 1 < lq ? i + w + 1 : lq) - 1;
+            uint32_t cur = 0;
+            while (i >= 0 && k >= 0) {
+                const int lo = i > w ? i - w : 0;
+                const uint32_t d = dirw[(size_t)i * row_words + ((k - lo) >> 3)] >> (4 * ((k - lo) & 7));
+                state = state == 0 ? (int)(d & 3u) : state == 1 ? (int)((d >> 2) & 1u) : (int)((d >> 3) & 1u) * 2;
+                const uint32_t op = state == 0 ? 0u : (state == 1 ? 2u : 1u);
+                if (cur && (cur & 0xf) == op) cur += 1u << 4;
+                else {
+                    if (cur) { if (nc < max_cigar) cig[nc++] = cur; else overflow = true; }
+                    cur = 1u << 4 | op;
+                }
+                if (state == 0) { --i; --k; } else if (state == 1) --i; else --k;
+            }
+            for (int pass = 0; pass < 2; ++pass) {
+                const int len = pass == 0 ? i + 1 : k + 1;
+                const uint32_t op = pass == 0 ? 2u : 1u;
+                if (len <= 0) continue;
+                if (cur && (cur & 0xf) == op) cur += (uint32_t)len << 4;
+                else {
+                    if (cur) { if (nc < max_cigar) cig[nc++] = cur; else overflow = true; }
+                    cur = (uint32_t)len << 4 | op;
+                }
+            }
+            if (cur) { if (nc < max_cigar) cig[nc++] = cur; else overflow = true; }
+        }
+        if (overflow) {
+            rec->rid = -1; rec->pos = -1; rec->flag |= 0x4; rec->flag &= ~0x10; rec->n_cigar = 255; rec->nm = -1;
+            rec->score = 0; rec->sub = 0; rec->qb = 0; rec->qe = 0;
+            continue;
+        }
+        // cig[] is in reverse order: operation a of the forward CIGAR is cig[nc - 1 - a]
+        int nm = -1;
+        if (nc > 0) {
+            int x = 0, y = 0, n_mm = 0, n_gap = 0;
+            for (int a = 0; a < nc; ++a) {
+                const uint32_t c = cig[nc - 1 - a];
+                const int op = c & 0xf, len = (int)(c >> 4);
+                if (op == 0) { for (int u = 0; u < len; ++u) n_mm += S.qb(x + u) != S.tb(y + u); x += len; y += len; }
+                else if (op == 2) { if (a > 0 && a < nc - 1) n_gap += len; y += len; }
+                else if (op == 1) { x += len; n_gap += len; }
+            }
+            nm = n_mm + n_gap;
+        }
+        const bool is_rev = t.rb >= V.l_pac;
+        int64_t pos = t.rb < V.l_pac ? t.rb : 2 * V.l_pac - 1 - (t.re - 1);
+        int a0 = 0, a1 = nc;                        // forward-order slice [a0, a1) after squeezing a leading / trailing deletion
+        if (nc > 0) {
+            if ((cig[nc - 1] & 0xf) == 2) { pos += cig[nc - 1] >> 4; a0 = 1; }
+            else if ((cig[0] & 0xf) == 2) a1 = nc - 1;
+        }
+        int m = 0;
+        const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+        if (clip5) rec->cigar[m++] = (uint32_t)clip5 << 4 | 4;
+        for (int a = a0; a < a1; ++a) rec->cigar[m++] = cig[nc - 1 - a];
+        if (clip3) rec->cigar[m++] = (uint32_t)clip3 << 4 | 4;
+        rec->n_cigar = (uint8_t)m;
+        const int rid = qm_pos2rid(V, pos);
+        rec->rid = rid;
+        rec->pos = (int32_t)(pos - V.off[rid]);
+        rec->nm = nm;
+    }
+}
+#undef SX
+
 // ---- kernel 2 (one warp per task): banded global DP with traceback, bwa's band-doubling retry, NM, clips ----
 __global__ void __launch_bounds__(kCigWarps * 32)
 cigar_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
@@ -860,7 +1036,9 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
     const size_t o_tasks = o_misc + 256;
     const size_t o_left = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
-    const size_t o_over = (o_left + (size_t)5 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    const size_t o_slab = (o_left + (size_t)6 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    const int tr_blocks = ctx->sm_count * 4;                       // thread-per-task traceback kernel: 4 blocks x 48 KB per SM
+    const size_t o_over = (o_slab + (size_t)tr_blocks * 128 * (kTraceCellsPerThread / 2) + 255) & ~(size_t)255;
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
@@ -875,7 +1053,8 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
     int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
     // task lists of 2 n_pairs slots each: [0..2] score-only pass by band class, [3] needs traceback (filled by kernel 1),
-    // [4] needs traceback after all (filled by the score-only kernels); counters n_list[0..4]
+    // [4] needs traceback after all (filled by the score-only kernels), [5] what the thread-per-task traceback kernel passes
+    // on to the warp-per-task one; counters n_list[0..5]
     int *n_list = (int *)(b + o_misc + 32), *lists = (int *)(b + o_left);
     const int64_t lstride = 2 * n_pairs;
     CigTask *tasks = (CigTask *)(b + o_tasks);
@@ -886,6 +1065,7 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kCsT * 10));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * kCsT * 10));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * kCsT * 10));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 6));
         attr_set = true;
     }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
@@ -903,8 +1083,12 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
         if (c == 3) {
             // the tasks kernel 1 already knows to need a traceback (length difference, wide band) start right away, next to
             // the score-only classes
-            cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 3 * lstride,
-                                                                                  n_list + 3, cursor2, (uint8_t *)(b + o_over), d_alns, err);
+            // (thread per task, direction bytes in a global slab; what it cannot hold -- band > 31, bwa's band-doubling
+            // retry, oversized matrices -- moves on to the warp-per-task kernel behind it)
+            cig_trace_kernel<64, 128><<<tr_blocks, 128, 64 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 3 * lstride, n_list + 3,
+                                                                             31, (uint8_t *)(b + o_slab), d_alns, lists + 5 * lstride, n_list + 5);
+            cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 5 * lstride,
+                                                                                  n_list + 5, cursor2, (uint8_t *)(b + o_over), d_alns, err);
         } else if (c == 0) {
             const size_t sm = 32 * kCsT * 10;
             const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
