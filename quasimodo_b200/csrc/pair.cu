@@ -249,13 +249,15 @@ __device__ __forceinline__ int cig_band(const qm_opt &o, int w2, int lq, int rle
 }
 // which kernel takes a CIGAR task first: 0 / 1 / 2 = score-only thread-per-task pass with 32 / 48 / 72 circular slots
 // (equal lengths, band <= 15 / 23 / 35 -- 35 is the most bwa_gen_cigar2 allows for equal lengths up to 140 bp),
-// 3 = the kernels with traceback
+// 3 / 4 / 5 = thread-per-task pass with traceback and 32 / 64 / 128 slots (length difference, band <= 15 / 31 / 63),
+// 6 = the warp-per-task kernel with traceback
 __device__ __forceinline__ int cig_class(const IndexView &V, const qm_opt &o, const CigTask &t, int lq)
 {
     const int rlen = (int)(t.re - t.rb);
-    if (lq != rlen || (t.rb < V.l_pac && t.re > V.l_pac)) return 3;
+    if (t.rb < V.l_pac && t.re > V.l_pac) return 6;
     const int w = cig_band(o, t.w2, lq, rlen);
-    return w <= 15 ? 0 : w <= 23 ? 1 : w <= 35 ? 2 : 3;
+    if (lq != rlen) return w <= 15 ? 3 : w <= 31 ? 4 : w <= 63 ? 5 : 6;     // traceback needed: thread-per-task kernels by band, else warp
+    return w <= 15 ? 0 : w <= 23 ? 1 : w <= 35 ? 2 : 6;
 }
 
 constexpr int kCigWarps = 4;                  // warps per block of the CIGAR kernel
@@ -716,76 +718,80 @@ cig_trace_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
         const int l_query = lens[t.read];
         const int qb = rec->qb, qe = rec->qe;
         const int lq = qe - qb, rlen = (int)(t.re - t.rb);
-        const int w = cig_band(o, t.w2, lq, rlen);
-        const int n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
-        const int row_words = (n_col + 7) >> 3;
-        if (w > wmax || (size_t)row_words * rlen > kTraceCellsPerThread / 8 || lq > 500 || rlen > 1000 || (t.rb < V.l_pac && t.re > V.l_pac) || lq <= 0 || rlen <= 0) {
-            next[atomicAdd(n_next, 1)] = ti;
-            continue;
-        }
+        if ((t.rb < V.l_pac && t.re > V.l_pac) || lq <= 0 || rlen <= 0 || lq > 500 || rlen > 1000) { next[atomicAdd(n_next, 1)] = ti; continue; }
         SeqPair S;
         S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
-        HS[0] = 0; ES[0] = NEG16;
-        for (int j = 1; j <= lq && j <= w; ++j) { HS[SX(j & (B - 1))] = (short)-(o.o_ins + o.e_ins * j); ES[SX(j & (B - 1))] = NEG16; }
-        if (w + 1 <= lq) { HS[SX((w + 1) & (B - 1))] = NEG16; ES[SX((w + 1) & (B - 1))] = NEG16; }
-        for (int j = 0; j < lq && j <= w; ++j) {
-            int c = S.qb(j);
-            c = c > 4 ? 4 : c;
-            SS[SX(j & (B - 1))] = (unsigned short)(c * 0x1111 + 0x8880);
-        }
-        for (int i = 0; i < rlen; ++i) {
-            const int tb = S.tb(i);
-            const int beg = i > w ? i - w : 0;
-            const int end = i + w + 1 < lq ? i + w + 1 : lq;
-            if (i > 0 && i + w < lq) {
-                int c = S.qb(i + w);
+        // bwa_gen_cigar2 / mem_reg2aln: first try with the inferred band, doubled (at most twice) while the score stays
+        // below truesc - a; the CIGAR is the LAST try's.  A try whose band this kernel cannot hold passes the task on.
+        int w2 = t.w2, last_sc = -(1 << 30), it = 0, score = 0, w = 0, n_col = 0, row_words = 0;
+        bool pass_on = false;
+        for (;;) {
+            if (w2 > o.w << 2) w2 = o.w << 2;
+            w = cig_band(o, w2, lq, rlen);
+            n_col = lq < 2 * w + 1 ? lq : 2 * w + 1;
+            row_words = (n_col + 7) >> 3;
+            if (w > wmax || (size_t)row_words * rlen > kTraceCellsPerThread / 8) { pass_on = true; break; }
+            HS[0] = 0; ES[0] = NEG16;
+            for (int j = 1; j <= lq && j <= w; ++j) { HS[SX(j & (B - 1))] = (short)-(o.o_ins + o.e_ins * j); ES[SX(j & (B - 1))] = NEG16; }
+            if (w + 1 <= lq) { HS[SX((w + 1) & (B - 1))] = NEG16; ES[SX((w + 1) & (B - 1))] = NEG16; }
+            for (int j = 0; j < lq && j <= w; ++j) {
+                int c = S.qb(j);
                 c = c > 4 ? 4 : c;
-                SS[SX((i + w) & (B - 1))] = (unsigned short)(c * 0x1111 + 0x8880);
+                SS[SX(j & (B - 1))] = (unsigned short)(c * 0x1111 + 0x8880);
             }
-            Lut L;
-            if (tb > 3) { L.lo = 0xffffffffu; L.hi = 0xffffffffu; }
-            else {
-                const unsigned mis = (unsigned)(-o.b) & 0xffu, mat = (unsigned)o.a & 0xffu;
-                unsigned v = mis * 0x01010101u;
-                v = (v & ~(0xffu << (8 * tb))) | (mat << (8 * tb));
-                L.lo = v; L.hi = 0xffffffffu;
+            for (int i = 0; i < rlen; ++i) {
+                const int tb = S.tb(i);
+                const int beg = i > w ? i - w : 0;
+                const int end = i + w + 1 < lq ? i + w + 1 : lq;
+                if (i > 0 && i + w < lq) {
+                    int c = S.qb(i + w);
+                    c = c > 4 ? 4 : c;
+                    SS[SX((i + w) & (B - 1))] = (unsigned short)(c * 0x1111 + 0x8880);
+                }
+                Lut L;
+                if (tb > 3) { L.lo = 0xffffffffu; L.hi = 0xffffffffu; }
+                else {
+                    const unsigned mis = (unsigned)(-o.b) & 0xffu, mat = (unsigned)o.a & 0xffu;
+                    unsigned v = mis * 0x01010101u;
+                    v = (v & ~(0xffu << (8 * tb))) | (mat << (8 * tb));
+                    L.lo = v; L.hi = 0xffffffffu;
+                }
+                int f = NEG16;
+                int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : NEG16;
+                uint32_t *drow = dirw + (size_t)i * row_words;
+                uint32_t acc = 0;
+                int cn = 0;                                     // cells of this row so far
+                for (int j = beg; j < end; ++j) {
+                    const int sl = SX(j & (B - 1));
+                    int m = HS[sl], e = ES[sl];
+                    HS[sl] = (short)h1;
+                    m += lut_score(L, SS[sl]);
+                    uint32_t d = m >= e ? 0u : 1u;
+                    int h = m >= e ? m : e;
+                    d = h >= f ? d : 2u;
+                    h = h >= f ? h : f;
+                    h1 = h;
+                    int tt = m - oe_del;
+                    e -= o.e_del;
+                    if (e > tt) d |= 4u; else e = tt;
+                    ES[sl] = (short)e;
+                    tt = m - oe_ins;
+                    f -= o.e_ins;
+                    if (f > tt) d |= 8u; else f = tt;
+                    acc |= d << (4 * (cn & 7));
+                    if ((++cn & 7) == 0) { drow[(cn >> 3) - 1] = acc; acc = 0; }
+                }
+                if (cn & 7) drow[cn >> 3] = acc;
+                const int sl = SX(end & (B - 1));
+                HS[sl] = (short)h1; ES[sl] = NEG16;
             }
-            int f = NEG16;
-            int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : NEG16;
-            uint32_t *drow = dirw + (size_t)i * row_words;
-            uint32_t acc = 0;
-            int cn = 0;                                     // cells of this row so far
-            for (int j = beg; j < end; ++j) {
-                const int sl = SX(j & (B - 1));
-                int m = HS[sl], e = ES[sl];
-                HS[sl] = (short)h1;
-                m += lut_score(L, SS[sl]);
-                uint32_t d = m >= e ? 0u : 1u;
-                int h = m >= e ? m : e;
-                d = h >= f ? d : 2u;
-                h = h >= f ? h : f;
-                h1 = h;
-                int tt = m - oe_del;
-                e -= o.e_del;
-                if (e > tt) d |= 4u; else e = tt;
-                ES[sl] = (short)e;
-                tt = m - oe_ins;
-                f -= o.e_ins;
-                if (f > tt) d |= 8u; else f = tt;
-                acc |= d << (4 * (cn & 7));
-                if ((++cn & 7) == 0) { drow[(cn >> 3) - 1] = acc; acc = 0; }
-            }
-            if (cn & 7) drow[cn >> 3] = acc;
-            const int sl = SX(end & (B - 1));
-            HS[sl] = (short)h1; ES[sl] = NEG16;
+            score = HS[SX(lq & (B - 1))];
+            if (score == last_sc || w2 == o.w << 2) break;
+            last_sc = score;
+            w2 <<= 1;
+            if (!(++it < 3 && score < t.truesc - o.a)) break;
         }
-        const int score = HS[SX(lq & (B - 1))];
-        int w2c = t.w2;
-        if (w2c > o.w << 2) w2c = o.w << 2;
-        if (!(w2c == o.w << 2) && score < t.truesc - o.a) {      // bwa would retry with a doubled band
-            next[atomicAdd(n_next, 1)] = ti;
-            continue;
-        }
+        if (pass_on) { next[atomicAdd(n_next, 1)] = ti; continue; }
         // traceback, CIGAR built back to front
         uint32_t cig[QM_MAX_CIGAR];
         int nc = 0;
@@ -1036,9 +1042,10 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const size_t o_misc = (o_term + term.size() * 8 + 255) & ~(size_t)255;
     const size_t o_tasks = o_misc + 256;
     const size_t o_left = (o_tasks + (size_t)2 * n_pairs * sizeof(CigTask) + 255) & ~(size_t)255;
-    const size_t o_slab = (o_left + (size_t)6 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
-    const int tr_blocks = ctx->sm_count * 4;                       // thread-per-task traceback kernel: 4 blocks x 48 KB per SM
-    const size_t o_over = (o_slab + (size_t)tr_blocks * 128 * (kTraceCellsPerThread / 2) + 255) & ~(size_t)255;
+    const size_t o_slab = (o_left + (size_t)9 * 2 * n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    // thread-per-task traceback kernels (32 / 64 / 128 slots of 6 B per thread): 8 / 4 / 2 blocks of 128 threads per SM
+    const int tr_blocks[3] = { ctx->sm_count * 8, ctx->sm_count * 4, ctx->sm_count * 2 };
+    const size_t o_over = (o_slab + (size_t)(tr_blocks[0] + tr_blocks[1] + tr_blocks[2]) * 128 * (kTraceCellsPerThread / 2) + 255) & ~(size_t)255;
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 5, o_over + (size_t)cig_blocks * kCigWarps * kOverflowPerWarp, &p);
     if (rc) return rc;
@@ -1052,9 +1059,7 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     T.mapq_l = (const double *)(b + o_tab); T.subn = (const int *)(b + o_subn);
     for (int d = 0; d < 4; ++d) { T.pair_term[d] = (const double *)(b + o_term) + term_off[d]; T.pes[d] = pes[d]; }
     int *n_tasks = (int *)(b + o_misc), *cursor = (int *)(b + o_misc + 8), *err = (int *)(b + o_misc + 16);
-    // task lists of 2 n_pairs slots each: [0..2] score-only pass by band class, [3] needs traceback (filled by kernel 1),
-    // [4] needs traceback after all (filled by the score-only kernels), [5] what the thread-per-task traceback kernel passes
-    // on to the warp-per-task one; counters n_list[0..5]
+    // task lists of 2 n_pairs slots each, see the launches below; counters n_list[0..8]
     int *n_list = (int *)(b + o_misc + 32), *lists = (int *)(b + o_left);
     const int64_t lstride = 2 * n_pairs;
     CigTask *tasks = (CigTask *)(b + o_tasks);
@@ -1066,51 +1071,49 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * kCsT * 10));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * kCsT * 10));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 6));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 6));
         attr_set = true;
     }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
     pair_decide_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, T, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns,
                                              tasks, n_tasks, lists, lstride, n_list);
-    // score-only thread-per-task pass (three band classes), then traceback only where needed.  The three classes are
-    // independent and none of them fills the GPU alone (shared memory caps the resident warps): side streams, as the
-    // extension classes do.
-    int *trace_list = lists + 4 * lstride, *n_trace = n_list + 4;
-    int *cursor2 = (int *)(b + o_misc + 12);
+    // Eight independent kernels, none of which fills the GPU alone (shared memory caps the resident warps): side streams,
+    // as the extension classes do.  [0..2] score-only pass by band (equal lengths); [3..5] thread-per-task traceback by band
+    // (length difference); [6] warp-per-task traceback for what kernel 1 already knows to be too wide.  What the score-only
+    // kernels cannot finish lands in list 7, what the thread-per-task traceback kernels cannot hold in list 8: two more
+    // warp-per-task launches behind the join.
+    int *cursor2 = (int *)(b + o_misc + 12), *cursor3 = (int *)(b + o_misc + 20);
+    uint8_t *slab = (uint8_t *)(b + o_slab);
+    const size_t slab_per_thread = kTraceCellsPerThread / 2;
     QM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 7; ++c) {
         cudaStream_t sc = ctx->side[c];
         QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
-        if (c == 3) {
-            // the tasks kernel 1 already knows to need a traceback (length difference, wide band) start right away, next to
-            // the score-only classes
-            // (thread per task, direction bytes in a global slab; what it cannot hold -- band > 31, bwa's band-doubling
-            // retry, oversized matrices -- moves on to the warp-per-task kernel behind it)
-            cig_trace_kernel<64, 128><<<tr_blocks, 128, 64 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 3 * lstride, n_list + 3,
-                                                                             31, (uint8_t *)(b + o_slab), d_alns, lists + 5 * lstride, n_list + 5);
-            cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 5 * lstride,
-                                                                                  n_list + 5, cursor2, (uint8_t *)(b + o_over), d_alns, err);
-        } else if (c == 0) {
-            const size_t sm = 32 * kCsT * 10;
-            const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
-            cig_score_kernel<32><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists, n_list, d_alns, trace_list, n_trace);
-        } else if (c == 1) {
-            const size_t sm = 48 * kCsT * 10;
-            const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
-            cig_score_kernel<48><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + lstride, n_list + 1, d_alns, trace_list, n_trace);
-        } else {
-            const size_t sm = 72 * kCsT * 10;
-            const unsigned g = (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024)));
-            cig_score_kernel<72><<<g, kCsT, sm, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 2 * lstride, n_list + 2, d_alns, trace_list, n_trace);
+        const int *mine = lists + c * lstride, *n_mine = n_list + c;
+        auto blocks_for = [&](size_t sm) { return (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024))); };
+        switch (c) {
+        case 0: cig_score_kernel<32><<<blocks_for(32 * kCsT * 10), kCsT, 32 * kCsT * 10, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
+        case 1: cig_score_kernel<48><<<blocks_for(48 * kCsT * 10), kCsT, 48 * kCsT * 10, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
+        case 2: cig_score_kernel<72><<<blocks_for(72 * kCsT * 10), kCsT, 72 * kCsT * 10, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
+        case 3: cig_trace_kernel<32, 128><<<tr_blocks[0], 128, 32 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, 15, slab, d_alns,
+                                                                                  lists + 8 * lstride, n_list + 8); break;
+        case 4: cig_trace_kernel<64, 128><<<tr_blocks[1], 128, 64 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, 31,
+                                                                                  slab + (size_t)tr_blocks[0] * 128 * slab_per_thread, d_alns, lists + 8 * lstride, n_list + 8); break;
+        case 5: cig_trace_kernel<128, 128><<<tr_blocks[2], 128, 128 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, 63,
+                                                                                    slab + (size_t)(tr_blocks[0] + tr_blocks[1]) * 128 * slab_per_thread, d_alns,
+                                                                                    lists + 8 * lstride, n_list + 8); break;
+        default: cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, cursor2,
+                                                                                       (uint8_t *)(b + o_over), d_alns, err); break;
         }
         QM_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], sc));
         QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
     }
-    // everything that needs a traceback (length difference, real gaps, band-doubling retries): warp-per-task kernel.
-    // (A thread-per-task traceback variant was measured slower: too few such tasks to hide its per-task latency.)
-    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, trace_list, n_trace,
+    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 8 * lstride, n_list + 8,
+                                                                          cursor3, (uint8_t *)(b + o_over), d_alns, err);
+    cigar_kernel<<<cig_blocks, kCigWarps * 32, kCigWarps * kDirBytes, st>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, lists + 7 * lstride, n_list + 7,
                                                                           cursor, (uint8_t *)(b + o_over), d_alns, err);
     pair_finish_kernel<<<grid, 128, 0, st>>>(idx->v, T, n_pairs, d_regs, d_alns);
-    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 6);
+    qm_prof_end(ctx, QM_ST_PAIR, sp, st, 11);
     QM_CUDA(ctx, cudaGetLastError());
     int h_err = 0;
     QM_CUDA(ctx, cudaMemcpyAsync(&h_err, err, 4, cudaMemcpyDeviceToHost, st));
