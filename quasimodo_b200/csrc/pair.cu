@@ -594,10 +594,14 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
                  const CigTask *__restrict__ tasks, const int *__restrict__ mine, const int *__restrict__ n_mine,
                  qm_aln *__restrict__ alns, int *__restrict__ left, int *__restrict__ n_left)
 {
-    extern __shared__ int cs_smem[];
-    int *HS = cs_smem + threadIdx.x;                           // HS[slot * kCsT]            eh[].h
-    int *ES = cs_smem + B * kCsT + threadIdx.x;                // ES[slot * kCsT]            eh[].e
-    unsigned short *SS = (unsigned short *)(cs_smem + 2 * B * kCsT) + threadIdx.x;   // PRMT selector of q[j]
+    // eh[] in 16 bits (see cig_trace_kernel: -20000 orders like the reference's -2^30); slots (2s, 2s+1) of a thread share
+    // one 32-bit word, so lane t always hits bank t
+    extern __shared__ short cs_smem[];
+    constexpr int NEG16 = -20000;
+    short *HS = cs_smem + 2 * threadIdx.x;                     // HS[CX(slot)]  eh[].h
+    short *ES = HS + B * kCsT;                                 // ES[CX(slot)]  eh[].e
+    unsigned short *SS = (unsigned short *)(HS + 2 * B * kCsT);   // PRMT selector of q[j]
+#define CX(sl) ((((sl) >> 1) * (2 * kCsT)) + ((sl) & 1))
     const int n = *n_mine;
     const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
     for (int li = blockIdx.x * kCsT + threadIdx.x; li < n; li += gridDim.x * kCsT) {
@@ -611,13 +615,13 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
         SeqPair S;
         S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
         // first row of eh[] and the selectors of the columns row 0 can reach
-        HS[0] = 0; ES[0] = QM_NEG_INF;
-        for (int j = 1; j <= lq && j <= w; ++j) { HS[(j % B) * kCsT] = -(o.o_ins + o.e_ins * j); ES[(j % B) * kCsT] = QM_NEG_INF; }
-        if (w + 1 <= lq) { HS[((w + 1) % B) * kCsT] = QM_NEG_INF; ES[((w + 1) % B) * kCsT] = QM_NEG_INF; }
+        HS[0] = 0; ES[0] = NEG16;
+        for (int j = 1; j <= lq && j <= w; ++j) { HS[CX(j % B)] = (short)-(o.o_ins + o.e_ins * j); ES[CX(j % B)] = NEG16; }
+        if (w + 1 <= lq) { HS[CX((w + 1) % B)] = NEG16; ES[CX((w + 1) % B)] = NEG16; }
         for (int j = 0; j < lq && j <= w; ++j) {
             int c = S.qb(j);
             c = c > 4 ? 4 : c;
-            SS[(j % B) * kCsT] = (unsigned short)(c * 0x1111 + 0x8880);
+            SS[CX(j % B)] = (unsigned short)(c * 0x1111 + 0x8880);
         }
         int us = 0, n_mm = 0;                              // ungapped score and mismatches (the main diagonal)
         for (int i = 0; i < rlen; ++i) {
@@ -627,7 +631,7 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
             if (i > 0 && i + w < lq) {                     // the column entering the band on the right
                 int c = S.qb(i + w);
                 c = c > 4 ? 4 : c;
-                SS[((i + w) % B) * kCsT] = (unsigned short)(c * 0x1111 + 0x8880);
+                SS[CX((i + w) % B)] = (unsigned short)(c * 0x1111 + 0x8880);
             }
             Lut L;
             if (tb > 3) { L.lo = 0xffffffffu; L.hi = 0xffffffffu; }
@@ -638,16 +642,17 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
                 L.lo = v; L.hi = 0xffffffffu;
             }
             {   // main-diagonal cell: ungapped score / mismatch bookkeeping
-                const unsigned sel = SS[(i % B) * kCsT];
+                const unsigned sel = SS[CX(i % B)];
                 us += lut_score(L, sel);
                 n_mm += (int)(sel & 7u) != tb;
             }
-            int f = QM_NEG_INF;
-            int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : QM_NEG_INF;
-            int sl = (beg % B) * kCsT;                     // slot of column j, advanced with wrap-around
+            int f = NEG16;
+            int h1 = beg == 0 ? -(o.o_del + o.e_del * (i + 1)) : NEG16;
+            int slot = beg % B;                            // slot of column j, advanced with wrap-around
             for (int j = beg; j < end; ++j) {
+                const int sl = CX(slot);
                 int m = HS[sl], e = ES[sl];
-                HS[sl] = h1;
+                HS[sl] = (short)h1;
                 m += lut_score(L, SS[sl]);
                 int h = m >= e ? m : e;
                 h = h >= f ? h : f;
@@ -655,16 +660,15 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
                 int tt = m - oe_del;
                 e -= o.e_del;
                 e = e > tt ? e : tt;
-                ES[sl] = e;
+                ES[sl] = (short)e;
                 tt = m - oe_ins;
                 f -= o.e_ins;
                 f = f > tt ? f : tt;
-                sl += kCsT;
-                if (sl == B * kCsT) sl = 0;
+                if (++slot == B) slot = 0;
             }
-            HS[sl] = h1; ES[sl] = QM_NEG_INF;              // sl is now the slot of column `end` (beg when the row is empty)
+            HS[CX(slot)] = (short)h1; ES[CX(slot)] = NEG16;        // slot is now that of column `end` (beg when the row is empty)
         }
-        const int score = HS[(lq % B) * kCsT];
+        const int score = HS[CX(lq % B)];
         if (score == us && !(score < t.truesc - o.a)) {
             // final and gap-free: <lq>M with clips, exactly what mem_reg2aln writes
             const bool is_rev = t.rb >= V.l_pac;
@@ -682,6 +686,7 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
         } else left[atomicAdd(n_left, 1)] = ti;
     }
 }
+#undef CX
 
 // ---- kernel 2b (one THREAD per task): banded global DP WITH traceback for the tasks the score-only pass could not
 // finish (length difference, real gaps).  Same row/column loop plus the reference's direction byte per cell, written
@@ -1067,9 +1072,9 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     static bool attr_set = false;
     if (!attr_set) {
         QM_CUDA(ctx, cudaFuncSetAttribute(cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCigWarps * kDirBytes));
-        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kCsT * 10));
-        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * kCsT * 10));
-        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * kCsT * 10));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kCsT * 6));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * kCsT * 6));
+        QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * kCsT * 6));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 6));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 6));
         attr_set = true;
@@ -1092,9 +1097,9 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
         const int *mine = lists + c * lstride, *n_mine = n_list + c;
         auto blocks_for = [&](size_t sm) { return (unsigned)(ctx->sm_count * (int)std::min<size_t>(16, (227u * 1024u) / (sm + 1024))); };
         switch (c) {
-        case 0: cig_score_kernel<32><<<blocks_for(32 * kCsT * 10), kCsT, 32 * kCsT * 10, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
-        case 1: cig_score_kernel<48><<<blocks_for(48 * kCsT * 10), kCsT, 48 * kCsT * 10, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
-        case 2: cig_score_kernel<72><<<blocks_for(72 * kCsT * 10), kCsT, 72 * kCsT * 10, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
+        case 0: cig_score_kernel<32><<<blocks_for(32 * kCsT * 6), kCsT, 32 * kCsT * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
+        case 1: cig_score_kernel<48><<<blocks_for(48 * kCsT * 6), kCsT, 48 * kCsT * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
+        case 2: cig_score_kernel<72><<<blocks_for(72 * kCsT * 6), kCsT, 72 * kCsT * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, d_alns, lists + 7 * lstride, n_list + 7); break;
         case 3: cig_trace_kernel<32, 128><<<tr_blocks[0], 128, 32 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, 15, slab, d_alns,
                                                                                   lists + 8 * lstride, n_list + 8); break;
         case 4: cig_trace_kernel<64, 128><<<tr_blocks[1], 128, 64 * 128 * 6, sc>>>(idx->v, *opt, d_codes, stride, d_lens, tasks, mine, n_mine, 31,
