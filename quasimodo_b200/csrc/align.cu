@@ -723,17 +723,24 @@ __device__ __forceinline__ qm_ext_result tail_extend(const ExtParams &P, const I
 }
 
 constexpr int kTailWarps = 4;
+constexpr int kTailMinTasks = 8192;         // a round with fewer tasks hands the still-active reads to tail_kernel
 
+// MAXC = 4: only queries of <= 127 bases (every extension of a 150-base read) -- the warp-wide extension then keeps four
+// column slots per lane in registers instead of sixteen and four times as many warps fit on an SM.  A read whose next
+// extension is longer is parked (its state written back, the task appended to `over`) for the MAXC = 16 launch behind.
+template <int MAXC>
 __global__ void __launch_bounds__(kTailWarps * 32)
 tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
             const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
             ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
-            const ExtTaskI *__restrict__ tasks, int n_tasks, int *__restrict__ cursor, unsigned long long *__restrict__ cells)
+            const ExtTaskI *__restrict__ tasks, int n_tasks_host, const int *__restrict__ n_tasks_dev, int *__restrict__ cursor,
+            unsigned long long *__restrict__ cells, ExtTaskI *__restrict__ over, int *__restrict__ n_over)
 {
     __shared__ ExtTaskI s_task[kTailWarps];
     __shared__ qm_ext_result s_res[kTailWarps];
     __shared__ int s_more[kTailWarps];
     const int lane = qm_lane(), wib = threadIdx.x >> 5;
+    const int n_tasks = n_tasks_dev ? *n_tasks_dev : n_tasks_host;
     for (;;) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(cursor, 1);
@@ -744,10 +751,16 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
         const int64_t r = s_task[wib].pad[0];
         ReadState s;
         if (lane == 0) s = st[r];
+        bool parked = false;
         for (;;) {
             const ExtTaskI t = s_task[wib];
+            if (MAXC < 16 && t.qlen > 127) {            // too long for this instantiation: park the read (warp-uniform)
+                if (lane == 0) { const int k = atomicAdd(n_over, 1); over[k] = t; s.task = k; st[r] = s; }
+                parked = true;
+                break;
+            }
             qm_ext_result x;
-            if (t.qlen <= 127) x = tail_extend<4>(P, V, t, lane);
+            if (MAXC < 16 || t.qlen <= 127) x = tail_extend<4>(P, V, t, lane);
             else if (t.qlen <= 287) x = tail_extend<9>(P, V, t, lane);
             else x = tail_extend<16>(P, V, t, lane);
             __syncwarp();
@@ -762,13 +775,12 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
             __syncwarp();
             if (!s_more[wib]) break;
         }
-        if (lane == 0) { s.task = -1; st[r] = s; }
+        if (lane == 0 && !parked) { s.task = -1; st[r] = s; }
         __syncwarp();
     }
 }
 
-constexpr int64_t kSeBatch = 1 << 22;
-constexpr int kTailMinTasks = 8192;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
+constexpr int64_t kSeBatch = 1 << 22;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
 
 struct SeScratch {
     qm_seed *seeds; int32_t *n_seeds; uint16_t *plan; uint8_t *n_plan; ReadState *st;
@@ -784,7 +796,7 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     const size_t o_plan = take((size_t)nb * QM_MAX_SEEDS * 2);
     const size_t o_np = take((size_t)nb);
     const size_t o_st = take((size_t)nb * sizeof(ReadState));
-    const size_t o_tasks = take((size_t)nb * sizeof(ExtTaskI));
+    const size_t o_tasks = take((size_t)(nb + kTailMinTasks) * sizeof(ExtTaskI));       // + the tail kernel's parked tasks
     const size_t o_res = take((size_t)nb * sizeof(qm_ext_result));
     const size_t o_lists = take((size_t)nb * kExtClasses * 4 * 2);      // class lists, then the fallback lists
     const size_t o_ctr = take(sizeof(RoundCounters));
@@ -875,11 +887,17 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 // few reads left: finish them on the device, one warp per read, no more round trips
                 sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
                 int blocks = (h_ctr->n_tasks + kTailWarps - 1) / kTailWarps;
-                if (blocks > ctx->sm_count * 2) blocks = ctx->sm_count * 2;
-                tail_kernel<<<blocks, kTailWarps * 32, 0, st>>>(idx->v, *opt, P, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan,
-                                                                sc.st, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.tasks,
-                                                                h_ctr->n_tasks, &sc.ctr->tail_cursor, (unsigned long long *)d_cells);
-                qm_prof_end(ctx, QM_ST_EXTEND, sp, st, 1);
+                if (blocks > ctx->sm_count * 6) blocks = ctx->sm_count * 6;
+                ExtTaskI *over = sc.tasks + nb;
+                int *n_over = &sc.ctr->pad[0], *cursor2 = &sc.ctr->pad[1];
+                tail_kernel<4><<<blocks, kTailWarps * 32, 0, st>>>(idx->v, *opt, P, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan,
+                                                                   sc.st, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.tasks, h_ctr->n_tasks, nullptr,
+                                                                   &sc.ctr->tail_cursor, (unsigned long long *)d_cells, over, n_over);
+                // reads parked because an extension is longer than 127 bases (none for 150-base reads)
+                tail_kernel<16><<<ctx->sm_count * 2, kTailWarps * 32, 0, st>>>(idx->v, *opt, P, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan,
+                                                                               sc.st, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, over, 0, n_over,
+                                                                               cursor2, (unsigned long long *)d_cells, nullptr, nullptr);
+                qm_prof_end(ctx, QM_ST_EXTEND, sp, st, 2);
                 break;
             }
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
