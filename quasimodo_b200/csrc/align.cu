@@ -16,6 +16,7 @@
 //   The host loops advance -> extend until no read emits a task (one 24-byte read-back per round).
 // Tasks reference the read batch and the reference in place (ExtTaskI, QM_EXTI_INDIRECT); no sequence
 // bytes are materialised.
+#include <stdlib.h>
 #include "pipeline.cuh"
 #include "ext_warp.cuh"
 
@@ -723,7 +724,7 @@ __device__ __forceinline__ qm_ext_result tail_extend(const ExtParams &P, const I
 }
 
 constexpr int kTailWarps = 4;
-constexpr int kTailMinTasks = 8192;         // a round with fewer tasks hands the still-active reads to tail_kernel
+constexpr int kTailMinTasks = 32768;        // a round with fewer tasks hands the still-active reads to tail_kernel
 
 // MAXC = 4: only queries of <= 127 bases (every extension of a 150-base read) -- the warp-wide extension then keeps four
 // column slots per lane in registers instead of sixteen and four times as many warps fit on an SM.  A read whose next

@@ -17,12 +17,29 @@ constexpr int kWarpsPerBlock = 4;
 
 struct AlnS {                         // the fields of a qm_aln the walkers need, in shared memory
     int32_t pos, n_cigar;
+    int32_t m0, m1;                   // gap-free alignment ([clip] M [clip], the common case): query bases [m0, m1) are the
+                                      // M bases, base i sits at pos + i - m0; m1 = 0: not gap-free, walk the CIGAR
     uint32_t cigar[QM_MAX_CIGAR];
 };
+
+// [clip] <len>M [clip] ?  -> the query interval of the M bases
+__device__ __forceinline__ void simple_span(const uint32_t *cigar, int nc, int32_t *m0, int32_t *m1)
+{
+    int k = 0, x = 0;
+    *m0 = 0; *m1 = 0;
+    if (k < nc && (cigar[k] & 0xf) == 4) { x = (int)(cigar[k] >> 4); ++k; }
+    if (k >= nc || (cigar[k] & 0xf) != 0) return;
+    const int len = (int)(cigar[k] >> 4);
+    ++k;
+    if (k < nc && (cigar[k] & 0xf) == 4) ++k;
+    if (k != nc) return;
+    *m0 = x; *m1 = x + len;
+}
 
 // reference position (contig coordinate) of query base i in SEQ order, or -1 when i is not an M-type base
 __device__ __forceinline__ int rpos_of(const AlnS &a, int i)
 {
+    if (a.m1) return i >= a.m0 && i < a.m1 ? a.pos + i - a.m0 : -1;
     int x = 0, p = a.pos;
     for (int k = 0; k < a.n_cigar; ++k) {
         const int op = a.cigar[k] & 0xf, len = (int)(a.cigar[k] >> 4);
@@ -35,6 +52,7 @@ __device__ __forceinline__ int rpos_of(const AlnS &a, int i)
 // query index (SEQ order) of the M-type base aligned to contig position p, or -1
 __device__ __forceinline__ int qidx_of(const AlnS &a, int p)
 {
+    if (a.m1) return p >= a.pos && p < a.pos + (a.m1 - a.m0) ? a.m0 + (p - a.pos) : -1;
     int x = 0, pp = a.pos;
     for (int k = 0; k < a.n_cigar; ++k) {
         const int op = a.cigar[k] & 0xf, len = (int)(a.cigar[k] >> 4);
@@ -75,7 +93,10 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
             ok[e] = !(flag[e] & (0x4 | 0x100 | 0x200 | 0x400)) && nc != 0 && nc != 255 && mapq >= po.min_mapq &&
                     !((flag[e] & 0x1) && !(flag[e] & 0x2) && !po.count_orphans) && L[e] <= kMaxLen;
             if (ok[e]) {
-                if (lane == 0) { s_aln[wib][e].pos = g[e]->pos; s_aln[wib][e].n_cigar = nc; }
+                if (lane == 0) {
+                    s_aln[wib][e].pos = g[e]->pos; s_aln[wib][e].n_cigar = nc;
+                    simple_span(g[e]->cigar, nc, &s_aln[wib][e].m0, &s_aln[wib][e].m1);
+                }
                 if (lane < nc) s_aln[wib][e].cigar[lane] = g[e]->cigar[lane];
                 const uint8_t *qv = quals + (2 * pi + e) * stride;
                 for (int i = lane; i < L[e]; i += 32) s_q[wib][e][i] = rev[e] ? qv[L[e] - 1 - i] : qv[i];
