@@ -272,6 +272,22 @@ int qm_sort_keys_host(qm_ctx *ctx, const uint64_t *h_keys, int64_t n, int key_bi
 int  qm_host_alloc(qm_ctx *ctx, size_t bytes, void **out);
 void qm_host_free(qm_ctx *ctx, void *p);
 
+/* ---- duplicate removal (replaces `picard MarkDuplicates REMOVE_DUPLICATES=true`, rules/rmdup.smk:13-16, the step between
+ * rule `bwa` and every caller; semantics SURVEY.md B.9) ----
+ * Fully placed pairs are keyed by {contig, unclipped 5' coordinate, strand} of both ends; the pair with the highest sum of
+ * base qualities >= 15 stays, ties go to the earliest pair of the input.  A read with an unplaced mate is a duplicate
+ * whenever an end of a fully placed pair shares its {contig, unclipped 5' coordinate, strand}, otherwise the best such read
+ * stays.  Duplicates get flag 0x400 (the pileup's read admission skips them).
+ * qm_mark_duplicates: the records of one sample in n_chunks device chunks, input order.  Synchronous.
+ * qm_sample_set_rmdup(on) before the first pairs: the sample keeps reads and records on the device and does not count;
+ * qm_sample_rmdup_finish marks the duplicates over everything added and then counts the survivors;
+ * qm_sample_kept_alns_host returns all records (input order) with their final flags. */
+int qm_mark_duplicates(qm_ctx *ctx, int n_chunks, qm_aln *const *d_alns, const uint8_t *const *d_quals, const int32_t *strides,
+                       const int32_t *const *d_lens, const int64_t *n_pairs, int64_t *h_n_dup_pairs, void *stream);
+int qm_sample_set_rmdup(qm_sample *s, int on);
+int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream);
+int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records);
+
 /* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
  * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,
  * 4 pileup, 5 h2d, 6 d2h, 7 other.  qm_profile_collect synchronises the device and returns + clears the totals;

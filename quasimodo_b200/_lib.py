@@ -105,6 +105,10 @@ SIGNATURES = {
     "qm_sort_keys_host": (C.c_int, [_P, _P, _L, C.c_int, _P]),
     "qm_host_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p)]),
     "qm_host_free": (None, [_P, _P]),
+    "qm_mark_duplicates": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(C.c_int64), _P]),
+    "qm_sample_set_rmdup": (C.c_int, [_P, C.c_int]),
+    "qm_sample_rmdup_finish": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
+    "qm_sample_kept_alns_host": (C.c_int, [_P, _P, _L]),
     "qm_profile_enable": (C.c_int, [_P, C.c_int]),
     "qm_profile_collect": (C.c_int, [_P, _P, _P]),
     "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),

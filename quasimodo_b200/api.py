@@ -100,6 +100,21 @@ class Sample:
                                                  int(pair_id0), hp(h_alns))
         _check(self.ctx._h, rc, "qm_sample_add_pairs_host")
 
+    def set_rmdup(self, on=True):
+        """duplicate removal (picard MarkDuplicates REMOVE_DUPLICATES=true): keep reads + records, count at rmdup_finish()"""
+        _check(self.ctx._h, _lib.lib().qm_sample_set_rmdup(self._h, 1 if on else 0), "qm_sample_set_rmdup")
+
+    def rmdup_finish(self, stream=0):
+        """-> number of duplicate pairs; the count tensor then holds the survivors' counts"""
+        n = C.c_int64()
+        _check(self.ctx._h, _lib.lib().qm_sample_rmdup_finish(self._h, C.byref(n), C.c_void_p(stream)), "qm_sample_rmdup_finish")
+        return n.value
+
+    def kept_alns(self, n_pairs):
+        a = np.zeros(2 * n_pairs, dtype=_lib.ALN_DTYPE)
+        _check(self.ctx._h, _lib.lib().qm_sample_kept_alns_host(self._h, a.ctypes.data, len(a)), "qm_sample_kept_alns_host")
+        return a
+
     def counts_ptr(self):
         return _lib.lib().qm_sample_counts(self._h)
 

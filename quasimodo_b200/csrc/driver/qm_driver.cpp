@@ -4,6 +4,10 @@
 //
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf] [--gpu I] [-t THREADS] [-w BAND]
+//                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]]
+//        --rmdup: duplicates are marked on the device with picard MarkDuplicates' rule (rules/rmdup.smk:13-16) before
+//        anything is counted, as in the reference where every caller reads the .rmdup.bam; --bam still holds all records
+//        (duplicates flagged 0x400), --rmdup-bam is the REMOVE_DUPLICATES=true file
 //        = rules/bwa.smk:15-18 (bwa mem | samtools view | samtools sort | samtools index -> BAM + BAI),
 //          rules/vcfcall.smk:39 (pileup path: count TSV) and rules/vcfcall.smk:115-117 (VCF)
 //   qm_driver decontam --ref CONTAMINANT.fa[,MORE.fa] --r1 .. --r2 .. --out-r1 CLEAN1.fq --out-r2 CLEAN2.fq
@@ -692,7 +696,12 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     qm_sample *smp = nullptr;
     L.check(qm_sample_begin(L.ctx, idx, &opt, &popt, &smp), "qm_sample_begin");
 
-    const bool keep = !bam.empty() || decontam;       // records / reads needed after the batch loop
+    const bool rmdup = !decontam && atoi(a.get("rmdup", "0").c_str()) != 0;
+    const std::string rmdup_bam = a.get("rmdup-bam"), metrics = a.get("metrics");
+    if (!rmdup && (!rmdup_bam.empty() || !metrics.empty())) die(1, "--rmdup-bam / --metrics need --rmdup 1");
+    if (rmdup) L.check(qm_sample_set_rmdup(smp, 1), "qm_sample_set_rmdup");
+    const bool want_bam = !bam.empty() || !rmdup_bam.empty();
+    const bool keep = want_bam || decontam;           // records / reads needed after the batch loop
     FastqPairReader fr(a.get("r1"), a.get("r2"));
     std::vector<Batch> batches;
     std::vector<int64_t> first_read;
@@ -721,7 +730,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         }
         first_read.push_back(2 * n_pairs);
         n_pairs += b.n_pairs;
-        if (!bam.empty()) batches.push_back(std::move(b));
+        if (want_bam) batches.push_back(std::move(b));
         else free_batch(L, b);
     }
     if (decontam) {
@@ -731,6 +740,25 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     int64_t cells = 0;
     L.check(qm_sample_stats_sync(smp, nullptr, &cells, nullptr), "qm_sample_stats_sync");
     fprintf(stderr, "[qm_driver] %lld pairs aligned, %lld extension cells\n", (long long)n_pairs, (long long)cells);
+    if (rmdup) {
+        int64_t n_dup = 0;
+        L.check(qm_sample_rmdup_finish(smp, &n_dup, nullptr), "qm_sample_rmdup_finish");
+        fprintf(stderr, "[qm_driver] rmdup: %lld of %lld pairs are duplicates\n", (long long)n_dup, (long long)n_pairs);
+        if (want_bam) {                                // final flags of every record, batch by batch
+            std::vector<qm_aln> all((size_t)2 * n_pairs);
+            L.check(qm_sample_kept_alns_host(smp, all.data(), (int64_t)all.size()), "qm_sample_kept_alns_host");
+            size_t off = 0;
+            for (auto &b : batches) { memcpy(b.alns, all.data() + off, (size_t)2 * b.n_pairs * sizeof(qm_aln)); off += (size_t)2 * b.n_pairs; }
+        }
+        if (!metrics.empty()) {
+            FILE *fm = fopen(metrics.c_str(), "w");
+            if (!fm) die(2, "cannot create %s", metrics.c_str());
+            fprintf(fm, "## METRICS CLASS\tquasimodo_b200.DuplicationMetrics\nLIBRARY\tREAD_PAIRS_EXAMINED\tREAD_PAIR_DUPLICATES\tPERCENT_DUPLICATION\n"
+                        "%s\t%lld\t%lld\t%.6f\n", a.get("sample", "sample").c_str(), (long long)n_pairs, (long long)n_dup,
+                    n_pairs ? (double)n_dup / (double)n_pairs : 0.0);
+            fclose(fm);
+        }
+    }
 
     if (!counts.empty()) {
         std::vector<int32_t> rows(g.codes.size() * QM_NCH);
@@ -748,7 +776,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         calls.resize((size_t)nc);
         write_vcf(vcf, g, a.get("sample", "sample"), split(a.get("ref"), ',')[0], calls);
     }
-    if (!bam.empty()) {
+    if (want_bam) {
         // coordinate sort on the device: keys from the records, stable radix sort, gather through the permutation
         int pos_bits = 0;
         const int key_bits = sort_key_bits(g, pos_bits);
@@ -759,7 +787,16 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
                 keys[k] = qm_sort_key(b.alns[r].rid, b.alns[r].pos, (b.alns[r].flag & 0x10) != 0, (int)g.names.size(), pos_bits);
         std::vector<uint32_t> perm(keys.size());
         L.check(qm_sort_keys_host(L.ctx, keys.data(), (int64_t)keys.size(), key_bits, perm.data()), "qm_sort_keys_host");
-        write_bam(bam, g, batches, perm, first_read, cmdline, threads);
+        if (!bam.empty()) write_bam(bam, g, batches, perm, first_read, cmdline, threads);
+        if (!rmdup_bam.empty()) {                      // REMOVE_DUPLICATES=true: the same order without the flagged records
+            std::vector<uint32_t> kept_perm;
+            kept_perm.reserve(perm.size());
+            for (uint32_t gr : perm) {
+                const size_t bi = (size_t)(std::upper_bound(first_read.begin(), first_read.end(), (int64_t)gr) - first_read.begin()) - 1;
+                if (!(batches[bi].alns[gr - first_read[bi]].flag & 0x400)) kept_perm.push_back(gr);
+            }
+            write_bam(rmdup_bam, g, batches, kept_perm, first_read, cmdline, threads);
+        }
     }
     for (auto &b : batches) free_batch(L, b);
     qm_sample_destroy(smp);

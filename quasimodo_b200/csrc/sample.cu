@@ -36,6 +36,11 @@ struct qm_sample {
     bool have_pes = false;
     qm_pestat pes[4];
     int64_t n_pairs = 0;
+    // duplicate removal (qm_sample_set_rmdup): every chunk's reads and records stay on the device, counting waits for
+    // qm_sample_rmdup_finish
+    bool rmdup = false;
+    struct Kept { uint8_t *codes, *quals; int32_t *lens; qm_aln *alns; int64_t n; int32_t stride; };
+    std::vector<Kept> kept;
 };
 
 namespace {
@@ -56,6 +61,25 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
     qm_aln *alns = d_alns_out ? d_alns_out : s->d_alns;
     rc = qm_pair_finish(ctx, s->idx, &s->opt, d_codes, stride, d_lens, n, pair_id0, s->d_regs, s->d_n_regs, s->pes, alns, st);
     if (rc) return rc;
+    if (s->rmdup) {
+        // keep the chunk for qm_sample_rmdup_finish: duplicates are a property of the whole sample
+        qm_sample::Kept k = {nullptr, nullptr, nullptr, nullptr, n, stride};
+        const size_t sb = (size_t)2 * n * stride;
+        cudaError_t e;
+        if ((e = cudaMalloc(&k.codes, sb)) != cudaSuccess || (e = cudaMalloc(&k.quals, sb)) != cudaSuccess ||
+            (e = cudaMalloc(&k.lens, (size_t)2 * n * 4)) != cudaSuccess || (e = cudaMalloc(&k.alns, (size_t)2 * n * sizeof(qm_aln))) != cudaSuccess) {
+            cudaFree(k.codes); cudaFree(k.quals); cudaFree(k.lens); cudaFree(k.alns);
+            return qm_fail(ctx, QM_ENOMEM, "rmdup: cannot keep a chunk of %lld pairs on the device: %s", (long long)n, cudaGetErrorString(e));
+        }
+        if (quals_ready) QM_CUDA(ctx, cudaStreamWaitEvent(st, quals_ready, 0));
+        QM_CUDA(ctx, cudaMemcpyAsync(k.codes, d_codes, sb, cudaMemcpyDeviceToDevice, st));
+        QM_CUDA(ctx, cudaMemcpyAsync(k.quals, d_quals, sb, cudaMemcpyDeviceToDevice, st));
+        QM_CUDA(ctx, cudaMemcpyAsync(k.lens, d_lens, (size_t)2 * n * 4, cudaMemcpyDeviceToDevice, st));
+        QM_CUDA(ctx, cudaMemcpyAsync(k.alns, alns, (size_t)2 * n * sizeof(qm_aln), cudaMemcpyDeviceToDevice, st));
+        s->kept.push_back(k);
+        s->n_pairs += n;
+        return QM_OK;
+    }
     if (quals_ready) QM_CUDA(ctx, cudaStreamWaitEvent(st, quals_ready, 0));
     rc = qm_pileup_accumulate(ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n, s->d_counts, st);
     if (rc) return rc;
@@ -96,11 +120,18 @@ int qm_sample_begin(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const q
     return QM_OK;
 }
 
+static void free_kept(qm_sample *s)
+{
+    for (auto &k : s->kept) { cudaFree(k.codes); cudaFree(k.quals); cudaFree(k.lens); cudaFree(k.alns); }
+    s->kept.clear();
+}
+
 void qm_sample_destroy(qm_sample *s)
 {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaDeviceSynchronize();
+    free_kept(s);
     cudaFree(s->d_counts); cudaFree(s->d_cells); cudaFree(s->d_regs); cudaFree(s->d_n_regs); cudaFree(s->d_alns);
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->d_stage[i]);
@@ -121,6 +152,58 @@ int qm_sample_reset(qm_sample *s, void *stream)
     QM_CUDA(ctx, cudaMemsetAsync(s->d_counts, 0, (size_t)QM_NCH * s->idx->v.l_pac * sizeof(int32_t), (cudaStream_t)stream));
     QM_CUDA(ctx, cudaMemsetAsync(s->d_cells, 0, 8, (cudaStream_t)stream));
     s->have_pes = false; s->n_pairs = 0;
+    if (!s->kept.empty()) { QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream)); free_kept(s); }
+    return QM_OK;
+}
+
+// ---- duplicate removal (the reference's rule `rmdup`: picard MarkDuplicates REMOVE_DUPLICATES=true, rules/rmdup.smk:13-16) ----
+int qm_sample_set_rmdup(qm_sample *s, int on)
+{
+    if (!s) return QM_EINVAL;
+    if (s->n_pairs != 0) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_set_rmdup: pairs were already added; reset the sample first");
+    s->rmdup = on != 0;
+    return QM_OK;
+}
+
+// marks the duplicates among everything added since the last reset (flag 0x400 on their records), then counts the rest
+int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
+{
+    if (!s) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    if (!s->rmdup) return qm_fail(ctx, QM_EINVAL, "qm_sample_rmdup_finish: the sample is not in rmdup mode");
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    QM_CUDA(ctx, cudaDeviceSynchronize());                 // chunks may have been added on any stream
+    const int nc = (int)s->kept.size();
+    std::vector<qm_aln *> a(nc);
+    std::vector<const uint8_t *> q(nc);
+    std::vector<const int32_t *> l(nc);
+    std::vector<int32_t> st(nc);
+    std::vector<int64_t> n(nc);
+    for (int c = 0; c < nc; ++c) { a[c] = s->kept[c].alns; q[c] = s->kept[c].quals; l[c] = s->kept[c].lens; st[c] = s->kept[c].stride; n[c] = s->kept[c].n; }
+    int rc = qm_mark_duplicates(ctx, nc, a.data(), q.data(), st.data(), l.data(), n.data(), n_dup_pairs, stream);
+    if (rc) return rc;
+    for (int c = 0; c < nc; ++c) {
+        const auto &k = s->kept[c];
+        rc = qm_pileup_accumulate(ctx, s->idx, &s->popt, k.alns, k.codes, k.quals, k.stride, k.lens, k.n, s->d_counts, stream);
+        if (rc) return rc;
+    }
+    QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    for (auto &k : s->kept) { cudaFree(k.codes); cudaFree(k.quals); cudaFree(k.lens); k.codes = k.quals = nullptr; k.lens = nullptr; }
+    return QM_OK;
+}
+
+// the records of everything added in rmdup mode, in input order, with their final flags; synchronous
+int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records)
+{
+    if (!s || (!h_alns && max_records > 0)) return QM_EINVAL;
+    qm_ctx *ctx = s->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t off = 0;
+    for (auto &k : s->kept) {
+        if (off + 2 * k.n > max_records) return qm_fail(ctx, QM_EINVAL, "qm_sample_kept_alns_host: buffer of %lld records is too small", (long long)max_records);
+        QM_CUDA(ctx, cudaMemcpy(h_alns + off, k.alns, (size_t)2 * k.n * sizeof(qm_aln), cudaMemcpyDeviceToHost));
+        off += 2 * k.n;
+    }
     return QM_OK;
 }
 
