@@ -81,3 +81,18 @@ def test_shards_sum_to_whole(run):
         assert pes.tobytes() == run["pes"].tobytes()
         total += c
     assert np.array_equal(total, run["counts"])
+
+
+def test_packed_genomes_equal_bwas_own_index_files():
+    """the genomes this repo ships (quasimodo_b200/data/genomes/*.qmg) against digests of the reference's own bwa index
+    (ref/*.pac + *.ann, tests/golden/make_pac_digests.py): same contigs, same lengths, same bases"""
+    import hashlib
+    import json
+    import os
+    from quasimodo_b200 import genomes
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pac_digests.json")))
+    assert set(gold) == {"Merlin", "TB40E", "AD169", "Phix", "Ecoli"}
+    for stem, g in gold.items():
+        G = genomes.load(stem)
+        assert G.names == g["names"] and G.lens == g["lens"] and G.total == g["l_pac"], stem
+        assert hashlib.sha256(G.codes.tobytes()).hexdigest() == g["sha256_codes"], stem
