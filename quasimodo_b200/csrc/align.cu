@@ -139,6 +139,10 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
     int64_t trk_p = -1;             // forward position of the previous k-mer's only hit, -1 = none / several
     int64_t trk_p2 = -1;            // >= 0: the previous k-mer had one hit per strand, trk_p (as is) and trk_p2 (reverse complement)
     int trk_pass = 0;               // strand of a lone hit: 0 = read k-mer as is, 1 = reverse complement
+    // 2..4 hits of any strand mix (repeats in a few copies): all of them tracked, in look-up order
+    int nt = 0;
+    int64_t tp[4] = {0, 0, 0, 0};
+    unsigned tpass = 0;             // bit t: strand of tracked hit t
     // the seed each strand is currently growing lives in registers (a clean read extends ONE seed ~120 times);
     // S[] in global memory is only touched when a seed is created, looked for, or handed back
     int64_t cur_diag[2] = {0, 0};
@@ -169,6 +173,55 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
     const int q_last = len - k;                         // last k-mer start
     int q = 0;
     while (q <= q_last) {
+        if (nt >= 2) {
+            // every hit of position q-1 is tracked: position q+j has exactly these hits, one step further, as long as the new
+            // read base continues ALL of them and the index says the reference k-mer there occurs nt times in total
+            const int nb = q + k - 1;
+            const uint64_t rbits = R.get2(nb);
+            const uint32_t nbits = (uint32_t)R.getn(nb);
+            int m = nbits ? __ffs((int)nbits) - 1 : 32;
+            if (m > q_last - q + 1) m = q_last - q + 1;
+            {
+                const uint32_t *map = V.cnteqp[nt - 2];
+                const uint32_t cm = (tpass & 1u) ? __brev(uniq_get(map, tp[0] - 32)) : uniq_get(map, tp[0] + 1);
+                const int m_c = ~cm ? __ffs((int)~cm) - 1 : 32;
+                m = m < m_c ? m : m_c;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (t >= nt) break;
+                const bool r = (tpass >> t) & 1u;
+                const uint64_t x = rbits ^ (r ? ~grouprev(ref_get2(V, tp[t] - 32)) : ref_get2(V, tp[t] + k));
+                const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+                const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
+                const int64_t lim = r ? tp[t] : V.l_pac - k - tp[t];
+                m = m < m_b ? m : m_b; m = (int64_t)m > lim ? (int)lim : m;
+            }
+            if (m > 0) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t >= nt) break;
+                    const int pass = (int)((tpass >> t) & 1u);
+                    const int64_t rpos = pass ? 2 * V.l_pac - tp[t] - k : tp[t];             // of the hit at q-1
+                    const int64_t diag = rpos - (q - 1);
+                    if (cur_idx[pass] >= 0 && cur_diag[pass] == diag && cur_qnext[pass] == q) { cur_len[pass] += m; cur_qnext[pass] += m; }
+                    else {
+                        flush();
+                        for (int sidx = 0; sidx < n; ++sidx)
+                            if (S[sidx].rbeg - S[sidx].qbeg == diag && S[sidx].qbeg + S[sidx].len - k + 1 == q) {
+                                S[sidx].len += m;
+                                cur_idx[pass] = sidx; cur_len[pass] = S[sidx].len; cur_diag[pass] = diag; cur_qnext[pass] = q + m;
+                                break;
+                            }
+                    }
+                    tp[t] += pass ? -m : m;
+                }
+                q += m;
+                if (m == 32) continue;
+                if (q > q_last) break;
+            }
+            // position q does not continue all of them: the general path below decides
+        }
         if (trk_p >= 0) {
             // How many of the positions q, q+1, ... continue the match of position q-1 (at most 32 per step).  Tracked is
             // either the ONLY hit of that k-mer (trk_p on strand trk_pass; trk_p2 < 0) or its only hit on EACH strand
@@ -216,7 +269,7 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
         }
         const uint64_t nm = R.getn(q) & kbits;
         if (nm) {                                       // an N inside the k-mer: skip every k-mer that covers it
-            trk_p = -1; trk_p2 = -1;
+            trk_p = -1; trk_p2 = -1; nt = 0;
             q += 64 - __clzll((long long)nm);
             continue;
         }
@@ -230,25 +283,30 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
             qm_bloom_pos(fw < rc ? fw : rc, V.bloom_bits, bp);
             const uint32_t hit = (__ldg(&bloom[bp[0] >> 5]) >> (bp[0] & 31)) & (__ldg(&bloom[bp[1] >> 5]) >> (bp[1] & 31)) &
                                  (__ldg(&bloom[bp[2] >> 5]) >> (bp[2] & 31)) & 1u;
-            if (!hit) { trk_p = -1; trk_p2 = -1; ++q; continue; }
+            if (!hit) { trk_p = -1; trk_p2 = -1; nt = 0; ++q; continue; }
         }
         int n_hits = 0, one_pass = 0, n_pass[2] = {0, 0};
         int64_t one_p = -1, p_of[2] = {-1, -1};
+        bool ignored = false;
+        nt = 0; tpass = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             uint32_t first, cnt;
             if (!qm_idx_lookup(V, pass ? rc : fw, first, cnt)) continue;
-            if (cnt > occ_cap) { n_hits += 2; continue; }          // ignored k-mer: never a tracked single hit
+            if (cnt > occ_cap) { n_hits += 2; ignored = true; continue; }          // ignored k-mer: nothing of this position is tracked
             for (uint32_t t = 0; t < cnt; ++t) {
                 const int64_t p = V.pos[first + t];
                 add_hit(pass, p, q, cnt == 1);
                 one_p = p; one_pass = pass; p_of[pass] = p;
+                if (nt < 4) { tp[nt] = p; tpass |= (unsigned)pass << nt; }
+                ++nt;
             }
             n_hits += (int)cnt; n_pass[pass] = (int)cnt;
         }
         trk_p = -1; trk_p2 = -1;
-        if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; }
-        else if (n_hits == 2 && n_pass[0] == 1 && n_pass[1] == 1) { trk_p = p_of[0]; trk_p2 = p_of[1]; trk_pass = 0; }
+        if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; nt = 0; }
+        else if (n_hits == 2 && n_pass[0] == 1 && n_pass[1] == 1) { trk_p = p_of[0]; trk_p2 = p_of[1]; trk_pass = 0; nt = 0; }
+        else if (ignored || nt < 2 || nt > 4) nt = 0;                  // (otherwise: 2..4 hits, all tracked)
         ++q;
     }
     flush();

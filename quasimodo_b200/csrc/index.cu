@@ -67,6 +67,8 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
     }
     // uniqueness bitmap: k-mer occurs once and its reverse complement never (see IndexView::uniq)
     std::vector<uint32_t> uniq((size_t)(total + 31) / 32 + 1, 0u), uniq2((size_t)(total + 31) / 32 + 1, 0u);
+    std::vector<uint32_t> cnteqp[3];
+    for (auto &m : cnteqp) m.assign((size_t)(total + 32 + 31) / 32 + 2, 0u);
     {
         auto count_of = [&](uint64_t key) -> uint32_t {
             uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> v.shift;
@@ -81,6 +83,16 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         for (size_t i = 0; i < km.size();) {
             size_t j = i;
             while (j < km.size() && km[j].first == km[i].first) ++j;
+            {   // total occurrences on both strands in 2..4: the padded "count == T" bitmaps
+                const uint64_t key = km[i].first;
+                uint64_t rc = 0;
+                for (int b = 0; b < k; ++b) rc |= (uint64_t)(3 - ((key >> (2 * b)) & 3)) << (2 * (k - 1 - b));
+                if (rc != key) {
+                    const size_t tot = (j - i) + count_of(rc);
+                    if (tot >= 2 && tot <= 4)
+                        for (size_t t = i; t < j; ++t) { const size_t x = (size_t)km[t].second + 32; cnteqp[tot - 2][x >> 5] |= 1u << (x & 31); }
+                }
+            }
             if (j - i == 1) {
                 const uint64_t key = km[i].first;
                 uint64_t rc = 0;
@@ -139,6 +151,14 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
     }
     v.ref2p = (const uint64_t *)ix->d_ref2p; v.uniqp = (const uint32_t *)ix->d_uniqp; v.uniq2p = (const uint32_t *)ix->d_uniq2p;
+    for (int t = 0; t < 3; ++t) {
+        if ((e = cudaMalloc(&ix->d_cnteqp[t], cnteqp[t].size() * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(ix->d_cnteqp[t], cnteqp[t].data(), cnteqp[t].size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            qm_index_destroy(ctx, ix);
+            return qm_fail(ctx, QM_ECUDA, "qm_index_build: %s", cudaGetErrorString(e));
+        }
+        v.cnteqp[t] = (const uint32_t *)ix->d_cnteqp[t];
+    }
     if ((e = cudaMalloc(&ix->d_uniq, uniq.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_uniq, uniq.data(), uniq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
@@ -168,6 +188,7 @@ void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
     if (ix->d_ref2p) cudaFree(ix->d_ref2p);
     if (ix->d_uniqp) cudaFree(ix->d_uniqp);
     if (ix->d_uniq2p) cudaFree(ix->d_uniq2p);
+    for (int t = 0; t < 3; ++t) if (ix->d_cnteqp[t]) cudaFree(ix->d_cnteqp[t]);
     delete ix;
 }
 

@@ -15,6 +15,8 @@ struct IndexView {
     const uint32_t *uniqp;    // the uniq bitmap with the same padding: bit x+32 (pad bits are 0)
     const uint32_t *uniq2p;   // same layout: the k-mer starting at x occurs once, and its reverse complement occurs once too
                               // (inverted repeats): a read k-mer equal to it has exactly one hit per strand
+    const uint32_t *cnteqp[3];// same layout: the k-mer starting at x and its reverse complement occur 2 / 3 / 4 times in total
+                              // (repeats in a few copies): a read k-mer equal to it has exactly that many hits
     const uint32_t *bloom;    // Bloom filter over the canonical (min of k-mer and its reverse complement) reference k-mers,
     uint32_t bloom_bits;      // 3 hash functions; 0 bits = no filter (reference too large for a shared-memory filter)
     uint64_t mask;            // table size - 1
@@ -27,7 +29,7 @@ struct IndexView {
 struct qm_index {
     IndexView v;
     void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr, *d_uniq = nullptr, *d_bloom = nullptr, *d_ref2p = nullptr,
-         *d_uniqp = nullptr, *d_uniq2p = nullptr;
+         *d_uniqp = nullptr, *d_uniq2p = nullptr, *d_cnteqp[3] = {nullptr, nullptr, nullptr};
     int64_t n_kmers = 0, n_unique = 0, table_size = 0;
 };
 
