@@ -900,8 +900,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
     SeScratch sc;
     int rc = se_scratch(ctx, nbmax, &sc);
     if (rc) return rc;
-    RoundCounters *h_ctr = nullptr;
-    QM_CUDA(ctx, cudaMallocHost(&h_ctr, sizeof(RoundCounters)));
+    static_assert(kRoundHeader <= 8192, "round header must fit the context's pinned buffer");
+    RoundCounters *h_ctr = (RoundCounters *)ctx->h_pinned;          // only the first kRoundHeader bytes are ever read back
     const ExtParams P = qm_ext_params(opt);
     const int tpb = 128;
     for (int64_t b0 = 0; b0 < n_reads; b0 += kSeBatch) {
@@ -940,7 +940,7 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
             cudaMemcpyAsync(h_ctr, sc.ctr, kRoundHeader, cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { cudaFreeHost(h_ctr); return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
+            if (e != cudaSuccess) { return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
             if (h_ctr->n_tasks == 0) break;
             if (h_ctr->n_tasks < kTailMinTasks) {
                 // few reads left: finish them on the device, one warp per read, no more round trips
@@ -970,10 +970,9 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                                        h_ctr->class_count, sc.res, sc.lists + (int64_t)kExtClasses * nb, sc.ctr->fb, st,
                                        h_ctr->max_score <= 255);
             qm_prof_end(ctx, QM_ST_EXTEND, sp, st, n_launch);
-            if (rc) { cudaFreeHost(h_ctr); return rc; }
+            if (rc) return rc;
         }
     }
-    cudaFreeHost(h_ctr);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }

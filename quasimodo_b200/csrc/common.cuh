@@ -34,6 +34,7 @@ struct qm_ctx {
     int se_n_parts = 0;
     int64_t se_part_end[16] = {};
     cudaEvent_t se_part_ev[16] = {};
+    void *h_pinned = nullptr;          // 8 KB of page-locked host memory for the small per-round read-backs
     bool prof_on = false;
     std::vector<qm_prof_span> prof_spans;
     std::vector<cudaEvent_t> prof_pool;

@@ -121,6 +121,7 @@ int qm_ctx_create(int device, qm_ctx **out)
             cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { qm_ctx_destroy(c); return QM_ECUDA; }
     }
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { qm_ctx_destroy(c); return QM_ECUDA; }
+    if (cudaMallocHost(&c->h_pinned, 8192) != cudaSuccess) { qm_ctx_destroy(c); return QM_ENOMEM; }
     *out = c;
     return QM_OK;
 }
@@ -137,6 +138,7 @@ void qm_ctx_destroy(qm_ctx *ctx)
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     delete ctx;

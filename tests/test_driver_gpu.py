@@ -194,3 +194,39 @@ def test_driver_fails_loudly_without_outputs(tmp_path, sample_case):
     assert p.returncode == 1
     p = drvutil.run_driver(["sample", "--ref", sample_case["fa"], "--r1", sample_case["r1"], "--r2", sample_case["r2"], "--gpu", 99], check=False)
     assert p.returncode == 3 and "no usable B200" in p.stderr
+
+
+def test_driver_edge_inputs(tmp_path):
+    """empty input, a single pair, reads shorter than the seed length, all-N reads: the driver still writes valid files"""
+    from quasimodo_b200 import genomes
+    from tests import bamio, drvutil
+    phix = genomes.load("Phix")
+    fa = str(tmp_path / "phix.fa")
+    drvutil.write_fasta(phix, fa)
+    seq = "".join("ACGT"[c] for c in phix.codes[100:250])
+    rc = "".join("ACGT"[3 - c] for c in phix.codes[300:450][::-1])
+    cases = {
+        "empty": [],
+        "one": [("p0", seq, rc)],
+        "odd": [("p0", seq, rc), ("short", seq[:20], rc[:25]), ("allN", "N" * 150, "N" * 150), ("p1", seq[:100], rc[:131])],
+    }
+    for tag, pairs in cases.items():
+        r1, r2 = str(tmp_path / f"{tag}.r1.fq"), str(tmp_path / f"{tag}.r2.fq")
+        with open(r1, "w") as f1, open(r2, "w") as f2:
+            for nm, a, b in pairs:
+                f1.write(f"@{nm}/1\n{a}\n+\n{'I' * len(a)}\n")
+                f2.write(f"@{nm}/2\n{b}\n+\n{'I' * len(b)}\n")
+        bam, tsv, vcf = (str(tmp_path / f"{tag}.{x}") for x in ("bam", "tsv", "vcf"))
+        drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--bam", bam, "--counts", tsv, "--vcf", vcf])
+        B = bamio.Bam(bam)
+        assert len(B.records) == 2 * len(pairs)
+        assert sum(1 for _ in open(tsv)) == 1 + phix.total
+        assert open(vcf).read().startswith("##fileformat=VCFv4.2")
+        bamio.read_bai(bam + ".bai")
+        if tag != "empty":
+            first = [r for r in B.records if r["name"] == "p0"]
+            assert sorted(r["pos"] for r in first) == [100, 300] and all(r["tags"]["NM"] == 0 for r in first)
+        if tag == "odd":
+            by = {(r["name"], r["flag"] & 0x40): r for r in B.records}
+            assert by[("short", 0x40)]["flag"] & 4 and by[("allN", 0x40)]["flag"] & 4 and by[("allN", 0)]["seq"] == "N" * 150
+            assert by[("p1", 0x40)]["pos"] == 100 and by[("p1", 0)]["cigar"] == [131 << 4]
