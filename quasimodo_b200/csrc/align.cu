@@ -537,7 +537,7 @@ constexpr size_t kRoundHeader = (2 * kExtCtr + 8) * sizeof(int);
 // regions sorted / de-duplicated, *n_regs_out set).
 __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t *query, int lq, const qm_seed *S, uint16_t *PL,
                              int np, ReadState &s, qm_reg *av, int32_t *n_regs_out, const qm_ext_result *xres, int64_t r,
-                             ExtTaskI *t_out, unsigned long long *cells)
+                             ExtTaskI *t_out, unsigned long long *cells /* caller's local sum, may be NULL */)
 {
     const int64_t l_pac = V.l_pac;
 
@@ -545,7 +545,7 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
         const qm_ext_result x = *xres;
         const qm_seed sd = S[PL[s.cursor] & 63];
         qm_reg *a = &av[s.n_av];
-        if (cells) atomicAdd(cells, (unsigned long long)x.cells);
+        if (cells) *cells += (unsigned long long)x.cells;
         a->score = x.score; a->w = x.w_used;
         if (x.gscore <= 0 || x.gscore <= x.score - o.pen_clip5) { a->qb = sd.qbeg - x.qle; a->rb = sd.rbeg - x.tle; a->truesc = x.score; }
         else { a->qb = 0; a->rb = sd.rbeg - x.gtle; a->truesc = x.gscore; }
@@ -555,7 +555,7 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
         const qm_seed sd = S[PL[s.cursor] & 63];
         qm_reg *a = &av[s.n_av];
         const int sc0 = a->score;        // score before the right extension (= the task's h0)
-        if (cells) atomicAdd(cells, (unsigned long long)x.cells);
+        if (cells) *cells += (unsigned long long)x.cells;
         const int qe = sd.qbeg + sd.len;
         const int64_t re = sd.rbeg + sd.len;
         a->score = x.score;
@@ -706,6 +706,10 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
     }
 }
 
+// The round's counters sit at a handful of addresses (task count, 10 class counts, 512 length bins, the cell total, the
+// score maximum) and every read that emits a task used to hit five of them with its own atomic: two million same-address
+// atomics per round, serialised in L2.  They are combined first -- per block in shared memory for the bins, per warp for
+// the task slots, the cell sum and the maximum -- so that a block issues a few dozen global atomics instead of hundreds.
 __global__ void __launch_bounds__(128)
 advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
                int64_t n, const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
@@ -713,22 +717,48 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
                const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks,
                RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
 {
+    __shared__ int s_hist[512];
+    __shared__ int s_class[kExtCtr];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x < kExtCtr) s_class[threadIdx.x] = 0;
+    __syncthreads();
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    ReadState s = st[r];
-    if (s.phase == PH_DONE) return;
+    const int lane = qm_lane();
+    ReadState s;
+    bool live = r < n;
+    if (live) { s = st[r]; live = s.phase != PH_DONE; }
     ExtTaskI t;
-    const bool emit = advance_read(V, o, codes + r * stride, lens[r], seeds + r * QM_MAX_SEEDS, plan + r * QM_MAX_SEEDS, n_plan[r], s,
-                                   regs + r * QM_MAX_REGS, n_regs + r, s.task >= 0 ? res + s.task : nullptr, r, &t, cells);
+    unsigned long long my_cells = 0;
+    bool emit = false;
+    if (live)
+        emit = advance_read(V, o, codes + r * stride, lens[r], seeds + r * QM_MAX_SEEDS, plan + r * QM_MAX_SEEDS, n_plan[r], s,
+                            regs + r * QM_MAX_REGS, n_regs + r, s.task >= 0 ? res + s.task : nullptr, r, &t, &my_cells);
+    // task slots: one atomic per warp
+    const unsigned em = __ballot_sync(0xffffffffu, emit);
+    int base = 0;
+    if (lane == 0 && em) base = atomicAdd(&ctr->n_tasks, __popc(em));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int score = 0;
     if (emit) {
-        const int slot = atomicAdd(&ctr->n_tasks, 1);
+        const int slot = base + __popc(em & ((1u << lane) - 1u));
         tasks[slot] = t;
-        atomicAdd(&ctr->class_count[qm_ext_class(t.qlen)], 1);
-        atomicAdd(&ctr->hist[t.qlen], 1);
-        atomicMax(&ctr->max_score, t.h0 + t.qlen * o.a);
+        atomicAdd(&s_class[qm_ext_class(t.qlen)], 1);
+        atomicAdd(&s_hist[t.qlen], 1);
+        score = t.h0 + t.qlen * o.a;
         s.task = slot;
     }
-    st[r] = s;
+    if (live) st[r] = s;
+    const int wmax = __reduce_max_sync(0xffffffffu, score);
+    if (lane == 0 && wmax > 0) atomicMax(&ctr->max_score, wmax);
+    if (cells) {
+        // 64-bit sum over the warp
+        unsigned long long v = my_cells;
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane == 0 && v) atomicAdd(cells, v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) if (s_hist[i]) atomicAdd(&ctr->hist[i], s_hist[i]);
+    if (threadIdx.x < kExtCtr && s_class[threadIdx.x]) atomicAdd(&ctr->class_count[threadIdx.x], s_class[threadIdx.x]);
 }
 
 // Counting sort of a round's tasks by query length into the per-class lists: warp-mates of the thread-per-task
@@ -800,6 +830,7 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
     __shared__ int s_more[kTailWarps];
     const int lane = qm_lane(), wib = threadIdx.x >> 5;
     const int n_tasks = n_tasks_dev ? *n_tasks_dev : n_tasks_host;
+    unsigned long long my_cells = 0;               // lane 0: executed cells of this warp's reads, added once at the end
     for (;;) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(cursor, 1);
@@ -827,7 +858,7 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
                 s_res[wib] = x;
                 ExtTaskI nt;
                 const bool more = advance_read(V, o, codes + r * stride, lens[r], seeds + r * QM_MAX_SEEDS, plan + r * QM_MAX_SEEDS,
-                                               n_plan[r], s, regs + r * QM_MAX_REGS, n_regs + r, &s_res[wib], r, &nt, cells);
+                                               n_plan[r], s, regs + r * QM_MAX_REGS, n_regs + r, &s_res[wib], r, &nt, &my_cells);
                 if (more) s_task[wib] = nt;
                 s_more[wib] = more ? 1 : 0;
             }
@@ -837,6 +868,7 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
         if (lane == 0 && !parked) { s.task = -1; st[r] = s; }
         __syncwarp();
     }
+    if (lane == 0 && cells && my_cells) atomicAdd(cells, my_cells);
 }
 
 constexpr int64_t kSeBatch = 1 << 22;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
