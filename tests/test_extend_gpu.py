@@ -80,3 +80,17 @@ def test_extend_rejects_bad_task(ctx):
     seq, tasks = pack_ext_tasks([(np.zeros(600, np.uint8), np.zeros(10, np.uint8))], [31], [100], 5)
     with pytest.raises(QmError):
         ctx.extend_batch_host(seq, tasks)
+
+
+def test_paired_kernel_variant_is_bit_exact():
+    """the two-tasks-per-thread s16x2 kernel (extend2p.cu, off by default, QM_PAIRED=1) on the random, adversarial and
+    band-retry tasks above; the switch is read once per process, hence the subprocess"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("QM_PAIRED"):
+        pytest.skip("already inside the QM_PAIRED run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_extend_gpu.py", "-q", "-x", "-k", "random or adversarial or band_retry"],
+                       cwd=root, env=dict(os.environ, QM_PAIRED="1"), capture_output=True, text=True)
+    assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
