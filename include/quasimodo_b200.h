@@ -48,8 +48,10 @@ typedef struct {
     int32_t mapq_coef_len;
     float   mask_level, drop_ratio, mask_level_redun;
     int32_t min_chain_weight;
-    int32_t reserved[3];
+    int32_t flags;                /* QM_F_*                                              */
+    int32_t reserved[2];
 } qm_opt;
+#define QM_F_NO_RESCUE 1          /* bwa mem -S: skip mate rescue                        */
 
 void qm_opt_default(qm_opt *opt);
 
@@ -112,7 +114,7 @@ int64_t qm_index_lpac(const qm_index *idx);
  *                             mem_chain_flt), extension (mem_chain2aln -> the batched ksw_extend2 kernel),
  *                             redundancy removal (mem_sort_dedup_patch) -> per-read region lists.
  * Stage 2  qm_pestat_sync   : insert-size model of the batch (bwamem_pair.c mem_pestat).
- * Stage 3  qm_pair_finish   : primary marking, pairing, MAPQ (mem_sam_pe without mate rescue), CIGAR/NM
+ * Stage 3  qm_pair_finish   : mate rescue (qm_mate_rescue), primary marking, pairing, MAPQ (mem_sam_pe), CIGAR/NM
  *                             (mem_reg2aln -> bwa_gen_cigar2 -> ksw_global2), SAM flags -> qm_aln records.
  * Hard limits (shared with the oracle): QM_MAX_SEEDS seeds and QM_MAX_REGS regions per read, k-mers with
  * more than min(max_occ, QM_OCC_CAP) occurrences are ignored, QM_MAX_CIGAR operations per alignment. */
@@ -147,6 +149,14 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 int64_t *d_cells, void *stream);
 int qm_pestat_sync(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm_reg *d_regs, const int32_t *d_n_regs,
                    int64_t n_pairs, qm_pestat h_pes[4], void *stream);
+/* mate rescue (bwamem_pair.c mem_matesw as driven by mem_sam_pe; ksw.c ksw_align2): for every region of an end that
+ * scores within pen_unpaired of the end's best and has no properly placed region of the mate, the mate is aligned
+ * locally inside the window the insert-size model implies; hits of at least min_seed_len join the mate's list.
+ * d_regs / d_n_regs are updated in place.  d_stats (may be NULL): two int64, += local alignments run, += their cells.
+ * qm_pair_finish runs it first unless opt->flags & QM_F_NO_RESCUE.  Windows longer than 4096 bases are not searched. */
+int qm_mate_rescue(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
+                   const int32_t *d_lens, int64_t n_pairs, qm_reg *d_regs, int32_t *d_n_regs, const qm_pestat pes[4],
+                   int64_t *d_stats, void *stream);
 int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8_t *d_codes, int32_t stride,
                    const int32_t *d_lens, int64_t n_pairs, int64_t pair_id0, qm_reg *d_regs, int32_t *d_n_regs,
                    const qm_pestat h_pes[4], qm_aln *d_alns, void *stream);
@@ -290,9 +300,9 @@ int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records);
 
 /* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
  * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,
- * 4 pileup, 5 h2d, 6 d2h, 7 other.  qm_profile_collect synchronises the device and returns + clears the totals;
+ * 4 pileup, 5 h2d, 6 d2h, 7 other, 8 mate rescue.  qm_profile_collect synchronises the device and returns + clears the totals;
  * launch counts are kept even when timing is disabled. */
-#define QM_N_STAGES 8
+#define QM_N_STAGES 9
 int qm_profile_enable(qm_ctx *ctx, int on);
 int qm_profile_collect(qm_ctx *ctx, double ms_out[QM_N_STAGES], int64_t launches_out[QM_N_STAGES]);
 

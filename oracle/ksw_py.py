@@ -73,3 +73,51 @@ def ksw_extend2(query, target, h0, w, end_bonus, a=1, b=4, o_del=6, e_del=1, o_i
             j -= 1
         end = min(j + 2, qlen)
     return (mx, mx_j + 1, mx_i + 1, mx_ie + 1, gscore, max_off), cells
+
+
+def _local_matrix(query, target, a, b, o_del, e_del, o_ins, e_ins):
+    """Full H matrix of the affine local alignment (rows = target, columns = query), Gotoh form."""
+    n, m = len(target), len(query)
+    NEG = -10 ** 9
+    H = [[0] * (m + 1) for _ in range(n + 1)]
+    E = [[NEG] * (m + 1) for _ in range(n + 1)]     # gap consuming target only (deletion), comes from the row above
+    F = [[NEG] * (m + 1) for _ in range(n + 1)]     # gap consuming query only (insertion), comes from the left
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            E[i][j] = max(E[i - 1][j] - e_del, H[i - 1][j] - o_del - e_del)
+            F[i][j] = max(F[i][j - 1] - e_ins, H[i][j - 1] - o_ins - e_ins)
+            H[i][j] = max(0, H[i - 1][j - 1] + score(a, b, target[i - 1], query[j - 1]), E[i][j], F[i][j])
+    return H
+
+
+def ksw_align2(query, target, minsc, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1):
+    """Independent restatement of ksw_align2 with KSW_XSUBO | KSW_XSTART (see oracle/qmo_ksw.c): works on the full
+    matrix instead of rolling rows.  Returns (score, te, qe, score2, te2, tb, qb)."""
+    def scan(q, t, minsc_, endsc):
+        H = _local_matrix(q, t, a, b, o_del, e_del, o_ins, e_ins)
+        best, te, qe, log = 0, -1, -1, []
+        for i in range(len(t)):
+            row = H[i + 1][1:]
+            imax = max(row) if row else 0
+            if imax >= minsc_:
+                if not log or log[-1][1] + 1 != i:
+                    log.append([imax, i])
+                elif log[-1][0] < imax:
+                    log[-1] = [imax, i]
+            if imax > best:
+                best, te, qe = imax, i, row.index(imax)
+                if best >= endsc:
+                    break
+        return best, te, qe, log
+    sc, te, qe, log = scan(query, target, minsc if minsc >= 0 else 1 << 16, 1 << 16)
+    score2, te2 = -1, -1
+    mx = (sc + max(a, 1) - 1) // max(a, 1)
+    for s, r in log:
+        if (r < te - mx or r > te + mx) and s > score2:
+            score2, te2 = s, r
+    tb = qb = -1
+    if minsc >= 0 and sc >= minsc and te >= 0:
+        s2, t2, q2, _ = scan(query[:qe + 1][::-1], target[:te + 1][::-1], 1 << 16, sc)
+        if s2 == sc:
+            tb, qb = te - t2, qe - q2
+    return sc, te, qe, score2, te2, tb, qb

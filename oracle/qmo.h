@@ -42,8 +42,10 @@ typedef struct {
     int32_t mapq_coef_len;
     float   mask_level, drop_ratio, mask_level_redun;
     int32_t min_chain_weight;
-    int32_t reserved[3];
+    int32_t flags;                /* QMO_F_*                                            */
+    int32_t reserved[2];
 } qmo_opt_t;
+#define QMO_F_NO_RESCUE 1         /* bwa mem -S: skip mate rescue                       */
 
 void qmo_opt_default(qmo_opt_t *o);
 
@@ -59,11 +61,20 @@ int64_t qmo_ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t 
 int qmo_ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                     const qmo_opt_t *o, int w, int *n_cigar, uint32_t *cigar, int max_cigar);
 
+/* local alignment of a whole query inside a target window (ksw.c ksw_align2 with KSW_XSUBO | KSW_XSTART | minsc):
+ * score, end (te, qe inclusive), second-best score away from the best (score2, te2; -1 = none) and start (tb, qb; -1 when
+ * score < minsc).  Returns executed cells. */
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb, pad; } qmo_sw_t;
+int64_t qmo_ksw_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const qmo_opt_t *o,
+                       int minsc, qmo_sw_t *r);
+
 /* ---- reference + k-mer index (replaces `bwa index`, rules/index.smk:13) ---- */
 #define QMO_MAX_SEEDS 64
 #define QMO_MAX_REGS  16
 #define QMO_MAX_CIGAR 21
 #define QMO_OCC_CAP   32
+#define QMO_MAX_MATESW 50            /* bwa's max_matesw (never reached: at most QMO_MAX_REGS anchors per end) */
+#define QMO_RESCUE_MAX_WINDOW 4096   /* mate-rescue windows longer than this are not searched                   */
 
 typedef struct qmo_ref qmo_ref_t;
 /* codes: concatenated forward strands (0..3), contig i has lens[i] bases */
@@ -109,7 +120,13 @@ void qmo_align_se(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n, const uint8
 void qmo_pestat(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, const qmo_reg_t *regs,
                 const int32_t *n_regs, qmo_pestat_t pes[4]);
 
-/* paired-end stage (bwamem_pair.c mem_sam_pe without mate rescue) + CIGAR generation
+/* mate rescue for every pair (bwamem_pair.c mem_matesw as driven by mem_sam_pe): regs / n_regs updated in place;
+ * n_sw / cells (may be NULL) = local alignments run and their cells */
+void qmo_mate_rescue(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, const uint8_t *reads, int stride,
+                     const int32_t *lens, qmo_reg_t *regs, int32_t *n_regs, const qmo_pestat_t pes[4],
+                     int64_t *n_sw_total, int64_t *cells_total);
+
+/* paired-end stage (bwamem_pair.c mem_sam_pe; mate rescue unless flags & QMO_F_NO_RESCUE) + CIGAR generation
  * (bwamem.c mem_reg2aln / bwa.c bwa_gen_cigar2).  pair_id0 = global index of pair 0 (tie-break hash).
  * regs/n_regs are modified in place (primary marking re-sorts them). */
 void qmo_pair_and_finish(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, int64_t pair_id0,

@@ -189,3 +189,81 @@ int qmo_ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *tar
     free(cells); free(dir);
     return score;
 }
+
+/* ---- ksw_align2 (ksw.c ksw_u8 / ksw_i16 / ksw_align2): local alignment of the whole query against the target,
+ * the kernel of mate rescue (bwamem_pair.c mem_matesw).  Upstream runs Farrar's striped SSE2 loop; its results are
+ * those of the plain recurrence below (the striping, the lazy F loop and the zero-score padding columns do not
+ * change any value that is read), PROVIDED no 8-bit saturation happens, which the caller guarantees by asking
+ * for the byte version only when qlen * a < 250.  What has to be kept exactly are the bookkeeping rules:
+ *   - row maximum imax; the best score moves only on a STRICTLY greater row maximum (first row wins), te = that row;
+ *   - qe = the smallest query index holding the maximum in row te;
+ *   - rows with imax >= minsc are logged in b[]: a new entry unless the last entry's row is i - 1, otherwise the
+ *     last entry is overwritten when imax is strictly greater (so a logged row stays where its run peaked first);
+ *   - score2 / te2 = best logged entry whose row is further than `score` rows (max = (score + max_sc - 1) / max_sc
+ *     with max_sc = a) from te, first such entry on ties;
+ *   - the start is found by running the same loop on the reversed prefixes query[0..qe], target[0..te] until the
+ *     best score reaches `score` (KSW_XSTOP); tb / qb are only set when that pass ends with exactly `score`.
+ * minsc < 0: no sub-optimal score, no start (plain score query).  Returns cells executed. */
+static void local_pass(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int q_step, int t_step,
+                       const qmo_opt_t *o, int minsc, int endsc, int *score, int *te_out, int *qe_out,
+                       int **b_sc, int **b_row, int *n_b_out, int64_t *cells)
+{
+    const int oe_del = o->o_del + o->e_del, oe_ins = o->o_ins + o->e_ins;
+    int *H = (int *)calloc((size_t)qlen + 1, sizeof(int)), *E = (int *)calloc((size_t)qlen + 1, sizeof(int));
+    int gmax = 0, te = -1, qe = -1, n_b = 0, m_b = 0, i, j;
+    int *bs = 0, *br = 0;
+    for (i = 0; i < tlen; ++i) {
+        const int tb = target[(int64_t)i * t_step];
+        int f = 0, diag = 0, imax = 0, imax_j = -1;      /* H[-1] of every row is 0 */
+        for (j = 0; j < qlen; ++j) {
+            /* H[j] still holds row i-1; E[j] is the deletion score entering (i, j) */
+            int h = diag + sc(o, tb, query[(int64_t)j * q_step]), e = E[j], t;
+            diag = H[j];
+            if (h < e) h = e;
+            if (h < f) h = f;
+            if (h < 0) h = 0;
+            H[j] = h;
+            if (h > imax) { imax = h; imax_j = j; }
+            t = h - oe_del; e -= o->e_del; if (e < t) e = t; if (e < 0) e = 0; E[j] = e;
+            t = h - oe_ins; f -= o->e_ins; if (f < t) f = t; if (f < 0) f = 0;
+        }
+        *cells += qlen;
+        if (imax >= minsc) {
+            if (n_b == 0 || br[n_b - 1] + 1 != i) {
+                if (n_b == m_b) { m_b = m_b ? m_b << 1 : 8; bs = (int *)realloc(bs, sizeof(int) * m_b); br = (int *)realloc(br, sizeof(int) * m_b); }
+                bs[n_b] = imax; br[n_b++] = i;
+            } else if (bs[n_b - 1] < imax) { bs[n_b - 1] = imax; br[n_b - 1] = i; }
+        }
+        if (imax > gmax) {
+            gmax = imax; te = i; qe = imax_j;
+            if (gmax >= endsc) break;
+        }
+    }
+    free(H); free(E);
+    *score = gmax; *te_out = te; *qe_out = qe;
+    if (b_sc) { *b_sc = bs; *b_row = br; *n_b_out = n_b; } else { free(bs); free(br); }
+}
+
+int64_t qmo_ksw_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const qmo_opt_t *o,
+                       int minsc, qmo_sw_t *r)
+{
+    int64_t cells = 0;
+    int *bs = 0, *br = 0, n_b = 0, i;
+    const int no_limit = 0x10000;
+    r->score = 0; r->te = r->qe = -1; r->score2 = -1; r->te2 = -1; r->tb = r->qb = -1;
+    local_pass(qlen, query, tlen, target, 1, 1, o, minsc >= 0 ? minsc : no_limit, no_limit, &r->score, &r->te, &r->qe, &bs, &br, &n_b, &cells);
+    if (n_b > 0) {
+        const int max_sc = o->a > 1 ? o->a : 1;
+        const int mx = (r->score + max_sc - 1) / max_sc, low = r->te - mx, high = r->te + mx;
+        for (i = 0; i < n_b; ++i)
+            if ((br[i] < low || br[i] > high) && bs[i] > r->score2) { r->score2 = bs[i]; r->te2 = br[i]; }
+    }
+    free(bs); free(br);
+    if (minsc < 0 || r->score < minsc || r->te < 0) return cells;
+    {
+        int sc2, te2, qe2;
+        local_pass(r->qe + 1, query + r->qe, r->te + 1, target + r->te, -1, -1, o, no_limit, r->score, &sc2, &te2, &qe2, 0, 0, 0, &cells);
+        if (sc2 == r->score) { r->tb = r->te - te2; r->qb = r->qe - qe2; }
+    }
+    return cells;
+}

@@ -9,7 +9,7 @@
  * reference, found through a k-mer index with k = min_seed_len (SURVEY.md A.2 first bullet).  The
  * oracle looks k-mers up by binary search in a sorted array; the product uses a hash table.
  * Documented simplifications shared with the product (DESIGN.md "deviations"): no re-seeding, no
- * mem_patch_reg, no mate rescue (mem_matesw), frac_rep = 0, csub = 0, primary alignment only.
+ * mem_patch_reg, frac_rep = 0, csub = 0 for extended regions, primary alignment only.
  */
 #include <math.h>
 #include <stdlib.h>
@@ -796,11 +796,118 @@ static void finish_pair(qmo_aln_t h[2], int extra_flag)
     }
 }
 
+/* ---- mate rescue (bwamem_pair.c mem_matesw, and the loop around it in mem_sam_pe) ----
+ * `a` = one region of the anchoring end, ms = the mate as sequenced, ma / *n_ma = the mate's regions (sorted by score).
+ * For every orientation with a usable insert-size model in which the mate has no region at a proper distance from
+ * `a`, the mate (reverse-complemented when the orientation asks for the opposite strand) is aligned locally inside the
+ * window the model implies; a hit of at least min_seed_len joins the mate's list, which is then de-duplicated again.
+ * Returns the number of local alignments run.  Limits shared with the product: a window longer than
+ * QMO_RESCUE_MAX_WINDOW is not searched; a full list (QMO_MAX_REGS) drops its lowest-scoring entry. */
+static int matesw(const qmo_ref_t *R, const qmo_opt_t *o, const qmo_pestat_t pes[4], const qmo_reg_t *a, int l_ms,
+                  const uint8_t *ms, qmo_reg_t *ma, int *n_ma, int64_t *cells)
+{
+    const int64_t l_pac = R->l_pac;
+    int skip[4], r, i, n = 0;
+    for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+    for (i = 0; i < *n_ma; ++i) {
+        int64_t dist;
+        r = infer_dir(l_pac, a->rb, ma[i].rb, &dist);
+        if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+    }
+    if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
+    for (r = 0; r < 4; ++r) {
+        int is_rev, is_larger, rid = -1;
+        int64_t rb, re;
+        if (skip[r]) continue;
+        is_rev = (r >> 1) != (r & 1);          /* the mate is searched as its reverse complement */
+        is_larger = !(r >> 1);                 /* the mate lies at the larger coordinate          */
+        if (!is_rev) {
+            rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
+            re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
+        } else {
+            rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
+            re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
+        }
+        if (rb < 0) rb = 0;
+        if (re > l_pac << 1) re = l_pac << 1;
+        if (rb < re) {                          /* bns_fetch_seq: clip to the contig and strand of the midpoint */
+            int mrev;
+            int64_t mid = (rb + re) >> 1, far_beg, far_end;
+            rid = pos2rid(R, depos(R, mid, &mrev));
+            far_beg = R->off[rid]; far_end = far_beg + R->len[rid];
+            if (mrev) { int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+            if (rb < far_beg) rb = far_beg;
+            if (re > far_end) re = far_end;
+        }
+        if (a->rid == rid && re - rb >= o->min_seed_len && re - rb <= QMO_RESCUE_MAX_WINDOW) {
+            const int tlen = (int)(re - rb);
+            uint8_t *ref = (uint8_t *)malloc((size_t)tlen), *seq = (uint8_t *)malloc((size_t)l_ms);
+            qmo_sw_t aln;
+            for (i = 0; i < tlen; ++i) ref[i] = (uint8_t)ref_base(R, rb + i);
+            if (is_rev) for (i = 0; i < l_ms; ++i) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4;
+            else memcpy(seq, ms, (size_t)l_ms);
+            *cells += qmo_ksw_align2(l_ms, seq, tlen, ref, o, o->min_seed_len * o->a, &aln);
+            if (aln.score >= o->min_seed_len && aln.qb >= 0) {
+                qmo_reg_t b;
+                int at;
+                memset(&b, 0, sizeof(b));
+                b.rid = a->rid;
+                b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+                b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+                b.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
+                b.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
+                b.score = aln.score;
+                b.csub = aln.score2;
+                b.secondary = -1;
+                b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+                /* insert behind the entries that score at least as much */
+                for (at = 0; at < *n_ma; ++at) if (ma[at].score < b.score) break;
+                if (*n_ma < QMO_MAX_REGS) ++*n_ma;
+                if (at < *n_ma) {
+                    for (i = *n_ma - 1; i > at; --i) ma[i] = ma[i - 1];
+                    ma[at] = b;
+                }
+            }
+            ++n;
+            free(ref); free(seq);
+        }
+        if (n) *n_ma = sort_dedup(o, *n_ma, ma);
+    }
+    return n;
+}
+
+/* mem_sam_pe's rescue loop: the anchors are the regions of each end within pen_unpaired of its best, taken BEFORE any
+ * rescue; end 0's anchors go first.  regs / n_regs are updated in place. */
+void qmo_mate_rescue(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, const uint8_t *reads, int stride,
+                     const int32_t *lens, qmo_reg_t *regs, int32_t *n_regs, const qmo_pestat_t pes[4],
+                     int64_t *n_sw_total, int64_t *cells_total)
+{
+    int64_t pi, n_sw = 0, cells = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_sw, cells)
+    for (pi = 0; pi < n_pairs; ++pi) {
+        qmo_reg_t *a[2] = { regs + (2 * pi) * QMO_MAX_REGS, regs + (2 * pi + 1) * QMO_MAX_REGS };
+        int n[2] = { n_regs[2 * pi], n_regs[2 * pi + 1] }, nb[2] = {0, 0}, i, j;
+        qmo_reg_t b[2][QMO_MAX_REGS];
+        int64_t mycells = 0;
+        for (i = 0; i < 2; ++i)
+            for (j = 0; j < n[i]; ++j)
+                if (a[i][j].score >= a[i][0].score - o->pen_unpaired) b[i][nb[i]++] = a[i][j];
+        for (i = 0; i < 2; ++i)
+            for (j = 0; j < nb[i] && j < QMO_MAX_MATESW; ++j)
+                n_sw += matesw(R, o, pes, &b[i][j], lens[2 * pi + !i], reads + (2 * pi + !i) * (int64_t)stride, a[!i], &n[!i], &mycells);
+        n_regs[2 * pi] = n[0]; n_regs[2 * pi + 1] = n[1];
+        cells += mycells;
+    }
+    if (n_sw_total) *n_sw_total = n_sw;
+    if (cells_total) *cells_total = cells;
+}
+
 void qmo_pair_and_finish(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n_pairs, int64_t pair_id0,
                          const uint8_t *reads, int stride, const int32_t *lens,
                          qmo_reg_t *regs, int32_t *n_regs, const qmo_pestat_t pes[4], qmo_aln_t *alns)
 {
     int64_t pi;
+    if (!(o->flags & QMO_F_NO_RESCUE)) qmo_mate_rescue(R, o, n_pairs, reads, stride, lens, regs, n_regs, pes, 0, 0);
 #pragma omp parallel for schedule(dynamic, 256)
     for (pi = 0; pi < n_pairs; ++pi) {
         qmo_reg_t *a[2] = { regs + (2 * pi) * QMO_MAX_REGS, regs + (2 * pi + 1) * QMO_MAX_REGS };

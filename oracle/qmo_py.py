@@ -16,7 +16,7 @@ class Opt(C.Structure):
                 ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "w", "zdrop", "pen_clip5", "pen_clip3",
                  "min_seed_len", "max_occ", "T", "pen_unpaired", "max_ins", "max_chain_gap", "mapq_coef_len")] + \
                [("mask_level", C.c_float), ("drop_ratio", C.c_float), ("mask_level_redun", C.c_float),
-                ("min_chain_weight", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("min_chain_weight", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 EXT_DTYPE = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
@@ -37,6 +37,7 @@ def lib():
         _LIB = C.CDLL(build())
         _LIB.qmo_ksw_extend2.restype = C.c_int64
         _LIB.qmo_ksw_global2.restype = C.c_int
+        _LIB.qmo_ksw_align2.restype = C.c_int64
     return _LIB
 
 
@@ -74,6 +75,20 @@ def ksw_global2(query, target, w, opt=None, max_cigar=64):
     if n.value < 0:
         raise OverflowError("cigar overflow")
     return int(s), [(int(c & 0xf), int(c >> 4)) for c in cig[:n.value]]
+
+
+SW_DTYPE = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"),
+                     ("tb", "<i4"), ("qb", "<i4"), ("pad", "<i4")])
+
+
+def ksw_align2(query, target, minsc, opt=None):
+    """-> ((score, te, qe, score2, te2, tb, qb), executed_cells)"""
+    opt = opt or default_opt()
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    out = np.zeros(1, dtype=SW_DTYPE)
+    cells = lib().qmo_ksw_align2(len(q), qp, len(t), tp, C.byref(opt), int(minsc), out.ctypes.data_as(C.c_void_p))
+    return tuple(int(x) for x in out[0])[:7], int(cells)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -164,6 +179,24 @@ def pestat(ref, regs, n_regs, opt=None):
     pes = np.zeros(4, dtype=PESTAT_DTYPE)
     L.qmo_pestat(ref._h, C.byref(opt), len(n_regs) // 2, regs.ctypes.data, n_regs.ctypes.data, pes.ctypes.data)
     return pes
+
+
+F_NO_RESCUE = 1
+
+
+def mate_rescue(ref, reads, lens, regs, n_regs, pes, opt=None):
+    """regs / n_regs updated in place -> (local alignments run, cells)"""
+    opt = opt or default_opt()
+    L = lib()
+    L.qmo_mate_rescue.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    n_sw, cells = C.c_int64(0), C.c_int64(0)
+    L.qmo_mate_rescue(ref._h, C.byref(opt), n // 2, reads.ctypes.data, stride, lens.ctypes.data, regs.ctypes.data,
+                      n_regs.ctypes.data, pes.ctypes.data, C.byref(n_sw), C.byref(cells))
+    return n_sw.value, cells.value
 
 
 def pair_and_finish(ref, reads, lens, regs, n_regs, pes, pair_id0=0, opt=None):

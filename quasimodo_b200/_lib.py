@@ -22,7 +22,7 @@ class Opt(C.Structure):
                 ("a", "b", "o_del", "e_del", "o_ins", "e_ins", "w", "zdrop", "pen_clip5", "pen_clip3",
                  "min_seed_len", "max_occ", "T", "pen_unpaired", "max_ins", "max_chain_gap", "mapq_coef_len")] + \
                [("mask_level", C.c_float), ("drop_ratio", C.c_float), ("mask_level_redun", C.c_float),
-                ("min_chain_weight", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("min_chain_weight", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class SimParams(C.Structure):
@@ -40,8 +40,8 @@ class CallOpt(C.Structure):
     _fields_ = [("min_dp", C.c_int32), ("min_alt", C.c_int32), ("min_af", C.c_float), ("reserved", C.c_int32)]
 
 
-MAX_SEEDS, MAX_REGS, MAX_CIGAR, NCH, N_STAGES, PESTAT_PAIRS = 64, 16, 21, 16, 8, 65536
-STAGES = ("seed_chain", "advance", "extend", "pair_cigar", "pileup", "h2d", "d2h", "other")
+MAX_SEEDS, MAX_REGS, MAX_CIGAR, NCH, N_STAGES, PESTAT_PAIRS = 64, 16, 21, 16, 9, 65536
+STAGES = ("seed_chain", "advance", "extend", "pair_cigar", "pileup", "h2d", "d2h", "other", "rescue")
 CALL_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("ref", "u1"), ("alt", "u1"), ("pad", "u1", (2,)), ("dp", "<i4"),
                        ("ad_ref_f", "<i4"), ("ad_ref_r", "<i4"), ("ad_alt_f", "<i4"), ("ad_alt_r", "<i4"),
                        ("qual", "<f4"), ("af", "<f4")])
@@ -80,6 +80,7 @@ SIGNATURES = {
     "qm_collect_seeds": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P]),
     "qm_align_se": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
     "qm_pestat_sync": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P]),
+    "qm_mate_rescue": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P, _P]),
     "qm_pair_finish": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _L, _P, _P, _P, _P, _P]),
     "qm_pileup_opt_default": (None, [_P]),
     "qm_pileup_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P]),

@@ -255,6 +255,16 @@ class Context:
         _check(self._h, rc, "qm_pestat_sync")
         return pes
 
+    def mate_rescue(self, idx, d_codes, d_lens, d_regs, d_n_regs, pes, d_stats=None, stream=0, opt=None):
+        """mem_matesw for every pair: d_regs / d_n_regs updated in place; d_stats: int64[2] += (alignments run, cells)"""
+        opt = opt or self.opt
+        n, stride = d_codes.shape
+        pes = np.ascontiguousarray(pes, dtype=_lib.PESTAT_DTYPE)
+        rc = _lib.lib().qm_mate_rescue(self._h, idx._h, C.byref(opt), _ptr(d_codes), stride, _ptr(d_lens), n // 2, _ptr(d_regs),
+                                       _ptr(d_n_regs), pes.ctypes.data, _ptr(d_stats) if d_stats is not None else None,
+                                       C.c_void_p(stream))
+        _check(self._h, rc, "qm_mate_rescue")
+
     def pair_finish(self, idx, d_codes, d_lens, d_regs, d_n_regs, pes, pair_id0=0, d_alns=None, stream=0, opt=None):
         import torch
         opt = opt or self.opt

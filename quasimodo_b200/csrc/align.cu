@@ -481,43 +481,6 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
     return cudaGetLastError();
 }
 
-// ---- mem_sort_dedup_patch without mem_patch_reg (stable sorts) ----
-__device__ int sort_dedup(const qm_opt &o, int n, qm_reg *a)
-{
-    if (n <= 1) return n;
-    for (int i = 1; i < n; ++i) { const qm_reg x = a[i]; int j = i - 1; while (j >= 0 && a[j].re > x.re) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
-    for (int i = 1; i < n; ++i) {
-        qm_reg *p = &a[i];
-        if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + o.max_chain_gap) continue;
-        for (int j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + o.max_chain_gap; --j) {
-            qm_reg *q = &a[j];
-            if (q->qe == q->qb) continue;
-            const int64_t orr = q->re - p->rb;
-            const int64_t oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
-            const int64_t mr = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
-            const int64_t mq = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
-            if (orr > o.mask_level_redun * mr && oq > o.mask_level_redun * mq) {
-                if (p->score < q->score) { p->qe = p->qb; break; }
-                else q->qe = q->qb;
-            }
-        }
-    }
-    int m = 0;
-    for (int i = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
-    n = m;
-    for (int i = 1; i < n; ++i) {
-        const qm_reg x = a[i];
-        int j = i - 1;
-        while (j >= 0 && !(a[j].score > x.score || (a[j].score == x.score && (a[j].rb < x.rb || (a[j].rb == x.rb && a[j].qb <= x.qb))))) { a[j + 1] = a[j]; --j; }
-        a[j + 1] = x;
-    }
-    for (int i = 1; i < n; ++i)
-        if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
-    m = n ? 1 : 0;
-    for (int i = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
-    return m;
-}
-
 struct RoundCounters {        // zeroed before every advance round; the host reads back the first kRoundHeader bytes
     int class_count[kExtCtr];     // tasks per query-length class
     int class_cursor[kExtCtr];    // work cursors of the extension kernels
@@ -626,7 +589,7 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
                 break;
             }
             if (!have) {
-                *n_regs_out = sort_dedup(o, s.n_av, av);
+                *n_regs_out = qm_sort_dedup(o, s.n_av, av);
                 s.phase = PH_DONE;
                 return false;
             }

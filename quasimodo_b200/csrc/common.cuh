@@ -15,7 +15,7 @@ struct qm_scratch {
 };
 
 // stage timers (CUDA events on the launching stream; enabled by qm_profile_enable)
-enum { QM_ST_SEED = 0, QM_ST_ADVANCE, QM_ST_EXTEND, QM_ST_PAIR, QM_ST_PILEUP, QM_ST_H2D, QM_ST_D2H, QM_ST_OTHER, QM_ST_N };
+enum { QM_ST_SEED = 0, QM_ST_ADVANCE, QM_ST_EXTEND, QM_ST_PAIR, QM_ST_PILEUP, QM_ST_H2D, QM_ST_D2H, QM_ST_OTHER, QM_ST_RESCUE, QM_ST_N };
 struct qm_prof_span { int stage; cudaEvent_t e0, e1; };
 
 struct qm_ctx {

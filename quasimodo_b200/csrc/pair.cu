@@ -1,6 +1,6 @@
 // pair.cu -- paired-end stage: insert-size model, primary marking, pairing, MAPQ, CIGAR/NM, SAM flags.
-// Replaces the compute of `bwa mem` worker2 (bwamem_pair.c mem_pestat, mem_pair, mem_sam_pe without mate
-// rescue; bwamem.c mem_mark_primary_se, mem_approx_mapq_se, mem_reg2aln; bwa.c bwa_gen_cigar2;
+// Replaces the compute of `bwa mem` worker2 (bwamem_pair.c mem_pestat, mem_pair, mem_sam_pe -- mate rescue
+// lives in rescue.cu; bwamem.c mem_mark_primary_se, mem_approx_mapq_se, mem_reg2aln; bwa.c bwa_gen_cigar2;
 // ksw.c ksw_global2 -- reference call site rules/bwa.smk:15; semantics SURVEY.md A.4-A.6).
 // One thread per pair.  The floating-point pieces (log / erfc) are evaluated on the HOST into small
 // tables (same libm as the CPU path) so that the integer MAPQ / pair scores are bit-identical; the
@@ -30,14 +30,6 @@ __device__ __forceinline__ uint64_t hash64(uint64_t key)
     return key;
 }
 
-__device__ __forceinline__ int infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist)
-{
-    const int r1 = (b1 >= l_pac), r2 = (b2 >= l_pac);
-    const int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;
-    *dist = p2 > b1 ? p2 - b1 : b1 - p2;
-    return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
-}
-
 __device__ int cal_sub(const qm_opt &o, const qm_reg *a, int n)
 {
     int j;
@@ -64,7 +56,7 @@ __global__ void pestat_hist_kernel(IndexView V, qm_opt o, const qm_reg *__restri
     if (n0 && n1 && !(cal_sub(o, r0, n0) > 0.8 * r0[0].score) && !(cal_sub(o, r1, n1) > 0.8 * r1[0].score) &&
         r0[0].rid == r1[0].rid) {
         int64_t is;
-        const int dir = infer_dir(V.l_pac, r0[0].rb, r1[0].rb, &is);
+        const int dir = qm_infer_dir(V.l_pac, r0[0].rb, r1[0].rb, &is);
         if (is && is <= o.max_ins) atomicAdd(&hist[(int64_t)dir * (o.max_ins + 1) + is], 1u);
     }
 }
@@ -942,7 +934,7 @@ pair_finish_kernel(IndexView V, PairTables T, int64_t n_pairs, const qm_reg *__r
     h[0].tlen = 0;
     if (!paired_done && h[0].rid == h[1].rid && h[0].rid >= 0) {
         int64_t dist;
-        const int d = infer_dir(V.l_pac, regs[(2 * pi) * QM_MAX_REGS].rb, regs[(2 * pi + 1) * QM_MAX_REGS].rb, &dist);
+        const int d = qm_infer_dir(V.l_pac, regs[(2 * pi) * QM_MAX_REGS].rb, regs[(2 * pi + 1) * QM_MAX_REGS].rb, &dist);
         if (!T.pes[d].failed && dist >= T.pes[d].low && dist <= T.pes[d].high) extra_flag |= 2;
     }
     finish_pair(h, extra_flag);
@@ -1022,6 +1014,12 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     if (n_pairs == 0) return QM_OK;
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (!(opt->flags & QM_F_NO_RESCUE)) {
+        const int sr = qm_prof_begin(ctx, QM_ST_RESCUE, st);
+        const int rr = qm_mate_rescue(ctx, idx, opt, d_codes, stride, d_lens, n_pairs, d_regs, d_n_regs, pes, nullptr, stream);
+        qm_prof_end(ctx, QM_ST_RESCUE, sr, st, 2);
+        if (rr) return rr;
+    }
     // host-evaluated tables (libm): MAPQ length factor, sub_n penalty, pairing term per insert size
     std::vector<double> tab(kMapqTabLen);
     for (int l = 0; l < kMapqTabLen; ++l)

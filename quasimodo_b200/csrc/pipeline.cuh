@@ -66,6 +66,54 @@ static __device__ __forceinline__ bool qm_idx_lookup(const IndexView &V, uint64_
     }
 }
 
+// orientation class (FF FR RF RR) and distance of two hits in doubled coordinates (bwamem_pair.c mem_infer_dir)
+static __device__ __forceinline__ int qm_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist)
+{
+    const int r1 = (b1 >= l_pac), r2 = (b2 >= l_pac);
+    const int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;
+    *dist = p2 > b1 ? p2 - b1 : b1 - p2;
+    return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
+}
+
+
+// ---- mem_sort_dedup_patch without mem_patch_reg (stable sorts) ----
+__device__ inline int qm_sort_dedup(const qm_opt &o, int n, qm_reg *a)
+{
+    if (n <= 1) return n;
+    for (int i = 1; i < n; ++i) { const qm_reg x = a[i]; int j = i - 1; while (j >= 0 && a[j].re > x.re) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
+    for (int i = 1; i < n; ++i) {
+        qm_reg *p = &a[i];
+        if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + o.max_chain_gap) continue;
+        for (int j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + o.max_chain_gap; --j) {
+            qm_reg *q = &a[j];
+            if (q->qe == q->qb) continue;
+            const int64_t orr = q->re - p->rb;
+            const int64_t oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
+            const int64_t mr = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
+            const int64_t mq = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
+            if (orr > o.mask_level_redun * mr && oq > o.mask_level_redun * mq) {
+                if (p->score < q->score) { p->qe = p->qb; break; }
+                else q->qe = q->qb;
+            }
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+    n = m;
+    for (int i = 1; i < n; ++i) {
+        const qm_reg x = a[i];
+        int j = i - 1;
+        while (j >= 0 && !(a[j].score > x.score || (a[j].score == x.score && (a[j].rb < x.rb || (a[j].rb == x.rb && a[j].qb <= x.qb))))) { a[j + 1] = a[j]; --j; }
+        a[j + 1] = x;
+    }
+    for (int i = 1; i < n; ++i)
+        if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+    m = n ? 1 : 0;
+    for (int i = 1; i < n; ++i) if (a[i].qe > a[i].qb) { if (m != i) a[m] = a[i]; ++m; }
+    return m;
+}
+
+
 // ---- internal extension task (superset of qm_ext_task) ----
 #define QM_EXTI_INDIRECT 0x100u   // target = reference bases at doubled coordinate t0 + i*tstep
 struct ExtTaskI {

@@ -76,3 +76,51 @@ def test_global_simple():
     s, cig = qmo_py.ksw_global2(q, t, 5)
     assert s == 12 - 8 and sum(l for op, l in cig if op in (0, 1)) == 12 and sum(l for op, l in cig if op in (0, 2)) == 14
     assert [op for op, _ in cig] == [0, 2, 0]
+
+
+# ---- ksw_align2 (mate rescue's local alignment): C restatement vs the independent full-matrix Python one ----
+def random_local_task(rng):
+    qlen = int(rng.integers(1, 90))
+    q = rng.integers(0, 4, qlen).astype(np.uint8)
+    kind = rng.integers(0, 5)
+    left = rng.integers(0, 4, int(rng.integers(0, 60))).astype(np.uint8)
+    right = rng.integers(0, 4, int(rng.integers(0, 60))).astype(np.uint8)
+    if kind == 0:
+        t = rng.integers(0, 4, int(rng.integers(0, 150))).astype(np.uint8)
+    elif kind == 4:      # two copies: the sub-optimal score is exercised
+        t = np.concatenate([left, mutate(rng, q, 0.02, 0.0), right, mutate(rng, q, 0.06, 0.02), left])
+    else:
+        t = np.concatenate([left, mutate(rng, q, [0.0, 0.04, 0.12][kind - 1], [0.0, 0.02, 0.05][kind - 1]), right])
+    if rng.random() < 0.15 and qlen > 2:
+        q[rng.integers(0, qlen)] = 4
+    if rng.random() < 0.1 and len(t) > 2:
+        t[rng.integers(0, len(t))] = 4
+    return q, t, int(rng.choice([0, 10, 19, 31]))
+
+
+def test_align2_c_vs_python_random():
+    rng = np.random.default_rng(11)
+    n_sub = n_start = 0
+    for _ in range(600):
+        q, t, minsc = random_local_task(rng)
+        c_res, c_cells = qmo_py.ksw_align2(q, t, minsc)
+        p_res = ksw_py.ksw_align2(list(q), list(t), minsc)
+        assert c_res == p_res, (list(q), list(t), minsc)
+        n_sub += c_res[3] > 0
+        n_start += c_res[6] >= 0
+    assert n_sub > 30 and n_start > 200
+
+
+def test_align2_known_answers():
+    q = [0, 1, 2, 3, 0, 1, 2, 3, 2, 2, 1, 0]
+    # exact copy at offset 3: score 12, ends inclusive, start recovered
+    t = [3, 3, 3] + q + [0, 0]
+    assert qmo_py.ksw_align2(q, t, 5)[0] == (12, 14, 11, -1, -1, 3, 0)
+    # below minsc: no start
+    assert qmo_py.ksw_align2(q, t, 13)[0] == (12, 14, 11, -1, -1, -1, -1)
+    # empty target
+    assert qmo_py.ksw_align2(q, [], 5)[0] == (0, -1, -1, -1, -1, -1, -1)
+    # two exact copies: the first one wins, the second is the sub-optimal hit (more than `score` rows away)
+    t2 = q + [3] * 20 + q
+    r = qmo_py.ksw_align2(q, t2, 5)[0]
+    assert r[0] == 12 and r[1] == 11 and r[3] == 12 and r[4] == 43 and (r[5], r[6]) == (0, 0)

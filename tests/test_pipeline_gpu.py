@@ -45,8 +45,10 @@ def run_both(ctx, W, n_pairs, pair0=0):
     # ---- oracle ----
     ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
     o = qmo_py.align_se(ref, codes, lens, opt=opt_o)
-    o_regs_se = o["regs"].copy()
+    o_regs_se, o_nr_se = o["regs"].copy(), o["n_regs"].copy()
     o_pes = qmo_py.pestat(ref, o["regs"], o["n_regs"], opt=opt_o)
+    o_regs_resc, o_nr_resc = o["regs"].copy(), o["n_regs"].copy()
+    o_resc_stats = qmo_py.mate_rescue(ref, codes, lens, o_regs_resc, o_nr_resc, o_pes, opt=opt_o)
     o_alns = qmo_py.pair_and_finish(ref, codes, lens, o["regs"], o["n_regs"], o_pes, pair_id0=pair0, opt=opt_o)
     o_counts = qmo_py.pileup(ref, o_alns, codes, quals, lens)
     # ---- device ----
@@ -60,17 +62,26 @@ def run_both(ctx, W, n_pairs, pair0=0):
     d_regs, d_nr = ctx.align_se(idx, d_codes, d_lens, d_cells=d_cells, opt=opt_g)
     torch.cuda.synchronize()
     g_regs_se = d_regs.cpu().numpy().view(_lib.REG_DTYPE).reshape(-1, _lib.MAX_REGS)
+    g_nr_se = d_nr.cpu().numpy().copy()
     g_pes = ctx.pestat(idx, d_regs, d_nr, n_pairs, opt=opt_g)
+    # the rescue stage on its own (on copies: pair_finish below runs it again as part of the paired stage)
+    d_regs_resc, d_nr_resc = d_regs.clone(), d_nr.clone()
+    d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    ctx.mate_rescue(idx, d_codes, d_lens, d_regs_resc, d_nr_resc, g_pes, d_stats=d_stats, opt=opt_g)
+    torch.cuda.synchronize()
     d_alns = ctx.pair_finish(idx, d_codes, d_lens, d_regs, d_nr, g_pes, pair_id0=pair0, opt=opt_g)
     d_counts = torch.zeros(_lib.NCH * idx.l_pac, dtype=torch.int32, device=dev)
     ctx.pileup_accumulate(idx, d_alns, d_codes, d_quals, d_lens, d_counts)
     rows = ctx.counts_to_rows(idx, d_counts)
     torch.cuda.synchronize()
     g = dict(seeds=d_seeds.cpu().numpy().view(_lib.SEED_DTYPE).reshape(-1, _lib.MAX_SEEDS), n_seeds=d_ns.cpu().numpy(),
-             regs_se=g_regs_se, n_regs=d_nr.cpu().numpy(), cells=int(d_cells.item()), pes=g_pes,
+             regs_se=g_regs_se, n_regs=g_nr_se, cells=int(d_cells.item()), pes=g_pes,
+             regs_resc=d_regs_resc.cpu().numpy().view(_lib.REG_DTYPE).reshape(-1, _lib.MAX_REGS), n_regs_resc=d_nr_resc.cpu().numpy(),
+             resc_stats=tuple(int(x) for x in d_stats.cpu()),
              alns=d_alns.cpu().numpy().view(_lib.ALN_DTYPE), counts=rows.cpu().numpy(),
              planes=d_counts.cpu().numpy().reshape(_lib.NCH, idx.l_pac))
-    oo = dict(seeds=o["seeds"], n_seeds=o["n_seeds"], regs_se=o_regs_se, n_regs=o["n_regs"], cells=o["cells"], pes=o_pes,
+    oo = dict(seeds=o["seeds"], n_seeds=o["n_seeds"], regs_se=o_regs_se, n_regs=o_nr_se, cells=o["cells"], pes=o_pes,
+              regs_resc=o_regs_resc.reshape(-1, qmo_py.MAX_REGS), n_regs_resc=o_nr_resc, resc_stats=o_resc_stats,
               alns=o_alns, counts=o_counts)
     idx.close()
     return g, oo
@@ -86,6 +97,12 @@ def compare(g, o):
     assert not bad, f"{len(bad)} reads with different regions, first {bad[:5]}"
     assert g["cells"] == o["cells"]
     assert g["pes"].tobytes() == o["pes"].tobytes(), (g["pes"], o["pes"])
+    # mate rescue: alignments run, their cells, and every region list afterwards
+    assert g["resc_stats"] == o["resc_stats"], (g["resc_stats"], o["resc_stats"])
+    assert np.array_equal(g["n_regs_resc"], o["n_regs_resc"])
+    bad = [r for r in range(len(o["n_regs_resc"]))
+           if not np.array_equal(g["regs_resc"][r, :o["n_regs_resc"][r]], o["regs_resc"][r, :o["n_regs_resc"][r]])]
+    assert not bad, f"{len(bad)} reads with different regions after mate rescue, first {bad[:5]}"
     # alignment records: compare field by field; cigar only up to n_cigar
     for f in ("rid", "pos", "flag", "mapq", "n_cigar", "score", "sub", "nm", "mate_rid", "mate_pos", "tlen", "qb", "qe"):
         d = np.nonzero(g["alns"][f] != o["alns"][f])[0]
@@ -104,6 +121,7 @@ def test_pipeline_parity(ctx, name, n):
     compare(g, o)
     mapped = (o["alns"]["flag"] & 4) == 0
     assert mapped.mean() > 0.8
+    assert o["resc_stats"][0] > 0 and (o["n_regs_resc"] != o["n_regs"]).any()      # rescue ran and placed something
     assert o["counts"][:, 14].sum() > 0
 
 
