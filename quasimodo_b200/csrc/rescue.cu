@@ -27,42 +27,59 @@ struct SwOut { int score, te, qe, score2, te2, tb, qb; };
 // memory through (base, step): element i is base[i * step].  minsc: rows whose maximum reaches it are logged in
 // log[] as (imax << 16 | row), same merge rule as ksw_u8's b[]; endsc: stop at the first row whose maximum reaches it.
 // All lanes return the same (score, te, qe, n_log).
+// Per cell 10 integer instructions: compare + select (score), viaddmax.relu + max (H), shift-add + max (row maximum
+// and its FIRST column as one key: imax << 16 | 0xffff - column), sub + viaddmax twice (E and F; neither is clamped at
+// zero as the byte-wide upstream loop does: both stay >= -(gap open + extend) and no non-positive value can win a cell).
 template <int C>
 __device__ void local_pass_warp(const qm_opt &o, const uint8_t *qbase, int qstep, int qlen, const uint8_t *tbase, int tstep, int tlen,
                                 int minsc, int endsc, uint32_t *log, int &score, int &te, int &qe, int &n_log, long long &cells)
 {
     const int lane = threadIdx.x & 31;
     const int c0 = lane * C;
-    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, e_del = o.e_del, e_ins = o.e_ins, sa = o.a, sb = -o.b;
-    int q[C], H[C], E[C];
+    const int oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins, ne_del = -o.e_del, ne_ins = -o.e_ins, sa = o.a;
+    int q[C], msk[C], H[C], E[C], kcol[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { q[c] = c0 + c < qlen ? qbase[(c0 + c) * qstep] : 5; H[c] = 0; E[c] = 0; }
-    int out_h = 0, out_f = 0, out_max = 0, out_maxj = -1, left_prev = 0;
+    for (int c = 0; c < C; ++c) {
+        const int code = c0 + c < qlen ? qbase[(c0 + c) * qstep] : 5;
+        q[c] = code < 4 ? code : 8;                                  // N and padding equal no target base
+        msk[c] = code == 5 ? -30000 : code == 4 ? -1 : -o.b;         // the score of a column when the bases differ
+        H[c] = 0; E[c] = 0; kcol[c] = 0xffff - (c0 + c);
+    }
+    constexpr uint32_t kKey0 = 0x0000ffffu;                          // row maximum 0, no column
+    uint32_t out_hf = 0, out_key = kKey0;                            // H of my last column | F leaving it << 16; running key
+    int left_prev = 0;
     int gmax = 0, g_te = -1, g_qe = -1, nl = 0, last_row = -2, last_sc = 0;
     bool done = false;
     const int n_steps = tlen + 31;
     for (int s = 0; s < n_steps; ++s) {
-        int in_h = __shfl_up_sync(0xffffffffu, out_h, 1), in_f = __shfl_up_sync(0xffffffffu, out_f, 1);
-        int in_max = __shfl_up_sync(0xffffffffu, out_max, 1), in_maxj = __shfl_up_sync(0xffffffffu, out_maxj, 1);
-        if (lane == 0) { in_h = 0; in_f = 0; in_max = 0; in_maxj = -1; }
+        uint32_t in_hf = __shfl_up_sync(0xffffffffu, out_hf, 1), key = __shfl_up_sync(0xffffffffu, out_key, 1);
+        if (lane == 0) { in_hf = 0; key = kKey0; }
         const int i = s - lane;
         if (i >= 0 && i < tlen) {
             const int tb = tbase[i * tstep];
-            int diag = left_prev, f = in_f, imax = in_max, imax_j = in_maxj;
-            left_prev = in_h;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int sc = q[c] == 5 ? -30000 : (tb > 3 || q[c] > 3) ? -1 : tb == q[c] ? sa : sb;
-                int h = diag + sc;
-                diag = H[c];
-                h = max(max(h, E[c]), max(f, 0));
-                H[c] = h;
-                if (h > imax) { imax = h; imax_j = c0 + c; }
-                E[c] = max(max(E[c] - e_del, h - oe_del), 0);
-                f = max(max(f - e_ins, h - oe_ins), 0);
+            int diag = left_prev, f = (int)in_hf >> 16;
+            left_prev = (int)(in_hf & 0xffffu);
+#define QM_RES_CELL(SC)                                                                  \
+            {                                                                            \
+                int h = __viaddmax_s32_relu(diag, (SC), E[c]);                            \
+                diag = H[c];                                                             \
+                h = max(h, f);                                                           \
+                H[c] = h;                                                                \
+                key = max(key, ((uint32_t)h << 16) + (uint32_t)kcol[c]);                  \
+                E[c] = __viaddmax_s32(E[c], ne_del, h - oe_del);                          \
+                f = __viaddmax_s32(f, ne_ins, h - oe_ins);                                \
             }
-            out_h = H[C - 1]; out_f = f; out_max = imax; out_maxj = imax_j;
+            if (tb < 4) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) QM_RES_CELL(q[c] == tb ? sa : msk[c])
+            } else {                                            // N in the reference: -1 against every real base
+#pragma unroll
+                for (int c = 0; c < C; ++c) QM_RES_CELL(msk[c] < -1000 ? msk[c] : -1)
+            }
+#undef QM_RES_CELL
+            out_hf = (uint32_t)H[C - 1] | ((uint32_t)f << 16); out_key = key;
             if (lane == 31) {                               // the row is complete
+                const int imax = (int)(key >> 16), imax_j = 0xffff - (int)(key & 0xffffu);
                 if (imax >= minsc) {
                     if (nl == 0 || last_row + 1 != i) { if (nl < kResLog) log[nl] = (uint32_t)imax << 16 | (uint32_t)i; ++nl; last_row = i; last_sc = imax; }
                     else if (last_sc < imax) { log[nl - 1] = (uint32_t)imax << 16 | (uint32_t)i; last_row = i; last_sc = imax; }
@@ -154,7 +171,8 @@ rescue_scan_kernel(IndexView V, qm_opt o, PesArg P, int64_t n_pairs, const qm_re
     }
 }
 
-__global__ void __launch_bounds__(kResWarps * 32)
+template <int C>                        // query columns per lane: reads of up to 32 * C bases
+__global__ void __launch_bounds__(kResWarps * 32, C <= 5 ? 4 : C <= 8 ? 3 : 2)
 rescue_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
               qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs, const int *__restrict__ list, const int *__restrict__ n_list,
               int *__restrict__ cursor, uint32_t *__restrict__ logs, unsigned long long *__restrict__ stats)
@@ -232,16 +250,13 @@ rescue_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes
                     if (rb < far_beg) rb = far_beg;
                     if (re > far_end) re = far_end;
                 }
-                if (arid == rid && re - rb >= o.min_seed_len && re - rb <= kResMaxWindow && l_ms <= kResMaxQuery) {
+                if (arid == rid && re - rb >= o.min_seed_len && re - rb <= kResMaxWindow && l_ms <= 32 * C) {
                     const int tlen = (int)(re - rb);
                     for (int x = lane; x < tlen; x += 32) win[x] = (uint8_t)qm_ref_base(V, rb + x);
                     for (int x = lane; x < l_ms; x += 32) { const int c = ms[is_rev ? l_ms - 1 - x : x]; seq[x] = (uint8_t)(is_rev ? (c < 4 ? 3 - c : 4) : c); }
                     __syncwarp();
                     const int minsc = o.min_seed_len * o.a;
-                    SwOut aln;
-                    if (l_ms <= 160) aln = sw_align2_warp<5>(o, seq, l_ms, win, tlen, minsc, log, cells);
-                    else if (l_ms <= 256) aln = sw_align2_warp<8>(o, seq, l_ms, win, tlen, minsc, log, cells);
-                    else aln = sw_align2_warp<16>(o, seq, l_ms, win, tlen, minsc, log, cells);
+                    const SwOut aln = sw_align2_warp<C>(o, seq, l_ms, win, tlen, minsc, log, cells);
                     __syncwarp();
                     if (lane == 0 && aln.score >= o.min_seed_len && aln.qb >= 0) {
                         qm_reg b;
@@ -291,7 +306,8 @@ int qm_mate_rescue(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     bool any = false;
     for (int d = 0; d < 4; ++d) any |= !pes[d].failed;
     if (!any) return QM_OK;                       // no usable insert-size model: every orientation is skipped
-    const int blocks = ctx->sm_count * 2;
+    if (stride > kResMaxQuery) return qm_fail(ctx, QM_ELIMIT, "qm_mate_rescue: reads longer than %d bases", kResMaxQuery);
+    const int blocks = ctx->sm_count * (stride <= 160 ? 4 : stride <= 256 ? 3 : 2);
     // scratch 14: counters | pair list | per-warp row logs
     const size_t o_list = 256, o_log = (o_list + (size_t)n_pairs * sizeof(int) + 255) & ~(size_t)255;
     void *p = nullptr;
@@ -303,8 +319,12 @@ int qm_mate_rescue(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     PesArg P;
     for (int d = 0; d < 4; ++d) P.p[d] = pes[d];
     rescue_scan_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(idx->v, *opt, P, n_pairs, d_regs, d_n_regs, list, n_list);
-    rescue_kernel<<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor,
-                                                    (uint32_t *)(b + o_log), (unsigned long long *)d_stats);
+    uint32_t *logs = (uint32_t *)(b + o_log);
+    unsigned long long *stats = (unsigned long long *)d_stats;
+    // reads are at most `stride` long: 5 / 8 / 16 query columns per lane
+    if (stride <= 160) rescue_kernel<5><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor, logs, stats);
+    else if (stride <= 256) rescue_kernel<8><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor, logs, stats);
+    else rescue_kernel<16><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor, logs, stats);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }
