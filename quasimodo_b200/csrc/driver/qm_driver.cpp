@@ -4,7 +4,8 @@
 //
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf] [--gpu I] [-t THREADS] [-w BAND]
-//                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]]
+//                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1]
+//        --no-rescue 1 = bwa mem -S (mate rescue off; on by default as in the reference's command line)
 //        --rmdup: duplicates are marked on the device with picard MarkDuplicates' rule (rules/rmdup.smk:13-16) before
 //        anything is counted, as in the reference where every caller reads the .rmdup.bam; --bam still holds all records
 //        (duplicates flagged 0x400), --rmdup-bam is the REMOVE_DUPLICATES=true file
@@ -688,6 +689,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     qm_opt opt; qm_opt_default(&opt);
     if (a.has("w")) opt.w = atoi(a.get("w").c_str());
     if (a.has("k")) opt.min_seed_len = atoi(a.get("k").c_str());
+    if (atoi(a.get("no-rescue", "0").c_str())) opt.flags |= QM_F_NO_RESCUE;          // bwa mem -S
     qm_pileup_opt popt; qm_pileup_opt_default(&popt);
     if (a.has("min-mapq")) popt.min_mapq = atoi(a.get("min-mapq").c_str());
     if (a.has("min-bq")) popt.min_bq = atoi(a.get("min-bq").c_str());

@@ -1017,7 +1017,7 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     if (!(opt->flags & QM_F_NO_RESCUE)) {
         const int sr = qm_prof_begin(ctx, QM_ST_RESCUE, st);
         const int rr = qm_mate_rescue(ctx, idx, opt, d_codes, stride, d_lens, n_pairs, d_regs, d_n_regs, pes, nullptr, stream);
-        qm_prof_end(ctx, QM_ST_RESCUE, sr, st, 2);
+        qm_prof_end(ctx, QM_ST_RESCUE, sr, st, 3);
         if (rr) return rr;
     }
     // host-evaluated tables (libm): MAPQ length factor, sub_n penalty, pairing term per insert size

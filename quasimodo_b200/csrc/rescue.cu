@@ -132,8 +132,10 @@ __device__ SwOut sw_align2_warp(const qm_opt &o, const uint8_t *seq, int l_ms, c
     return r;
 }
 
-// does any anchor of the pair trigger an alignment with the lists as they are now?  (thread per pair)
-__device__ bool anchor_triggers(const IndexView &V, const qm_pestat *pes, int64_t arb, const qm_reg *ma, int n_ma)
+struct PesArg { qm_pestat p[4]; };
+
+// orientations (bit r) in which the anchor at arb needs no alignment: no usable model, or a region of the mate at a proper distance
+__device__ __forceinline__ int served_dirs(const IndexView &V, const qm_pestat *pes, int64_t arb, const qm_reg *ma, int n_ma)
 {
     int skip = 0;
     for (int r = 0; r < 4; ++r) if (pes[r].failed) skip |= 1 << r;
@@ -142,56 +144,158 @@ __device__ bool anchor_triggers(const IndexView &V, const qm_pestat *pes, int64_
         const int r = qm_infer_dir(V.l_pac, arb, ma[i].rb, &dist);
         if (dist >= pes[r].low && dist <= pes[r].high) skip |= 1 << r;
     }
-    return skip != 15;
+    return skip;
 }
 
-struct PesArg { qm_pestat p[4]; };
+// the window orientation r implies for a mate of l_ms bases around an anchor at arb on contig arid (mem_matesw +
+// bns_fetch_seq); false: nothing to align there
+__device__ __forceinline__ bool rescue_window(const IndexView &V, const qm_opt &o, const qm_pestat *pes, int64_t arb, int arid, int r, int l_ms,
+                                              int max_query, int64_t &rb, int64_t &re, bool &is_rev)
+{
+    const int64_t l_pac = V.l_pac;
+    is_rev = (r >> 1) != (r & 1);                         // the mate is searched as its reverse complement
+    const bool is_larger = !(r >> 1);                     // the mate lies at the larger coordinate
+    if (!is_rev) {
+        rb = is_larger ? arb + pes[r].low : arb - pes[r].high;
+        re = (is_larger ? arb + pes[r].high : arb - pes[r].low) + l_ms;
+    } else {
+        rb = (is_larger ? arb + pes[r].low : arb - pes[r].high) - l_ms;
+        re = is_larger ? arb + pes[r].high : arb - pes[r].low;
+    }
+    if (rb < 0) rb = 0;
+    if (re > l_pac << 1) re = l_pac << 1;
+    int rid = -1;
+    if (rb < re) {                                        // the contig and strand of the midpoint
+        const int64_t mid = (rb + re) >> 1;
+        const bool mrev = mid >= l_pac;
+        rid = qm_pos2rid(V, mrev ? 2 * l_pac - 1 - mid : mid);
+        int64_t far_beg = V.off[rid], far_end = far_beg + V.len[rid];
+        if (mrev) { const int64_t x = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - x; }
+        if (rb < far_beg) rb = far_beg;
+        if (re > far_end) re = far_end;
+    }
+    return arid == rid && re - rb >= o.min_seed_len && re - rb <= kResMaxWindow && l_ms <= max_query;
+}
 
+// The alignments of a pair depend on one another only through WHETHER they run (an earlier hit can serve the
+// orientation a later anchor would have searched); what an alignment finds depends on its window alone.  So every
+// alignment the lists would trigger as they stand is run up front, one warp each, and the pass that walks the
+// anchors in bwa's order only looks the results up (and runs the rare alignment that becomes necessary later itself).
+struct ResTask { int32_t pair; int32_t tr; };          // tr = anchor slot (end << 4 | index) << 2 | orientation
+struct ResOut { int32_t score, te, qe, score2, te2, tb, qb; int32_t cells; };     // cells < 2^31: 512 x 4096 x 2 passes
+
+// thread per pair: the alignments to run up front, in (anchor, orientation) order, as one block of the task list
 __global__ void __launch_bounds__(128)
-rescue_scan_kernel(IndexView V, qm_opt o, PesArg P, int64_t n_pairs, const qm_reg *__restrict__ regs, const int32_t *__restrict__ n_regs,
-                   int *__restrict__ list, int *__restrict__ n_list)
+rescue_scan_kernel(IndexView V, qm_opt o, PesArg P, int64_t n_pairs, int max_query, const qm_reg *__restrict__ regs, const int32_t *__restrict__ n_regs,
+                   const int32_t *__restrict__ lens, int *__restrict__ list, int2 *__restrict__ blocks, ResTask *__restrict__ tasks, int cap_tasks,
+                   int *__restrict__ ctr)
 {
     const int64_t pi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool need = false;
-    if (pi < n_pairs) {
-        for (int i = 0; i < 2 && !need; ++i) {
+    if (pi >= n_pairs) return;
+    int k = 0, base = 0;
+    for (int pass = 0; pass < 2; ++pass) {              // count, then write
+        int w = 0;
+        for (int i = 0; i < 2; ++i) {
             const qm_reg *a = regs + (2 * pi + i) * QM_MAX_REGS, *ma = regs + (2 * pi + !i) * QM_MAX_REGS;
-            const int n = n_regs[2 * pi + i], n_ma = n_regs[2 * pi + !i];
-            for (int j = 0; j < n && !need; ++j)
-                if (a[j].score >= a[0].score - o.pen_unpaired) need = anchor_triggers(V, P.p, a[j].rb, ma, n_ma);
+            const int n = n_regs[2 * pi + i], n_ma = n_regs[2 * pi + !i], l_ms = lens[2 * pi + !i];
+            for (int j = 0; j < n; ++j) {
+                if (a[j].score < a[0].score - o.pen_unpaired) continue;
+                const int skip = served_dirs(V, P.p, a[j].rb, ma, n_ma);
+                if (skip == 15) continue;
+                for (int r = 0; r < 4; ++r) {
+                    int64_t rb, re;
+                    bool is_rev;
+                    if ((skip >> r & 1) || !rescue_window(V, o, P.p, a[j].rb, a[j].rid, r, l_ms, max_query, rb, re, is_rev)) continue;
+                    if (pass && base + w < cap_tasks) { ResTask t; t.pair = k ? (int)pi : -1; t.tr = ((i << 4 | j) << 2) | r; tasks[base + w] = t; }
+                    ++w;
+                }
+            }
         }
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, need);
-    if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(n_list, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (need) list[base + __popc(m & ((1u << lane) - 1))] = (int)pi;
+        if (!pass) {
+            k = w;
+            if (k == 0) return;                          // nothing runs, nothing changes
+            base = atomicAdd(ctr + 1, k);
+            if (base > cap_tasks) base = cap_tasks;      // (the counter can run past the list, never wrap: <= 128 per pair)
+            if (base + k > cap_tasks) k = 0;             // no room: slots taken are marked void, the pair aligns as it goes
+            const int item = atomicAdd(ctr, 1);
+            list[item] = (int)pi;
+            blocks[item] = make_int2(base, k);
+        }
     }
 }
 
+// stage window and mate in shared memory and align (all lanes get the result)
+template <int C>
+__device__ ResOut run_alignment(const IndexView &V, const qm_opt &o, const uint8_t *ms, int l_ms, int64_t rb, int64_t re, bool is_rev,
+                                uint8_t *win, uint8_t *seq, uint32_t *log)
+{
+    const int lane = threadIdx.x & 31;
+    const int tlen = (int)(re - rb);
+    __syncwarp();
+    for (int x = lane; x < tlen; x += 32) win[x] = (uint8_t)qm_ref_base(V, rb + x);
+    for (int x = lane; x < l_ms; x += 32) { const int c = ms[is_rev ? l_ms - 1 - x : x]; seq[x] = (uint8_t)(is_rev ? (c < 4 ? 3 - c : 4) : c); }
+    __syncwarp();
+    long long cells = 0;
+    const SwOut a = sw_align2_warp<C>(o, seq, l_ms, win, tlen, o.min_seed_len * o.a, log, cells);
+    ResOut r;
+    r.score = a.score; r.te = a.te; r.qe = a.qe; r.score2 = a.score2; r.te2 = a.te2; r.tb = a.tb; r.qb = a.qb; r.cells = (int32_t)cells;
+    return r;
+}
+
+// warp per task of the up-front list
 template <int C>                        // query columns per lane: reads of up to 32 * C bases
 __global__ void __launch_bounds__(kResWarps * 32, C <= 5 ? 4 : C <= 8 ? 3 : 2)
-rescue_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
-              qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs, const int *__restrict__ list, const int *__restrict__ n_list,
-              int *__restrict__ cursor, uint32_t *__restrict__ logs, unsigned long long *__restrict__ stats)
+rescue_align_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                    const qm_reg *__restrict__ regs, const ResTask *__restrict__ tasks, int cap_tasks, int *__restrict__ ctr,
+                    uint32_t *__restrict__ logs, ResOut *__restrict__ out)
 {
     __shared__ uint8_t s_win[kResWarps][kResMaxWindow];
     __shared__ uint8_t s_seq[kResWarps][kResMaxQuery];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint8_t *win = s_win[wib], *seq = s_seq[wib];
     uint32_t *log = logs + (size_t)(blockIdx.x * kResWarps + wib) * kResLog;
-    const int total = *n_list;
+    const int total = ctr[1] < cap_tasks ? ctr[1] : cap_tasks;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(ctr + 2, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        const ResTask t = tasks[item];
+        if (t.pair < 0) continue;
+        const int slot = t.tr >> 2, r = t.tr & 3, i = slot >> 4, j = slot & 15;
+        const qm_reg *a = regs + (2 * (int64_t)t.pair + i) * QM_MAX_REGS + j;
+        const int l_ms = lens[2 * (int64_t)t.pair + !i];
+        int64_t rb, re;
+        bool is_rev;
+        rescue_window(V, o, P.p, a->rb, a->rid, r, l_ms, 32 * C, rb, re, is_rev);
+        const ResOut res = run_alignment<C>(V, o, codes + (2 * (int64_t)t.pair + !i) * stride, l_ms, rb, re, is_rev, s_win[wib], s_seq[wib], log);
+        if (lane == 0) out[item] = res;
+    }
+}
+
+// warp per listed pair: mem_sam_pe's loop over the anchors, mem_matesw per anchor
+template <int C>
+__global__ void __launch_bounds__(kResWarps * 32, C <= 5 ? 4 : C <= 8 ? 3 : 2)
+rescue_apply_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                    qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs, const int *__restrict__ list, const int2 *__restrict__ blocks,
+                    const ResTask *__restrict__ tasks, const ResOut *__restrict__ results, int *__restrict__ ctr, uint32_t *__restrict__ logs,
+                    unsigned long long *__restrict__ stats)
+{
+    __shared__ uint8_t s_win[kResWarps][kResMaxWindow];
+    __shared__ uint8_t s_seq[kResWarps][kResMaxQuery];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t *log = logs + (size_t)(blockIdx.x * kResWarps + wib) * kResLog;
+    const int total = ctr[0];
     const int64_t l_pac = V.l_pac;
     long long cells = 0;
     int n_sw = 0;
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(cursor, 1);
+        if (lane == 0) item = atomicAdd(ctr + 3, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= total) break;
         const int64_t pi = list[item];
+        const int2 blk = blocks[item];
+        int next = 0;                                   // first result of the pair's block not yet passed
         // anchors: lane t holds anchor j = t & 15 of end t >> 4 as the lists were BEFORE any rescue
         int64_t my_rb = 0;
         int my_rid = -1;
@@ -210,7 +314,6 @@ rescue_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes
             qm_reg *ma = regs + (2 * pi + !i) * QM_MAX_REGS;
             int n_ma = n_regs[2 * pi + !i];
             const int l_ms = lens[2 * pi + !i];
-            const uint8_t *ms = codes + (2 * pi + !i) * (int64_t)stride;
             // orientations already served by a region of the mate (lanes over the mate's regions)
             int skip = 0;
             for (int r = 0; r < 4; ++r) if (P.p[r].failed) skip |= 1 << r;
@@ -229,35 +332,15 @@ rescue_kernel(IndexView V, qm_opt o, PesArg P, const uint8_t *__restrict__ codes
             int n = 0;
             for (int r = 0; r < 4; ++r) {
                 if (skip >> r & 1) continue;
-                const bool is_rev = (r >> 1) != (r & 1), is_larger = !(r >> 1);
                 int64_t rb, re;
-                if (!is_rev) {
-                    rb = is_larger ? arb + P.p[r].low : arb - P.p[r].high;
-                    re = (is_larger ? arb + P.p[r].high : arb - P.p[r].low) + l_ms;
-                } else {
-                    rb = (is_larger ? arb + P.p[r].low : arb - P.p[r].high) - l_ms;
-                    re = is_larger ? arb + P.p[r].high : arb - P.p[r].low;
-                }
-                if (rb < 0) rb = 0;
-                if (re > l_pac << 1) re = l_pac << 1;
-                int rid = -1;
-                if (rb < re) {                               // bns_fetch_seq: the contig and strand of the midpoint
-                    const int64_t mid = (rb + re) >> 1;
-                    const bool mrev = mid >= l_pac;
-                    rid = qm_pos2rid(V, mrev ? 2 * l_pac - 1 - mid : mid);
-                    int64_t far_beg = V.off[rid], far_end = far_beg + V.len[rid];
-                    if (mrev) { const int64_t x = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - x; }
-                    if (rb < far_beg) rb = far_beg;
-                    if (re > far_end) re = far_end;
-                }
-                if (arid == rid && re - rb >= o.min_seed_len && re - rb <= kResMaxWindow && l_ms <= 32 * C) {
-                    const int tlen = (int)(re - rb);
-                    for (int x = lane; x < tlen; x += 32) win[x] = (uint8_t)qm_ref_base(V, rb + x);
-                    for (int x = lane; x < l_ms; x += 32) { const int c = ms[is_rev ? l_ms - 1 - x : x]; seq[x] = (uint8_t)(is_rev ? (c < 4 ? 3 - c : 4) : c); }
-                    __syncwarp();
-                    const int minsc = o.min_seed_len * o.a;
-                    const SwOut aln = sw_align2_warp<C>(o, seq, l_ms, win, tlen, minsc, log, cells);
-                    __syncwarp();
+                bool is_rev;
+                if (rescue_window(V, o, P.p, arb, arid, r, l_ms, 32 * C, rb, re, is_rev)) {
+                    const int want = (t << 2) | r;
+                    while (next < blk.y && tasks[blk.x + next].tr < want) ++next;       // run up front, not needed after all
+                    ResOut aln;
+                    if (next < blk.y && tasks[blk.x + next].tr == want) aln = results[blk.x + next++];
+                    else aln = run_alignment<C>(V, o, codes + (2 * pi + !i) * (int64_t)stride, l_ms, rb, re, is_rev, s_win[wib], s_seq[wib], log);
+                    cells += aln.cells;
                     if (lane == 0 && aln.score >= o.min_seed_len && aln.qb >= 0) {
                         qm_reg b;
                         b.rid = arid;
@@ -300,7 +383,7 @@ int qm_mate_rescue(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
 {
     if (!ctx || !idx || !opt || !pes || n_pairs < 0 || (n_pairs > 0 && (!d_codes || !d_lens || !d_regs || !d_n_regs))) return QM_EINVAL;
     if (n_pairs == 0) return QM_OK;
-    if (n_pairs > 0x7fffffffll) return qm_fail(ctx, QM_ELIMIT, "qm_mate_rescue: more than 2^31 pairs in one call");
+    if (n_pairs > (1ll << 24)) return qm_fail(ctx, QM_ELIMIT, "qm_mate_rescue: more than 2^24 pairs in one call");
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     bool any = false;
@@ -308,23 +391,40 @@ int qm_mate_rescue(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     if (!any) return QM_OK;                       // no usable insert-size model: every orientation is skipped
     if (stride > kResMaxQuery) return qm_fail(ctx, QM_ELIMIT, "qm_mate_rescue: reads longer than %d bases", kResMaxQuery);
     const int blocks = ctx->sm_count * (stride <= 160 ? 4 : stride <= 256 ? 3 : 2);
-    // scratch 14: counters | pair list | per-warp row logs
-    const size_t o_list = 256, o_log = (o_list + (size_t)n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    // scratch 14: counters | pair list | task blocks of the pairs | tasks | results | per-warp row logs
+    // The up-front task list holds 4 tasks per pair of the batch (a pair can have 32 anchors x 4 orientations, a batch in
+    // which few pairs need rescue -- every realistic one -- uses a small part of it); a pair whose block does not fit is
+    // not run up front, the apply pass then aligns for it as it goes.
+    const size_t cap_tasks = (size_t)n_pairs * 4 + 1024;
+    const size_t o_list = 256, o_blk = (o_list + (size_t)n_pairs * sizeof(int) + 255) & ~(size_t)255;
+    const size_t o_task = (o_blk + (size_t)n_pairs * sizeof(int2) + 255) & ~(size_t)255;
+    const size_t o_res = (o_task + cap_tasks * sizeof(ResTask) + 255) & ~(size_t)255;
+    const size_t o_log = (o_res + cap_tasks * sizeof(ResOut) + 255) & ~(size_t)255;
     void *p = nullptr;
     const int rc = qm_scratch_reserve(ctx, 14, o_log + (size_t)blocks * kResWarps * kResLog * sizeof(uint32_t), &p);
     if (rc) return rc;
     char *b = (char *)p;
-    int *n_list = (int *)b, *cursor = (int *)(b + 4), *list = (int *)(b + o_list);
+    int *ctr = (int *)b;                              // [0] listed pairs, [1] tasks, [2] task cursor, [3] pair cursor
+    int *list = (int *)(b + o_list);
+    int2 *blk = (int2 *)(b + o_blk);
+    ResTask *tasks = (ResTask *)(b + o_task);
+    ResOut *results = (ResOut *)(b + o_res);
+    uint32_t *logs = (uint32_t *)(b + o_log);
+    unsigned long long *stats = (unsigned long long *)d_stats;
     QM_CUDA(ctx, cudaMemsetAsync(b, 0, 256, st));
     PesArg P;
     for (int d = 0; d < 4; ++d) P.p[d] = pes[d];
-    rescue_scan_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(idx->v, *opt, P, n_pairs, d_regs, d_n_regs, list, n_list);
-    uint32_t *logs = (uint32_t *)(b + o_log);
-    unsigned long long *stats = (unsigned long long *)d_stats;
     // reads are at most `stride` long: 5 / 8 / 16 query columns per lane
-    if (stride <= 160) rescue_kernel<5><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor, logs, stats);
-    else if (stride <= 256) rescue_kernel<8><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor, logs, stats);
-    else rescue_kernel<16><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, n_list, cursor, logs, stats);
+    const int C = stride <= 160 ? 5 : stride <= 256 ? 8 : 16;
+    rescue_scan_kernel<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(idx->v, *opt, P, n_pairs, 32 * C, d_regs, d_n_regs, d_lens, list, blk, tasks, (int)cap_tasks, ctr);
+#define QM_RES_LAUNCH(C_)                                                                                                                   \
+    do {                                                                                                                                    \
+        rescue_align_kernel<C_><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, tasks, (int)cap_tasks, ctr, logs, results); \
+        rescue_apply_kernel<C_><<<blocks, kResWarps * 32, 0, st>>>(idx->v, *opt, P, d_codes, stride, d_lens, d_regs, d_n_regs, list, blk, tasks,    \
+                                                                  results, ctr, logs, stats);                                               \
+    } while (0)
+    if (C == 5) QM_RES_LAUNCH(5); else if (C == 8) QM_RES_LAUNCH(8); else QM_RES_LAUNCH(16);
+#undef QM_RES_LAUNCH
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }

@@ -32,7 +32,7 @@ def _workload(name, n):
     raise KeyError(name)
 
 
-def run_both(ctx, W, n_pairs, pair0=0):
+def run_both(ctx, W, n_pairs, pair0=0, flags=0):
     import torch
     from quasimodo_b200 import _lib
     from oracle import qmo_py
@@ -40,8 +40,10 @@ def run_both(ctx, W, n_pairs, pair0=0):
     lens = np.full(2 * n_pairs, W.params.read_len, np.int32)
     opt_o = qmo_py.default_opt()
     opt_o.w = W.w
+    opt_o.flags = flags
     opt_g = _lib.default_opt()
     opt_g.w = W.w
+    opt_g.flags = flags
     # ---- oracle ----
     ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
     o = qmo_py.align_se(ref, codes, lens, opt=opt_o)
@@ -123,6 +125,17 @@ def test_pipeline_parity(ctx, name, n):
     assert mapped.mean() > 0.8
     assert o["resc_stats"][0] > 0 and (o["n_regs_resc"] != o["n_regs"]).any()      # rescue ran and placed something
     assert o["counts"][:, 14].sum() > 0
+
+
+def test_pipeline_without_mate_rescue(ctx):
+    """bwa mem -S (QM_F_NO_RESCUE): the paired stage skips mem_matesw on both sides; fewer reads are placed than with it"""
+    from quasimodo_b200 import _lib
+    W = _workload("cfg1", 3000)
+    g, o = run_both(ctx, W, 3000, flags=_lib.F_NO_RESCUE)
+    compare(g, o)
+    g2, _ = run_both(ctx, W, 3000)
+    placed = lambda a: int(((a["flag"] & 4) == 0).sum())
+    assert placed(g2["alns"]) > placed(g["alns"])
 
 
 def test_pipeline_pair_offset(ctx):
