@@ -144,7 +144,7 @@ def run_reference(args):
     per_step = max(20_000, int(calibrated_cpu_sample(args) / max(1, args.steps + args.warmup) * 4))
     per_step -= per_step % 1000
     value, ms = cpu_arm(args, args.steps, args.warmup, per_step)
-    sample = f"{per_step} pairs per step (prefix of each step's sample), oracle port: seeding+extension+pairing+CIGAR+pileup"
+    sample = f"{per_step} pairs per step (prefix of each step's sample), oracle port: seeding+extension+mate rescue+pairing+CIGAR+pileup"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "int32", "data": "synthetic", "config": config_dict(args, args.gpus),
@@ -399,7 +399,7 @@ def run_ours(args):
         v, cms = cpu_arm(args, 1, 0, n)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": qmo_py.n_threads(), "kind": "port",
                                "sample": f"first {n} pairs of sample TA-1-0 ({cms / 1e3:.1f} s): oracle port of bwa-mem "
-                                         "extension + pairing + CIGAR + bcftools-style counting, OpenMP over reads"}
+                                         "extension + mate rescue + pairing + CIGAR + bcftools-style counting, OpenMP over reads"}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
