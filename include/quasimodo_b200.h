@@ -298,6 +298,21 @@ int qm_sample_set_rmdup(qm_sample *s, int on);
 int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream);
 int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records);
 
+/* ---- text pileup (replaces `samtools mpileup -f ref bam`, rules/vcfcall.smk:39; consumer: the VarScan rule) ----
+ * One line per column covered by an admitted read: chrom, 1-based position, reference base, number of entries with base
+ * quality >= min_bq, base string (. , ACGTN acgtn * ^X $ +nSEQ -nSEQ), quality string; SURVEY.md A.10.  Admission and
+ * mate-overlap quality rewrite as qm_pileup_accumulate (BAQ off, no depth cap); reads enter a column in coordinate-sorted
+ * order.  names[i] = name of contig i.  The text is left in library scratch on the device: *d_text is valid until the
+ * next text-producing call on the context.  The _host form takes the sample's records / reads / qualities from host
+ * memory; qm_mpileup_text_fetch copies the text of the last call out.  Synchronous. */
+int qm_mpileup_text(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns, const uint8_t *d_codes,
+                    const uint8_t *d_quals, int32_t stride, const int32_t *d_lens, int64_t n_pairs, const char *const *names,
+                    const char **d_text, int64_t *h_bytes, void *stream);
+int qm_mpileup_text_host(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *h_alns, const uint8_t *h_codes,
+                         const uint8_t *h_quals, int32_t stride, const int32_t *h_lens, int64_t n_pairs, const char *const *names,
+                         int64_t *h_bytes);
+int qm_mpileup_text_fetch(qm_ctx *ctx, char *h_out, int64_t bytes);
+
 /* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
  * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,
  * 4 pileup, 5 h2d, 6 d2h, 7 other, 8 mate rescue.  qm_profile_collect synchronises the device and returns + clears the totals;

@@ -151,6 +151,13 @@ void qmo_pileup_opt_default(qmo_pileup_opt_t *p);
 void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs, const qmo_aln_t *alns,
                 const uint8_t *reads, const uint8_t *quals, int stride, const int32_t *lens, int32_t *counts);
 
+/* samtools-mpileup text of the batch (rules/vcfcall.smk:39) with the admission / overlap rules above;
+ * names[i] = name of contig i.  *out is malloc'ed (release with qmo_free); returns its length (< 2 GB). */
+int64_t qmo_mpileup_text(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs, const qmo_aln_t *alns,
+                         const uint8_t *reads, const uint8_t *quals, int stride, const int32_t *lens,
+                         const char *const *names, char **out);
+void qmo_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

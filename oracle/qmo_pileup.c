@@ -115,3 +115,145 @@ void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs,
     free(rp[0]); free(rp[1]); free(sq[0]); free(sq[1]); free(ql[0]); free(ql[1]);
     }
 }
+
+/* ---- samtools mpileup text (reference call site rules/vcfcall.smk:39, consumer VarScan; upstream samtools 1.9
+ * bam_plcmd.c mpileup / pileup_seq and htslib sam.c resolve_cigar2 are not vendored -- SURVEY.md A.10 is the spec).
+ * Same read admission and mate-overlap quality rewrite as the counting above (BAQ off, no depth cap).  Reads enter a
+ * column in coordinate-sorted order (samtools sort: contig, position, strand; input order on ties).  A line is
+ * written for every column some admitted read covers: chrom, 1-based position, reference base, the number of
+ * entries whose base quality reaches min_bq, their base string and their quality string.  Per entry:
+ *   ^X   the read starts here (X = min(MAPQ, 93) + 33)
+ *   . ,  base equal to the reference (forward / reverse strand);  ACGTN acgtn otherwise;  * deleted here
+ *   +nSEQ / -nSEQ  an insertion / deletion follows this position (inserted read bases / deleted reference bases)
+ *   $    the read ends here
+ * The quality of a deleted position is the one of the first read base behind the deletion (resolve_cigar2 leaves qpos
+ * there).  PARITY UNPINNED. */
+typedef struct { char *s; int n, cap; } dstr_t;
+static void dput(dstr_t *d, int c)
+{
+    if (d->n == d->cap) { d->cap = d->cap ? d->cap * 2 : 16; d->s = (char *)realloc(d->s, (size_t)d->cap); }
+    d->s[d->n++] = (char)c;
+}
+static void dnum(dstr_t *d, int v) { char b[16]; int n = 0; do { b[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) dput(d, b[--n]); }
+
+typedef struct { int64_t key; int32_t rec; } srt_t;
+static int srt_cmp(const void *a, const void *b)
+{
+    const srt_t *x = (const srt_t *)a, *y = (const srt_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->rec < y->rec ? -1 : x->rec > y->rec;
+}
+
+int64_t qmo_mpileup_text(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs, const qmo_aln_t *alns,
+                         const uint8_t *reads, const uint8_t *quals, int stride, const int32_t *lens,
+                         const char *const *names, char **out)
+{
+    const int64_t n = 2 * n_pairs;
+    uint8_t *sq = (uint8_t *)malloc((size_t)n * stride), *ql = (uint8_t *)malloc((size_t)n * stride);
+    uint8_t *ok = (uint8_t *)calloc((size_t)n, 1);
+    int32_t *rpa = (int32_t *)malloc(4 * (size_t)stride), *rpb = (int32_t *)malloc(4 * (size_t)stride);
+    dstr_t *bs = (dstr_t *)calloc((size_t)R->l_pac, sizeof(dstr_t)), *qs = (dstr_t *)calloc((size_t)R->l_pac, sizeof(dstr_t));
+    uint8_t *covered = (uint8_t *)calloc((size_t)R->l_pac, 1);
+    srt_t *order = (srt_t *)malloc(sizeof(srt_t) * (size_t)n);
+    int64_t pi, r, m = 0, c, total = 0;
+    static const char up[] = "ACGTN", lo[] = "acgtn";
+    for (pi = 0; pi < n_pairs; ++pi) {
+        const qmo_aln_t *a[2] = { &alns[2 * pi], &alns[2 * pi + 1] };
+        int e, i, L[2] = { lens[2 * pi], lens[2 * pi + 1] };
+        for (e = 0; e < 2; ++e) {
+            const uint8_t *rd = reads + (2 * pi + e) * stride, *qv = quals + (2 * pi + e) * stride;
+            uint8_t *s = sq + (2 * pi + e) * stride, *q = ql + (2 * pi + e) * stride;
+            const int rev = (a[e]->flag & 0x10) != 0;
+            ok[2 * pi + e] = (uint8_t)admitted(po, a[e]);
+            for (i = 0; i < L[e]; ++i) {
+                int cc = rev ? rd[L[e] - 1 - i] : rd[i];
+                s[i] = (uint8_t)(rev ? (cc > 3 ? 4 : 3 - cc) : cc);
+                q[i] = rev ? qv[L[e] - 1 - i] : qv[i];
+            }
+        }
+        if (!po->ignore_overlaps && ok[2 * pi] && ok[2 * pi + 1] && a[0]->rid == a[1]->rid &&
+            (a[0]->flag & 0x2) && !(a[0]->flag & 0x8) && abs(a[0]->tlen) < 2 * L[0] && abs(a[1]->tlen) < 2 * L[1]) {
+            int first = 0, r0 = (a[0]->flag & 0x10) != 0, r1 = (a[1]->flag & 0x10) != 0, ia, ib = 0;
+            if (a[1]->pos < a[0]->pos || (a[1]->pos == a[0]->pos && r1 < r0)) first = 1;
+            {
+                const int A = first, B = !first;
+                uint8_t *sA = sq + (2 * pi + A) * stride, *sB = sq + (2 * pi + B) * stride;
+                uint8_t *qA = ql + (2 * pi + A) * stride, *qB = ql + (2 * pi + B) * stride;
+                expand(a[A], L[A], rpa); expand(a[B], L[B], rpb);
+                for (ia = 0; ia < L[A]; ++ia) {
+                    int p = rpa[ia];
+                    if (p < 0) continue;
+                    while (ib < L[B] && (rpb[ib] < 0 || rpb[ib] < p)) ++ib;
+                    if (ib >= L[B]) break;
+                    if (rpb[ib] != p) continue;
+                    if (sA[ia] == sB[ib]) { int q = qA[ia] + qB[ib]; qA[ia] = (uint8_t)(q > 200 ? 200 : q); qB[ib] = 0; }
+                    else if (qA[ia] >= qB[ib]) { qA[ia] = (uint8_t)(0.8 * qA[ia]); qB[ib] = 0; }
+                    else { qB[ib] = (uint8_t)(0.8 * qB[ib]); qA[ia] = 0; }
+                }
+            }
+        }
+    }
+    for (r = 0; r < n; ++r)
+        if (ok[r]) { order[m].key = ((R->off[alns[r].rid] + alns[r].pos) << 1) | ((alns[r].flag & 0x10) != 0); order[m].rec = (int32_t)r; ++m; }
+    qsort(order, (size_t)m, sizeof(srt_t), srt_cmp);
+    for (r = 0; r < m; ++r) {
+        const qmo_aln_t *a = &alns[order[r].rec];
+        const uint8_t *s = sq + (int64_t)order[r].rec * stride, *q = ql + (int64_t)order[r].rec * stride;
+        const int L = lens[order[r].rec], rev = (a->flag & 0x10) != 0;
+        const int64_t base = R->off[a->rid], clen = R->len[a->rid];
+        const char *let = rev ? lo : up;
+        int k, x = a->pos, y = 0, end = a->pos, i, j;
+        for (k = 0; k < a->n_cigar; ++k) { int op = a->cigar[k] & 0xf; if (op == 0 || op == 2) end += (int)(a->cigar[k] >> 4); }
+        for (k = 0; k < a->n_cigar; ++k) {
+            const int op = a->cigar[k] & 0xf, len = (int)(a->cigar[k] >> 4);
+            if (op == 1 || op == 4) { y += len; continue; }
+            if (op != 0 && op != 2) continue;
+            for (i = 0; i < len; ++i) {
+                const int p = x + i, is_del = op == 2, qpos = is_del ? y : y + i;
+                const int qual = qpos < L ? q[qpos] : 0;
+                int indel = 0;
+                covered[base + p] = 1;
+                if (i == len - 1 && k + 1 < a->n_cigar) {
+                    const int op2 = a->cigar[k + 1] & 0xf, l2 = (int)(a->cigar[k + 1] >> 4);
+                    if (op2 == 2) indel = -l2; else if (op2 == 1) indel = l2;
+                }
+                if (qual < po->min_bq) continue;
+                {
+                    dstr_t *d = &bs[base + p];
+                    if (p == a->pos) { dput(d, '^'); dput(d, a->mapq > 93 ? 126 : a->mapq + 33); }
+                    if (!is_del) {
+                        const int cc = qpos < L ? s[qpos] : 4;
+                        if (cc < 4 && cc == R->fwd[base + p]) dput(d, rev ? ',' : '.'); else dput(d, let[cc]);
+                    } else dput(d, '*');
+                    if (indel > 0) { dput(d, '+'); dnum(d, indel); for (j = 1; j <= indel; ++j) dput(d, let[qpos + j < L ? s[qpos + j] : 4]); }
+                    else if (indel < 0) { dput(d, '-'); dnum(d, -indel); for (j = 1; j <= -indel; ++j) dput(d, p + j < clen ? let[R->fwd[base + p + j]] : let[4]); }
+                    if (p == end - 1) dput(d, '$');
+                    dput(&qs[base + p], qual + 33 < 126 ? qual + 33 : 126);
+                }
+            }
+            x += len; if (op == 0) y += len;
+        }
+    }
+    {
+        dstr_t o = {0, 0, 0};
+        int ci;
+        for (ci = 0; ci < R->n_contigs; ++ci)
+            for (c = 0; c < R->len[ci]; ++c) {
+                const int64_t g = R->off[ci] + c;
+                const char *nm = names[ci];
+                int i;
+                if (!covered[g]) continue;
+                while (*nm) dput(&o, *nm++);
+                dput(&o, '\t'); dnum(&o, (int)(c + 1)); dput(&o, '\t'); dput(&o, up[R->fwd[g]]); dput(&o, '\t'); dnum(&o, qs[g].n); dput(&o, '\t');
+                for (i = 0; i < bs[g].n; ++i) dput(&o, bs[g].s[i]);
+                dput(&o, '\t');
+                for (i = 0; i < qs[g].n; ++i) dput(&o, qs[g].s[i]);
+                dput(&o, '\n');
+            }
+        *out = o.s; total = o.n;
+    }
+    for (c = 0; c < R->l_pac; ++c) { free(bs[c].s); free(qs[c].s); }
+    free(bs); free(qs); free(covered); free(order); free(sq); free(ql); free(ok); free(rpa); free(rpb);
+    return total;
+}
+void qmo_free(void *p) { free(p); }

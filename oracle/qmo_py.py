@@ -241,6 +241,30 @@ def pileup(ref, alns, reads, quals, lens, popt=None):
     return counts
 
 
+def mpileup_text(ref, alns, reads, quals, lens, names, popt=None):
+    """-> bytes: samtools-mpileup text of the batch"""
+    L = lib()
+    L.qmo_mpileup_text.restype = C.c_int64
+    L.qmo_mpileup_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    L.qmo_free.argtypes = [C.c_void_p]
+    if popt is None:
+        popt = PileupOpt()
+        L.qmo_pileup_opt_default(C.byref(popt))
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    alns = np.ascontiguousarray(alns, dtype=ALN_DTYPE)
+    arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+    out = C.c_void_p()
+    size = L.qmo_mpileup_text(ref._h, C.byref(popt), n // 2, alns.ctypes.data, reads.ctypes.data, quals.ctypes.data, stride,
+                              lens.ctypes.data, arr, C.byref(out))
+    text = C.string_at(out, size)
+    L.qmo_free(out)
+    return text
+
+
 PESTAT_PAIRS = 65536
 
 

@@ -111,6 +111,9 @@ SIGNATURES = {
     "qm_sample_set_rmdup": (C.c_int, [_P, C.c_int]),
     "qm_sample_rmdup_finish": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
     "qm_sample_kept_alns_host": (C.c_int, [_P, _P, _L]),
+    "qm_mpileup_text": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
+    "qm_mpileup_text_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P]),
+    "qm_mpileup_text_fetch": (C.c_int, [_P, _P, _L]),
     "qm_profile_enable": (C.c_int, [_P, C.c_int]),
     "qm_profile_collect": (C.c_int, [_P, _P, _P]),
     "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),

@@ -286,6 +286,19 @@ class Context:
         _check(self._h, rc, "qm_pileup_accumulate")
         return d_counts
 
+    def mpileup_text(self, idx, d_alns, d_codes, d_quals, d_lens, names, stream=0, popt=None):
+        """samtools-mpileup text of the device-resident records -> bytes (copied to the host)"""
+        popt = popt or self.pileup_opt
+        n, stride = d_codes.shape
+        arr = (C.c_char_p * len(names))(*[s.encode() for s in names])
+        d_text, nbytes = C.c_void_p(), C.c_int64(0)
+        rc = _lib.lib().qm_mpileup_text(self._h, idx._h, C.byref(popt), _ptr(d_alns), _ptr(d_codes), _ptr(d_quals), stride, _ptr(d_lens),
+                                        n // 2, arr, C.byref(d_text), C.byref(nbytes), C.c_void_p(stream))
+        _check(self._h, rc, "qm_mpileup_text")
+        buf = C.create_string_buffer(max(1, nbytes.value))
+        _check(self._h, _lib.lib().qm_mpileup_text_fetch(self._h, buf, nbytes.value), "qm_mpileup_text_fetch")
+        return buf.raw[:nbytes.value]
+
     def counts_to_rows(self, idx, d_planes, stream=0):
         import torch
         rows = torch.empty(idx.l_pac * _lib.NCH, dtype=torch.int32, device=d_planes.device)

@@ -23,7 +23,7 @@ struct qm_ctx {
     int sm_count = 0;
     std::string err;
     // scratch arenas grown on demand (never shrunk); index = purpose
-    qm_scratch scratch[16];
+    qm_scratch scratch[20];
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     // side streams: the independent per-class extension kernels of one round run concurrently (fork/join by events)
     cudaStream_t side[12] = {};
@@ -34,6 +34,7 @@ struct qm_ctx {
     int se_n_parts = 0;
     int64_t se_part_end[16] = {};
     cudaEvent_t se_part_ev[16] = {};
+    int64_t text_bytes = 0;            // length of the text the last qm_mpileup_text left in scratch 17
     void *h_pinned = nullptr;          // 8 KB of page-locked host memory for the small per-round read-backs
     bool prof_on = false;
     std::vector<qm_prof_span> prof_spans;

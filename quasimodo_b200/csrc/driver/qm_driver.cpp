@@ -4,7 +4,9 @@
 //
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf] [--gpu I] [-t THREADS] [-w BAND]
-//                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1]
+//                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
+//        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
+//        semantics, formatted on the device (with --rmdup 1: of the duplicate-free records, as the reference's rule reads them)
 //        --no-rescue 1 = bwa mem -S (mate rescue off; on by default as in the reference's command line)
 //        --rmdup: duplicates are marked on the device with picard MarkDuplicates' rule (rules/rmdup.smk:13-16) before
 //        anything is counted, as in the reference where every caller reads the .rmdup.bam; --bam still holds all records
@@ -702,8 +704,10 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     const std::string rmdup_bam = a.get("rmdup-bam"), metrics = a.get("metrics");
     if (!rmdup && (!rmdup_bam.empty() || !metrics.empty())) die(1, "--rmdup-bam / --metrics need --rmdup 1");
     if (rmdup) L.check(qm_sample_set_rmdup(smp, 1), "qm_sample_set_rmdup");
+    const std::string mpileup = a.get("mpileup");
     const bool want_bam = !bam.empty() || !rmdup_bam.empty();
-    const bool keep = want_bam || decontam;           // records / reads needed after the batch loop
+    const bool want_batches = want_bam || !mpileup.empty();
+    const bool keep = want_batches || decontam;       // records / reads needed after the batch loop
     FastqPairReader fr(a.get("r1"), a.get("r2"));
     std::vector<Batch> batches;
     std::vector<int64_t> first_read;
@@ -732,7 +736,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         }
         first_read.push_back(2 * n_pairs);
         n_pairs += b.n_pairs;
-        if (want_bam) batches.push_back(std::move(b));
+        if (want_batches) batches.push_back(std::move(b));
         else free_batch(L, b);
     }
     if (decontam) {
@@ -746,7 +750,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         int64_t n_dup = 0;
         L.check(qm_sample_rmdup_finish(smp, &n_dup, nullptr), "qm_sample_rmdup_finish");
         fprintf(stderr, "[qm_driver] rmdup: %lld of %lld pairs are duplicates\n", (long long)n_dup, (long long)n_pairs);
-        if (want_bam) {                                // final flags of every record, batch by batch
+        if (want_batches) {                            // final flags of every record, batch by batch
             std::vector<qm_aln> all((size_t)2 * n_pairs);
             L.check(qm_sample_kept_alns_host(smp, all.data(), (int64_t)all.size()), "qm_sample_kept_alns_host");
             size_t off = 0;
@@ -777,6 +781,34 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         L.check(qm_sample_call_snps_host(smp, &copt, calls.data(), (int64_t)calls.size(), &nc), "qm_sample_call_snps_host");
         calls.resize((size_t)nc);
         write_vcf(vcf, g, a.get("sample", "sample"), split(a.get("ref"), ',')[0], calls);
+    }
+    if (!mpileup.empty()) {
+        // text pileup (samtools mpileup format) of the whole sample: records, reads and qualities go to the device once more,
+        // at one common stride; the text comes back in one piece
+        int32_t stride = 1;
+        for (auto &b : batches) stride = std::max(stride, b.stride);
+        std::vector<qm_aln> alns((size_t)2 * n_pairs);
+        std::vector<uint8_t> codes((size_t)2 * n_pairs * stride, 4), quals((size_t)2 * n_pairs * stride, 0);
+        std::vector<int32_t> lens((size_t)2 * n_pairs);
+        size_t r0 = 0;
+        for (auto &b : batches) {
+            for (int64_t r = 0; r < 2 * b.n_pairs; ++r) {
+                alns[r0 + r] = b.alns[r]; lens[r0 + r] = b.lens[r];
+                memcpy(&codes[(r0 + r) * stride], b.codes + (size_t)r * b.stride, (size_t)b.lens[r]);
+                memcpy(&quals[(r0 + r) * stride], b.quals + (size_t)r * b.stride, (size_t)b.lens[r]);
+            }
+            r0 += (size_t)2 * b.n_pairs;
+        }
+        std::vector<const char *> nm;
+        for (auto &s : g.names) nm.push_back(s.c_str());
+        int64_t bytes = 0;
+        L.check(qm_mpileup_text_host(L.ctx, idx, &popt, alns.data(), codes.data(), quals.data(), stride, lens.data(), n_pairs, nm.data(), &bytes),
+                "qm_mpileup_text_host");
+        std::vector<char> text((size_t)bytes);
+        L.check(qm_mpileup_text_fetch(L.ctx, text.data(), bytes), "qm_mpileup_text_fetch");
+        FILE *fp = fopen(mpileup.c_str(), "w");
+        if (!fp || (bytes && fwrite(text.data(), 1, (size_t)bytes, fp) != (size_t)bytes) || fclose(fp) != 0) die(2, "cannot write %s", mpileup.c_str());
+        fprintf(stderr, "[qm_driver] text pileup: %lld bytes\n", (long long)bytes);
     }
     if (want_bam) {
         // coordinate sort on the device: keys from the records, stable radix sort, gather through the permutation

@@ -82,11 +82,11 @@ def sample_case(tmp_path_factory):
     fa, r1, r2 = str(d / "ref.fa"), str(d / "r1.fq.gz"), str(d / "r2.fq.gz")
     drvutil.write_fasta(W.ref, fa)
     drvutil.write_fastq(codes, quals, lens, names, r1, r2, gz=True)
-    bam, tsv, vcf = str(d / "s.bam"), str(d / "s.mpileup"), str(d / "s.vcf")
+    bam, tsv, vcf, txt = str(d / "s.bam"), str(d / "s.mpileup"), str(d / "s.vcf"), str(d / "s.text.mpileup")
     p = drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--bam", bam, "--counts", tsv, "--vcf", vcf, "--sample", "TM-1-1",
-                            "--min-dp", 3, "--min-alt", 2, "-t", 4])
+                            "--min-dp", 3, "--min-alt", 2, "-t", 4, "--mpileup", txt])
     return dict(W=W, n=n, codes=codes, quals=quals, lens=lens, alns=alns, counts=counts, cells=cells, names=names, perm=sort_py.sort_perm(alns),
-                bam=bamio.Bam(bam), bam_path=bam, tsv=tsv, vcf=vcf, fa=fa, r1=r1, r2=r2, dir=d, stderr=p.stderr)
+                bam=bamio.Bam(bam), bam_path=bam, tsv=tsv, vcf=vcf, txt=txt, ref=ref, fa=fa, r1=r1, r2=r2, dir=d, stderr=p.stderr)
 
 
 def test_driver_bam_matches_oracle_records_in_samtools_order(sample_case):
@@ -95,6 +95,15 @@ def test_driver_bam_matches_oracle_records_in_samtools_order(sample_case):
     assert drvutil.check_bam_records(sample_case) > sample_case["n"]
     refs, n_no_coor = bamio.read_bai(sample_case["bam_path"] + ".bai")
     assert n_no_coor == int((sample_case["alns"]["rid"] < 0).sum()) > 0
+
+
+def test_driver_text_pileup_matches_oracle(sample_case):
+    """--mpileup: the samtools-mpileup text of the sample (reads of ragged lengths, two contigs) equals the oracle's, byte for byte"""
+    from oracle import qmo_py
+    c = sample_case
+    want = qmo_py.mpileup_text(c["ref"], c["alns"], c["codes"], c["quals"], c["lens"], list(c["W"].ref.names))
+    got = open(c["txt"], "rb").read()
+    assert len(want) > 100000 and got == want
 
 
 def test_driver_count_tsv_matches_oracle(sample_case):

@@ -1,0 +1,78 @@
+"""Text pileup (samtools mpileup format) produced on the device against the oracle's
+restatement, byte for byte, on the BASELINE configs (indels: cfg5; several contigs: cfg3), plus format properties."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from quasimodo_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def run(ctx, W, n):
+    import torch
+    from quasimodo_b200 import _lib
+    from oracle import qmo_py
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    opt_o = qmo_py.default_opt(); opt_o.w = W.w
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns, _, _, _ = qmo_py.run_sample(ref, codes, quals, lens, opt=opt_o)
+    names = [f"contig{i}" for i in range(len(W.ref.lens))]
+    o_text = qmo_py.mpileup_text(ref, alns, codes, quals, lens, names)
+    dev = torch.device("cuda:0")
+    idx = ctx.index(W.ref, 31)
+    g_text = ctx.mpileup_text(idx, torch.from_numpy(alns.view(np.uint8).reshape(-1)).to(dev), torch.from_numpy(codes).to(dev),
+                              torch.from_numpy(quals).to(dev), torch.from_numpy(lens).to(dev), names)
+    idx.close()
+    return g_text, o_text, alns
+
+
+@pytest.mark.parametrize("name,n", [("cfg1", 3000), ("cfg5", 2000), ("cfg3", 3000), ("cfg2", 20000)])
+def test_text_pileup_equals_oracle(ctx, name, n):
+    from tests.test_pipeline_gpu import _workload
+    g, o, _ = run(ctx, _workload(name, n), n)
+    assert len(o) > 100000
+    if g != o:
+        gl, ol = g.split(b"\n"), o.split(b"\n")
+        assert len(gl) == len(ol), (len(gl), len(ol))
+        bad = [i for i in range(len(ol)) if gl[i] != ol[i]]
+        assert not bad, (len(bad), gl[bad[0]][:200], ol[bad[0]][:200])
+    assert g == o
+
+
+def test_text_pileup_format(ctx):
+    from tests.test_pipeline_gpu import _workload
+    g, _, alns = run(ctx, _workload("cfg5", 1500), 1500)
+    lines = [l.split(b"\t") for l in g.split(b"\n") if l]
+    assert all(len(f) == 6 for f in lines)
+    assert all(int(f[3]) == len(f[5]) for f in lines)
+    pos = [int(f[1]) for f in lines]
+    assert pos == sorted(pos)
+    text = b"".join(f[4] for f in lines)
+    # every admitted read opens and closes once, unless the quality at its first / last column fails the filter
+    admitted = ((alns["flag"] & 4) == 0) & ((alns["flag"] & 2) != 0)
+    assert 0.9 * admitted.sum() < text.count(b"^") <= admitted.sum()
+    assert b"+" in text and b"-" in text and b"*" in text
+
+
+def test_text_pileup_empty(ctx):
+    """no admitted read -> no line"""
+    import torch
+    from quasimodo_b200 import workloads, _lib
+    W = workloads.config1(64)
+    codes, quals, _, _ = W.simulate_host(0, 64)
+    lens = np.full(128, 150, np.int32)
+    alns = np.zeros(128, dtype=_lib.ALN_DTYPE)
+    alns["flag"] = 4; alns["rid"] = -1; alns["n_cigar"] = 0
+    dev = torch.device("cuda:0")
+    idx = ctx.index(W.ref, 31)
+    g = ctx.mpileup_text(idx, torch.from_numpy(alns.view(np.uint8).reshape(-1)).to(dev), torch.from_numpy(codes).to(dev),
+                         torch.from_numpy(quals).to(dev), torch.from_numpy(lens).to(dev), ["x"])
+    idx.close()
+    assert g == b""

@@ -96,3 +96,45 @@ def test_packed_genomes_equal_bwas_own_index_files():
         G = genomes.load(stem)
         assert G.names == g["names"] and G.lens == g["lens"] and G.total == g["l_pac"], stem
         assert hashlib.sha256(G.codes.tobytes()).hexdigest() == g["sha256_codes"], stem
+
+
+def test_text_pileup_agrees_with_the_count_tensor(run):
+    """the two restatements of the column walk (counts, samtools-mpileup text) agree column by column"""
+    import re
+    text = qmo_py.mpileup_text(qmo_py.Ref(run["W"].ref.codes, run["W"].ref.lens, k=31), run["alns"], run["codes"], run["quals"],
+                               np.full(2 * run["n"], 150, np.int32), ["Merlin"])
+    cnt = run["counts"]
+    seen = np.zeros(len(cnt), bool)
+    strip = re.compile(rb"\^.|\$|[+-](\d+)")
+    for line in text.split(b"\n"):
+        if not line:
+            continue
+        chrom, pos, refb, depth, bases, quals = line.split(b"\t")
+        p = int(pos) - 1
+        seen[p] = True
+        assert chrom == b"Merlin" and refb == b"ACGT"[run["W"].ref.codes[p]:run["W"].ref.codes[p] + 1]
+        assert int(depth) == len(quals)
+        # drop ^X, $ and indel strings, then one character per entry
+        out, i = [], 0
+        while i < len(bases):
+            c = bases[i:i + 1]
+            if c == b"^":
+                i += 2
+            elif c == b"$":
+                i += 1
+            elif c in b"+-":
+                m = re.match(rb"\d+", bases[i + 1:])
+                i += 1 + len(m.group()) + int(m.group())
+            else:
+                out.append(c)
+                i += 1
+        assert len(out) == int(depth)
+        n_star = sum(1 for c in out if c == b"*")
+        assert int(depth) - n_star == int(cnt[p, 0:5].sum() + cnt[p, 6:11].sum())
+        assert n_star <= int(cnt[p, 5] + cnt[p, 11])
+        fwd_ref = sum(1 for c in out if c == b".")
+        rev_ref = sum(1 for c in out if c == b",")
+        r = run["W"].ref.codes[p]
+        assert fwd_ref == cnt[p, r] and rev_ref == cnt[p, 6 + r]
+    # a column has a line iff an admitted read covers it (raw depth or a deletion)
+    assert np.array_equal(seen, (cnt[:, 14] + cnt[:, 5] + cnt[:, 11]) > 0)
