@@ -92,6 +92,97 @@ def extract_tp_fp_snp(vcf_file, snp_file):
         fh.write("".join(x + "\n" for x in header + [b for b, h in zip(body, hit) if not h]))
 
 
+# ---- "bring your own data" variant (program/extract_TP_FP_SNPs.py:60-105; eval_variant_custom.smk) ----
+def custom_truth_patterns(rows):
+    """awk -F"\t" '$2!="."&&$3!="."{print $1,".",$2,$3}' on `show-snps -CTHIlr` rows (P1, ref base, query base, ...)"""
+    pats = set()
+    for ln in rows:
+        f = ln.rstrip("\n").split("\t")
+        f += [""] * (3 - len(f))
+        if f[1] != "." and f[2] != ".":
+            pats.add((f[0], f[1], f[2]))
+    return pats
+
+
+def line_matches_any(line, pats):
+    """`fgrep -w` of "P1\t.\tX\tY" for arbitrary field texts: some occurrence of the fixed string starts at the line start or
+    behind a non-word character and ends at the line end or before one"""
+    for p0, x, y in pats:
+        s = f"{p0}\t.\t{x}\t{y}"
+        if not s:
+            continue
+        at = line.find(s)
+        while at >= 0:
+            before_ok = at == 0 or not _WORD.match(line[at - 1])
+            end = at + len(s)
+            after_ok = end == len(line) or not _WORD.match(line[end])
+            if before_ok and after_ok:
+                return True
+            at = line.find(s, at + 1)
+    return False
+
+
+def extract_tp_fp_custom_snp(vcf_file, snp_file, outdir, caller):
+    """same outputs as the reference function: <outdir>/<caller>.filtered.vcf, fp/<caller>.fp.vcf, tp/<caller>.tp.vcf
+    (fp/ must exist)"""
+    filtered_out = os.path.join(outdir, caller + ".filtered.vcf")
+    fp_out = os.path.join(outdir, "fp", caller + ".fp.vcf")
+    lines = open(vcf_file).read().split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    header = [ln for ln in lines if ln.startswith("#")]
+    body = [ln for ln in lines if is_snp_line(ln.split("\t"))]
+
+    def dump(path, rows):
+        with open(path, "w") as fh:
+            fh.write("".join(x + "\n" for x in header + rows))
+
+    dump(filtered_out, body)
+    if os.path.basename(vcf_file).split(".")[0].endswith(("-1-0", "-0-1")):
+        dump(fp_out, body)
+        return
+    os.makedirs(os.path.join(outdir, "tp"), exist_ok=True)
+    rows = open(snp_file).read().split("\n")
+    if rows and rows[-1] == "":
+        rows.pop()
+    pats = custom_truth_patterns(rows)
+    hit = [line_matches_any(ln, pats) for ln in body]
+    dump(os.path.join(outdir, "tp", caller + ".tp.vcf"), [b for b, h in zip(body, hit) if h])
+    dump(fp_out, [b for b, h in zip(body, hit) if not h])
+
+
+CUSTOM_HEADER = ["caller", "genomediff", "calleridentify", "TP", "FP", "precision", "recall", "f1"]
+
+
+def custom_performance_row(filtered_vcf, snp_file, caller):
+    """one row of scripts/custom_snp_benchmark.R:23-27,41-88: truth = "P1-ref-alt" of the show-snps rows whose bases are
+    not "." (comment lines '#' skipped, duplicates kept in the count), calls = rows with single A/C/G/T REF and ALT"""
+    truth = []
+    for ln in open(snp_file):
+        if ln.startswith("#") or not ln.strip():
+            continue
+        f = ln.rstrip("\n").split("\t")
+        if len(f) >= 3 and f[1] != "." and f[2] != ".":
+            truth.append(f"{f[0]}-{f[1]}-{f[2]}")
+    n_truth = len(truth)
+    snp = make_snp_vector(filtered_vcf)
+    n_rows = sum(1 for ln in open(filtered_vcf) if not ln.startswith("#") and ln.strip())
+    if n_rows == 0:
+        return [caller, str(n_truth), "0", "0", "0", "NA", "NA", "NA"]
+    n_id = len(snp)
+    s, t = set(snp), set(truth)
+    tp, fp = len(s & t), len(s - t)
+
+    def div(a, b):
+        return float("nan") if b == 0 else a / b
+    precision = r_round3(div(tp, n_id)) if n_id else float("nan")
+    recall = r_round3(div(tp, n_truth)) if n_truth else float("nan")
+    den = precision + recall
+    f1 = r_round3(2 * (precision * recall) / den) if den == den and den != 0 else float("nan")
+    fmt = lambda v: "NaN" if v != v else r_num(v)
+    return [caller, str(n_truth), str(n_id), str(tp), str(fp), fmt(precision), fmt(recall), fmt(f1)]
+
+
 # ---- scripts/caller_performance_compare.R ----
 CALLER_MAP = {"bcftools": "BCFtools", "clc": "CLC", "freebayes": "FreeBayes", "gatk": "GATK", "lofreq": "LoFreq",
               "varscan": "VarScan2"}

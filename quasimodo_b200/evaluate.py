@@ -109,6 +109,97 @@ def extract_tp_fp_snp(ctx, vcf_file, snp_file):
     return len(body), len(tp), len(fp)
 
 
+# ---- "bring your own data" variant: truth = `show-snps -CTHIlr` rows (program/extract_TP_FP_SNPs.py:60-105, rule
+# eval_variant_custom.smk:58-92; table scripts/custom_snp_benchmark.R:23-27,41-88) ----
+def custom_truth_keys(snp_file):
+    """keys of the rows the script's pattern generator ($2!="."&&$3!=".") emits AND a filtered caller line can match:
+    a caller line's REF / ALT are single A/C/G/T and its POS is a plain number, so only such patterns can ever hit"""
+    keys = []
+    for ln in open(snp_file):
+        f = ln.rstrip("\n").split("\t")
+        if len(f) >= 3 and f[1] in _BASE and f[2] in _BASE and f[0].isdigit() and f[0].isascii() and (f[0] == "0" or f[0][0] != "0"):
+            keys.append(snp_key(f[0], f[1], f[2]))
+    return np.array(keys, dtype=np.uint64)
+
+
+def extract_tp_fp_custom_snp(ctx, vcf_file, snp_file, outdir, caller):
+    """program/extract_TP_FP_SNPs.py:60-105 -- writes <outdir>/<caller>.filtered.vcf, fp/<caller>.fp.vcf and (mixtures)
+    tp/<caller>.tp.vcf; returns (n_filtered, n_tp, n_fp)"""
+    filtered_out = os.path.join(outdir, caller + ".filtered.vcf")
+    os.makedirs(os.path.join(outdir, "fp"), exist_ok=True)
+    fp_out = os.path.join(outdir, "fp", caller + ".fp.vcf")
+    lines = open(vcf_file).read().split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    header = [ln for ln in lines if ln.startswith("#")]
+    body = []
+    for ln in lines:
+        f = ln.split("\t")
+        if _is_snp(f) and _qual_ok(f[5] if len(f) > 5 else ""):
+            body.append(ln)
+
+    def dump(path, rows):
+        with open(path, "w") as fh:
+            fh.write("".join(x + "\n" for x in header + rows))
+
+    dump(filtered_out, body)
+    if os.path.basename(vcf_file).split(".")[0].endswith(("-1-0", "-0-1")):
+        dump(fp_out, body)
+        return len(body), 0, len(body)
+    os.makedirs(os.path.join(outdir, "tp"), exist_ok=True)
+    flags, _ = match_keys(ctx, call_keys(body), custom_truth_keys(snp_file))
+    tp = [b for b, h in zip(body, flags) if h]
+    fp = [b for b, h in zip(body, flags) if not h]
+    dump(os.path.join(outdir, "tp", caller + ".tp.vcf"), tp)
+    dump(fp_out, fp)
+    return len(body), len(tp), len(fp)
+
+
+CUSTOM_TABLE_HEADER = ["caller", "genomediff", "calleridentify", "TP", "FP", "precision", "recall", "f1"]
+
+
+def custom_performance_row(ctx, filtered_vcf, snp_file, caller):
+    """one row of the table of scripts/custom_snp_benchmark.R; set sizes from the device matcher.  A truth row whose bases
+    are not single A/C/G/T can never equal a call: it only counts in genomediff."""
+    truth, n_truth = [], 0
+    for ln in open(snp_file):
+        if ln.startswith("#") or not ln.strip():
+            continue
+        f = ln.rstrip("\n").split("\t")
+        if len(f) >= 3 and f[1] != "." and f[2] != ".":
+            n_truth += 1
+            if f[1] in _BASE and f[2] in _BASE:
+                truth.append((f[0], f[1], f[2]))
+    snp = _snp_rows(filtered_vcf)
+    n_rows = sum(1 for ln in open(filtered_vcf) if not ln.startswith("#") and ln.strip())
+    if n_rows == 0:
+        return [caller, str(n_truth), "0", "0", "0", "NA", "NA", "NA"]
+    n_id = len(snp)
+    uniq_c, uniq_t = sorted(set(snp)), sorted(set(truth))
+    # R compares the strings "POS-REF-ALT": a position text that is not a plain number only ever equals itself
+    num = lambda p: p.isdigit() and p.isascii() and (p == "0" or p[0] != "0")
+    plain_c, plain_t = [x for x in uniq_c if num(x[0])], [x for x in uniq_t if num(x[0])]
+    odd = len(set(uniq_c) - set(plain_c) & set(uniq_t) - set(plain_t)) if len(plain_c) != len(uniq_c) else 0
+    ck = np.array([snp_key(int(p), r, a) for p, r, a in plain_c], dtype=np.uint64)
+    tk = np.array([snp_key(int(p), r, a) for p, r, a in plain_t], dtype=np.uint64)
+    cf, _ = match_keys(ctx, ck, tk)
+    tp = int(cf.sum()) + odd
+    fp = len(uniq_c) - tp
+    nan = float("nan")
+    precision = round(tp / n_id, 3) if n_id else nan
+    recall = round(tp / n_truth, 3) if n_truth else nan
+    den = precision + recall
+    f1 = round(2 * (precision * recall) / den, 3) if den == den and den != 0 else nan
+    return [caller, str(n_truth), str(n_id), str(tp), str(fp), _r_num(precision), _r_num(recall), _r_num(f1)]
+
+
+def write_custom_benchmark_table(path, rows):
+    with open(path, "w") as fh:
+        fh.write("\t".join(CUSTOM_TABLE_HEADER) + "\n")
+        for r in rows:
+            fh.write("\t".join(r) + "\n")
+
+
 # ---- table part of scripts/caller_performance_compare.R:29-55,77-143 ----
 CALLER_MAP = {"bcftools": "BCFtools", "clc": "CLC", "freebayes": "FreeBayes", "gatk": "GATK", "lofreq": "LoFreq",
               "varscan": "VarScan2"}

@@ -76,6 +76,28 @@ def main():
         open(tpath, "w").write("\n".join(truth) + "\n")
         subprocess.check_call([sys.executable, REF_SCRIPT, vcf, tpath, "hcmv", d, "bcftools"])
         time.sleep(1.0)                          # the script does not wait for its `tp` child
+    # "bring your own data" mode: truth = show-snps -CTHIlr rows (P1, ref base, query base, P2, BUFF, DIST, R, Q, LEN R, LEN Q,
+    # FRM, FRM, TAG R, TAG Q); "." marks an indel side
+    d = os.path.join(OUT, "custom")
+    os.makedirs(os.path.join(d, "fp"))
+    rows = []
+    for r in truth:
+        if r.startswith("#"):
+            continue
+        f = r.split("\t")
+        if len(f[3]) == 1 and len(f[4]) == 1:
+            rows.append(f"{f[1]}\t{f[3]}\t{f[4]}\t{int(f[1]) + 17}\t12\t{f[1]}\t0\t0\t245038\t237683\t1\t1\tRefGenome\tQryGenome")
+    rows.append("9000\t.\tA\t9017\t0\t9000\t0\t0\t245038\t237683\t1\t1\tRefGenome\tQryGenome")      # insertion: no pattern
+    rows.append("9100\tC\t.\t9117\t0\t9100\t0\t0\t245038\t237683\t1\t1\tRefGenome\tQryGenome")      # deletion: no pattern
+    rows.append("9200\tN\tA\t9217\t0\t9200\t0\t0\t245038\t237683\t1\t1\tRefGenome\tQryGenome")      # pattern no SNP line can match
+    snp_rows = os.path.join(d, "genome_diff.snps")
+    open(snp_rows, "w").write("\n".join(rows) + "\n")
+    vcf = os.path.join(d, "mysample.calls.vcf")
+    body = caller_vcf(rng, truth)
+    body.append("Merlin_1555\t9200\t.\tA\tC\t50\tPASS\tDP=40\tGT\t1")
+    open(vcf, "w").write("\n".join(body) + "\n")
+    subprocess.check_call([sys.executable, REF_SCRIPT, vcf, snp_rows, "custom", d, "mycaller"])
+    time.sleep(1.0)
     print("wrote", OUT)
 
 

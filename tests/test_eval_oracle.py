@@ -28,6 +28,22 @@ def test_extract_matches_reference_script(tmp_path, sample):
         assert not (d / "tp").exists()
 
 
+def test_custom_mode_matches_reference_script(tmp_path):
+    """the "bring your own data" variant (truth = show-snps rows; program/extract_TP_FP_SNPs.py:60-105) against the files the
+    reference's script wrote in that mode"""
+    src = os.path.join(GOLD, "custom")
+    d = tmp_path / "custom"
+    os.makedirs(d / "fp")
+    eval_py.extract_tp_fp_custom_snp(os.path.join(src, "mysample.calls.vcf"), os.path.join(src, "genome_diff.snps"), str(d), "mycaller")
+    for rel in ("mycaller.filtered.vcf", os.path.join("fp", "mycaller.fp.vcf"), os.path.join("tp", "mycaller.tp.vcf")):
+        assert filecmp.cmp(d / rel, os.path.join(src, rel), shallow=False), rel
+    tp = open(os.path.join(src, "tp", "mycaller.tp.vcf")).read()
+    fp = open(os.path.join(src, "fp", "mycaller.fp.vcf")).read()
+    assert "\t9200\t.\tA\tC\t" in fp and "\t1100\t.\tA\tC\t" in tp          # an N row of the truth matches nothing
+    row = eval_py.custom_performance_row(os.path.join(src, "mycaller.filtered.vcf"), os.path.join(src, "genome_diff.snps"), "mycaller")
+    assert row[0] == "mycaller" and int(row[3]) + int(row[4]) <= int(row[2]) and 0 < float(row[5]) < 1
+
+
 def test_quirks_present_in_golden():
     """the golden TP file holds the hits the script's word matching implies"""
     tp = open(os.path.join(GOLD, "TM-1-1", "tp", "TM-1-1.Merlin.bcftools.tp.vcf")).read()

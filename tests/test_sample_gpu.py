@@ -129,6 +129,22 @@ def test_extract_tp_fp_matches_reference_script(ctx, tmp_path, sample):
         assert filecmp.cmp(d / "tp" / (name + ".tp.vcf"), os.path.join(src, "tp", name + ".tp.vcf"), shallow=False)
 
 
+def test_custom_dataset_evaluator_matches_reference_script(ctx, tmp_path):
+    """product evaluate.extract_tp_fp_custom_snp (truth = show-snps rows, CUDA matcher) == the files the reference's own
+    script writes in its "custom" mode; the benchmark-table row == the restatement of custom_snp_benchmark.R"""
+    from quasimodo_b200 import evaluate
+    from oracle import eval_py
+    src = os.path.join(GOLD, "custom")
+    d = tmp_path / "custom"
+    os.makedirs(d)
+    n, tp, fp = evaluate.extract_tp_fp_custom_snp(ctx, os.path.join(src, "mysample.calls.vcf"), os.path.join(src, "genome_diff.snps"), str(d), "mycaller")
+    assert tp > 50 and fp > 50 and n == tp + fp
+    for rel in ("mycaller.filtered.vcf", os.path.join("fp", "mycaller.fp.vcf"), os.path.join("tp", "mycaller.tp.vcf")):
+        assert filecmp.cmp(d / rel, os.path.join(src, rel), shallow=False), rel
+    got = evaluate.custom_performance_row(ctx, str(d / "mycaller.filtered.vcf"), os.path.join(src, "genome_diff.snps"), "mycaller")
+    assert got == eval_py.custom_performance_row(os.path.join(src, "mycaller.filtered.vcf"), os.path.join(src, "genome_diff.snps"), "mycaller")
+
+
 def test_performance_row_matches_oracle(ctx):
     from quasimodo_b200 import evaluate
     from oracle import eval_py
