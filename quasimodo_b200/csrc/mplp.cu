@@ -107,13 +107,41 @@ mplp_prepare_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ al
     if (lane == 0 && my_max) atomicMax(max_span, my_max);
 }
 
+// what the column walk needs of a record, in SORTED order (16 B, read coalesced by the lanes of a column's warp); the
+// alignment record itself is only touched for reads with an indel
+struct SInfo {
+    int32_t gstart;            // forward-strand start, contigs concatenated
+    uint16_t span;             // reference span; 0 = not admitted
+    uint16_t m0;               // gap-free alignments: query index of the first aligned base (the leading soft clip)
+    uint32_t rec;              // index of the record
+    uint16_t len;              // read length
+    uint8_t mapq, flags;       // flags: 1 = reverse strand, 2 = gap-free ([clip] M [clip])
+};
+
 // sorted start positions (records that are not admitted keep their place in the order but never cover a column)
-__global__ void mplp_starts_kernel(const uint32_t *__restrict__ perm, const qm_aln *__restrict__ alns, IndexView V, int64_t n, int32_t *__restrict__ starts)
+__global__ void mplp_starts_kernel(const uint32_t *__restrict__ perm, const qm_aln *__restrict__ alns, const RecInfo *__restrict__ info,
+                                   const int32_t *__restrict__ lens, IndexView V, int64_t n, int32_t *__restrict__ starts, SInfo *__restrict__ sinfo)
 {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const qm_aln &a = alns[perm[k]];
+    const uint32_t rec = perm[k];
+    const qm_aln &a = alns[rec];
     starts[k] = a.rid < 0 ? 0x7fffffff : (int32_t)(V.off[a.rid] + a.pos);      // an unplaced read sits at its mate's position
+    const RecInfo ri = info[rec];
+    SInfo s;
+    s.gstart = ri.gstart; s.span = (uint16_t)ri.span; s.m0 = 0; s.rec = rec; s.len = (uint16_t)lens[rec]; s.mapq = a.mapq;
+    s.flags = (a.flag & 0x10) ? 1 : 0;
+    if (ri.span > 0) {
+        int kk = 0, x = 0;
+        const int nc = a.n_cigar;
+        if (kk < nc && (a.cigar[kk] & 0xf) == 4) { x = (int)(a.cigar[kk] >> 4); ++kk; }
+        if (kk < nc && (a.cigar[kk] & 0xf) == 0) {
+            ++kk;
+            if (kk < nc && (a.cigar[kk] & 0xf) == 4) ++kk;
+            if (kk == nc) { s.flags |= 2; s.m0 = (uint16_t)x; }
+        }
+    }
+    sinfo[k] = s;
 }
 
 __device__ __forceinline__ int n_digits(int v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
@@ -150,8 +178,8 @@ struct NameTab { int32_t off[QM_MAX_CONTIGS + 1]; };
 template <bool WRITE>
 __global__ void __launch_bounds__(kWarps * 32)
 mplp_column_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, const uint8_t *__restrict__ codes,
-                   const uint8_t *__restrict__ tq, int stride, const int32_t *__restrict__ lens, const RecInfo *__restrict__ info,
-                   const uint32_t *__restrict__ perm, const int32_t *__restrict__ starts, int64_t n_rec, const int *__restrict__ max_span,
+                   const uint8_t *__restrict__ tq, int stride, const SInfo *__restrict__ sinfo,
+                   const int32_t *__restrict__ starts, int64_t n_rec, const int *__restrict__ max_span,
                    const char *__restrict__ names, NameTab NT, int64_t *__restrict__ line_len, int32_t *__restrict__ n_entries,
                    const int64_t *__restrict__ line_off, char *__restrict__ out)
 {
@@ -192,17 +220,18 @@ mplp_column_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ aln
             const int64_t k = k0 + lane;
             int nb = 0, nq = 0, cov = 0;
             Entry e; e.covers = false;
-            uint32_t rec = 0;
+            SInfo si; si.rec = 0; si.span = 0; si.flags = 0; si.len = 0; si.mapq = 0;
             int qual = 0;
             if (k < hi) {
-                rec = perm[k];
-                const RecInfo ri = info[rec];
-                if (ri.span > 0 && g < (int64_t)ri.gstart + ri.span) {
-                    e = entry_at(alns[rec], ri.span, p);
+                si = sinfo[k];
+                if (si.span > 0 && g < (int64_t)si.gstart + si.span) {
+                    if (si.flags & 2) {
+                        e.covers = true; e.is_del = false; e.indel = 0; e.qpos = si.m0 + (int)(g - si.gstart);
+                        e.head = g == si.gstart; e.tail = g == (int64_t)si.gstart + si.span - 1;
+                    } else e = entry_at(alns[si.rec], si.span, p);
                     if (e.covers) {
                         cov = 1;
-                        const int L = lens[rec];
-                        qual = e.qpos < L ? tq[(int64_t)rec * stride + e.qpos] : 0;
+                        qual = e.qpos < si.len ? tq[(int64_t)si.rec * stride + e.qpos] : 0;
                         if (qual >= po.min_bq) {
                             nq = 1;
                             nb = (e.head ? 2 : 0) + 1 + (e.tail ? 1 : 0);
@@ -220,15 +249,14 @@ mplp_column_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ aln
             }
             any |= __any_sync(0xffffffffu, cov);
             if (WRITE && nq) {
-                const qm_aln &a = alns[rec];
-                const bool rev = (a.flag & 0x10) != 0;
-                const int L = lens[rec];
-                const uint8_t *rd = codes + (int64_t)rec * stride;
+                const bool rev = (si.flags & 1) != 0;
+                const int L = si.len;
+                const uint8_t *rd = codes + (int64_t)si.rec * stride;
                 auto seq_base = [&](int i) { if (i >= L) return 4; const int c = rev ? rd[L - 1 - i] : rd[i]; return rev ? (c > 3 ? 4 : 3 - c) : c; };
                 const char *let = rev ? "acgtn" : "ACGTN";
                 char *o = out + b_off + tot_b + (sb - nb);
                 int w = 0;
-                if (e.head) { o[w++] = '^'; o[w++] = (char)(a.mapq > 93 ? 126 : a.mapq + 33); }
+                if (e.head) { o[w++] = '^'; o[w++] = (char)(si.mapq > 93 ? 126 : si.mapq + 33); }
                 if (!e.is_del) { const int cc = seq_base(e.qpos); o[w++] = (cc < 4 && cc == refc) ? (rev ? ',' : '.') : let[cc]; }
                 else o[w++] = '*';
                 if (e.indel) {
@@ -285,7 +313,8 @@ int qm_mpileup_text(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, c
     size_t cub_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int64_t *)nullptr, (int64_t *)nullptr, (int)(l_pac + 1), st);
     const size_t o_tq = 0, o_info = o_tq + al((size_t)n * stride), o_keys = o_info + al((size_t)n * sizeof(RecInfo));
-    const size_t o_perm = o_keys + al((size_t)n * 8), o_starts = o_perm + al((size_t)n * 4), o_len = o_starts + al((size_t)n * 4);
+    const size_t o_perm = o_keys + al((size_t)n * 8), o_starts = o_perm + al((size_t)n * 4), o_sinfo = o_starts + al((size_t)n * 4);
+    const size_t o_len = o_sinfo + al((size_t)n * sizeof(SInfo));
     const size_t o_off = o_len + al((size_t)(l_pac + 1) * 8), o_cnt = o_off + al((size_t)(l_pac + 1) * 8), o_names = o_cnt + al((size_t)l_pac * 4);
     const size_t o_misc = o_names + al(all.size() + 1), o_cub = o_misc + 256;
     void *p = nullptr;
@@ -299,6 +328,7 @@ int qm_mpileup_text(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, c
     int32_t *starts = (int32_t *)(b + o_starts), *cnt = (int32_t *)(b + o_cnt);
     int64_t *line_len = (int64_t *)(b + o_len), *line_off = (int64_t *)(b + o_off);
     char *d_names = b + o_names;
+    SInfo *sinfo = (SInfo *)(b + o_sinfo);
     int *max_span = (int *)(b + o_misc);
     QM_CUDA(ctx, cudaMemsetAsync(max_span, 0, 256, st));
     QM_CUDA(ctx, cudaMemsetAsync(line_len + l_pac, 0, 8, st));
@@ -310,8 +340,8 @@ int qm_mpileup_text(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, c
     if (rc) return rc;
     rc = qm_sort_pairs(ctx, keys, perm, n, key_bits, stream);
     if (rc) return rc;
-    mplp_starts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(perm, d_alns, V, n, starts);
-    mplp_column_kernel<false><<<blocks, kWarps * 32, 0, st>>>(V, *po, d_alns, d_codes, tq, stride, d_lens, info, perm, starts, n, max_span, d_names, NT,
+    mplp_starts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(perm, d_alns, info, d_lens, V, n, starts, sinfo);
+    mplp_column_kernel<false><<<blocks, kWarps * 32, 0, st>>>(V, *po, d_alns, d_codes, tq, stride, sinfo, starts, n, max_span, d_names, NT,
                                                              line_len, cnt, nullptr, nullptr);
     QM_CUDA(ctx, cub::DeviceScan::ExclusiveSum(b + o_cub, cub_bytes, line_len, line_off, (int)(l_pac + 1), st));
     int64_t total = 0;
@@ -321,7 +351,7 @@ int qm_mpileup_text(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, c
     rc = qm_scratch_reserve(ctx, 17, (size_t)total + 256, &tp);
     ctx->text_bytes = total;
     if (rc) return rc;
-    mplp_column_kernel<true><<<blocks, kWarps * 32, 0, st>>>(V, *po, d_alns, d_codes, tq, stride, d_lens, info, perm, starts, n, max_span, d_names, NT,
+    mplp_column_kernel<true><<<blocks, kWarps * 32, 0, st>>>(V, *po, d_alns, d_codes, tq, stride, sinfo, starts, n, max_span, d_names, NT,
                                                             line_len, cnt, line_off, (char *)tp);
     QM_CUDA(ctx, cudaGetLastError());
     QM_CUDA(ctx, cudaStreamSynchronize(st));
