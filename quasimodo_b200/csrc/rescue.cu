@@ -11,6 +11,7 @@
 // s - l, and the row's state at the strip boundary (H, F, running row maximum and its first column) moves to lane
 // l + 1 by shuffle; lane 31 closes a row: best score / first row / first column, the log of rows above min score
 // that gives the sub-optimal score, the early stop of the reversed pass.  Target window and query sit in shared memory.
+#include <stdlib.h>
 #include "pipeline.cuh"
 
 namespace {
@@ -395,7 +396,8 @@ int qm_mate_rescue(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     // The up-front task list holds 4 tasks per pair of the batch (a pair can have 32 anchors x 4 orientations, a batch in
     // which few pairs need rescue -- every realistic one -- uses a small part of it); a pair whose block does not fit is
     // not run up front, the apply pass then aligns for it as it goes.
-    const size_t cap_tasks = (size_t)n_pairs * 4 + 1024;
+    // QM_RESCUE_INLINE=1 (test knob): an empty list, every alignment is run by the apply pass as it goes
+    const size_t cap_tasks = getenv("QM_RESCUE_INLINE") ? 0 : (size_t)n_pairs * 4 + 1024;
     const size_t o_list = 256, o_blk = (o_list + (size_t)n_pairs * sizeof(int) + 255) & ~(size_t)255;
     const size_t o_task = (o_blk + (size_t)n_pairs * sizeof(int2) + 255) & ~(size_t)255;
     const size_t o_res = (o_task + cap_tasks * sizeof(ResTask) + 255) & ~(size_t)255;

@@ -152,3 +152,17 @@ def test_pileup_start_channel_counts_admitted_reads(ctx):
     a = o["alns"]
     admitted = ((a["flag"] & 4) == 0) & ((a["flag"] & 2) != 0) & (a["n_cigar"] != 0) & (a["n_cigar"] != 255)
     assert int(g["counts"][:, 15].sum()) == int(admitted.sum())
+
+
+def test_mate_rescue_inline_path_is_bit_exact():
+    """QM_RESCUE_INLINE=1 empties the up-front alignment list, so the per-pair pass runs every local alignment itself (the
+    path it otherwise takes only for an alignment that becomes necessary after an earlier hit was removed again)"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("QM_RESCUE_INLINE"):
+        pytest.skip("already inside the QM_RESCUE_INLINE run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_pipeline_gpu.py", "-q", "-x", "-k", "cfg1-3000 or cfg5 or without_mate_rescue"],
+                       cwd=root, env=dict(os.environ, QM_RESCUE_INLINE="1"), capture_output=True, text=True)
+    assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
