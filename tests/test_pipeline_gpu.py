@@ -23,6 +23,8 @@ def _workload(name, n):
         return workloads.config1(n)
     if name == "cfg2":
         return workloads.config2(6, n)
+    if name == "cfg2-rescue-heavy":           # TA-50-1: TB40E reads on AD169, 5.6 % of the pairs go through mate rescue
+        return workloads.config2(1, n)
     if name == "cfg3":
         return workloads.config3(n)
     if name == "cfg4":
@@ -116,7 +118,8 @@ def compare(g, o):
     assert np.array_equal(g["planes"].T, o["counts"])
 
 
-@pytest.mark.parametrize("name,n", [("cfg1", 3000), ("cfg2", 3000), ("cfg4", 3000), ("cfg5", 2000), ("cfg3", 3000)])
+@pytest.mark.parametrize("name,n", [("cfg1", 3000), ("cfg2", 3000), ("cfg4", 3000), ("cfg5", 2000), ("cfg3", 3000),
+                                    ("cfg2-rescue-heavy", 30000), ("cfg5", 12000)])
 def test_pipeline_parity(ctx, name, n):
     W = _workload(name, n)
     g, o = run_both(ctx, W, n)
