@@ -97,7 +97,7 @@ __device__ __forceinline__ ExtState ext_run(const ExtParams &P, const SeqFetch &
             int s = (qc[k] == tb) ? P.a : mis[k];
             if (tN) s = -1;
             const int hk = h[k];
-            const int m = hk + min(s, hk);          // == hk ? hk + s : <=0  (a dead diagonal stays dead)
+            const int m = hk + min(s, hk << 8);     // == hk ? hk + s : <= 0  (a dead diagonal stays dead; scores are < 256)
             M[k] = m;
             en[k] = __viaddmax_s32_relu(e[k], -P.e_del, m - oe_del);
             fin[k] = f;

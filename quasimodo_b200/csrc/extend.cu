@@ -118,7 +118,7 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
         // the pipeline's own tasks (rows of ~45 columns, ~85 rows) its per-row bookkeeping for two tasks eats the gain:
         // measured 1.7x SLOWER per class launch (profiles/r01_v8_paired_vs_scalar.md).  Off unless QM_PAIRED is set.
         static const bool paired = getenv("QM_PAIRED") != nullptr;
-        if (big && c < 8 && d_fb_lists && d_fb_ctr && paired) {
+        if (big && c < 8 && d_fb_lists && d_fb_ctr && paired && P.a == 1) {       // (its packed dead-diagonal rule needs a == 1)
             // two tasks per thread; what the packed arithmetic cannot hold (N in the query, scores above 255) comes back
             // through the fallback list and runs on the scalar thread-per-task kernel right behind it
             const int hc = h_counts ? h_counts[c] : -1;

@@ -161,7 +161,8 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
                 if (BYTES) { const int he = p[O]; hh = he & 0xff; e = he >> 8; }                 \
                 else { hh = p[O]; e = p[PL + (O)]; }                                             \
                 const int s = lut_score(L, p[SEL + (O)]);                                        \
-                const int M = hh + min(s, hh);              /* h ? h + s : <= 0 */               \
+                /* h ? h + s : <= 0 (a dead diagonal stays dead); s <= h whenever h > 0 needs a <= 1 */ \
+                const int M = hh + min(s, SYM ? hh : hh << 8);                                   \
                 const int H = __vimax3_s32(M, e, f);                                             \
                 const int td = M - oe_del;                                                       \
                 const int en = __viaddmax_s32_relu(e, -P.e_del, td);                             \
@@ -268,7 +269,8 @@ void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
         if (need < blocks) blocks = need;
     }
     if (blocks < 1) return;
-    const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins;
+    // SYM = the standard scheme: equal gap costs (one subtraction serves E and F) and match score 1 (see QM_CELL)
+    const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins && P.a == 1;
     if (sym) ext2_kernel<CAP, true, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
     else ext2_kernel<CAP, false, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
 }

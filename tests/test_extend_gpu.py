@@ -18,14 +18,14 @@ def ctx():
     c.close()
 
 
-def oracle_results(pairs, h0s, ws, eb, retry=False, prev_h0=False):
+def oracle_results(pairs, h0s, ws, eb, retry=False, prev_h0=False, opt=None):
     from oracle import qmo_py
     out = []
     for (q, t), h0, w in zip(pairs, h0s, ws):
         cells, prev, res, wu = 0, (int(h0) if prev_h0 else -1), None, int(w)
         for a in range(2 if retry else 1):
             wu = int(w) << a
-            res, c = qmo_py.ksw_extend2(q, t, int(h0), wu, eb)
+            res, c = qmo_py.ksw_extend2(q, t, int(h0), wu, eb, opt=opt)
             cells += c
             if res[0] == prev or res[5] < (wu >> 1) + (wu >> 2):
                 break
@@ -34,11 +34,17 @@ def oracle_results(pairs, h0s, ws, eb, retry=False, prev_h0=False):
     return out
 
 
-def check(ctx, pairs, h0s, ws, eb, flags=0):
+def check(ctx, pairs, h0s, ws, eb, flags=0, scoring=None):
+    from quasimodo_b200 import _lib
     from quasimodo_b200.api import pack_ext_tasks
+    from oracle import qmo_py
+    og, oo = _lib.default_opt(), qmo_py.default_opt()
+    for k, v in (scoring or {}).items():
+        setattr(og, k, v)
+        setattr(oo, k, v)
     seq, tasks = pack_ext_tasks(pairs, h0s, ws, eb, flags)
-    got = ctx.extend_batch_host(seq, tasks)
-    want = oracle_results(pairs, h0s, ws, eb, retry=bool(flags & 1), prev_h0=bool(flags & 2))
+    got = ctx.extend_batch_host(seq, tasks, opt=og)
+    want = oracle_results(pairs, h0s, ws, eb, retry=bool(flags & 1), prev_h0=bool(flags & 2), opt=oo)
     bad = []
     for i, wnt in enumerate(want):
         g = tuple(int(got[i][f]) for f in FIELDS) + (int(got[i]["w_used"]), int(got[i]["cells"]))
@@ -52,6 +58,19 @@ def test_extend_random(ctx, eb):
     rng = np.random.default_rng(1234 + eb)
     pairs, h0s, ws = extgen.random_tasks(rng, 4000)
     check(ctx, pairs, h0s, ws, eb)
+
+
+@pytest.mark.parametrize("scoring", [dict(a=2, b=5), dict(o_del=5, e_del=2, o_ins=7, e_ins=1), dict(a=3, b=4, o_del=4, e_del=3, o_ins=9, e_ins=2),
+                                     dict(a=1, b=1, o_del=1, e_del=1, o_ins=1, e_ins=1)])
+@pytest.mark.parametrize("n", [5000, 40000])
+def test_extend_other_scoring_schemes(ctx, scoring, n):
+    """match scores above 1 and unequal gap costs; 5,000 tasks run on the warp-per-task kernel, 40,000 (more than 4,096 per
+    query-length class) on the thread-per-task kernel.  (A match score of 2 used to break the "dead diagonal" shortcut
+    h + min(s, h) of both kernels: a cell with H = 1 on its diagonal got 1 + 1 instead of 1 + 2.)"""
+    rng = np.random.default_rng(5)
+    pairs, h0s, ws = extgen.random_tasks(rng, n)
+    h0s = rng.integers(1, 250, len(h0s))
+    check(ctx, pairs, h0s, ws, 5, scoring=scoring)
 
 
 def test_extend_adversarial(ctx):

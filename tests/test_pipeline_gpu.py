@@ -34,7 +34,7 @@ def _workload(name, n):
     raise KeyError(name)
 
 
-def run_both(ctx, W, n_pairs, pair0=0, flags=0):
+def run_both(ctx, W, n_pairs, pair0=0, flags=0, scoring=None, all_orientations=False):
     import torch
     from quasimodo_b200 import _lib
     from oracle import qmo_py
@@ -46,13 +46,20 @@ def run_both(ctx, W, n_pairs, pair0=0, flags=0):
     opt_g = _lib.default_opt()
     opt_g.w = W.w
     opt_g.flags = flags
+    for k, v in (scoring or {}).items():
+        setattr(opt_o, k, v)
+        setattr(opt_g, k, v)
     # ---- oracle ----
     ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
     o = qmo_py.align_se(ref, codes, lens, opt=opt_o)
     o_regs_se, o_nr_se = o["regs"].copy(), o["n_regs"].copy()
     o_pes = qmo_py.pestat(ref, o["regs"], o["n_regs"], opt=opt_o)
     o_regs_resc, o_nr_resc = o["regs"].copy(), o["n_regs"].copy()
-    o_resc_stats = qmo_py.mate_rescue(ref, codes, lens, o_regs_resc, o_nr_resc, o_pes, opt=opt_o)
+    resc_pes = o_pes.copy()
+    if all_orientations:            # every orientation gets the FR model: all four window shapes of mem_matesw are searched
+        for d in (0, 2, 3):
+            resc_pes[d] = o_pes[1]
+    o_resc_stats = qmo_py.mate_rescue(ref, codes, lens, o_regs_resc, o_nr_resc, resc_pes, opt=opt_o)
     o_alns = qmo_py.pair_and_finish(ref, codes, lens, o["regs"], o["n_regs"], o_pes, pair_id0=pair0, opt=opt_o)
     o_counts = qmo_py.pileup(ref, o_alns, codes, quals, lens)
     # ---- device ----
@@ -71,7 +78,7 @@ def run_both(ctx, W, n_pairs, pair0=0, flags=0):
     # the rescue stage on its own (on copies: pair_finish below runs it again as part of the paired stage)
     d_regs_resc, d_nr_resc = d_regs.clone(), d_nr.clone()
     d_stats = torch.zeros(2, dtype=torch.int64, device=dev)
-    ctx.mate_rescue(idx, d_codes, d_lens, d_regs_resc, d_nr_resc, g_pes, d_stats=d_stats, opt=opt_g)
+    ctx.mate_rescue(idx, d_codes, d_lens, d_regs_resc, d_nr_resc, resc_pes, d_stats=d_stats, opt=opt_g)
     torch.cuda.synchronize()
     d_alns = ctx.pair_finish(idx, d_codes, d_lens, d_regs, d_nr, g_pes, pair_id0=pair0, opt=opt_g)
     d_counts = torch.zeros(_lib.NCH * idx.l_pac, dtype=torch.int32, device=dev)
@@ -139,6 +146,24 @@ def test_pipeline_without_mate_rescue(ctx):
     g2, _ = run_both(ctx, W, 3000)
     placed = lambda a: int(((a["flag"] & 4) == 0).sum())
     assert placed(g2["alns"]) > placed(g["alns"])
+
+
+def test_mate_rescue_all_four_orientations(ctx):
+    """the standalone rescue stage with a usable insert-size model in every orientation (FF, FR, RF, RR): mate searched as is and
+    reverse-complemented, at the smaller and at the larger coordinate"""
+    W = _workload("cfg1", 2500)
+    g, o = run_both(ctx, W, 2500, all_orientations=True)
+    compare(g, o)
+    base = run_both(ctx, W, 2500)[1]["resc_stats"]
+    assert o["resc_stats"][0] > 2 * base[0]            # the other three orientations really ran
+
+
+def test_pipeline_nondefault_scoring(ctx):
+    """another scoring scheme (a = 2, unequal gap costs) through every stage, mate rescue included"""
+    W = _workload("cfg5", 1500)
+    g, o = run_both(ctx, W, 1500, scoring=dict(a=2, b=5, o_del=5, e_del=2, o_ins=7, e_ins=1, T=50, pen_unpaired=25))
+    compare(g, o)
+    assert o["resc_stats"][0] > 0 and ((o["alns"]["flag"] & 4) == 0).mean() > 0.8
 
 
 def test_pipeline_pair_offset(ctx):
