@@ -34,23 +34,27 @@ def _workload(name, n):
     raise KeyError(name)
 
 
-def run_both(ctx, W, n_pairs, pair0=0, flags=0, scoring=None, all_orientations=False):
+def run_both(ctx, W, n_pairs, pair0=0, flags=0, scoring=None, all_orientations=False, k=31, ragged=False, popt=None):
     import torch
     from quasimodo_b200 import _lib
     from oracle import qmo_py
     codes, quals, _, _ = W.simulate_host(pair0, n_pairs)
     lens = np.full(2 * n_pairs, W.params.read_len, np.int32)
+    if ragged:                      # reads trimmed to 35 .. full length (the tail of the row is padding)
+        lens = np.random.default_rng(11).integers(35, W.params.read_len + 1, 2 * n_pairs).astype(np.int32)
+        for r in range(2 * n_pairs):
+            codes[r, lens[r]:] = 4
     opt_o = qmo_py.default_opt()
     opt_o.w = W.w
     opt_o.flags = flags
     opt_g = _lib.default_opt()
     opt_g.w = W.w
     opt_g.flags = flags
-    for k, v in (scoring or {}).items():
-        setattr(opt_o, k, v)
-        setattr(opt_g, k, v)
+    for name, v in (scoring or {}).items():
+        setattr(opt_o, name, v)
+        setattr(opt_g, name, v)
     # ---- oracle ----
-    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=k)
     o = qmo_py.align_se(ref, codes, lens, opt=opt_o)
     o_regs_se, o_nr_se = o["regs"].copy(), o["n_regs"].copy()
     o_pes = qmo_py.pestat(ref, o["regs"], o["n_regs"], opt=opt_o)
@@ -61,10 +65,16 @@ def run_both(ctx, W, n_pairs, pair0=0, flags=0, scoring=None, all_orientations=F
             resc_pes[d] = o_pes[1]
     o_resc_stats = qmo_py.mate_rescue(ref, codes, lens, o_regs_resc, o_nr_resc, resc_pes, opt=opt_o)
     o_alns = qmo_py.pair_and_finish(ref, codes, lens, o["regs"], o["n_regs"], o_pes, pair_id0=pair0, opt=opt_o)
-    o_counts = qmo_py.pileup(ref, o_alns, codes, quals, lens)
+    po_o = None
+    if popt:
+        po_o = qmo_py.PileupOpt()
+        qmo_py.lib().qmo_pileup_opt_default(__import__("ctypes").byref(po_o))
+        for kk, v in popt.items():
+            setattr(po_o, kk, v)
+    o_counts = qmo_py.pileup(ref, o_alns, codes, quals, lens, popt=po_o)
     # ---- device ----
     dev = torch.device("cuda:0")
-    idx = ctx.index(W.ref, 31)
+    idx = ctx.index(W.ref, k)
     d_codes = torch.from_numpy(codes).to(dev)
     d_quals = torch.from_numpy(quals).to(dev)
     d_lens = torch.from_numpy(lens).to(dev)
@@ -82,7 +92,12 @@ def run_both(ctx, W, n_pairs, pair0=0, flags=0, scoring=None, all_orientations=F
     torch.cuda.synchronize()
     d_alns = ctx.pair_finish(idx, d_codes, d_lens, d_regs, d_nr, g_pes, pair_id0=pair0, opt=opt_g)
     d_counts = torch.zeros(_lib.NCH * idx.l_pac, dtype=torch.int32, device=dev)
-    ctx.pileup_accumulate(idx, d_alns, d_codes, d_quals, d_lens, d_counts)
+    po_g = None
+    if popt:
+        po_g = _lib.default_pileup_opt()
+        for kk, v in popt.items():
+            setattr(po_g, kk, v)
+    ctx.pileup_accumulate(idx, d_alns, d_codes, d_quals, d_lens, d_counts, popt=po_g)
     rows = ctx.counts_to_rows(idx, d_counts)
     torch.cuda.synchronize()
     g = dict(seeds=d_seeds.cpu().numpy().view(_lib.SEED_DTYPE).reshape(-1, _lib.MAX_SEEDS), n_seeds=d_ns.cpu().numpy(),
@@ -164,6 +179,22 @@ def test_pipeline_nondefault_scoring(ctx):
     g, o = run_both(ctx, W, 1500, scoring=dict(a=2, b=5, o_del=5, e_del=2, o_ins=7, e_ins=1, T=50, pen_unpaired=25))
     compare(g, o)
     assert o["resc_stats"][0] > 0 and ((o["alns"]["flag"] & 4) == 0).mean() > 0.8
+
+
+@pytest.mark.parametrize("case", [
+    dict(scoring=dict(w=8, zdrop=20, pen_clip5=0, pen_clip3=9)),          # narrow band (retries), early z-drop, unequal end bonuses
+    dict(scoring=dict(min_seed_len=20), k=20),                            # -k 20: shorter seeds, more of them
+    dict(ragged=True),                                                    # reads of 35 .. 150 bases in one batch
+    dict(scoring=dict(T=60, pen_unpaired=5, mask_level=0.3, drop_ratio=0.7)),
+    dict(popt=dict(min_bq=25, min_mapq=30, count_orphans=1)),
+    dict(popt=dict(ignore_overlaps=1)),
+])
+def test_pipeline_option_variants(ctx, case):
+    """options off their defaults, stage by stage against the oracle"""
+    W = _workload("cfg5" if "scoring" in case and "w" in case["scoring"] else "cfg1", 2000)
+    g, o = run_both(ctx, W, 2000, **case)
+    compare(g, o)
+    assert ((o["alns"]["flag"] & 4) == 0).mean() > 0.6 and o["counts"][:, 14].sum() > 0
 
 
 def test_pipeline_pair_offset(ctx):
