@@ -14,7 +14,7 @@ def ctx():
     c.close()
 
 
-def run(ctx, W, n):
+def run(ctx, W, n, popt=None):
     import torch
     from quasimodo_b200 import _lib
     from oracle import qmo_py
@@ -24,11 +24,19 @@ def run(ctx, W, n):
     ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
     alns, _, _, _ = qmo_py.run_sample(ref, codes, quals, lens, opt=opt_o)
     names = [f"contig{i}" for i in range(len(W.ref.lens))]
-    o_text = qmo_py.mpileup_text(ref, alns, codes, quals, lens, names)
+    po_o = po_g = None
+    if popt:
+        import ctypes
+        po_o, po_g = qmo_py.PileupOpt(), _lib.default_pileup_opt()
+        qmo_py.lib().qmo_pileup_opt_default(ctypes.byref(po_o))
+        for k, v in popt.items():
+            setattr(po_o, k, v)
+            setattr(po_g, k, v)
+    o_text = qmo_py.mpileup_text(ref, alns, codes, quals, lens, names, popt=po_o)
     dev = torch.device("cuda:0")
     idx = ctx.index(W.ref, 31)
     g_text = ctx.mpileup_text(idx, torch.from_numpy(alns.view(np.uint8).reshape(-1)).to(dev), torch.from_numpy(codes).to(dev),
-                              torch.from_numpy(quals).to(dev), torch.from_numpy(lens).to(dev), names)
+                              torch.from_numpy(quals).to(dev), torch.from_numpy(lens).to(dev), names, popt=po_g)
     idx.close()
     return g_text, o_text, alns
 
@@ -44,6 +52,14 @@ def test_text_pileup_equals_oracle(ctx, name, n):
         bad = [i for i in range(len(ol)) if gl[i] != ol[i]]
         assert not bad, (len(bad), gl[bad[0]][:200], ol[bad[0]][:200])
     assert g == o
+
+
+@pytest.mark.parametrize("popt", [dict(min_bq=25, min_mapq=20), dict(count_orphans=1, ignore_overlaps=1), dict(min_bq=0)])
+def test_text_pileup_options(ctx, popt):
+    """-Q / -q / -A / -x off their defaults"""
+    from tests.test_pipeline_gpu import _workload
+    g, o, _ = run(ctx, _workload("cfg5", 1500), 1500, popt=popt)
+    assert len(o) > 100000 and g == o
 
 
 def test_text_pileup_format(ctx):

@@ -197,6 +197,17 @@ def test_pipeline_option_variants(ctx, case):
     assert ((o["alns"]["flag"] & 4) == 0).mean() > 0.6 and o["counts"][:, 14].sum() > 0
 
 
+def test_pipeline_long_reads(ctx):
+    """2 x 400 bp: the widest classes of every kernel (extension queries up to 369, rescue with 16 columns per lane, long
+    CIGAR tasks, pileup rows of 400 bases)"""
+    from quasimodo_b200 import workloads
+    W = workloads.Workload("long", [("Merlin", 10), ("TB40E", 3)], ["Merlin"], 800, 77, read_len=400, w=200, indel_ppm=300,
+                           ins_mean=900, ins_sd=80, ins_max=1600)
+    g, o = run_both(ctx, W, 800)
+    compare(g, o)
+    assert o["resc_stats"][0] > 0 and ((o["alns"]["flag"] & 4) == 0).mean() > 0.8
+
+
 def test_pipeline_pair_offset(ctx):
     """a shard starting at pair 5000 gives the records the full run gives for those pairs (index-addressable input)"""
     W = _workload("cfg1", 8000)
