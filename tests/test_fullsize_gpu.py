@@ -149,3 +149,39 @@ def test_full_size_sort_is_stable_and_ordered(ctx, full):
     alns = full["d_alns"].cpu().numpy().view(_lib.ALN_DTYPE)
     sk = sort_py.samtools_keys(alns)[d_perm.cpu().numpy().view(np.uint32)]
     assert (sk[1:] >= sk[:-1]).all()
+
+
+def test_call_larger_than_one_internal_chunk(ctx, full):
+    """2.3 M pairs in ONE call (the library walks it in chunks of 2^21 pairs, seeding in batches of 4 M reads) equals the sum of
+    two calls split at an odd boundary, records included"""
+    import torch
+    from quasimodo_b200 import _lib
+    n = 2_300_000
+    W, idx = full["W"], full["idx"]
+    dev = torch.device("cuda:0")
+    g = torch.from_numpy(W.src_codes).to(dev)
+    c = torch.empty((2 * n, 150), dtype=torch.uint8, device=dev)
+    q = torch.empty_like(c)
+    ctx.simulate_pairs(W, 0, n, g, c, q, 0)
+    lens = torch.full((2 * n,), 150, dtype=torch.int32, device=dev)
+    whole_alns = torch.zeros(2 * n * 128, dtype=torch.uint8, device=dev)
+    s = ctx.sample(idx)
+    s.add_pairs(c, q, lens, d_alns=whole_alns)
+    whole = s.counts_host()
+    assert s.stats()[0] == n
+    s.close()
+    cut = 1_000_003
+    npre = _lib.PESTAT_PAIRS
+    total = np.zeros_like(whole)
+    parts = []
+    for lo, hi in ((0, cut), (cut, n)):
+        s = ctx.sample(idx)
+        if lo:
+            s.estimate_pestat(c[:2 * npre], lens[:2 * npre])
+        d_alns = torch.zeros(2 * (hi - lo) * 128, dtype=torch.uint8, device=dev)
+        s.add_pairs(c[2 * lo:2 * hi], q[2 * lo:2 * hi], lens[2 * lo:2 * hi], pair_id0=lo, d_alns=d_alns)
+        total += s.counts_host()
+        parts.append(d_alns)
+        s.close()
+    assert np.array_equal(total, whole)
+    assert torch.equal(torch.cat(parts), whole_alns)
