@@ -40,8 +40,9 @@ def run_both(ctx, W, n_pairs, pair0=0, flags=0, scoring=None, all_orientations=F
     from oracle import qmo_py
     codes, quals, _, _ = W.simulate_host(pair0, n_pairs)
     lens = np.full(2 * n_pairs, W.params.read_len, np.int32)
-    if ragged:                      # reads trimmed to 35 .. full length (the tail of the row is padding)
+    if ragged:                      # reads trimmed to 35 .. full length (the tail of the row is padding); a few degenerate ones
         lens = np.random.default_rng(11).integers(35, W.params.read_len + 1, 2 * n_pairs).astype(np.int32)
+        lens[[5, 18, 40, 77, 100, 101]] = [0, 1, 20, 30, 31, 32]
         for r in range(2 * n_pairs):
             codes[r, lens[r]:] = 4
     opt_o = qmo_py.default_opt()
@@ -195,6 +196,15 @@ def test_pipeline_option_variants(ctx, case):
     g, o = run_both(ctx, W, 2000, **case)
     compare(g, o)
     assert ((o["alns"]["flag"] & 4) == 0).mean() > 0.6 and o["counts"][:, 14].sum() > 0
+
+
+def test_pipeline_reads_full_of_n(ctx):
+    """3 % of the bases are N (30x the simulator's default): N handling of seeding, extension, rescue, CIGAR and pileup"""
+    W = _workload("cfg1", 2500)
+    W.params.n_ppm = 30000
+    g, o = run_both(ctx, W, 2500)
+    compare(g, o)
+    assert 0.3 < ((o["alns"]["flag"] & 4) == 0).mean() and o["resc_stats"][0] > 100
 
 
 def test_pipeline_long_reads(ctx):
