@@ -69,9 +69,9 @@ def test_driver_rmdup_bam(deep, tmp_path):
     drvutil.write_fasta(W.ref, fa)
     names = drvutil.pair_names("d", deep["n"])
     drvutil.write_fastq(deep["codes"], deep["quals"], deep["lens"], names, r1, r2)
-    bam, rbam, tsv, met = (str(tmp_path / x) for x in ("s.bam", "s.rmdup.bam", "s.tsv", "s.metrics.txt"))
+    bam, rbam, tsv, met, txt = (str(tmp_path / x) for x in ("s.bam", "s.rmdup.bam", "s.tsv", "s.metrics.txt", "s.mpileup"))
     p = drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--rmdup", 1, "--bam", bam, "--rmdup-bam", rbam, "--counts", tsv,
-                            "--metrics", met, "--sample", "phix-deep"])
+                            "--metrics", met, "--sample", "phix-deep", "--mpileup", txt])
     n_dup = int(deep["dup"].sum())
     assert f"rmdup: {n_dup} of {deep['n']} pairs are duplicates" in p.stderr
     full, kept = bamio.Bam(bam), bamio.Bam(rbam)
@@ -84,3 +84,8 @@ def test_driver_rmdup_bam(deep, tmp_path):
     assert open(met).read().splitlines()[-1].split("\t")[1:3] == [str(deep["n"]), str(n_dup)]
     refs, _ = bamio.read_bai(rbam + ".bai")
     assert len(refs) == 1
+    # the text pileup is the one of the duplicate-free records (depth ~1700: lines of several kilobytes)
+    from oracle import qmo_py
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    want = qmo_py.mpileup_text(ref, deep["marked"], deep["codes"], deep["quals"], deep["lens"], list(W.ref.names))
+    assert open(txt, "rb").read() == want and len(want) > 10_000_000
