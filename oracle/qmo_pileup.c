@@ -245,9 +245,12 @@ int64_t qmo_mpileup_text(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t
                 if (!covered[g]) continue;
                 while (*nm) dput(&o, *nm++);
                 dput(&o, '\t'); dnum(&o, (int)(c + 1)); dput(&o, '\t'); dput(&o, up[R->fwd[g]]); dput(&o, '\t'); dnum(&o, qs[g].n); dput(&o, '\t');
+                /* samtools 1.9 bam_plcmd.c: a column whose reads all failed -Q prints "*" for both strings */
                 for (i = 0; i < bs[g].n; ++i) dput(&o, bs[g].s[i]);
+                if (qs[g].n == 0) dput(&o, '*');
                 dput(&o, '\t');
                 for (i = 0; i < qs[g].n; ++i) dput(&o, qs[g].s[i]);
+                if (qs[g].n == 0) dput(&o, '*');
                 dput(&o, '\n');
             }
         *out = o.s; total = o.n;

@@ -16,7 +16,9 @@ constexpr uint64_t kNoKey = ~0ull;
 constexpr int kCoordBias = 4096;                 // unclipped coordinates can be negative (clipped bases before the contig)
 
 // {contig, unclipped 5' coordinate} of a placed record as a 30-bit code, and its strand
-__device__ __forceinline__ uint32_t end_code(const qm_aln &a, int *rev)
+// (26 bits of coordinate, 4 of contig: a contig of >= 2^26 - 4096 bases or a 17th contig does not fit; *bad is raised then
+// and qm_mark_duplicates fails with QM_ELIMIT instead of letting keys collide)
+__device__ __forceinline__ uint32_t end_code(const qm_aln &a, int *rev, int *bad)
 {
     const bool r = (a.flag & 0x10) != 0;
     int lead = 0, trail = 0, rlen = 0;
@@ -29,6 +31,7 @@ __device__ __forceinline__ uint32_t end_code(const qm_aln &a, int *rev)
     if (nc > 1 && (a.cigar[nc - 1] & 0xf) == 4) trail = (int)(a.cigar[nc - 1] >> 4);
     const int coord = r ? a.pos + rlen - 1 + trail : a.pos - lead;
     *rev = r ? 1 : 0;
+    if (coord + kCoordBias < 0 || coord + kCoordBias >= (1 << 26) || a.rid >= 16) *bad = 1;
     return ((uint32_t)a.rid << 26) | (uint32_t)(coord + kCoordBias);
 }
 
@@ -37,7 +40,8 @@ __device__ __forceinline__ bool placed(const qm_aln &a) { return !(a.flag & 0x4)
 // key, score and (for fully placed pairs) the two end keys of every pair
 __global__ void __launch_bounds__(128)
 dup_keys_kernel(const qm_aln *__restrict__ alns, const uint8_t *__restrict__ quals, int stride, const int32_t *__restrict__ lens,
-                int64_t n_pairs, int64_t pair0, uint64_t *__restrict__ keys, int32_t *__restrict__ scores, uint64_t *__restrict__ ends)
+                int64_t n_pairs, int64_t pair0, uint64_t *__restrict__ keys, int32_t *__restrict__ scores, uint64_t *__restrict__ ends,
+                unsigned long long *__restrict__ n_bad)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
@@ -52,20 +56,21 @@ dup_keys_kernel(const qm_aln *__restrict__ alns, const uint8_t *__restrict__ qua
         sc[e] = s;
     }
     uint64_t key = kNoKey, e0 = kNoKey, e1 = kNoKey;
-    int score = 0;
+    int score = 0, bad = 0;
     if (pa && pb) {
         int ra, rb;
-        uint32_t ca = end_code(a, &ra), cb = end_code(b, &rb);
+        uint32_t ca = end_code(a, &ra, &bad), cb = end_code(b, &rb, &bad);
         if (cb < ca || (cb == ca && rb < ra)) { const uint32_t t = ca; ca = cb; cb = t; const int u = ra; ra = rb; rb = u; }
         key = ((uint64_t)ca << 32) | ((uint64_t)cb << 2) | (uint64_t)(ra << 1 | rb);
         e0 = (uint64_t)ca << 1 | (uint64_t)ra; e1 = (uint64_t)cb << 1 | (uint64_t)rb;
         score = sc[0] + sc[1];
     } else if (pa || pb) {
         int r;
-        const uint32_t c = end_code(pa ? a : b, &r);
+        const uint32_t c = end_code(pa ? a : b, &r, &bad);
         key = (1ull << 63) | ((uint64_t)c << 1) | (uint64_t)r;
         score = pa ? sc[0] : sc[1];
     }
+    if (bad) atomicAdd(n_bad, 1ull);
     keys[pair0 + i] = key;
     scores[pair0 + i] = score;
     ends[2 * (pair0 + i)] = e0; ends[2 * (pair0 + i) + 1] = e1;
@@ -137,11 +142,11 @@ int qm_mark_duplicates(qm_ctx *ctx, int n_chunks, qm_aln *const *d_alns, const u
     uint8_t *dup = (uint8_t *)(b + o_dup);
     unsigned long long *cnt = (unsigned long long *)(b + o_cnt);
     QM_CUDA(ctx, cudaMemsetAsync(dup, 0, (size_t)N, st));
-    QM_CUDA(ctx, cudaMemsetAsync(cnt, 0, 8, st));
+    QM_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16, st));             // cnt[0] = duplicates, cnt[1] = pairs whose end code does not fit
     int64_t p0 = 0;
     for (int c = 0; c < n_chunks; ++c) {
         if (n_pairs[c]) dup_keys_kernel<<<(unsigned)((n_pairs[c] + 127) / 128), 128, 0, st>>>(d_alns[c], d_quals[c], strides[c], d_lens[c], n_pairs[c], p0,
-                                                                                        keys, scores, ends);
+                                                                                        keys, scores, ends, cnt + 1);
         p0 += n_pairs[c];
     }
     rc = qm_sort_pairs(ctx, keys, perm, N, 64, st);
@@ -155,10 +160,11 @@ int qm_mark_duplicates(qm_ctx *ctx, int n_chunks, qm_aln *const *d_alns, const u
         p0 += n_pairs[c];
     }
     QM_CUDA(ctx, cudaGetLastError());
-    unsigned long long h = 0;
-    QM_CUDA(ctx, cudaMemcpyAsync(&h, cnt, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[2] = {0, 0};
+    QM_CUDA(ctx, cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, st));
     QM_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h_n_dup) *h_n_dup = (int64_t)h;
+    if (h[1]) return qm_fail(ctx, QM_ELIMIT, "qm_mark_duplicates: %llu pairs lie beyond what the 30-bit end code holds (contigs of up to 2^26 - 4096 bases, 16 contigs)", h[1]);
+    if (h_n_dup) *h_n_dup = (int64_t)h[0];
     return QM_OK;
 }
 

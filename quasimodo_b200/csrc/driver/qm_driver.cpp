@@ -430,7 +430,7 @@ void encode_record(const Genome &g, const RecRef &rr, std::vector<uint8_t> &out,
     out.insert(out.end(), (const uint8_t *)name, (const uint8_t *)name + l_name);
     for (int k = 0; k < n_cig; ++k) put32(out, a.cigar[k]);
     // SEQ / QUAL as SAM stores them: reverse-complemented / reversed for reverse-strand records
-    const bool rev = (a.flag & 0x10) != 0 && mapped;
+    const bool rev = (a.flag & 0x10) != 0;            // bwa mem_aln2sam: an unmapped read placed at its reverse-strand mate carries 0x10 and is stored reverse-complemented too
     static const uint8_t nib[5] = {1, 2, 4, 8, 15};
     std::vector<uint8_t> seq((size_t)l_seq);
     for (int j = 0; j < l_seq; ++j) {

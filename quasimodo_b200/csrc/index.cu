@@ -12,8 +12,8 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
 {
     if (!ctx || !out) return QM_EINVAL;
     *out = nullptr;
-    if (!h_codes || !h_lens || n_contigs <= 0 || n_contigs > QM_MAX_CONTIGS || k < 8 || k > 32)
-        return qm_fail(ctx, QM_EINVAL, "qm_index_build: need 1..%d contigs and 8 <= k <= 32", QM_MAX_CONTIGS);
+    if (!h_codes || !h_lens || n_contigs <= 0 || n_contigs > QM_MAX_CONTIGS || k < 8 || k > 31)
+        return qm_fail(ctx, QM_EINVAL, "qm_index_build: need 1..%d contigs and 8 <= k <= 31 (the all-ones key marks an empty slot, which at k = 32 is the all-T k-mer)", QM_MAX_CONTIGS);
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     qm_index *ix = new qm_index();
     IndexView &v = ix->v;

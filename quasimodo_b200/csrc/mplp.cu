@@ -213,6 +213,10 @@ mplp_column_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ aln
             }
             b_off = line_off[g] + hdr;
             q_off = line_off[g] + line_len[g] - 1 - cnt;      // the quality string ends right before the newline
+            if (cnt == 0) {                                   // covered, but every base failed -Q: samtools prints "*" for both strings
+                if (lane == 0) { o[hdr] = '*'; o[hdr + 1] = '\t'; o[hdr + 2] = '*'; o[hdr + 3] = '\n'; }
+                continue;
+            }
             if (lane == 0) { out[q_off - 1] = '\t'; out[line_off[g] + line_len[g] - 1] = '\n'; }
         }
         int tot_b = 0, tot_q = 0, any = 0;
@@ -277,6 +281,7 @@ mplp_column_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ aln
             if (any) {
                 const int name_len = NT.off[rid + 1] - NT.off[rid];
                 len = name_len + 1 + n_digits(p + 1) + 1 + 1 + 1 + n_digits(tot_q) + 1 + tot_b + 1 + tot_q + 1;
+                if (tot_q == 0) len += 2;                     // "*" for the empty base string and the empty quality string
             }
             line_len[g] = len;
             n_entries[g] = tot_q;

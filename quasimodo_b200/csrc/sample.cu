@@ -39,6 +39,7 @@ struct qm_sample {
     // duplicate removal (qm_sample_set_rmdup): every chunk's reads and records stay on the device, counting waits for
     // qm_sample_rmdup_finish
     bool rmdup = false;
+    bool rmdup_finished = false;                  // qm_sample_rmdup_finish has run: no more pairs, no second finish until a reset
     struct Kept { uint8_t *codes, *quals; int32_t *lens; qm_aln *alns; int64_t n; int32_t stride; };
     std::vector<Kept> kept;
 };
@@ -51,6 +52,8 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
                  int64_t n, int64_t pair_id0, qm_aln *d_alns_out, cudaStream_t st, cudaEvent_t quals_ready = nullptr)
 {
     qm_ctx *ctx = s->ctx;
+    if (s->rmdup && s->rmdup_finished)
+        return qm_fail(ctx, QM_EINVAL, "pairs added after qm_sample_rmdup_finish: reset the sample first");
     int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, s->d_cells, st);
     if (rc) return rc;
     if (!s->have_pes) {
@@ -151,7 +154,7 @@ int qm_sample_reset(qm_sample *s, void *stream)
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     QM_CUDA(ctx, cudaMemsetAsync(s->d_counts, 0, (size_t)QM_NCH * s->idx->v.l_pac * sizeof(int32_t), (cudaStream_t)stream));
     QM_CUDA(ctx, cudaMemsetAsync(s->d_cells, 0, 8, (cudaStream_t)stream));
-    s->have_pes = false; s->n_pairs = 0;
+    s->have_pes = false; s->n_pairs = 0; s->rmdup_finished = false;
     if (!s->kept.empty()) { QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream)); free_kept(s); }
     return QM_OK;
 }
@@ -171,6 +174,7 @@ int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
     if (!s) return QM_EINVAL;
     qm_ctx *ctx = s->ctx;
     if (!s->rmdup) return qm_fail(ctx, QM_EINVAL, "qm_sample_rmdup_finish: the sample is not in rmdup mode");
+    if (s->rmdup_finished) return qm_fail(ctx, QM_EINVAL, "qm_sample_rmdup_finish: already finished; reset the sample first");
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     QM_CUDA(ctx, cudaDeviceSynchronize());                 // chunks may have been added on any stream
     const int nc = (int)s->kept.size();
@@ -189,6 +193,7 @@ int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
     }
     QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     for (auto &k : s->kept) { cudaFree(k.codes); cudaFree(k.quals); cudaFree(k.lens); k.codes = k.quals = nullptr; k.lens = nullptr; }
+    s->rmdup_finished = true;
     return QM_OK;
 }
 

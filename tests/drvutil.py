@@ -60,6 +60,7 @@ def check_bam_records(case):
     bam, alns, perm = case["bam"], case["alns"], case["perm"]
     n_pairs = len(alns) // 2
     n_md = 0
+    n_unmapped_rev = 0
     for rec, gi in zip(bam.records, perm):
         a = alns[gi]
         assert rec["name"] == case["names"][gi // 2]
@@ -70,8 +71,9 @@ def check_bam_records(case):
         assert rec["cigar"] == [int(x) for x in a["cigar"][:n_cig]]
         L = case["lens"][gi]
         c, q = case["codes"][gi, :L], case["quals"][gi, :L]
-        if mapped and a["flag"] & 0x10:
+        if a["flag"] & 0x10:       # flag alone, as every BAM -> FASTQ extractor does (an unmapped read placed at its reverse mate too)
             c, q = revcomp_codes(c), q[::-1]
+            n_unmapped_rev += not mapped
         assert rec["seq"] == "".join("ACGTN"[x] for x in c)
         assert np.array_equal(rec["qual"], q)
         rlen = sum(x >> 4 for x in rec["cigar"] if (x & 15) in (0, 2))

@@ -53,6 +53,16 @@ def test_rmdup_matches_oracle(ctx, deep):
         assert np.array_equal(got[f], deep["alns"][f]), f
     assert np.array_equal(s.counts_host(), deep["counts"])
     assert deep["counts"][:, 14].sum() < deep["counts_all"][:, 14].sum()
+    # a finished sample takes neither a second finish nor more pairs until it is reset (its kept chunks are gone)
+    from quasimodo_b200 import QmError
+    with pytest.raises(QmError):
+        s.rmdup_finish()
+    with pytest.raises(QmError):
+        s.add_pairs_host(deep["codes"][:4], deep["quals"][:4], deep["lens"][:4])
+    assert np.array_equal(s.counts_host(), deep["counts"])
+    s.reset()
+    s.add_pairs_host(deep["codes"][:half], deep["quals"][:half], deep["lens"][:half])
+    assert s.rmdup_finish() >= 0
     s.close()
     # without rmdup the same sample counts everything
     s = ctx.sample(idx)

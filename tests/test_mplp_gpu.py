@@ -60,6 +60,9 @@ def test_text_pileup_options(ctx, popt):
     from tests.test_pipeline_gpu import _workload
     g, o, _ = run(ctx, _workload("cfg5", 1500), 1500, popt=popt)
     assert len(o) > 100000 and g == o
+    if popt.get("min_bq") == 25:
+        # columns whose every base fails -Q: depth 0 and "*" for both strings (samtools 1.9 bam_plcmd.c), never empty fields
+        assert b"\t0\t*\t*\n" in g and b"\t\t" not in g
 
 
 def test_text_pileup_format(ctx):
