@@ -2,19 +2,26 @@
 """bench.py -- read pairs/s aligned + piled up (+ called + classified) on B200, BASELINE.json's metric.
 
 A STEP is one pass of the whole read-level hot path over one sample's batch of synthetic read pairs:
-seeding/chaining -> ksw_extend2 rounds -> pairing + CIGAR -> pileup counts -> (N>1: NCCL all-reduce of the
+seeding/chaining -> ksw_extend2 rounds -> mate rescue -> pairing + CIGAR -> pileup counts -> (N>1: all-reduce of the
 int32 count tensor) -> SNP calls -> TP/FP/FN match against the strain-difference truth set.
 
-Workload (config.workload): BASELINE.json configs[1], the 10-sample TB40E:AD169 abundance-ratio series,
-2,000,000 synthetic 2x150 bp pairs per sample per GPU; step i runs sample i % 10.  With N GPUs each rank
-takes pairs [r*P, (r+1)*P) of an N*P-pair sample (weak scaling), counts are merged with one all-reduce.
+Workloads (--config, BASELINE.json `configs`; the default is configs[1], the one the metric is quoted on):
+  1  TM-1-1, 100,000 2x150 bp pairs vs Merlin (the reference's own CPU-runnable case); steps rotate over 16 windows
+  2  10-sample TA-* abundance-ratio series, 2,000,000 2x150 bp pairs each; step i runs sample i % 10        [default]
+  3  AD169:Merlin 1:10 + 5 % PhiX + 5 % E. coli, 1,000,000 pairs vs the concatenated Merlin|PhiX|E. coli index
+  4  TM-1-50, 50,000,000 pairs (about 61,000x), STRONG scaling: the sample is split over the N GPUs
+  5  Merlin:TB40E:AD169 10:3:1, 2,000,000 2x250 bp pairs with simulated indels, band w = 200
+With N GPUs each rank takes a contiguous range of the sample's pairs (configs 1, 2, 3, 5: N x the pairs, weak scaling;
+config 4: the same 50 M pairs, strong scaling); the insert-size model comes from the sample's first 65,536 pairs on
+every rank, the counts are merged with one all-reduce.
 
   value : whole-job pairs/s with the reads already resident in HBM (timed with CUDA events, max over ranks)
   e2e   : the same through the host-buffer C-ABI call (qm_sample_add_pairs_host): pinned host reads -> H2D ->
           pipeline -> calls D2H, all inside the timed region
   roofline / stages : per-stage CUDA-event times measured live by the library's stage timers (same run)
   cpu_baseline : the oracle port (oracle/, CPU restatement of bwa-mem extension + bcftools counting, OpenMP on
-          all host cores) on a bounded sample of the same workload -- a reported baseline, not the target
+          all host cores, built -O3 -march=native on the host it runs on) on a bounded sample of the same workload
+          -- a reported baseline, not the target
   --impl reference : that CPU path as its own arm (the upstream binaries are not in the image: kind "port")
 """
 import argparse
@@ -31,8 +38,9 @@ if ROOT not in sys.path:
 
 METRIC = "read_pairs_per_s_aligned_piledup"
 UNIT = "pairs/s"
-N_SAMPLES = 10
-ALGO_BYTES_PER_PAIR_PILEUP = 424          # 2 x (38 + 150 + 16 + 8)
+CHUNK = 2_000_000                          # pairs handed to the library per call (bounds its per-chunk scratch)
+CPU_NOTE = ("bwa/samtools/bcftools are not in the image and not vendored: the CPU arm is the repo's C restatement "
+            "(oracle/, scalar C, OpenMP over reads), not the upstream binaries")
 
 
 def parse():
@@ -41,19 +49,50 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=2_000_000, help="pairs per sample per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[N-1]")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (config 4: in the whole sample); 0 = the config's own size")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def config_dict(args, n_gpus):
-    return {"workload": "cfg2: 10-sample TA-* abundance-ratio series (TB40E:AD169 1:0 ... 0:1), synthetic 2x150 bp pairs, "
-                        "step i = sample i%10, reference AD169 (TB40E for TA-1-0)",
-            "pairs_per_step_per_gpu": args.pairs, "read_len": 150, "global_pairs_per_step": args.pairs * n_gpus,
-            "parallelism": f"reads sharded over {n_gpus} GPU(s), int32 count tensor all-reduced" if n_gpus > 1 else "1 GPU",
-            "l2_policy": "inputs larger than L2: 1.2 GB of reads per step vs 126 MB L2; every step runs another sample"}
+class Plan:
+    """what one step of a config is: which workload window, how many pairs per rank, read length, band, truth set"""
+
+    def __init__(self, args, world):
+        from quasimodo_b200 import workloads
+        c = args.config
+        self.cfg, self.world = c, world
+        self.strong = c == 4
+        own = {1: 100_000, 2: 2_000_000, 3: 1_000_000, 4: 50_000_000, 5: 2_000_000}[c]
+        size = args.pairs or own
+        self.total = size if self.strong else size * world          # pairs of one sample (all ranks together)
+        self.L = 250 if c == 5 else 150
+        self.w = 200 if c == 5 else 100
+        self.truth = {1: "TM", 2: "TA", 4: "TM"}.get(c)
+        self.n_inputs = {1: 16, 2: 10}.get(c, 1)                    # distinct step inputs the steps rotate over
+        mk = {1: lambda i: workloads.config1(self.total * 16), 2: lambda i: workloads.config2(i, self.total),
+              3: lambda i: workloads.config3(self.total), 4: lambda i: workloads.config4(self.total),
+              5: lambda i: workloads.config5(self.total)}[c]
+        self.make = mk
+        self.names = {1: "cfg1: TM-1-1 (TB40E:Merlin 1:1) vs Merlin, 2x150 bp; steps rotate over 16 windows of the pair stream",
+                      2: "cfg2: 10-sample TA-* abundance-ratio series (TB40E:AD169 1:0 ... 0:1), synthetic 2x150 bp pairs, "
+                         "step i = sample i%10, reference AD169 (TB40E for TA-1-0)",
+                      3: "cfg3: AD169:Merlin 1:10 + 5% PhiX + 5% E. coli pairs vs the concatenated Merlin|PhiX|E. coli index (4.89 Mb), 2x150 bp",
+                      4: "cfg4: TM-1-50 deep sample (TB40E:Merlin 1:50) vs Merlin, 2x150 bp, the sample split over the GPUs",
+                      5: "cfg5: Merlin:TB40E:AD169 10:3:1 vs Merlin, 2x250 bp with simulated indels, band w=200"}
+
+    def window(self, i):
+        """first pair (in the simulator's index space) of step input i"""
+        return (i % 16) * self.total if self.cfg == 1 else 0
+
+    def config_dict(self, n_gpus, per_rank):
+        return {"workload": self.names[self.cfg], "baseline_config": self.cfg,
+                "pairs_per_step_per_gpu": per_rank, "read_len": self.L, "band_w": self.w, "global_pairs_per_step": self.total,
+                "parallelism": (f"reads sharded over {n_gpus} GPU(s), int32 count tensor all-reduced" if n_gpus > 1 else "1 GPU"),
+                "l2_policy": f"inputs larger than L2: the steps rotate over {self.n_inputs} input(s) of "
+                             f"{per_rank * 4 * self.L / 1e6:.0f} MB (bases + qualities) each vs 126 MB of L2"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -105,21 +144,31 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_arm(args, steps, warmup, sample_pairs):
-    """the oracle port on host cores; each step = `sample_pairs` pairs of sample i % 10.  -> (pairs/s, ms/step)"""
+def cpu_setup():
+    """the CPU arms use every host core (torchrun exports OMP_NUM_THREADS=1) and a build tuned for this host"""
+    from oracle import qmo_py
+    qmo_py.build()
+    qmo_py.use_native_build()
+    qmo_py.set_threads(os.cpu_count() or 1)
+    return qmo_py
+
+
+def cpu_arm(plan, steps, warmup, sample_pairs):
+    """the oracle port on host cores; each step = the first `sample_pairs` pairs of step input i.  -> (pairs/s, ms/step)"""
     import numpy as np
-    from quasimodo_b200 import workloads
     from oracle import qmo_py
     refs, times = {}, []
+    opt = qmo_py.default_opt()
+    opt.w = plan.w
     for i in range(warmup + steps):
-        W = workloads.config2(i % N_SAMPLES, sample_pairs)
-        key = W.ref_stems[0]
+        W = plan.make(i % plan.n_inputs)
+        key = "|".join(W.ref_stems)
         if key not in refs:
             refs[key] = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
-        codes, quals, _, _ = W.simulate_host(0, sample_pairs)
-        lens = np.full(2 * sample_pairs, W.params.read_len, np.int32)
+        codes, quals = qmo_py.simulate_pairs(W, plan.window(i % plan.n_inputs), sample_pairs)
+        lens = np.full(2 * sample_pairs, plan.L, np.int32)
         t0 = time.perf_counter()
-        qmo_py.run_sample(refs[key], codes, quals, lens)
+        qmo_py.run_sample(refs[key], codes, quals, lens, opt=opt)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -127,10 +176,10 @@ def cpu_arm(args, steps, warmup, sample_pairs):
     return sample_pairs * len(times) / tot, tot / len(times) * 1e3
 
 
-def calibrated_cpu_sample(args):
-    """pick a sample size that costs about args.cpu_seconds of CPU wall time"""
-    rate, _ = cpu_arm(args, 1, 0, 20_000)
-    n = int(max(20_000, min(args.pairs, rate * args.cpu_seconds)))
+def calibrated_cpu_sample(plan, seconds, cap):
+    """pick a sample size that costs about `seconds` of CPU wall time"""
+    rate, _ = cpu_arm(plan, 1, 0, 20_000)
+    n = int(max(20_000, min(cap, rate * seconds)))
     return n - n % 1000
 
 
@@ -138,30 +187,44 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import qmo_py
-    qmo_py.build()
+    qmo_py = cpu_setup()
+    plan = Plan(args, args.gpus)
+    per_rank = plan.total // args.gpus
     cores = qmo_py.n_threads()
-    per_step = max(20_000, int(calibrated_cpu_sample(args) / max(1, args.steps + args.warmup) * 4))
-    per_step -= per_step % 1000
-    value, ms = cpu_arm(args, args.steps, args.warmup, per_step)
-    sample = f"{per_step} pairs per step (prefix of each step's sample), oracle port: seeding+extension+mate rescue+pairing+CIGAR+pileup"
+    per_step = max(20_000, int(calibrated_cpu_sample(plan, args.cpu_seconds, per_rank) / max(1, args.steps + args.warmup) * 4))
+    per_step = min(per_step - per_step % 1000, plan.total)
+    value, ms = cpu_arm(plan, args.steps, args.warmup, per_step)
+    sample = (f"{per_step} pairs per step (prefix of each step's sample), oracle port: seeding+extension+mate rescue+pairing+CIGAR+pileup; "
+              f"build {qmo_py.BUILD_KIND}")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "int32", "data": "synthetic", "config": config_dict(args, args.gpus),
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if plan.strong else "weak",
+           "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": plan.config_dict(args.gpus, per_rank),
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0,
-           "note": "bwa/samtools/bcftools are not in the image and not vendored: the CPU arm is the repo's C restatement "
-                   "(oracle/, OpenMP over reads), not the upstream binaries"}
+           "gpu_launches": 0, "note": CPU_NOTE}
     print(json.dumps(out), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
+def load_truth_keys(name):
+    import gzip
+    import numpy as np
+    from quasimodo_b200 import evaluate
+    tk = []
+    with gzip.open(os.path.join(ROOT, "quasimodo_b200", "data", "truth", f"{name}.maskrepeat.variants.vcf.gz"), "rt") as fh:
+        for ln in fh:
+            f = ln.rstrip("\n").split("\t")
+            if len(f) >= 5 and f[3] in "ACGT" and f[4] in "ACGT" and len(f[3]) == 1 and len(f[4]) == 1 and f[1].isdigit():
+                tk.append(int(evaluate.snp_key(f[1], f[3], f[4])))
+    return np.array(tk, dtype=np.uint64)
+
+
 def run_ours(args):
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
-    from quasimodo_b200 import Context, _lib, evaluate, workloads
+    from quasimodo_b200 import Context, _lib, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,45 +236,45 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    P, K, Wm = args.pairs, args.steps, args.warmup
+    K, Wm = args.steps, args.warmup
+    plan = Plan(args, world)
+    L = plan.L
+    lo, hi = sharding.shard_range(plan.total, rank, world)
+    P = hi - lo                                       # this rank's pairs per step
     ctx = Context(local)                              # raises without the CUDA library / a B200: no CPU fallback
+    lib = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
-    n_used = min(N_SAMPLES, K + Wm)
+    opt = _lib.default_opt()
+    opt.w = plan.w
+    n_used = min(plan.n_inputs, K + Wm)
 
-    # ---- per-sample state: workload, index + qm_sample per reference, truth keys, resident reads ----
-    wl = [workloads.config2(i, P * world) for i in range(n_used)]
-    idx, smp, tkeys_dev, tkeys = {}, {}, {}, {}
+    # ---- per-input state: workload, index + qm_sample per reference, resident reads ----
+    wl = [plan.make(i) for i in range(n_used)]
+    idx, smp = {}, {}
     for W in wl:
-        key = W.ref_stems[0]
+        key = "|".join(W.ref_stems)
         if key not in idx:
             idx[key] = ctx.index(W.ref, 31)
-            smp[key] = ctx.sample(idx[key])
-    truth_path = os.path.join(ROOT, "quasimodo_b200", "data", "truth", "TA.maskrepeat.variants.vcf.gz")
-    import gzip
-    with gzip.open(truth_path, "rt") as fh:
-        tk = []
-        for ln in fh:
-            f = ln.rstrip("\n").split("\t")
-            if len(f) >= 5 and f[3] in "ACGT" and f[4] in "ACGT" and len(f[3]) == 1 and len(f[4]) == 1 and f[1].isdigit():
-                tk.append(int(evaluate.snp_key(f[1], f[3], f[4])))
-    tkeys = np.array(tk, dtype=np.uint64)
+            smp[key] = ctx.sample(idx[key], opt)
+    tkeys = load_truth_keys(plan.truth) if plan.truth else np.zeros(0, np.uint64)
     d_tkeys = torch.from_numpy(tkeys.view(np.int64)).to(dev)
-    L = 150
-    d_lens = torch.full((2 * P,), L, dtype=torch.int32, device=dev)
-    d_lens_pre = torch.full((2 * _lib.PESTAT_PAIRS,), L, dtype=torch.int32, device=dev)
-    d_reads = []
-    d_prefix = []
-    npre = min(_lib.PESTAT_PAIRS, P * world)
-    for W in wl:
+    d_lens = torch.full((2 * min(P, CHUNK),), L, dtype=torch.int32, device=dev)
+    npre = min(_lib.PESTAT_PAIRS, plan.total)
+    need_pre = sharding.needs_prefix(lo, hi, plan.total, _lib.PESTAT_PAIRS)      # on every rank, rank 0 included
+    d_lens_pre = torch.full((2 * npre,), L, dtype=torch.int32, device=dev)
+    d_reads, d_prefix = [], []
+    for i, W in enumerate(wl):
         g = torch.from_numpy(W.src_codes).to(dev)
         c = torch.empty((2 * P, L), dtype=torch.uint8, device=dev)
         q = torch.empty((2 * P, L), dtype=torch.uint8, device=dev)
-        ctx.simulate_pairs(W, rank * P, P, g, c, q, st)
+        for o in range(0, P, 8 * CHUNK):
+            n = min(8 * CHUNK, P - o)
+            ctx.simulate_pairs(W, plan.window(i) + lo + o, n, g, c[2 * o:2 * (o + n)], q[2 * o:2 * (o + n)], st)
         d_reads.append((c, q))
-        if rank != 0:                                  # the sample's designated insert-size prefix (pairs 0..65535)
+        if need_pre:                                   # the sample's designated insert-size prefix (its first 65,536 pairs)
             pc = torch.empty((2 * npre, L), dtype=torch.uint8, device=dev)
             pq = torch.empty((2 * npre, L), dtype=torch.uint8, device=dev)
-            ctx.simulate_pairs(W, 0, npre, g, pc, pq, st)
+            ctx.simulate_pairs(W, plan.window(i), npre, g, pc, pq, st)
             d_prefix.append(pc)
             del pq
         else:
@@ -219,12 +282,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     max_calls = 1 << 18
     d_calls = torch.empty(max_calls * 40, dtype=torch.uint8, device=dev)
-    d_ckeys = torch.empty(max_calls, dtype=torch.int64, device=dev)
-    d_cflags = torch.zeros(max_calls, dtype=torch.uint8, device=dev)
-    d_tflags = torch.zeros(len(tkeys), dtype=torch.uint8, device=dev)
     copt = _lib.default_call_opt()
-    import ctypes as C
-    lib = _lib.lib()
     results = {}
 
     def finish_sample(i, s, key):
@@ -239,33 +297,31 @@ def run_ours(args):
         if rc:
             raise RuntimeError(lib.qm_last_error(ctx._h).decode())
         nc = n.value
-        calls = d_calls[:nc * 40].view(torch.int32).view(nc, 10)
-        # key = (pos+1) << 8 | ref << 4 | alt ; ref/alt are bytes 0/1 of the third int32
-        ra = calls[:, 2].to(torch.int64)
-        d_ckeys[:nc] = ((calls[:, 1].to(torch.int64) + 1) << 8) | ((ra & 0xff) << 4) | ((ra >> 8) & 0xff)
         pure = wl[i].name.endswith(("-1-0", "-0-1"))
-        if pure or nc == 0:
+        if pure or nc == 0 or not plan.truth:
             return nc, 0, nc, 0
-        rc = lib.qm_eval_match(ctx._h, C.c_void_p(d_ckeys.data_ptr()), nc, C.c_void_p(d_tkeys.data_ptr()), len(tkeys),
-                               C.c_void_p(d_cflags.data_ptr()), C.c_void_p(d_tflags.data_ptr()), C.c_void_p(st))
+        tpfpfn = (C.c_int64 * 3)()
+        rc = lib.qm_eval_calls(ctx._h, C.c_void_p(d_calls.data_ptr()), nc, C.c_void_p(d_tkeys.data_ptr()), len(tkeys), None,
+                               tpfpfn, C.c_void_p(st))
         if rc:
             raise RuntimeError(lib.qm_last_error(ctx._h).decode())
-        tp = int(d_cflags[:nc].sum().item())
-        fn = int(len(tkeys) - d_tflags.sum().item())
-        return nc, tp, nc - tp, fn
+        return nc, int(tpfpfn[0]), int(tpfpfn[1]), int(tpfpfn[2])
 
     def step_resident(i):
-        W = wl[i % n_used]
-        key = W.ref_stems[0]
+        j = i % n_used
+        W = wl[j]
+        key = "|".join(W.ref_stems)
         s = smp[key]
         s.reset(st)
-        c, q = d_reads[i % n_used]
-        if rank != 0:
-            s.estimate_pestat(d_prefix[i % n_used], d_lens_pre[:2 * npre], st)
-        s.add_pairs(c, q, d_lens, pair_id0=rank * P, stream=st)
-        r = finish_sample(i % n_used, s, key)
+        c, q = d_reads[j]
+        if need_pre:
+            s.estimate_pestat(d_prefix[j], d_lens_pre, st)
+        for o in range(0, P, CHUNK):
+            n = min(CHUNK, P - o)
+            s.add_pairs(c[2 * o:2 * (o + n)], q[2 * o:2 * (o + n)], d_lens[:2 * n], pair_id0=lo + o, stream=st)
+        r = finish_sample(j, s, key)
         if r is not None:
-            results[W.name] = r
+            results[W.name + (f"@{plan.window(j)}" if plan.cfg == 1 else "")] = r
         return s.stats(st)[1]                          # executed ksw_extend2 cells of this step (8-byte read-back)
 
     def barrier():
@@ -299,7 +355,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = P * world * K / ms * 1e3
+    value = plan.total * K / ms * 1e3
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
     e2e = None
@@ -311,15 +367,18 @@ def run_ours(args):
         e2e_times, d2h = [], 0
 
         def step_host(i):
-            W = wl[i % n_used]
-            key = W.ref_stems[0]
+            j = i % n_used
+            W = wl[j]
+            key = "|".join(W.ref_stems)
             s = smp[key]
             s.reset(st)
-            if rank != 0:
-                s.estimate_pestat(d_prefix[i % n_used], d_lens_pre[:2 * npre], st)
+            if need_pre:
+                s.estimate_pestat(d_prefix[j], d_lens_pre, st)
             torch.cuda.synchronize()
-            s.add_pairs_host(h_codes, h_quals, h_lens, pair_id0=rank * P)
-            r = finish_sample(i % n_used, s, key)
+            for o in range(0, P, 4 * CHUNK):            # the library chunks and double-buffers its copies itself
+                n = min(4 * CHUNK, P - o)
+                s.add_pairs_host(h_codes[2 * o:2 * (o + n)], h_quals[2 * o:2 * (o + n)], h_lens[2 * o:2 * (o + n)], pair_id0=lo + o)
+            r = finish_sample(j, s, key)
             nb = 0
             if r is not None:
                 nb = r[0] * 40
@@ -327,10 +386,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             return nb + 8
 
+        last = -1
         for i in range(Wm + K):
-            c, q = d_reads[i % n_used]
-            h_codes.copy_(c)
-            h_quals.copy_(q)
+            if i % n_used != last:                      # outside the timed region: this step's reads into the pinned buffers
+                c, q = d_reads[i % n_used]
+                h_codes.copy_(c)
+                h_quals.copy_(q)
+                last = i % n_used
             barrier()
             t0 = time.perf_counter()
             nb = step_host(i)
@@ -342,10 +404,10 @@ def run_ours(args):
         te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": P * world * K / float(te.item()), "unit": UNIT,
+        e2e = {"value": plan.total * K / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * (2 * P * L) + 4 * 2 * P), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(te.item()) / K * 1e3,
-               "api": "qm_sample_add_pairs_host (+ qm_call_snps, qm_eval_match), pinned host buffers"}
+               "api": "qm_sample_add_pairs_host (+ qm_call_snps, qm_eval_calls), pinned host buffers"}
 
     if rank != 0:
         if world > 1:
@@ -368,38 +430,53 @@ def run_ours(args):
     except (OSError, KeyError, ValueError):
         pass
     ext_ms = stage_ms["extend"]
-    dom = max(("seed_chain", "advance", "extend", "pair_cigar", "pileup"), key=lambda k: stage_ms[k])
+    dom = max(("seed_chain", "advance", "extend", "pair_cigar", "pileup", "rescue"), key=lambda k: stage_ms[k])
     gcups = cells_total / ext_ms / 1e6 if ext_ms > 0 else 0.0
-    roofline = {"kernel": "ext2_kernel<CAP> + ext_kernel<C> (batched ksw_extend2)", "bound": "int-issue (DPX), not hbm/tensor",
+    Pk = P * K
+    roofline = {"kernel": "ksw_extend2 kernels (thread-per-task-pair ext3_kernel / ext2_kernel, warp-per-task ext_kernel, tail_kernel)",
+                "bound": "int-issue (DPX), not hbm/tensor",
                 "achieved": gcups, "peak": gcups_peak, "unit": "GCUPS", "frac": gcups / gcups_peak if gcups_peak else None,
-                "traffic": traffic, "traffic_how": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per ext2_kernel launch "
+                "traffic": traffic, "traffic_how": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per extension-kernel launch "
                                                "(profiles/ext2_traffic.json); the kernel is issue-bound, not DRAM-bound",
                 "avg_launch_ms": ext_ms / max(1, stage_launch["extend"]),
-                "work": f"{cells_total} executed ksw_extend2 cells in {K} steps ({cells_total / (P * K):.0f} cells/pair)",
+                "work": f"{cells_total} executed ksw_extend2 cells in {K} steps ({cells_total / max(1, Pk):.0f} cells/pair)",
+                "cells_per_pair": cells_total / max(1, Pk),
                 "peak_how": f"measured in this run: {dpx_gops:.0f} G lane-instr/s of viaddmax_s16x2_relu x 2 cells / 9 instr",
                 "dominant_stage": dom}
     pile_ms = stage_ms["pileup"]
-    pile_gbs = ALGO_BYTES_PER_PAIR_PILEUP * P * K / pile_ms / 1e6 if pile_ms > 0 else 0.0
+    pile_b = 2 * ((L + 3) // 4 + L + 16 + 8)            # packed bases + qualities + header + 2 CIGAR ops, per read
+    pile_gbs = pile_b * Pk / pile_ms / 1e6 if pile_ms > 0 else 0.0
+    pile_traffic = None
+    try:
+        pile_traffic = json.load(open(os.path.join(ROOT, "profiles", "pileup_traffic.json")))["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline_pileup = {"kernel": "pileup_kernel", "bound": "hbm", "achieved": pile_gbs, "peak": hbm_peak, "unit": "GB/s",
-                       "frac": pile_gbs / hbm_peak, "traffic": None, "peak_how": hbm_src,
-                       "work": f"{ALGO_BYTES_PER_PAIR_PILEUP} B/pair algorithmic x {P * K} pairs"}
+                       "frac": pile_gbs / hbm_peak, "traffic": pile_traffic, "peak_how": hbm_src,
+                       "work": f"{pile_b} B/pair algorithmic x {Pk} pairs"}
+    seed_ms = stage_ms["seed_chain"]
+    seed_b = 2 * ((L + 3) // 4)                         # packed read bytes read once (seed records are reported apart)
+    seed_gbs = seed_b * Pk / seed_ms / 1e6 if seed_ms > 0 else 0.0
+    roofline_seed = {"kernel": "seed_chain_kernel", "bound": "hbm (algorithmic); in practice L2 probe latency + integer issue",
+                     "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": seed_gbs / hbm_peak, "traffic": None,
+                     "work": f"{seed_b} B/pair of 2-bit packed read bases x {Pk} pairs; reads arrive 1 B/base ({2 * L} B/pair actually read)"}
     launches = int(sum(stage_launch.values()))
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-           "data": "synthetic", "config": config_dict(args, world), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
-           "roofline": roofline, "roofline_pileup": roofline_pileup,
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if plan.strong else "weak", "vs_baseline": None,
+           "dtype": "int32", "data": "synthetic", "config": plan.config_dict(world, P), "clocks": clk, "e2e": e2e,
+           "gpu_launches": launches, "roofline": roofline, "roofline_pileup": roofline_pileup, "roofline_seed": roofline_seed,
            "stages_ms_per_step": {k: v / K for k, v in stage_ms.items()},
            "stage_launches": stage_launch,
            "results": {k: {"calls": v[0], "TP": v[1], "FP": v[2], "FN": v[3]} for k, v in results.items()}}
 
     if not args.no_cpu_baseline and world == 1:
-        from oracle import qmo_py
-        qmo_py.build()
-        n = calibrated_cpu_sample(args)
-        v, cms = cpu_arm(args, 1, 0, n)
+        qmo_py = cpu_setup()
+        n = calibrated_cpu_sample(plan, args.cpu_seconds, P)
+        v, cms = cpu_arm(plan, 1, 0, n)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": qmo_py.n_threads(), "kind": "port",
-                               "sample": f"first {n} pairs of sample TA-1-0 ({cms / 1e3:.1f} s): oracle port of bwa-mem "
-                                         "extension + mate rescue + pairing + CIGAR + bcftools-style counting, OpenMP over reads"}
+                               "sample": f"first {n} pairs of the first step's sample ({cms / 1e3:.1f} s): oracle port of bwa-mem "
+                                         f"extension + mate rescue + pairing + CIGAR + bcftools-style counting, OpenMP over reads; "
+                                         f"build {qmo_py.BUILD_KIND}", "note": CPU_NOTE}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

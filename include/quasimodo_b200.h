@@ -242,6 +242,11 @@ int  qm_sample_call_snps_host(qm_sample *s, const qm_call_opt *copt, qm_call *h_
  * NULL.  Asynchronous on `stream`. */
 int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, const uint64_t *d_truth_keys, int64_t n_truth,
                   uint8_t *d_call_flags, uint8_t *d_truth_flags, void *stream);
+/* one sample's device-resident calls against the truth keys in one call: keys from the qm_call records, both membership
+ * passes and the totals h_tp_fp_fn = {TP, FP, FN} (scripts/caller_performance_compare.R:93-99).  d_call_flags may be NULL.
+ * Synchronous (24 bytes come back). */
+int qm_eval_calls(qm_ctx *ctx, const qm_call *d_calls, int64_t n_call, const uint64_t *d_truth_keys, int64_t n_truth,
+                  uint8_t *d_call_flags, int64_t h_tp_fp_fn[3], void *stream);
 int qm_eval_match_host(qm_ctx *ctx, const uint64_t *h_call_keys, int64_t n_call, const uint64_t *h_truth_keys, int64_t n_truth,
                        uint8_t *h_call_flags, uint8_t *h_truth_flags /* may be NULL */);
 

@@ -25,16 +25,35 @@ EXT_DTYPE = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle",
 
 def build(force=False):
     so = os.path.join(_HERE, "libqmo.so")
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h", ".cpp"))] + [os.path.join(_HERE, "Makefile")]
+    outs = [so, os.path.join(_HERE, "libqmsim.so")]
+    if force or any(not os.path.exists(o) or any(os.path.getmtime(s) > os.path.getmtime(o) for s in srcs) for o in outs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "all"])
     return so
 
 
-def lib():
+BUILD_KIND = "-O3, portable x86-64"
+
+
+def use_native_build():
+    """bench.py's CPU arms: rebuild the restatement with -O3 -march=native ON THIS HOST (never shipped) and use it from now on.
+    Falls back to the portable build when the compile fails."""
+    global _LIB, BUILD_KIND
+    so = os.path.join(_HERE, "libqmo_native.so")
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libqmo_native.so"])
+    except (subprocess.CalledProcessError, OSError):
+        return False
+    _LIB = None
+    lib(so)
+    BUILD_KIND = "-O3 -march=native (built on this host)"
+    return True
+
+
+def lib(path=None):
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        _LIB = C.CDLL(path or build())
         _LIB.qmo_ksw_extend2.restype = C.c_int64
         _LIB.qmo_ksw_global2.restype = C.c_int
         _LIB.qmo_ksw_align2.restype = C.c_int64
@@ -286,6 +305,35 @@ def run_sample(ref, codes, quals, lens, pair_id0=0, opt=None, popt=None, prefix=
     alns = pair_and_finish(ref, codes, lens, o["regs"], o["n_regs"], pes, pair_id0=pair_id0, opt=opt)
     counts = pileup(ref, alns, codes, quals, lens, popt)
     return alns, counts, o["cells"], pes
+
+
+_SIM = None
+
+
+def simulate_pairs(W, pair0, n_pairs, stride=None):
+    """host half of the input simulator (oracle/libqmsim.so): the same bytes as the product's qm_simulate_pairs*"""
+    global _SIM
+    if _SIM is None:
+        build()
+        _SIM = C.CDLL(os.path.join(_HERE, "libqmsim.so"))
+    stride = stride or W.params.read_len
+    codes = np.empty((2 * n_pairs, stride), dtype=np.uint8)
+    quals = np.empty((2 * n_pairs, stride), dtype=np.uint8)
+    rc = _SIM.qmsim_pairs_host(C.byref(W.params), C.c_void_p(W.src_codes.ctypes.data), C.c_void_p(W.src_off.ctypes.data),
+                               C.c_void_p(W.src_len.ctypes.data), C.c_void_p(W.src_cum.ctypes.data), C.c_int64(pair0),
+                               C.c_int64(n_pairs), C.c_int32(stride), C.c_void_p(codes.ctypes.data), C.c_void_p(quals.ctypes.data),
+                               None, None)
+    if rc:
+        raise RuntimeError("qmsim_pairs_host failed")
+    return codes, quals
+
+
+def set_threads(n):
+    """OpenMP threads of the restatement (torchrun exports OMP_NUM_THREADS=1: the CPU arm must undo that itself)"""
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
 
 
 def n_threads():

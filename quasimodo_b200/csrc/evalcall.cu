@@ -124,6 +124,24 @@ __global__ void member_kernel(const uint64_t *__restrict__ q, int64_t nq, const 
     flags[i] = (lo < ns && sorted[lo] == key) ? 1 : 0;
 }
 
+// qm_call records -> matcher keys (1-based POS << 8 | ref << 4 | alt)
+__global__ void call_keys_kernel(const qm_call *__restrict__ calls, int64_t n, uint64_t *__restrict__ keys)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const qm_call c = calls[i];
+    keys[i] = ((uint64_t)(uint32_t)(c.pos + 1) << 8) | ((uint64_t)c.ref << 4) | (uint64_t)c.alt;
+}
+
+// out[which] += number of set flags
+__global__ void __launch_bounds__(256) flag_count_kernel(const uint8_t *__restrict__ flags, int64_t n, unsigned long long *__restrict__ out)
+{
+    unsigned v = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v += flags[i] != 0;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
+}
+
 int sorted_copy(qm_ctx *ctx, int which, const uint64_t *d_keys, int64_t n, uint64_t **out, cudaStream_t st)
 {
     int64_t n_pad = 2;
@@ -199,6 +217,37 @@ int qm_eval_match(qm_ctx *ctx, const uint64_t *d_call_keys, int64_t n_call, cons
     }
     qm_prof_end(ctx, QM_ST_OTHER, sp, st, launches);
     QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}
+
+// calls of one sample against the truth keys, everything on the device: keys from the qm_call records, both membership
+// passes, the three totals.  h_tp_fp_fn = {TP, FP, FN}.  d_call_flags (may be NULL) receives the per-call TP flags.  Synchronous.
+int qm_eval_calls(qm_ctx *ctx, const qm_call *d_calls, int64_t n_call, const uint64_t *d_truth_keys, int64_t n_truth,
+                  uint8_t *d_call_flags, int64_t h_tp_fp_fn[3], void *stream)
+{
+    if (!ctx || !h_tp_fp_fn || n_call < 0 || n_truth < 0 || (n_call > 0 && !d_calls) || (n_truth > 0 && !d_truth_keys)) return QM_EINVAL;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_keys = 0, o_cf = al((size_t)n_call * 8), o_tf = o_cf + al((size_t)n_call), o_cnt = o_tf + al((size_t)n_truth);
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 19, o_cnt + 256, &p);
+    if (rc) return rc;
+    char *b = (char *)p;
+    uint64_t *keys = (uint64_t *)(b + o_keys);
+    uint8_t *cf = d_call_flags ? d_call_flags : (uint8_t *)(b + o_cf), *tf = (uint8_t *)(b + o_tf);
+    unsigned long long *cnt = (unsigned long long *)(b + o_cnt);
+    QM_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16, st));
+    if (n_call) call_keys_kernel<<<(unsigned)((n_call + 255) / 256), 256, 0, st>>>(d_calls, n_call, keys);
+    rc = qm_eval_match(ctx, keys, n_call, d_truth_keys, n_truth, cf, tf, st);
+    if (rc) return rc;
+    if (n_call) flag_count_kernel<<<(unsigned)((n_call + 4095) / 4096 < 1024 ? (n_call + 4095) / 4096 : 1024), 256, 0, st>>>(cf, n_call, cnt);
+    if (n_truth) flag_count_kernel<<<(unsigned)((n_truth + 4095) / 4096 < 1024 ? (n_truth + 4095) / 4096 : 1024), 256, 0, st>>>(tf, n_truth, cnt + 1);
+    QM_CUDA(ctx, cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    QM_CUDA(ctx, cudaMemcpyAsync(h, cnt, 16, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    h_tp_fp_fn[0] = (int64_t)h[0]; h_tp_fp_fn[1] = n_call - (int64_t)h[0]; h_tp_fp_fn[2] = n_truth - (int64_t)h[1];
     return QM_OK;
 }
 
