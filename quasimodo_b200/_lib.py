@@ -101,6 +101,7 @@ SIGNATURES = {
     "qm_call_snps": (C.c_int, [_P, _P, _P, _P, _P, _L, C.POINTER(C.c_int64), _P]),
     "qm_eval_match": (C.c_int, [_P, _P, _L, _P, _L, _P, _P, _P]),
     "qm_eval_match_host": (C.c_int, [_P, _P, _L, _P, _L, _P, _P]),
+    "qm_eval_calls": (C.c_int, [_P, _P, _L, _P, _L, _P, _P, _P]),
     "qm_sample_call_snps_host": (C.c_int, [_P, _P, _P, _L, C.POINTER(C.c_int64)]),
     "qm_aln_sort_keys": (C.c_int, [_P, _P, _P, _L, _P, C.POINTER(C.c_int), _P]),
     "qm_sort_pairs": (C.c_int, [_P, _P, _P, _L, C.c_int, _P]),

@@ -950,6 +950,12 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { return qm_fail(ctx, QM_ECUDA, "qm_align_se round %d: %s", round, cudaGetErrorString(e)); }
             if (h_ctr->n_tasks == 0) break;
+            static const bool round_log = getenv("QM_ROUND_LOG") != nullptr;       // diagnostics: the round's task counts per class
+            if (round_log) {
+                fprintf(stderr, "[qm round %d] tasks %d max_score %d classes", round, h_ctr->n_tasks, h_ctr->max_score);
+                for (int c = 0; c < kExtClasses; ++c) fprintf(stderr, " %d", h_ctr->class_count[c]);
+                fprintf(stderr, "\n");
+            }
             if (h_ctr->n_tasks < kTailMinTasks) {
                 // few reads left: finish them on the device, one warp per read, no more round trips
                 sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);

@@ -168,3 +168,32 @@ def test_eval_match_large_random(ctx):
     assert np.array_equal(tf.astype(bool), np.isin(t, c))
     cf, tf = evaluate.match_keys(ctx, c[:0], t)
     assert len(cf) == 0 and not tf.any()
+
+
+def test_eval_calls_totals_match_the_key_matcher(ctx):
+    """qm_eval_calls (keys from the call records + both membership passes + TP/FP/FN totals, all on the device) against
+    qm_eval_match_host on keys packed on the host"""
+    import ctypes as C
+    import torch
+    from quasimodo_b200 import _lib, evaluate
+    rng = np.random.default_rng(11)
+    n, nt = 30_000, 25_000
+    calls = np.zeros(n, dtype=_lib.CALL_DTYPE)
+    calls["pos"] = np.sort(rng.integers(0, 200_000, n))
+    calls["ref"] = rng.integers(0, 4, n)
+    calls["alt"] = (calls["ref"] + rng.integers(1, 4, n)) & 3
+    keys = ((calls["pos"].astype(np.uint64) + 1) << 8) | (calls["ref"].astype(np.uint64) << 4) | calls["alt"].astype(np.uint64)
+    truth = np.concatenate([rng.choice(keys, 9_000, replace=False), rng.integers(1 << 8, 1 << 26, nt - 9_000).astype(np.uint64)])
+    cf, tf = evaluate.match_keys(ctx, keys, truth)
+    d_calls = torch.from_numpy(calls.view(np.uint8)).cuda()
+    d_truth = torch.from_numpy(truth.view(np.int64)).cuda()
+    d_flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    out = (C.c_int64 * 3)()
+    for flags in (d_flags, None):
+        rc = _lib.lib().qm_eval_calls(ctx._h, C.c_void_p(d_calls.data_ptr()), n, C.c_void_p(d_truth.data_ptr()), nt,
+                                      C.c_void_p(flags.data_ptr()) if flags is not None else None, out, None)
+        assert rc == 0
+        assert list(out) == [int(cf.sum()), n - int(cf.sum()), nt - int(tf.sum())]
+    assert np.array_equal(d_flags.cpu().numpy(), cf)
+    rc = _lib.lib().qm_eval_calls(ctx._h, None, 0, C.c_void_p(d_truth.data_ptr()), nt, None, out, None)
+    assert rc == 0 and list(out) == [0, 0, nt]
