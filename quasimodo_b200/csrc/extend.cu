@@ -113,23 +113,25 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
         if (h_counts && h_counts[c] == 0) continue;
         cudaStream_t sc = ctx->side[c];
         QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
-        const bool big = c < 9 && (!h_counts || h_counts[c] >= kThreadPerTaskMin);
-        // The paired kernel (extend2p.cu) is bit-exact and 10 % faster than the scalar one on wide synthetic tasks, but on
-        // the pipeline's own tasks (rows of ~45 columns, ~85 rows) its per-row bookkeeping for two tasks eats the gain:
-        // measured 1.7x SLOWER per class launch (profiles/r01_v8_paired_vs_scalar.md).  Off unless QM_PAIRED is set.
-        static const bool paired = getenv("QM_PAIRED") != nullptr;
-        if (big && c < 8 && d_fb_lists && d_fb_ctr && paired && P.a == 1) {       // (its packed dead-diagonal rule needs a == 1)
-            // two tasks per thread; what the packed arithmetic cannot hold (N in the query, scores above 255) comes back
-            // through the fallback list and runs on the scalar thread-per-task kernel right behind it
+        static const int tpt_min = getenv("QM_TPT_MIN") ? atoi(getenv("QM_TPT_MIN")) : kThreadPerTaskMin;      // tuning knob
+        const bool big = c < 9 && (!h_counts || h_counts[c] >= tpt_min);
+        // The packed two-tasks-per-thread kernel (extend3.cu) takes every class it can hold; QM_EXT3=0 keeps the scalar
+        // thread-per-task kernel (extend2.cu) for A/B measurements.
+        static const bool ext3 = !(getenv("QM_EXT3") && atoi(getenv("QM_EXT3")) == 0);
+        if (big && d_fb_lists && d_fb_ctr && ext3 && qm_ext3_scores_ok(P)) {
             const int hc = h_counts ? h_counts[c] : -1;
-            int rc = qm_ext2p_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, hc, d_out, d_fb_lists, d_fb_ctr, sc);
+            int rc = qm_ext3_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, hc, d_out, d_fb_lists, d_fb_ctr, sc);
             if (rc) return rc;
-            // (few tasks, and a thread-per-task chain would add its full latency behind the paired kernel: warp per task)
-            switch (c) {
-            case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-            case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-            case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-            default: launch_class<5>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+            // what the packed arithmetic cannot hold (scores above 255) comes back through the fallback list; the caller
+            // that knows the round's maximum score (scores_fit_bytes) knows the list stays empty
+            if (!scores_fit_bytes) {
+                switch (c) {
+                case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 6: case 7: launch_class<5>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                default: launch_class<9>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                }
             }
         } else if (big) {
             int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc,

@@ -1,0 +1,178 @@
+// extend3.cu -- batched ksw_extend2, formulation "P2": the device side of ext3_core.cuh (ONE THREAD PER PAIR OF TASKS,
+// both tasks in the halves of s16x2 DPX words; bwa 0.7.17 ksw.c:ksw_extend2 as called by bwamem.c:mem_chain2aln,
+// reference call site rules/bwa.smk:15, semantics SURVEY.md A.3).  The per-thread statements live in ext3_core.cuh, which
+// the CPU test suite compiles for the host and checks against the oracle; this file adds what only exists on the device:
+// the shared-memory planes, the target fetch, the persistent grid with its warp-batched refill, the launch shapes.
+//
+// Why this shape on B200: the extension is bound by the integer ALU pipe (16 lanes/clk/SMSP, DPX included).  The scalar
+// kernel (extend2.cu) spends ~11 ALU-pipe instructions per cell plus ~8 of per-row control; here a PAIR of cells costs ~9.5
+// and the per-row control of two tasks is one instruction stream.  Shared memory per thread: 12 bytes per column (64-bit
+// {h2, e2} + 32-bit query codes) for two tasks; block sizes are chosen per class so that a few blocks fit an SM.
+#include "pipeline.cuh"
+#include "ext3_core.cuh"
+
+namespace {
+
+template <int KT>
+struct SmemPlanes {                         // this thread's columns: word j of a plane sits at [j][thread]
+    uint2 *ehp;
+    uint32_t *qp;
+    __device__ __forceinline__ uint2 &eh(int j) { return ehp[j * KT]; }
+    __device__ __forceinline__ uint32_t &q(int j) { return qp[j * KT]; }
+    __device__ __forceinline__ uint16_t &h16(int j, int X) { return ((uint16_t *)&ehp[j * KT].x)[X]; }
+    __device__ __forceinline__ uint16_t &e16(int j, int X) { return ((uint16_t *)&ehp[j * KT].y)[X]; }
+    __device__ __forceinline__ uint16_t &q16(int j, int X) { return ((uint16_t *)&qp[j * KT])[X]; }
+};
+
+struct DevTgt {                             // where the two tasks' target rows come from
+    const IndexView *V;
+    const uint8_t *t[2];
+    int64_t t0[2];
+    int tstep[2];
+    bool indirect[2];
+    __device__ __forceinline__ int base(int X, int i) const
+    {
+        const int c = indirect[X] ? qm_ref_base(*V, t0[X] + (int64_t)i * tstep[X]) : t[X][i];
+        return c > 4 ? 4 : c;
+    }
+};
+
+struct DevQry {
+    const uint8_t *q;
+    int qstep;
+    __device__ __forceinline__ int code(int j) const { const int c = q[(int64_t)j * qstep]; return c > 4 ? 4 : c; }
+};
+
+template <int CAP, int KT, bool SYM>
+__global__ void __launch_bounds__(KT)
+ext3_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const int *__restrict__ list,
+            const int *__restrict__ count, int *__restrict__ cursor, qm_ext_result *__restrict__ out,
+            int *__restrict__ fb_list, int *__restrict__ fb_count)
+{
+    extern __shared__ uint2 smem_u2[];
+    SmemPlanes<KT> mem;
+    mem.ehp = smem_u2 + threadIdx.x;
+    mem.qp = (uint32_t *)(smem_u2 + (CAP + 1) * KT) + threadIdx.x;
+    // dead storage must hold small non-negative values (a half without a task rides along on its partner's columns)
+    for (int j = 0; j <= CAP; ++j) mem.eh(j) = make_uint2(0u, 0u);
+    for (int j = 0; j < CAP; ++j) mem.q(j) = 0u;
+    const E3Scores S = {P.a, P.b, P.o_del, P.e_del, P.o_ins, P.e_ins, P.zdrop};
+    const E3Consts K = e3_consts(S);
+    const int n = *count;
+    E3Half A, B;
+    A.tk = B.tk = -1; A.phase = B.phase = 0;
+    DevTgt tgt;
+    tgt.V = &V;
+    tgt.t[0] = tgt.t[1] = nullptr; tgt.t0[0] = tgt.t0[1] = 0; tgt.tstep[0] = tgt.tstep[1] = 0; tgt.indirect[0] = tgt.indirect[1] = false;
+
+    auto load = [&](E3Half &H, int X, int tk) {
+        const ExtTaskI t = tasks[tk];
+        if (!e3_task_ok(S, t.qlen, t.h0, CAP)) { fb_list[atomicAdd(fb_count, 1)] = tk; return; }      // the scalar kernel takes it
+        H.tk = tk; H.phase = 1;
+        H.qlen = t.qlen; H.tlen = t.tlen; H.h0 = t.h0; H.w0 = t.w; H.w = t.w; H.end_bonus = t.end_bonus;
+        H.tries_left = (t.flags & QM_EXT_BAND_RETRY) ? 2 : 1;
+        H.prev = (t.flags & QM_EXT_PREV_H0) ? t.h0 : -1;
+        H.cells = 0;
+        tgt.t[X] = t.t; tgt.t0[X] = t.t0; tgt.tstep[X] = t.tstep; tgt.indirect[X] = (t.flags & QM_EXTI_INDIRECT) != 0;
+        DevQry qry = {t.q, t.qstep};
+        e3_load_query(K, t.qlen, X, mem, qry);
+    };
+    auto finish = [&](E3Half &H) {
+        E3Result r;
+        if (e3_end_try(H, &r)) {
+            qm_ext_result o;
+            o.score = r.score; o.qle = r.qle; o.tle = r.tle; o.gtle = r.gtle; o.gscore = r.gscore;
+            o.max_off = r.max_off; o.w_used = r.w_used; o.cells = r.cells;
+            out[H.tk] = o;
+            H.tk = -1;
+        }
+    };
+
+    // The lanes of a warp walk the same loop body (refill / start of a try / row) and reconverge once per row.  A lane whose
+    // two tasks are finished does not fetch the next pair at once: loading a task is a serial loop over its query, and 32
+    // lanes refilling one by one would stall the warp's row loop 32 times per generation.  Idle lanes wait until kRefill of
+    // them are idle (or nobody works) and refill together.
+    constexpr int kRefill = 8;
+    bool exhausted = false;
+    for (;;) {
+        const bool idle = A.phase == 0 && B.phase == 0;
+        const unsigned idle_m = __ballot_sync(0xffffffffu, idle);
+        const unsigned want_m = __ballot_sync(0xffffffffu, idle && !exhausted);
+        if (idle_m == 0xffffffffu && want_m == 0u) break;
+        if (idle && !exhausted && (__popc(want_m) >= kRefill || idle_m == 0xffffffffu)) {
+            const int idx = atomicAdd(cursor, 2);
+            if (idx >= n) exhausted = true;
+            else {
+                load(A, 0, list[idx]);
+                if (idx + 1 < n) load(B, 1, list[idx + 1]);
+            }
+        }
+        if (A.phase == 1) e3_start_try(K, A, 0, mem, tgt);
+        if (B.phase == 1) e3_start_try(K, B, 1, mem, tgt);
+        if (A.phase == 0 && B.phase == 0) continue;
+        bool dA, dB;
+        e3_row<SYM>(K, A, B, mem, tgt, dA, dB);
+        if (dA) finish(A);
+        if (dB) finish(B);
+    }
+}
+
+template <int CAP, int KT>
+void launch3(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
+             int64_t list_stride, const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, int *d_fb_lists,
+             int *d_fb_ctr, cudaStream_t st)
+{
+    const size_t smem = (size_t)KT * ((CAP + 1) * 8 + CAP * 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ext3_kernel<CAP, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ext3_kernel<CAP, KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    int per_sm = (int)((227u * 1024u) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32) per_sm = 32;
+    int64_t blocks = (int64_t)ctx->sm_count * per_sm;
+    if (h_count >= 0) {
+        const int64_t need = ((h_count + 1) / 2 + KT - 1) / KT;
+        if (need < blocks) blocks = need;
+    }
+    if (blocks < 1) return;
+    const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins && P.a == 1;
+    const int *list = d_lists + cls * list_stride;
+    int *fb = d_fb_lists + cls * list_stride;
+    if (sym) ext3_kernel<CAP, KT, true><<<(unsigned)blocks, KT, smem, st>>>(P, V, d_tasks, list, d_counts + cls, d_cursors + cls, d_out, fb, d_fb_ctr + cls);
+    else ext3_kernel<CAP, KT, false><<<(unsigned)blocks, KT, smem, st>>>(P, V, d_tasks, list, d_counts + cls, d_cursors + cls, d_out, fb, d_fb_ctr + cls);
+}
+
+}  // namespace
+
+bool qm_ext3_scores_ok(const ExtParams &P)
+{
+    const E3Scores S = {P.a, P.b, P.o_del, P.e_del, P.o_ins, P.e_ins, P.zdrop};
+    return e3_scores_ok(S);
+}
+
+// one class (0..8) on the packed kernel; tasks it cannot hold (scores above 255) are appended to the class's fallback list
+// d_fb_lists[cls][.] (count d_fb_ctr[cls]) for the scalar kernel.  h_count < 0: unknown on the host.
+int qm_ext3_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
+                         qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st)
+{
+#define QM_L3(CAPV, KTV) launch3<CAPV, KTV>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, d_fb_lists, d_fb_ctr, st)
+    switch (cls) {
+    case 0: QM_L3(16, 64); break;
+    case 1: QM_L3(32, 64); break;
+    case 2: QM_L3(48, 64); break;
+    case 3: QM_L3(64, 64); break;
+    case 4: QM_L3(80, 32); break;
+    case 5: QM_L3(96, 32); break;
+    case 6: QM_L3(112, 32); break;
+    case 7: QM_L3(128, 32); break;
+    case 8: QM_L3(256, 32); break;
+    default: return qm_fail(ctx, QM_EINVAL, "qm_ext3_launch_class: class %d has no packed kernel", cls);
+    }
+#undef QM_L3
+    QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}

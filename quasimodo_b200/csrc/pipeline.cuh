@@ -150,11 +150,12 @@ static __host__ __device__ __forceinline__ int qm_ext_class(int qlen)
 int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                          const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
                          qm_ext_result *d_out, cudaStream_t st, bool bytes = false);
-// two tasks per thread in one s16x2 word (extend2p.cu), classes 0..7; tasks it cannot hold are appended to the
-// class's fallback list d_fb_lists[cls][.] (count d_fb_ctr[cls]) for the scalar kernel
-int qm_ext2p_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
-                          const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
-                          qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st);
+// two tasks per thread in the halves of s16x2 words (extend3.cu), classes 0..8; tasks it cannot hold (scores above 255) are
+// appended to the class's fallback list d_fb_lists[cls][.] (count d_fb_ctr[cls]) for a scalar kernel
+bool qm_ext3_scores_ok(const ExtParams &P);
+int qm_ext3_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
+                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
+                         qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st);
 // d_fb_lists: [kExtClasses][list_stride] ints, d_fb_ctr: 2 * kExtCtr ints zeroed by the caller (fallback counts,
 // then fallback cursors); both NULL: the paired kernel is not used
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,

@@ -1,0 +1,73 @@
+// ext3_host.cpp -- HOST build of the packed two-tasks-per-thread extension logic (quasimodo_b200/csrc/ext3_core.cuh) for the
+// CPU test suite: the statements the CUDA kernel runs, with the DPX instructions emulated, driven task pair by task pair.
+// Test infrastructure (built by tests/test_ext3_host.py into tests/_build/); the product has no host path.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include "../quasimodo_b200/csrc/ext3_core.cuh"
+
+namespace {
+struct HostMem {
+    std::vector<uint2> ehv;
+    std::vector<uint32_t> qv;
+    explicit HostMem(int cap) : ehv((size_t)cap + 1), qv((size_t)cap + 1) {}
+    uint2 &eh(int j) { return ehv.at((size_t)j); }
+    uint32_t &q(int j) { return qv.at((size_t)j); }
+    uint16_t &h16(int j, int X) { return ((uint16_t *)&ehv.at((size_t)j).x)[X]; }
+    uint16_t &e16(int j, int X) { return ((uint16_t *)&ehv.at((size_t)j).y)[X]; }
+    uint16_t &q16(int j, int X) { return ((uint16_t *)&qv.at((size_t)j))[X]; }
+};
+struct HostTgt {
+    const uint8_t *t[2];
+    int n[2];
+    int base(int X, int i) const { if (i < 0 || i >= n[X]) __builtin_trap(); return t[X][i] > 4 ? 4 : t[X][i]; }
+};
+struct HostQry { const uint8_t *q; int code(int j) const { return q[j] > 4 ? 4 : q[j]; } };
+}  // namespace
+
+// tasks i: query seq + q_off[i] (qlen[i]), target seq + t_off[i] (tlen[i]); flags bit 0 = band retry, bit 1 = prev starts at h0.
+// Tasks are run in pairs (2k, 2k+1) in the given order; dirty != 0 leaves the previous pair's cells in place (what a
+// persistent kernel thread sees), otherwise the planes start zeroed.  out[i] = 8 ints; not_ok[i] = 1: the packed kernel
+// refuses the task (the launcher's fallback), out untouched.  Returns 0, or -1 when the scoring scheme is refused.
+extern "C" int ext3_host_run(const int *scores /* a b o_del e_del o_ins e_ins zdrop */, int cap, int64_t n, const uint8_t *seq,
+                             const int64_t *q_off, const int64_t *t_off, const int *qlen, const int *tlen, const int *h0, const int *w,
+                             int end_bonus, const unsigned *flags, int *out, uint8_t *not_ok)
+{
+    E3Scores S = {scores[0], scores[1], scores[2], scores[3], scores[4], scores[5], scores[6]};
+    if (!e3_scores_ok(S)) return -1;
+    const E3Consts K = e3_consts(S);
+    const bool sym = S.o_del == S.o_ins && S.e_del == S.e_ins && S.a == 1;
+    HostMem mem(cap);
+    for (int64_t i0 = 0; i0 < n; i0 += 2) {
+        E3Half H[2];
+        HostTgt tgt;
+        for (int X = 0; X < 2; ++X) {
+            H[X].tk = -1; H[X].phase = 0; tgt.t[X] = nullptr; tgt.n[X] = 0;
+            const int64_t i = i0 + X;
+            if (i >= n) continue;
+            not_ok[i] = !e3_task_ok(S, qlen[i], h0[i], cap);
+            if (not_ok[i]) continue;
+            H[X].tk = (int)i; H[X].phase = 1;
+            H[X].qlen = qlen[i]; H[X].tlen = tlen[i]; H[X].h0 = h0[i]; H[X].w0 = w[i]; H[X].w = w[i]; H[X].end_bonus = end_bonus;
+            H[X].tries_left = (flags[i] & 1u) ? 2 : 1;
+            H[X].prev = (flags[i] & 2u) ? h0[i] : -1;
+            H[X].cells = 0;
+            tgt.t[X] = seq + t_off[i]; tgt.n[X] = tlen[i];
+            HostQry qry = {seq + q_off[i]};
+            e3_load_query(K, qlen[i], X, mem, qry);
+        }
+        while (H[0].phase || H[1].phase) {
+            for (int X = 0; X < 2; ++X) if (H[X].phase == 1) e3_start_try(K, H[X], X, mem, tgt);
+            bool dA = false, dB = false;
+            if (sym) e3_row<true>(K, H[0], H[1], mem, tgt, dA, dB);
+            else e3_row<false>(K, H[0], H[1], mem, tgt, dA, dB);
+            const bool d[2] = {dA, dB};
+            for (int X = 0; X < 2; ++X)
+                if (d[X]) {
+                    E3Result r;
+                    if (e3_end_try(H[X], &r)) { memcpy(out + 8 * (int64_t)H[X].tk, &r, sizeof r); H[X].tk = -1; }
+                }
+        }
+    }
+    return 0;
+}

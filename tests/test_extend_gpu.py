@@ -101,15 +101,29 @@ def test_extend_rejects_bad_task(ctx):
         ctx.extend_batch_host(seq, tasks)
 
 
-def test_paired_kernel_variant_is_bit_exact():
-    """the two-tasks-per-thread s16x2 kernel (extend2p.cu, off by default, QM_PAIRED=1) on the random, adversarial and
-    band-retry tasks above; the switch is read once per process, hence the subprocess"""
+def test_scalar_kernel_variant_is_bit_exact():
+    """the default path is the packed two-tasks-per-thread kernel (extend3.cu); QM_EXT3=0 keeps the scalar thread-per-task
+    kernel (extend2.cu: scores above 255, exotic scoring schemes) -- the same tasks through it; the switch is read once per
+    process, hence the subprocess"""
     import os
     import subprocess
     import sys
-    if os.environ.get("QM_PAIRED"):
-        pytest.skip("already inside the QM_PAIRED run")
+    if os.environ.get("QM_EXT3"):
+        pytest.skip("already inside the QM_EXT3 run")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_extend_gpu.py", "-q", "-x", "-k", "random or adversarial or band_retry"],
-                       cwd=root, env=dict(os.environ, QM_PAIRED="1"), capture_output=True, text=True)
+    p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_extend_gpu.py", "-q", "-x", "-k", "random or adversarial or band_retry or other_scoring"],
+                       cwd=root, env=dict(os.environ, QM_EXT3="0"), capture_output=True, text=True)
     assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_packed_kernel_equals_its_host_build(ctx):
+    """ext3_kernel on tasks sorted by query length as the pipeline hands them over (the host build of the same statements is
+    checked against the oracle in tests/test_ext3_host.py), scores up to and beyond the packed kernel's limit of 255: the
+    tasks beyond it come back right through the fallback list"""
+    rng = np.random.default_rng(2024)
+    pairs, h0s, ws = extgen.random_tasks(rng, 60000, max_qlen=125)
+    h0s = rng.integers(1, 250, len(h0s))
+    order = np.argsort([len(q) for q, _ in pairs], kind="stable")
+    pairs = [pairs[i] for i in order]
+    h0s, ws = h0s[order], ws[order]
+    check(ctx, pairs, h0s, ws, 5, flags=3)
