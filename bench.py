@@ -225,6 +225,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from quasimodo_b200 import Context, _lib, sharding
+    from quasimodo_b200.api import Comm
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,6 +244,11 @@ def run_ours(args):
     P = hi - lo                                       # this rank's pairs per step
     ctx = Context(local)                              # raises without the CUDA library / a B200: no CPU fallback
     lib = _lib.lib()
+    comm = None
+    if world > 1:                                     # the library's own NCCL communicator: torch only carries the 128-byte id
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = Comm(ctx, world, rank, box[0])
     st = torch.cuda.current_stream().cuda_stream
     opt = _lib.default_opt()
     opt.w = plan.w
@@ -256,11 +262,17 @@ def run_ours(args):
         if key not in idx:
             idx[key] = ctx.index(W.ref, 31)
             smp[key] = ctx.sample(idx[key], opt)
+            if comm is not None:
+                smp[key].set_comm(comm)
     tkeys = load_truth_keys(plan.truth) if plan.truth else np.zeros(0, np.uint64)
     d_tkeys = torch.from_numpy(tkeys.view(np.int64)).to(dev)
     d_lens = torch.full((2 * min(P, CHUNK),), L, dtype=torch.int32, device=dev)
     npre = min(_lib.PESTAT_PAIRS, plan.total)
-    need_pre = sharding.needs_prefix(lo, hi, plan.total, _lib.PESTAT_PAIRS)      # on every rank, rank 0 included
+    # The insert-size model is the one of the sample's first 65,536 pairs on every rank.  When rank 0's first batch holds them
+    # (always at BASELINE sizes) it is rank 0's, broadcast by the library (qm_sample_set_comm); a shard too small for that
+    # aligns the designated prefix itself -- every rank alike, rank 0 included.
+    r0_lo, r0_hi = sharding.shard_range(plan.total, 0, world)
+    need_pre = world > 1 and min(r0_hi - r0_lo, CHUNK) < npre
     d_lens_pre = torch.full((2 * npre,), L, dtype=torch.int32, device=dev)
     d_reads, d_prefix = [], []
     for i, W in enumerate(wl):
@@ -288,7 +300,7 @@ def run_ours(args):
     def finish_sample(i, s, key):
         """all-reduce (N>1), call SNPs, classify against the truth set; returns (n_calls, tp, fp, fn)"""
         if world > 1:
-            dist.all_reduce(s.counts_tensor(), op=dist.ReduceOp.SUM)
+            s.allreduce_counts(st)                     # qm_counts_allreduce: one in-place ncclAllReduce(int32, sum) over NVLink
         if rank != 0:
             return None
         n = C.c_int64()
@@ -410,8 +422,10 @@ def run_ours(args):
                "api": "qm_sample_add_pairs_host (+ qm_call_snps, qm_eval_calls), pinned host buffers"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        for x in smp.values():
+            x.close()
+        comm.close()
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel + every stage ----
@@ -479,6 +493,9 @@ def run_ours(args):
                                          f"build {qmo_py.BUILD_KIND}", "note": CPU_NOTE}
     print(json.dumps(out), flush=True)
     if world > 1:
+        for x in smp.values():
+            x.close()
+        comm.close()
         dist.destroy_process_group()
 
 

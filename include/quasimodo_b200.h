@@ -318,6 +318,34 @@ int qm_mpileup_text_host(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *
                          int64_t *h_bytes);
 int qm_mpileup_text_fetch(qm_ctx *ctx, char *h_out, int64_t bytes);
 
+/* ---- multi-GPU: the one collective of the path (north_star: "per-GPU int32 count tensors are merged with one NCCL allreduce
+ * over NVLink").  Reads shard by pair index with no data-path exchange; what crosses GPUs is the count
+ * tensor (one in-place integer sum per sample: order independent, bit-exact for any number of GPUs) and the 128 bytes of the
+ * insert-size model, so that every rank pairs its reads against the same mem_pestat result (bwamem_pair.c).
+ * NCCL is bound at run time (dlopen libnccl.so.2; inside a torch process that is torch's own copy): qm_comm_available() says
+ * whether it could be.  Communicators: one process per GPU -- rank 0 calls qm_comm_unique_id, the host carries the 128 bytes
+ * to the other ranks (torch.distributed, MPI, a file), every rank calls qm_comm_init_rank; or one process driving N GPUs --
+ * qm_comm_init_all (what `qm_driver sample --gpus` does; comms[i] belongs to ctxs[i], call the collectives from one host
+ * thread per GPU).  qm_counts_allreduce_nccl takes a caller-owned ncclComm_t instead.  The all-reduce is asynchronous on
+ * `stream`; qm_pestat_bcast is synchronous. */
+typedef struct qm_comm qm_comm;
+int  qm_comm_available(void);
+int  qm_comm_unique_id(uint8_t id[128]);
+int  qm_comm_init_rank(qm_ctx *ctx, int n_ranks, int rank, const uint8_t id[128], qm_comm **out);
+int  qm_comm_init_all(int n, qm_ctx *const *ctxs, qm_comm **comms);
+void qm_comm_destroy(qm_comm *c);
+int  qm_comm_rank(const qm_comm *c);
+int  qm_comm_size(const qm_comm *c);
+int  qm_counts_allreduce(qm_ctx *ctx, qm_comm *comm, int32_t *d_counts, int64_t n, void *stream);
+int  qm_counts_allreduce_nccl(qm_ctx *ctx, void *nccl_comm /* ncclComm_t */, int32_t *d_counts, int64_t n, void *stream);
+int  qm_pestat_bcast(qm_ctx *ctx, qm_comm *comm, qm_pestat pes[4], int root, void *stream);
+/* a sample spread over the communicator's ranks: rank r holds a contiguous range of the sample's pairs, rank 0 the range
+ * that starts at pair 0 (its first batch at least min(sample, QM_PESTAT_PAIRS) pairs).  The insert-size model is then rank
+ * 0's, broadcast once every rank has aligned its first batch (no rank aligns the prefix twice); qm_sample_allreduce_counts
+ * sums the count tensors in place on every rank (asynchronous on `stream`).  Set before the first pairs; NULL clears. */
+int  qm_sample_set_comm(qm_sample *s, qm_comm *comm);
+int  qm_sample_allreduce_counts(qm_sample *s, void *stream);
+
 /* ---- stage timers: CUDA events recorded on the launching stream around every kernel group ----
  * stages: 0 seed+chain, 1 advance (extension state machine), 2 extend (ksw_extend2 kernels), 3 pair+CIGAR,
  * 4 pileup, 5 h2d, 6 d2h, 7 other, 8 mate rescue.  qm_profile_collect synchronises the device and returns + clears the totals;

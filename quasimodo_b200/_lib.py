@@ -119,6 +119,18 @@ SIGNATURES = {
     "qm_profile_collect": (C.c_int, [_P, _P, _P]),
     "qm_simulate_pairs_host": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
     "qm_simulate_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P]),
+    "qm_comm_available": (C.c_int, []),
+    "qm_comm_unique_id": (C.c_int, [_P]),
+    "qm_comm_init_rank": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(C.c_void_p)]),
+    "qm_comm_init_all": (C.c_int, [C.c_int, _P, _P]),
+    "qm_comm_destroy": (None, [_P]),
+    "qm_comm_rank": (C.c_int, [_P]),
+    "qm_comm_size": (C.c_int, [_P]),
+    "qm_counts_allreduce": (C.c_int, [_P, _P, _P, _L, _P]),
+    "qm_counts_allreduce_nccl": (C.c_int, [_P, _P, _P, _L, _P]),
+    "qm_pestat_bcast": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "qm_sample_set_comm": (C.c_int, [_P, _P]),
+    "qm_sample_allreduce_counts": (C.c_int, [_P, _P]),
     "qm_dpx_peak_sync": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 EXPORTS = sorted(SIGNATURES)

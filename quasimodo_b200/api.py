@@ -44,6 +44,46 @@ class Index:
             pass
 
 
+class Comm:
+    """NCCL communicator of the library (one process per GPU): rank 0 makes the id with Comm.unique_id(), the host carries the
+    128 bytes to the other ranks (e.g. torch.distributed.broadcast), every rank constructs Comm(ctx, n_ranks, rank, id)."""
+
+    @staticmethod
+    def available():
+        return bool(_lib.lib().qm_comm_available())
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.lib().qm_comm_unique_id(buf)
+        if rc:
+            raise QmError(f"qm_comm_unique_id failed with code {rc} (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def __init__(self, ctx, n_ranks, rank, uid):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        _check(ctx._h, _lib.lib().qm_comm_init_rank(ctx._h, int(n_ranks), int(rank), buf, C.byref(self._h)), "qm_comm_init_rank")
+        self.rank, self.size = int(rank), int(n_ranks)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().qm_comm_destroy(self._h)
+        self._h = None
+
+    def bcast_pestat(self, pes, root=0, stream=0):
+        pes = np.ascontiguousarray(pes, dtype=_lib.PESTAT_DTYPE)
+        _check(self.ctx._h, _lib.lib().qm_pestat_bcast(self.ctx._h, self._h, pes.ctypes.data, int(root), C.c_void_p(stream)), "qm_pestat_bcast")
+        return pes
+
+    def allreduce_counts(self, d_counts, stream=0):
+        """in-place integer sum of a torch int32 tensor over the ranks"""
+        _check(self.ctx._h, _lib.lib().qm_counts_allreduce(self.ctx._h, self._h, _ptr(d_counts), d_counts.numel(), C.c_void_p(stream)),
+               "qm_counts_allreduce")
+        return d_counts
+
+
 class Sample:
     """One {sample}.{ref_name}: owns the count tensor; pairs are added batch by batch (qm_sample_*)."""
 
@@ -68,6 +108,13 @@ class Sample:
 
     def reset(self, stream=0):
         _check(self.ctx._h, _lib.lib().qm_sample_reset(self._h, C.c_void_p(stream)), "qm_sample_reset")
+
+    def set_comm(self, comm):
+        """spread the sample over the communicator's ranks (see qm_sample_set_comm); None clears"""
+        _check(self.ctx._h, _lib.lib().qm_sample_set_comm(self._h, comm._h if comm is not None else None), "qm_sample_set_comm")
+
+    def allreduce_counts(self, stream=0):
+        _check(self.ctx._h, _lib.lib().qm_sample_allreduce_counts(self._h, C.c_void_p(stream)), "qm_sample_allreduce_counts")
 
     def set_pestat(self, pes):
         pes = np.ascontiguousarray(pes, dtype=_lib.PESTAT_DTYPE)

@@ -23,7 +23,7 @@ struct qm_ctx {
     int sm_count = 0;
     std::string err;
     // scratch arenas grown on demand (never shrunk); index = purpose
-    qm_scratch scratch[20];
+    qm_scratch scratch[32];
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     // side streams: the independent per-class extension kernels of one round run concurrently (fork/join by events)
     cudaStream_t side[12] = {};

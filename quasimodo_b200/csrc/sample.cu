@@ -35,6 +35,7 @@ struct qm_sample {
     cudaEvent_t ev_part[2][kCopyParts] = {};      // pieces of a chunk's bases (see qm_ctx::se_part_ev)
     bool have_pes = false;
     qm_pestat pes[4];
+    qm_comm *comm = nullptr;                      // multi-GPU: model broadcast from rank 0, counts all-reduced (qm_sample_set_comm)
     int64_t n_pairs = 0;
     // duplicate removal (qm_sample_set_rmdup): every chunk's reads and records stay on the device, counting waits for
     // qm_sample_rmdup_finish
@@ -57,8 +58,17 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
     int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, s->d_cells, st);
     if (rc) return rc;
     if (!s->have_pes) {
-        rc = qm_pestat_sync(ctx, s->idx, &s->opt, s->d_regs, s->d_n_regs, n < kPestatPairs ? n : kPestatPairs, s->pes, st);
-        if (rc) return rc;
+        // one model per sample.  With a communicator it is rank 0's (the rank that holds the sample's first pairs), broadcast:
+        // the other ranks have aligned their own first chunk meanwhile and only wait for 128 bytes.
+        const bool root = !s->comm || qm_comm_rank(s->comm) == 0;
+        if (root) {
+            rc = qm_pestat_sync(ctx, s->idx, &s->opt, s->d_regs, s->d_n_regs, n < kPestatPairs ? n : kPestatPairs, s->pes, st);
+            if (rc) return rc;
+        }
+        if (s->comm && qm_comm_size(s->comm) > 1) {
+            rc = qm_pestat_bcast(ctx, s->comm, s->pes, 0, st);
+            if (rc) return rc;
+        }
         s->have_pes = true;
     }
     qm_aln *alns = d_alns_out ? d_alns_out : s->d_alns;
@@ -210,6 +220,24 @@ int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records)
         off += 2 * k.n;
     }
     return QM_OK;
+}
+
+// Multi-GPU sample: this rank holds a contiguous range of the sample's pairs, rank 0 the range that starts at pair 0 (with at
+// least min(sample, QM_PESTAT_PAIRS) pairs in its first batch).  The insert-size model is then rank 0's, broadcast when the
+// first batch of every rank has been aligned; qm_sample_allreduce_counts sums the count tensors in place on every rank.
+int qm_sample_set_comm(qm_sample *s, qm_comm *comm)
+{
+    if (!s) return QM_EINVAL;
+    if (s->n_pairs != 0) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_set_comm: pairs were already added; reset the sample first");
+    s->comm = comm;
+    return QM_OK;
+}
+
+int qm_sample_allreduce_counts(qm_sample *s, void *stream)
+{
+    if (!s) return QM_EINVAL;
+    if (!s->comm) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_allreduce_counts: no communicator set");
+    return qm_counts_allreduce(s->ctx, s->comm, s->d_counts, (int64_t)QM_NCH * s->idx->v.l_pac, stream);
 }
 
 int qm_sample_set_pestat(qm_sample *s, const qm_pestat pes[4])

@@ -208,7 +208,7 @@ int qm_host_alloc(qm_ctx *ctx, size_t bytes, void **out)
     if (!ctx || !out) return QM_EINVAL;
     *out = nullptr;
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);      // page-locked for every device: the multi-GPU driver deals batches to any GPU
     if (e != cudaSuccess) return qm_fail(ctx, QM_ENOMEM, "qm_host_alloc(%zu): %s", bytes, cudaGetErrorString(e));
     return QM_OK;
 }
