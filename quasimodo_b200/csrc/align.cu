@@ -488,8 +488,6 @@ struct RoundCounters {        // zeroed before every advance round; the host rea
     int tail_cursor;
     int max_score;            // max over the round's tasks of h0 + qlen * a: <= 255 lets the extension kernel hold eh[] in bytes
     int pad[5];
-    int hist[512];            // tasks per query length (counting sort of the task lists by qlen)
-    int offs[512];            // running output offsets of the scatter pass, relative to the class's list
     int fb[2 * kExtCtr];      // fallback lists of the paired extension kernel: counts, then cursors
 };
 constexpr size_t kRoundHeader = (2 * kExtCtr + 8) * sizeof(int);
@@ -677,12 +675,10 @@ __global__ void __launch_bounds__(128)
 advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
                int64_t n, const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
                ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs,
-               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks,
+               const qm_ext_result *__restrict__ res, ExtTaskI *__restrict__ tasks, uint64_t *__restrict__ keys,
                RoundCounters *__restrict__ ctr, unsigned long long *__restrict__ cells)
 {
-    __shared__ int s_hist[512];
     __shared__ int s_class[kExtCtr];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x < kExtCtr) s_class[threadIdx.x] = 0;
     __syncthreads();
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -705,8 +701,8 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
     if (emit) {
         const int slot = base + __popc(em & ((1u << lane) - 1u));
         tasks[slot] = t;
+        keys[slot] = qm_ext_sort_key(t.qlen, t.tlen, t.h0);
         atomicAdd(&s_class[qm_ext_class(t.qlen)], 1);
-        atomicAdd(&s_hist[t.qlen], 1);
         score = t.h0 + t.qlen * o.a;
         s.task = slot;
     }
@@ -720,46 +716,7 @@ advance_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int str
         if (lane == 0 && v) atomicAdd(cells, v);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) if (s_hist[i]) atomicAdd(&ctr->hist[i], s_hist[i]);
     if (threadIdx.x < kExtCtr && s_class[threadIdx.x]) atomicAdd(&ctr->class_count[threadIdx.x], s_class[threadIdx.x]);
-}
-
-// Counting sort of a round's tasks by query length into the per-class lists: warp-mates of the thread-per-task
-// extension kernel then run rows of similar length and finish at similar times.
-__global__ void __launch_bounds__(512) sort_offsets_kernel(RoundCounters *__restrict__ ctr)
-{
-    __shared__ int s_h[512];
-    const int q = threadIdx.x;
-    s_h[q] = ctr->hist[q];
-    __syncthreads();
-    // exclusive prefix of hist[] restricted to the query lengths of q's own class (classes are contiguous ranges)
-    const int c = qm_ext_class(q);
-    int acc = 0;
-    for (int k = q - 1; k >= 0 && qm_ext_class(k) == c; --k) acc += s_h[k];
-    ctr->offs[q] = acc;
-}
-
-// Counting-sort scatter by query length.  One global atomic per task on ~120 hot addresses was all this kernel did (measured:
-// 0.2 ms per launch at 0.5 % of the issue slots, every warp waiting for its atomic to come back); now a block of 1024 tasks
-// ranks itself in shared memory and reserves one range per query length it holds.
-constexpr int kScatT = 1024;
-__global__ void __launch_bounds__(kScatT)
-sort_scatter_kernel(const ExtTaskI *__restrict__ tasks, RoundCounters *__restrict__ ctr, int *__restrict__ lists, int64_t list_stride)
-{
-    __shared__ int s_cnt[512];
-    for (int b = threadIdx.x; b < 512; b += kScatT) s_cnt[b] = 0;
-    __syncthreads();
-    const int i = blockIdx.x * kScatT + threadIdx.x;
-    const bool live = i < ctr->n_tasks;
-    int q = 0, rank = 0;
-    if (live) { q = tasks[i].qlen; rank = atomicAdd(&s_cnt[q], 1); }
-    __syncthreads();
-    if (threadIdx.x < 512) {
-        const int c = s_cnt[threadIdx.x];
-        s_cnt[threadIdx.x] = c ? atomicAdd(&ctr->offs[threadIdx.x], c) : 0;      // count -> the block's base in that bin
-    }
-    __syncthreads();
-    if (live) lists[(int64_t)qm_ext_class(q) * list_stride + s_cnt[q] + rank] = i;
 }
 
 // ---- tail: the reads still active after the bulk rounds (reads with many chains, up to 2 x QM_MAX_REGS dependent
@@ -851,7 +808,7 @@ constexpr int64_t kSeBatch = 1 << 22;         // a round with fewer tasks hands 
 
 struct SeScratch {
     qm_seed *seeds; int32_t *n_seeds; uint16_t *plan; uint8_t *n_plan; ReadState *st;
-    ExtTaskI *tasks; qm_ext_result *res; int *lists; RoundCounters *ctr; RoundCounters *h_ctr;
+    ExtTaskI *tasks; qm_ext_result *res; int *lists; uint64_t *keys; RoundCounters *ctr; RoundCounters *h_ctr;
 };
 
 int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
@@ -865,7 +822,8 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     const size_t o_st = take((size_t)nb * sizeof(ReadState));
     const size_t o_tasks = take((size_t)(nb + kTailMinTasks) * sizeof(ExtTaskI));       // + the tail kernel's parked tasks
     const size_t o_res = take((size_t)nb * sizeof(qm_ext_result));
-    const size_t o_lists = take((size_t)nb * kExtClasses * 4 * 2);      // class lists, then the fallback lists
+    const size_t o_lists = take((size_t)nb * (1 + kExtClasses) * 4);   // the round's sorted task list, then the fallback lists
+    const size_t o_keys = take((size_t)nb * 8);
     const size_t o_ctr = take(sizeof(RoundCounters));
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 3, off, &p);
@@ -873,7 +831,7 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     char *b = (char *)p;
     sc->seeds = (qm_seed *)(b + o_seeds); sc->n_seeds = (int32_t *)(b + o_ns); sc->plan = (uint16_t *)(b + o_plan);
     sc->n_plan = (uint8_t *)(b + o_np); sc->st = (ReadState *)(b + o_st); sc->tasks = (ExtTaskI *)(b + o_tasks);
-    sc->res = (qm_ext_result *)(b + o_res); sc->lists = (int *)(b + o_lists); sc->ctr = (RoundCounters *)(b + o_ctr);
+    sc->res = (qm_ext_result *)(b + o_res); sc->lists = (int *)(b + o_lists); sc->keys = (uint64_t *)(b + o_keys); sc->ctr = (RoundCounters *)(b + o_ctr);
     return QM_OK;
 }
 
@@ -943,7 +901,7 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
             cudaMemsetAsync(sc.ctr, 0, sizeof(RoundCounters), st);
             advance_kernel<<<grid, tpb, 0, st>>>(idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.plan, sc.n_plan, sc.st,
-                                                 d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.res, sc.tasks,
+                                                 d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, sc.res, sc.tasks, sc.keys,
                                                  sc.ctr, (unsigned long long *)d_cells);
             qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
             cudaMemcpyAsync(h_ctr, sc.ctr, kRoundHeader, cudaMemcpyDeviceToHost, st);
@@ -973,16 +931,21 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 qm_prof_end(ctx, QM_ST_EXTEND, sp, st, 2);
                 break;
             }
+            // The round's tasks sorted by (query length, rows, seed score): the classes become contiguous runs of one list, the
+            // two tasks a thread of the packed kernel takes are near twins (same columns, same rows, same band) and the lanes of
+            // a warp finish together.  Stable LSD radix sort of 24-bit keys (sort.cu), values = task indices.
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
-            sort_offsets_kernel<<<1, 512, 0, st>>>(sc.ctr);
-            sort_scatter_kernel<<<(unsigned)((h_ctr->n_tasks + kScatT - 1) / kScatT), kScatT, 0, st>>>(sc.tasks, sc.ctr, sc.lists, nb);
-            qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 2);
+            rc = qm_sort_pairs(ctx, sc.keys, (uint32_t *)sc.lists, h_ctr->n_tasks, kExtSortKeyBits, st);
+            qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 0);
+            if (rc) return rc;
+            int64_t list_off[kExtClasses];
+            { int64_t acc = 0; for (int c = 0; c < kExtClasses; ++c) { list_off[c] = acc; acc += h_ctr->class_count[c]; } }
             sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
             int n_launch = 0;
             for (int c = 0; c < kExtClasses; ++c) n_launch += h_ctr->class_count[c] > 0;
             rc = qm_ext_launch_classes(ctx, P, idx->v, sc.tasks, sc.lists, nb, sc.ctr->class_count, sc.ctr->class_cursor,
-                                       h_ctr->class_count, sc.res, sc.lists + (int64_t)kExtClasses * nb, sc.ctr->fb, st,
-                                       h_ctr->max_score <= 255);
+                                       h_ctr->class_count, sc.res, sc.lists + nb, sc.ctr->fb, st,
+                                       h_ctr->max_score <= 255, list_off);
             qm_prof_end(ctx, QM_ST_EXTEND, sp, st, n_launch);
             if (rc) return rc;
         }

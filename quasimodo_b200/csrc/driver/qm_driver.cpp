@@ -3,7 +3,7 @@
 // coordinate sort all run in libquasimodo_b200.so on the B200; this file is file formats and plumbing.
 //
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
-//                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf] [--gpu I] [-t THREADS] [-w BAND]
+//                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf [--vcf-gz 0]] [--gpu I | --gpus A,B,..|A-B] [-t THREADS] [-w BAND]
 //                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
 //        semantics, formatted on the device (with --rmdup 1: of the duplicate-free records, as the reference's rule reads them)
@@ -28,11 +28,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <string>
 #include <thread>
@@ -524,7 +526,7 @@ void write_bai(const std::string &path, const Genome &g, const std::vector<BamIn
     if (fclose(fp) != 0) die(2, "write error on %s", path.c_str());
 }
 
-void write_bam(const std::string &path, const Genome &g, const std::vector<Batch> &batches, const std::vector<uint32_t> &perm,
+void write_bam(const std::string &path, const Genome &g, const std::deque<Batch> &batches, const std::vector<uint32_t> &perm,
                const std::vector<int64_t> &batch_first_read, const std::string &cmdline, int threads)
 {
     BgzfWriter bw(path, threads, 1);
@@ -612,6 +614,96 @@ void write_vcf(const std::string &path, const Genome &g, const std::string &samp
     if (fclose(fp) != 0) die(2, "write error on %s", path.c_str());
 }
 
+// bgzip + tabix of a VCF (rule `bcftools`: `bgzip -c vcf > vcf.gz; tabix -p vcf vcf.gz`, rules/vcfcall.smk:118-119; the same two
+// commands close rule `genome_diff`, rules/genome_diff.smk:24-25).  The .tbi is the tabix index of the spec: BGZF-compressed,
+// format 2 (VCF: sequence column 1, begin column 2, meta char '#'), the UCSC binning of BAI with 16 kb linear windows, one
+// entry per data line covering [POS-1, POS-1 + len(REF)), sequences listed in order of first appearance, htslib's
+// pseudo-bin 37450 with the sequence's file range and record count.
+void write_vcf_gz_tbi(const std::string &vcf_path, const std::string &gz_path, int threads)
+{
+    FILE *in = fopen(vcf_path.c_str(), "r");
+    if (!in) die(2, "cannot open %s", vcf_path.c_str());
+    BgzfWriter bw(gz_path, threads, 6);
+    struct Ent { int ref; int64_t beg, end; uint64_t blk0; uint32_t off0; uint64_t blk1; uint32_t off1; };
+    std::vector<Ent> ents;
+    std::vector<std::string> names;
+    std::map<std::string, int> name_id;
+    char *line = nullptr;
+    size_t cap = 0;
+    ssize_t len;
+    while ((len = getline(&line, &cap, in)) > 0) {
+        if (line[0] != '#') {
+            const char *t1 = (const char *)memchr(line, '\t', (size_t)len);
+            const char *t2 = t1 ? (const char *)memchr(t1 + 1, '\t', (size_t)(line + len - t1 - 1)) : nullptr;
+            const char *t3 = t2 ? (const char *)memchr(t2 + 1, '\t', (size_t)(line + len - t2 - 1)) : nullptr;
+            const char *t4 = t3 ? (const char *)memchr(t3 + 1, '\t', (size_t)(line + len - t3 - 1)) : nullptr;
+            if (!t4) die(2, "%s: malformed VCF line", vcf_path.c_str());
+            const std::string chrom(line, (size_t)(t1 - line));
+            auto it = name_id.find(chrom);
+            if (it == name_id.end()) { it = name_id.emplace(chrom, (int)names.size()).first; names.push_back(chrom); }
+            Ent e;
+            e.ref = it->second;
+            e.beg = atoll(t1 + 1) - 1;
+            e.end = e.beg + std::max<int64_t>(1, (int64_t)(t4 - t3 - 1));
+            if (!ents.empty() && (e.ref < ents.back().ref || (e.ref == ents.back().ref && e.beg < ents.back().beg)))
+                die(2, "%s: records are not sorted by position: cannot index", vcf_path.c_str());
+            bw.reserve((size_t)len);
+            bw.tell(e.blk0, e.off0);
+            bw.write(line, (size_t)len);
+            bw.tell(e.blk1, e.off1);
+            ents.push_back(e);
+        } else bw.write(line, (size_t)len);
+    }
+    free(line);
+    fclose(in);
+    bw.finish();
+    std::vector<uint8_t> out;
+    auto w32 = [&](uint32_t x) { put32(out, x); };
+    auto w64 = [&](uint64_t x) { uint8_t b[8]; memcpy(b, &x, 8); out.insert(out.end(), b, b + 8); };
+    out.insert(out.end(), {'T', 'B', 'I', 1});
+    w32((uint32_t)names.size());
+    w32(2); w32(1); w32(2); w32(0); w32('#'); w32(0);
+    size_t l_nm = 0;
+    for (auto &n : names) l_nm += n.size() + 1;
+    w32((uint32_t)l_nm);
+    for (auto &n : names) { out.insert(out.end(), n.begin(), n.end()); out.push_back(0); }
+    size_t e = 0;
+    for (size_t c = 0; c < names.size(); ++c) {
+        std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+        std::vector<uint64_t> lin;
+        uint64_t off_beg = ~0ull, off_end = 0, n_rec = 0;
+        int last_bin = -1;
+        for (; e < ents.size() && ents[e].ref == (int)c; ++e) {
+            const Ent &x = ents[e];
+            const uint64_t v0 = bw.voffset(x.blk0, x.off0), v1 = bw.voffset(x.blk1, x.off1);
+            const int bin = reg2bin(x.beg, x.end);
+            auto &ch = bins[(uint32_t)bin];
+            if (last_bin == bin && !ch.empty()) ch.back().second = v1;
+            else ch.emplace_back(v0, v1);
+            last_bin = bin;
+            const size_t w0 = (size_t)(x.beg >> 14), w1 = (size_t)((x.end - 1) >> 14);
+            if (lin.size() <= w1) lin.resize(w1 + 1, ~0ull);
+            for (size_t w = w0; w <= w1; ++w) if (lin[w] == ~0ull) lin[w] = v0;
+            if (off_beg == ~0ull) off_beg = v0;
+            off_end = v1;
+            ++n_rec;
+        }
+        for (size_t w = 0; w < lin.size(); ++w) if (lin[w] == ~0ull) lin[w] = w ? lin[w - 1] : 0;
+        w32((uint32_t)bins.size() + 1);
+        for (auto &kv : bins) {
+            w32(kv.first); w32((uint32_t)kv.second.size());
+            for (auto &ch : kv.second) { w64(ch.first); w64(ch.second); }
+        }
+        w32(37450); w32(2); w64(off_beg); w64(off_end); w64(n_rec); w64(0);
+        w32((uint32_t)lin.size());
+        for (uint64_t v : lin) w64(v);
+    }
+    w64(0);                                            // n_no_coor
+    BgzfWriter tw(gz_path + ".tbi", 1, 6);
+    tw.write(out.data(), out.size());
+    tw.finish();
+}
+
 void write_fastq_pair(FILE *f1, FILE *f2, const Batch &b, int64_t pi)
 {
     const char *name = b.names.data() + b.name_off[pi];
@@ -685,9 +777,25 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     const int keep_contigs = atoi(a.get("keep-contigs", "0").c_str());
     Genome g;
     load_refs(a.get("ref"), g);
-    Lib L;
-    int rc = qm_ctx_create(atoi(a.get("gpu", "0").c_str()), &L.ctx);
-    if (rc != QM_OK) die(3, "qm_ctx_create failed (%d): no usable B200 (there is no CPU fallback)", rc);
+    // --gpus A,B,C or A-B: one context, index and sample per GPU in this one process; batches are dealt round-robin, the
+    // count tensors merged with one NCCL all-reduce (north_star).  --gpu I: the single-GPU form.
+    std::vector<int> devs;
+    if (a.has("gpus")) {
+        for (auto &tok : split(a.get("gpus"), ',')) {
+            const size_t dash = tok.find('-');
+            if (dash != std::string::npos && dash > 0) { for (int d = atoi(tok.substr(0, dash).c_str()); d <= atoi(tok.substr(dash + 1).c_str()); ++d) devs.push_back(d); }
+            else if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
+        }
+        if (devs.empty()) die(1, "--gpus: no device given");
+        if (decontam && devs.size() > 1) die(1, "decontam runs on one GPU (--gpu I)");
+    } else devs.push_back(atoi(a.get("gpu", "0").c_str()));
+    const int n_gpu = (int)devs.size();
+    std::vector<Lib> Ls((size_t)n_gpu);
+    for (int d = 0; d < n_gpu; ++d) {
+        const int rc = qm_ctx_create(devs[d], &Ls[d].ctx);
+        if (rc != QM_OK) die(3, "qm_ctx_create(%d) failed (%d): no usable B200 (there is no CPU fallback)", devs[d], rc);
+    }
+    Lib &L = Ls[0];
     qm_opt opt; qm_opt_default(&opt);
     if (a.has("w")) opt.w = atoi(a.get("w").c_str());
     if (a.has("k")) opt.min_seed_len = atoi(a.get("k").c_str());
@@ -695,21 +803,26 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     qm_pileup_opt popt; qm_pileup_opt_default(&popt);
     if (a.has("min-mapq")) popt.min_mapq = atoi(a.get("min-mapq").c_str());
     if (a.has("min-bq")) popt.min_bq = atoi(a.get("min-bq").c_str());
-    qm_index *idx = nullptr;
-    L.check(qm_index_build(L.ctx, g.codes.data(), (int)g.names.size(), g.lens.data(), opt.min_seed_len, &idx), "qm_index_build");
-    qm_sample *smp = nullptr;
-    L.check(qm_sample_begin(L.ctx, idx, &opt, &popt, &smp), "qm_sample_begin");
+    std::vector<qm_index *> idxs((size_t)n_gpu, nullptr);
+    std::vector<qm_sample *> smps((size_t)n_gpu, nullptr);
+    for (int d = 0; d < n_gpu; ++d) {
+        Ls[d].check(qm_index_build(Ls[d].ctx, g.codes.data(), (int)g.names.size(), g.lens.data(), opt.min_seed_len, &idxs[d]), "qm_index_build");
+        Ls[d].check(qm_sample_begin(Ls[d].ctx, idxs[d], &opt, &popt, &smps[d]), "qm_sample_begin");
+    }
+    qm_index *idx = idxs[0];
+    qm_sample *smp = smps[0];
 
     const bool rmdup = !decontam && atoi(a.get("rmdup", "0").c_str()) != 0;
     const std::string rmdup_bam = a.get("rmdup-bam"), metrics = a.get("metrics");
     if (!rmdup && (!rmdup_bam.empty() || !metrics.empty())) die(1, "--rmdup-bam / --metrics need --rmdup 1");
+    if (rmdup && n_gpu > 1) die(1, "--rmdup 1 needs the records of the whole sample on one device: run it with one GPU");
     if (rmdup) L.check(qm_sample_set_rmdup(smp, 1), "qm_sample_set_rmdup");
     const std::string mpileup = a.get("mpileup");
     const bool want_bam = !bam.empty() || !rmdup_bam.empty();
     const bool want_batches = want_bam || !mpileup.empty();
     const bool keep = want_batches || decontam;       // records / reads needed after the batch loop
     FastqPairReader fr(a.get("r1"), a.get("r2"));
-    std::vector<Batch> batches;
+    std::deque<Batch> batches;                        // (a deque: the workers hold references while more batches arrive)
     std::vector<int64_t> first_read;
     std::vector<RawPair> raw;
     int64_t n_pairs = 0, kept = 0;
@@ -718,11 +831,39 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         f1 = fopen(o1.c_str(), "w"); f2 = fopen(o2.c_str(), "w");
         if (!f1 || !f2) die(2, "cannot create %s / %s", o1.c_str(), o2.c_str());
     }
+    // one host thread per GPU (a context is not thread-safe, distinct contexts are independent); worker d holds at most one batch
+    std::vector<std::thread> workers((size_t)n_gpu);
+    std::vector<Batch *> in_flight((size_t)n_gpu, nullptr);
+    auto join_worker = [&](int d) {
+        if (workers[d].joinable()) workers[d].join();
+        if (in_flight[d] && !want_batches) { free_batch(Ls[d], *in_flight[d]); }
+        in_flight[d] = nullptr;
+    };
+    int64_t n_batches = 0;
+    const auto t_loop = std::chrono::steady_clock::now();
     while (read_batch(fr, batch_pairs, raw)) {
-        Batch b;
-        pack_batch(L, raw, keep, b);
+        const int d = (int)(n_batches % n_gpu);
+        join_worker(d);
+        batches.emplace_back();
+        Batch &b = batches.back();
+        pack_batch(Ls[d], raw, keep, b);
         raw.clear();
-        L.check(qm_sample_add_pairs_host(smp, b.codes, b.quals, b.stride, b.lens, b.n_pairs, n_pairs, b.alns), "qm_sample_add_pairs_host");
+        const int64_t pair0 = n_pairs;
+        if (n_batches == 0 || n_gpu == 1) {
+            // the first batch fixes the sample's insert-size model (its first QM_PESTAT_PAIRS pairs): every GPU gets that model
+            // before it sees a batch of its own, so the records do not depend on the number of GPUs
+            L.check(qm_sample_add_pairs_host(smp, b.codes, b.quals, b.stride, b.lens, b.n_pairs, pair0, b.alns), "qm_sample_add_pairs_host");
+            if (n_gpu > 1) {
+                qm_pestat pes[4];
+                L.check(qm_sample_get_pestat(smp, pes), "qm_sample_get_pestat");
+                for (int e = 1; e < n_gpu; ++e) Ls[e].check(qm_sample_set_pestat(smps[e], pes), "qm_sample_set_pestat");
+            }
+        } else {
+            in_flight[d] = &b;
+            workers[d] = std::thread([&Ls, &smps, d, &b, pair0]() {
+                Ls[d].check(qm_sample_add_pairs_host(smps[d], b.codes, b.quals, b.stride, b.lens, b.n_pairs, pair0, b.alns), "qm_sample_add_pairs_host");
+            });
+        }
         if (decontam) {
             for (int64_t p = 0; p < b.n_pairs; ++p) {
                 const qm_aln &x = b.alns[2 * p], &y = b.alns[2 * p + 1];
@@ -736,16 +877,45 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         }
         first_read.push_back(2 * n_pairs);
         n_pairs += b.n_pairs;
-        if (want_batches) batches.push_back(std::move(b));
-        else free_batch(L, b);
+        ++n_batches;
+        if (!want_batches && in_flight[d] == nullptr) { free_batch(Ls[d], b); }
+        if (!want_batches && n_gpu == 1) batches.pop_back();
     }
+    for (int d = 0; d < n_gpu; ++d) join_worker(d);
+    const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
     if (decontam) {
         if (fclose(f1) != 0 || fclose(f2) != 0) die(2, "write error on the cleaned FASTQ files");
         fprintf(stderr, "[qm_driver] decontam: %lld of %lld pairs kept\n", (long long)kept, (long long)n_pairs);
     }
     int64_t cells = 0;
-    L.check(qm_sample_stats_sync(smp, nullptr, &cells, nullptr), "qm_sample_stats_sync");
+    for (int d = 0; d < n_gpu; ++d) {
+        int64_t c = 0;
+        Ls[d].check(qm_sample_stats_sync(smps[d], nullptr, &c, nullptr), "qm_sample_stats_sync");
+        cells += c;
+    }
     fprintf(stderr, "[qm_driver] %lld pairs aligned, %lld extension cells\n", (long long)n_pairs, (long long)cells);
+    fprintf(stderr, "[qm_driver] %d GPU(s), %lld batch(es): %.2f s from the first read to the last record, %.3f M pairs/s, %.1f G extension cells/s "
+                    "(FASTQ parsing included)\n", n_gpu, (long long)n_batches, loop_s, loop_s > 0 ? n_pairs / loop_s / 1e6 : 0.0,
+            loop_s > 0 ? cells / loop_s / 1e9 : 0.0);
+    if (n_gpu > 1) {
+        // per-GPU int32 count tensors -> one NCCL all-reduce over NVLink; every GPU ends up with the sample's totals
+        std::vector<qm_ctx *> ctxs;
+        for (auto &x : Ls) ctxs.push_back(x.ctx);
+        std::vector<qm_comm *> comms((size_t)n_gpu, nullptr);
+        L.check(qm_comm_init_all(n_gpu, ctxs.data(), comms.data()), "qm_comm_init_all");
+        std::vector<std::thread> team;
+        for (int d = 0; d < n_gpu; ++d)
+            team.emplace_back([&, d]() {
+                Ls[d].check(qm_sample_set_comm(smps[d], nullptr), "qm_sample_set_comm");
+                Ls[d].check(qm_counts_allreduce(Ls[d].ctx, comms[d], qm_sample_counts(smps[d]), (int64_t)QM_NCH * (int64_t)g.codes.size(), nullptr),
+                            "qm_counts_allreduce");
+                Ls[d].check(qm_sample_stats_sync(smps[d], nullptr, nullptr, nullptr), "qm_sample_stats_sync");
+            });
+        for (auto &t : team) t.join();
+        for (auto c : comms) qm_comm_destroy(c);
+        fprintf(stderr, "[qm_driver] count tensors of %d GPUs merged (ncclAllReduce, int32 sum, %lld values)\n", n_gpu,
+                (long long)QM_NCH * (long long)g.codes.size());
+    }
     if (rmdup) {
         int64_t n_dup = 0;
         L.check(qm_sample_rmdup_finish(smp, &n_dup, nullptr), "qm_sample_rmdup_finish");
@@ -781,6 +951,8 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         L.check(qm_sample_call_snps_host(smp, &copt, calls.data(), (int64_t)calls.size(), &nc), "qm_sample_call_snps_host");
         calls.resize((size_t)nc);
         write_vcf(vcf, g, a.get("sample", "sample"), split(a.get("ref"), ',')[0], calls);
+        // rule `bcftools` declares vcf_bgz = vcf + ".gz" and tabix-indexes it (rules/vcfcall.smk:107,118-119): written unless --vcf-gz 0
+        if (atoi(a.get("vcf-gz", "1").c_str())) write_vcf_gz_tbi(vcf, vcf + ".gz", threads);
     }
     if (!mpileup.empty()) {
         // text pileup (samtools mpileup format) of the whole sample: records, reads and qualities go to the device once more,
@@ -833,9 +1005,11 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         }
     }
     for (auto &b : batches) free_batch(L, b);
-    qm_sample_destroy(smp);
-    qm_index_destroy(L.ctx, idx);
-    qm_ctx_destroy(L.ctx);
+    for (int d = 0; d < n_gpu; ++d) {
+        qm_sample_destroy(smps[d]);
+        qm_index_destroy(Ls[d].ctx, idxs[d]);
+        qm_ctx_destroy(Ls[d].ctx);
+    }
     return 0;
 }
 
@@ -900,7 +1074,7 @@ int cmd_bam_from_records(const Args &a, const std::string &cmdline)
         qm_ctx_destroy(L.ctx);
     }
     if (perm.size() != alns.size()) die(2, "permutation of %zu entries for %zu records", perm.size(), alns.size());
-    std::vector<Batch> batches;
+    std::deque<Batch> batches;
     batches.push_back(b);
     write_bam(a.get("bam"), g, batches, perm, {0}, cmdline, std::max(1, atoi(a.get("t", "2").c_str())));
     return 0;
@@ -910,7 +1084,7 @@ int cmd_bam_from_records(const Args &a, const std::string &cmdline)
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records [options]   (%s)", qm_version());
+    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records|vcf-index [options]   (%s)", qm_version());
     std::string cmdline;
     for (int i = 0; i < argc; ++i) { if (i) cmdline += ' '; cmdline += argv[i]; }
     const std::string cmd = argv[1];
@@ -918,5 +1092,10 @@ int main(int argc, char **argv)
     if (cmd == "sample") return cmd_sample(a, cmdline, false);
     if (cmd == "decontam") return cmd_sample(a, cmdline, true);
     if (cmd == "bam-from-records") return cmd_bam_from_records(a, cmdline);
+    if (cmd == "vcf-index") {                          // bgzip -c X > X.gz; tabix -p vcf X.gz  (host only: rules/vcfcall.smk:118-119, rules/genome_diff.smk:24-25)
+        if (!a.has("vcf")) die(1, "--vcf is required");
+        write_vcf_gz_tbi(a.get("vcf"), a.get("out", a.get("vcf") + ".gz"), std::max(1, atoi(a.get("t", "2").c_str())));
+        return 0;
+    }
     die(1, "unknown command '%s'", cmd.c_str());
 }

@@ -22,7 +22,7 @@
 // band retry: the two tasks are independent in everything but the shared instruction stream.
 //
 // Shared memory per thread and column: one 64-bit word {h2, e2} = the reference's eh[j] of both tasks, and one 32-bit word
-// with the two query codes.  Layout [column][thread]: a warp's accesses hit consecutive banks whatever column each lane is at.
+// with the two query codes (kE3Pad extra columns behind the query plane: the row loop fetches one trip ahead).  Layout [column][thread]: a warp's accesses hit consecutive banks whatever column each lane is at.
 //
 // Limits (the launcher sends everything else to the scalar kernel of extend2.cu): scores <= 255 and columns <= 256 (the
 // packed key), 1 <= a <= 127, 1 <= b, a + b <= 256, gap penalties < 2^14.
@@ -75,7 +75,17 @@ E3_HD unsigned e3_umax3(unsigned a, unsigned b, unsigned c) { return e3_umax(e3_
 E3_HD unsigned e3_uaddmax(unsigned a, unsigned b, unsigned c) { using namespace e3emu; return umx((ulo(a) + ulo(b)) & 0xffffu, ulo(c)) | umx((uhi(a) + uhi(b)) & 0xffffu, uhi(c)) << 16; }
 #endif
 
+// host-side instrumentation of the test build (tests/ext3_host.cpp -DE3_STATS): where the columns go
+#if defined(E3_STATS) && !defined(__CUDA_ARCH__)
+struct E3Stats { long long rows, core_cols, masked_cols, solo_rows; int last_pre, last_core, last_post; };
+extern E3Stats g_e3_stats;
+#define E3_COUNT(field, n) (g_e3_stats.field += (n))
+#else
+#define E3_COUNT(field, n) ((void)0)
+#endif
+
 E3_HD unsigned e3_pack2(int v) { return ((unsigned)v & 0xffffu) * 0x10001u; }
+constexpr int kE3Pad = 4;                         // columns the one-trip-ahead fetch may read past a range
 constexpr unsigned kE3Neg = 0x80008000u;         // -32768 | -32768: the neutral third operand of max(a + b, c)
 
 struct E3Scores { int a, b, o_del, e_del, o_ins, e_ins, zdrop; };
@@ -230,10 +240,19 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         f2 = e3_addmax(f2, K.nei2, SYM ? td : e3_addmax_relu(M2, K.noe_ins2, kE3Neg));                                \
     }
     // ---- columns only one task visits before the common range ----
-    const int cs = cbA > cbB ? cbA : cbB;
+    // Left of its beg a task only has cells the zero-span trimming dropped (h = e = 0, untouched since): running the cell on
+    // them writes the same zeros back, so the task whose range starts later simply starts with its partner -- as long as the
+    // columns are inside its band (a column the BAND cut off keeps a non-zero stale value and must stay untouched).  The
+    // executed-cell count and the trimming still use the task's own beg.  The right edge has no such freedom: past end the
+    // reference drops insertion tails that the cell would carry on.
+    int cs = cbA < cbB ? cbA : cbB;
+    if (ra) { const int z = A.i - A.w; cs = cs > z ? cs : z; }
+    if (rb) { const int z = B.i - B.w; cs = cs > z ? cs : z; }
     int ce = ceA < ceB ? ceA : ceB;
     ce = ce > cs ? ce : cs;
     auto masked = [&](int j0, int j1, unsigned mask) {
+        E3_COUNT(masked_cols, j1 > j0 ? j1 - j0 : 0);
+        E3_COUNT(last_pre, j1 > j0 ? j1 - j0 : 0);            /* columns before + after the common range, this row */
         for (int j = j0; j < j1; ++j) {
             uint2 &p = mem.eh(j);
             const uint2 he = p;
@@ -253,31 +272,47 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         if (begA < cs) masked(begA, endA < cs ? endA : cs, 0x0000ffffu);
         else if (begB < cs) masked(begB, endB < cs ? endB : cs, 0xffff0000u);
     }
-    // ---- the common range: both tasks per instruction, four columns per trip ----
+    // ---- the common range: both tasks per instruction, four columns per trip.  The next trip's eight shared-memory words are
+    // fetched before this trip's arithmetic starts: a thread's columns are private, so nothing written here can change them,
+    // and with only a few warps per scheduler the loads have to be in flight early.  (The fetch may run up to four columns
+    // past the range: the planes are padded, the values unused.) ----
     {
+        E3_COUNT(rows, 1); E3_COUNT(core_cols, ce - cs); E3_COUNT(solo_rows, (ra && rb) ? 0 : 1); E3_COUNT(last_core, ce - cs);
         int j = cs;
         unsigned jb = e3_pack2(cs);
-        for (; j + 3 < ce; j += 4) {
-            unsigned k0, k1, k2, k3;
-#define E3_STEP(U, KU)                                                                       \
+#define E3_STEP(JJ, HE, Q2, U, KU)                                                           \
             {                                                                                \
-                uint2 &p = mem.eh(j + (U));                                                  \
-                const uint2 he = p;                                                          \
                 unsigned Hn, En;                                                             \
-                E3_CELL(j + (U), he, mem.q(j + (U)), h1, Hn, En)                             \
-                p = make_uint2(h1, En);                                                      \
+                E3_CELL(JJ, HE, Q2, h1, Hn, En)                                              \
+                mem.eh(JJ) = make_uint2(h1, En);                                             \
                 h1 = Hn;                                                                     \
                 KU = Hn * 256u + (unsigned)((U) * 0x10001);                                  \
             }
-            E3_STEP(0, k0) E3_STEP(1, k1) E3_STEP(2, k2) E3_STEP(3, k3)
-            bkey = e3_uaddmax(e3_umax(e3_umax3(k0, k1, k2), k3), jb, bkey);
-            jb += 0x00040004u;
-        }
-        for (; j < ce; ++j) {
-            unsigned k0;
-            E3_STEP(0, k0)
-            bkey = e3_uaddmax(k0, jb, bkey);
-            jb += 0x00010001u;
+        if (j + 3 < ce) {
+            uint2 a0 = mem.eh(j), a1 = mem.eh(j + 1), a2 = mem.eh(j + 2), a3 = mem.eh(j + 3);
+            unsigned b0 = mem.q(j), b1 = mem.q(j + 1), b2 = mem.q(j + 2), b3 = mem.q(j + 3);
+            do {
+                const uint2 n0 = mem.eh(j + 4), n1 = mem.eh(j + 5), n2 = mem.eh(j + 6), n3 = mem.eh(j + 7);
+                const unsigned m0 = mem.q(j + 4), m1 = mem.q(j + 5), m2 = mem.q(j + 6), m3 = mem.q(j + 7);
+                unsigned k0, k1, k2, k3;
+                E3_STEP(j, a0, b0, 0, k0) E3_STEP(j + 1, a1, b1, 1, k1) E3_STEP(j + 2, a2, b2, 2, k2) E3_STEP(j + 3, a3, b3, 3, k3)
+                bkey = e3_uaddmax(e3_umax(e3_umax3(k0, k1, k2), k3), jb, bkey);
+                jb += 0x00040004u;
+                j += 4;
+                a0 = n0; a1 = n1; a2 = n2; a3 = n3; b0 = m0; b1 = m1; b2 = m2; b3 = m3;
+            } while (j + 3 < ce);
+            // up to three columns left, already in registers
+            if (j < ce) { unsigned k0; E3_STEP(j, a0, b0, 0, k0) bkey = e3_uaddmax(k0, jb, bkey); }
+            if (j + 1 < ce) { unsigned k0; E3_STEP(j + 1, a1, b1, 1, k0) bkey = e3_uaddmax(k0, jb, bkey); }
+            if (j + 2 < ce) { unsigned k0; E3_STEP(j + 2, a2, b2, 2, k0) bkey = e3_uaddmax(k0, jb, bkey); }
+        } else {
+            for (; j < ce; ++j) {
+                const uint2 he = mem.eh(j);
+                unsigned k0;
+                E3_STEP(j, he, mem.q(j), 0, k0)
+                bkey = e3_uaddmax(k0, jb, bkey);
+                jb += 0x00010001u;
+            }
         }
 #undef E3_STEP
     }

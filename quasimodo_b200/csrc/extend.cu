@@ -82,8 +82,8 @@ ext_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const i
 }
 
 template <int C>
-void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
-                  int64_t list_stride, const int *d_counts, int *d_cursors, const int *h_counts, qm_ext_result *d_out,
+void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_list,
+                  const int *d_counts, int *d_cursors, const int *h_counts, qm_ext_result *d_out,
                   cudaStream_t st)
 {
     int64_t warps = (int64_t)ctx->sm_count * 64;          // persistent: up to 16 blocks of 4 warps per SM
@@ -93,7 +93,7 @@ void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, 
     }
     unsigned blocks = (unsigned)((warps + 3) / 4);
     if (blocks > (unsigned)ctx->sm_count) blocks = ((blocks + ctx->sm_count - 1) / ctx->sm_count) * ctx->sm_count;
-    ext_kernel<C><<<blocks, 128, 0, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
+    ext_kernel<C><<<blocks, 128, 0, st>>>(P, V, d_tasks, d_list, d_counts + cls, d_cursors + cls, d_out);
 }
 
 }  // namespace
@@ -101,7 +101,7 @@ void launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, 
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
                           const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st,
-                          bool scores_fit_bytes)
+                          bool scores_fit_bytes, const int64_t *h_list_off)
 {
     // A class with many tasks goes to the thread-per-task kernel (extend2.cu: high throughput, but one task is a
     // long serial chain, ~0.3 ms); a class with few tasks (the tail rounds of mem_chain2aln, where only reads with
@@ -113,6 +113,8 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
         if (h_counts && h_counts[c] == 0) continue;
         cudaStream_t sc = ctx->side[c];
         QM_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_fork, 0));
+        const int *lst = h_list_off ? d_lists + h_list_off[c] : d_lists + c * list_stride;
+        int *fbl = d_fb_lists ? d_fb_lists + c * list_stride : nullptr;
         static const int tpt_min = getenv("QM_TPT_MIN") ? atoi(getenv("QM_TPT_MIN")) : kThreadPerTaskMin;      // tuning knob
         const bool big = c < 9 && (!h_counts || h_counts[c] >= tpt_min);
         // The packed two-tasks-per-thread kernel (extend3.cu) takes every class it can hold; QM_EXT3=0 keeps the scalar
@@ -120,31 +122,31 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
         static const bool ext3 = !(getenv("QM_EXT3") && atoi(getenv("QM_EXT3")) == 0);
         if (big && d_fb_lists && d_fb_ctr && ext3 && qm_ext3_scores_ok(P)) {
             const int hc = h_counts ? h_counts[c] : -1;
-            int rc = qm_ext3_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, hc, d_out, d_fb_lists, d_fb_ctr, sc);
+            int rc = qm_ext3_launch_class(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, hc, d_out, fbl, d_fb_ctr, sc);
             if (rc) return rc;
             // what the packed arithmetic cannot hold (scores above 255) comes back through the fallback list; the caller
             // that knows the round's maximum score (scores_fit_bytes) knows the list stays empty
             if (!scores_fit_bytes) {
                 switch (c) {
-                case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-                case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-                case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-                case 6: case 7: launch_class<5>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
-                default: launch_class<9>(ctx, c, P, V, d_tasks, d_fb_lists, list_stride, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, fbl, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, fbl, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, fbl, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                case 6: case 7: launch_class<5>(ctx, c, P, V, d_tasks, fbl, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
+                default: launch_class<9>(ctx, c, P, V, d_tasks, fbl, d_fb_ctr, d_fb_ctr + kExtCtr, nullptr, d_out, sc); break;
                 }
             }
         } else if (big) {
-            int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc,
+            int rc = qm_ext2_launch_class(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts ? h_counts[c] : -1, d_out, sc,
                                           scores_fit_bytes);
             if (rc) return rc;
         } else {
             switch (c) {
-            case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
-            case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
-            case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
-            case 6: case 7: launch_class<5>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
-            case 8: launch_class<9>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
-            default: launch_class<16>(ctx, c, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 0: case 1: launch_class<2>(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 2: case 3: launch_class<3>(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 4: case 5: launch_class<4>(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 6: case 7: launch_class<5>(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts, d_out, sc); break;
+            case 8: launch_class<9>(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts, d_out, sc); break;
+            default: launch_class<16>(ctx, c, P, V, d_tasks, lst, d_counts, d_cursors, h_counts, d_out, sc); break;
             }
         }
         QM_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], sc));

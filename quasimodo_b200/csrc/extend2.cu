@@ -250,8 +250,8 @@ ext2_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
 }
 
 template <int CAP, bool BYTES>
-void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
-             int64_t list_stride, const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, cudaStream_t st)
+void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_list,
+             const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, cudaStream_t st)
 {
     const size_t smem = (size_t)(BYTES ? 2 : 3) * (CAP / 2 + 1) * kT * 2 * 2;
     static bool attr_set = false;
@@ -271,18 +271,18 @@ void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
     if (blocks < 1) return;
     // SYM = the standard scheme: equal gap costs (one subtraction serves E and F) and match score 1 (see QM_CELL)
     const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins && P.a == 1;
-    if (sym) ext2_kernel<CAP, true, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
-    else ext2_kernel<CAP, false, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_lists + cls * list_stride, d_counts + cls, d_cursors + cls, d_out);
+    if (sym) ext2_kernel<CAP, true, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_list, d_counts + cls, d_cursors + cls, d_out);
+    else ext2_kernel<CAP, false, BYTES><<<(unsigned)blocks, kT, smem, st>>>(P, V, d_tasks, d_list, d_counts + cls, d_cursors + cls, d_out);
 }
 
 }  // namespace
 
 int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
-                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
+                         const int *d_list, const int *d_counts, int *d_cursors, int h_count,
                          qm_ext_result *d_out, cudaStream_t st, bool bytes)
 {
-#define QM_L2(CAPV) { if (bytes) launch2<CAPV, true>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); \
-                      else launch2<CAPV, false>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, st); }
+#define QM_L2(CAPV) { if (bytes) launch2<CAPV, true>(ctx, cls, P, V, d_tasks, d_list, d_counts, d_cursors, h_count, d_out, st); \
+                      else launch2<CAPV, false>(ctx, cls, P, V, d_tasks, d_list, d_counts, d_cursors, h_count, d_out, st); }
     switch (cls) {
     case 0: QM_L2(16) break;
     case 1: QM_L2(32) break;

@@ -24,16 +24,22 @@ struct SmemPlanes {                         // this thread's columns: word j of 
     __device__ __forceinline__ uint16_t &q16(int j, int X) { return ((uint16_t *)&qp[j * KT])[X]; }
 };
 
-struct DevTgt {                             // where the two tasks' target rows come from
-    const IndexView *V;
-    const uint8_t *t[2];
-    int64_t t0[2];
-    int tstep[2];
-    bool indirect[2];
+struct DevTgt {                             // where the two tasks' target rows come from: base of row i = p[i * step] ^ flip
+    const uint8_t *p[2];
+    int step[2];
+    int flip[2];                            // 3 on the reverse-complement strand of the doubled coordinates, else 0
     __device__ __forceinline__ int base(int X, int i) const
     {
-        const int c = indirect[X] ? qm_ref_base(*V, t0[X] + (int64_t)i * tstep[X]) : t[X][i];
+        const int c = p[X][(int64_t)i * step[X]] ^ flip[X];
         return c > 4 ? 4 : c;
+    }
+    // a task's window never crosses the strand boundary (mem_chain2aln clamps rmax[] to one strand), so the strand test of
+    // qm_ref_base is made once per task instead of once per row
+    __device__ __forceinline__ void set(int X, const IndexView &V, const ExtTaskI &t)
+    {
+        if (!(t.flags & QM_EXTI_INDIRECT)) { p[X] = t.t; step[X] = 1; flip[X] = 0; }
+        else if (t.t0 < V.l_pac) { p[X] = V.refb + t.t0; step[X] = t.tstep; flip[X] = 0; }
+        else { p[X] = V.refb + (2 * V.l_pac - 1 - t.t0); step[X] = -t.tstep; flip[X] = 3; }
     }
 };
 
@@ -55,15 +61,14 @@ ext3_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
     mem.qp = (uint32_t *)(smem_u2 + (CAP + 1) * KT) + threadIdx.x;
     // dead storage must hold small non-negative values (a half without a task rides along on its partner's columns)
     for (int j = 0; j <= CAP; ++j) mem.eh(j) = make_uint2(0u, 0u);
-    for (int j = 0; j < CAP; ++j) mem.q(j) = 0u;
+    for (int j = 0; j < CAP + kE3Pad; ++j) mem.q(j) = 0u;
     const E3Scores S = {P.a, P.b, P.o_del, P.e_del, P.o_ins, P.e_ins, P.zdrop};
     const E3Consts K = e3_consts(S);
     const int n = *count;
     E3Half A, B;
     A.tk = B.tk = -1; A.phase = B.phase = 0;
     DevTgt tgt;
-    tgt.V = &V;
-    tgt.t[0] = tgt.t[1] = nullptr; tgt.t0[0] = tgt.t0[1] = 0; tgt.tstep[0] = tgt.tstep[1] = 0; tgt.indirect[0] = tgt.indirect[1] = false;
+    tgt.p[0] = tgt.p[1] = nullptr; tgt.step[0] = tgt.step[1] = 0; tgt.flip[0] = tgt.flip[1] = 0;
 
     auto load = [&](E3Half &H, int X, int tk) {
         const ExtTaskI t = tasks[tk];
@@ -73,7 +78,7 @@ ext3_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
         H.tries_left = (t.flags & QM_EXT_BAND_RETRY) ? 2 : 1;
         H.prev = (t.flags & QM_EXT_PREV_H0) ? t.h0 : -1;
         H.cells = 0;
-        tgt.t[X] = t.t; tgt.t0[X] = t.t0; tgt.tstep[X] = t.tstep; tgt.indirect[X] = (t.flags & QM_EXTI_INDIRECT) != 0;
+        tgt.set(X, V, t);
         DevQry qry = {t.q, t.qstep};
         e3_load_query(K, t.qlen, X, mem, qry);
     };
@@ -118,11 +123,11 @@ ext3_kernel(ExtParams P, IndexView V, const ExtTaskI *__restrict__ tasks, const 
 }
 
 template <int CAP, int KT>
-void launch3(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *d_lists,
-             int64_t list_stride, const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, int *d_fb_lists,
+void launch3(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks, const int *list,
+             const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, int *fb,
              int *d_fb_ctr, cudaStream_t st)
 {
-    const size_t smem = (size_t)KT * ((CAP + 1) * 8 + CAP * 4);
+    const size_t smem = (size_t)KT * ((CAP + 1) * 8 + (CAP + kE3Pad) * 4);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(ext3_kernel<CAP, KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -139,8 +144,6 @@ void launch3(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
     }
     if (blocks < 1) return;
     const bool sym = P.o_del == P.o_ins && P.e_del == P.e_ins && P.a == 1;
-    const int *list = d_lists + cls * list_stride;
-    int *fb = d_fb_lists + cls * list_stride;
     if (sym) ext3_kernel<CAP, KT, true><<<(unsigned)blocks, KT, smem, st>>>(P, V, d_tasks, list, d_counts + cls, d_cursors + cls, d_out, fb, d_fb_ctr + cls);
     else ext3_kernel<CAP, KT, false><<<(unsigned)blocks, KT, smem, st>>>(P, V, d_tasks, list, d_counts + cls, d_cursors + cls, d_out, fb, d_fb_ctr + cls);
 }
@@ -153,13 +156,13 @@ bool qm_ext3_scores_ok(const ExtParams &P)
     return e3_scores_ok(S);
 }
 
-// one class (0..8) on the packed kernel; tasks it cannot hold (scores above 255) are appended to the class's fallback list
-// d_fb_lists[cls][.] (count d_fb_ctr[cls]) for the scalar kernel.  h_count < 0: unknown on the host.
+// one class (0..8) on the packed kernel (d_list = the class's task indices); tasks it cannot hold (scores above 255) are
+// appended to the class's fallback list d_fb_list (count d_fb_ctr[cls]) for the scalar kernel.  h_count < 0: unknown on the host.
 int qm_ext3_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
-                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
-                         qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st)
+                         const int *d_list, const int *d_counts, int *d_cursors, int h_count,
+                         qm_ext_result *d_out, int *d_fb_list, int *d_fb_ctr, cudaStream_t st)
 {
-#define QM_L3(CAPV, KTV) launch3<CAPV, KTV>(ctx, cls, P, V, d_tasks, d_lists, list_stride, d_counts, d_cursors, h_count, d_out, d_fb_lists, d_fb_ctr, st)
+#define QM_L3(CAPV, KTV) launch3<CAPV, KTV>(ctx, cls, P, V, d_tasks, d_list, d_counts, d_cursors, h_count, d_out, d_fb_list, d_fb_ctr, st)
     switch (cls) {
     case 0: QM_L3(16, 64); break;
     case 1: QM_L3(32, 64); break;

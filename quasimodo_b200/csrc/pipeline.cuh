@@ -143,22 +143,32 @@ static __host__ __device__ __forceinline__ int qm_ext_class(int qlen)
     return qlen <= 128 ? (qlen <= 0 ? 0 : (qlen - 1) >> 4) : qlen <= 256 ? 8 : 9;
 }
 
-// Launch the per-class extension kernels.  lists: [kExtClasses][list_stride] task indices; h_counts may be
+// sort key of a round's extension tasks: query length (9 bits: the classes are ranges of it), rows / 4 (8 bits), seed score / 2
+// (7 bits) -- tasks that agree in all three run the same rectangle of cells
+constexpr int kExtSortKeyBits = 24;
+static __host__ __device__ __forceinline__ uint64_t qm_ext_sort_key(int qlen, int tlen, int h0)
+{
+    const int q = qlen < 0 ? 0 : qlen > 511 ? 511 : qlen, t = tlen < 0 ? 0 : (tlen >> 2) > 255 ? 255 : tlen >> 2, h = h0 < 0 ? 0 : (h0 >> 1) > 127 ? 127 : h0 >> 1;
+    return (uint64_t)q << 15 | (uint64_t)t << 7 | (uint64_t)h;
+}
+
+// Launch the per-class extension kernels.  lists: [kExtClasses][list_stride] task indices, or (h_list_off given) ONE array in
+// which class c starts at h_list_off[c] (the round's tasks sorted by query length, rows and seed score); h_counts may be
 // NULL (unknown on the host: persistent grids sized for the SM count) or the 5 class counts.
 // one class (0..8) on the thread-per-task kernel; h_count < 0: unknown on the host
 // bytes: the caller guarantees h0 + qlen*a <= 255 for every task of the list (eh[] held in bytes, see extend2.cu)
 int qm_ext2_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
-                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
+                         const int *d_list, const int *d_counts, int *d_cursors, int h_count,
                          qm_ext_result *d_out, cudaStream_t st, bool bytes = false);
 // two tasks per thread in the halves of s16x2 words (extend3.cu), classes 0..8; tasks it cannot hold (scores above 255) are
 // appended to the class's fallback list d_fb_lists[cls][.] (count d_fb_ctr[cls]) for a scalar kernel
 bool qm_ext3_scores_ok(const ExtParams &P);
 int qm_ext3_launch_class(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
-                         const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors, int h_count,
-                         qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st);
+                         const int *d_list, const int *d_counts, int *d_cursors, int h_count,
+                         qm_ext_result *d_out, int *d_fb_list, int *d_fb_ctr, cudaStream_t st);
 // d_fb_lists: [kExtClasses][list_stride] ints, d_fb_ctr: 2 * kExtCtr ints zeroed by the caller (fallback counts,
 // then fallback cursors); both NULL: the paired kernel is not used
 int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, const ExtTaskI *d_tasks,
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
                           const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st,
-                          bool scores_fit_bytes = false);
+                          bool scores_fit_bytes = false, const int64_t *h_list_off = nullptr);

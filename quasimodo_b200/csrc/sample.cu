@@ -381,6 +381,7 @@ int qm_sample_stats_sync(qm_sample *s, int64_t *n_pairs, int64_t *cells, void *s
     if (!s) return QM_EINVAL;
     qm_ctx *ctx = s->ctx;
     int64_t c = 0;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
     QM_CUDA(ctx, cudaMemcpyAsync(&c, s->d_cells, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     if (n_pairs) *n_pairs = s->n_pairs;

@@ -110,3 +110,81 @@ def read_bai(path):
         refs.append((bins, lin))
     n_no_coor = struct.unpack_from("<Q", d, p)[0] if p + 8 <= len(d) else None
     return refs, n_no_coor
+
+
+def read_tbi(path):
+    """tabix index -> dict(format, col_seq, col_beg, col_end, meta, skip, names, refs=[(bins, linear)], n_no_coor)"""
+    d = b"".join(x for _, x in bgzf_blocks(path))
+    assert d[:4] == b"TBI\x01"
+    n_ref, fmt, col_seq, col_beg, col_end, meta, skip, l_nm = struct.unpack_from("<8i", d, 4)
+    p = 36
+    names = d[p:p + l_nm].split(b"\0")[:-1]
+    assert len(names) == n_ref
+    p += l_nm
+    refs = []
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", d, p)[0]
+        p += 4
+        bins = {}
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", d, p)
+            p += 8
+            bins[b] = [struct.unpack_from("<QQ", d, p + 16 * k) for k in range(n_chunk)]
+            p += 16 * n_chunk
+        n_intv = struct.unpack_from("<i", d, p)[0]
+        p += 4
+        lin = list(struct.unpack_from(f"<{n_intv}Q", d, p))
+        p += 8 * n_intv
+        refs.append((bins, lin))
+    n_no_coor = struct.unpack_from("<Q", d, p)[0] if p + 8 <= len(d) else None
+    assert p + (8 if n_no_coor is not None else 0) == len(d)
+    return dict(format=fmt, col_seq=col_seq, col_beg=col_beg, col_end=col_end, meta=meta, skip=skip,
+                names=[n.decode() for n in names], refs=refs, n_no_coor=n_no_coor)
+
+
+def reg2bins(beg, end):
+    """all bins overlapping [beg, end) (SAM spec 5.3)"""
+    end -= 1
+    out = [0]
+    for shift, off in ((26, 1), (23, 9), (20, 73), (17, 585), (14, 4681)):
+        out += list(range(off + (beg >> shift), off + (end >> shift) + 1))
+    return out
+
+
+class BgzfText:
+    """random access into a BGZF text file by virtual offset"""
+
+    def __init__(self, path):
+        self.blocks = bgzf_blocks(path)
+        self.index = {off: i for i, (off, _) in enumerate(self.blocks)}
+
+    def lines_between(self, v0, v1):
+        i0, o0 = self.index[v0 >> 16], v0 & 0xffff
+        i1, o1 = self.index[v1 >> 16], v1 & 0xffff
+        if i0 == i1:
+            data = self.blocks[i0][1][o0:o1]
+        else:
+            data = self.blocks[i0][1][o0:] + b"".join(self.blocks[k][1] for k in range(i0 + 1, i1)) + self.blocks[i1][1][:o1]
+        return [ln for ln in data.split(b"\n") if ln]
+
+
+def tabix_query(tbi, text, name, beg, end):
+    """data lines of sequence `name` overlapping [beg, end) (0-based), the way tabix finds them: candidate chunks from the
+    bins, trimmed by the linear index, then filtered by coordinates"""
+    if name not in tbi["names"]:
+        return []
+    bins, lin = tbi["refs"][tbi["names"].index(name)]
+    min_off = lin[min(beg >> 14, len(lin) - 1)] if lin else 0
+    out = []
+    for b in reg2bins(beg, end):
+        for v0, v1 in bins.get(b, []):
+            if v1 <= min_off:
+                continue
+            for ln in text.lines_between(v0, v1):
+                f = ln.split(b"\t")
+                if f[0].decode() != name:
+                    continue
+                p = int(f[1]) - 1
+                if p < end and p + len(f[3]) > beg:
+                    out.append(ln)
+    return sorted(set(out), key=lambda ln: int(ln.split(b"\t")[1]))

@@ -3,14 +3,18 @@
 // Test infrastructure (built by tests/test_ext3_host.py into tests/_build/); the product has no host path.
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
+#define E3_STATS 1
 #include "../quasimodo_b200/csrc/ext3_core.cuh"
+E3Stats g_e3_stats = {0, 0, 0, 0, 0, 0, 0};
+extern "C" void ext3_host_stats(long long *out, int reset) { out[0] = g_e3_stats.rows; out[1] = g_e3_stats.core_cols; out[2] = g_e3_stats.masked_cols; out[3] = g_e3_stats.solo_rows; if (reset) g_e3_stats = E3Stats{0, 0, 0, 0, 0, 0, 0}; }
 
 namespace {
 struct HostMem {
     std::vector<uint2> ehv;
     std::vector<uint32_t> qv;
-    explicit HostMem(int cap) : ehv((size_t)cap + 1), qv((size_t)cap + 1) {}
+    explicit HostMem(int cap) : ehv((size_t)cap + 1 + kE3Pad), qv((size_t)cap + kE3Pad) {}
     uint2 &eh(int j) { return ehv.at((size_t)j); }
     uint32_t &q(int j) { return qv.at((size_t)j); }
     uint16_t &h16(int j, int X) { return ((uint16_t *)&ehv.at((size_t)j).x)[X]; }
@@ -68,6 +72,62 @@ extern "C" int ext3_host_run(const int *scores /* a b o_del e_del o_ins e_ins zd
                     if (e3_end_try(H[X], &r)) { memcpy(out + 8 * (int64_t)H[X].tk, &r, sizeof r); H[X].tk = -1; }
                 }
         }
+    }
+    return 0;
+}
+
+// Warp model (analysis tool for the kernel's launch shape, not a test of results): `lanes` threads walk the task list the way
+// ext3_kernel does (a thread takes two consecutive tasks; idle threads refill once `refill` of them are idle or nobody works)
+// and step their rows in lockstep.  out[0] = row steps, out[1] = sum over steps of max-over-lanes common columns,
+// out[2] = sum over steps of max-over-lanes one-task-only columns, out[3] = useful pair columns (common + one-task-only, all
+// lanes), out[4] = steps in which some lane had one-task-only columns, out[5] = sum over steps of active lanes.
+extern "C" int ext3_host_warpsim(const int *scores, int cap, int64_t n, const uint8_t *seq, const int64_t *q_off, const int64_t *t_off,
+                                 const int *qlen, const int *tlen, const int *h0, const int *w, int end_bonus, const unsigned *flags,
+                                 int lanes, int refill, long long *out)
+{
+    E3Scores S = {scores[0], scores[1], scores[2], scores[3], scores[4], scores[5], scores[6]};
+    if (!e3_scores_ok(S)) return -1;
+    const E3Consts K = e3_consts(S);
+    const bool sym = S.o_del == S.o_ins && S.e_del == S.e_ins && S.a == 1;
+    struct Lane { HostMem mem; E3Half H[2]; HostTgt tgt; explicit Lane(int c) : mem(c) { H[0].phase = H[1].phase = 0; H[0].tk = H[1].tk = -1; } };
+    std::vector<Lane> L;
+    for (int l = 0; l < lanes; ++l) L.emplace_back(cap);
+    int64_t cursor = 0;
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    for (;;) {
+        int n_idle = 0, n_want = 0;
+        for (auto &x : L) { const bool idle = !x.H[0].phase && !x.H[1].phase; n_idle += idle; n_want += idle && cursor < n; }
+        if (n_idle == lanes && cursor >= n) break;
+        if (n_want >= refill || n_idle == lanes)
+            for (auto &x : L) {
+                if (x.H[0].phase || x.H[1].phase || cursor >= n) continue;
+                for (int X = 0; X < 2 && cursor < n; ++X, ++cursor) {
+                    const int64_t i = cursor;
+                    if (!e3_task_ok(S, qlen[i], h0[i], cap)) continue;
+                    E3Half &H = x.H[X];
+                    H.tk = (int)i; H.phase = 1; H.qlen = qlen[i]; H.tlen = tlen[i]; H.h0 = h0[i]; H.w0 = w[i]; H.w = w[i]; H.end_bonus = end_bonus;
+                    H.tries_left = (flags[i] & 1u) ? 2 : 1; H.prev = (flags[i] & 2u) ? h0[i] : -1; H.cells = 0;
+                    x.tgt.t[X] = seq + t_off[i]; x.tgt.n[X] = tlen[i];
+                    HostQry qry = {seq + q_off[i]};
+                    e3_load_query(K, qlen[i], X, x.mem, qry);
+                }
+            }
+        int mx_core = 0, mx_masked = 0, active = 0;
+        for (auto &x : L) {
+            for (int X = 0; X < 2; ++X) if (x.H[X].phase == 1) e3_start_try(K, x.H[X], X, x.mem, x.tgt);
+            if (!x.H[0].phase && !x.H[1].phase) continue;
+            ++active;
+            g_e3_stats.last_pre = g_e3_stats.last_core = 0;
+            bool dA = false, dB = false;
+            if (sym) e3_row<true>(K, x.H[0], x.H[1], x.mem, x.tgt, dA, dB);
+            else e3_row<false>(K, x.H[0], x.H[1], x.mem, x.tgt, dA, dB);
+            mx_core = std::max(mx_core, g_e3_stats.last_core); mx_masked = std::max(mx_masked, g_e3_stats.last_pre);
+            out[3] += g_e3_stats.last_core + g_e3_stats.last_pre;
+            E3Result r;
+            if (dA && e3_end_try(x.H[0], &r)) x.H[0].tk = -1;
+            if (dB && e3_end_try(x.H[1], &r)) x.H[1].tk = -1;
+        }
+        if (active) { out[0] += 1; out[1] += mx_core; out[2] += mx_masked; out[4] += mx_masked > 0; out[5] += active; }
     }
     return 0;
 }

@@ -133,3 +133,42 @@ def test_driver_rejects_bad_input(case):
     assert p.returncode == 2 and "only A/C/G/T" in p.stderr
     p = drvutil.run_driver(["frobnicate"], check=False)
     assert p.returncode == 1
+
+
+def test_vcf_gz_and_tabix_index(tmp_path):
+    """rule `bcftools` declares {sample}.vcf.gz and tabix-indexes it (rules/vcfcall.smk:107,118-119); `qm_driver vcf-index` is the
+    host-only entry of the same writer the sample command uses: the .gz must inflate to the VCF, the .tbi must find exactly
+    the records a scan finds, for every kind of region"""
+    import gzip
+    from tests import bamio, drvutil
+    rng = np.random.default_rng(8)
+    vcf = tmp_path / "s.vcf"
+    rows = []
+    for chrom, n, L in (("Merlin", 4000, 235000), ("phiX", 30, 5386), ("ecoli", 2500, 4_641_652)):
+        pos = np.sort(rng.choice(np.arange(1, L), n, replace=False))
+        for p in pos:
+            ref = "ACGT"[rng.integers(0, 4)] * (1 if rng.random() < 0.9 else int(rng.integers(2, 40)))
+            rows.append((chrom, int(p), ref))
+    with open(vcf, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n##contig=<ID=Merlin,length=235000>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts\n")
+        for chrom, p, ref in rows:
+            fh.write(f"{chrom}\t{p}\t.\t{ref}\tG\t50\tPASS\tDP=30\tGT\t1\n")
+    drvutil.run_driver(["vcf-index", "--vcf", vcf])
+    gz = str(vcf) + ".gz"
+    assert gzip.open(gz, "rb").read() == open(vcf, "rb").read()
+    tbi = bamio.read_tbi(gz + ".tbi")
+    assert (tbi["format"], tbi["col_seq"], tbi["col_beg"], tbi["col_end"], tbi["meta"], tbi["skip"]) == (2, 1, 2, 0, ord("#"), 0)
+    assert tbi["names"] == ["Merlin", "phiX", "ecoli"]
+    for (bins, lin), n in zip(tbi["refs"], (4000, 30, 2500)):
+        assert bins[37450][1][0] == n                      # htslib's pseudo-bin: records of the sequence
+    text = bamio.BgzfText(gz)
+    regions = [("Merlin", 0, 235000), ("Merlin", 1000, 1001), ("Merlin", 16383, 16385), ("Merlin", 100000, 163840), ("phiX", 0, 100),
+               ("phiX", 5000, 5386), ("ecoli", 4_000_000, 4_641_652), ("ecoli", 131071, 131073), ("nope", 0, 10)]
+    regions += [("ecoli", int(b), int(b) + int(rng.integers(1, 300000))) for b in rng.integers(0, 4_600_000, 20)]
+    for name, b, e in regions:
+        want = [f"{c}\t{p}\t.\t{r}\tG\t50\tPASS\tDP=30\tGT\t1".encode() for c, p, r in rows if c == name and p - 1 < e and p - 1 + len(r) > b]
+        assert bamio.tabix_query(tbi, text, name, b, e) == want, (name, b, e)
+    # unsorted input cannot be indexed: non-zero exit, as tabix
+    bad = tmp_path / "bad.vcf"
+    bad.write_text("#CHROM\tPOS\tID\tREF\tALT\nMerlin\t500\t.\tA\tG\nMerlin\t20\t.\tA\tG\n")
+    assert drvutil.run_driver(["vcf-index", "--vcf", bad], check=False).returncode == 2

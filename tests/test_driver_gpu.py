@@ -239,3 +239,56 @@ def test_driver_edge_inputs(tmp_path):
             by = {(r["name"], r["flag"] & 0x40): r for r in B.records}
             assert by[("short", 0x40)]["flag"] & 4 and by[("allN", 0x40)]["flag"] & 4 and by[("allN", 0)]["seq"] == "N" * 150
             assert by[("p1", 0x40)]["pos"] == 100 and by[("p1", 0)]["cigar"] == [131 << 4]
+
+
+def test_driver_writes_every_declared_output_of_the_replaced_rules(sample_case, tmp_path):
+    """one `qm_driver sample` call at the reference's own path patterns (quasimodo_b200/rules.py, checked against the rule files
+    in tests/test_rules_cpu.py): sorted BAM + BAI, duplicate-free BAM + BAI, metrics, text pileup, VCF, bgzipped VCF + tabix index"""
+    import gzip
+    from quasimodo_b200 import rules
+    from tests import bamio, drvutil
+    dirs = {k: str(tmp_path / k) for k in ("seq_dir", "snpcall_dir", "report_dir")}
+    argv, paths = rules.sample_command(drvutil.driver_path(), dirs, "TM-1-1", "Merlin", sample_case["fa"], sample_case["r1"], sample_case["r2"],
+                                       extra=["--min-dp", "3", "--min-alt", "2"])
+    drvutil.run_driver(argv[1:])
+    for p in paths:
+        assert os.path.exists(p) and os.path.getsize(p) > 0, p
+    vcf = rules.expand(dirs, "bcftools", "vcf", "TM-1-1", "Merlin")
+    assert gzip.open(vcf + ".gz", "rb").read() == open(vcf, "rb").read()
+    tbi = bamio.read_tbi(vcf + ".gz.tbi")
+    text = bamio.BgzfText(vcf + ".gz")
+    recs = [ln.rstrip("\n").encode() for ln in open(vcf) if not ln.startswith("#")]
+    assert len(recs) > 20 and tbi["names"] == [recs[0].split(b"\t")[0].decode()]
+    name = tbi["names"][0]
+    assert bamio.tabix_query(tbi, text, name, 0, 1 << 29) == recs
+    lo, hi = int(recs[5].split(b"\t")[1]) - 1, int(recs[9].split(b"\t")[1])
+    assert bamio.tabix_query(tbi, text, name, lo, hi) == recs[5:10]
+    kept = bamio.Bam(rules.expand(dirs, "rmdup", "rmdupbam", "TM-1-1", "Merlin"))
+    assert 0 < len(kept.records) <= 2 * sample_case["n"] and not any(r["flag"] & 0x400 for r in kept.records)
+    bamio.read_bai(rules.expand(dirs, "rmdup", "rmdupbam", "TM-1-1", "Merlin") + ".bai")
+
+
+def test_driver_on_two_gpus_writes_the_same_files(tmp_path):
+    """--gpus 0,1: batches dealt over two GPUs, the first batch's insert-size model handed to both, counts merged with one NCCL
+    all-reduce -- BAM records, count TSV and VCF identical to the single-GPU run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from quasimodo_b200 import workloads
+    from tests import bamio, drvutil
+    n = 300_000
+    W = workloads.config1(n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    fa, r1, r2 = str(tmp_path / "ref.fa"), str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    drvutil.write_fasta(W.ref, fa)
+    drvutil.write_fastq(codes, quals, lens, drvutil.pair_names("p", n), r1, r2)
+    outs = []
+    for tag, gp in (("one", ["--gpu", 0]), ("two", ["--gpus", "0,1"])):
+        bam, tsv, vcf = (str(tmp_path / f"{tag}.{x}") for x in ("bam", "tsv", "vcf"))
+        p = drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--bam", bam, "--counts", tsv, "--vcf", vcf, "--batch-pairs", 65536] + gp)
+        data = b"".join(d for _, d in bamio.bgzf_blocks(bam))
+        l_text = int.from_bytes(data[4:8], "little")
+        outs.append((data[8 + l_text:], open(tsv, "rb").read(), [ln for ln in open(vcf) if not ln.startswith("##reference")], p.stderr))
+    assert "count tensors of 2 GPUs merged" in outs[1][3]
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
