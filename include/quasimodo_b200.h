@@ -185,6 +185,31 @@ void qm_pileup_opt_default(qm_pileup_opt *p);
 int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
                          const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
                          int64_t n_pairs, int32_t *d_counts, void *stream);
+/* Indel alleles: every insertion / deletion operation of an admitted read's CIGAR is tallied per
+ * (anchor position = the reference base in front of the event, type, length, inserted bases) in a device hash table, forward and
+ * reverse reads apart.  Insertions are told apart by their first QM_INDEL_SEQ_BASES bases (plus a flag when one of them is N);
+ * lengths above 255 are clamped.  The table is sparse (a few alleles per kb at the simulated error rates); it is what crosses GPUs
+ * next to the dense count tensor: qm_indel_table_merge adds gathered records of other ranks into the local table. */
+#define QM_INDEL_SEQ_BASES 11
+typedef struct {
+    int32_t  rid, pos;            /* anchor: 0-based position on contig rid of the base in front of the event      */
+    int32_t  len;                 /* inserted / deleted bases                                                       */
+    uint8_t  type;                /* 0 insertion, 1 deletion                                                        */
+    uint8_t  has_n, pad[2];       /* an N among the first QM_INDEL_SEQ_BASES inserted bases (stored as A)           */
+    uint32_t seq;                 /* insertion: base k (forward strand of the reference) at bits 2k, k < 11        */
+    int32_t  n_fwd, n_rev;        /* supporting forward / reverse reads                                             */
+    uint64_t key;                 /* the table key: sorts by (global position, type, length, bases)                 */
+} qm_indel;                       /* 40 B */
+typedef struct qm_indel_table qm_indel_table;
+int  qm_indel_table_create(qm_ctx *ctx, int log2_slots, qm_indel_table **out);
+void qm_indel_table_destroy(qm_indel_table *t);
+int  qm_indel_table_reset(qm_indel_table *t, void *stream);
+int  qm_indel_table_fetch_host(qm_indel_table *t, const qm_index *idx, qm_indel *h_out, int64_t max_out, int64_t *n_out);
+int  qm_indel_table_merge(qm_indel_table *t, const qm_indel *d_records, int64_t n, void *stream);
+/* qm_pileup_accumulate plus the indel alleles of the batch into `tab` (may be NULL) */
+int  qm_pileup_accumulate_indels(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
+                                 const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                                 int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, void *stream);
 /* planes [QM_NCH][l_pac] -> rows [l_pac][QM_NCH] (row order of the count TSV) */
 int qm_counts_to_rows(qm_ctx *ctx, const qm_index *idx, const int32_t *d_planes, int32_t *d_rows, void *stream);
 
@@ -216,6 +241,8 @@ int  qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_
 int32_t *qm_sample_counts(qm_sample *s);                          /* device pointer, planes [QM_NCH][l_pac] */
 int  qm_sample_stats_sync(qm_sample *s, int64_t *n_pairs, int64_t *cells, void *stream);
 int  qm_sample_counts_host(qm_sample *s, int32_t *h_rows /* [l_pac][QM_NCH] */);
+/* the sample's indel alleles (see qm_indel below), sorted by (position, type, length, bases); synchronous */
+struct qm_indel_table *qm_sample_indel_table(qm_sample *s);
 
 /* ---- SNP calls from the count tensor (stands in for `bcftools call -p 0.01 --ploidy 1 -mv | bcftools view
  * -i 'INFO/DP>=10'`, rules/vcfcall.smk:116-117).  A threshold caller: a non-reference base b is called at a
@@ -339,10 +366,13 @@ int  qm_comm_size(const qm_comm *c);
 int  qm_counts_allreduce(qm_ctx *ctx, qm_comm *comm, int32_t *d_counts, int64_t n, void *stream);
 int  qm_counts_allreduce_nccl(qm_ctx *ctx, void *nccl_comm /* ncclComm_t */, int32_t *d_counts, int64_t n, void *stream);
 int  qm_pestat_bcast(qm_ctx *ctx, qm_comm *comm, qm_pestat pes[4], int root, void *stream);
+/* every rank's `bytes` bytes at d_send, concatenated in rank order into d_recv on every rank (the sparse indel tables) */
+int  qm_comm_allgather(qm_ctx *ctx, qm_comm *comm, const void *d_send, void *d_recv, size_t bytes, void *stream);
 /* a sample spread over the communicator's ranks: rank r holds a contiguous range of the sample's pairs, rank 0 the range
  * that starts at pair 0 (its first batch at least min(sample, QM_PESTAT_PAIRS) pairs).  The insert-size model is then rank
  * 0's, broadcast once every rank has aligned its first batch (no rank aligns the prefix twice); qm_sample_allreduce_counts
- * sums the count tensors in place on every rank (asynchronous on `stream`).  Set before the first pairs; NULL clears. */
+ * sums the count tensors in place on every rank and merges the indel allele tables (each rank's records all-gathered and added
+ * into every rank's table); synchronous.  Set the communicator before the first pairs; NULL clears. */
 int  qm_sample_set_comm(qm_sample *s, qm_comm *comm);
 int  qm_sample_allreduce_counts(qm_sample *s, void *stream);
 

@@ -29,6 +29,7 @@ struct Nccl {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GetVersion)(int *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     std::string why;
@@ -49,6 +50,7 @@ Nccl *nccl()
         N.CommDestroy = (int (*)(ncclComm_t))sym("ncclCommDestroy");
         N.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclAllReduce");
         N.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclBroadcast");
+        N.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))sym("ncclAllGather");
         N.GetVersion = (int (*)(int *))sym("ncclGetVersion");
         N.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
     });
@@ -152,6 +154,23 @@ int qm_counts_allreduce(qm_ctx *ctx, qm_comm *comm, int32_t *d_counts, int64_t n
     if (!comm) return QM_EINVAL;
     if (comm->size == 1) return QM_OK;
     return qm_counts_allreduce_nccl(ctx, comm->comm, d_counts, n, stream);
+}
+
+// every rank's `bytes` bytes at d_send, concatenated in rank order into d_recv (size * bytes) on every rank; asynchronous
+int qm_comm_allgather(qm_ctx *ctx, qm_comm *comm, const void *d_send, void *d_recv, size_t bytes, void *stream)
+{
+    if (!ctx || !comm || (bytes > 0 && (!d_send || !d_recv))) return QM_EINVAL;
+    if (bytes == 0) return QM_OK;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (comm->size == 1) {
+        if (d_send != d_recv) QM_CUDA(ctx, cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, st));
+        return QM_OK;
+    }
+    Nccl *N = nccl();
+    if (!N) return qm_fail(ctx, QM_ENODEV, "%s", nccl_why());
+    QM_NCCL(ctx, N->AllGather(d_send, d_recv, bytes, ncclInt8, comm->comm, st));
+    return QM_OK;
 }
 
 // the insert-size model of rank `root` to every rank (4 x qm_pestat = 128 bytes); synchronous

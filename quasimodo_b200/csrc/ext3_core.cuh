@@ -99,14 +99,16 @@ E3_HD bool e3_scores_ok(const E3Scores &S)
 // can it hold this task?  (packed key: score <= 255 in 8 bits, column <= 255 in 8 bits)
 E3_HD bool e3_task_ok(const E3Scores &S, int qlen, int h0, int cap) { return qlen <= cap && qlen <= 256 && h0 + qlen * S.a <= 255 && h0 >= 0; }
 
-// Substitution score without a table: the query base is stored per column as a 16-bit code, the row's target base becomes a
-// mask and a floor:   s = min((qcode & tmask) + floor, a)
-//   query A/C/G/T : 0x100 << base            query N : b - 1 (low byte)
-//   target A/C/G/T: mask 0x100 << base | 0xff, floor -b        target N: mask 0, floor -1
-// match: >= 0x100 - b >= a -> a.  mismatch: 0 - b.  query N vs base: (b - 1) - b = -1.  anything vs target N: 0 - 1 = -1.
-E3_HD unsigned e3_qcode(const E3Scores &S, int c) { return c > 3 ? (unsigned)(S.b - 1) & 0xffu : 0x100u << c; }
-E3_HD unsigned e3_tmask(int tb) { return tb > 3 ? 0u : (0x100u << tb) | 0xffu; }
+// Substitution score without a table: the query base is stored per column as a small code, the row's target base becomes a
+// mask and a floor:   s = min((qcode & tmask) + floor, a)          (U = 0x100 with 16-bit planes, 0x10 with byte planes)
+//   query A/C/G/T : U << base                query N : b - 1 (below U)
+//   target A/C/G/T: mask U << base | (U - 1), floor -b         target N: mask 0, floor -1
+// match: >= U - b >= a -> a.  mismatch: 0 - b.  query N vs base: (b - 1) - b = -1.  anything vs target N: 0 - 1 = -1.
+template <bool NARROW> E3_HD unsigned e3_qcode(const E3Scores &S, int c) { return c > 3 ? (unsigned)(S.b - 1) & (NARROW ? 0xfu : 0xffu) : (NARROW ? 0x10u : 0x100u) << c; }
+template <bool NARROW> E3_HD unsigned e3_tmask(int tb) { return tb > 3 ? 0u : ((NARROW ? 0x10u : 0x100u) << tb) | (NARROW ? 0xfu : 0xffu); }
 E3_HD unsigned e3_tfloor(const E3Scores &S, int tb) { return (unsigned)(tb > 3 ? -1 : -S.b) & 0xffffu; }
+// byte planes: the query code is a byte, so the scores must satisfy a + b <= 16 (the default scheme does)
+E3_HD bool e3_scores_ok_narrow(const E3Scores &S) { return e3_scores_ok(S) && S.a + S.b <= 16; }
 
 struct E3Consts {
     E3Scores S;
@@ -135,8 +137,11 @@ struct E3Half {
 
 struct E3Result { int score, qle, tle, gtle, gscore, max_off, w_used, cells; };
 
-// Mem: eh(j) -> uint2& {h2, e2} of column j; q(j) -> uint32_t& query codes of column j;
-//      h16(j, X), e16(j, X), q16(j, X) -> uint16_t& the half of task X.
+// Mem (the thread's columns; two layouts, see extend3.cu):
+//   Raw raw(j)                      the stored words of column j, as loaded;  unpack(raw, h2, e2, q2) -> packed halves
+//   put(j, h2, e2)                  store eh[j] of both tasks
+//   set_he(j, X, h, e), zero(j, X)  eh[j] of task X alone (row -1, eh[end], the trimming scans)
+//   set_q(j, X, code)               query code of task X at column j;  Mem::kNarrow tells which code set is in use
 // Tgt: base(X, i) -> target base code (0..4) of row i of task X.
 
 // row -1 of one half (SURVEY.md A.3 first lines) and the band clamp of this try
@@ -145,12 +150,12 @@ E3_HD void e3_start_try(const E3Consts &K, E3Half &H, int X, Mem &mem, Tgt &tgt)
 {
     const E3Scores &S = K.S;
     const int qlen = H.qlen, h0 = H.h0;
-    mem.h16(0, X) = (uint16_t)h0; mem.e16(0, X) = 0;
+    mem.set_he(0, X, h0, 0);
     int v = h0 > K.oe_ins ? h0 - K.oe_ins : 0;
-    if (qlen >= 1) { mem.h16(1, X) = (uint16_t)v; mem.e16(1, X) = 0; }
+    if (qlen >= 1) mem.set_he(1, X, v, 0);
     int j = 2;
-    for (; j <= qlen && v > S.e_ins; ++j) { v -= S.e_ins; mem.h16(j, X) = (uint16_t)v; mem.e16(j, X) = 0; }
-    for (; j <= qlen; ++j) { mem.h16(j, X) = 0; mem.e16(j, X) = 0; }
+    for (; j <= qlen && v > S.e_ins; ++j) { v -= S.e_ins; mem.set_he(j, X, v, 0); }
+    for (; j <= qlen; ++j) mem.set_he(j, X, 0, 0);
     int best = S.a > -1 ? S.a : -1;
     if (-S.b > best) best = -S.b;
     int w = H.w0;
@@ -171,7 +176,7 @@ E3_HD void e3_start_try(const E3Consts &K, E3Half &H, int X, Mem &mem, Tgt &tgt)
 template <class Mem, class Qry>
 E3_HD void e3_load_query(const E3Consts &K, int qlen, int X, Mem &mem, Qry &qry)
 {
-    for (int j = 0; j < qlen; ++j) mem.q16(j, X) = (uint16_t)e3_qcode(K.S, qry.code(j));
+    for (int j = 0; j < qlen; ++j) mem.set_q(j, X, e3_qcode<Mem::kNarrow>(K.S, qry.code(j)));
 }
 
 // the end of a try of half H: second try with a doubled band (mem_chain2aln's rule), or the result.  Returns true when
@@ -207,7 +212,7 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         endA = A.end < i + A.w + 1 ? A.end : i + A.w + 1;
         endA = endA < A.qlen ? endA : A.qlen;
         if (begA == 0) { h1A = A.h0 - (S.o_del + S.e_del * (i + 1)); h1A = h1A > 0 ? h1A : 0; }
-        tmA = e3_tmask(tb); flA = e3_tfloor(S, tb);
+        tmA = e3_tmask<Mem::kNarrow>(tb); flA = e3_tfloor(S, tb);
     }
     if (rb) {
         const int i = B.i, tb = B.tb_next;
@@ -216,7 +221,7 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         endB = B.end < i + B.w + 1 ? B.end : i + B.w + 1;
         endB = endB < B.qlen ? endB : B.qlen;
         if (begB == 0) { h1B = B.h0 - (S.o_del + S.e_del * (i + 1)); h1B = h1B > 0 ? h1B : 0; }
-        tmB = e3_tmask(tb); flB = e3_tfloor(S, tb);
+        tmB = e3_tmask<Mem::kNarrow>(tb); flB = e3_tfloor(S, tb);
     }
     // a half without a row rides along on the partner's columns: its cells are dead storage (a finished task, or one whose
     // next try rewrites row -1 first), so the common loop needs no mask for it
@@ -228,15 +233,15 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
     unsigned f2 = 0, bkey = 0;
 
     // one cell of each task at column j: the reference's inner loop body on packed halves; KEY = H << 8 (both halves)
-#define E3_CELL(J, HE, Q2, H1IN, HOUT, EOUT)                                                                          \
+#define E3_CELL(H2, E2, Q2, HOUT, EOUT)                                                                               \
     {                                                                                                                 \
         const unsigned an = (Q2) & tm2;                                                                               \
         const unsigned s2 = e3_addmin(an, fl2, K.a2);                                                                 \
-        const unsigned m2 = e3_min(s2, SYM ? (HE).x : (HE).x * 128u);      /* h ? s : min(s, 0): a dead diagonal stays dead */ \
-        const unsigned M2 = e3_add((HE).x, m2);                                                                       \
-        HOUT = e3_max3(M2, (HE).y, f2);                                                                               \
+        const unsigned m2 = e3_min(s2, SYM ? (H2) : (H2) * 128u);          /* h ? s : min(s, 0): a dead diagonal stays dead */ \
+        const unsigned M2 = e3_add((H2), m2);                                                                         \
+        HOUT = e3_max3(M2, (E2), f2);                                                                                 \
         const unsigned td = e3_addmax_relu(M2, K.noe_del2, kE3Neg);                                                   \
-        EOUT = e3_addmax((HE).y, K.ned2, td);                                                                         \
+        EOUT = e3_addmax((E2), K.ned2, td);                                                                           \
         f2 = e3_addmax(f2, K.nei2, SYM ? td : e3_addmax_relu(M2, K.noe_ins2, kE3Neg));                                \
     }
     // ---- columns only one task visits before the common range ----
@@ -254,14 +259,11 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         E3_COUNT(masked_cols, j1 > j0 ? j1 - j0 : 0);
         E3_COUNT(last_pre, j1 > j0 ? j1 - j0 : 0);            /* columns before + after the common range, this row */
         for (int j = j0; j < j1; ++j) {
-            uint2 &p = mem.eh(j);
-            const uint2 he = p;
-            const unsigned q2 = mem.q(j);
-            unsigned Hn, En;
+            unsigned h2, e2, q2, Hn, En;
+            Mem::unpack(mem.raw(j), h2, e2, q2);
             const unsigned fkeep = f2;
-            E3_CELL(j, he, q2, h1, Hn, En)
-            p.x = (h1 & mask) | (he.x & ~mask);
-            p.y = (En & mask) | (he.y & ~mask);
+            E3_CELL(h2, e2, q2, Hn, En)
+            mem.put(j, (h1 & mask) | (h2 & ~mask), (En & mask) | (e2 & ~mask));
             Hn &= mask;                      // the other half computed on cells it does not own: unbounded garbage, keep it out of the key
             h1 = Hn | (h1 & ~mask);
             f2 = (f2 & mask) | (fkeep & ~mask);
@@ -280,36 +282,35 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         E3_COUNT(rows, 1); E3_COUNT(core_cols, ce - cs); E3_COUNT(solo_rows, (ra && rb) ? 0 : 1); E3_COUNT(last_core, ce - cs);
         int j = cs;
         unsigned jb = e3_pack2(cs);
-#define E3_STEP(JJ, HE, Q2, U, KU)                                                           \
+#define E3_STEP(JJ, RAW, U, KU)                                                              \
             {                                                                                \
-                unsigned Hn, En;                                                             \
-                E3_CELL(JJ, HE, Q2, h1, Hn, En)                                              \
-                mem.eh(JJ) = make_uint2(h1, En);                                             \
+                unsigned h2, e2, q2, Hn, En;                                                 \
+                Mem::unpack(RAW, h2, e2, q2);                                                \
+                E3_CELL(h2, e2, q2, Hn, En)                                                  \
+                mem.put(JJ, h1, En);                                                         \
                 h1 = Hn;                                                                     \
                 KU = Hn * 256u + (unsigned)((U) * 0x10001);                                  \
             }
         if (j + 3 < ce) {
-            uint2 a0 = mem.eh(j), a1 = mem.eh(j + 1), a2 = mem.eh(j + 2), a3 = mem.eh(j + 3);
-            unsigned b0 = mem.q(j), b1 = mem.q(j + 1), b2 = mem.q(j + 2), b3 = mem.q(j + 3);
+            typename Mem::Raw a0 = mem.raw(j), a1 = mem.raw(j + 1), a2 = mem.raw(j + 2), a3 = mem.raw(j + 3);
             do {
-                const uint2 n0 = mem.eh(j + 4), n1 = mem.eh(j + 5), n2 = mem.eh(j + 6), n3 = mem.eh(j + 7);
-                const unsigned m0 = mem.q(j + 4), m1 = mem.q(j + 5), m2 = mem.q(j + 6), m3 = mem.q(j + 7);
+                const typename Mem::Raw n0 = mem.raw(j + 4), n1 = mem.raw(j + 5), n2 = mem.raw(j + 6), n3 = mem.raw(j + 7);
                 unsigned k0, k1, k2, k3;
-                E3_STEP(j, a0, b0, 0, k0) E3_STEP(j + 1, a1, b1, 1, k1) E3_STEP(j + 2, a2, b2, 2, k2) E3_STEP(j + 3, a3, b3, 3, k3)
+                E3_STEP(j, a0, 0, k0) E3_STEP(j + 1, a1, 1, k1) E3_STEP(j + 2, a2, 2, k2) E3_STEP(j + 3, a3, 3, k3)
                 bkey = e3_uaddmax(e3_umax(e3_umax3(k0, k1, k2), k3), jb, bkey);
                 jb += 0x00040004u;
                 j += 4;
-                a0 = n0; a1 = n1; a2 = n2; a3 = n3; b0 = m0; b1 = m1; b2 = m2; b3 = m3;
+                a0 = n0; a1 = n1; a2 = n2; a3 = n3;
             } while (j + 3 < ce);
             // up to three columns left, already in registers
-            if (j < ce) { unsigned k0; E3_STEP(j, a0, b0, 0, k0) bkey = e3_uaddmax(k0, jb, bkey); }
-            if (j + 1 < ce) { unsigned k0; E3_STEP(j + 1, a1, b1, 1, k0) bkey = e3_uaddmax(k0, jb, bkey); }
-            if (j + 2 < ce) { unsigned k0; E3_STEP(j + 2, a2, b2, 2, k0) bkey = e3_uaddmax(k0, jb, bkey); }
+            if (j < ce) { unsigned k0; E3_STEP(j, a0, 0, k0) bkey = e3_uaddmax(k0, jb, bkey); }
+            if (j + 1 < ce) { unsigned k0; E3_STEP(j + 1, a1, 1, k0) bkey = e3_uaddmax(k0, jb, bkey); }
+            if (j + 2 < ce) { unsigned k0; E3_STEP(j + 2, a2, 2, k0) bkey = e3_uaddmax(k0, jb, bkey); }
         } else {
             for (; j < ce; ++j) {
-                const uint2 he = mem.eh(j);
+                const typename Mem::Raw r0 = mem.raw(j);
                 unsigned k0;
-                E3_STEP(j, he, mem.q(j), 0, k0)
+                E3_STEP(j, r0, 0, k0)
                 bkey = e3_uaddmax(k0, jb, bkey);
                 jb += 0x00010001u;
             }
@@ -328,7 +329,7 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         const int h1x = (int)((h1 >> (16 * X)) & 0xffffu);
         const unsigned key = (bkey >> (16 * X)) & 0xffffu;
         const int jstop = end > beg ? end : beg;                      // the reference's j after the loop
-        mem.h16(end, X) = (uint16_t)h1x; mem.e16(end, X) = 0;         // eh[end] = {h1, 0}
+        mem.set_he(end, X, h1x, 0);                                   // eh[end] = {h1, 0}
         int m = 0, mj = -1;
         if (end > beg) { H.cells += end - beg; m = (int)(key >> 8); mj = (int)(key & 0xffu); }
         if (jstop == qlen) {
@@ -349,9 +350,9 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         }
         if (stop) { done = true; return; }
         int a = beg;
-        while (a < end && (mem.h16(a, X) | mem.e16(a, X)) == 0) ++a;
+        while (a < end && mem.zero(a, X)) ++a;
         int b = end;
-        while (b >= a && (mem.h16(b, X) | mem.e16(b, X)) == 0) --b;
+        while (b >= a && mem.zero(b, X)) --b;
         H.beg = a;
         H.end = b + 2 < qlen ? b + 2 : qlen;
         H.i = i + 1;

@@ -17,7 +17,8 @@
 namespace {
 
 constexpr int kNumClasses = kExtClasses;
-constexpr int kThreadPerTaskMin = 4096;        // tasks in a class below which the warp-per-task kernel is used
+constexpr int kThreadPerTaskMin = 16384;       // tasks in a class below which the warp-per-task kernel is used (a thread of the
+                                               // packed kernel holds two tasks: fewer would leave most SMs without a warp)
 
 // ---- public tasks -> internal tasks, binned by striping class (device side, no host sync) ----
 __global__ void ext_classify_kernel(const qm_ext_task *__restrict__ tasks, const uint8_t *__restrict__ seq, int64_t n,

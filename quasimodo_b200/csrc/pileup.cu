@@ -8,6 +8,7 @@
 // fire-and-forget `red.global.add.s32` into the channel-major count tensor counts[ch][l_pac].  With
 // consecutive lanes on consecutive reference positions of one channel plane the 32 reductions of a warp
 // fall into one or two 128-byte lines of the L2-resident tensor.
+#include <algorithm>
 #include "pipeline.cuh"
 
 namespace {
@@ -65,10 +66,34 @@ __device__ __forceinline__ int qidx_of(const AlnS &a, int p)
 
 __device__ __forceinline__ void red_add(int32_t *p) { atomicAdd(p, 1); }   // result unused => RED.ADD
 
+// ---- indel allele table (SURVEY.md 8a9 "indel alleles into a small hash table", 8e "gather of the sparse indel table") ----
+// Open addressing on 64-bit keys: anchor position (forward coordinate on the concatenated contigs, 32 bits) | type (1) |
+// length (8, clamped to 255) | "an N among the inserted bases" (1) | the first 11 inserted bases, 2 bits each (22).  Two int32
+// counters per slot (forward / reverse reads).  A full table raises the overflow flag; the fetch then fails with QM_ELIMIT.
+constexpr unsigned long long kIndelEmpty = ~0ull;
+constexpr int kIndelSeqBases = 11;
+struct IndelView { unsigned long long *keys; int32_t *cnt; uint32_t mask; int *overflow; };
+
+__device__ __forceinline__ unsigned long long indel_key(int64_t gpos, int type, int len, uint32_t seq, int has_n)
+{
+    return (unsigned long long)(uint32_t)gpos << 32 | (unsigned long long)(type & 1) << 31 | (unsigned long long)(len > 255 ? 255 : len) << 23 |
+           (unsigned long long)(has_n & 1) << 22 | (unsigned long long)(seq & 0x3fffffu);
+}
+__device__ __forceinline__ void indel_add(const IndelView &T, unsigned long long key, int rev, int n)
+{
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & T.mask;
+    for (int probe = 0; probe < 4096; ++probe) {
+        const unsigned long long old = atomicCAS(&T.keys[h], kIndelEmpty, key);
+        if (old == kIndelEmpty || old == key) { atomicAdd(&T.cnt[2 * h + rev], n); return; }
+        h = (h + 1) & T.mask;
+    }
+    atomicExch(T.overflow, 1);
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, const uint8_t *__restrict__ codes,
               const uint8_t *__restrict__ quals, int stride, const int32_t *__restrict__ lens, int64_t n_pairs,
-              int32_t *__restrict__ counts, unsigned long long *__restrict__ n_admitted)
+              int32_t *__restrict__ counts, unsigned long long *__restrict__ n_admitted, IndelView T)
 {
     __shared__ AlnS s_aln[kWarpsPerBlock][2];
     __shared__ uint8_t s_q[kWarpsPerBlock][2][kMaxLen];
@@ -141,18 +166,30 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
                 if (s_q[wib][e][i] >= po.min_bq) red_add(counts + (int64_t)((rev[e] ? 6 : 0) + seq_base(e, i)) * L_pac + base + p);
             }
             if (lane < a.n_cigar) {          // operation-level channels: lane k owns CIGAR operation k
-                int p = a.pos, last_m = -1;
+                int p = a.pos, last_m = -1, x = 0;
                 bool started = false;
                 for (int k = 0; k < lane; ++k) {
                     const int op = a.cigar[k] & 0xf, len = (int)(a.cigar[k] >> 4);
-                    if (op == 0) { p += len; last_m = p - 1; started = true; }
+                    if (op == 0) { p += len; x += len; last_m = p - 1; started = true; }
                     else if (op == 2) p += len;
+                    else if (op == 1 || op == 4) x += len;
                 }
                 const int op = a.cigar[lane] & 0xf, len = (int)(a.cigar[lane] >> 4);
                 if (op == 0 && !started) red_add(counts + 15 * L_pac + base + p);
-                else if (op == 1) { if (last_m >= 0) red_add(counts + 12 * L_pac + base + last_m); }
-                else if (op == 2) {
-                    if (last_m >= 0) red_add(counts + 13 * L_pac + base + last_m);
+                else if (op == 1) {
+                    if (last_m >= 0) {
+                        red_add(counts + 12 * L_pac + base + last_m);
+                        if (T.keys) {                  // the inserted bases as the forward strand of the reference reads them
+                            uint32_t seq = 0; int has_n = 0;
+                            for (int i = 0; i < len && i < kIndelSeqBases; ++i) { const int c = seq_base(e, x + i); if (c > 3) has_n = 1; else seq |= (uint32_t)c << (2 * i); }
+                            indel_add(T, indel_key(base + last_m, 0, len, seq, has_n), rev[e] ? 1 : 0, 1);
+                        }
+                    }
+                } else if (op == 2) {
+                    if (last_m >= 0) {
+                        red_add(counts + 13 * L_pac + base + last_m);
+                        if (T.keys) indel_add(T, indel_key(base + last_m, 1, len, 0, 0), rev[e] ? 1 : 0, 1);
+                    }
                     for (int i = 0; i < len; ++i) red_add(counts + (int64_t)(rev[e] ? 11 : 5) * L_pac + base + p + i);
                 }
             }
@@ -187,12 +224,139 @@ void qm_pileup_opt_default(qm_pileup_opt *p)
     p->min_mapq = 0; p->min_bq = 13; p->count_orphans = 0; p->ignore_overlaps = 0;
 }
 
-int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
-                         const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
-                         int64_t n_pairs, int32_t *d_counts, void *stream)
+// ---- the indel allele table as an object: device arrays owned by the library ----
+struct qm_indel_table {
+    qm_ctx *ctx = nullptr;
+    unsigned long long *d_keys = nullptr;
+    int32_t *d_cnt = nullptr;
+    int *d_overflow = nullptr;
+    uint32_t cap = 0;
+};
+
+int qm_indel_table_create(qm_ctx *ctx, int log2_slots, qm_indel_table **out)
+{
+    if (!ctx || !out || log2_slots < 8 || log2_slots > 28) return QM_EINVAL;
+    *out = nullptr;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    qm_indel_table *t = new qm_indel_table;
+    t->ctx = ctx; t->cap = 1u << log2_slots;
+    cudaError_t e;
+    if ((e = cudaMalloc(&t->d_keys, (size_t)t->cap * 8)) != cudaSuccess || (e = cudaMalloc(&t->d_cnt, (size_t)t->cap * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&t->d_overflow, 4)) != cudaSuccess) {
+        cudaFree(t->d_keys); cudaFree(t->d_cnt); cudaFree(t->d_overflow); delete t;
+        return qm_fail(ctx, QM_ENOMEM, "qm_indel_table_create: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return qm_indel_table_reset(t, nullptr);
+}
+
+void qm_indel_table_destroy(qm_indel_table *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaFree(t->d_keys); cudaFree(t->d_cnt); cudaFree(t->d_overflow);
+    delete t;
+}
+
+int qm_indel_table_reset(qm_indel_table *t, void *stream)
+{
+    if (!t) return QM_EINVAL;
+    qm_ctx *ctx = t->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    QM_CUDA(ctx, cudaMemsetAsync(t->d_keys, 0xff, (size_t)t->cap * 8, (cudaStream_t)stream));
+    QM_CUDA(ctx, cudaMemsetAsync(t->d_cnt, 0, (size_t)t->cap * 8, (cudaStream_t)stream));
+    QM_CUDA(ctx, cudaMemsetAsync(t->d_overflow, 0, 4, (cudaStream_t)stream));
+    return QM_OK;
+}
+
+namespace {
+// slots in use -> records, compacted through a counter (order fixed afterwards by sorting on the key)
+__global__ void indel_collect_kernel(IndelView T, uint32_t cap, const IndexView V, qm_indel *__restrict__ out, int64_t max_out,
+                                     unsigned long long *__restrict__ n_out)
+{
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= cap) return;
+    const unsigned long long k = T.keys[h];
+    if (k == kIndelEmpty) return;
+    const unsigned long long slot = atomicAdd(n_out, 1ull);
+    if ((int64_t)slot >= max_out) return;
+    qm_indel r;
+    const int64_t g = (int64_t)(k >> 32);
+    int rid = 0;
+    for (int c = 0; c < V.n_contigs; ++c) if (g >= V.off[c] && g < V.off[c] + V.len[c]) rid = c;
+    r.rid = rid; r.pos = (int32_t)(g - V.off[rid]);
+    r.type = (uint8_t)((k >> 31) & 1); r.has_n = (uint8_t)((k >> 22) & 1); r.pad[0] = r.pad[1] = 0;
+    r.len = (int32_t)((k >> 23) & 0xff);
+    r.seq = (uint32_t)(k & 0x3fffffu);
+    r.n_fwd = T.cnt[2 * h]; r.n_rev = T.cnt[2 * h + 1];
+    r.key = k;
+    out[slot] = r;
+}
+__global__ void indel_merge_kernel(IndelView T, const qm_indel *__restrict__ in, int64_t n)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const qm_indel r = in[i];
+    if (r.n_fwd) indel_add(T, r.key, 0, r.n_fwd);
+    if (r.n_rev) indel_add(T, r.key, 1, r.n_rev);
+    if (!r.n_fwd && !r.n_rev) indel_add(T, r.key, 0, 0);
+}
+IndelView view_of(qm_indel_table *t)
+{
+    IndelView T = {nullptr, nullptr, 0, nullptr};
+    if (t) { T.keys = t->d_keys; T.cnt = t->d_cnt; T.mask = t->cap - 1; T.overflow = t->d_overflow; }
+    return T;
+}
+}  // namespace
+
+// records of the table, sorted by (position, type, length, bases), on the host.  Synchronous.
+int qm_indel_table_fetch_host(qm_indel_table *t, const qm_index *idx, qm_indel *h_out, int64_t max_out, int64_t *n_out)
+{
+    if (!t || !idx || !n_out || max_out < 0 || (max_out > 0 && !h_out)) return QM_EINVAL;
+    qm_ctx *ctx = t->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    QM_CUDA(ctx, cudaDeviceSynchronize());
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 21, (size_t)(max_out > 0 ? max_out : 1) * sizeof(qm_indel) + 256, &p);
+    if (rc) return rc;
+    qm_indel *d_out = (qm_indel *)((char *)p + 256);
+    unsigned long long *d_n = (unsigned long long *)p;
+    QM_CUDA(ctx, cudaMemsetAsync(d_n, 0, 8, st));
+    indel_collect_kernel<<<(t->cap + 255) / 256, 256, 0, st>>>(view_of(t), t->cap, idx->v, d_out, max_out, d_n);
+    QM_CUDA(ctx, cudaGetLastError());
+    unsigned long long n = 0;
+    int ovf = 0;
+    QM_CUDA(ctx, cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaMemcpyAsync(&ovf, t->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_out = (int64_t)n;
+    if (ovf) return qm_fail(ctx, QM_ELIMIT, "the indel allele table (%u slots) overflowed", t->cap);
+    if ((int64_t)n > max_out) return qm_fail(ctx, QM_ELIMIT, "qm_indel_table_fetch_host: %llu alleles exceed max_out=%lld", n, (long long)max_out);
+    if (n) QM_CUDA(ctx, cudaMemcpy(h_out, d_out, (size_t)n * sizeof(qm_indel), cudaMemcpyDeviceToHost));
+    std::sort(h_out, h_out + n, [](const qm_indel &a, const qm_indel &b) { return a.key < b.key; });
+    return QM_OK;
+}
+
+// merge records (e.g. another GPU's table, gathered by the caller) into this table: counts add up.  Asynchronous.
+int qm_indel_table_merge(qm_indel_table *t, const qm_indel *d_records, int64_t n, void *stream)
+{
+    if (!t || n < 0 || (n > 0 && !d_records)) return QM_EINVAL;
+    if (n == 0) return QM_OK;
+    qm_ctx *ctx = t->ctx;
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    indel_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(view_of(t), d_records, n);
+    QM_CUDA(ctx, cudaGetLastError());
+    return QM_OK;
+}
+
+int qm_pileup_accumulate_indels(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
+                                const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                                int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, void *stream)
 {
     if (!ctx || !idx || !po || n_pairs < 0 || (n_pairs > 0 && (!d_alns || !d_codes || !d_quals || !d_lens || !d_counts)))
         return QM_EINVAL;
+    if (tab && tab->ctx != ctx) return qm_fail(ctx, QM_EINVAL, "the indel table belongs to another context");
     if (n_pairs == 0) return QM_OK;
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     int64_t blocks = (n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -200,10 +364,17 @@ int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *
     if (blocks > cap) blocks = cap;
     const int sp = qm_prof_begin(ctx, QM_ST_PILEUP, (cudaStream_t)stream);
     pileup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr);
+        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab));
     qm_prof_end(ctx, QM_ST_PILEUP, sp, (cudaStream_t)stream, 1);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
+}
+
+int qm_pileup_accumulate(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
+                         const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                         int64_t n_pairs, int32_t *d_counts, void *stream)
+{
+    return qm_pileup_accumulate_indels(ctx, idx, po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, stream);
 }
 
 int qm_counts_to_rows(qm_ctx *ctx, const qm_index *idx, const int32_t *d_planes, int32_t *d_rows, void *stream)

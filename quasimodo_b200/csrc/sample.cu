@@ -25,6 +25,7 @@ struct qm_sample {
     qm_opt opt;
     qm_pileup_opt popt;
     int32_t *d_counts = nullptr;
+    qm_indel_table *indels = nullptr;             // sparse indel alleles next to the dense counts
     int64_t *d_cells = nullptr;
     qm_reg *d_regs = nullptr;
     int32_t *d_n_regs = nullptr;
@@ -94,7 +95,7 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
         return QM_OK;
     }
     if (quals_ready) QM_CUDA(ctx, cudaStreamWaitEvent(st, quals_ready, 0));
-    rc = qm_pileup_accumulate(ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n, s->d_counts, st);
+    rc = qm_pileup_accumulate_indels(ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n, s->d_counts, s->indels, st);
     if (rc) return rc;
     s->n_pairs += n;
     return QM_OK;
@@ -123,6 +124,7 @@ int qm_sample_begin(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const q
         qm_sample_destroy(s);
         return qm_fail(ctx, QM_ENOMEM, "qm_sample_begin: %s", cudaGetErrorString(e));
     }
+    if (qm_indel_table_create(ctx, 20, &s->indels) != QM_OK) { qm_sample_destroy(s); return QM_ENOMEM; }
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s->ev_quals[i], cudaEventDisableTiming);
@@ -145,6 +147,7 @@ void qm_sample_destroy(qm_sample *s)
     cudaSetDevice(s->ctx->device);
     cudaDeviceSynchronize();
     free_kept(s);
+    qm_indel_table_destroy(s->indels);
     cudaFree(s->d_counts); cudaFree(s->d_cells); cudaFree(s->d_regs); cudaFree(s->d_n_regs); cudaFree(s->d_alns);
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->d_stage[i]);
@@ -164,6 +167,7 @@ int qm_sample_reset(qm_sample *s, void *stream)
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     QM_CUDA(ctx, cudaMemsetAsync(s->d_counts, 0, (size_t)QM_NCH * s->idx->v.l_pac * sizeof(int32_t), (cudaStream_t)stream));
     QM_CUDA(ctx, cudaMemsetAsync(s->d_cells, 0, 8, (cudaStream_t)stream));
+    { const int rc = qm_indel_table_reset(s->indels, stream); if (rc) return rc; }
     s->have_pes = false; s->n_pairs = 0; s->rmdup_finished = false;
     if (!s->kept.empty()) { QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream)); free_kept(s); }
     return QM_OK;
@@ -198,7 +202,7 @@ int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
     if (rc) return rc;
     for (int c = 0; c < nc; ++c) {
         const auto &k = s->kept[c];
-        rc = qm_pileup_accumulate(ctx, s->idx, &s->popt, k.alns, k.codes, k.quals, k.stride, k.lens, k.n, s->d_counts, stream);
+        rc = qm_pileup_accumulate_indels(ctx, s->idx, &s->popt, k.alns, k.codes, k.quals, k.stride, k.lens, k.n, s->d_counts, s->indels, stream);
         if (rc) return rc;
     }
     QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
@@ -236,9 +240,52 @@ int qm_sample_set_comm(qm_sample *s, qm_comm *comm)
 int qm_sample_allreduce_counts(qm_sample *s, void *stream)
 {
     if (!s) return QM_EINVAL;
-    if (!s->comm) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_allreduce_counts: no communicator set");
-    return qm_counts_allreduce(s->ctx, s->comm, s->d_counts, (int64_t)QM_NCH * s->idx->v.l_pac, stream);
+    qm_ctx *ctx = s->ctx;
+    if (!s->comm) return qm_fail(ctx, QM_EINVAL, "qm_sample_allreduce_counts: no communicator set");
+    int rc = qm_counts_allreduce(ctx, s->comm, s->d_counts, (int64_t)QM_NCH * s->idx->v.l_pac, stream);
+    if (rc) return rc;
+    const int size = qm_comm_size(s->comm), rank = qm_comm_rank(s->comm);
+    if (size == 1) return QM_OK;
+    // the sparse part: every rank's alleles to every rank (counts first, then the records padded to the largest count),
+    // the others' records added into the local table
+    QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int64_t kMaxRec = 1 << 18;
+    std::vector<qm_indel> mine((size_t)kMaxRec);
+    int64_t n = 0;
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    rc = qm_indel_table_fetch_host(s->indels, s->idx, mine.data(), kMaxRec, &n);
+    if (rc) return rc;
+    void *p = nullptr;
+    rc = qm_scratch_reserve(ctx, 22, 256 + (size_t)size * 8, &p);
+    if (rc) return rc;
+    int64_t *d_n = (int64_t *)p, *d_all_n = (int64_t *)((char *)p + 256);
+    QM_CUDA(ctx, cudaMemcpyAsync(d_n, &n, 8, cudaMemcpyHostToDevice, st));
+    rc = qm_comm_allgather(ctx, s->comm, d_n, d_all_n, 8, st);
+    if (rc) return rc;
+    std::vector<int64_t> all_n((size_t)size);
+    QM_CUDA(ctx, cudaMemcpyAsync(all_n.data(), d_all_n, (size_t)size * 8, cudaMemcpyDeviceToHost, st));
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    int64_t mx = 0;
+    for (int64_t v : all_n) mx = v > mx ? v : mx;
+    if (mx == 0) return QM_OK;
+    rc = qm_scratch_reserve(ctx, 23, (size_t)(size + 1) * mx * sizeof(qm_indel), &p);
+    if (rc) return rc;
+    qm_indel *d_send = (qm_indel *)p, *d_recv = d_send + mx;
+    QM_CUDA(ctx, cudaMemsetAsync(d_send, 0, (size_t)mx * sizeof(qm_indel), st));
+    if (n) QM_CUDA(ctx, cudaMemcpyAsync(d_send, mine.data(), (size_t)n * sizeof(qm_indel), cudaMemcpyHostToDevice, st));
+    rc = qm_comm_allgather(ctx, s->comm, d_send, d_recv, (size_t)mx * sizeof(qm_indel), st);
+    if (rc) return rc;
+    for (int r = 0; r < size; ++r)
+        if (r != rank && all_n[r] > 0) {
+            rc = qm_indel_table_merge(s->indels, d_recv + (size_t)r * mx, all_n[r], st);
+            if (rc) return rc;
+        }
+    QM_CUDA(ctx, cudaStreamSynchronize(st));
+    return QM_OK;
 }
+
+qm_indel_table *qm_sample_indel_table(qm_sample *s) { return s ? s->indels : nullptr; }
 
 int qm_sample_set_pestat(qm_sample *s, const qm_pestat pes[4])
 {

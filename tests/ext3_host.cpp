@@ -11,15 +11,33 @@ E3Stats g_e3_stats = {0, 0, 0, 0, 0, 0, 0};
 extern "C" void ext3_host_stats(long long *out, int reset) { out[0] = g_e3_stats.rows; out[1] = g_e3_stats.core_cols; out[2] = g_e3_stats.masked_cols; out[3] = g_e3_stats.solo_rows; if (reset) g_e3_stats = E3Stats{0, 0, 0, 0, 0, 0, 0}; }
 
 namespace {
-struct HostMem {
-    std::vector<uint2> ehv;
-    std::vector<uint32_t> qv;
-    explicit HostMem(int cap) : ehv((size_t)cap + 1 + kE3Pad), qv((size_t)cap + kE3Pad) {}
-    uint2 &eh(int j) { return ehv.at((size_t)j); }
-    uint32_t &q(int j) { return qv.at((size_t)j); }
-    uint16_t &h16(int j, int X) { return ((uint16_t *)&ehv.at((size_t)j).x)[X]; }
-    uint16_t &e16(int j, int X) { return ((uint16_t *)&ehv.at((size_t)j).y)[X]; }
-    uint16_t &q16(int j, int X) { return ((uint16_t *)&qv.at((size_t)j))[X]; }
+struct WideMem {                        // 16-bit planes: {h2, e2} 64-bit word + 32-bit query word per column (SmemWide of extend3.cu)
+    static constexpr bool kNarrow = false;
+    struct Raw { unsigned h2, e2, q2; };
+    std::vector<Raw> v;
+    explicit WideMem(int cap) : v((size_t)cap + 1 + kE3Pad) {}
+    Raw raw(int j) { return v.at((size_t)j); }
+    static void unpack(const Raw &r, unsigned &h2, unsigned &e2, unsigned &q2) { h2 = r.h2; e2 = r.e2; q2 = r.q2; }
+    void put(int j, unsigned h2, unsigned e2) { v.at((size_t)j).h2 = h2; v.at((size_t)j).e2 = e2; }
+    void set_he(int j, int X, int h, int e) { ((uint16_t *)&v.at((size_t)j).h2)[X] = (uint16_t)h; ((uint16_t *)&v.at((size_t)j).e2)[X] = (uint16_t)e; }
+    bool zero(int j, int X) { return (((uint16_t *)&v.at((size_t)j).h2)[X] | ((uint16_t *)&v.at((size_t)j).e2)[X]) == 0; }
+    void set_q(int j, int X, unsigned code) { ((uint16_t *)&v.at((size_t)j).q2)[X] = (uint16_t)code; }
+};
+struct NarrowMem {                      // byte planes: one 32-bit word (h | e << 8 per task) + a 16-bit query word per column (SmemNarrow)
+    static constexpr bool kNarrow = true;
+    struct Raw { unsigned he; unsigned q; };
+    std::vector<unsigned> ehv;
+    std::vector<uint16_t> qv;
+    explicit NarrowMem(int cap) : ehv((size_t)cap + 1 + kE3Pad), qv((size_t)cap + kE3Pad) {}
+    Raw raw(int j) { Raw r; r.he = ehv.at((size_t)j); r.q = (size_t)j < qv.size() ? qv[(size_t)j] : 0; return r; }
+    static void unpack(const Raw &r, unsigned &h2, unsigned &e2, unsigned &q2)
+    {
+        h2 = r.he & 0x00ff00ffu; e2 = (r.he >> 8) & 0x00ff00ffu; q2 = (r.q & 0xffu) | (r.q & 0xff00u) << 8;
+    }
+    void put(int j, unsigned h2, unsigned e2) { ehv.at((size_t)j) = (h2 & 0x00ff00ffu) | (e2 & 0x00ff00ffu) << 8; }
+    void set_he(int j, int X, int h, int e) { ((uint16_t *)&ehv.at((size_t)j))[X] = (uint16_t)((h & 0xff) | (e & 0xff) << 8); }
+    bool zero(int j, int X) { return ((uint16_t *)&ehv.at((size_t)j))[X] == 0; }
+    void set_q(int j, int X, unsigned code) { ((uint8_t *)&qv.at((size_t)j))[X] = (uint8_t)code; }
 };
 struct HostTgt {
     const uint8_t *t[2];
@@ -33,12 +51,13 @@ struct HostQry { const uint8_t *q; int code(int j) const { return q[j] > 4 ? 4 :
 // Tasks are run in pairs (2k, 2k+1) in the given order; dirty != 0 leaves the previous pair's cells in place (what a
 // persistent kernel thread sees), otherwise the planes start zeroed.  out[i] = 8 ints; not_ok[i] = 1: the packed kernel
 // refuses the task (the launcher's fallback), out untouched.  Returns 0, or -1 when the scoring scheme is refused.
-extern "C" int ext3_host_run(const int *scores /* a b o_del e_del o_ins e_ins zdrop */, int cap, int64_t n, const uint8_t *seq,
-                             const int64_t *q_off, const int64_t *t_off, const int *qlen, const int *tlen, const int *h0, const int *w,
-                             int end_bonus, const unsigned *flags, int *out, uint8_t *not_ok)
+template <class HostMem>
+static int host_run(const int *scores /* a b o_del e_del o_ins e_ins zdrop */, int cap, int64_t n, const uint8_t *seq,
+                    const int64_t *q_off, const int64_t *t_off, const int *qlen, const int *tlen, const int *h0, const int *w,
+                    int end_bonus, const unsigned *flags, int *out, uint8_t *not_ok)
 {
     E3Scores S = {scores[0], scores[1], scores[2], scores[3], scores[4], scores[5], scores[6]};
-    if (!e3_scores_ok(S)) return -1;
+    if (HostMem::kNarrow ? !e3_scores_ok_narrow(S) : !e3_scores_ok(S)) return -1;
     const E3Consts K = e3_consts(S);
     const bool sym = S.o_del == S.o_ins && S.e_del == S.e_ins && S.a == 1;
     HostMem mem(cap);
@@ -76,6 +95,15 @@ extern "C" int ext3_host_run(const int *scores /* a b o_del e_del o_ins e_ins zd
     return 0;
 }
 
+// narrow != 0: the byte-plane layout (needs a + b <= 16, returns -1 otherwise), else the 16-bit planes
+extern "C" int ext3_host_run(const int *scores, int cap, int64_t n, const uint8_t *seq, const int64_t *q_off, const int64_t *t_off,
+                             const int *qlen, const int *tlen, const int *h0, const int *w, int end_bonus, const unsigned *flags, int *out,
+                             uint8_t *not_ok, int narrow)
+{
+    return narrow ? host_run<NarrowMem>(scores, cap, n, seq, q_off, t_off, qlen, tlen, h0, w, end_bonus, flags, out, not_ok)
+                  : host_run<WideMem>(scores, cap, n, seq, q_off, t_off, qlen, tlen, h0, w, end_bonus, flags, out, not_ok);
+}
+
 // Warp model (analysis tool for the kernel's launch shape, not a test of results): `lanes` threads walk the task list the way
 // ext3_kernel does (a thread takes two consecutive tasks; idle threads refill once `refill` of them are idle or nobody works)
 // and step their rows in lockstep.  out[0] = row steps, out[1] = sum over steps of max-over-lanes common columns,
@@ -89,6 +117,7 @@ extern "C" int ext3_host_warpsim(const int *scores, int cap, int64_t n, const ui
     if (!e3_scores_ok(S)) return -1;
     const E3Consts K = e3_consts(S);
     const bool sym = S.o_del == S.o_ins && S.e_del == S.e_ins && S.a == 1;
+    using HostMem = WideMem;
     struct Lane { HostMem mem; E3Half H[2]; HostTgt tgt; explicit Lane(int c) : mem(c) { H[0].phase = H[1].phase = 0; H[0].tk = H[1].tk = -1; } };
     std::vector<Lane> L;
     for (int l = 0; l < lanes; ++l) L.emplace_back(cap);

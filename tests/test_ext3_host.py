@@ -43,7 +43,7 @@ def oracle_results(pairs, h0s, ws, eb, flags, opt):
     return out
 
 
-def run_host(host, pairs, h0s, ws, eb, flags=0, scoring=None, cap=256, order=None):
+def run_host(host, pairs, h0s, ws, eb, flags=0, scoring=None, cap=256, order=None, narrow=None):
     opt = qmo_py.default_opt()
     for k, v in (scoring or {}).items():
         setattr(opt, k, v)
@@ -65,8 +65,13 @@ def run_host(host, pairs, h0s, ws, eb, flags=0, scoring=None, cap=256, order=Non
     out = np.zeros((n, FIELDS), np.int32)
     bad = np.zeros(n, np.uint8)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if narrow is None:            # both plane layouts (the byte planes only hold schemes with a + b <= 16)
+        n_run = run_host(host, pairs, h0s, ws, eb, flags, scoring, cap, order, narrow=0)
+        if opt.a + opt.b <= 16:
+            assert run_host(host, pairs, h0s, ws, eb, flags, scoring, cap, order, narrow=1) == n_run
+        return n_run
     rc = host.ext3_host_run(p(sc), C.c_int(cap), C.c_int64(n), p(seq), p(q_off), p(t_off), p(qlen), p(tlen), p(h0), p(w), C.c_int(eb),
-                            p(fl), p(out), p(bad))
+                            p(fl), p(out), p(bad), C.c_int(narrow))
     assert rc == 0
     want = oracle_results([pairs[i] for i in order], h0, w, eb, flags, opt)
     n_run, wrong = 0, []
