@@ -116,6 +116,73 @@ void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs,
     }
 }
 
+/* ---- indel alleles ("indel alleles into a small hash table"): every insertion / deletion operation of an
+ * admitted read's CIGAR, keyed by (anchor = the reference base in front of the event, type, length clamped to 255, the first 11
+ * inserted bases as the forward strand reads them + an "N among them" flag), forward and reverse reads counted apart.  Same
+ * admission as the counting above.  Records come out sorted by key.  out: 10 int32 per record {rid, pos, len, type, has_n, seq,
+ * n_fwd, n_rev, key_lo, key_hi}.  Returns the number of alleles (<= max_out are written). ---- */
+typedef struct { uint64_t key; int32_t rev; } ind_t;
+static int ind_cmp(const void *a, const void *b)
+{
+    const ind_t *x = (const ind_t *)a, *y = (const ind_t *)b;
+    return x->key < y->key ? -1 : x->key > y->key;
+}
+int64_t qmo_indels(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs, const qmo_aln_t *alns,
+                   const uint8_t *reads, int stride, const int32_t *lens, int32_t *out, int64_t max_out)
+{
+    int64_t r, n = 0, cap = 1024, m = 0, i;
+    ind_t *ev = (ind_t *)malloc(sizeof(ind_t) * (size_t)cap);
+    for (r = 0; r < 2 * n_pairs; ++r) {
+        const qmo_aln_t *a = &alns[r];
+        const uint8_t *rd = reads + r * stride;
+        const int L = lens[r], rev = (a->flag & 0x10) != 0;
+        int k, x = 0, p = a->pos, last_m = -1;
+        if (!admitted(po, a)) continue;
+        for (k = 0; k < a->n_cigar; ++k) {
+            const int op = a->cigar[k] & 0xf, len = (int)(a->cigar[k] >> 4);
+            if (op == 0) { x += len; p += len; last_m = p - 1; }
+            else if (op == 4) x += len;
+            else if (op == 1 || op == 2) {
+                if (last_m >= 0) {
+                    uint32_t seq = 0; int has_n = 0, j;
+                    if (op == 1)
+                        for (j = 0; j < len && j < 11; ++j) {
+                            int c = rev ? rd[L - 1 - (x + j)] : rd[x + j];
+                            c = rev ? (c > 3 ? 4 : 3 - c) : c;
+                            if (c > 3) has_n = 1; else seq |= (uint32_t)c << (2 * j);
+                        }
+                    if (n == cap) { cap *= 2; ev = (ind_t *)realloc(ev, sizeof(ind_t) * (size_t)cap); }
+                    ev[n].key = (uint64_t)(uint32_t)(R->off[a->rid] + last_m) << 32 | (uint64_t)(op == 2) << 31 |
+                                (uint64_t)(len > 255 ? 255 : len) << 23 | (uint64_t)has_n << 22 | (uint64_t)(seq & 0x3fffffu);
+                    ev[n].rev = rev;
+                    ++n;
+                }
+                if (op == 1) x += len; else p += len;
+            }
+        }
+    }
+    qsort(ev, (size_t)n, sizeof(ind_t), ind_cmp);
+    for (i = 0; i < n;) {
+        int64_t j = i;
+        int32_t nf = 0, nr = 0;
+        while (j < n && ev[j].key == ev[i].key) { if (ev[j].rev) ++nr; else ++nf; ++j; }
+        if (m < max_out) {
+            const uint64_t key = ev[i].key;
+            const int64_t g = (int64_t)(key >> 32);
+            int rid = 0, c;
+            int32_t *o = out + 10 * m;
+            for (c = 0; c < R->n_contigs; ++c) if (g >= R->off[c] && g < R->off[c] + R->len[c]) rid = c;
+            o[0] = rid; o[1] = (int32_t)(g - R->off[rid]); o[2] = (int32_t)((key >> 23) & 0xff); o[3] = (int32_t)((key >> 31) & 1);
+            o[4] = (int32_t)((key >> 22) & 1); o[5] = (int32_t)(key & 0x3fffffu); o[6] = nf; o[7] = nr;
+            o[8] = (int32_t)(uint32_t)key; o[9] = (int32_t)(uint32_t)(key >> 32);
+        }
+        ++m;
+        i = j;
+    }
+    free(ev);
+    return m;
+}
+
 /* ---- samtools mpileup text (reference call site rules/vcfcall.smk:39, consumer VarScan; upstream samtools 1.9
  * bam_plcmd.c mpileup / pileup_seq and htslib sam.c resolve_cigar2 are not vendored -- SURVEY.md A.10 is the spec).
  * Same read admission and mate-overlap quality rewrite as the counting above (BAQ off, no depth cap).  Reads enter a

@@ -260,6 +260,24 @@ def pileup(ref, alns, reads, quals, lens, popt=None):
     return counts
 
 
+def indels(ref, alns, reads, lens, popt=None, max_out=1 << 20):
+    """-> int32 [n, 10]: rid, pos, len, type (0 ins, 1 del), has_n, seq, n_fwd, n_rev, key_lo, key_hi; sorted by key"""
+    L = lib()
+    L.qmo_indels.restype = C.c_int64
+    L.qmo_indels.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+    if popt is None:
+        popt = PileupOpt()
+        L.qmo_pileup_opt_default(C.byref(popt))
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    alns = np.ascontiguousarray(alns, dtype=ALN_DTYPE)
+    out = np.zeros((max_out, 10), dtype=np.int32)
+    m = L.qmo_indels(ref._h, C.byref(popt), n // 2, alns.ctypes.data, reads.ctypes.data, stride, lens.ctypes.data, out.ctypes.data, max_out)
+    assert m <= max_out
+    return out[:m].copy()
+
+
 def mpileup_text(ref, alns, reads, quals, lens, names, popt=None):
     """-> bytes: samtools-mpileup text of the batch"""
     L = lib()

@@ -47,6 +47,9 @@ CALL_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("ref", "u1"), ("alt", "u
                        ("ad_ref_f", "<i4"), ("ad_ref_r", "<i4"), ("ad_alt_f", "<i4"), ("ad_alt_r", "<i4"),
                        ("qual", "<f4"), ("af", "<f4")])
 assert CALL_DTYPE.itemsize == 40
+INDEL_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("len", "<i4"), ("type", "u1"), ("has_n", "u1"), ("pad", "u1", (2,)),
+                        ("seq", "<u4"), ("n_fwd", "<i4"), ("n_rev", "<i4"), ("pad2", "<u4"), ("key", "<u8")])
+assert INDEL_DTYPE.itemsize == 40
 EXT_TASK_DTYPE = np.dtype([("q_off", "<u4"), ("t_off", "<u4"), ("qlen", "<i4"), ("tlen", "<i4"),
                            ("h0", "<i4"), ("w", "<i4"), ("end_bonus", "<i4"), ("flags", "<u4")])
 EXT_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
@@ -129,6 +132,14 @@ SIGNATURES = {
     "qm_counts_allreduce": (C.c_int, [_P, _P, _P, _L, _P]),
     "qm_counts_allreduce_nccl": (C.c_int, [_P, _P, _P, _L, _P]),
     "qm_pestat_bcast": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "qm_comm_allgather": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
+    "qm_indel_table_create": (C.c_int, [_P, C.c_int, C.POINTER(C.c_void_p)]),
+    "qm_indel_table_destroy": (None, [_P]),
+    "qm_indel_table_reset": (C.c_int, [_P, _P]),
+    "qm_indel_table_fetch_host": (C.c_int, [_P, _P, _P, _L, C.POINTER(C.c_int64)]),
+    "qm_indel_table_merge": (C.c_int, [_P, _P, _L, _P]),
+    "qm_pileup_accumulate_indels": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _P]),
+    "qm_sample_indel_table": (_P, [_P]),
     "qm_sample_set_comm": (C.c_int, [_P, _P]),
     "qm_sample_allreduce_counts": (C.c_int, [_P, _P]),
     "qm_dpx_peak_sync": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

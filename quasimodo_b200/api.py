@@ -182,6 +182,15 @@ class Sample:
         _check(self.ctx._h, rc, "qm_sample_stats_sync")
         return n.value, c.value
 
+    def indels(self, max_out=1 << 18):
+        """the sample's indel alleles -> structured array INDEL_DTYPE, sorted by (position, type, length, bases)"""
+        out = np.zeros(max_out, dtype=_lib.INDEL_DTYPE)
+        n = C.c_int64()
+        tab = _lib.lib().qm_sample_indel_table(self._h)
+        rc = _lib.lib().qm_indel_table_fetch_host(tab, self.idx._h, out.ctypes.data, max_out, C.byref(n))
+        _check(self.ctx._h, rc, "qm_indel_table_fetch_host")
+        return out[:n.value].copy()
+
     def counts_host(self):
         rows = np.empty((self.idx.l_pac, _lib.NCH), dtype=np.int32)
         _check(self.ctx._h, _lib.lib().qm_sample_counts_host(self._h, rows.ctypes.data), "qm_sample_counts_host")

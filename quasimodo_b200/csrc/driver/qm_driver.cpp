@@ -33,6 +33,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -594,8 +595,13 @@ std::string trim_float3(double x)
     return s;
 }
 
+// An indel allele that passes the caller's thresholds (same rule as the SNPs: raw depth at the anchor >= min_dp, supporting
+// reads >= min_alt and >= min_af x depth), as the VCF shows it: anchor base first, POS = anchor (the convention of
+// program/mummer2vcf.py for the truth set and of bcftools).
+struct IndelCall { qm_indel a; int dp; double af, qual; };
+
 void write_vcf(const std::string &path, const Genome &g, const std::string &sample, const std::string &ref_path,
-               const std::vector<qm_call> &calls)
+               const std::vector<qm_call> &calls, const std::vector<IndelCall> &indels)
 {
     FILE *fp = fopen(path.c_str(), "w");
     if (!fp) die(2, "cannot create %s", path.c_str());
@@ -605,12 +611,30 @@ void write_vcf(const std::string &path, const Genome &g, const std::string &samp
     for (size_t c = 0; c < g.names.size(); ++c) fprintf(fp, "##contig=<ID=%s,length=%lld>\n", g.names[c].c_str(), (long long)g.lens[c]);
     fprintf(fp, "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Raw read depth\">\n"
                 "##INFO=<ID=AF,Number=1,Type=Float,Description=\"Alternate allele fraction among bases passing the BQ filter\">\n"
-                "##INFO=<ID=DP4,Number=4,Type=Integer,Description=\"ref-forward, ref-reverse, alt-forward, alt-reverse bases\">\n"
-                "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+                "##INFO=<ID=DP4,Number=4,Type=Integer,Description=\"ref-forward, ref-reverse, alt-forward, alt-reverse bases\">\n");
+    if (!indels.empty())
+        fprintf(fp, "##INFO=<ID=INDEL,Number=0,Type=Flag,Description=\"Indicates that the variant is an INDEL.\">\n"
+                    "##INFO=<ID=IDV,Number=1,Type=Integer,Description=\"Reads supporting the indel (forward + reverse)\">\n"
+                    "##INFO=<ID=ADF,Number=1,Type=Integer,Description=\"Supporting forward reads\">\n"
+                    "##INFO=<ID=ADR,Number=1,Type=Integer,Description=\"Supporting reverse reads\">\n");
+    fprintf(fp, "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
                 "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n", sample.c_str());
-    for (const qm_call &c : calls)
+    size_t k = 0;
+    auto put_indel = [&](const IndelCall &x) {
+        const qm_indel &a = x.a;
+        const uint8_t *ref = g.codes.data() + g.offs[a.rid] + a.pos;
+        std::string r(1, "ACGT"[ref[0]]), alt(1, "ACGT"[ref[0]]);
+        if (a.type == 1) { for (int i = 1; i <= a.len && a.pos + i < g.lens[a.rid]; ++i) r.push_back("ACGT"[ref[i]]); }
+        else for (int i = 0; i < a.len; ++i) alt.push_back(i < QM_INDEL_SEQ_BASES && !(a.has_n) ? "ACGT"[(a.seq >> (2 * i)) & 3] : 'N');
+        fprintf(fp, "%s\t%d\t.\t%s\t%s\t%s\tPASS\tINDEL;DP=%d;AF=%.3f;IDV=%d;ADF=%d;ADR=%d\tGT\t1\n", g.names[a.rid].c_str(), a.pos + 1, r.c_str(),
+                alt.c_str(), trim_float3(x.qual).c_str(), x.dp, x.af, a.n_fwd + a.n_rev, a.n_fwd, a.n_rev);
+    };
+    for (const qm_call &c : calls) {
+        while (k < indels.size() && (indels[k].a.rid < c.rid || (indels[k].a.rid == c.rid && indels[k].a.pos < c.pos))) put_indel(indels[k++]);
         fprintf(fp, "%s\t%d\t.\t%c\t%c\t%s\tPASS\tDP=%d;AF=%.3f;DP4=%d,%d,%d,%d\tGT\t1\n", g.names[c.rid].c_str(), c.pos + 1,
                 "ACGT"[c.ref], "ACGT"[c.alt], trim_float3((double)c.qual).c_str(), c.dp, (double)c.af, c.ad_ref_f, c.ad_ref_r, c.ad_alt_f, c.ad_alt_r);
+    }
+    while (k < indels.size()) put_indel(indels[k++]);
     if (fclose(fp) != 0) die(2, "write error on %s", path.c_str());
 }
 
@@ -950,7 +974,29 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         int64_t nc = 0;
         L.check(qm_sample_call_snps_host(smp, &copt, calls.data(), (int64_t)calls.size(), &nc), "qm_sample_call_snps_host");
         calls.resize((size_t)nc);
-        write_vcf(vcf, g, a.get("sample", "sample"), split(a.get("ref"), ',')[0], calls);
+        // indel records (--indels 0 leaves them out): the sample's allele table against the raw depth at the anchor
+        std::vector<IndelCall> icalls;
+        if (atoi(a.get("indels", "1").c_str())) {
+            std::vector<qm_indel> tab((size_t)1 << 18);
+            int64_t nt = 0;
+            L.check(qm_indel_table_fetch_host(qm_sample_indel_table(smp), idx, tab.data(), (int64_t)tab.size(), &nt), "qm_indel_table_fetch_host");
+            std::vector<int32_t> rows(g.codes.size() * QM_NCH);
+            L.check(qm_sample_counts_host(smp, rows.data()), "qm_sample_counts_host");
+            for (int64_t i = 0; i < nt; ++i) {
+                const qm_indel &x = tab[(size_t)i];
+                const int dp = rows[(size_t)(g.offs[x.rid] + x.pos) * QM_NCH + 14], ad = x.n_fwd + x.n_rev;
+                if (dp < copt.min_dp || ad < copt.min_alt || (double)ad < (double)copt.min_af * dp) continue;
+                IndelCall c;
+                c.a = x; c.dp = dp; c.af = dp > 0 ? (double)ad / dp : 0.0;
+                const double f = c.af > 1.0 ? 1.0 : c.af, e = 0.002;     // same Chernoff-bound QUAL as the SNP records
+                double kl = f > 0 ? f * log(f / e) : 0.0;
+                if (f < 1.0) kl += (1.0 - f) * log((1.0 - f) / (1.0 - e));
+                const double q = f > e ? 4.342944819032518 * dp * kl : 0.0;
+                c.qual = q > 999.0 ? 999.0 : q;
+                icalls.push_back(c);
+            }
+        }
+        write_vcf(vcf, g, a.get("sample", "sample"), split(a.get("ref"), ',')[0], calls, icalls);
         // rule `bcftools` declares vcf_bgz = vcf + ".gz" and tabix-indexes it (rules/vcfcall.smk:107,118-119): written unless --vcf-gz 0
         if (atoi(a.get("vcf-gz", "1").c_str())) write_vcf_gz_tbi(vcf, vcf + ".gz", threads);
     }

@@ -132,7 +132,8 @@ struct E3Half {
     int qlen, tlen, h0, w0, w, end_bonus, tries_left, prev, cells;
     int i, beg, end;
     int mx, mx_i, mx_j, mx_ie, gscore, max_off;
-    int tb_next;            // target base of row i, fetched one row ahead
+    int tb_next;            // target byte of row i as fetched one row ahead (Tgt::decode turns it into a base code when the row
+                            // starts: nothing may touch the loaded value earlier, or the row waits for the load at once)
 };
 
 struct E3Result { int score, qle, tle, gtle, gscore, max_off, w_used, cells; };
@@ -142,7 +143,7 @@ struct E3Result { int score, qle, tle, gtle, gscore, max_off, w_used, cells; };
 //   put(j, h2, e2)                  store eh[j] of both tasks
 //   set_he(j, X, h, e), zero(j, X)  eh[j] of task X alone (row -1, eh[end], the trimming scans)
 //   set_q(j, X, code)               query code of task X at column j;  Mem::kNarrow tells which code set is in use
-// Tgt: base(X, i) -> target base code (0..4) of row i of task X.
+// Tgt: raw(X, i) -> the stored byte of row i of task X's target; decode(X, byte) -> its base code 0..4.
 
 // row -1 of one half (SURVEY.md A.3 first lines) and the band clamp of this try
 template <class Mem, class Tgt>
@@ -168,7 +169,7 @@ E3_HD void e3_start_try(const E3Consts &K, E3Half &H, int X, Mem &mem, Tgt &tgt)
     H.w = w;                                         // clamped band of this try (w_used reports the unclamped one)
     H.mx = h0; H.mx_i = -1; H.mx_j = -1; H.mx_ie = -1; H.gscore = -1; H.max_off = 0;
     H.beg = 0; H.end = qlen; H.i = 0;
-    H.tb_next = H.tlen > 0 ? tgt.base(X, 0) : 0;
+    H.tb_next = H.tlen > 0 ? tgt.raw(X, 0) : 0;
     H.phase = 2;
 }
 
@@ -206,8 +207,8 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
     int begA = 0, endA = 0, begB = 0, endB = 0, h1A = 0, h1B = 0;
     unsigned tmA = 0, tmB = 0, flA = 0, flB = 0;
     if (ra) {
-        const int i = A.i, tb = A.tb_next;
-        if (i + 1 < A.tlen) A.tb_next = tgt.base(0, i + 1);
+        const int i = A.i, tb = tgt.decode(0, A.tb_next);
+        if (i + 1 < A.tlen) A.tb_next = tgt.raw(0, i + 1);
         begA = A.beg > i - A.w ? A.beg : i - A.w;
         endA = A.end < i + A.w + 1 ? A.end : i + A.w + 1;
         endA = endA < A.qlen ? endA : A.qlen;
@@ -215,8 +216,8 @@ E3_HD void e3_row(const E3Consts &K, E3Half &A, E3Half &B, Mem &mem, Tgt &tgt, b
         tmA = e3_tmask<Mem::kNarrow>(tb); flA = e3_tfloor(S, tb);
     }
     if (rb) {
-        const int i = B.i, tb = B.tb_next;
-        if (i + 1 < B.tlen) B.tb_next = tgt.base(1, i + 1);
+        const int i = B.i, tb = tgt.decode(1, B.tb_next);
+        if (i + 1 < B.tlen) B.tb_next = tgt.raw(1, i + 1);
         begB = B.beg > i - B.w ? B.beg : i - B.w;
         endB = B.end < i + B.w + 1 ? B.end : i + B.w + 1;
         endB = endB < B.qlen ? endB : B.qlen;

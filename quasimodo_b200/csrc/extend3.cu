@@ -66,11 +66,8 @@ struct DevTgt {                             // where the two tasks' target rows 
     const uint8_t *p[2];
     int step[2];
     int flip[2];                            // 3 on the reverse-complement strand of the doubled coordinates, else 0
-    __device__ __forceinline__ int base(int X, int i) const
-    {
-        const int c = p[X][(int64_t)i * step[X]] ^ flip[X];
-        return c > 4 ? 4 : c;
-    }
+    __device__ __forceinline__ int raw(int X, int i) const { return p[X][(int64_t)i * step[X]]; }
+    __device__ __forceinline__ int decode(int X, int c) const { c ^= flip[X]; return c > 4 ? 4 : c; }
     // a task's window never crosses the strand boundary (mem_chain2aln clamps rmax[] to one strand), so the strand test of
     // qm_ref_base is made once per task instead of once per row
     __device__ __forceinline__ void set(int X, const IndexView &V, const ExtTaskI &t)

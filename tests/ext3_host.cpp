@@ -42,7 +42,8 @@ struct NarrowMem {                      // byte planes: one 32-bit word (h | e <
 struct HostTgt {
     const uint8_t *t[2];
     int n[2];
-    int base(int X, int i) const { if (i < 0 || i >= n[X]) __builtin_trap(); return t[X][i] > 4 ? 4 : t[X][i]; }
+    int raw(int X, int i) const { if (i < 0 || i >= n[X]) __builtin_trap(); return t[X][i]; }
+    int decode(int, int c) const { return c > 4 ? 4 : c; }
 };
 struct HostQry { const uint8_t *q; int code(int j) const { return q[j] > 4 ? 4 : q[j]; } };
 }  // namespace

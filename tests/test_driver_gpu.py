@@ -133,8 +133,21 @@ def test_driver_vcf_matches_python_writer(ctx, sample_case, tmp_path):
     want = str(tmp_path / "py.vcf")
     formats.write_vcf(want, W.ref, "TM-1-1", calls)
     a = [ln for ln in open(want) if not ln.startswith("##reference")]
-    b = [ln for ln in open(sample_case["vcf"]) if not ln.startswith("##reference")]
+    full = [ln for ln in open(sample_case["vcf"]) if not ln.startswith("##reference")]
+    indel_hdr = ("##INFO=<ID=INDEL", "##INFO=<ID=IDV", "##INFO=<ID=ADF", "##INFO=<ID=ADR")
+    b = [ln for ln in full if not ln.startswith(indel_hdr) and "\tINDEL;" not in ln]
     assert a == b
+    # the indel records (AD169 reads against Merlin carry real strain indels): anchor base first, sorted in with the SNPs
+    ind = [ln.split("\t") for ln in full if "\tINDEL;" in ln]
+    assert len(ind) > 3
+    codes, names = W.ref.codes, list(W.ref.names)
+    offs = np.concatenate([[0], np.cumsum(W.ref.lens)])
+    for f in ind:
+        o = offs[names.index(f[0])] + int(f[1]) - 1
+        assert f[3][0] == f[4][0] == "ACGT"[codes[o]] and (len(f[3]) == 1) != (len(f[4]) == 1)
+        assert f[3] == "".join("ACGT"[c] for c in codes[o:o + len(f[3])])
+    pos = [(names.index(ln.split("\t")[0]), int(ln.split("\t")[1])) for ln in full if not ln.startswith("#")]
+    assert pos == sorted(pos)
     s.close()
     idx.close()
 
