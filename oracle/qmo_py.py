@@ -325,6 +325,59 @@ def run_sample(ref, codes, quals, lens, pair_id0=0, opt=None, popt=None, prefix=
     return alns, counts, o["cells"], pes
 
 
+class FmIndex:
+    """bwa's FM-index (oracle/qmo_fm.c): built from the packed genome as `bwa index` builds it, or loaded from bwa's own
+    .bwt / .sa files; bwt_bytes() / sa_bytes() serialise it exactly as bwa writes those files"""
+
+    def __init__(self, codes=None, bwt=None, sa=None, sa_intv=32):
+        L = lib()
+        L.qmo_fm_build.restype = C.c_void_p
+        L.qmo_fm_build.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+        L.qmo_fm_load.restype = C.c_void_p
+        L.qmo_fm_load.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.qmo_fm_free.argtypes = [C.c_void_p]
+        for f in ("qmo_fm_bwt_bytes", "qmo_fm_sa_bytes"):
+            getattr(L, f).restype = C.c_int64
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+        L.qmo_fm_seeds.restype = C.c_int
+        L.qmo_fm_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        if codes is not None:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            self._h = L.qmo_fm_build(codes.ctypes.data, len(codes), sa_intv)
+        else:
+            b, s = np.frombuffer(bwt, np.uint8), np.frombuffer(sa, np.uint8)
+            self._h = L.qmo_fm_load(b.ctypes.data, len(b), s.ctypes.data, len(s))
+        if not self._h:
+            raise ValueError("FM-index: inconsistent .bwt / .sa contents")
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().qmo_fm_free(self._h)
+        except Exception:
+            pass
+
+    def _bytes(self, fn):
+        n = fn(self._h, None)
+        out = np.zeros(n, np.uint8)
+        fn(self._h, out.ctypes.data)
+        return out.tobytes()
+
+    def bwt_bytes(self):
+        return self._bytes(lib().qmo_fm_bwt_bytes)
+
+    def sa_bytes(self):
+        return self._bytes(lib().qmo_fm_sa_bytes)
+
+    def seeds(self, ref, read, opt=None, max_mem_intv=20, max_seeds=4096):
+        """bwa-mem's seeds of one read (codes 0..4), in the order mem_chain visits them -> int64 [n, 3]: rbeg, qbeg, len"""
+        opt = opt or default_opt()
+        q = np.ascontiguousarray(read, dtype=np.uint8)
+        out = np.zeros((max_seeds, 3), np.int64)
+        n = lib().qmo_fm_seeds(self._h, ref._h, C.byref(opt), len(q), q.ctypes.data, max_mem_intv, out.ctypes.data, max_seeds)
+        return out[:min(n, max_seeds)].copy()
+
+
 _SIM = None
 
 
