@@ -52,6 +52,8 @@ typedef struct {
     int32_t reserved[2];
 } qm_opt;
 #define QM_F_NO_RESCUE 1          /* bwa mem -S: skip mate rescue                        */
+#define QM_F_FM_SEEDS  2          /* seeds through bwa's FM-index (qm_index_attach_bwa / _build_fm) instead of the k-mer hash */
+#define QM_F_FM_NO_ROUND3 4       /* with QM_F_FM_SEEDS: skip the third seeding round (bwa's max_mem_intv = 0)       */
 
 void qm_opt_default(qm_opt *opt);
 
@@ -107,6 +109,15 @@ int     qm_index_build(qm_ctx *ctx, const uint8_t *h_codes /* 0..3 */, int n_con
                        int k, qm_index **out);
 void    qm_index_destroy(qm_ctx *ctx, qm_index *idx);
 int64_t qm_index_lpac(const qm_index *idx);
+/* bwa's own FM-index of the same genome as an alternative seeder: with qm_opt.flags & QM_F_FM_SEEDS the seeds
+ * are bwa-mem's -- the three rounds of mem_collect_intv (SMEMs, re-seeding, the LAST-like round) and the suffix-array walk of
+ * mem_chain, at most QM_MAX_SEEDS per read in bwa's order -- instead of all exact matches of the k-mer hash index.
+ * qm_index_attach_bwa takes the bytes of the index files `bwa index` wrote (rules/index.smk:13: X.bwt and X.sa; the reference
+ * ships them as ref/X.bwt, ref/X.sa); qm_index_build_fm rebuilds the same bytes from the genome given to qm_index_build;
+ * qm_index_fm_export returns them (pass NULL buffers for the sizes).  Host work, once per genome. */
+int qm_index_attach_bwa(qm_ctx *ctx, qm_index *idx, const uint8_t *h_bwt, int64_t bwt_bytes, const uint8_t *h_sa, int64_t sa_bytes);
+int qm_index_build_fm(qm_ctx *ctx, qm_index *idx, const uint8_t *h_codes);
+int qm_index_fm_export(const qm_index *idx, uint8_t *h_bwt, int64_t *bwt_bytes, uint8_t *h_sa, int64_t *sa_bytes);
 
 /* ---- alignment of read pairs (replaces `bwa mem -k 31 ref r1 r2`, rules/bwa.smk:15) ----
  * Read batch layout: see the simulator below (codes/quals, reads 2i and 2i+1 are mates).

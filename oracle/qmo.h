@@ -46,6 +46,7 @@ typedef struct {
     int32_t reserved[2];
 } qmo_opt_t;
 #define QMO_F_NO_RESCUE 1         /* bwa mem -S: skip mate rescue                       */
+#define QMO_F_FM_SEEDS  2         /* seeds from bwa's FM-index (qmo_ref_set_fm) instead of the k-mer hash index */
 
 void qmo_opt_default(qmo_opt_t *o);
 
@@ -81,6 +82,7 @@ typedef struct qmo_ref qmo_ref_t;
 qmo_ref_t *qmo_ref_create(const uint8_t *codes, int n_contigs, const int64_t *lens, int k);
 void qmo_ref_destroy(qmo_ref_t *r);
 int64_t qmo_ref_lpac(const qmo_ref_t *r);
+void qmo_ref_set_fm(qmo_ref_t *r, const void *fm /* qmo_fm_t, not owned */, int max_mem_intv);
 
 typedef struct { int64_t rbeg; int32_t qbeg, len; } qmo_seed_t;              /* 16 B */
 typedef struct {

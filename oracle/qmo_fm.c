@@ -15,8 +15,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#include "qmo.h"
-struct qmo_ref { int n_contigs, k; int64_t l_pac, *off, *len; uint8_t *fwd; int64_t n_km; uint64_t *km_key; uint32_t *km_pos; };
+#include "qmo_priv.h"
 
 #define OCC_INTV 128
 
@@ -213,8 +212,9 @@ static void fm_extend(const qmo_fm_t *F, const fm_intv *ik, fm_intv ok[4], int i
 }
 
 /* bwt.c bwt_smem1a with max_intv = 0 (what bwt_smem1 passes): all SMEMs through position x, leftmost first */
-#define QMO_FM_MAXV 512
-static int fm_smem1(const qmo_fm_t *F, int len, const uint8_t *q, int x, int64_t min_intv, fm_intv *mem, int *n_mem)
+#define QMO_FM_MAXV 48            /* interval sizes one forward search can pass through (limit shared with the device code) */
+#define QMO_FM_MAXIV 96           /* intervals collected per read over the three rounds (shared limit) */
+static int fm_smem1(const qmo_fm_t *F, int len, const uint8_t *q, int x, int64_t min_intv, fm_intv *mem, int *n_mem, int max_mem)
 {
     fm_intv ik, ok[4], va[QMO_FM_MAXV], vb[QMO_FM_MAXV], *prev = va, *curr = vb, *swap;
     int i, j, c, ret, n_prev = 0, n_curr = 0;
@@ -247,7 +247,7 @@ static int fm_smem1(const qmo_fm_t *F, int len, const uint8_t *q, int x, int64_t
                 if (n_curr == 0) {
                     if (*n_mem == 0 || i + 1 < (int)(mem[*n_mem - 1].info >> 32)) {
                         ik = *p; ik.info |= (int64_t)(i + 1) << 32;
-                        if (*n_mem < QMO_FM_MAXV) mem[(*n_mem)++] = ik;
+                        if (*n_mem < max_mem) mem[(*n_mem)++] = ik;
                     }
                 }
             } else if (n_curr == 0 || ok[c].x2 != curr[n_curr - 1].x2) {
@@ -303,26 +303,27 @@ static int64_t fm_sa(const qmo_fm_t *F, int64_t k)
 /* bwamem.c mem_collect_intv + the seed loop of mem_chain: intervals of the three rounds sorted by (start, end) of the match,
  * each turned into at most max_occ seeds (every step-th occurrence), seeds that bridge two contigs or the strand boundary
  * dropped.  seeds: {rbeg (doubled coordinates), qbeg, len} in bwa's order; returns their number (<= max_seeds are written). */
-int qmo_fm_seeds(const qmo_fm_t *F, const qmo_ref_t *R, const qmo_opt_t *o, int len, const uint8_t *q, int max_mem_intv,
+int qmo_fm_seeds(const void *Fv, const qmo_ref_t *R, const qmo_opt_t *o, int len, const uint8_t *q, int max_mem_intv,
                  int64_t *seeds /* 3 per seed */, int max_seeds)
 {
-    fm_intv mem[4 * QMO_FM_MAXV], m1[QMO_FM_MAXV];
+    const qmo_fm_t *F = (const qmo_fm_t *)Fv;
+    fm_intv mem[QMO_FM_MAXIV], m1[QMO_FM_MAXIV];
     int n = 0, n1, x = 0, i, k, old_n, ns = 0;
     const int split_len = (int)(o->min_seed_len * 1.5 + .499), split_width = 10;
     while (x < len) {
         if (q[x] < 4) {
-            x = fm_smem1(F, len, q, x, 1, m1, &n1);
+            x = fm_smem1(F, len, q, x, 1, m1, &n1, QMO_FM_MAXIV - n);
             for (i = 0; i < n1; ++i)
-                if ((int)(uint32_t)m1[i].info - (int)(m1[i].info >> 32) >= o->min_seed_len && n < 4 * QMO_FM_MAXV) mem[n++] = m1[i];
+                if ((int)(uint32_t)m1[i].info - (int)(m1[i].info >> 32) >= o->min_seed_len && n < QMO_FM_MAXIV) mem[n++] = m1[i];
         } else ++x;
     }
     old_n = n;
     for (k = 0; k < old_n; ++k) {
         const int start = (int)(mem[k].info >> 32), end = (int)(uint32_t)mem[k].info;
         if (end - start < split_len || mem[k].x2 > split_width) continue;
-        fm_smem1(F, len, q, (start + end) >> 1, mem[k].x2 + 1, m1, &n1);
+        fm_smem1(F, len, q, (start + end) >> 1, mem[k].x2 + 1, m1, &n1, QMO_FM_MAXIV - n);
         for (i = 0; i < n1; ++i)
-            if ((int)(uint32_t)m1[i].info - (int)(m1[i].info >> 32) >= o->min_seed_len && n < 4 * QMO_FM_MAXV) mem[n++] = m1[i];
+            if ((int)(uint32_t)m1[i].info - (int)(m1[i].info >> 32) >= o->min_seed_len && n < QMO_FM_MAXIV) mem[n++] = m1[i];
     }
     if (max_mem_intv > 0) {
         x = 0;
@@ -330,7 +331,7 @@ int qmo_fm_seeds(const qmo_fm_t *F, const qmo_ref_t *R, const qmo_opt_t *o, int 
             if (q[x] < 4) {
                 fm_intv m;
                 x = fm_seed_strategy1(F, len, q, x, o->min_seed_len, max_mem_intv, &m);
-                if (m.x2 > 0 && n < 4 * QMO_FM_MAXV) mem[n++] = m;
+                if (m.x2 > 0 && n < QMO_FM_MAXIV) mem[n++] = m;
             } else ++x;
         }
     }

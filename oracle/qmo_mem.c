@@ -14,16 +14,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
-#include "qmo.h"
+#include "qmo_priv.h"
 
-struct qmo_ref {
-    int n_contigs, k;
-    int64_t l_pac, *off, *len;
-    uint8_t *fwd;
-    int64_t n_km;
-    uint64_t *km_key;
-    uint32_t *km_pos;
-};
 
 typedef struct { uint64_t key; uint32_t pos; } kmpair_t;
 static int kmpair_cmp(const void *a, const void *b)
@@ -433,6 +425,20 @@ static int sort_dedup(const qmo_opt_t *o, int n, qmo_reg_t *a)
     return n ? m : 0;
 }
 
+/* bwa's own seeds (opt.flags & QMO_F_FM_SEEDS): SMEMs + re-seeding + third round through the FM-index attached with
+ * qmo_ref_set_fm, in the order mem_chain visits them, the first QMO_MAX_SEEDS of them */
+void qmo_ref_set_fm(qmo_ref_t *R, const void *fm, int max_mem_intv) { R->fm = fm; R->fm_max_mem_intv = max_mem_intv; }
+static int fm_collect(const qmo_ref_t *R, const qmo_opt_t *o, const uint8_t *q, int len, qmo_seed_t *S)
+{
+    int64_t tmp[3 * QMO_MAX_SEEDS];
+    int i, n;
+    if (!R->fm) return 0;
+    n = qmo_fm_seeds(R->fm, R, o, len, q, R->fm_max_mem_intv, tmp, QMO_MAX_SEEDS);
+    if (n > QMO_MAX_SEEDS) n = QMO_MAX_SEEDS;
+    for (i = 0; i < n; ++i) { S[i].rbeg = tmp[3 * i]; S[i].qbeg = (int32_t)tmp[3 * i + 1]; S[i].len = (int32_t)tmp[3 * i + 2]; }
+    return n;
+}
+
 void qmo_align_se(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n, const uint8_t *reads, int stride,
                   const int32_t *lens, qmo_seed_t *seeds, int32_t *n_seeds, qmo_reg_t *regs, int32_t *n_regs,
                   qmo_ext_log_t *log, int64_t *cells_total)
@@ -445,7 +451,7 @@ void qmo_align_se(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n, const uint8
         chain_t *chn = (chain_t *)malloc(sizeof(chain_t) * QMO_MAX_SEEDS);
         qmo_reg_t av[QMO_MAX_REGS];
         const uint8_t *q = reads + r * stride;
-        int ns = qmo_collect_seeds(R, o, q, lens[r], S);
+        int ns = (o->flags & QMO_F_FM_SEEDS) ? fm_collect(R, o, q, lens[r], S) : qmo_collect_seeds(R, o, q, lens[r], S);
         int nc = build_chains(R, o, S, ns, chn), c, nav = 0;
         int64_t mycells = 0;
         for (c = 0; c < nc; ++c) chain_to_regs(R, o, lens[r], q, S, &chn[c], av, &nav, log, &mycells);

@@ -6,10 +6,9 @@
  */
 #include <stdlib.h>
 #include <string.h>
-#include "qmo.h"
+#include "qmo_priv.h"
 
 /* mirror of the private layout in qmo_mem.c: only offsets are needed here */
-struct qmo_ref { int n_contigs, k; int64_t l_pac, *off, *len; uint8_t *fwd; int64_t n_km; uint64_t *km_key; uint32_t *km_pos; };
 
 void qmo_pileup_opt_default(qmo_pileup_opt_t *p) { p->min_mapq = 0; p->min_bq = 13; p->count_orphans = 0; p->ignore_overlaps = 0; }
 

@@ -145,10 +145,20 @@ class Ref:
         self.k = k
         self._h = L.qmo_ref_create(codes.ctypes.data, len(lens), lens.ctypes.data, k)
 
+    def set_fm(self, fm, max_mem_intv=20):
+        """attach bwa's FM-index of the same genome (FmIndex, kept alive here): opt.flags |= F_FM_SEEDS then seeds through it"""
+        L = lib()
+        L.qmo_ref_set_fm.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._fm = fm
+        L.qmo_ref_set_fm(self._h, fm._h if fm is not None else None, max_mem_intv)
+
     def __del__(self):
         if getattr(self, "_h", None):
             lib().qmo_ref_destroy(self._h)
             self._h = None
+
+
+F_NO_RESCUE, F_FM_SEEDS = 1, 2
 
 
 def _libc_free(ptr):

@@ -42,6 +42,7 @@ class CallOpt(C.Structure):
 
 MAX_SEEDS, MAX_REGS, MAX_CIGAR, NCH, N_STAGES, PESTAT_PAIRS = 64, 16, 21, 16, 9, 65536
 F_NO_RESCUE = 1          # qm_opt.flags: bwa mem -S
+F_FM_SEEDS, F_FM_NO_ROUND3 = 2, 4   # seeds through bwa's FM-index; without its third seeding round
 STAGES = ("seed_chain", "advance", "extend", "pair_cigar", "pileup", "h2d", "d2h", "other", "rescue")
 CALL_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("ref", "u1"), ("alt", "u1"), ("pad", "u1", (2,)), ("dp", "<i4"),
                        ("ad_ref_f", "<i4"), ("ad_ref_r", "<i4"), ("ad_alt_f", "<i4"), ("ad_alt_r", "<i4"),
@@ -81,6 +82,9 @@ SIGNATURES = {
     "qm_index_build": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.POINTER(C.c_void_p)]),
     "qm_index_destroy": (None, [_P, _P]),
     "qm_index_lpac": (_L, [_P]),
+    "qm_index_attach_bwa": (C.c_int, [_P, _P, _P, _L, _P, _L]),
+    "qm_index_build_fm": (C.c_int, [_P, _P, _P]),
+    "qm_index_fm_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64)]),
     "qm_collect_seeds": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P]),
     "qm_align_se": (C.c_int, [_P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
     "qm_pestat_sync": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P]),

@@ -32,6 +32,23 @@ class Index:
         self.l_pac = int(_lib.lib().qm_index_lpac(self._h))
         self.offsets = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
 
+    def build_fm(self):
+        """bwa's FM-index of this genome, rebuilt here (enables opt.flags |= F_FM_SEEDS)"""
+        codes = np.ascontiguousarray(self.genome.codes, dtype=np.uint8)
+        _check(self.ctx._h, _lib.lib().qm_index_build_fm(self.ctx._h, self._h, codes.ctypes.data), "qm_index_build_fm")
+
+    def attach_bwa(self, bwt_bytes, sa_bytes):
+        """bwa's own index files (the bytes of X.bwt and X.sa) as this index's FM-index"""
+        b, s = np.frombuffer(bwt_bytes, np.uint8), np.frombuffer(sa_bytes, np.uint8)
+        _check(self.ctx._h, _lib.lib().qm_index_attach_bwa(self.ctx._h, self._h, b.ctypes.data, len(b), s.ctypes.data, len(s)), "qm_index_attach_bwa")
+
+    def fm_export(self):
+        nb, ns = C.c_int64(), C.c_int64()
+        _check(self.ctx._h, _lib.lib().qm_index_fm_export(self._h, None, C.byref(nb), None, C.byref(ns)), "qm_index_fm_export")
+        b, s = np.zeros(nb.value, np.uint8), np.zeros(ns.value, np.uint8)
+        _check(self.ctx._h, _lib.lib().qm_index_fm_export(self._h, b.ctypes.data, C.byref(nb), s.ctypes.data, C.byref(ns)), "qm_index_fm_export")
+        return b.tobytes(), s.tobytes()
+
     def close(self):
         if getattr(self, "_h", None) and self.ctx._h:
             _lib.lib().qm_index_destroy(self.ctx._h, self._h)

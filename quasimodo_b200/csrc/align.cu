@@ -481,6 +481,41 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
     return cudaGetLastError();
 }
 
+// ---- bwa's own seeds (opt.flags & QM_F_FM_SEEDS): FM-index search of fm_core.cuh, one thread per read, then the same
+// chaining.  The seeds come in mem_chain's order (not sorted by position): build_plan takes them as they are, like bwa. ----
+struct CtgView { int n; const int64_t *off, *len; int64_t l_pac; };
+
+__global__ void __launch_bounds__(128)
+fm_seed_kernel(IndexView V, FmView F, qm_opt o, int max_mem_intv, const uint8_t *__restrict__ codes, int stride,
+               const int32_t *__restrict__ lens, int64_t n, qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds,
+               uint16_t *__restrict__ plan, uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    CtgView G = {V.n_contigs, V.off, V.len, V.l_pac};
+    FmSeedOut tmp[QM_MAX_SEEDS];
+    const int ns = fm_collect_seeds(F, G, o.min_seed_len, o.max_occ, max_mem_intv, lens[r], codes + r * stride, 1, tmp, QM_MAX_SEEDS);
+    qm_seed *S = seeds + r * QM_MAX_SEEDS;
+    for (int i = 0; i < ns; ++i) { qm_seed s; s.rbeg = tmp[i].rbeg; s.qbeg = tmp[i].qbeg; s.len = tmp[i].len; S[i] = s; }
+    n_seeds[r] = ns;
+    if (seeds_only) return;
+    const int np = build_plan(V, o, S, ns, plan + r * QM_MAX_SEEDS);
+    n_plan[r] = (uint8_t)np;
+    ReadState s;
+    s.cursor = 0; s.phase = PH_NEXT; s.n_av = 0; s.task = -1;
+    st[r] = s;
+}
+
+static cudaError_t launch_fm_seed(const qm_index *idx, const qm_opt &o, const uint8_t *codes, int stride, const int32_t *lens, int64_t n,
+                                  qm_seed *seeds, int32_t *n_seeds, uint16_t *plan, uint8_t *n_plan, ReadState *st, bool seeds_only,
+                                  cudaStream_t stream)
+{
+    const int max_mem_intv = (o.flags & QM_F_FM_NO_ROUND3) ? 0 : 20;          // bwa's max_mem_intv
+    fm_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(idx->v, idx->fm, o, max_mem_intv, codes, stride, lens, n, seeds, n_seeds,
+                                                                      plan, n_plan, st, seeds_only);
+    return cudaGetLastError();
+}
+
 struct RoundCounters {        // zeroed before every advance round; the host reads back the first kRoundHeader bytes
     int class_count[kExtCtr];     // tasks per query-length class
     int class_cursor[kExtCtr];    // work cursors of the extension kernels
@@ -847,6 +882,11 @@ int qm_collect_seeds(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const 
     if (opt->min_seed_len != idx->v.k) return qm_fail(ctx, QM_EINVAL, "index built with k=%d but min_seed_len=%d", idx->v.k, opt->min_seed_len);
     if (n_reads == 0) return QM_OK;
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (opt->flags & QM_F_FM_SEEDS) {
+        if (!idx->have_fm) return qm_fail(ctx, QM_EINVAL, "QM_F_FM_SEEDS needs an FM-index: qm_index_attach_bwa or qm_index_build_fm first");
+        QM_CUDA(ctx, launch_fm_seed(idx, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true, (cudaStream_t)stream));
+        return QM_OK;
+    }
     QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true,
                                    (cudaStream_t)stream));
     return QM_OK;
@@ -877,7 +917,12 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
         const int32_t *lens = d_lens + b0;
         int sp = qm_prof_begin(ctx, QM_ST_SEED, st);
         int n_seed_launches = 0;
-        if (ctx->se_n_parts > 0 && b0 == 0 && n_reads <= kSeBatch) {
+        if (opt->flags & QM_F_FM_SEEDS) {
+            if (!idx->have_fm) return qm_fail(ctx, QM_EINVAL, "QM_F_FM_SEEDS needs an FM-index: qm_index_attach_bwa or qm_index_build_fm first");
+            for (int pt = 0; pt < ctx->se_n_parts; ++pt) QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->se_part_ev[pt], 0));
+            QM_CUDA(ctx, launch_fm_seed(idx, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
+            n_seed_launches = 1;
+        } else if (ctx->se_n_parts > 0 && b0 == 0 && n_reads <= kSeBatch) {
             // the batch is still arriving piece by piece (host entry): seed each piece as soon as its copy has landed
             int64_t r0 = 0;
             for (int pt = 0; pt < ctx->se_n_parts; ++pt) {

@@ -5,6 +5,7 @@
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf [--vcf-gz 0]] [--gpu I | --gpus A,B,..|A-B] [-t THREADS] [-w BAND]
 //                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
+//                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0]
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
 //        semantics, formatted on the device (with --rmdup 1: of the duplicate-free records, as the reference's rule reads them)
 //        --no-rescue 1 = bwa mem -S (mate rescue off; on by default as in the reference's command line)
@@ -789,6 +790,8 @@ int sort_key_bits(const Genome &g, int &pos_bits)
     return qm_sort_key_bits((int)g.names.size(), pos_bits);
 }
 
+template <class T> std::vector<T> read_binary(const std::string &path);
+
 int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
 {
     if (!a.has("ref") || !a.has("r1") || !a.has("r2")) die(1, "--ref, --r1 and --r2 are required");
@@ -827,10 +830,23 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     qm_pileup_opt popt; qm_pileup_opt_default(&popt);
     if (a.has("min-mapq")) popt.min_mapq = atoi(a.get("min-mapq").c_str());
     if (a.has("min-bq")) popt.min_bq = atoi(a.get("min-bq").c_str());
+    // --bwa-index PREFIX: seeds through bwa's own index files PREFIX.bwt + PREFIX.sa (what `bwa index` left next to the genome,
+    // rules/index.smk:13) -- bwa-mem's seeds (SMEMs, re-seeding, third round) instead of the k-mer hash index's exact matches;
+    // --fm-seeds 1 rebuilds the same index from the FASTA when the files are not at hand
+    std::vector<uint8_t> bwt_file, sa_file;
+    const bool fm_build = atoi(a.get("fm-seeds", "0").c_str()) != 0;
+    if (a.has("bwa-index")) {
+        bwt_file = read_binary<uint8_t>(a.get("bwa-index") + ".bwt");
+        sa_file = read_binary<uint8_t>(a.get("bwa-index") + ".sa");
+    }
+    if (a.has("bwa-index") || fm_build) opt.flags |= QM_F_FM_SEEDS;
     std::vector<qm_index *> idxs((size_t)n_gpu, nullptr);
     std::vector<qm_sample *> smps((size_t)n_gpu, nullptr);
     for (int d = 0; d < n_gpu; ++d) {
         Ls[d].check(qm_index_build(Ls[d].ctx, g.codes.data(), (int)g.names.size(), g.lens.data(), opt.min_seed_len, &idxs[d]), "qm_index_build");
+        if (!bwt_file.empty())
+            Ls[d].check(qm_index_attach_bwa(Ls[d].ctx, idxs[d], bwt_file.data(), (int64_t)bwt_file.size(), sa_file.data(), (int64_t)sa_file.size()), "qm_index_attach_bwa");
+        else if (fm_build) Ls[d].check(qm_index_build_fm(Ls[d].ctx, idxs[d], g.codes.data()), "qm_index_build_fm");
         Ls[d].check(qm_sample_begin(Ls[d].ctx, idxs[d], &opt, &popt, &smps[d]), "qm_sample_begin");
     }
     qm_index *idx = idxs[0];

@@ -189,6 +189,8 @@ void qm_index_destroy(qm_ctx *ctx, qm_index *ix)
     if (ix->d_uniqp) cudaFree(ix->d_uniqp);
     if (ix->d_uniq2p) cudaFree(ix->d_uniq2p);
     for (int t = 0; t < 3; ++t) if (ix->d_cnteqp[t]) cudaFree(ix->d_cnteqp[t]);
+    if (ix->d_fm_bwt) cudaFree(ix->d_fm_bwt);
+    if (ix->d_fm_sa) cudaFree(ix->d_fm_sa);
     delete ix;
 }
 

@@ -1,6 +1,7 @@
 // pipeline.cuh -- device-side views and internal task formats shared by the alignment kernels.
 #pragma once
 #include "common.cuh"
+#include "fm_core.cuh"
 
 // ---- reference index as kernels see it (passed by value) ----
 struct IndexView {
@@ -31,6 +32,11 @@ struct qm_index {
     void *d_refb = nullptr, *d_table = nullptr, *d_pos = nullptr, *d_uniq = nullptr, *d_bloom = nullptr, *d_ref2p = nullptr,
          *d_uniqp = nullptr, *d_uniq2p = nullptr, *d_cnteqp[3] = {nullptr, nullptr, nullptr};
     int64_t n_kmers = 0, n_unique = 0, table_size = 0;
+    // bwa's FM-index of the same genome (fmindex.cu), when attached: the seeds then can be bwa's own (QM_F_FM_SEEDS)
+    bool have_fm = false;
+    FmView fm = {};
+    void *d_fm_bwt = nullptr, *d_fm_sa = nullptr;
+    std::vector<uint8_t> fm_bwt_bytes, fm_sa_bytes;       // the index as bwa's two files (qm_index_fm_export)
 };
 
 static __device__ __forceinline__ int qm_ref_base(const IndexView &V, int64_t x)
