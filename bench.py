@@ -36,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_json_out = sys.stdout                     # replaced in __main__ by the saved original stdout
 METRIC = "read_pairs_per_s_aligned_piledup"
 UNIT = "pairs/s"
 CHUNK = 2_000_000                          # pairs handed to the library per call (bounds its per-chunk scratch)
@@ -202,7 +203,7 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "note": CPU_NOTE}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_json_out, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -491,7 +492,7 @@ def run_ours(args):
                                "sample": f"first {n} pairs of the first step's sample ({cms / 1e3:.1f} s): oracle port of bwa-mem "
                                          f"extension + mate rescue + pairing + CIGAR + bcftools-style counting, OpenMP over reads; "
                                          f"build {qmo_py.BUILD_KIND}", "note": CPU_NOTE}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_json_out, flush=True)
     if world > 1:
         for x in smp.values():
             x.close()
@@ -500,6 +501,11 @@ def run_ours(args):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: whatever else a library prints there (NCCL's version banner, for one) goes to
+    # stderr -- file descriptor 1 is pointed at stderr for the whole run and the line is written to the saved original
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -254,11 +254,12 @@ void launch2(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
              const int *d_counts, int *d_cursors, int h_count, qm_ext_result *d_out, cudaStream_t st)
 {
     const size_t smem = (size_t)(BYTES ? 2 : 3) * (CAP / 2 + 1) * kT * 2 * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};              // per device: function attributes belong to a device's context, and one
+                                                // process may drive several GPUs (qm_driver --gpus)
+    if (!attr_set[ctx->device & 63]) {
         cudaFuncSetAttribute(ext2_kernel<CAP, true, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(ext2_kernel<CAP, false, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;

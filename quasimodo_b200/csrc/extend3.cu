@@ -161,11 +161,12 @@ void launch3(qm_ctx *ctx, int cls, const ExtParams &P, const IndexView &V, const
              int *d_fb_ctr, cudaStream_t st)
 {
     const size_t smem = (size_t)KT * (NARROW ? SmemNarrow<KT>::bytes_per_thread(CAP) : SmemWide<KT>::bytes_per_thread(CAP));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};              // per device: function attributes belong to a device's context, and one
+                                                // process may drive several GPUs (qm_driver --gpus)
+    if (!attr_set[ctx->device & 63]) {
         cudaFuncSetAttribute(ext3_kernel<CAP, KT, true, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(ext3_kernel<CAP, KT, false, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     int per_sm = (int)((227u * 1024u) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;

@@ -1083,15 +1083,16 @@ int qm_pair_finish(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ui
     const int64_t lstride = 2 * n_pairs;
     CigTask *tasks = (CigTask *)(b + o_tasks);
     const unsigned grid = (unsigned)((n_pairs + 127) / 128);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};              // per device: function attributes belong to a device's context, and one
+                                                // process may drive several GPUs (qm_driver --gpus)
+    if (!attr_set[ctx->device & 63]) {
         QM_CUDA(ctx, cudaFuncSetAttribute(cigar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCigWarps * kDirBytes));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kCsT * 6));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * kCsT * 6));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_score_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * kCsT * 6));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * 6));
         QM_CUDA(ctx, cudaFuncSetAttribute(cig_trace_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 6));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     const int sp = qm_prof_begin(ctx, QM_ST_PAIR, st);
     pair_decide_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, T, d_codes, stride, d_lens, n_pairs, pair_id0, d_regs, d_n_regs, d_alns,
