@@ -341,6 +341,18 @@ int qm_sample_set_rmdup(qm_sample *s, int on);
 int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream);
 int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records);
 
+/* ---- depth cap (`bcftools mpileup -d N`, rules/vcfcall.smk:115 runs with bcftools' default) ----
+ * htslib's pileup iterator refuses a read whose start equals the position it is assembling while more than N reads are
+ * buffered: an order-dependent rule, replayed here read by read over the records in BAM order (qm_depth_cap; d_drop[c][r] = 1
+ * for a refused read).  OFF by default: at BASELINE depths the cap discards most of the sample.
+ * qm_sample_set_max_depth(N > 0) before the first pairs: like rmdup mode the sample keeps reads and records on the device and
+ * counts in qm_sample_finish, which marks duplicates (when rmdup is on), applies the cap to what is left and counts the rest;
+ * qm_sample_rmdup_finish is qm_sample_finish for a sample in rmdup mode. */
+int qm_depth_cap(qm_ctx *ctx, const qm_pileup_opt *po, int n_chunks, const qm_aln *const *d_alns, const int64_t *n_pairs, int max_depth,
+                 uint8_t *const *d_drop, int64_t *h_n_dropped, void *stream);
+int qm_sample_set_max_depth(qm_sample *s, int max_depth);
+int qm_sample_finish(qm_sample *s, int64_t *n_dup_pairs, int64_t *n_capped_reads, void *stream);
+
 /* ---- text pileup (replaces `samtools mpileup -f ref bam`, rules/vcfcall.smk:39; consumer: the VarScan rule) ----
  * One line per column covered by an admitted read: chrom, 1-based position, reference base, number of entries with base
  * quality >= min_bq, base string (. , ACGTN acgtn * ^X $ +nSEQ -nSEQ), quality string; SURVEY.md A.10.  Admission and

@@ -115,6 +115,94 @@ void qmo_pileup(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_pairs,
     }
 }
 
+/* ---- depth cap: which admitted reads htslib's pileup iterator keeps under `bcftools mpileup -d N`.
+ * htslib 1.9 sam.c: bam_plp_push drops a read whose start equals the iterator's current position while more than maxcnt
+ * nodes are allocated (the reads buffered and not yet passed, plus the iterator's spare tail node); bam_plp_next frees the
+ * reads that ended at or before the position it is assembling, then moves one position on (or jumps to the first buffered
+ * read); bam_plp_auto feeds one read whenever the iterator has nothing beyond its position.  Reads come in BAM order
+ * (contig, position, strand, input order).  The rule is order dependent by design; this restates it step by step.
+ * keep[r] = 1 for reads the iterator keeps, 0 for dropped or not admitted ones.  PARITY UNPINNED (no htslib here). ---- */
+typedef struct { int64_t key; int64_t rec; } cap_t;
+static int cap_cmp(const void *a, const void *b)
+{
+    const cap_t *x = (const cap_t *)a, *y = (const cap_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->rec < y->rec ? -1 : x->rec > y->rec;
+}
+/* min-heap of linked reads on (contig, end): what bam_plp_next releases first */
+typedef struct { int tid; int64_t end; int64_t node; } cap_heap_t;
+static int heap_less(const cap_heap_t *a, const cap_heap_t *b) { return a->tid != b->tid ? a->tid < b->tid : a->end < b->end; }
+static void heap_push(cap_heap_t *h, int64_t *n, cap_heap_t v)
+{
+    int64_t i = (*n)++;
+    while (i > 0 && heap_less(&v, &h[(i - 1) >> 1])) { h[i] = h[(i - 1) >> 1]; i = (i - 1) >> 1; }
+    h[i] = v;
+}
+static void heap_pop(cap_heap_t *h, int64_t *n)
+{
+    const cap_heap_t v = h[--(*n)];
+    int64_t i = 0;
+    for (;;) {
+        int64_t c = 2 * i + 1;
+        if (c >= *n) break;
+        if (c + 1 < *n && heap_less(&h[c + 1], &h[c])) ++c;
+        if (!heap_less(&h[c], &v)) break;
+        h[i] = h[c]; i = c;
+    }
+    h[i] = v;
+}
+void qmo_depth_cap(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_reads, const qmo_aln_t *alns, int max_depth, uint8_t *keep)
+{
+    cap_t *ord = (cap_t *)malloc(sizeof(cap_t) * (size_t)(n_reads ? n_reads : 1));
+    int64_t m = 0, r, i;
+    (void)R;
+    memset(keep, 0, (size_t)n_reads);
+    for (r = 0; r < n_reads; ++r)
+        if (admitted(po, &alns[r])) {
+            ord[m].key = ((int64_t)alns[r].rid << 40) | ((int64_t)alns[r].pos << 1) | ((alns[r].flag & 0x10) != 0);
+            ord[m].rec = r; ++m;
+        }
+    qsort(ord, (size_t)m, sizeof(cap_t), cap_cmp);
+    {
+        int it_tid = 0, max_tid = -1;
+        int64_t it_pos = 0, max_pos = -1, cnt = 1 /* the iterator's spare tail node */;
+        cap_heap_t *heap = (cap_heap_t *)malloc(sizeof(cap_heap_t) * (size_t)(m ? m : 1));
+        int64_t n_heap = 0, head = 0, n_link = 0;
+        int64_t *lbeg = (int64_t *)malloc(8 * (size_t)(m ? m : 1));
+        int *ltid = (int *)malloc(4 * (size_t)(m ? m : 1));
+        uint8_t *gone = (uint8_t *)calloc((size_t)(m ? m : 1), 1);
+        for (i = 0; i < m; ++i) {
+            const qmo_aln_t *a = &alns[ord[i].rec];
+            int k; int64_t rlen = 0, end;
+            for (k = 0; k < a->n_cigar; ++k) { const int op = a->cigar[k] & 0xf; if (op == 0 || op == 2) rlen += (int64_t)(a->cigar[k] >> 4); }
+            end = a->pos + (rlen > 0 ? rlen : 1);
+            /* bam_plp_next: as long as something beyond the iterator's position is buffered */
+            while (max_tid > it_tid || (max_tid == it_tid && max_pos > it_pos)) {
+                while (n_heap && (heap[0].tid < it_tid || (heap[0].tid == it_tid && heap[0].end <= it_pos))) {      /* release */
+                    gone[heap[0].node] = 1; --cnt;
+                    heap_pop(heap, &n_heap);
+                }
+                while (head < n_link && gone[head]) ++head;
+                if (head < n_link && it_tid < ltid[head]) { it_tid = ltid[head]; it_pos = lbeg[head]; }          /* next contig */
+                else if (head < n_link && it_pos < lbeg[head]) it_pos = lbeg[head];                              /* jump a gap */
+                else ++it_pos;
+            }
+            /* bam_plp_push */
+            if (it_tid == a->rid && it_pos == a->pos && cnt > max_depth) continue;                 /* dropped */
+            keep[ord[i].rec] = 1;
+            max_tid = a->rid; max_pos = a->pos;
+            if (end > it_pos || a->rid > it_tid) {                                                  /* linked: a node is taken */
+                cap_heap_t v;
+                v.tid = a->rid; v.end = end; v.node = n_link;
+                heap_push(heap, &n_heap, v);
+                lbeg[n_link] = a->pos; ltid[n_link] = a->rid; ++n_link; ++cnt;
+            }
+        }
+        free(heap); free(lbeg); free(ltid); free(gone);
+    }
+    free(ord);
+}
+
 /* ---- indel alleles ("indel alleles into a small hash table"): every insertion / deletion operation of an
  * admitted read's CIGAR, keyed by (anchor = the reference base in front of the event, type, length clamped to 255, the first 11
  * inserted bases as the forward strand reads them + an "N among them" flag), forward and reverse reads counted apart.  Same

@@ -270,6 +270,29 @@ def pileup(ref, alns, reads, quals, lens, popt=None):
     return counts
 
 
+def depth_cap(ref, alns, max_depth, popt=None):
+    """htslib's per-file depth cap (bcftools mpileup -d): -> bool mask of the reads the pileup iterator keeps (False for dropped
+    and for not admitted reads)"""
+    L = lib()
+    L.qmo_depth_cap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    if popt is None:
+        popt = PileupOpt()
+        L.qmo_pileup_opt_default(C.byref(popt))
+    alns = np.ascontiguousarray(alns, dtype=ALN_DTYPE)
+    keep = np.zeros(len(alns), np.uint8)
+    L.qmo_depth_cap(ref._h, C.byref(popt), len(alns), alns.ctypes.data, int(max_depth), keep.ctypes.data)
+    return keep.astype(bool)
+
+
+def pileup_capped(ref, alns, reads, quals, lens, max_depth, popt=None):
+    """counts with the depth cap on: the dropped reads never reach the pileup (flag QCFAIL on a copy of the records)"""
+    keep = depth_cap(ref, alns, max_depth, popt)
+    a = np.array(alns, dtype=ALN_DTYPE, copy=True)
+    adm = depth_cap(ref, alns, 1 << 30, popt)
+    a["flag"][adm & ~keep] |= 0x200
+    return pileup(ref, a, reads, quals, lens, popt), keep
+
+
 def indels(ref, alns, reads, lens, popt=None, max_out=1 << 20):
     """-> int32 [n, 10]: rid, pos, len, type (0 ins, 1 del), has_n, seq, n_fwd, n_rev, key_lo, key_hi; sorted by key"""
     L = lib()

@@ -119,6 +119,9 @@ SIGNATURES = {
     "qm_sample_set_rmdup": (C.c_int, [_P, C.c_int]),
     "qm_sample_rmdup_finish": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
     "qm_sample_kept_alns_host": (C.c_int, [_P, _P, _L]),
+    "qm_depth_cap": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.POINTER(C.c_int64), _P]),
+    "qm_sample_set_max_depth": (C.c_int, [_P, C.c_int]),
+    "qm_sample_finish": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
     "qm_mpileup_text": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
     "qm_mpileup_text_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P]),
     "qm_mpileup_text_fetch": (C.c_int, [_P, _P, _L]),

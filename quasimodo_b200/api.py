@@ -168,6 +168,16 @@ class Sample:
         """duplicate removal (picard MarkDuplicates REMOVE_DUPLICATES=true): keep reads + records, count at rmdup_finish()"""
         _check(self.ctx._h, _lib.lib().qm_sample_set_rmdup(self._h, 1 if on else 0), "qm_sample_set_rmdup")
 
+    def set_max_depth(self, max_depth):
+        """bcftools mpileup -d: htslib's depth cap (0 = off); counting is deferred to finish()"""
+        _check(self.ctx._h, _lib.lib().qm_sample_set_max_depth(self._h, int(max_depth)), "qm_sample_set_max_depth")
+
+    def finish(self, stream=0):
+        """deferred counting (rmdup and / or depth cap) -> (duplicate pairs, reads the cap dropped)"""
+        nd, nc = C.c_int64(), C.c_int64()
+        _check(self.ctx._h, _lib.lib().qm_sample_finish(self._h, C.byref(nd), C.byref(nc), C.c_void_p(stream)), "qm_sample_finish")
+        return nd.value, nc.value
+
     def rmdup_finish(self, stream=0):
         """-> number of duplicate pairs; the count tensor then holds the survivors' counts"""
         n = C.c_int64()

@@ -5,7 +5,7 @@
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf [--vcf-gz 0]] [--gpu I | --gpus A,B,..|A-B] [-t THREADS] [-w BAND]
 //                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
-//                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0]
+//                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0] [--max-depth N]
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
 //        semantics, formatted on the device (with --rmdup 1: of the duplicate-free records, as the reference's rule reads them)
 //        --no-rescue 1 = bwa mem -S (mate rescue off; on by default as in the reference's command line)
@@ -857,6 +857,11 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     if (!rmdup && (!rmdup_bam.empty() || !metrics.empty())) die(1, "--rmdup-bam / --metrics need --rmdup 1");
     if (rmdup && n_gpu > 1) die(1, "--rmdup 1 needs the records of the whole sample on one device: run it with one GPU");
     if (rmdup) L.check(qm_sample_set_rmdup(smp, 1), "qm_sample_set_rmdup");
+    // --max-depth N: bcftools mpileup -d N (htslib's order-dependent depth cap); 0 / absent = no cap
+    const int max_depth = atoi(a.get("max-depth", "0").c_str());
+    if (max_depth < 0) die(1, "--max-depth must be >= 0");
+    if (max_depth > 0 && n_gpu > 1) die(1, "--max-depth needs the records of the whole sample on one device: run it with one GPU");
+    if (max_depth > 0) L.check(qm_sample_set_max_depth(smp, max_depth), "qm_sample_set_max_depth");
     const std::string mpileup = a.get("mpileup");
     const bool want_bam = !bam.empty() || !rmdup_bam.empty();
     const bool want_batches = want_bam || !mpileup.empty();
@@ -956,10 +961,14 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         fprintf(stderr, "[qm_driver] count tensors of %d GPUs merged (ncclAllReduce, int32 sum, %lld values)\n", n_gpu,
                 (long long)QM_NCH * (long long)g.codes.size());
     }
+    int64_t n_dup = 0;
+    if (rmdup || max_depth > 0) {
+        int64_t n_capped = 0;
+        L.check(qm_sample_finish(smp, &n_dup, &n_capped, nullptr), "qm_sample_finish");
+        if (rmdup) fprintf(stderr, "[qm_driver] rmdup: %lld of %lld pairs are duplicates\n", (long long)n_dup, (long long)n_pairs);
+        if (max_depth > 0) fprintf(stderr, "[qm_driver] depth cap %d: %lld reads dropped by the pileup iterator\n", max_depth, (long long)n_capped);
+    }
     if (rmdup) {
-        int64_t n_dup = 0;
-        L.check(qm_sample_rmdup_finish(smp, &n_dup, nullptr), "qm_sample_rmdup_finish");
-        fprintf(stderr, "[qm_driver] rmdup: %lld of %lld pairs are duplicates\n", (long long)n_dup, (long long)n_pairs);
         if (want_batches) {                            // final flags of every record, batch by batch
             std::vector<qm_aln> all((size_t)2 * n_pairs);
             L.check(qm_sample_kept_alns_host(smp, all.data(), (int64_t)all.size()), "qm_sample_kept_alns_host");

@@ -93,7 +93,8 @@ __device__ __forceinline__ void indel_add(const IndelView &T, unsigned long long
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, const uint8_t *__restrict__ codes,
               const uint8_t *__restrict__ quals, int stride, const int32_t *__restrict__ lens, int64_t n_pairs,
-              int32_t *__restrict__ counts, unsigned long long *__restrict__ n_admitted, IndelView T)
+              int32_t *__restrict__ counts, unsigned long long *__restrict__ n_admitted, IndelView T,
+              const uint8_t *__restrict__ drop /* may be NULL: reads the depth cap removed */)
 {
     __shared__ AlnS s_aln[kWarpsPerBlock][2];
     __shared__ uint8_t s_q[kWarpsPerBlock][2][kMaxLen];
@@ -116,7 +117,7 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
             rid[e] = g[e]->rid; tlen[e] = g[e]->tlen; L[e] = lens[2 * pi + e];
             rev[e] = (flag[e] & 0x10) != 0;
             ok[e] = !(flag[e] & (0x4 | 0x100 | 0x200 | 0x400)) && nc != 0 && nc != 255 && mapq >= po.min_mapq &&
-                    !((flag[e] & 0x1) && !(flag[e] & 0x2) && !po.count_orphans) && L[e] <= kMaxLen;
+                    !((flag[e] & 0x1) && !(flag[e] & 0x2) && !po.count_orphans) && L[e] <= kMaxLen && !(drop && drop[2 * pi + e]);
             if (ok[e]) {
                 if (lane == 0) {
                     s_aln[wib][e].pos = g[e]->pos; s_aln[wib][e].n_cigar = nc;
@@ -354,6 +355,14 @@ int qm_pileup_accumulate_indels(qm_ctx *ctx, const qm_index *idx, const qm_pileu
                                 const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
                                 int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, void *stream)
 {
+    return qm_pileup_accumulate_masked(ctx, idx, po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, tab, nullptr, stream);
+}
+
+// the same with a per-read drop mask (the depth cap's verdict, depthcap.cu): a dropped read is not admitted
+int qm_pileup_accumulate_masked(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
+                                const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                                int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, const uint8_t *d_drop, void *stream)
+{
     if (!ctx || !idx || !po || n_pairs < 0 || (n_pairs > 0 && (!d_alns || !d_codes || !d_quals || !d_lens || !d_counts)))
         return QM_EINVAL;
     if (tab && tab->ctx != ctx) return qm_fail(ctx, QM_EINVAL, "the indel table belongs to another context");
@@ -364,7 +373,7 @@ int qm_pileup_accumulate_indels(qm_ctx *ctx, const qm_index *idx, const qm_pileu
     if (blocks > cap) blocks = cap;
     const int sp = qm_prof_begin(ctx, QM_ST_PILEUP, (cudaStream_t)stream);
     pileup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab));
+        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab), d_drop);
     qm_prof_end(ctx, QM_ST_PILEUP, sp, (cudaStream_t)stream, 1);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;

@@ -178,3 +178,9 @@ int qm_ext_launch_classes(qm_ctx *ctx, const ExtParams &P, const IndexView &V, c
                           const int *d_lists, int64_t list_stride, const int *d_counts, int *d_cursors,
                           const int *h_counts, qm_ext_result *d_out, int *d_fb_lists, int *d_fb_ctr, cudaStream_t st,
                           bool scores_fit_bytes = false, const int64_t *h_list_off = nullptr);
+
+// internal: qm_pileup_accumulate_indels with a per-read drop mask (depth cap)
+struct qm_indel_table;
+extern "C" int qm_pileup_accumulate_masked(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
+                                const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                                int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, const uint8_t *d_drop, void *stream);

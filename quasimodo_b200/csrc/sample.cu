@@ -41,6 +41,7 @@ struct qm_sample {
     // duplicate removal (qm_sample_set_rmdup): every chunk's reads and records stay on the device, counting waits for
     // qm_sample_rmdup_finish
     bool rmdup = false;
+    int max_depth = 0;                            // > 0: `bcftools mpileup -d` depth cap (qm_sample_set_max_depth): deferred counting too
     bool rmdup_finished = false;                  // qm_sample_rmdup_finish has run: no more pairs, no second finish until a reset
     struct Kept { uint8_t *codes, *quals; int32_t *lens; qm_aln *alns; int64_t n; int32_t stride; };
     std::vector<Kept> kept;
@@ -54,7 +55,7 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
                  int64_t n, int64_t pair_id0, qm_aln *d_alns_out, cudaStream_t st, cudaEvent_t quals_ready = nullptr)
 {
     qm_ctx *ctx = s->ctx;
-    if (s->rmdup && s->rmdup_finished)
+    if ((s->rmdup || s->max_depth > 0) && s->rmdup_finished)
         return qm_fail(ctx, QM_EINVAL, "pairs added after qm_sample_rmdup_finish: reset the sample first");
     int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, s->d_cells, st);
     if (rc) return rc;
@@ -75,7 +76,7 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
     qm_aln *alns = d_alns_out ? d_alns_out : s->d_alns;
     rc = qm_pair_finish(ctx, s->idx, &s->opt, d_codes, stride, d_lens, n, pair_id0, s->d_regs, s->d_n_regs, s->pes, alns, st);
     if (rc) return rc;
-    if (s->rmdup) {
+    if (s->rmdup || s->max_depth > 0) {
         // keep the chunk for qm_sample_rmdup_finish: duplicates are a property of the whole sample
         qm_sample::Kept k = {nullptr, nullptr, nullptr, nullptr, n, stride};
         const size_t sb = (size_t)2 * n * stride;
@@ -183,12 +184,22 @@ int qm_sample_set_rmdup(qm_sample *s, int on)
 }
 
 // marks the duplicates among everything added since the last reset (flag 0x400 on their records), then counts the rest
-int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
+int qm_sample_set_max_depth(qm_sample *s, int max_depth)
+{
+    if (!s || max_depth < 0) return QM_EINVAL;
+    if (s->n_pairs != 0) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_set_max_depth: pairs were already added; reset the sample first");
+    s->max_depth = max_depth;
+    return QM_OK;
+}
+
+// Deferred counting: marks the duplicates among everything added since the last reset (rmdup mode), replays htslib's depth
+// cap over the records that are left (max_depth mode), then counts what survives both.
+int qm_sample_finish(qm_sample *s, int64_t *n_dup_pairs, int64_t *n_capped_reads, void *stream)
 {
     if (!s) return QM_EINVAL;
     qm_ctx *ctx = s->ctx;
-    if (!s->rmdup) return qm_fail(ctx, QM_EINVAL, "qm_sample_rmdup_finish: the sample is not in rmdup mode");
-    if (s->rmdup_finished) return qm_fail(ctx, QM_EINVAL, "qm_sample_rmdup_finish: already finished; reset the sample first");
+    if (!s->rmdup && s->max_depth <= 0) return qm_fail(ctx, QM_EINVAL, "qm_sample_finish: the sample counts as it goes (neither rmdup nor a depth cap is set)");
+    if (s->rmdup_finished) return qm_fail(ctx, QM_EINVAL, "qm_sample_finish: already finished; reset the sample first");
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
     QM_CUDA(ctx, cudaDeviceSynchronize());                 // chunks may have been added on any stream
     const int nc = (int)s->kept.size();
@@ -198,17 +209,37 @@ int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
     std::vector<int32_t> st(nc);
     std::vector<int64_t> n(nc);
     for (int c = 0; c < nc; ++c) { a[c] = s->kept[c].alns; q[c] = s->kept[c].quals; l[c] = s->kept[c].lens; st[c] = s->kept[c].stride; n[c] = s->kept[c].n; }
-    int rc = qm_mark_duplicates(ctx, nc, a.data(), q.data(), st.data(), l.data(), n.data(), n_dup_pairs, stream);
-    if (rc) return rc;
-    for (int c = 0; c < nc; ++c) {
-        const auto &k = s->kept[c];
-        rc = qm_pileup_accumulate_indels(ctx, s->idx, &s->popt, k.alns, k.codes, k.quals, k.stride, k.lens, k.n, s->d_counts, s->indels, stream);
+    if (n_dup_pairs) *n_dup_pairs = 0;
+    if (n_capped_reads) *n_capped_reads = 0;
+    int rc;
+    if (s->rmdup) {
+        rc = qm_mark_duplicates(ctx, nc, a.data(), q.data(), st.data(), l.data(), n.data(), n_dup_pairs, stream);
         if (rc) return rc;
     }
+    std::vector<uint8_t *> drop((size_t)nc, nullptr);
+    if (s->max_depth > 0 && nc > 0) {
+        for (int c = 0; c < nc; ++c) if (n[c]) QM_CUDA(ctx, cudaMalloc(&drop[c], (size_t)2 * n[c]));
+        rc = qm_depth_cap(ctx, &s->popt, nc, a.data(), n.data(), s->max_depth, drop.data(), n_capped_reads, stream);
+        if (rc) { for (auto d : drop) cudaFree(d); return rc; }
+    }
+    for (int c = 0; c < nc; ++c) {
+        const auto &k = s->kept[c];
+        rc = qm_pileup_accumulate_masked(ctx, s->idx, &s->popt, k.alns, k.codes, k.quals, k.stride, k.lens, k.n, s->d_counts, s->indels, drop[c], stream);
+        if (rc) { for (auto d : drop) cudaFree(d); return rc; }
+    }
     QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    for (auto d : drop) cudaFree(d);
     for (auto &k : s->kept) { cudaFree(k.codes); cudaFree(k.quals); cudaFree(k.lens); k.codes = k.quals = nullptr; k.lens = nullptr; }
     s->rmdup_finished = true;
     return QM_OK;
+}
+
+// marks the duplicates among everything added since the last reset (flag 0x400 on their records), then counts the rest
+int qm_sample_rmdup_finish(qm_sample *s, int64_t *n_dup_pairs, void *stream)
+{
+    if (!s) return QM_EINVAL;
+    if (!s->rmdup) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_rmdup_finish: the sample is not in rmdup mode");
+    return qm_sample_finish(s, n_dup_pairs, nullptr, stream);
 }
 
 // the records of everything added in rmdup mode, in input order, with their final flags; synchronous
