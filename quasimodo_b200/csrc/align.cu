@@ -959,7 +959,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 for (int c = 0; c < kExtClasses; ++c) fprintf(stderr, " %d", h_ctr->class_count[c]);
                 fprintf(stderr, "\n");
             }
-            if (h_ctr->n_tasks < kTailMinTasks) {
+            static const int tail_min = getenv("QM_TAIL_MIN") ? atoi(getenv("QM_TAIL_MIN")) : kTailMinTasks;       // tuning knob
+            if (h_ctr->n_tasks < tail_min) {
                 // few reads left: finish them on the device, one warp per read, no more round trips
                 sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
                 int blocks = (h_ctr->n_tasks + kTailWarps - 1) / kTailWarps;
