@@ -373,10 +373,24 @@ def run_ours(args):
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        h_codes = torch.empty((2 * P, L), dtype=torch.uint8).pin_memory()
+        # the public host entry with PACKED bases: 2 bits per base + an N bit per base cross the link (qm_sample_add_pairs_host_packed)
+        Lp = (L + 7) // 8 * 8
+        h_b2 = torch.empty((2 * P, (L + 3) // 4), dtype=torch.uint8).pin_memory()
+        h_nm = torch.empty((2 * P, (L + 7) // 8), dtype=torch.uint8).pin_memory()
         h_quals = torch.empty((2 * P, L), dtype=torch.uint8).pin_memory()
         h_lens = torch.full((2 * P,), L, dtype=torch.int32).pin_memory()
         h_calls = torch.empty(max_calls * 40, dtype=torch.uint8).pin_memory()
+        w4 = torch.tensor([1, 4, 16, 64], dtype=torch.uint8, device=dev)
+        w8 = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=dev)
+
+        def pack_to_host(c):
+            """what a FASTQ parser does as it goes (outside the timed region): codes -> packed bases + N mask, in pinned memory"""
+            for o in range(0, 2 * P, 1 << 20):
+                cp = torch.nn.functional.pad(c[o:o + (1 << 20)], (0, Lp - L), value=4)
+                isn = cp > 3
+                b = torch.where(isn, torch.zeros_like(cp), cp).view(cp.shape[0], Lp // 4, 4)
+                h_b2[o:o + cp.shape[0]].copy_((b * w4).sum(-1, dtype=torch.uint8)[:, :h_b2.shape[1]])
+                h_nm[o:o + cp.shape[0]].copy_((isn.view(cp.shape[0], Lp // 8, 8).to(torch.uint8) * w8).sum(-1, dtype=torch.uint8))
         e2e_times, d2h = [], 0
 
         def step_host(i):
@@ -390,7 +404,8 @@ def run_ours(args):
             torch.cuda.synchronize()
             for o in range(0, P, 4 * CHUNK):            # the library chunks and double-buffers its copies itself
                 n = min(4 * CHUNK, P - o)
-                s.add_pairs_host(h_codes[2 * o:2 * (o + n)], h_quals[2 * o:2 * (o + n)], h_lens[2 * o:2 * (o + n)], pair_id0=lo + o)
+                s.add_pairs_host_packed(h_b2[2 * o:2 * (o + n)], h_nm[2 * o:2 * (o + n)], h_quals[2 * o:2 * (o + n)], h_lens[2 * o:2 * (o + n)],
+                                        pair_id0=lo + o)
             r = finish_sample(j, s, key)
             nb = 0
             if r is not None:
@@ -403,7 +418,7 @@ def run_ours(args):
         for i in range(Wm + K):
             if i % n_used != last:                      # outside the timed region: this step's reads into the pinned buffers
                 c, q = d_reads[i % n_used]
-                h_codes.copy_(c)
+                pack_to_host(c)
                 h_quals.copy_(q)
                 last = i % n_used
             barrier()
@@ -418,9 +433,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": plan.total * K / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(2 * (2 * P * L) + 4 * 2 * P), "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": int(2 * P * (h_b2.shape[1] + h_nm.shape[1] + L) + 4 * 2 * P), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(te.item()) / K * 1e3,
-               "api": "qm_sample_add_pairs_host (+ qm_call_snps, qm_eval_calls), pinned host buffers"}
+               "api": "qm_sample_add_pairs_host_packed (2-bit bases + N mask + 1 B/base qualities; + qm_call_snps, qm_eval_calls), pinned host buffers"}
 
     if rank != 0:
         for x in smp.values():

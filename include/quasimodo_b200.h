@@ -249,6 +249,14 @@ int  qm_sample_add_pairs(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_
                          void *stream);
 int  qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t *h_quals, int32_t stride,
                               const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns /* may be NULL */);
+/* The same with the bases PACKED on the host side of the link (north_star: 2-bit-packed read input): h_bases2[r][(stride+3)/4]
+ * holds base j of read r at bits 2 (j & 3) of byte j >> 2, h_nmask[r][(stride+7)/8] one "this base is N" bit per base (bit j & 7
+ * of byte j >> 3).  0.375 instead of 1 byte per base crosses PCIe (the bases are what the first kernel waits for; the qualities
+ * travel behind them); a kernel on the copy stream expands each piece as it lands.  qm_pack_reads_host packs a 1-byte-per-base
+ * batch (the driver packs while it parses FASTQ). */
+int  qm_sample_add_pairs_host_packed(qm_sample *s, const uint8_t *h_bases2, const uint8_t *h_nmask, const uint8_t *h_quals, int32_t stride,
+                                     const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns /* may be NULL */);
+int  qm_pack_reads_host(const uint8_t *h_codes, int32_t stride, int64_t n_reads, uint8_t *h_bases2, uint8_t *h_nmask);
 int32_t *qm_sample_counts(qm_sample *s);                          /* device pointer, planes [QM_NCH][l_pac] */
 int  qm_sample_stats_sync(qm_sample *s, int64_t *n_pairs, int64_t *cells, void *stream);
 int  qm_sample_counts_host(qm_sample *s, int32_t *h_rows /* [l_pac][QM_NCH] */);

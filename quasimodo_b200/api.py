@@ -164,6 +164,15 @@ class Sample:
                                                  int(pair_id0), hp(h_alns))
         _check(self.ctx._h, rc, "qm_sample_add_pairs_host")
 
+    def add_pairs_host_packed(self, h_bases2, h_nmask, h_quals, h_lens, pair_id0=0, h_alns=None):
+        """host batch with the bases packed (pack_reads): 2 bits per base + an N bit per base cross the link instead of a byte"""
+        def hp(a):
+            return C.c_void_p(0) if a is None else C.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+        n, stride = h_quals.shape
+        rc = _lib.lib().qm_sample_add_pairs_host_packed(self._h, hp(h_bases2), hp(h_nmask), hp(h_quals), int(stride), hp(h_lens), n // 2,
+                                                        int(pair_id0), hp(h_alns))
+        _check(self.ctx._h, rc, "qm_sample_add_pairs_host_packed")
+
     def set_rmdup(self, on=True):
         """duplicate removal (picard MarkDuplicates REMOVE_DUPLICATES=true): keep reads + records, count at rmdup_finish()"""
         _check(self.ctx._h, _lib.lib().qm_sample_set_rmdup(self._h, 1 if on else 0), "qm_sample_set_rmdup")
@@ -395,6 +404,21 @@ class Context:
                                           workload.src_len.ctypes.data, workload.src_cum.ctypes.data, int(pair0),
                                           int(n_pairs), int(stride), _ptr(d_codes), _ptr(d_quals), C.c_void_p(stream))
         _check(self._h, rc, "qm_simulate_pairs")
+
+
+def pack_reads(codes, out_bases2=None, out_nmask=None):
+    """codes [n, stride] (0..3, else N) -> (bases2 [n, (stride+3)//4], nmask [n, (stride+7)//8]) for add_pairs_host_packed;
+    numpy arrays or (pinned) torch CPU tensors, optionally into given buffers"""
+    def hp(a):
+        return C.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+    n, stride = codes.shape
+    if out_bases2 is None:
+        out_bases2 = np.empty((n, (stride + 3) // 4), np.uint8)
+        out_nmask = np.empty((n, (stride + 7) // 8), np.uint8)
+    rc = _lib.lib().qm_pack_reads_host(hp(codes), int(stride), int(n), hp(out_bases2), hp(out_nmask))
+    if rc:
+        raise QmError(f"qm_pack_reads_host failed with code {rc}")
+    return out_bases2, out_nmask
 
 
 def pack_ext_tasks(pairs, h0s, ws, end_bonus, flags=0):

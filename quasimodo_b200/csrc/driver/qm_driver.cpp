@@ -144,6 +144,7 @@ struct Batch {
     int64_t n_pairs = 0;
     int32_t stride = 0;
     uint8_t *codes = nullptr, *quals = nullptr;      // page-locked (qm_host_alloc)
+    uint8_t *bases2 = nullptr, *nmask = nullptr;      // the packed form of codes that crosses the link (2 bits per base + an N bit)
     int32_t *lens = nullptr;
     qm_aln *alns = nullptr;
     std::string names;                                // NUL-separated, one per pair
@@ -242,11 +243,17 @@ void pack_batch(Lib &L, const std::vector<RawPair> &raw, bool want_alns, Batch &
             b.lens[2 * i + m] = (int32_t)s.size();
         }
     }
+    // codes stay on the host for the BAM records; the device receives 3 bits per base instead of 8
+    L.check(qm_host_alloc(L.ctx, (size_t)2 * b.n_pairs * (b.stride / 4), &p), "qm_host_alloc"); b.bases2 = (uint8_t *)p;
+    L.check(qm_host_alloc(L.ctx, (size_t)2 * b.n_pairs * (b.stride / 8), &p), "qm_host_alloc"); b.nmask = (uint8_t *)p;
+    L.check(qm_pack_reads_host(b.codes, b.stride, 2 * b.n_pairs, b.bases2, b.nmask), "qm_pack_reads_host");
 }
 
 void free_batch(Lib &L, Batch &b)
 {
     qm_host_free(L.ctx, b.codes); qm_host_free(L.ctx, b.quals); qm_host_free(L.ctx, b.lens); qm_host_free(L.ctx, b.alns);
+    qm_host_free(L.ctx, b.bases2); qm_host_free(L.ctx, b.nmask);
+    b.bases2 = b.nmask = nullptr;
     b.codes = b.quals = nullptr; b.lens = nullptr; b.alns = nullptr;
 }
 
@@ -897,7 +904,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         if (n_batches == 0 || n_gpu == 1) {
             // the first batch fixes the sample's insert-size model (its first QM_PESTAT_PAIRS pairs): every GPU gets that model
             // before it sees a batch of its own, so the records do not depend on the number of GPUs
-            L.check(qm_sample_add_pairs_host(smp, b.codes, b.quals, b.stride, b.lens, b.n_pairs, pair0, b.alns), "qm_sample_add_pairs_host");
+            L.check(qm_sample_add_pairs_host_packed(smp, b.bases2, b.nmask, b.quals, b.stride, b.lens, b.n_pairs, pair0, b.alns), "qm_sample_add_pairs_host_packed");
             if (n_gpu > 1) {
                 qm_pestat pes[4];
                 L.check(qm_sample_get_pestat(smp, pes), "qm_sample_get_pestat");
@@ -906,7 +913,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         } else {
             in_flight[d] = &b;
             workers[d] = std::thread([&Ls, &smps, d, &b, pair0]() {
-                Ls[d].check(qm_sample_add_pairs_host(smps[d], b.codes, b.quals, b.stride, b.lens, b.n_pairs, pair0, b.alns), "qm_sample_add_pairs_host");
+                Ls[d].check(qm_sample_add_pairs_host_packed(smps[d], b.bases2, b.nmask, b.quals, b.stride, b.lens, b.n_pairs, pair0, b.alns), "qm_sample_add_pairs_host_packed");
             });
         }
         if (decontam) {

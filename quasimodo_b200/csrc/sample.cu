@@ -49,6 +49,27 @@ struct qm_sample {
 
 namespace {
 
+// Packed read input (qm_sample_add_pairs_host_packed): 2 bits per base (base j of a read at bits 2 (j & 3) of byte j >> 2 of its
+// row) + 1 bit per base "this is an N" (bit j & 7 of byte j >> 3).  One thread writes four unpacked base codes as one word.
+__global__ void __launch_bounds__(256)
+unpack_reads_kernel(const uint8_t *__restrict__ bases2, const uint8_t *__restrict__ nmask, int stride, int stride_p, int stride_m,
+                    int64_t n_reads, uint8_t *__restrict__ codes)
+{
+    const int groups = (stride + 3) >> 2;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_reads * groups) return;
+    const int64_t r = t / groups;
+    const int g = (int)(t - r * groups);
+    const unsigned b = bases2[r * stride_p + g];
+    const unsigned m = nmask[r * stride_m + (g >> 1)] >> ((g & 1) << 2);
+    uint8_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = (m >> k) & 1u ? 4 : (uint8_t)((b >> (2 * k)) & 3u);
+    uint8_t *o = codes + r * stride + 4 * g;
+    if (4 * g + 3 < stride && (((uintptr_t)o) & 3u) == 0) *(uint32_t *)o = (uint32_t)c[0] | (uint32_t)c[1] << 8 | (uint32_t)c[2] << 16 | (uint32_t)c[3] << 24;
+    else for (int k = 0; k < 4 && 4 * g + k < stride; ++k) o[k] = c[k];
+}
+
 // quals_ready (may be NULL): event after which d_quals is valid; only the pileup reads the qualities, so their copy
 // may still be in flight while the reads are being aligned
 int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
@@ -368,16 +389,22 @@ int qm_sample_add_pairs(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_q
 
 // Host entry: h_* should be page-locked for the copies to overlap the previous chunk's kernels.
 // h_alns (may be NULL) receives the alignment records, 2 per pair, in input order.  Synchronous.
-int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t *h_quals, int32_t stride,
-                             const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns)
+// h_codes (1 byte per base) or, when it is NULL, h_bases2 + h_nmask (packed: 0.375 bytes per base over the host link)
+static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8_t *h_bases2, const uint8_t *h_nmask, const uint8_t *h_quals,
+                               int32_t stride, const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns)
 {
-    if (!s || n_pairs < 0 || (n_pairs > 0 && (!h_codes || !h_quals || !h_lens)) || stride <= 0) return QM_EINVAL;
+    const bool packed = h_codes == nullptr;
+    if (!s || n_pairs < 0 || (n_pairs > 0 && ((packed ? (!h_bases2 || !h_nmask) : false) || !h_quals || !h_lens)) || stride <= 0) return QM_EINVAL;
     if (n_pairs == 0) return QM_OK;
     qm_ctx *ctx = s->ctx;
     QM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int stride_p = (stride + 3) >> 2, stride_m = (stride + 7) >> 3;
     const size_t seq_bytes = (size_t)2 * kChunkPairs * stride;
     const size_t seq_al = (seq_bytes + 255) & ~(size_t)255;
-    const size_t need = 2 * seq_al + (size_t)2 * kChunkPairs * sizeof(int32_t);
+    const size_t lens_al = ((size_t)2 * kChunkPairs * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t pk_al = ((size_t)2 * kChunkPairs * stride_p + 255) & ~(size_t)255, mk_al = ((size_t)2 * kChunkPairs * stride_m + 255) & ~(size_t)255;
+    const size_t o_pk = 2 * seq_al + lens_al, o_mk = o_pk + pk_al;
+    const size_t need = o_mk + mk_al;
     if (need > s->stage_cap) {
         for (int i = 0; i < 2; ++i) {
             if (s->d_stage[i]) QM_CUDA(ctx, cudaFree(s->d_stage[i]));
@@ -424,8 +451,16 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
         // the bases in kCopyParts pieces, an event behind each: seeding starts on piece 0 while the others are in flight
         for (int pt = 0; pt < kCopyParts; ++pt) {
             const int64_t r0 = 2 * n * pt / kCopyParts, r1 = 2 * n * (pt + 1) / kCopyParts;
-            if (r1 > r0 && (e = cudaMemcpyAsync(s->d_stage[b] + r0 * stride, h_codes + (2 * p0 + r0) * stride, (size_t)(r1 - r0) * stride,
-                                                cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+            if (r1 > r0 && !packed && (e = cudaMemcpyAsync(s->d_stage[b] + r0 * stride, h_codes + (2 * p0 + r0) * stride, (size_t)(r1 - r0) * stride,
+                                                           cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+            if (r1 > r0 && packed) {                   // the packed piece, then its expansion to one byte per base, both on the copy stream
+                uint8_t *d_pk = s->d_stage[b] + o_pk + r0 * stride_p, *d_mk = s->d_stage[b] + o_mk + r0 * stride_m;
+                if ((e = cudaMemcpyAsync(d_pk, h_bases2 + (2 * p0 + r0) * stride_p, (size_t)(r1 - r0) * stride_p, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+                if ((e = cudaMemcpyAsync(d_mk, h_nmask + (2 * p0 + r0) * stride_m, (size_t)(r1 - r0) * stride_m, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+                const int64_t work = (r1 - r0) * ((stride + 3) >> 2);
+                unpack_reads_kernel<<<(unsigned)((work + 255) / 256), 256, 0, cs>>>(d_pk, d_mk, stride, stride_p, stride_m, r1 - r0, s->d_stage[b] + r0 * stride);
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            }
             if ((e = cudaEventRecord(s->ev_part[b][pt], cs)) != cudaSuccess) return e;
         }
         if ((e = cudaMemcpyAsync(s->d_stage[b] + seq_al, h_quals + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
@@ -448,6 +483,39 @@ int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t
         QM_CUDA(ctx, cudaEventRecord(s->ev_consumed[b], ks));
     }
     QM_CUDA(ctx, cudaStreamSynchronize(ks));
+    return QM_OK;
+}
+
+int qm_sample_add_pairs_host(qm_sample *s, const uint8_t *h_codes, const uint8_t *h_quals, int32_t stride,
+                             const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns)
+{
+    if (n_pairs > 0 && !h_codes) return QM_EINVAL;
+    return add_pairs_host_impl(s, h_codes, nullptr, nullptr, h_quals, stride, h_lens, n_pairs, pair_id0, h_alns);
+}
+
+// the same with the bases packed on the host side of the link: 2 bits per base + 1 bit per base for N
+int qm_sample_add_pairs_host_packed(qm_sample *s, const uint8_t *h_bases2, const uint8_t *h_nmask, const uint8_t *h_quals, int32_t stride,
+                                    const int32_t *h_lens, int64_t n_pairs, int64_t pair_id0, qm_aln *h_alns)
+{
+    if (n_pairs > 0 && (!h_bases2 || !h_nmask)) return QM_EINVAL;
+    return add_pairs_host_impl(s, nullptr, h_bases2, h_nmask, h_quals, stride, h_lens, n_pairs, pair_id0, h_alns);
+}
+
+// host-side packer for the entry above: codes [n_reads][stride] (0..3, anything else = N) -> bases2 [n_reads][(stride + 3) / 4],
+// nmask [n_reads][(stride + 7) / 8]
+int qm_pack_reads_host(const uint8_t *h_codes, int32_t stride, int64_t n_reads, uint8_t *h_bases2, uint8_t *h_nmask)
+{
+    if (stride <= 0 || n_reads < 0 || (n_reads > 0 && (!h_codes || !h_bases2 || !h_nmask))) return QM_EINVAL;
+    const int sp = (stride + 3) >> 2, sm = (stride + 7) >> 3;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const uint8_t *c = h_codes + r * stride;
+        uint8_t *b = h_bases2 + r * sp, *m = h_nmask + r * sm;
+        memset(b, 0, (size_t)sp); memset(m, 0, (size_t)sm);
+        for (int j = 0; j < stride; ++j) {
+            if (c[j] > 3) m[j >> 3] |= (uint8_t)(1u << (j & 7));
+            else b[j >> 2] |= (uint8_t)(c[j] << (2 * (j & 3)));
+        }
+    }
     return QM_OK;
 }
 

@@ -197,3 +197,28 @@ def test_eval_calls_totals_match_the_key_matcher(ctx):
     assert np.array_equal(d_flags.cpu().numpy(), cf)
     rc = _lib.lib().qm_eval_calls(ctx._h, None, 0, C.c_void_p(d_truth.data_ptr()), nt, None, out, None)
     assert rc == 0 and list(out) == [0, 0, nt]
+
+
+def test_packed_host_entry_equals_the_byte_entry(ctx):
+    """qm_sample_add_pairs_host_packed (2-bit bases + N mask over the link, expanded on the device) against the 1-byte-per-base
+    entry: same records, same counts -- ragged read lengths, N bases, a stride that is not a multiple of 8"""
+    from quasimodo_b200 import _lib, workloads
+    from quasimodo_b200.api import pack_reads
+    n = 5000
+    W = workloads.config1(n)
+    codes, quals, _, _ = W.simulate_host(0, n, stride=157)
+    lens = np.full(2 * n, 150, np.int32)
+    rng = np.random.default_rng(4)
+    for r in rng.integers(0, 2 * n, 200):
+        lens[r] = int(rng.integers(40, 150))
+        codes[r, lens[r]:] = 4
+    idx = ctx.index(W.ref, 31)
+    a, b = ctx.sample(idx), ctx.sample(idx)
+    ha, hb = np.zeros(2 * n, dtype=_lib.ALN_DTYPE), np.zeros(2 * n, dtype=_lib.ALN_DTYPE)
+    a.add_pairs_host(codes, quals, lens, h_alns=ha)
+    b2, nm = pack_reads(codes)
+    assert b2.shape == (2 * n, 40) and nm.shape == (2 * n, 20) and nm.any()
+    b.add_pairs_host_packed(b2, nm, quals, lens, h_alns=hb)
+    assert ha.tobytes() == hb.tobytes()
+    assert np.array_equal(a.counts_host(), b.counts_host()) and a.stats() == b.stats()
+    a.close(); b.close(); idx.close()
