@@ -356,11 +356,15 @@ def run_ours(args):
     cells_total = 0
     barrier()
     e0.record()
+    marks = []
     for i in range(K):
         cells_total += step_resident(Wm + i)
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     stage_ms, stage_launch = ctx.profile_collect()
     ctx.profile_enable(False)
     clk = clocks.stop() if rank == 0 else None
@@ -429,12 +433,20 @@ def run_ours(args):
             if i >= Wm:
                 e2e_times.append(dt)
                 d2h = max(d2h, nb)
+        # where the host-entry step spends its time (2 extra untimed steps with the stage events on)
+        ctx.profile_collect()
+        ctx.profile_enable(True)
+        for i in range(Wm + K - 2, Wm + K):
+            step_host(i if i % n_used == last else last)
+        e2e_stage_ms, _ = ctx.profile_collect()
+        ctx.profile_enable(False)
         te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": plan.total * K / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * P * (h_b2.shape[1] + h_nm.shape[1] + L) + 4 * 2 * P), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(te.item()) / K * 1e3,
+               "ms_per_step": float(te.item()) / K * 1e3, "step_ms": [round(x * 1e3, 3) for x in e2e_times],
+               "stages_ms_per_step": {k: v / 2 for k, v in e2e_stage_ms.items()},
                "api": "qm_sample_add_pairs_host_packed (2-bit bases + N mask + 1 B/base qualities; + qm_call_snps, qm_eval_calls), pinned host buffers"}
 
     if rank != 0:
@@ -495,6 +507,7 @@ def run_ours(args):
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if plan.strong else "weak", "vs_baseline": None,
            "dtype": "int32", "data": "synthetic", "config": plan.config_dict(world, P), "clocks": clk, "e2e": e2e,
            "gpu_launches": launches, "roofline": roofline, "roofline_pileup": roofline_pileup, "roofline_seed": roofline_seed,
+           "step_ms": [round(x, 3) for x in step_ms],
            "stages_ms_per_step": {k: v / K for k, v in stage_ms.items()},
            "stage_launches": stage_launch,
            "results": {k: {"calls": v[0], "TP": v[1], "FP": v[2], "FN": v[3]} for k, v in results.items()}}

@@ -441,6 +441,14 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         }
     }
     const int64_t n_chunks = (int64_t)starts.size();
+    // QM_HOST_TRACE=1 (diagnostics): when each copy piece and the chunk's compute finished, relative to the call's start
+    static const bool trace = getenv("QM_HOST_TRACE") != nullptr;
+    cudaEvent_t tr0 = nullptr, tr_part[kCopyParts] = {}, tr_quals = nullptr, tr_done = nullptr;
+    if (trace) {
+        cudaEventCreate(&tr0); cudaEventCreate(&tr_quals); cudaEventCreate(&tr_done);
+        for (int i = 0; i < kCopyParts; ++i) cudaEventCreate(&tr_part[i]);
+        cudaEventRecord(tr0, ctx->copy_stream);
+    }
     auto enqueue_copy = [&](int64_t c) -> cudaError_t {
         const int b = (int)(c & 1);
         const int64_t p0 = starts[c], n = sizes[c];
@@ -462,12 +470,16 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
                 if ((e = cudaGetLastError()) != cudaSuccess) return e;
             }
             if ((e = cudaEventRecord(s->ev_part[b][pt], cs)) != cudaSuccess) return e;
+            if (trace && c == 0) cudaEventRecord(tr_part[pt], cs);
         }
         if ((e = cudaMemcpyAsync(s->d_stage[b] + seq_al, h_quals + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
+        if (trace && c == 0) cudaEventRecord(tr_quals, cs);
         return cudaEventRecord(s->ev_quals[b], cs);
     };
     // a fresh event counts as completed, so the first two waits on ev_consumed pass immediately
     QM_CUDA(ctx, enqueue_copy(0));
+    static const bool no_overlap = getenv("QM_HOST_SEQ") != nullptr;          // diagnostics: copies and kernels one after the other
+    if (no_overlap) QM_CUDA(ctx, cudaStreamSynchronize(cs));
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
         const int64_t p0 = starts[c], n = sizes[c];
@@ -481,8 +493,17 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         if (rc) return rc;
         if (h_alns) QM_CUDA(ctx, cudaMemcpyAsync(h_alns + 2 * p0, s->d_alns, (size_t)2 * n * sizeof(qm_aln), cudaMemcpyDeviceToHost, ks));
         QM_CUDA(ctx, cudaEventRecord(s->ev_consumed[b], ks));
+        if (trace && c == 0) cudaEventRecord(tr_done, ks);
     }
     QM_CUDA(ctx, cudaStreamSynchronize(ks));
+    if (trace) {
+        float ms = 0;
+        fprintf(stderr, "[qm host trace] pairs %lld pieces", (long long)sizes[0]);
+        for (int i = 0; i < kCopyParts; ++i) { cudaEventElapsedTime(&ms, tr0, tr_part[i]); fprintf(stderr, " %.2f", ms); cudaEventDestroy(tr_part[i]); }
+        cudaEventElapsedTime(&ms, tr0, tr_quals); fprintf(stderr, " quals %.2f", ms);
+        cudaEventElapsedTime(&ms, tr0, tr_done); fprintf(stderr, " chunk done %.2f ms\n", ms);
+        cudaEventDestroy(tr0); cudaEventDestroy(tr_quals); cudaEventDestroy(tr_done);
+    }
     return QM_OK;
 }
 
