@@ -818,7 +818,11 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
                 break;
             }
             qm_ext_result x;
-            if (MAXC < 16 || t.qlen <= 127) x = tail_extend<4>(P, V, t, lane);
+            // column slots per lane by query length (warp-uniform): every row costs C cell updates per lane whatever the band
+            if (t.qlen <= 31) x = tail_extend<1>(P, V, t, lane);
+            else if (t.qlen <= 63) x = tail_extend<2>(P, V, t, lane);
+            else if (t.qlen <= 95) x = tail_extend<3>(P, V, t, lane);
+            else if (MAXC < 16 || t.qlen <= 127) x = tail_extend<4>(P, V, t, lane);
             else if (t.qlen <= 287) x = tail_extend<9>(P, V, t, lane);
             else x = tail_extend<16>(P, V, t, lane);
             __syncwarp();

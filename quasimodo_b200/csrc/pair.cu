@@ -224,7 +224,23 @@ struct SeqPair {            // query / reference bases of one CIGAR task, revers
 struct CigTask {
     int64_t rb, re;
     int32_t read, w2, truesc, regw;
+    int32_t wcap, pad;          // equal lengths: no diagonal further than wcap from the main one can hold a better path (cig_gain_cap)
 };
+
+// Equal-length tasks: how far from the main diagonal can a path that beats the UNGAPPED alignment stray?
+// Such a path has as many inserted query bases as deleted reference bases, >= 1 of each; reaching diagonal d costs at least
+// (o_ins + o_del) + (e_ins + e_del) |d|.  All it can win back sits at the n_low main-diagonal positions that score below a
+// (mismatch or N): at most a + max(b, 1) each, and one inserted query base is not aligned at all (it gives up a match, or
+// wins only b): total gain <= (a + max(b,1)) n_low - a - gap cost.  The largest |d| that leaves the gain positive is
+// returned (0: the ungapped alignment is optimal in every band).  ksw_global2 run with band min(w, cap) therefore equals
+// the ungapped score exactly when it does with any wider band -- and then its traceback is all-M (ties choose M).
+__device__ __forceinline__ int cig_gain_cap(const qm_opt &o, int n_low)
+{
+    const int mb = o.b > 1 ? o.b : 1;
+    const int x = (o.a + mb) * n_low - o.a - o.o_ins - o.o_del, es = o.e_ins + o.e_del;
+    if (x <= es) return 0;
+    return (x - 1) / es;
+}
 
 // band of the first try, exactly as bwa_gen_cigar2 derives it from w2
 __device__ __forceinline__ int cig_band(const qm_opt &o, int w2, int lq, int rlen)
@@ -247,8 +263,9 @@ __device__ __forceinline__ int cig_class(const IndexView &V, const qm_opt &o, co
 {
     const int rlen = (int)(t.re - t.rb);
     if (t.rb < V.l_pac && t.re > V.l_pac) return 6;
-    const int w = cig_band(o, t.w2, lq, rlen);
+    int w = cig_band(o, t.w2, lq, rlen);
     if (lq != rlen) return w <= 15 ? 3 : w <= 31 ? 4 : w <= 63 ? 5 : 6;     // traceback needed: thread-per-task kernels by band, else warp
+    w = w < t.wcap ? w : t.wcap;            // the score-only pass may narrow its band (cig_gain_cap)
     return w <= 15 ? 0 : w <= 23 ? 1 : w <= 35 ? 2 : 6;
 }
 
@@ -414,7 +431,7 @@ __device__ int gen_cigar_warp(const IndexView &V, const qm_opt &o, int w_, int l
 // mem_reg2aln, first half: MAPQ / flags / band inference; reads on the no-DP path (equal lengths, w2 == 0) are
 // completed here, the others become CigTasks.  Returns true when a task is needed.
 __device__ bool reg_to_aln_prepare(const IndexView &V, const qm_opt &o, const PairTables &T, int l_query, const uint8_t *query,
-                                   const qm_reg *ar, qm_aln *a, int *w2_out)
+                                   const qm_reg *ar, qm_aln *a, int *w2_out, int *wcap_out)
 {
     qm_aln r = {};
     if (ar == nullptr || ar->rb < 0 || ar->re < 0) { r.rid = -1; r.pos = -1; r.flag |= 0x4; *a = r; return false; }
@@ -430,24 +447,30 @@ __device__ bool reg_to_aln_prepare(const IndexView &V, const qm_opt &o, const Pa
     r.qb = qb; r.qe = qe;
     const bool is_rev = rb >= V.l_pac;            // a region never straddles l_pac
     if (is_rev) r.flag |= 0x10;
-    if (qe - qb == (int)(re - rb) && w2 == 0 && !(rb < V.l_pac && re > V.l_pac)) {
-        // bwa_gen_cigar2's shortcut: <len>M, NM = mismatches
+    *wcap_out = 1 << 20;
+    if (qe - qb == (int)(re - rb) && !(rb < V.l_pac && re > V.l_pac)) {
         SeqPair S;
         S.q = query + qb; S.lq = qe - qb; S.rlen = qe - qb; S.rb = rb; S.rev = is_rev; S.V = &V;
-        int n_mm = 0;
-        for (int i = 0; i < S.lq; ++i) n_mm += S.qb(i) != S.tb(i);
-        r.nm = n_mm;
-        const int64_t pos = rb < V.l_pac ? rb : 2 * V.l_pac - 1 - (re - 1);
-        int m = 0;
-        const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
-        if (clip5) r.cigar[m++] = (uint32_t)clip5 << 4 | 4;
-        r.cigar[m++] = (uint32_t)(qe - qb) << 4;
-        if (clip3) r.cigar[m++] = (uint32_t)clip3 << 4 | 4;
-        r.n_cigar = (uint8_t)m;
-        r.rid = qm_pos2rid(V, pos);
-        r.pos = (int32_t)(pos - V.off[r.rid]);
-        *a = r;
-        return false;
+        int n_mm = 0, n_low = 0;                  // q != t (NM); positions scoring below a (mismatch, or N on either side)
+        for (int i = 0; i < S.lq; ++i) { const int qc = S.qb(i), tc = S.tb(i); n_mm += qc != tc; n_low += (qc != tc) | (qc > 3); }
+        const int cap = cig_gain_cap(o, n_low);
+        if (w2 == 0 || cap == 0) {
+            // bwa_gen_cigar2's shortcut (w2 == 0), or no gapped path can beat the ungapped one in any band (cig_gain_cap):
+            // <len>M, NM = mismatches
+            r.nm = n_mm;
+            const int64_t pos = rb < V.l_pac ? rb : 2 * V.l_pac - 1 - (re - 1);
+            int m = 0;
+            const int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+            if (clip5) r.cigar[m++] = (uint32_t)clip5 << 4 | 4;
+            r.cigar[m++] = (uint32_t)(qe - qb) << 4;
+            if (clip3) r.cigar[m++] = (uint32_t)clip3 << 4 | 4;
+            r.n_cigar = (uint8_t)m;
+            r.rid = qm_pos2rid(V, pos);
+            r.pos = (int32_t)(pos - V.off[r.rid]);
+            *a = r;
+            return false;
+        }
+        *wcap_out = cap;
     }
     r.rid = ar->rid; r.pos = -1; r.n_cigar = 0;
     *a = r;
@@ -556,15 +579,15 @@ pair_decide_kernel(IndexView V, qm_opt o, PairTables T, const uint8_t *__restric
     }
     for (int i = 0; i < 2; ++i) {
         qm_aln h;
-        int w2 = 0;
-        const bool need = reg_to_aln_prepare(V, o, T, l_seq[i], seq[i], chosen[i], &h, &w2);
+        int w2 = 0, wcap = 0;
+        const bool need = reg_to_aln_prepare(V, o, T, l_seq[i], seq[i], chosen[i], &h, &w2, &wcap);
         if (paired_done) { h.mapq = (uint8_t)q_se[i]; h.flag &= ~0x100; }
         if (i == 0) h.tlen = extra_flag | (paired_done ? 4 : 0);
         alns[2 * pi + i] = h;
         if (need) {
             CigTask t;
             t.rb = chosen[i]->rb; t.re = chosen[i]->re; t.read = (int32_t)(2 * pi + i); t.w2 = w2;
-            t.truesc = chosen[i]->truesc; t.regw = chosen[i]->w;
+            t.truesc = chosen[i]->truesc; t.regw = chosen[i]->w; t.wcap = wcap; t.pad = 0;
             const int slot = atomicAdd(n_tasks, 1);
             tasks[slot] = t;
             const int c = cig_class(V, o, t, h.qe - h.qb);
@@ -605,7 +628,8 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
         const int l_query = lens[t.read];
         const int qb = rec->qb, qe = rec->qe;
         const int lq = qe - qb, rlen = (int)(t.re - t.rb);
-        const int w = cig_band(o, t.w2, lq, rlen);          // the band pair_decide_kernel classified this task by
+        int w = cig_band(o, t.w2, lq, rlen);                // the band pair_decide_kernel classified this task by:
+        w = w < t.wcap ? w : t.wcap;                        // bwa's, narrowed to the diagonals a better-than-ungapped path can reach
         SeqPair S;
         S.q = codes + (int64_t)t.read * stride + qb; S.lq = lq; S.rlen = rlen; S.rb = t.rb; S.rev = t.rb >= V.l_pac; S.V = &V;
         // first row of eh[] and the selectors of the columns row 0 can reach
@@ -663,8 +687,8 @@ cig_score_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int s
             HS[CX(slot)] = (short)h1; ES[CX(slot)] = NEG16;        // slot is now that of column `end` (beg when the row is empty)
         }
         const int score = HS[CX(lq % B)];
-        if (score == us && !(score < t.truesc - o.a)) {
-            // final and gap-free: <lq>M with clips, exactly what mem_reg2aln writes
+        if (score == us) {
+            // gap-free in every band (cig_gain_cap), so every retry of mem_reg2aln ends here too: <lq>M with clips
             const bool is_rev = t.rb >= V.l_pac;
             const int64_t pos = t.rb < V.l_pac ? t.rb : 2 * V.l_pac - 1 - (t.re - 1);
             int m = 0;
