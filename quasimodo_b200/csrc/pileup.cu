@@ -4,11 +4,17 @@
 // semantics SURVEY.md A.8-A.9; depth cap disabled, see DESIGN.md "deviations").
 //
 // One warp per read pair: the mate-overlap quality rewrite is pair-local, so both mates' qualities sit
-// in shared memory (BAM SEQ orientation), the lanes walk the query bases, and every counted base is one
-// fire-and-forget `red.global.add.s32` into the channel-major count tensor counts[ch][l_pac].  With
-// consecutive lanes on consecutive reference positions of one channel plane the 32 reductions of a warp
-// fall into one or two 128-byte lines of the L2-resident tensor.
+// in shared memory (BAM SEQ orientation) and the lanes walk the query bases.  Almost every base of a read equals the
+// reference and passes the quality threshold, so those are not counted one by one (round 1 did: two
+// `red.global.add` per base, 1.2 G reductions per 2 M pairs, the whole kernel time):
+//   * coverage is a DIFFERENCE ARRAY per strand: +1 at the first column of an M block, -1 behind its last;
+//   * a base that fails the threshold, or differs from the reference, is one reduction into minus[strand][column]
+//     (plus its own channel when it counts);
+//   * pileup_finish_kernel turns the prefix sum of the difference array into the depth channel and
+//     coverage - minus into the reference base's channel.
+// Same integers as counting every base; 4 reductions per read + ~0.05 per base instead of 2 per base.
 #include <algorithm>
+#include <cub/device/device_scan.cuh>
 #include "pipeline.cuh"
 
 namespace {
@@ -94,27 +100,50 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, const uint8_t *__restrict__ codes,
               const uint8_t *__restrict__ quals, int stride, const int32_t *__restrict__ lens, int64_t n_pairs,
               int32_t *__restrict__ counts, unsigned long long *__restrict__ n_admitted, IndelView T,
-              const uint8_t *__restrict__ drop /* may be NULL: reads the depth cap removed */)
+              const uint8_t *__restrict__ drop /* may be NULL: reads the depth cap removed */,
+              int32_t *__restrict__ cov /* [2][l_pac + 1] difference arrays */, int32_t *__restrict__ minus /* [2][l_pac] */,
+              bool wide /* stride even, codes / quals 4-byte aligned, stride <= kMaxLen */)
 {
+    // The pair's records, bases and qualities come in with a few wide loads per lane, all issued before any is used (round 1
+    // walked them byte by byte, one 32-byte sector per warp load and each behind the last: 0.7 TB/s of requests in flight).
+    static_assert(sizeof(qm_aln) == 128, "two records = sixteen 16-byte words");
+    __shared__ uint4 s_rec[kWarpsPerBlock][16];
+    __shared__ __align__(16) uint8_t s_c[kWarpsPerBlock][2 * kMaxLen];      // bases as stored (read orientation); mate e at e * moff
+    __shared__ __align__(16) uint8_t s_qr[kWarpsPerBlock][2 * kMaxLen];     // qualities likewise; the mate-overlap rewrite edits them in place
     __shared__ AlnS s_aln[kWarpsPerBlock][2];
-    __shared__ uint8_t s_q[kWarpsPerBlock][2][kMaxLen];
     const int lane = qm_lane(), wib = threadIdx.x >> 5;
     const int64_t warp0 = blockIdx.x * (int64_t)kWarpsPerBlock + wib;
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerBlock;
     const int64_t L_pac = V.l_pac;
     unsigned long long admitted_local = 0;
+    const int moff = wide ? stride : kMaxLen;
+    const int n_copy = stride < kMaxLen ? stride : kMaxLen;
 
     for (int64_t pi = warp0; pi < n_pairs; pi += n_warps) {
-        const qm_aln *g[2] = { alns + 2 * pi, alns + 2 * pi + 1 };
+        __syncwarp();
+        if (lane < 16) s_rec[wib][lane] = ((const uint4 *)(alns + 2 * pi))[lane];
+        if (wide) {                                 // 2 * stride bytes of the pair are contiguous and 4-byte aligned
+            const uint32_t *gc = (const uint32_t *)(codes + 2 * pi * stride), *gq = (const uint32_t *)(quals + 2 * pi * stride);
+            uint32_t *sc = (uint32_t *)s_c[wib], *sq = (uint32_t *)s_qr[wib];
+            for (int k = lane; k < (stride >> 1); k += 32) { sc[k] = gc[k]; sq[k] = gq[k]; }
+        } else {
+            for (int e = 0; e < 2; ++e)
+                for (int k = lane; k < n_copy; k += 32) {
+                    s_c[wib][e * moff + k] = codes[(2 * pi + e) * stride + k];
+                    s_qr[wib][e * moff + k] = quals[(2 * pi + e) * stride + k];
+                }
+        }
+        const int len0 = lens[2 * pi], len1 = lens[2 * pi + 1];
+        __syncwarp();
+        const qm_aln *g[2] = { (const qm_aln *)&s_rec[wib][0], (const qm_aln *)&s_rec[wib][8] };
         int flag[2], rid[2], tlen[2], L[2];
         bool ok[2], rev[2];
-        __syncwarp();
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const uint32_t fm = *(const uint32_t *)&g[e]->flag;           // flag | mapq<<16 | n_cigar<<24
             flag[e] = fm & 0xffff;
             const int mapq = (fm >> 16) & 0xff, nc = fm >> 24;
-            rid[e] = g[e]->rid; tlen[e] = g[e]->tlen; L[e] = lens[2 * pi + e];
+            rid[e] = g[e]->rid; tlen[e] = g[e]->tlen; L[e] = e ? len1 : len0;
             rev[e] = (flag[e] & 0x10) != 0;
             ok[e] = !(flag[e] & (0x4 | 0x100 | 0x200 | 0x400)) && nc != 0 && nc != 255 && mapq >= po.min_mapq &&
                     !((flag[e] & 0x1) && !(flag[e] & 0x2) && !po.count_orphans) && L[e] <= kMaxLen && !(drop && drop[2 * pi + e]);
@@ -124,16 +153,17 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
                     simple_span(g[e]->cigar, nc, &s_aln[wib][e].m0, &s_aln[wib][e].m1);
                 }
                 if (lane < nc) s_aln[wib][e].cigar[lane] = g[e]->cigar[lane];
-                const uint8_t *qv = quals + (2 * pi + e) * stride;
-                for (int i = lane; i < L[e]; i += 32) s_q[wib][e][i] = rev[e] ? qv[L[e] - 1 - i] : qv[i];
             }
         }
         __syncwarp();
-        const uint8_t *rd[2] = { codes + (2 * pi) * stride, codes + (2 * pi + 1) * stride };
+        uint8_t *const rd[2] = { s_c[wib], s_c[wib] + moff };
+        uint8_t *const qr[2] = { s_qr[wib], s_qr[wib] + moff };
+        // base / quality i of mate e in BAM SEQ orientation
         auto seq_base = [&](int e, int i) {
             const int c = rev[e] ? rd[e][L[e] - 1 - i] : rd[e][i];
             return rev[e] ? (c > 3 ? 4 : 3 - c) : c;
         };
+        auto qual = [&](int e, int i) -> uint8_t & { return qr[e][rev[e] ? L[e] - 1 - i : i]; };
         // ---- mate overlap: the mate that comes first in coordinate order plays htslib's `a` ----
         if (!po.ignore_overlaps && ok[0] && ok[1] && rid[0] == rid[1] && (flag[0] & 0x2) && !(flag[0] & 0x8) &&
             abs(tlen[0]) < 2 * L[0] && abs(tlen[1]) < 2 * L[1]) {
@@ -144,12 +174,12 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
                 if (p < 0) continue;
                 const int ib = qidx_of(s_aln[wib][B], p);
                 if (ib < 0) continue;
-                const int qa = s_q[wib][A][ia], qb = s_q[wib][B][ib];
+                const int qa = qual(A, ia), qb = qual(B, ib);
                 if (seq_base(A, ia) == seq_base(B, ib)) {
                     const int q = qa + qb;
-                    s_q[wib][A][ia] = (uint8_t)(q > 200 ? 200 : q); s_q[wib][B][ib] = 0;
-                } else if (qa >= qb) { s_q[wib][A][ia] = (uint8_t)(0.8 * qa); s_q[wib][B][ib] = 0; }
-                else { s_q[wib][B][ib] = (uint8_t)(0.8 * qb); s_q[wib][A][ia] = 0; }
+                    qual(A, ia) = (uint8_t)(q > 200 ? 200 : q); qual(B, ib) = 0;
+                } else if (qa >= qb) { qual(A, ia) = (uint8_t)(0.8 * qa); qual(B, ib) = 0; }
+                else { qual(B, ib) = (uint8_t)(0.8 * qb); qual(A, ia) = 0; }
             }
         }
         __syncwarp();
@@ -160,11 +190,16 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
             ++admitted_local;
             const AlnS &a = s_aln[wib][e];
             const int64_t base = V.off[rid[e]];
+            int32_t *const mns = minus + (rev[e] ? L_pac : 0) + base;
             for (int i = lane; i < L[e]; i += 32) {
                 const int p = rpos_of(a, i);
                 if (p < 0) continue;
-                red_add(counts + 14 * L_pac + base + p);
-                if (s_q[wib][e][i] >= po.min_bq) red_add(counts + (int64_t)((rev[e] ? 6 : 0) + seq_base(e, i)) * L_pac + base + p);
+                const int c = seq_base(e, i);
+                if (qual(e, i) < po.min_bq) red_add(mns + p);                       // covered, not counted
+                else if (c != V.refb[base + p]) {                                       // counted in its own channel
+                    red_add(mns + p);
+                    red_add(counts + (int64_t)((rev[e] ? 6 : 0) + c) * L_pac + base + p);
+                }
             }
             if (lane < a.n_cigar) {          // operation-level channels: lane k owns CIGAR operation k
                 int p = a.pos, last_m = -1, x = 0;
@@ -176,8 +211,11 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
                     else if (op == 1 || op == 4) x += len;
                 }
                 const int op = a.cigar[lane] & 0xf, len = (int)(a.cigar[lane] >> 4);
-                if (op == 0 && !started) red_add(counts + 15 * L_pac + base + p);
-                else if (op == 1) {
+                if (op == 0) {                                                          // coverage of this M block
+                    int32_t *const cv = cov + (rev[e] ? L_pac + 1 : 0) + base + p;
+                    atomicAdd(cv, 1); atomicAdd(cv + len, -1);
+                    if (!started) red_add(counts + 15 * L_pac + base + p);
+                } else if (op == 1) {
                     if (last_m >= 0) {
                         red_add(counts + 12 * L_pac + base + last_m);
                         if (T.keys) {                  // the inserted bases as the forward strand of the reference reads them
@@ -197,6 +235,20 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
         }
     }
     if (n_admitted && lane == 0 && admitted_local) atomicAdd(n_admitted, admitted_local);
+}
+
+// cov holds the inclusive prefix sums of the difference arrays now = reads covering each column, per strand
+__global__ void pileup_finish_kernel(IndexView V, const int32_t *__restrict__ cov, const int32_t *__restrict__ minus, int32_t *__restrict__ counts)
+{
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t L = V.l_pac;
+    if (p >= L) return;
+    const int c0 = cov[p], c1 = cov[L + 1 + p];
+    if (c0 | c1) {
+        counts[14 * L + p] += c0 + c1;
+        const int r = V.refb[p];
+        if (r < 4) { counts[(int64_t)r * L + p] += c0 - minus[p]; counts[(int64_t)(6 + r) * L + p] += c1 - minus[L + p]; }
+    }
 }
 
 // [16][l_pac] planes -> [l_pac][16] rows (the count-TSV row order)
@@ -371,10 +423,27 @@ int qm_pileup_accumulate_masked(qm_ctx *ctx, const qm_index *idx, const qm_pileu
     int64_t blocks = (n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int64_t cap = (int64_t)ctx->sm_count * 16;       // persistent: 16 blocks x 4 warps per SM
     if (blocks > cap) blocks = cap;
-    const int sp = qm_prof_begin(ctx, QM_ST_PILEUP, (cudaStream_t)stream);
-    pileup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab), d_drop);
-    qm_prof_end(ctx, QM_ST_PILEUP, sp, (cudaStream_t)stream, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t L = idx->v.l_pac;
+    // scratch 25: difference arrays [2][L + 1] | minus [2][L] | cub temp
+    const size_t cov_bytes = (size_t)2 * (L + 1) * 4, minus_bytes = (size_t)2 * L * 4;
+    const size_t o_minus = (cov_bytes + 255) & ~(size_t)255, o_cub = (o_minus + minus_bytes + 255) & ~(size_t)255;
+    size_t cub_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (int32_t *)nullptr, (int)(2 * (L + 1)), st);
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 25, o_cub + cub_bytes, &p);
+    if (rc) return rc;
+    int32_t *cov = (int32_t *)p, *minus = (int32_t *)((char *)p + o_minus);
+    const int sp = qm_prof_begin(ctx, QM_ST_PILEUP, st);
+    QM_CUDA(ctx, cudaMemsetAsync(p, 0, o_minus + minus_bytes, st));
+    pileup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab), d_drop, cov, minus,
+        (stride & 1) == 0 && stride <= kMaxLen && (((uintptr_t)d_codes | (uintptr_t)d_quals) & 3u) == 0);
+    QM_CUDA(ctx, cudaGetLastError());
+    // both strands in one scan: a strand's differences sum to zero, so the running sum is back at 0 where the next one starts
+    QM_CUDA(ctx, cub::DeviceScan::InclusiveSum((char *)p + o_cub, cub_bytes, cov, cov, (int)(2 * (L + 1)), st));
+    pileup_finish_kernel<<<(unsigned)((L + 255) / 256), 256, 0, st>>>(idx->v, cov, minus, d_counts);
+    qm_prof_end(ctx, QM_ST_PILEUP, sp, st, 4);
     QM_CUDA(ctx, cudaGetLastError());
     return QM_OK;
 }

@@ -246,3 +246,20 @@ def test_mate_rescue_inline_path_is_bit_exact():
     p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_pipeline_gpu.py", "-q", "-x", "-k", "cfg1-3000 or cfg5 or without_mate_rescue"],
                        cwd=root, env=dict(os.environ, QM_RESCUE_INLINE="1"), capture_output=True, text=True)
     assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"QM_SPEC_DEPTH": "2"}, {"QM_SPEC": "0"}], ids=["two-seeds-ahead-per-pass", "serial-tail"])
+def test_speculative_finish_variants_are_bit_exact(env):
+    """the last reads of a batch run every remaining seed's extensions ahead of the state machine (align.cu spec_* kernels);
+    QM_SPEC_DEPTH=2 enters only two seeds per pass (reads run past their directory and open further passes), QM_SPEC=0 is the
+    serial warp-per-read tail.  All three give the oracle's regions and cell counts."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("QM_SPEC_DEPTH") or os.environ.get("QM_SPEC"):
+        pytest.skip("already inside a QM_SPEC run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_pipeline_gpu.py", "-q", "-x", "-k", "cfg1-3000 or cfg5-2000 or rescue-heavy or long_reads"],
+                       cwd=root, env=dict(os.environ, **env), capture_output=True, text=True)
+    assert p.returncode == 0 and " passed" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
