@@ -17,6 +17,7 @@
 // Tasks reference the read batch and the reference in place (ExtTaskI, QM_EXTI_INDIRECT); no sequence
 // bytes are materialised.
 #include <stdlib.h>
+#include <algorithm>
 #include "pipeline.cuh"
 #include "ext_warp.cuh"
 
@@ -527,6 +528,60 @@ struct RoundCounters {        // zeroed before every advance round; the host rea
 };
 constexpr size_t kRoundHeader = (2 * kExtCtr + 8) * sizeof(int);
 
+// the chain's reference window (mem_chain2aln rmax[], clamped to the contig as bns_fetch_seq does) and contig
+struct ChainWin { int64_t rmax0, rmax1; int rid; };
+__device__ ChainWin chain_window(const IndexView &V, const qm_opt &o, int lq, const qm_seed *S, const uint16_t *PL, int np, int chain,
+                                 const qm_seed &sd)
+{
+    const int64_t l_pac = V.l_pac;
+    int64_t rmax0 = l_pac << 1, rmax1 = 0;
+    qm_seed first_seed = sd;
+    int first_idx = 1 << 30;
+    for (int i = 0; i < np; ++i) {
+        if (((PL[i] >> 6) & 63) != chain) continue;
+        const int si = PL[i] & 63;
+        const qm_seed t = S[si];
+        const int64_t b = t.rbeg - (t.qbeg + max_gap_for(o, t.qbeg));
+        const int tail = lq - t.qbeg - t.len;
+        const int64_t e = t.rbeg + t.len + (tail + max_gap_for(o, tail));
+        rmax0 = b < rmax0 ? b : rmax0;
+        rmax1 = e > rmax1 ? e : rmax1;
+        if (si < first_idx) { first_idx = si; first_seed = t; }     // seed 0 of the chain = lowest seed index
+    }
+    rmax0 = rmax0 > 0 ? rmax0 : 0;
+    rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
+    if (rmax0 < l_pac && l_pac < rmax1) { if (first_seed.rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
+    ChainWin W;
+    const bool rev = first_seed.rbeg >= l_pac;
+    const int64_t f = rev ? 2 * l_pac - 1 - first_seed.rbeg : first_seed.rbeg;
+    W.rid = qm_pos2rid(V, f);
+    int64_t far_beg = V.off[W.rid], far_end = V.off[W.rid] + V.len[W.rid];
+    if (rev) { const int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
+    W.rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
+    W.rmax1 = rmax1 < far_end ? rmax1 : far_end;
+    return W;
+}
+// the two extensions of a seed (mem_chain2aln): left of it (query and target reversed), then right of it with the left score as h0.
+// A task is a function of the seed and its chain alone -- which is what lets the tail of a batch run them ahead of the
+// state machine (spec_* kernels below).
+__device__ __forceinline__ void left_task(const qm_opt &o, const uint8_t *query, const qm_seed &sd, const ChainWin &W, ExtTaskI *t)
+{
+    t->q = query + sd.qbeg - 1; t->qstep = -1; t->qlen = sd.qbeg;
+    t->t = nullptr; t->t0 = sd.rbeg - 1; t->tstep = -1; t->tlen = (int)(sd.rbeg - W.rmax0);
+    t->h0 = sd.len * o.a; t->w = o.w; t->end_bonus = o.pen_clip5;
+    t->flags = QM_EXT_BAND_RETRY | QM_EXTI_INDIRECT;
+}
+__device__ __forceinline__ void right_task(const qm_opt &o, const uint8_t *query, int lq, const qm_seed &sd, const ChainWin &W, int h0,
+                                           ExtTaskI *t)
+{
+    const int qe = sd.qbeg + sd.len;
+    const int64_t re = sd.rbeg + sd.len;
+    t->q = query + qe; t->qstep = 1; t->qlen = lq - qe;
+    t->t = nullptr; t->t0 = re; t->tstep = 1; t->tlen = (int)(W.rmax1 - re);
+    t->h0 = h0; t->w = o.w; t->end_bonus = o.pen_clip3;
+    t->flags = QM_EXT_BAND_RETRY | QM_EXT_PREV_H0 | QM_EXTI_INDIRECT;
+}
+
 // ---- mem_chain2aln as a per-read state machine ----
 // Consumes the result of the read's pending extension (xres, when the state is a WAIT state), then walks the plan
 // until the next extension task is known (returns true, task in *t_out) or the read is finished (returns false,
@@ -535,8 +590,6 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
                              int np, ReadState &s, qm_reg *av, int32_t *n_regs_out, const qm_ext_result *xres, int64_t r,
                              ExtTaskI *t_out, unsigned long long *cells /* caller's local sum, may be NULL */)
 {
-    const int64_t l_pac = V.l_pac;
-
     if (s.phase == PH_WAIT_LEFT) {
         const qm_ext_result x = *xres;
         const qm_seed sd = S[PL[s.cursor] & 63];
@@ -627,37 +680,10 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
                 return false;
             }
         }
-        // the chain's reference window (mem_chain2aln rmax[], clamped to the contig as bns_fetch_seq does)
         const int ent = PL[s.cursor];
-        const int chain = (ent >> 6) & 63;
         const qm_seed sd = S[ent & 63];
-        int64_t rmax0 = l_pac << 1, rmax1 = 0;
-        qm_seed first_seed = sd;
-        int first_idx = 1 << 30;
-        for (int i = 0; i < np; ++i) {
-            if (((PL[i] >> 6) & 63) != chain) continue;
-            const int si = PL[i] & 63;
-            const qm_seed t = S[si];
-            const int64_t b = t.rbeg - (t.qbeg + max_gap_for(o, t.qbeg));
-            const int tail = lq - t.qbeg - t.len;
-            const int64_t e = t.rbeg + t.len + (tail + max_gap_for(o, tail));
-            rmax0 = b < rmax0 ? b : rmax0;
-            rmax1 = e > rmax1 ? e : rmax1;
-            if (si < first_idx) { first_idx = si; first_seed = t; }     // seed 0 of the chain = lowest seed index
-        }
-        rmax0 = rmax0 > 0 ? rmax0 : 0;
-        rmax1 = rmax1 < l_pac << 1 ? rmax1 : l_pac << 1;
-        if (rmax0 < l_pac && l_pac < rmax1) { if (first_seed.rbeg < l_pac) rmax1 = l_pac; else rmax0 = l_pac; }
-        int rid;
-        {
-            const bool rev = first_seed.rbeg >= l_pac;
-            const int64_t f = rev ? 2 * l_pac - 1 - first_seed.rbeg : first_seed.rbeg;
-            rid = qm_pos2rid(V, f);
-            int64_t far_beg = V.off[rid], far_end = V.off[rid] + V.len[rid];
-            if (rev) { const int64_t t = far_beg; far_beg = (l_pac << 1) - far_end; far_end = (l_pac << 1) - t; }
-            rmax0 = rmax0 > far_beg ? rmax0 : far_beg;
-            rmax1 = rmax1 < far_end ? rmax1 : far_end;
-        }
+        const ChainWin W = chain_window(V, o, lq, S, PL, np, (ent >> 6) & 63, sd);
+        const int rid = W.rid;
         ExtTaskI t;
         bool emit = false;
         if (s.phase == PH_NEXT) {
@@ -666,10 +692,7 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
             z.w = o.w; z.score = z.truesc = -1; z.rid = rid; z.secondary = -1;
             *a = z;
             if (sd.qbeg) {
-                t.q = query + sd.qbeg - 1; t.qstep = -1; t.qlen = sd.qbeg;
-                t.t = nullptr; t.t0 = sd.rbeg - 1; t.tstep = -1; t.tlen = (int)(sd.rbeg - rmax0);
-                t.h0 = sd.len * o.a; t.w = o.w; t.end_bonus = o.pen_clip5;
-                t.flags = QM_EXT_BAND_RETRY | QM_EXTI_INDIRECT;
+                left_task(o, query, sd, W, &t);
                 emit = true;
                 s.phase = PH_WAIT_LEFT;
             } else {
@@ -680,12 +703,7 @@ __device__ bool advance_read(const IndexView &V, const qm_opt &o, const uint8_t 
         if (s.phase == PH_RIGHT) {
             qm_reg *a = &av[s.n_av];
             if (sd.qbeg + sd.len != lq) {
-                const int qe = sd.qbeg + sd.len;
-                const int64_t re = sd.rbeg + sd.len;
-                t.q = query + qe; t.qstep = 1; t.qlen = lq - qe;
-                t.t = nullptr; t.t0 = re; t.tstep = 1; t.tlen = (int)(rmax1 - re);
-                t.h0 = a->score; t.w = o.w; t.end_bonus = o.pen_clip3;
-                t.flags = QM_EXT_BAND_RETRY | QM_EXT_PREV_H0 | QM_EXTI_INDIRECT;
+                right_task(o, query, lq, sd, W, a->score, &t);
                 emit = true;
                 s.phase = PH_WAIT_RIGHT;
             } else {
@@ -843,6 +861,146 @@ tail_kernel(IndexView V, qm_opt o, ExtParams P, const uint8_t *__restrict__ code
     if (lane == 0 && cells && my_cells) atomicAdd(cells, my_cells);
 }
 
+// ---- speculative finish of a batch's last reads ----
+// After the bulk rounds only reads with many seeds are left (tandem repeats, terminal repeats: up to 2 x QM_MAX_REGS DEPENDENT
+// extensions each), and the batch waits for the longest such chain: extension after extension, each ~150 rows of a latency-bound
+// kernel (round 1's tail_kernel: 3.3 ms for 2 % of the cells, plus the three small rounds before it).  But an extension task is
+// a function of its seed and chain alone (left_task / right_task); what depends on earlier results is only whether
+// mem_chain2aln SKIPS the seed.  So every remaining seed of these reads is extended ahead of time, all at once, by the
+// throughput kernels -- left sides in one launch group, right sides (h0 = the left score) in a second -- and the state machine
+// then runs to the end on results that are already there.  Results of seeds it skips are discarded (and not counted as cells).
+// Same regions as the serial order, bit for bit; the dependent chain shrinks from dozens of extensions to two.
+constexpr int kSpecMinTasks = 1 << 17;       // a round with fewer tasks switches to this mode (rows of the directory)
+constexpr int kSpecCap = 1 << 20;             // tasks per launch group
+constexpr int kSpecDirRow = 2 * QM_MAX_SEEDS; // directory entries per read: [plan index][side]
+static_assert(QM_MAX_SEEDS <= 64, "plan index must fit the 6 bits of ExtTaskI::pad[1]");
+
+struct SpecScratch {
+    ExtTaskI *tasks;            // [2 * kSpecCap]: group A (pending + left sides + right sides of seeds without a left), group B at kSpecCap
+    qm_ext_result *res;         // [2 * kSpecCap]
+    uint64_t *keys;             // [2 * kSpecCap]
+    int *lists;                 // [2 * kSpecCap] sorted lists, then the fallback lists [2][kExtClasses][kSpecCap]
+    int *dir;                   // [kSpecMinTasks][kSpecDirRow]: slot of the task of (read, plan index, side), -1 = none
+    int *meta;                  // [kSpecMinTasks]: lo | hi << 8: plan indices [lo, hi) of the read are in the directory
+    ExtTaskI *next_tasks;       // [kSpecMinTasks]: what the next pass starts from (reads that ran past their directory)
+    uint64_t *next_keys;
+    RoundCounters *ctr;         // [3]: group A, group B, next pass
+};
+
+__device__ __forceinline__ void spec_emit(const ExtTaskI &t, int slot, ExtTaskI *tasks, uint64_t *keys, RoundCounters *ctr, const qm_opt &o)
+{
+    tasks[slot] = t;
+    keys[slot] = qm_ext_sort_key(t.qlen, t.tlen, t.h0);
+    atomicAdd(&ctr->class_count[qm_ext_class(t.qlen)], 1);
+    atomicMax(&ctr->max_score, t.h0 + t.qlen * o.a);
+}
+
+// one thread per pending task (= per active read): enter it and every later seed of the read's plan into group A
+__global__ void __launch_bounds__(128)
+spec_plan_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                 const qm_seed *__restrict__ seeds, const uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
+                 const ReadState *__restrict__ st, int n_active, int depth, SpecScratch X)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_active) return;
+    RoundCounters *ctr = X.ctr;
+    const int64_t r = X.tasks[row].pad[0];
+    const ReadState s = st[r];
+    const qm_seed *S = seeds + r * QM_MAX_SEEDS;
+    const uint16_t *PL = plan + r * QM_MAX_SEEDS;
+    const int np = n_plan[r], lq = lens[r];
+    const uint8_t *query = codes + r * stride;
+    int *d = X.dir + (size_t)row * kSpecDirRow;
+    const int lo = s.cursor, side0 = s.phase == PH_WAIT_RIGHT ? 1 : 0;
+    d[2 * lo + side0] = row; d[2 * lo + 1 - side0] = -1;
+    X.tasks[row].pad[1] = row << 8 | lo << 1 | side0;
+    int hi = lo + 1;
+    for (int i = lo + 1; i < np && i <= lo + depth; ++i) {
+        const int ent = PL[i];
+        const qm_seed sd = S[ent & 63];
+        int side = -1;
+        ExtTaskI t;
+        if (sd.qbeg) side = 0; else if (sd.qbeg + sd.len != lq) side = 1;
+        if (side >= 0) {
+            const int slot = atomicAdd(&ctr->n_tasks, 1);
+            if (slot >= kSpecCap) break;                // group full: the rest of this read waits for the next pass
+            const ChainWin W = chain_window(V, o, lq, S, PL, np, (ent >> 6) & 63, sd);
+            if (side == 0) left_task(o, query, sd, W, &t); else right_task(o, query, lq, sd, W, sd.len * o.a, &t);
+            t.pad[0] = (int)r; t.pad[1] = row << 8 | i << 1 | side;
+            spec_emit(t, slot, X.tasks, X.keys, ctr, o);
+            d[2 * i + side] = slot; d[2 * i + 1 - side] = -1;
+        } else { d[2 * i] = -1; d[2 * i + 1] = -1; }
+        hi = i + 1;
+    }
+    X.meta[row] = lo | hi << 8;
+}
+
+// one thread per task of group A: a left side that has run gives its seed's right side (group B)
+__global__ void __launch_bounds__(128)
+spec_right_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                  const qm_seed *__restrict__ seeds, const uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan, int n_a, SpecScratch X)
+{
+    const int ta = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ta >= n_a) return;
+    const int tag = X.tasks[ta].pad[1];
+    if (tag & 1) return;
+    const int i = (tag >> 1) & 63, row = tag >> 8;
+    const int64_t r = X.tasks[ta].pad[0];
+    const qm_seed *S = seeds + r * QM_MAX_SEEDS;
+    const uint16_t *PL = plan + r * QM_MAX_SEEDS;
+    const int ent = PL[i], lq = lens[r];
+    const qm_seed sd = S[ent & 63];
+    if (sd.qbeg + sd.len == lq) return;
+    RoundCounters *ctr = X.ctr + 1;
+    const int slot = atomicAdd(&ctr->n_tasks, 1);       // <= n_a <= kSpecCap
+    const ChainWin W = chain_window(V, o, lq, S, PL, n_plan[r], (ent >> 6) & 63, sd);
+    ExtTaskI t;
+    right_task(o, codes + r * stride, lq, sd, W, X.res[ta].score, &t);
+    t.pad[0] = (int)r; t.pad[1] = row << 8 | i << 1 | 1;
+    spec_emit(t, slot, X.tasks + kSpecCap, X.keys + kSpecCap, ctr, o);
+    X.dir[(size_t)row * kSpecDirRow + 2 * i + 1] = kSpecCap + slot;
+}
+
+// one thread per active read: the state machine, fed from the directory, to the end of the plan (or of the directory)
+__global__ void __launch_bounds__(128)
+spec_finish_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
+                   const qm_seed *__restrict__ seeds, uint16_t *__restrict__ plan, const uint8_t *__restrict__ n_plan,
+                   ReadState *__restrict__ st, qm_reg *__restrict__ regs, int32_t *__restrict__ n_regs, int n_active, SpecScratch X,
+                   unsigned long long *__restrict__ cells)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long my_cells = 0;
+    if (row < n_active) {
+        const int64_t r = X.tasks[row].pad[0];
+        ReadState s = st[r];
+        const int meta = X.meta[row], lo = meta & 255, hi = meta >> 8;
+        const int *d = X.dir + (size_t)row * kSpecDirRow;
+        const qm_ext_result *xres = X.res + row;
+        RoundCounters *ctr = X.ctr + 2;
+        for (;;) {
+            ExtTaskI t;
+            const bool more = advance_read(V, o, codes + r * stride, lens[r], seeds + r * QM_MAX_SEEDS, plan + r * QM_MAX_SEEDS, n_plan[r],
+                                           s, regs + r * QM_MAX_REGS, n_regs + r, xres, r, &t, &my_cells);
+            if (!more) { s.task = -1; break; }
+            const int i = s.cursor, side = s.phase == PH_WAIT_RIGHT ? 1 : 0;
+            const int slot = (i >= lo && i < hi) ? d[2 * i + side] : -1;
+            if (slot < 0) {                              // past the directory: this task opens the read's next pass
+                const int k = atomicAdd(&ctr->n_tasks, 1);
+                spec_emit(t, k, X.next_tasks, X.next_keys, ctr, o);
+                s.task = k;
+                break;
+            }
+            xres = X.res + slot;
+        }
+        st[r] = s;
+    }
+    if (cells) {
+        unsigned long long v = my_cells;
+        for (int dd = 16; dd > 0; dd >>= 1) v += __shfl_down_sync(0xffffffffu, v, dd);
+        if (qm_lane() == 0 && v) atomicAdd(cells, v);
+    }
+}
+
 constexpr int64_t kSeBatch = 1 << 22;         // a round with fewer tasks hands the still-active reads to tail_kernel       // reads per internal round-trip (bounds scratch memory)
 
 struct SeScratch {
@@ -872,6 +1030,93 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     sc->n_plan = (uint8_t *)(b + o_np); sc->st = (ReadState *)(b + o_st); sc->tasks = (ExtTaskI *)(b + o_tasks);
     sc->res = (qm_ext_result *)(b + o_res); sc->lists = (int *)(b + o_lists); sc->keys = (uint64_t *)(b + o_keys); sc->ctr = (RoundCounters *)(b + o_ctr);
     return QM_OK;
+}
+
+int spec_scratch(qm_ctx *ctx, SpecScratch *X)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_tasks = take((size_t)2 * kSpecCap * sizeof(ExtTaskI)), o_res = take((size_t)2 * kSpecCap * sizeof(qm_ext_result));
+    const size_t o_keys = take((size_t)2 * kSpecCap * 8), o_lists = take((size_t)(2 + 2 * kExtClasses) * kSpecCap * 4);
+    const size_t o_dir = take((size_t)kSpecMinTasks * kSpecDirRow * 4), o_meta = take((size_t)kSpecMinTasks * 4);
+    const size_t o_nt = take((size_t)kSpecMinTasks * sizeof(ExtTaskI)), o_nk = take((size_t)kSpecMinTasks * 8), o_ctr = take(3 * sizeof(RoundCounters));
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 26, off, &p);
+    if (rc) return rc;
+    char *b = (char *)p;
+    X->tasks = (ExtTaskI *)(b + o_tasks); X->res = (qm_ext_result *)(b + o_res); X->keys = (uint64_t *)(b + o_keys); X->lists = (int *)(b + o_lists);
+    X->dir = (int *)(b + o_dir); X->meta = (int *)(b + o_meta); X->next_tasks = (ExtTaskI *)(b + o_nt); X->next_keys = (uint64_t *)(b + o_nk);
+    X->ctr = (RoundCounters *)(b + o_ctr);
+    return QM_OK;
+}
+
+// sort one launch group by (query length, rows, seed score) and run it through the class kernels
+int spec_run_group(qm_ctx *ctx, const ExtParams &P, const IndexView &V, SpecScratch &X, int g, int n, const RoundCounters *h_ctr, cudaStream_t st)
+{
+    const size_t base = (size_t)g * kSpecCap;
+    int sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
+    int rc = qm_sort_pairs(ctx, X.keys + base, (uint32_t *)(X.lists + base), n, kExtSortKeyBits, st);
+    qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 0);
+    if (rc) return rc;
+    int64_t list_off[kExtClasses];
+    int n_launch = 0;
+    { int64_t acc = 0; for (int c = 0; c < kExtClasses; ++c) { list_off[c] = acc; acc += h_ctr->class_count[c]; n_launch += h_ctr->class_count[c] > 0; } }
+    sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
+    rc = qm_ext_launch_classes(ctx, P, V, X.tasks + base, X.lists + base, kSpecCap, X.ctr[g].class_count, X.ctr[g].class_cursor, h_ctr->class_count,
+                               X.res + base, X.lists + (size_t)(2 + g * kExtClasses) * kSpecCap, X.ctr[g].fb, st, h_ctr->max_score <= 255, list_off);
+    qm_prof_end(ctx, QM_ST_EXTEND, sp, st, n_launch);
+    return rc;
+}
+
+// the reads still active (their pending tasks are sc.tasks[0 .. n_active), counters sc.ctr) run to the end of their plans
+int spec_finish_batch(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const ExtParams &P, const uint8_t *codes, int stride, const int32_t *lens,
+                      const SeScratch &sc, qm_reg *regs, int32_t *n_regs, int64_t *d_cells, RoundCounters *h_ctr, int n_active, cudaStream_t st)
+{
+    SpecScratch X;
+    int rc = spec_scratch(ctx, &X);
+    if (rc) return rc;
+    static const int depth = getenv("QM_SPEC_DEPTH") ? atoi(getenv("QM_SPEC_DEPTH")) : QM_MAX_SEEDS;      // test knob: seeds entered ahead per pass
+    static const bool spec_log = getenv("QM_ROUND_LOG") != nullptr;
+    QM_CUDA(ctx, cudaMemcpyAsync(X.tasks, sc.tasks, (size_t)n_active * sizeof(ExtTaskI), cudaMemcpyDeviceToDevice, st));
+    QM_CUDA(ctx, cudaMemcpyAsync(X.keys, sc.keys, (size_t)n_active * 8, cudaMemcpyDeviceToDevice, st));
+    QM_CUDA(ctx, cudaMemcpyAsync(X.ctr, sc.ctr, sizeof(RoundCounters), cudaMemcpyDeviceToDevice, st));
+    for (int pass = 0; pass < 4 * QM_MAX_REGS + 8; ++pass) {
+        const unsigned grid = (unsigned)((n_active + 127) / 128);
+        int sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
+        QM_CUDA(ctx, cudaMemsetAsync(X.ctr + 1, 0, 2 * sizeof(RoundCounters), st));
+        spec_plan_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan, sc.st, n_active, depth, X);
+        qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
+        QM_CUDA(ctx, cudaMemcpyAsync(h_ctr, X.ctr, kRoundHeader, cudaMemcpyDeviceToHost, st));
+        QM_CUDA(ctx, cudaStreamSynchronize(st));
+        const int n_a = h_ctr->n_tasks < kSpecCap ? h_ctr->n_tasks : kSpecCap;
+        if (spec_log) fprintf(stderr, "[qm spec pass %d] reads %d group A %d", pass, n_active, n_a);
+        rc = spec_run_group(ctx, P, idx->v, X, 0, n_a, h_ctr, st);
+        if (rc) return rc;
+        sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
+        spec_right_kernel<<<(unsigned)((n_a + 127) / 128), 128, 0, st>>>(idx->v, *opt, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan, n_a, X);
+        qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
+        QM_CUDA(ctx, cudaMemcpyAsync(h_ctr, X.ctr + 1, kRoundHeader, cudaMemcpyDeviceToHost, st));
+        QM_CUDA(ctx, cudaStreamSynchronize(st));
+        const int n_b = h_ctr->n_tasks;
+        if (spec_log) fprintf(stderr, " group B %d", n_b);
+        if (n_b > 0) {
+            rc = spec_run_group(ctx, P, idx->v, X, 1, n_b, h_ctr, st);
+            if (rc) return rc;
+        }
+        sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
+        spec_finish_kernel<<<grid, 128, 0, st>>>(idx->v, *opt, codes, stride, lens, sc.seeds, sc.plan, sc.n_plan, sc.st, regs, n_regs, n_active, X,
+                                                 (unsigned long long *)d_cells);
+        qm_prof_end(ctx, QM_ST_ADVANCE, sp, st, 1);
+        QM_CUDA(ctx, cudaMemcpyAsync(h_ctr, X.ctr + 2, kRoundHeader, cudaMemcpyDeviceToHost, st));
+        QM_CUDA(ctx, cudaStreamSynchronize(st));
+        if (spec_log) fprintf(stderr, " -> next %d\n", h_ctr->n_tasks);
+        if (h_ctr->n_tasks == 0) return QM_OK;
+        n_active = h_ctr->n_tasks;
+        QM_CUDA(ctx, cudaMemcpyAsync(X.tasks, X.next_tasks, (size_t)n_active * sizeof(ExtTaskI), cudaMemcpyDeviceToDevice, st));
+        QM_CUDA(ctx, cudaMemcpyAsync(X.keys, X.next_keys, (size_t)n_active * 8, cudaMemcpyDeviceToDevice, st));
+        QM_CUDA(ctx, cudaMemcpyAsync(X.ctr, X.ctr + 2, sizeof(RoundCounters), cudaMemcpyDeviceToDevice, st));
+    }
+    return qm_fail(ctx, QM_ECUDA, "spec_finish_batch: reads still active after %d passes", 4 * QM_MAX_REGS + 8);
 }
 
 }  // namespace
@@ -971,6 +1216,14 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 fprintf(stderr, "[qm round %d] tasks %d max_score %d classes", round, h_ctr->n_tasks, h_ctr->max_score);
                 for (int c = 0; c < kExtClasses; ++c) fprintf(stderr, " %d", h_ctr->class_count[c]);
                 fprintf(stderr, "\n");
+            }
+            static const bool spec_on = !(getenv("QM_SPEC") && atoi(getenv("QM_SPEC")) == 0);       // QM_SPEC=0: the serial tail of round 1
+            static const int spec_min = getenv("QM_SPEC_MIN") ? std::min(atoi(getenv("QM_SPEC_MIN")), kSpecMinTasks) : kSpecMinTasks;   // tuning knob
+            if (spec_on && h_ctr->n_tasks < spec_min) {
+                rc = spec_finish_batch(ctx, idx, opt, P, codes, stride, lens, sc, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, d_cells, h_ctr,
+                                       h_ctr->n_tasks, st);
+                if (rc) return rc;
+                break;
             }
             static const int tail_min = getenv("QM_TAIL_MIN") ? atoi(getenv("QM_TAIL_MIN")) : kTailMinTasks;       // tuning knob
             if (h_ctr->n_tasks < tail_min) {
