@@ -53,22 +53,23 @@ __device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
 //  * a k-mer whose canonical form misses the Bloom filter occurs on neither strand.
 // The read is packed once into shared memory (2 bits per base + an N bitmap); k-mers are cut out of the packed words,
 // so no rolling state ties one position to the next and whole runs can be skipped.
-constexpr int kSeedThreads = 128;
+constexpr int kSeedThreads = 128;          // most a block may have (launch bounds); launched with kSeedThreadsDefault
 
 struct PackedRead {                 // per-thread view of the block's shared arrays, [word][thread]
     uint64_t *bits;                 // base j at bits 2*(j&31) of word j>>5
     uint64_t *nmask;                // bit j&63 of word j>>6: base j is N
+    int ts;                         // threads per block = stride of both arrays
     __device__ __forceinline__ uint64_t get2(int b) const
     {   // 32 bases starting at base b (words past the read are zero)
         const int w = b >> 5, sh = 2 * (b & 31);
-        const uint64_t lo = bits[w * kSeedThreads];
-        return sh ? (lo >> sh) | (bits[(w + 1) * kSeedThreads] << (64 - sh)) : lo;
+        const uint64_t lo = bits[w * ts];
+        return sh ? (lo >> sh) | (bits[(w + 1) * ts] << (64 - sh)) : lo;
     }
     __device__ __forceinline__ uint64_t getn(int b) const
     {   // N flags of 64 bases starting at base b
         const int w = b >> 6, sh = b & 63;
-        const uint64_t lo = nmask[w * kSeedThreads];
-        return sh ? (lo >> sh) | (nmask[(w + 1) * kSeedThreads] << (64 - sh)) : lo;
+        const uint64_t lo = nmask[w * ts];
+        return sh ? (lo >> sh) | (nmask[(w + 1) * ts] << (64 - sh)) : lo;
     }
 };
 
@@ -96,16 +97,16 @@ __device__ __forceinline__ uint32_t uniq_get(const uint32_t *__restrict__ map, i
 
 __device__ void pack_read(const uint8_t *__restrict__ rd, int len, int n_words, int n_nwords, PackedRead &R)
 {
-    for (int w = 0; w < n_words; ++w) R.bits[w * kSeedThreads] = 0;
-    for (int w = 0; w < n_nwords; ++w) R.nmask[w * kSeedThreads] = 0;
+    for (int w = 0; w < n_words; ++w) R.bits[w * R.ts] = 0;
+    for (int w = 0; w < n_nwords; ++w) R.nmask[w * R.ts] = 0;
     uint64_t acc = 0, nacc = 0;
     int j = 0;
     auto put = [&](unsigned c) {
         acc |= (uint64_t)(c & 3u) << (2 * (j & 31));
         nacc |= (uint64_t)(c >> 2) << (j & 63);
         ++j;
-        if ((j & 31) == 0) { R.bits[((j >> 5) - 1) * kSeedThreads] = acc; acc = 0; }
-        if ((j & 63) == 0) { R.nmask[((j >> 6) - 1) * kSeedThreads] = nacc; nacc = 0; }
+        if ((j & 31) == 0) { R.bits[((j >> 5) - 1) * R.ts] = acc; acc = 0; }
+        if ((j & 63) == 0) { R.nmask[((j >> 6) - 1) * R.ts] = nacc; nacc = 0; }
     };
     // head bytes up to 4-byte alignment, then whole words (4 bases per load), then the tail
     while (j < len && ((uintptr_t)(rd + j) & 3u)) put(rd[j]);
@@ -118,15 +119,15 @@ __device__ void pack_read(const uint8_t *__restrict__ rd, int len, int n_words, 
             acc |= (uint64_t)c4 << (2 * (j & 31));
             nacc |= (uint64_t)n4 << (j & 63);
             j += 4;
-            if ((j & 31) == 0) { R.bits[((j >> 5) - 1) * kSeedThreads] = acc; acc = 0; }
-            if ((j & 63) == 0) { R.nmask[((j >> 6) - 1) * kSeedThreads] = nacc; nacc = 0; }
+            if ((j & 31) == 0) { R.bits[((j >> 5) - 1) * R.ts] = acc; acc = 0; }
+            if ((j & 63) == 0) { R.nmask[((j >> 6) - 1) * R.ts] = nacc; nacc = 0; }
         } else {
             put(w4 & 0xffu); put((w4 >> 8) & 0xffu); put((w4 >> 16) & 0xffu); put(w4 >> 24);
         }
     }
     while (j < len) put(rd[j]);
-    if (j & 31) R.bits[(j >> 5) * kSeedThreads] = acc;
-    if (j & 63) R.nmask[(j >> 6) * kSeedThreads] = nacc;
+    if (j & 31) R.bits[(j >> 5) * R.ts] = acc;
+    if (j & 63) R.nmask[(j >> 6) * R.ts] = nacc;
 }
 
 __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
@@ -455,7 +456,8 @@ seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int 
     if (r >= n) return;
     PackedRead R;
     R.bits = s_read + threadIdx.x;
-    R.nmask = s_read + (size_t)n_words * kSeedThreads + threadIdx.x;
+    R.nmask = s_read + (size_t)n_words * blockDim.x + threadIdx.x;
+    R.ts = (int)blockDim.x;
     qm_seed *S = seeds + r * QM_MAX_SEEDS;
     // the filter is read through L1/L2 (a copy in shared memory was measured: the 208 KB carve-out shrinks L1 to the point
     // where the chaining scratch thrashes -- 16.3 -> 23.8 ms per 4 M reads)
@@ -476,8 +478,10 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
     (void)ctx;
     // packed read: one word per 32 bases + one spare (windows may start at the last base), N flags per 64 bases + one spare
     const int n_words = (stride + 31) / 32 + 2, n_nwords = (stride + 63) / 64 + 2;
-    const size_t smem = (size_t)(n_words + n_nwords) * kSeedThreads * sizeof(uint64_t);
-    seed_chain_kernel<<<(unsigned)((n + kSeedThreads - 1) / kSeedThreads), kSeedThreads, smem, stream>>>(
+    static const int threads = getenv("QM_SEED_THREADS") ? std::max(32, std::min(kSeedThreads, atoi(getenv("QM_SEED_THREADS")) & ~31)) : 64;   // tuning knob; 64: a block
+    // lives as long as its slowest read (repeats), and smaller blocks give their slots back sooner (7.47 -> 7.13 ms per 4 M reads; 32: 7.35)
+    const size_t smem = (size_t)(n_words + n_nwords) * threads * sizeof(uint64_t);
+    seed_chain_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, stream>>>(
         V, o, codes, stride, lens, n, seeds, n_seeds, plan, n_plan, st, seeds_only, n_words, n_nwords);
     return cudaGetLastError();
 }

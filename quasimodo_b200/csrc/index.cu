@@ -161,7 +161,8 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
     }
     if ((e = cudaMalloc(&ix->d_uniq, uniq.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_uniq, uniq.data(), uniq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMalloc(&ix->d_refb, (size_t)total)) != cudaSuccess ||
+        (e = cudaMalloc(&ix->d_refb, (size_t)total + 8)) != cudaSuccess ||        // + 8: word-wise readers (pileup.cu ld4) look one word past
+        (e = cudaMemset(ix->d_refb, 0, (size_t)total + 8)) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_table, (size_t)tsize * sizeof(uint4))) != cudaSuccess ||
         (e = cudaMalloc(&ix->d_pos, pos.size() * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMemcpy(ix->d_refb, h_codes, (size_t)total, cudaMemcpyHostToDevice)) != cudaSuccess ||

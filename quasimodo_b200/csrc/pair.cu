@@ -428,6 +428,47 @@ __device__ int gen_cigar_warp(const IndexView &V, const qm_opt &o, int w_, int l
     return score;
 }
 
+// Mismatches of an ungapped alignment, four bases per step: query bases q[0 .. lq) against the reference interval that
+// starts at rb in bwa's doubled coordinates (reverse strand: the query runs backwards against the complemented forward
+// strand).  One thread walks one read, so byte loads cost a 32-byte sector per lane and base; aligned words (only words that
+// hold a needed byte are touched) cost a quarter of the requests.  n_low also counts a query N that meets a reference N.
+__device__ void count_mismatches(const IndexView &V, const uint8_t *q, int lq, int64_t rb, bool rev, int *n_mm, int *n_low)
+{
+    const uint8_t *rp = V.refb + (rev ? 2 * V.l_pac - rb - lq : rb);          // forward-strand bases, ascending
+    int i = 0, mm = 0, low = 0;
+    if (lq >= 4) {
+        const uint32_t *rw = (const uint32_t *)((uintptr_t)rp & ~(uintptr_t)3);
+        const unsigned rsh = (unsigned)((uintptr_t)rp & 3u) * 8u;
+        uint32_t rcur = __ldg(rw);
+        const uint8_t *qa = rev ? q + lq - 4 : q;                             // the first group's lowest address
+        const uint32_t *qw = (const uint32_t *)((uintptr_t)qa & ~(uintptr_t)3);
+        const unsigned qsh = (unsigned)((uintptr_t)qa & 3u) * 8u;
+        uint32_t qlo = *qw, qhi = (rev && qsh) ? qw[1] : 0;
+        for (; i + 4 <= lq; i += 4) {
+            const bool more = i + 8 <= lq;
+            uint32_t r4, q4;
+            if (rsh) { const uint32_t nx = __ldg(++rw); r4 = __funnelshift_r(rcur, nx, rsh); rcur = nx; }
+            else { r4 = rcur; if (more) rcur = __ldg(++rw); }
+            if (!rev) {
+                if (qsh) { const uint32_t nx = *++qw; q4 = __funnelshift_r(qlo, nx, qsh); qlo = nx; }
+                else { q4 = qlo; if (more) qlo = *++qw; }
+            } else {                                                          // descending addresses: this group's low word is the next one's high word
+                q4 = __byte_perm(qsh ? __funnelshift_r(qlo, qhi, qsh) : qlo, 0, 0x0123);
+                r4 ^= 0x03030303u;                                            // complement; a reference N (4) becomes 7 and matches nothing
+                qhi = qlo;
+                if (more) qlo = *--qw;
+            }
+            const uint32_t ne = __vcmpne4(q4, r4), big = __vcmpgtu4(q4, 0x03030303u);
+            mm += __popc(ne) >> 3; low += __popc(ne | big) >> 3;
+        }
+    }
+    for (; i < lq; ++i) {
+        const int qc = rev ? q[lq - 1 - i] : q[i], tc = rev ? 3 - rp[i] : rp[i];
+        mm += qc != tc; low += (qc != tc) | (qc > 3);
+    }
+    *n_mm = mm; *n_low = low;
+}
+
 // mem_reg2aln, first half: MAPQ / flags / band inference; reads on the no-DP path (equal lengths, w2 == 0) are
 // completed here, the others become CigTasks.  Returns true when a task is needed.
 __device__ bool reg_to_aln_prepare(const IndexView &V, const qm_opt &o, const PairTables &T, int l_query, const uint8_t *query,
@@ -449,10 +490,8 @@ __device__ bool reg_to_aln_prepare(const IndexView &V, const qm_opt &o, const Pa
     if (is_rev) r.flag |= 0x10;
     *wcap_out = 1 << 20;
     if (qe - qb == (int)(re - rb) && !(rb < V.l_pac && re > V.l_pac)) {
-        SeqPair S;
-        S.q = query + qb; S.lq = qe - qb; S.rlen = qe - qb; S.rb = rb; S.rev = is_rev; S.V = &V;
         int n_mm = 0, n_low = 0;                  // q != t (NM); positions scoring below a (mismatch, or N on either side)
-        for (int i = 0; i < S.lq; ++i) { const int qc = S.qb(i), tc = S.tb(i); n_mm += qc != tc; n_low += (qc != tc) | (qc > 3); }
+        count_mismatches(V, query + qb, qe - qb, rb, is_rev, &n_mm, &n_low);
         const int cap = cig_gain_cap(o, n_low);
         if (w2 == 0 || cap == 0) {
             // bwa_gen_cigar2's shortcut (w2 == 0), or no gapped path can beat the ungapped one in any band (cig_gain_cap):

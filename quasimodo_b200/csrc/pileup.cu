@@ -72,6 +72,13 @@ __device__ __forceinline__ int qidx_of(const AlnS &a, int p)
 
 __device__ __forceinline__ void red_add(int32_t *p) { atomicAdd(p, 1); }   // result unused => RED.ADD
 
+// four bytes from any address (shared or global): the two aligned words around it, funnel-shifted; reads up to 4 bytes past
+__device__ __forceinline__ uint32_t ld4(const uint8_t *p)
+{
+    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (unsigned)((uintptr_t)p & 3u) * 8u);
+}
+
 // ---- indel allele table (SURVEY.md 8a9 "indel alleles into a small hash table", 8e "gather of the sparse indel table") ----
 // Open addressing on 64-bit keys: anchor position (forward coordinate on the concatenated contigs, 32 bits) | type (1) |
 // length (8, clamped to 255) | "an N among the inserted bases" (1) | the first 11 inserted bases, 2 bits each (22).  Two int32
@@ -96,6 +103,7 @@ __device__ __forceinline__ void indel_add(const IndelView &T, unsigned long long
     atomicExch(T.overflow, 1);
 }
 
+template <int kPre>                  // words per lane of a pair's bases (and of its qualities) held ahead: 64 * kPre >= stride
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, const uint8_t *__restrict__ codes,
               const uint8_t *__restrict__ quals, int stride, const int32_t *__restrict__ lens, int64_t n_pairs,
@@ -108,8 +116,8 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
     // walked them byte by byte, one 32-byte sector per warp load and each behind the last: 0.7 TB/s of requests in flight).
     static_assert(sizeof(qm_aln) == 128, "two records = sixteen 16-byte words");
     __shared__ uint4 s_rec[kWarpsPerBlock][16];
-    __shared__ __align__(16) uint8_t s_c[kWarpsPerBlock][2 * kMaxLen];      // bases as stored (read orientation); mate e at e * moff
-    __shared__ __align__(16) uint8_t s_qr[kWarpsPerBlock][2 * kMaxLen];     // qualities likewise; the mate-overlap rewrite edits them in place
+    __shared__ __align__(16) uint8_t s_c[kWarpsPerBlock][2 * kMaxLen + 16];      // bases as stored (read orientation); mate e at e * moff
+    __shared__ __align__(16) uint8_t s_qr[kWarpsPerBlock][2 * kMaxLen + 16];     // qualities likewise; the mate-overlap rewrite edits them in place
     __shared__ AlnS s_aln[kWarpsPerBlock][2];
     const int lane = qm_lane(), wib = threadIdx.x >> 5;
     const int64_t warp0 = blockIdx.x * (int64_t)kWarpsPerBlock + wib;
@@ -119,21 +127,45 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
     const int moff = wide ? stride : kMaxLen;
     const int n_copy = stride < kMaxLen ? stride : kMaxLen;
 
+    // the NEXT pair's words are fetched into registers before this pair is processed: the loads' latency (~1 us from HBM)
+    // runs under ~900 instructions of work instead of in front of them
+    uint4 p_rec = {};
+    uint32_t p_c[kPre], p_q[kPre];
+    int p_len0 = 0, p_len1 = 0;
+    auto fetch = [&](int64_t pi) {
+        if (lane < 16) p_rec = ((const uint4 *)(alns + 2 * pi))[lane];
+        const uint32_t *gc = (const uint32_t *)(codes + 2 * pi * stride), *gq = (const uint32_t *)(quals + 2 * pi * stride);
+#pragma unroll
+        for (int j = 0; j < kPre; ++j) {
+            const int k = lane + 32 * j;
+            if (k < (stride >> 1)) { p_c[j] = gc[k]; p_q[j] = gq[k]; }
+        }
+        p_len0 = lens[2 * pi]; p_len1 = lens[2 * pi + 1];
+    };
+    if (wide && warp0 < n_pairs) fetch(warp0);
+
     for (int64_t pi = warp0; pi < n_pairs; pi += n_warps) {
         __syncwarp();
-        if (lane < 16) s_rec[wib][lane] = ((const uint4 *)(alns + 2 * pi))[lane];
+        int len0, len1;
         if (wide) {                                 // 2 * stride bytes of the pair are contiguous and 4-byte aligned
-            const uint32_t *gc = (const uint32_t *)(codes + 2 * pi * stride), *gq = (const uint32_t *)(quals + 2 * pi * stride);
+            if (lane < 16) s_rec[wib][lane] = p_rec;
             uint32_t *sc = (uint32_t *)s_c[wib], *sq = (uint32_t *)s_qr[wib];
-            for (int k = lane; k < (stride >> 1); k += 32) { sc[k] = gc[k]; sq[k] = gq[k]; }
+#pragma unroll
+            for (int j = 0; j < kPre; ++j) {
+                const int k = lane + 32 * j;
+                if (k < (stride >> 1)) { sc[k] = p_c[j]; sq[k] = p_q[j]; }
+            }
+            len0 = p_len0; len1 = p_len1;
+            if (pi + n_warps < n_pairs) fetch(pi + n_warps);
         } else {
+            if (lane < 16) s_rec[wib][lane] = ((const uint4 *)(alns + 2 * pi))[lane];
             for (int e = 0; e < 2; ++e)
                 for (int k = lane; k < n_copy; k += 32) {
                     s_c[wib][e * moff + k] = codes[(2 * pi + e) * stride + k];
                     s_qr[wib][e * moff + k] = quals[(2 * pi + e) * stride + k];
                 }
+            len0 = lens[2 * pi]; len1 = lens[2 * pi + 1];
         }
-        const int len0 = lens[2 * pi], len1 = lens[2 * pi + 1];
         __syncwarp();
         const qm_aln *g[2] = { (const qm_aln *)&s_rec[wib][0], (const qm_aln *)&s_rec[wib][8] };
         int flag[2], rid[2], tlen[2], L[2];
@@ -191,14 +223,36 @@ pileup_kernel(IndexView V, qm_pileup_opt po, const qm_aln *__restrict__ alns, co
             const AlnS &a = s_aln[wib][e];
             const int64_t base = V.off[rid[e]];
             int32_t *const mns = minus + (rev[e] ? L_pac : 0) + base;
-            for (int i = lane; i < L[e]; i += 32) {
-                const int p = rpos_of(a, i);
-                if (p < 0) continue;
+            auto count_base = [&](int i, int p) {
                 const int c = seq_base(e, i);
-                if (qual(e, i) < po.min_bq) red_add(mns + p);                       // covered, not counted
+                if (qual(e, i) < po.min_bq) red_add(mns + p);                           // covered, not counted
                 else if (c != V.refb[base + p]) {                                       // counted in its own channel
                     red_add(mns + p);
                     red_add(counts + (int64_t)((rev[e] ? 6 : 0) + c) * L_pac + base + p);
+                }
+            };
+            if (a.m1 && po.min_bq >= 0 && po.min_bq <= 255) {
+                // gap-free alignment: four bases per lane and step; a group whose bases all equal the reference and pass the
+                // threshold (most groups) costs three word loads and two SIMD compares
+                const int len = a.m1 - a.m0;
+                const uint32_t bq4 = (uint32_t)po.min_bq * 0x01010101u;
+                for (int t0 = 4 * lane; t0 < len; t0 += 128) {
+                    if (t0 + 4 <= len) {
+                        const int sidx = rev[e] ? L[e] - 4 - (a.m0 + t0) : a.m0 + t0;     // the group's first byte as stored
+                        uint32_t c4 = ld4(rd[e] + sidx), q4 = ld4(qr[e] + sidx);
+                        if (rev[e]) { c4 = __byte_perm(c4, 0, 0x0123) ^ 0x03030303u; q4 = __byte_perm(q4, 0, 0x0123); }
+                        const uint32_t r4 = ld4(V.refb + base + a.pos + t0);
+                        uint32_t att = __vcmpne4(c4, r4) | __vcmpltu4(q4, bq4);
+                        for (int k = 0; att; ++k, att >>= 8)
+                            if (att & 0xffu) count_base(a.m0 + t0 + k, a.pos + t0 + k);
+                    } else {
+                        for (int k = 0; t0 + k < len; ++k) count_base(a.m0 + t0 + k, a.pos + t0 + k);
+                    }
+                }
+            } else {
+                for (int i = lane; i < L[e]; i += 32) {
+                    const int p = rpos_of(a, i);
+                    if (p >= 0) count_base(i, p);
                 }
             }
             if (lane < a.n_cigar) {          // operation-level channels: lane k owns CIGAR operation k
@@ -436,9 +490,11 @@ int qm_pileup_accumulate_masked(qm_ctx *ctx, const qm_index *idx, const qm_pileu
     int32_t *cov = (int32_t *)p, *minus = (int32_t *)((char *)p + o_minus);
     const int sp = qm_prof_begin(ctx, QM_ST_PILEUP, st);
     QM_CUDA(ctx, cudaMemsetAsync(p, 0, o_minus + minus_bytes, st));
-    pileup_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab), d_drop, cov, minus,
-        (stride & 1) == 0 && stride <= kMaxLen && (((uintptr_t)d_codes | (uintptr_t)d_quals) & 3u) == 0);
+    const bool wide = (stride & 1) == 0 && stride <= kMaxLen && (((uintptr_t)d_codes | (uintptr_t)d_quals) & 3u) == 0;
+#define QM_PILEUP_LAUNCH(PRE) pileup_kernel<PRE><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>( \
+        idx->v, *po, d_alns, d_codes, d_quals, stride, d_lens, n_pairs, d_counts, nullptr, view_of(tab), d_drop, cov, minus, wide)
+    if (stride <= 192) QM_PILEUP_LAUNCH(3); else if (stride <= 256) QM_PILEUP_LAUNCH(4); else QM_PILEUP_LAUNCH(8);
+#undef QM_PILEUP_LAUNCH
     QM_CUDA(ctx, cudaGetLastError());
     // both strands in one scan: a strand's differences sum to zero, so the running sum is back at 0 where the next one starts
     QM_CUDA(ctx, cub::DeviceScan::InclusiveSum((char *)p + o_cub, cub_bytes, cov, cov, (int)(2 * (L + 1)), st));
