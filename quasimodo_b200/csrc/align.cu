@@ -1036,6 +1036,14 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     return QM_OK;
 }
 
+// have all pieces of the batch the host entry announced arrived?
+bool se_parts_landed(qm_ctx *ctx)
+{
+    for (int pt = 0; pt < ctx->se_n_parts; ++pt)
+        if (cudaEventQuery(ctx->se_part_ev[pt]) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return true;
+}
+
 int spec_scratch(qm_ctx *ctx, SpecScratch *X)
 {
     size_t off = 0;
@@ -1173,9 +1181,10 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
         if (opt->flags & QM_F_FM_SEEDS) {
             if (!idx->have_fm) return qm_fail(ctx, QM_EINVAL, "QM_F_FM_SEEDS needs an FM-index: qm_index_attach_bwa or qm_index_build_fm first");
             for (int pt = 0; pt < ctx->se_n_parts; ++pt) QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->se_part_ev[pt], 0));
+            if (ctx->se_pk && b0 == 0) QM_CUDA(ctx, qm_unpack_reads_launch(ctx->se_pk, ctx->se_mk, stride, ctx->se_sp, ctx->se_sm, n_reads, (uint8_t *)d_codes, st));
             QM_CUDA(ctx, launch_fm_seed(idx, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
             n_seed_launches = 1;
-        } else if (ctx->se_n_parts > 0 && b0 == 0 && n_reads <= kSeBatch) {
+        } else if (ctx->se_n_parts > 0 && b0 == 0 && n_reads <= kSeBatch && !se_parts_landed(ctx)) {
             // the batch is still arriving piece by piece (host entry): seed each piece as soon as its copy has landed.  Each piece
             // is launched on a side stream of its own: one thread per read leaves every launch a tail of slow reads (repeats),
             // and eight launches in one stream paid eight tails (+4.3 ms per 4 M reads); side by side the next piece fills it.
@@ -1187,6 +1196,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 if (r1 > r0) {
                     QM_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
                     QM_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->se_part_ev[pt], 0));
+                    if (ctx->se_pk) QM_CUDA(ctx, qm_unpack_reads_launch(ctx->se_pk + r0 * ctx->se_sp, ctx->se_mk + r0 * ctx->se_sm, stride, ctx->se_sp, ctx->se_sm,
+                                                                        r1 - r0, (uint8_t *)codes + r0 * stride, ss));
                     QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes + r0 * stride, stride, lens + r0, r1 - r0, sc.seeds + r0 * QM_MAX_SEEDS,
                                                    sc.n_seeds + r0, sc.plan + r0 * QM_MAX_SEEDS, sc.n_plan + r0, sc.st + r0, false, ss));
                     QM_CUDA(ctx, cudaEventRecord(ctx->ev_join[pt % 12], ss));
@@ -1199,10 +1210,13 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             }
             if (r0 < nb) return qm_fail(ctx, QM_EINVAL, "qm_align_se: the announced pieces cover %lld of %lld reads", (long long)r0, (long long)nb);
         } else {
+            // (a chunk whose pieces have all landed already -- every chunk of a host call but the first -- is seeded in one launch)
+            for (int pt = 0; pt < ctx->se_n_parts; ++pt) QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->se_part_ev[pt], 0));
+            if (ctx->se_pk && b0 == 0) QM_CUDA(ctx, qm_unpack_reads_launch(ctx->se_pk, ctx->se_mk, stride, ctx->se_sp, ctx->se_sm, n_reads, (uint8_t *)d_codes, st));
             QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
             n_seed_launches = 1;
         }
-        ctx->se_n_parts = 0;
+        ctx->se_n_parts = 0; ctx->se_pk = ctx->se_mk = nullptr;
         qm_prof_end(ctx, QM_ST_SEED, sp, st, n_seed_launches);
         for (int round = 0; round < 4 * QM_MAX_REGS + 8; ++round) {
             sp = qm_prof_begin(ctx, QM_ST_ADVANCE, st);
@@ -1221,14 +1235,6 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 for (int c = 0; c < kExtClasses; ++c) fprintf(stderr, " %d", h_ctr->class_count[c]);
                 fprintf(stderr, "\n");
             }
-            static const bool spec_on = !(getenv("QM_SPEC") && atoi(getenv("QM_SPEC")) == 0);       // QM_SPEC=0: the serial tail of round 1
-            static const int spec_min = getenv("QM_SPEC_MIN") ? std::min(atoi(getenv("QM_SPEC_MIN")), kSpecMinTasks) : kSpecMinTasks;   // tuning knob
-            if (spec_on && h_ctr->n_tasks < spec_min) {
-                rc = spec_finish_batch(ctx, idx, opt, P, codes, stride, lens, sc, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, d_cells, h_ctr,
-                                       h_ctr->n_tasks, st);
-                if (rc) return rc;
-                break;
-            }
             static const int tail_min = getenv("QM_TAIL_MIN") ? atoi(getenv("QM_TAIL_MIN")) : kTailMinTasks;       // tuning knob
             if (h_ctr->n_tasks < tail_min) {
                 // few reads left: finish them on the device, one warp per read, no more round trips
@@ -1245,6 +1251,16 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                                                                                sc.st, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, over, 0, n_over,
                                                                                cursor2, (unsigned long long *)d_cells, nullptr, nullptr);
                 qm_prof_end(ctx, QM_ST_EXTEND, sp, st, 2);
+                break;
+            }
+            // between the two thresholds: every remaining seed ahead of the state machine (spec_finish_batch).  Below tail_min the
+            // serial warp-per-read tail above is quicker: two launch groups of the throughput kernels cost ~1 ms whatever they hold.
+            static const bool spec_on = !(getenv("QM_SPEC") && atoi(getenv("QM_SPEC")) == 0);       // QM_SPEC=0: the serial tail of round 1
+            static const int spec_min = getenv("QM_SPEC_MIN") ? std::min(atoi(getenv("QM_SPEC_MIN")), kSpecMinTasks) : kSpecMinTasks;   // tuning knob
+            if (spec_on && h_ctr->n_tasks < spec_min) {
+                rc = spec_finish_batch(ctx, idx, opt, P, codes, stride, lens, sc, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, d_cells, h_ctr,
+                                       h_ctr->n_tasks, st);
+                if (rc) return rc;
                 break;
             }
             // The round's tasks sorted by (query length, rows, seed score): the classes become contiguous runs of one list, the

@@ -34,6 +34,10 @@ struct qm_ctx {
     int se_n_parts = 0;
     int64_t se_part_end[16] = {};
     cudaEvent_t se_part_ev[16] = {};
+    // ... and when se_pk is set the pieces arrive PACKED (2 bits per base at se_pk, N flags at se_mk, row strides se_sp / se_sm):
+    // qm_align_se expands reads [r0, r1) into the batch's code rows on the stream that is about to read them
+    const uint8_t *se_pk = nullptr, *se_mk = nullptr;
+    int se_sp = 0, se_sm = 0;
     int64_t text_bytes = 0;            // length of the text the last qm_mpileup_text left in scratch 17
     void *h_pinned = nullptr;          // 8 KB of page-locked host memory for the small per-round read-backs
     bool prof_on = false;

@@ -8,6 +8,8 @@
 //     "POS\t.\tREF\tALT" patterns against the caller's SNP lines -- by a sorted-key membership test:
 //     key = pos << 8 | ref << 4 | alt (CHROM is not compared, exactly like the script; B.5).
 #include <math.h>
+#include <iterator>
+#include <cub/device/device_scan.cuh>
 #include "pipeline.cuh"
 
 namespace {
@@ -60,36 +62,16 @@ __global__ void call_kernel(IndexView V, qm_call_opt o, const int32_t *__restric
     if (!PASS) n_at[p] = n;
 }
 
-// single-block exclusive scan of n ints into int64 offsets; total to offs[n]
-__global__ void scan_kernel(const int *__restrict__ in, int64_t n, int64_t *__restrict__ offs)
-{
-    __shared__ int64_t warp_sum[32];
-    __shared__ int64_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += blockDim.x) {
-        const int64_t i = base + threadIdx.x;
-        int64_t v = i < n ? in[i] : 0, x = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-        if (lane == 31) warp_sum[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int64_t s = lane < (int)(blockDim.x >> 5) ? warp_sum[lane] : 0, t = s;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
-            warp_sum[lane] = t - s;         // exclusive prefix of the warp sums
-        }
-        __syncthreads();
-        const int64_t excl = carry + warp_sum[w] + x - v;
-        if (i < n) offs[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) offs[n] = carry;
-}
+// widening iterator for the device-wide scan below: int counts read as int64
+struct WidenInt {
+    const int *p;
+    using value_type = int64_t; using difference_type = int64_t; using pointer = const int64_t *; using reference = int64_t;
+    using iterator_category = std::random_access_iterator_tag;
+    __host__ __device__ int64_t operator[](int64_t i) const { return i < n ? (int64_t)p[i] : 0; }
+    __host__ __device__ int64_t operator*() const { return (*this)[0]; }
+    __host__ __device__ WidenInt operator+(int64_t k) const { WidenInt r = *this; r.p += k; r.n -= k; return r; }
+    int64_t n;
+};
 
 // ---- matcher ----
 __global__ void pad_copy_kernel(const uint64_t *__restrict__ in, int64_t n, int64_t n_pad, uint64_t *__restrict__ out)
@@ -170,14 +152,20 @@ int qm_call_snps(qm_ctx *ctx, const qm_index *idx, const qm_call_opt *copt, cons
     const int64_t L = idx->v.l_pac;
     void *p = nullptr;
     const size_t n_bytes = ((size_t)L * 4 + 255) & ~(size_t)255;
-    int rc = qm_scratch_reserve(ctx, 7, n_bytes + (size_t)(L + 1) * 8, &p);
+    // exclusive scan of the per-column call counts over L + 1 items (the last input reads as 0): offs[L] = the total.
+    // Device-wide (one block took 4 ms on the 4.9 Mb index of config 3).
+    size_t cub_bytes = 0;
+    WidenInt in_probe = {nullptr, 0};
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, in_probe, (int64_t *)nullptr, (int)(L + 1), st);
+    const size_t o_cub = (n_bytes + (size_t)(L + 1) * 8 + 255) & ~(size_t)255;
+    int rc = qm_scratch_reserve(ctx, 7, o_cub + cub_bytes, &p);
     if (rc) return rc;
     int *n_at = (int *)p;
     int64_t *offs = (int64_t *)((char *)p + n_bytes);
     const unsigned grid = (unsigned)((L + 127) / 128);
     const int sp = qm_prof_begin(ctx, QM_ST_OTHER, st);
     call_kernel<0><<<grid, 128, 0, st>>>(idx->v, *copt, d_counts, n_at, nullptr, nullptr, 0);
-    scan_kernel<<<1, 1024, 0, st>>>(n_at, L, offs);
+    { WidenInt in = {n_at, L}; QM_CUDA(ctx, cub::DeviceScan::ExclusiveSum((char *)p + o_cub, cub_bytes, in, offs, (int)(L + 1), st)); }
     call_kernel<1><<<grid, 128, 0, st>>>(idx->v, *copt, d_counts, nullptr, offs, d_calls, max_calls);
     qm_prof_end(ctx, QM_ST_OTHER, sp, st, 3);
     QM_CUDA(ctx, cudaGetLastError());

@@ -184,3 +184,7 @@ struct qm_indel_table;
 extern "C" int qm_pileup_accumulate_masked(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
                                 const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
                                 int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, const uint8_t *d_drop, void *stream);
+
+// sample.cu: packed reads (2 bits per base + N flags) -> one code byte per base, rows [0, n_reads)
+cudaError_t qm_unpack_reads_launch(const uint8_t *d_bases2, const uint8_t *d_nmask, int stride, int stride_p, int stride_m, int64_t n_reads,
+                                   uint8_t *d_codes, cudaStream_t st);

@@ -70,6 +70,19 @@ unpack_reads_kernel(const uint8_t *__restrict__ bases2, const uint8_t *__restric
     else for (int k = 0; k < 4 && 4 * g + k < stride; ++k) o[k] = c[k];
 }
 
+}  // namespace
+
+cudaError_t qm_unpack_reads_launch(const uint8_t *d_bases2, const uint8_t *d_nmask, int stride, int stride_p, int stride_m, int64_t n_reads,
+                                   uint8_t *d_codes, cudaStream_t st)
+{
+    if (n_reads <= 0) return cudaSuccess;
+    const int64_t work = n_reads * ((stride + 3) >> 2);
+    unpack_reads_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(d_bases2, d_nmask, stride, stride_p, stride_m, n_reads, d_codes);
+    return cudaGetLastError();
+}
+
+namespace {
+
 // quals_ready (may be NULL): event after which d_quals is valid; only the pileup reads the qualities, so their copy
 // may still be in flight while the reads are being aligned
 int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
@@ -443,10 +456,11 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
     const int64_t n_chunks = (int64_t)starts.size();
     // QM_HOST_TRACE=1 (diagnostics): when each copy piece and the chunk's compute finished, relative to the call's start
     static const bool trace = getenv("QM_HOST_TRACE") != nullptr;
-    cudaEvent_t tr0 = nullptr, tr_part[kCopyParts] = {}, tr_quals = nullptr, tr_done = nullptr;
+    cudaEvent_t tr0 = nullptr, tr_part[kCopyParts] = {}, tr_quals = nullptr, tr_done = nullptr, tr_chunk[16] = {}, tr_copy[16] = {};
     if (trace) {
         cudaEventCreate(&tr0); cudaEventCreate(&tr_quals); cudaEventCreate(&tr_done);
         for (int i = 0; i < kCopyParts; ++i) cudaEventCreate(&tr_part[i]);
+        for (int i = 0; i < 16; ++i) { cudaEventCreate(&tr_chunk[i]); cudaEventCreate(&tr_copy[i]); }
         cudaEventRecord(tr0, ctx->copy_stream);
     }
     auto enqueue_copy = [&](int64_t c) -> cudaError_t {
@@ -461,19 +475,20 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
             const int64_t r0 = 2 * n * pt / kCopyParts, r1 = 2 * n * (pt + 1) / kCopyParts;
             if (r1 > r0 && !packed && (e = cudaMemcpyAsync(s->d_stage[b] + r0 * stride, h_codes + (2 * p0 + r0) * stride, (size_t)(r1 - r0) * stride,
                                                            cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
-            if (r1 > r0 && packed) {                   // the packed piece, then its expansion to one byte per base, both on the copy stream
+            if (r1 > r0 && packed) {
+                // the packed piece.  Its expansion to one byte per base runs on the stream that seeds the piece (qm_align_se through
+                // qm_ctx::se_pk), NOT here: a kernel in the copy stream waits for SM slots behind the extension kernels of the
+                // chunk in flight, and every copy queued behind it waits with it (+6 ms per chunk of a multi-chunk call)
                 uint8_t *d_pk = s->d_stage[b] + o_pk + r0 * stride_p, *d_mk = s->d_stage[b] + o_mk + r0 * stride_m;
                 if ((e = cudaMemcpyAsync(d_pk, h_bases2 + (2 * p0 + r0) * stride_p, (size_t)(r1 - r0) * stride_p, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
                 if ((e = cudaMemcpyAsync(d_mk, h_nmask + (2 * p0 + r0) * stride_m, (size_t)(r1 - r0) * stride_m, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
-                const int64_t work = (r1 - r0) * ((stride + 3) >> 2);
-                unpack_reads_kernel<<<(unsigned)((work + 255) / 256), 256, 0, cs>>>(d_pk, d_mk, stride, stride_p, stride_m, r1 - r0, s->d_stage[b] + r0 * stride);
-                if ((e = cudaGetLastError()) != cudaSuccess) return e;
             }
             if ((e = cudaEventRecord(s->ev_part[b][pt], cs)) != cudaSuccess) return e;
             if (trace && c == 0) cudaEventRecord(tr_part[pt], cs);
         }
         if ((e = cudaMemcpyAsync(s->d_stage[b] + seq_al, h_quals + 2 * p0 * stride, (size_t)2 * n * stride, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
         if (trace && c == 0) cudaEventRecord(tr_quals, cs);
+        if (trace && c < 16) cudaEventRecord(tr_copy[c], cs);
         return cudaEventRecord(s->ev_quals[b], cs);
     };
     // a fresh event counts as completed, so the first two waits on ev_consumed pass immediately
@@ -486,14 +501,16 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         if (c + 1 < n_chunks) QM_CUDA(ctx, enqueue_copy(c + 1));
         QM_CUDA(ctx, cudaStreamWaitEvent(ks, s->ev_copied[b], 0));
         ctx->se_n_parts = kCopyParts;
+        if (packed) { ctx->se_pk = s->d_stage[b] + o_pk; ctx->se_mk = s->d_stage[b] + o_mk; ctx->se_sp = stride_p; ctx->se_sm = stride_m; }
         for (int pt = 0; pt < kCopyParts; ++pt) { ctx->se_part_end[pt] = 2 * n * (pt + 1) / kCopyParts; ctx->se_part_ev[pt] = s->ev_part[b][pt]; }
         int rc = sample_chunk(s, s->d_stage[b], s->d_stage[b] + seq_al, stride, (const int32_t *)(s->d_stage[b] + 2 * seq_al), n,
                               pair_id0 + p0, nullptr, ks, s->ev_quals[b]);
-        ctx->se_n_parts = 0;
+        ctx->se_n_parts = 0; ctx->se_pk = ctx->se_mk = nullptr;
         if (rc) return rc;
         if (h_alns) QM_CUDA(ctx, cudaMemcpyAsync(h_alns + 2 * p0, s->d_alns, (size_t)2 * n * sizeof(qm_aln), cudaMemcpyDeviceToHost, ks));
         QM_CUDA(ctx, cudaEventRecord(s->ev_consumed[b], ks));
         if (trace && c == 0) cudaEventRecord(tr_done, ks);
+        if (trace && c < 16) cudaEventRecord(tr_chunk[c], ks);
     }
     QM_CUDA(ctx, cudaStreamSynchronize(ks));
     if (trace) {
@@ -501,7 +518,17 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         fprintf(stderr, "[qm host trace] pairs %lld pieces", (long long)sizes[0]);
         for (int i = 0; i < kCopyParts; ++i) { cudaEventElapsedTime(&ms, tr0, tr_part[i]); fprintf(stderr, " %.2f", ms); cudaEventDestroy(tr_part[i]); }
         cudaEventElapsedTime(&ms, tr0, tr_quals); fprintf(stderr, " quals %.2f", ms);
-        cudaEventElapsedTime(&ms, tr0, tr_done); fprintf(stderr, " chunk done %.2f ms\n", ms);
+        cudaEventElapsedTime(&ms, tr0, tr_done); fprintf(stderr, " chunk done %.2f ms", ms);
+        if (n_chunks > 1) {
+            fprintf(stderr, "; chunks (copied / done):");
+            for (int64_t c = 0; c < n_chunks && c < 16; ++c) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, tr0, tr_copy[c]); cudaEventElapsedTime(&b, tr0, tr_chunk[c]);
+                fprintf(stderr, " %.1f/%.1f", a, b);
+            }
+        }
+        fprintf(stderr, "\n");
+        for (int i = 0; i < 16; ++i) { cudaEventDestroy(tr_chunk[i]); cudaEventDestroy(tr_copy[i]); }
         cudaEventDestroy(tr0); cudaEventDestroy(tr_quals); cudaEventDestroy(tr_done);
     }
     return QM_OK;

@@ -249,15 +249,17 @@ def test_mate_rescue_inline_path_is_bit_exact():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"QM_SPEC_DEPTH": "2"}, {"QM_SPEC": "0"}], ids=["two-seeds-ahead-per-pass", "serial-tail"])
+@pytest.mark.parametrize("env", [{"QM_TAIL_MIN": "0"}, {"QM_TAIL_MIN": "0", "QM_SPEC_DEPTH": "2"}, {"QM_SPEC": "0"}],
+                         ids=["all-seeds-ahead", "two-seeds-ahead-per-pass", "serial-tail"])
 def test_speculative_finish_variants_are_bit_exact(env):
     """the last reads of a batch run every remaining seed's extensions ahead of the state machine (align.cu spec_* kernels);
-    QM_SPEC_DEPTH=2 enters only two seeds per pass (reads run past their directory and open further passes), QM_SPEC=0 is the
-    serial warp-per-read tail.  All three give the oracle's regions and cell counts."""
+    a batch as small as a test's goes to the serial warp-per-read tail by default, so QM_TAIL_MIN=0 sends it down the speculative
+    path instead; QM_SPEC_DEPTH=2 enters only two seeds per pass (reads run past their directory and open further passes);
+    QM_SPEC=0 never speculates.  All give the oracle's regions and cell counts."""
     import os
     import subprocess
     import sys
-    if os.environ.get("QM_SPEC_DEPTH") or os.environ.get("QM_SPEC"):
+    if os.environ.get("QM_SPEC_DEPTH") or os.environ.get("QM_SPEC") or os.environ.get("QM_TAIL_MIN"):
         pytest.skip("already inside a QM_SPEC run")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_pipeline_gpu.py", "-q", "-x", "-k", "cfg1-3000 or cfg5-2000 or rescue-heavy or long_reads"],
