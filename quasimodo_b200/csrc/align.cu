@@ -53,6 +53,7 @@ __device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
 //  * a k-mer whose canonical form misses the Bloom filter occurs on neither strand.
 // The read is packed once into shared memory (2 bits per base + an N bitmap); k-mers are cut out of the packed words,
 // so no rolling state ties one position to the next and whole runs can be skipped.
+constexpr int kBloomBatch = 8;             // filter look-ups in flight per thread behind a mismatch (collect_seeds)
 constexpr int kSeedThreads = 128;          // most a block may have (launch bounds); launched with kSeedThreadsDefault
 
 struct PackedRead {                 // per-thread view of the block's shared arrays, [word][thread]
@@ -131,7 +132,8 @@ __device__ void pack_read(const uint8_t *__restrict__ rd, int len, int n_words, 
 }
 
 __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
-                             const uint32_t *__restrict__ bloom /* V.bloom, or NULL */, PackedRead &R, int n_words, int n_nwords)
+                             const uint32_t *__restrict__ bloom /* V.bloom, or NULL */, PackedRead &R, int n_words, int n_nwords,
+                             int bloom_batch = kBloomBatch)
 {
     const int k = V.k;
     const uint32_t occ_cap = (uint32_t)(o.max_occ < QM_OCC_CAP ? o.max_occ : QM_OCC_CAP);
@@ -275,18 +277,48 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
             q += 64 - __clzll((long long)nm);
             continue;
         }
+        if (bloom) {
+            // A k-mer whose canonical form misses the filter occurs on neither strand: no table probe (the common case for
+            // the k - 1 k-mers that cover a mismatch).  The filter words of kBloomBatch consecutive positions are fetched
+            // TOGETHER: behind a mismatch ~k positions in a row miss, and probing them one by one is a chain of ~k dependent
+            // L2 round trips per mismatch -- the bulk of this kernel's time -- where the batch pays one round trip per
+            // kBloomBatch positions.  Only positions whose k-mer holds no N are in a batch (nm == 0 covers the first).
+            int gmax = q_last - q + 1 < bloom_batch ? q_last - q + 1 : bloom_batch;
+            {
+                const uint64_t nn = R.getn(q) >> k;                    // N flags of the bases behind the first k-mer
+                const int free_n = nn ? __ffsll((long long)nn) : 64;   // positions q .. q+free_n-1 have an N-free k-mer
+                gmax = gmax < free_n ? gmax : free_n;
+            }
+            uint32_t bw[kBloomBatch][3], bs[kBloomBatch][3];
+#pragma unroll
+            for (int g = 0; g < kBloomBatch; ++g) {
+                if (g < gmax) {
+                    const uint64_t vg = R.get2(q + g) & mask;
+                    const uint64_t fg = grouprev(vg) >> (64 - 2 * k), rg = ~vg & mask;
+                    uint32_t bp[3];
+                    qm_bloom_pos(fg < rg ? fg : rg, V.bloom_bits, bp);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) { bw[g][t] = __ldg(&bloom[bp[t] >> 5]); bs[g][t] = bp[t] & 31; }
+                }
+            }
+            unsigned hitmask = 0;
+#pragma unroll
+            for (int g = 0; g < kBloomBatch; ++g)
+                if (g < gmax) hitmask |= ((bw[g][0] >> bs[g][0]) & (bw[g][1] >> bs[g][1]) & (bw[g][2] >> bs[g][2]) & 1u) << g;
+            const int lead = hitmask ? __ffs((int)hitmask) - 1 : gmax;             // positions in a row that miss
+            if (lead > 0) {
+                trk_p = -1; trk_p2 = -1; nt = 0;
+                q += lead;
+                if (lead == gmax) continue;
+            }
+            // position q passed the filter (and its k-mer holds no N)
+        }
         const uint64_t v = R.get2(q) & mask;            // first base in the lowest bits
         const uint64_t fw = grouprev(v) >> (64 - 2 * k);  // first base in the highest bits: the table's key order
         const uint64_t rc = ~v & mask;                  // reverse complement in the same order
-        if (bloom) {
-            // a k-mer whose canonical form misses the filter occurs on neither strand: no table probe (the common case
-            // for the k - 1 k-mers that cover a mismatch)
-            uint32_t bp[3];
-            qm_bloom_pos(fw < rc ? fw : rc, V.bloom_bits, bp);
-            const uint32_t hit = (__ldg(&bloom[bp[0] >> 5]) >> (bp[0] & 31)) & (__ldg(&bloom[bp[1] >> 5]) >> (bp[1] & 31)) &
-                                 (__ldg(&bloom[bp[2] >> 5]) >> (bp[2] & 31)) & 1u;
-            if (!hit) { trk_p = -1; trk_p2 = -1; nt = 0; ++q; continue; }
-        }
+        // the first table slot of both strands, fetched together (two dependent L2 round trips become one)
+        const uint64_t slot0[2] = {(fw * 0x9E3779B97F4A7C15ull) >> V.shift, (rc * 0x9E3779B97F4A7C15ull) >> V.shift};
+        const uint4 ent0[2] = {__ldg(&V.table[slot0[0]]), __ldg(&V.table[slot0[1]])};
         int n_hits = 0, one_pass = 0, n_pass[2] = {0, 0};
         int64_t one_p = -1, p_of[2] = {-1, -1};
         bool ignored = false;
@@ -294,7 +326,7 @@ __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t 
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             uint32_t first, cnt;
-            if (!qm_idx_lookup(V, pass ? rc : fw, first, cnt)) continue;
+            if (!qm_idx_lookup_from(V, pass ? rc : fw, pass ? slot0[1] : slot0[0], pass ? ent0[1] : ent0[0], first, cnt)) continue;
             if (cnt > occ_cap) { n_hits += 2; ignored = true; continue; }          // ignored k-mer: nothing of this position is tracked
             for (uint32_t t = 0; t < cnt; ++t) {
                 const int64_t p = V.pos[first + t];
@@ -446,13 +478,50 @@ __device__ int build_plan(const IndexView &V, const qm_opt &o, const qm_seed *S,
     return np;
 }
 
+// The block's reads are consecutive rows of the batch: one contiguous span of blockDim.x * stride bytes.  One thread asks the
+// copy engine for the whole span (cp.async.bulk: a single bulk-copy instruction, completion counted in bytes on an mbarrier)
+// and every thread then packs its own read out of shared memory -- instead of 32 lanes walking 32 rows with 4-byte loads,
+// ~40 dependent-latency trips through L1 per read.  The span is widened to 16-byte boundaries as the instruction demands;
+// the few extra bytes lie inside the same 256-byte allocation granule.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ const uint8_t *stage_block_reads(const uint8_t *__restrict__ codes, int stride, int64_t first, int n_rows,
+                                                            uint8_t *stage, uint64_t *bar)
+{
+    const uint8_t *src = codes + first * stride;
+    const unsigned head = (unsigned)((uintptr_t)src & 15u);
+    const unsigned bytes = (head + (unsigned)n_rows * (unsigned)stride + 15u) & ~15u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_addr(stage)), "l"(src - head), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+    }
+    __syncthreads();                                    // the barrier is initialised and armed for everybody
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_addr(bar)) : "memory");
+    return stage + head;
+}
+
 __global__ void __launch_bounds__(kSeedThreads)
 seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens,
                   int64_t n, qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds, uint16_t *__restrict__ plan,
-                  uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only, int n_words, int n_nwords)
+                  uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only, int n_words, int n_nwords, bool staged,
+                  int bloom_batch)
 {
-    extern __shared__ uint64_t s_read[];            // [n_words][threads] packed bases, then [n_nwords][threads] N flags
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) uint64_t s_read[];   // [n_words][threads] packed bases, [n_nwords][threads] N flags, then the staged rows
+    __shared__ uint64_t s_bar;
+    const int64_t r0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t r = r0 + threadIdx.x;
+    const uint8_t *rd = codes + r * stride;
+    if (staged) {
+        const int n_rows = n - r0 < (int64_t)blockDim.x ? (int)(n - r0) : (int)blockDim.x;
+        rd = stage_block_reads(codes, stride, r0, n_rows, (uint8_t *)(s_read + (size_t)(n_words + n_nwords) * blockDim.x), &s_bar) +
+             (size_t)threadIdx.x * stride;
+    }
     if (r >= n) return;
     PackedRead R;
     R.bits = s_read + threadIdx.x;
@@ -461,7 +530,7 @@ seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int 
     qm_seed *S = seeds + r * QM_MAX_SEEDS;
     // the filter is read through L1/L2 (a copy in shared memory was measured: the 208 KB carve-out shrinks L1 to the point
     // where the chaining scratch thrashes -- 16.3 -> 23.8 ms per 4 M reads)
-    const int ns = collect_seeds(V, o, codes + r * stride, lens[r], S, V.bloom_bits ? V.bloom : nullptr, R, n_words, n_nwords);
+    const int ns = collect_seeds(V, o, rd, lens[r], S, V.bloom_bits ? V.bloom : nullptr, R, n_words, n_nwords, bloom_batch);
     n_seeds[r] = ns;
     if (seeds_only) return;
     const int np = build_plan(V, o, S, ns, plan + r * QM_MAX_SEEDS);
@@ -480,9 +549,16 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
     const int n_words = (stride + 31) / 32 + 2, n_nwords = (stride + 63) / 64 + 2;
     static const int threads = getenv("QM_SEED_THREADS") ? std::max(32, std::min(kSeedThreads, atoi(getenv("QM_SEED_THREADS")) & ~31)) : 64;   // tuning knob; 64: a block
     // lives as long as its slowest read (repeats), and smaller blocks give their slots back sooner (7.47 -> 7.13 ms per 4 M reads; 32: 7.35)
-    const size_t smem = (size_t)(n_words + n_nwords) * threads * sizeof(uint64_t);
+    size_t smem = (size_t)(n_words + n_nwords) * threads * sizeof(uint64_t);
+    // the block's rows staged by one bulk copy (QM_SEED_STAGE=0: per-thread loads, for A/B measurements); very long rows stay
+    // with the per-thread loads (the default 48 KB of dynamic shared memory)
+    static const bool want_stage = !(getenv("QM_SEED_STAGE") && atoi(getenv("QM_SEED_STAGE")) == 0);
+    const size_t stage_bytes = (size_t)threads * stride + 32;
+    const bool staged = want_stage && smem + stage_bytes <= 40 * 1024;
+    if (staged) smem += stage_bytes;
+    static const int bloom_batch = getenv("QM_BLOOM_BATCH") ? std::max(1, std::min(kBloomBatch, atoi(getenv("QM_BLOOM_BATCH")))) : kBloomBatch;   // tuning knob
     seed_chain_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, stream>>>(
-        V, o, codes, stride, lens, n, seeds, n_seeds, plan, n_plan, st, seeds_only, n_words, n_nwords);
+        V, o, codes, stride, lens, n, seeds, n_seeds, plan, n_plan, st, seeds_only, n_words, n_nwords, staged, bloom_batch);
     return cudaGetLastError();
 }
 

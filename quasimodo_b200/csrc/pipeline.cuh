@@ -72,6 +72,18 @@ static __device__ __forceinline__ bool qm_idx_lookup(const IndexView &V, uint64_
     }
 }
 
+// the same look-up when the caller has fetched the key's first slot already (slot h, entry e)
+static __device__ __forceinline__ bool qm_idx_lookup_from(const IndexView &V, uint64_t key, uint64_t h, uint4 e, uint32_t &first, uint32_t &cnt)
+{
+    for (;;) {
+        const uint64_t kk = (uint64_t)e.x | ((uint64_t)e.y << 32);
+        if (kk == key) { first = e.z; cnt = e.w; return true; }
+        if (kk == ~0ull) return false;
+        h = (h + 1) & V.mask;
+        e = __ldg(&V.table[h]);
+    }
+}
+
 // orientation class (FF FR RF RR) and distance of two hits in doubled coordinates (bwamem_pair.c mem_infer_dir)
 static __device__ __forceinline__ int qm_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist)
 {
