@@ -221,6 +221,19 @@ int  qm_indel_table_merge(qm_indel_table *t, const qm_indel *d_records, int64_t 
 int  qm_pileup_accumulate_indels(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns,
                                  const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
                                  int64_t n_pairs, int32_t *d_counts, qm_indel_table *tab, void *stream);
+/* ---- base alignment quality (htslib 1.9 realn.c sam_prob_realn over probaln.c kpa_glocal) ----
+ * Both mpileups of the reference flow run WITHOUT -B (rules/vcfcall.smk:39 and :115), i.e. with BAQ on: every read is re-aligned
+ * to its reference window by a banded profile HMM in double precision and each aligned base's quality is capped by the phred-scaled
+ * posterior of its placement (flag 3: "extended" BAQ, the running-maximum form both tools pass; flag 1: plain BAQ).
+ * d_quals_out (same layout as d_quals, may not alias it) receives the capped qualities of every read the pileup admits under
+ * `po`; other reads keep theirs.  The pileup entries then take d_quals_out in place of d_quals.  Off by default everywhere:
+ * the north-star parity configuration is `-B`.  Bit-exact against oracle/qmo_baq.c (tests/test_baq_gpu.py). */
+int qm_baq_apply(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *d_alns, const uint8_t *d_codes,
+                 const uint8_t *d_quals, int32_t stride, const int32_t *d_lens, int64_t n_reads, int32_t flag, uint8_t *d_quals_out,
+                 void *stream);
+int qm_baq_apply_host(qm_ctx *ctx, const qm_index *idx, const qm_pileup_opt *po, const qm_aln *h_alns, const uint8_t *h_codes,
+                      const uint8_t *h_quals, int32_t stride, const int32_t *h_lens, int64_t n_reads, int32_t flag, uint8_t *h_quals_out);
+
 /* planes [QM_NCH][l_pac] -> rows [l_pac][QM_NCH] (row order of the count TSV) */
 int qm_counts_to_rows(qm_ctx *ctx, const qm_index *idx, const int32_t *d_planes, int32_t *d_rows, void *stream);
 
@@ -360,6 +373,10 @@ int qm_depth_cap(qm_ctx *ctx, const qm_pileup_opt *po, int n_chunks, const qm_al
                  uint8_t *const *d_drop, int64_t *h_n_dropped, void *stream);
 int qm_sample_set_max_depth(qm_sample *s, int max_depth);
 int qm_sample_finish(qm_sample *s, int64_t *n_dup_pairs, int64_t *n_capped_reads, void *stream);
+/* base alignment quality for the sample's pileup (qm_baq_apply above): 0 = off (default, `-B`), 3 = extended BAQ as both mpileups of
+ * the reference flow run it, 1 = plain BAQ; before the first pairs.  Works with the immediate and the deferred (rmdup / depth cap)
+ * counting; duplicate marking keeps the reads' own qualities. */
+int qm_sample_set_baq(qm_sample *s, int flag);
 
 /* ---- text pileup (replaces `samtools mpileup -f ref bam`, rules/vcfcall.smk:39; consumer: the VarScan rule) ----
  * One line per column covered by an admitted read: chrom, 1-based position, reference base, number of entries with base

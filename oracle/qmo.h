@@ -160,6 +160,17 @@ int64_t qmo_mpileup_text(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t
                          const char *const *names, char **out);
 void qmo_free(void *p);
 
+/* ---- base alignment quality (htslib 1.9 realn.c sam_prob_realn / probaln.c kpa_glocal, what both mpileups run unless -B is
+ * given: rules/vcfcall.smk:39,115 give no -B).  PARITY UNPINNED (no htslib here): qmo_baq.c. ----
+ * quals_out = quals (reads as sequenced) with every admitted read's base qualities capped by its BAQ; flag 3 = extended BAQ
+ * (what the mpileups pass), 1 = plain. */
+void qmo_baq(const qmo_ref_t *R, const qmo_pileup_opt_t *po, int64_t n_reads, const qmo_aln_t *alns, const uint8_t *reads,
+             const uint8_t *quals, int stride, const int32_t *lens, int flag, uint8_t *quals_out);
+/* the HMM alone: ref / query base codes (0..3, above = ambiguous), iqual phred values; state[i] = reference offset << 2 | (0 M, 1 I),
+ * q[i] = phred of the posterior of that state; returns the phred-scaled likelihood */
+int qmo_kpa_glocal(const uint8_t *ref, int l_ref, const uint8_t *query, int l_query, const uint8_t *iqual,
+                   double d, double e, int bw, int *state, uint8_t *q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,6 +335,38 @@ def mpileup_text(ref, alns, reads, quals, lens, names, popt=None):
     return text
 
 
+def baq(ref, alns, reads, quals, lens, popt=None, flag=3):
+    """-> quals with every admitted read's base qualities capped by its base alignment quality (htslib sam_prob_realn, flag 3 =
+    extended BAQ as both mpileups run it)"""
+    L = lib()
+    L.qmo_baq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.qmo_baq.restype = None
+    if popt is None:
+        popt = PileupOpt()
+        L.qmo_pileup_opt_default(C.byref(popt))
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    quals = np.ascontiguousarray(quals, dtype=np.uint8)
+    n, stride = reads.shape
+    lens = np.ascontiguousarray(lens, dtype=np.int32)
+    alns = np.ascontiguousarray(alns, dtype=ALN_DTYPE)
+    out = np.empty_like(quals)
+    L.qmo_baq(ref._h, C.byref(popt), n, alns.ctypes.data, reads.ctypes.data, quals.ctypes.data, stride, lens.ctypes.data, int(flag),
+              out.ctypes.data)
+    return out
+
+
+def kpa_glocal(ref_codes, query_codes, quals, d=0.001, e=0.1, bw=7):
+    """the banded profile HMM of BAQ -> (state[int32], q[uint8], phred likelihood)"""
+    L = lib()
+    L.qmo_kpa_glocal.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.qmo_kpa_glocal.restype = C.c_int
+    r = np.ascontiguousarray(ref_codes, dtype=np.uint8); qy = np.ascontiguousarray(query_codes, dtype=np.uint8)
+    ql = np.ascontiguousarray(quals, dtype=np.uint8)
+    state = np.zeros(len(qy), np.int32); q = np.zeros(len(qy), np.uint8)
+    pr = L.qmo_kpa_glocal(r.ctypes.data, len(r), qy.ctypes.data, len(qy), ql.ctypes.data, d, e, bw, state.ctypes.data, q.ctypes.data)
+    return state, q, pr
+
+
 PESTAT_PAIRS = 65536
 
 

@@ -124,6 +124,9 @@ SIGNATURES = {
     "qm_depth_cap": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.POINTER(C.c_int64), _P]),
     "qm_sample_set_max_depth": (C.c_int, [_P, C.c_int]),
     "qm_sample_finish": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
+    "qm_sample_set_baq": (C.c_int, [_P, C.c_int]),
+    "qm_baq_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P, _P]),
+    "qm_baq_apply_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P]),
     "qm_mpileup_text": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
     "qm_mpileup_text_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _P, _P]),
     "qm_mpileup_text_fetch": (C.c_int, [_P, _P, _L]),

@@ -181,6 +181,10 @@ class Sample:
         """bcftools mpileup -d: htslib's depth cap (0 = off); counting is deferred to finish()"""
         _check(self.ctx._h, _lib.lib().qm_sample_set_max_depth(self._h, int(max_depth)), "qm_sample_set_max_depth")
 
+    def set_baq(self, flag=3):
+        """base alignment quality for the pileup: 0 off (-B, default), 3 extended BAQ (what both mpileups run), 1 plain"""
+        _check(self.ctx._h, _lib.lib().qm_sample_set_baq(self._h, int(flag)), "qm_sample_set_baq")
+
     def finish(self, stream=0):
         """deferred counting (rmdup and / or depth cap) -> (duplicate pairs, reads the cap dropped)"""
         nd, nc = C.c_int64(), C.c_int64()
@@ -377,6 +381,29 @@ class Context:
                                              stride, _ptr(d_lens), n // 2, _ptr(d_counts), C.c_void_p(stream))
         _check(self._h, rc, "qm_pileup_accumulate")
         return d_counts
+
+    def baq_apply(self, idx, d_alns, d_codes, d_quals, d_lens, flag=3, stream=0, popt=None):
+        """-> device tensor like d_quals: the qualities capped by base alignment quality (htslib sam_prob_realn)"""
+        import torch
+        popt = popt or self.pileup_opt
+        n, stride = d_codes.shape
+        out = torch.empty_like(d_quals)
+        rc = _lib.lib().qm_baq_apply(self._h, idx._h, C.byref(popt), _ptr(d_alns), _ptr(d_codes), _ptr(d_quals), stride, _ptr(d_lens), n,
+                                     int(flag), _ptr(out), C.c_void_p(stream))
+        _check(self._h, rc, "qm_baq_apply")
+        return out
+
+    def baq_apply_host(self, idx, alns, codes, quals, lens, flag=3, popt=None):
+        """host arrays in, host array out (numpy)"""
+        popt = popt or self.pileup_opt
+        codes = np.ascontiguousarray(codes, dtype=np.uint8); quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.int32); alns = np.ascontiguousarray(alns, dtype=_lib.ALN_DTYPE)
+        n, stride = codes.shape
+        out = np.empty_like(quals)
+        rc = _lib.lib().qm_baq_apply_host(self._h, idx._h, C.byref(popt), alns.ctypes.data, codes.ctypes.data, quals.ctypes.data, stride,
+                                          lens.ctypes.data, n, int(flag), out.ctypes.data)
+        _check(self._h, rc, "qm_baq_apply_host")
+        return out
 
     def mpileup_text(self, idx, d_alns, d_codes, d_quals, d_lens, names, stream=0, popt=None):
         """samtools-mpileup text of the device-resident records -> bytes (copied to the host)"""

@@ -131,226 +131,285 @@ __device__ void pack_read(const uint8_t *__restrict__ rd, int len, int n_words, 
     if (j & 63) R.nmask[(j >> 6) * R.ts] = nacc;
 }
 
-__device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
-                             const uint32_t *__restrict__ bloom /* V.bloom, or NULL */, PackedRead &R, int n_words, int n_nwords,
-                             int bloom_batch = kBloomBatch)
+// The walk over one read's k-mer positions as a resumable state: seed_walk_step is one trip of the loop, so that a lane of the
+// persistent kernel can take its next read the moment this one is finished instead of idling until the warp's slowest read ends.
+struct SeedWalk {
+    qm_seed *S;                     // the read's seed slots (global memory)
+    int n, q, q_last;               // seeds so far, next k-mer start, last k-mer start (q > q_last: finished)
+    int64_t trk_p;                  // forward position of the previous k-mer's only hit, -1 = none / several
+    int64_t trk_p2;                 // >= 0: the previous k-mer had one hit per strand, trk_p (as is) and trk_p2 (reverse complement)
+    int trk_pass;                   // strand of a lone hit: 0 = read k-mer as is, 1 = reverse complement
+    // 2..4 hits of any strand mix (repeats in a few copies): all of them tracked, in look-up order
+    int nt;
+    int64_t tp[4];
+    unsigned tpass;                 // bit t: strand of tracked hit t
+    // the seed each strand is currently growing lives in registers (a clean read extends ONE seed ~120 times);
+    // S[] in global memory is only touched when a seed is created, looked for, or handed back
+    // (two named copies, one per strand, picked with selects: an array indexed by the strand would live in local memory)
+    struct Cur { int64_t diag; int idx, len, qnext; } cur0, cur1;
+    int miss_run;                   // the last filter look-up missed (or a tracked match just broke): the next look-ups come in batches
+};
+
+// index of the seed on diagonal `diag` whose last k-mer starts at q - 1, or -1; S[0..n) scanned four entries per round trip
+__device__ __forceinline__ int seed_find(const qm_seed *S, int n, int64_t diag, int q, int k)
+{
+    for (int m0 = 0; m0 < n; m0 += 4) {
+        int4 e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = *(const int4 *)&S[m0 + i < QM_MAX_SEEDS ? m0 + i : QM_MAX_SEEDS - 1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t rbeg = (int64_t)(((uint64_t)(uint32_t)e[i].y << 32) | (uint32_t)e[i].x);
+            if (m0 + i < n && rbeg - e[i].z == diag && e[i].z + e[i].w - k + 1 == q) return m0 + i;
+        }
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void seed_walk_init(SeedWalk &W, qm_seed *S, int len, int k)
+{
+    W.S = S; W.n = 0; W.q = 0; W.q_last = len - k;
+    W.trk_p = -1; W.trk_p2 = -1; W.trk_pass = 0; W.nt = 0; W.tpass = 0;
+    W.tp[0] = W.tp[1] = W.tp[2] = W.tp[3] = 0;
+    W.cur0.diag = W.cur1.diag = 0;
+    W.cur0.idx = W.cur1.idx = -1; W.cur0.len = W.cur1.len = 0; W.cur0.qnext = W.cur1.qnext = 0;
+    W.miss_run = 0;
+}
+
+// one trip: positions q .. of the read are decided (at least one), W.q moves on
+__device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt &o, SeedWalk &W, const uint32_t *__restrict__ bloom /* V.bloom, or NULL */,
+                                               const PackedRead &R, int bloom_batch)
 {
     const int k = V.k;
     const uint32_t occ_cap = (uint32_t)(o.max_occ < QM_OCC_CAP ? o.max_occ : QM_OCC_CAP);
     const uint64_t mask = k < 32 ? ((1ull << (2 * k)) - 1) : ~0ull;
     const uint64_t kbits = k < 64 ? ((1ull << k) - 1) : ~0ull;
-    int n = 0;
-    int64_t trk_p = -1;             // forward position of the previous k-mer's only hit, -1 = none / several
-    int64_t trk_p2 = -1;            // >= 0: the previous k-mer had one hit per strand, trk_p (as is) and trk_p2 (reverse complement)
-    int trk_pass = 0;               // strand of a lone hit: 0 = read k-mer as is, 1 = reverse complement
-    // 2..4 hits of any strand mix (repeats in a few copies): all of them tracked, in look-up order
-    int nt = 0;
-    int64_t tp[4] = {0, 0, 0, 0};
-    unsigned tpass = 0;             // bit t: strand of tracked hit t
-    // the seed each strand is currently growing lives in registers (a clean read extends ONE seed ~120 times);
-    // S[] in global memory is only touched when a seed is created, looked for, or handed back
-    int64_t cur_diag[2] = {0, 0};
-    int cur_idx[2] = {-1, -1}, cur_len[2] = {0, 0}, cur_qnext[2] = {0, 0};
+    qm_seed *S = W.S;
+    int &n = W.n, &q = W.q, &trk_pass = W.trk_pass, &nt = W.nt;
+    const int q_last = W.q_last;
+    int64_t &trk_p = W.trk_p, &trk_p2 = W.trk_p2;
+    int64_t (&tp)[4] = W.tp;
+    unsigned &tpass = W.tpass;
     auto flush = [&]() {
-        if (cur_idx[0] >= 0) S[cur_idx[0]].len = cur_len[0];
-        if (cur_idx[1] >= 0) S[cur_idx[1]].len = cur_len[1];
+        if (W.cur0.idx >= 0) S[W.cur0.idx].len = W.cur0.len;
+        if (W.cur1.idx >= 0) S[W.cur1.idx].len = W.cur1.len;
+    };
+    // is strand `pass` growing a seed on `diag` whose next k-mer starts at qq?
+    auto cur_is = [&](int pass, int64_t diag, int qq) {
+        const int idx = pass ? W.cur1.idx : W.cur0.idx, qn = pass ? W.cur1.qnext : W.cur0.qnext;
+        const int64_t d = pass ? W.cur1.diag : W.cur0.diag;
+        return idx >= 0 && d == diag && qn == qq;
+    };
+    auto cur_grow = [&](int pass, int m) {
+        if (pass) { W.cur1.len += m; W.cur1.qnext += m; } else { W.cur0.len += m; W.cur0.qnext += m; }
+    };
+    auto cur_set = [&](int pass, int idx, int len, int64_t diag, int qnext) {
+        if (pass) { W.cur1.idx = idx; W.cur1.len = len; W.cur1.diag = diag; W.cur1.qnext = qnext; }
+        else { W.cur0.idx = idx; W.cur0.len = len; W.cur0.diag = diag; W.cur0.qnext = qnext; }
     };
     auto add_hit = [&](int pass, int64_t p, int q, bool single) {
         const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
         const int64_t diag = rpos - q;
-        if (single && cur_idx[pass] >= 0 && cur_diag[pass] == diag && cur_qnext[pass] == q) {
-            ++cur_len[pass]; ++cur_qnext[pass];
-            return;
-        }
+        if (single && cur_is(pass, diag, q)) { cur_grow(pass, 1); return; }
         flush();
-        int m;
-        bool found = false;
-        for (m = 0; m < n; ++m)
-            if (S[m].rbeg - S[m].qbeg == diag && S[m].qbeg + S[m].len - k + 1 == q) { found = true; break; }
-        if (found) { cur_len[pass] = ++S[m].len; cur_idx[pass] = m; cur_diag[pass] = diag; cur_qnext[pass] = q + 1; }
+        const int m = seed_find(S, n, diag, q, k);
+        if (m >= 0) { const int len = S[m].len + 1; S[m].len = len; cur_set(pass, m, len, diag, q + 1); }
         else if (n < QM_MAX_SEEDS) {
             S[n].rbeg = rpos; S[n].qbeg = q; S[n].len = k;
-            cur_len[pass] = k; cur_idx[pass] = n++; cur_diag[pass] = diag; cur_qnext[pass] = q + 1;
+            cur_set(pass, n++, k, diag, q + 1);
         }
     };
-    pack_read(rd, len, n_words, n_nwords, R);
-    const int q_last = len - k;                         // last k-mer start
-    int q = 0;
-    while (q <= q_last) {
-        if (nt >= 2) {
-            // every hit of position q-1 is tracked: position q+j has exactly these hits, one step further, as long as the new
-            // read base continues ALL of them and the index says the reference k-mer there occurs nt times in total
-            const int nb = q + k - 1;
-            const uint64_t rbits = R.get2(nb);
-            const uint32_t nbits = (uint32_t)R.getn(nb);
-            int m = nbits ? __ffs((int)nbits) - 1 : 32;
-            if (m > q_last - q + 1) m = q_last - q + 1;
-            {
-                const uint32_t *map = V.cnteqp[nt - 2];
-                const uint32_t cm = (tpass & 1u) ? __brev(uniq_get(map, tp[0] - 32)) : uniq_get(map, tp[0] + 1);
-                const int m_c = ~cm ? __ffs((int)~cm) - 1 : 32;
-                m = m < m_c ? m : m_c;
-            }
+    if (nt >= 2) {
+        // every hit of position q-1 is tracked: position q+j has exactly these hits, one step further, as long as the new
+        // read base continues ALL of them and the index says the reference k-mer there occurs nt times in total
+        const int nb = q + k - 1;
+        const uint64_t rbits = R.get2(nb);
+        const uint32_t nbits = (uint32_t)R.getn(nb);
+        int m = nbits ? __ffs((int)nbits) - 1 : 32;
+        if (m > q_last - q + 1) m = q_last - q + 1;
+        {
+            const uint32_t *map = V.cnteqp[nt - 2];
+            const uint32_t cm = (tpass & 1u) ? __brev(uniq_get(map, tp[0] - 32)) : uniq_get(map, tp[0] + 1);
+            const int m_c = ~cm ? __ffs((int)~cm) - 1 : 32;
+            m = m < m_c ? m : m_c;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t >= nt) break;
+            const bool r = (tpass >> t) & 1u;
+            const uint64_t x = rbits ^ (r ? ~grouprev(ref_get2(V, tp[t] - 32)) : ref_get2(V, tp[t] + k));
+            const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+            const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
+            const int64_t lim = r ? tp[t] : V.l_pac - k - tp[t];
+            m = m < m_b ? m : m_b; m = (int64_t)m > lim ? (int)lim : m;
+        }
+        if (m > 0) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 if (t >= nt) break;
-                const bool r = (tpass >> t) & 1u;
-                const uint64_t x = rbits ^ (r ? ~grouprev(ref_get2(V, tp[t] - 32)) : ref_get2(V, tp[t] + k));
-                const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
-                const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
-                const int64_t lim = r ? tp[t] : V.l_pac - k - tp[t];
-                m = m < m_b ? m : m_b; m = (int64_t)m > lim ? (int)lim : m;
-            }
-            if (m > 0) {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (t >= nt) break;
-                    const int pass = (int)((tpass >> t) & 1u);
-                    const int64_t rpos = pass ? 2 * V.l_pac - tp[t] - k : tp[t];             // of the hit at q-1
-                    const int64_t diag = rpos - (q - 1);
-                    if (cur_idx[pass] >= 0 && cur_diag[pass] == diag && cur_qnext[pass] == q) { cur_len[pass] += m; cur_qnext[pass] += m; }
-                    else {
-                        flush();
-                        for (int sidx = 0; sidx < n; ++sidx)
-                            if (S[sidx].rbeg - S[sidx].qbeg == diag && S[sidx].qbeg + S[sidx].len - k + 1 == q) {
-                                S[sidx].len += m;
-                                cur_idx[pass] = sidx; cur_len[pass] = S[sidx].len; cur_diag[pass] = diag; cur_qnext[pass] = q + m;
-                                break;
-                            }
-                    }
-                    tp[t] += pass ? -m : m;
+                const int pass = (int)((tpass >> t) & 1u);
+                const int64_t rpos = pass ? 2 * V.l_pac - tp[t] - k : tp[t];             // of the hit at q-1
+                const int64_t diag = rpos - (q - 1);
+                if (cur_is(pass, diag, q)) cur_grow(pass, m);
+                else {
+                    flush();
+                    const int sidx = seed_find(S, n, diag, q, k);
+                    if (sidx >= 0) { const int len = S[sidx].len + m; S[sidx].len = len; cur_set(pass, sidx, len, diag, q + m); }
                 }
-                q += m;
-                if (m == 32) continue;
-                if (q > q_last) break;
+                tp[t] += pass ? -m : m;
             }
-            // position q does not continue all of them: the general path below decides
+            q += m;
+            if (m == 32) return;
+            if (q > q_last) return;
         }
-        if (trk_p >= 0) {
-            // How many of the positions q, q+1, ... continue the match of position q-1 (at most 32 per step).  Tracked is
-            // either the ONLY hit of that k-mer (trk_p on strand trk_pass; trk_p2 < 0) or its only hit on EACH strand
-            // (forward-strand hit at trk_p, reverse-complement hit at trk_p2: inverted repeats).
-            const int nb = q + k - 1;                   // index of the first new read base
-            const uint64_t rbits = R.get2(nb);
-            const uint32_t nbits = (uint32_t)R.getn(nb);
-            int m = nbits ? __ffs((int)nbits) - 1 : 32;
-            if (m > q_last - q + 1) m = q_last - q + 1;
-            const bool two = trk_p2 >= 0;
-            if (two || !trk_pass) {                     // a forward-strand hit at trk_p: positions p+1 .. l_pac-k
-                const uint64_t x = rbits ^ ref_get2(V, trk_p + k);
-                const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
-                const uint32_t ub = uniq_get(two ? V.uniq2p : V.uniqp, trk_p + 1);
-                const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32, m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
-                const int64_t lim = V.l_pac - k - trk_p;
-                m = m < m_b ? m : m_b; m = m < m_u ? m : m_u; m = (int64_t)m > lim ? (int)lim : m;
-            }
-            if (two || trk_pass) {                      // a reverse-complement hit at pr: positions pr-1 .. 0
-                const int64_t pr = two ? trk_p2 : trk_p;
-                const uint64_t x = rbits ^ ~grouprev(ref_get2(V, pr - 32));
-                const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
-                const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
-                m = m < m_b ? m : m_b; m = (int64_t)m > pr ? (int)pr : m;
-                if (!two) {
-                    const uint32_t ub = __brev(uniq_get(V.uniqp, pr - 32));
-                    const int m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
-                    m = m < m_u ? m : m_u;
-                }
-            }
-            if (m > 0) {
-                auto grow = [&](int pass, int64_t p) {
-                    const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;                 // of the hit at q-1
-                    if (cur_idx[pass] >= 0 && cur_diag[pass] == rpos - (q - 1) && cur_qnext[pass] == q) {
-                        cur_len[pass] += m; cur_qnext[pass] += m;
-                    }
-                };
-                if (two) { grow(0, trk_p); grow(1, trk_p2); trk_p += m; trk_p2 -= m; }
-                else { grow(trk_pass, trk_p); trk_p = trk_pass ? trk_p - m : trk_p + m; }
-                q += m;
-                if (m == 32) continue;
-                if (q > q_last) break;
-            }
-            // position q does not continue the match: the general path below decides
-        }
-        const uint64_t nm = R.getn(q) & kbits;
-        if (nm) {                                       // an N inside the k-mer: skip every k-mer that covers it
-            trk_p = -1; trk_p2 = -1; nt = 0;
-            q += 64 - __clzll((long long)nm);
-            continue;
-        }
-        if (bloom) {
-            // A k-mer whose canonical form misses the filter occurs on neither strand: no table probe (the common case for
-            // the k - 1 k-mers that cover a mismatch).  The filter words of kBloomBatch consecutive positions are fetched
-            // TOGETHER: behind a mismatch ~k positions in a row miss, and probing them one by one is a chain of ~k dependent
-            // L2 round trips per mismatch -- the bulk of this kernel's time -- where the batch pays one round trip per
-            // kBloomBatch positions.  Only positions whose k-mer holds no N are in a batch (nm == 0 covers the first).
-            int gmax = q_last - q + 1 < bloom_batch ? q_last - q + 1 : bloom_batch;
-            {
-                const uint64_t nn = R.getn(q) >> k;                    // N flags of the bases behind the first k-mer
-                const int free_n = nn ? __ffsll((long long)nn) : 64;   // positions q .. q+free_n-1 have an N-free k-mer
-                gmax = gmax < free_n ? gmax : free_n;
-            }
-            uint32_t bw[kBloomBatch][3], bs[kBloomBatch][3];
-#pragma unroll
-            for (int g = 0; g < kBloomBatch; ++g) {
-                if (g < gmax) {
-                    const uint64_t vg = R.get2(q + g) & mask;
-                    const uint64_t fg = grouprev(vg) >> (64 - 2 * k), rg = ~vg & mask;
-                    uint32_t bp[3];
-                    qm_bloom_pos(fg < rg ? fg : rg, V.bloom_bits, bp);
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) { bw[g][t] = __ldg(&bloom[bp[t] >> 5]); bs[g][t] = bp[t] & 31; }
-                }
-            }
-            unsigned hitmask = 0;
-#pragma unroll
-            for (int g = 0; g < kBloomBatch; ++g)
-                if (g < gmax) hitmask |= ((bw[g][0] >> bs[g][0]) & (bw[g][1] >> bs[g][1]) & (bw[g][2] >> bs[g][2]) & 1u) << g;
-            const int lead = hitmask ? __ffs((int)hitmask) - 1 : gmax;             // positions in a row that miss
-            if (lead > 0) {
-                trk_p = -1; trk_p2 = -1; nt = 0;
-                q += lead;
-                if (lead == gmax) continue;
-            }
-            // position q passed the filter (and its k-mer holds no N)
-        }
-        const uint64_t v = R.get2(q) & mask;            // first base in the lowest bits
-        const uint64_t fw = grouprev(v) >> (64 - 2 * k);  // first base in the highest bits: the table's key order
-        const uint64_t rc = ~v & mask;                  // reverse complement in the same order
-        // the first table slot of both strands, fetched together (two dependent L2 round trips become one)
-        const uint64_t slot0[2] = {(fw * 0x9E3779B97F4A7C15ull) >> V.shift, (rc * 0x9E3779B97F4A7C15ull) >> V.shift};
-        const uint4 ent0[2] = {__ldg(&V.table[slot0[0]]), __ldg(&V.table[slot0[1]])};
-        int n_hits = 0, one_pass = 0, n_pass[2] = {0, 0};
-        int64_t one_p = -1, p_of[2] = {-1, -1};
-        bool ignored = false;
-        nt = 0; tpass = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            uint32_t first, cnt;
-            if (!qm_idx_lookup_from(V, pass ? rc : fw, pass ? slot0[1] : slot0[0], pass ? ent0[1] : ent0[0], first, cnt)) continue;
-            if (cnt > occ_cap) { n_hits += 2; ignored = true; continue; }          // ignored k-mer: nothing of this position is tracked
-            for (uint32_t t = 0; t < cnt; ++t) {
-                const int64_t p = V.pos[first + t];
-                add_hit(pass, p, q, cnt == 1);
-                one_p = p; one_pass = pass; p_of[pass] = p;
-                if (nt < 4) { tp[nt] = p; tpass |= (unsigned)pass << nt; }
-                ++nt;
-            }
-            n_hits += (int)cnt; n_pass[pass] = (int)cnt;
-        }
-        trk_p = -1; trk_p2 = -1;
-        if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; nt = 0; }
-        else if (n_hits == 2 && n_pass[0] == 1 && n_pass[1] == 1) { trk_p = p_of[0]; trk_p2 = p_of[1]; trk_pass = 0; nt = 0; }
-        else if (ignored || nt < 2 || nt > 4) nt = 0;                  // (otherwise: 2..4 hits, all tracked)
-        ++q;
+        // position q does not continue all of them: the general path below decides
+        W.miss_run = 1;
     }
-    flush();
-    for (int i = 1; i < n; ++i) {       // order: (qbeg, rbeg)
+    if (trk_p >= 0) {
+        // How many of the positions q, q+1, ... continue the match of position q-1 (at most 32 per step).  Tracked is
+        // either the ONLY hit of that k-mer (trk_p on strand trk_pass; trk_p2 < 0) or its only hit on EACH strand
+        // (forward-strand hit at trk_p, reverse-complement hit at trk_p2: inverted repeats).
+        const int nb = q + k - 1;                   // index of the first new read base
+        const uint64_t rbits = R.get2(nb);
+        const uint32_t nbits = (uint32_t)R.getn(nb);
+        int m = nbits ? __ffs((int)nbits) - 1 : 32;
+        if (m > q_last - q + 1) m = q_last - q + 1;
+        const bool two = trk_p2 >= 0;
+        if (two || !trk_pass) {                     // a forward-strand hit at trk_p: positions p+1 .. l_pac-k
+            const uint64_t x = rbits ^ ref_get2(V, trk_p + k);
+            const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+            const uint32_t ub = uniq_get(two ? V.uniq2p : V.uniqp, trk_p + 1);
+            const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32, m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
+            const int64_t lim = V.l_pac - k - trk_p;
+            m = m < m_b ? m : m_b; m = m < m_u ? m : m_u; m = (int64_t)m > lim ? (int)lim : m;
+        }
+        if (two || trk_pass) {                      // a reverse-complement hit at pr: positions pr-1 .. 0
+            const int64_t pr = two ? trk_p2 : trk_p;
+            const uint64_t x = rbits ^ ~grouprev(ref_get2(V, pr - 32));
+            const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+            const int m_b = mm ? (__ffsll((long long)mm) - 1) >> 1 : 32;
+            m = m < m_b ? m : m_b; m = (int64_t)m > pr ? (int)pr : m;
+            if (!two) {
+                const uint32_t ub = __brev(uniq_get(V.uniqp, pr - 32));
+                const int m_u = ~ub ? __ffs((int)~ub) - 1 : 32;
+                m = m < m_u ? m : m_u;
+            }
+        }
+        if (m > 0) {
+            auto grow = [&](int pass, int64_t p) {
+                const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;                 // of the hit at q-1
+                if (cur_is(pass, rpos - (q - 1), q)) cur_grow(pass, m);
+            };
+            if (two) { grow(0, trk_p); grow(1, trk_p2); trk_p += m; trk_p2 -= m; }
+            else { grow(trk_pass, trk_p); trk_p = trk_pass ? trk_p - m : trk_p + m; }
+            q += m;
+            if (m == 32) return;
+            if (q > q_last) return;
+        }
+        // position q does not continue the match: the general path below decides (a mismatch: ~k positions in a row will miss)
+        W.miss_run = 1;
+    }
+    const uint64_t nm = R.getn(q) & kbits;
+    if (nm) {                                       // an N inside the k-mer: skip every k-mer that covers it
+        trk_p = -1; trk_p2 = -1; nt = 0;
+        q += 64 - __clzll((long long)nm);
+        return;
+    }
+    if (bloom) {
+        // A k-mer whose canonical form misses the filter occurs on neither strand: no table probe (the common case for
+        // the k - 1 k-mers that cover a mismatch).  The filter words of kBloomBatch consecutive positions are fetched
+        // TOGETHER: behind a mismatch ~k positions in a row miss, and probing them one by one is a chain of ~k dependent
+        // L2 round trips per mismatch -- the bulk of this kernel's time -- where the batch pays one round trip per
+        // kBloomBatch positions.  Only positions whose k-mer holds no N are in a batch (nm == 0 covers the first).
+        // (one position at a time until a look-up misses: at a read's start and behind a repeat the first look-up usually hits)
+        const int want = W.miss_run ? bloom_batch : 1;
+        int gmax = q_last - q + 1 < want ? q_last - q + 1 : want;
+        {
+            const uint64_t nn = R.getn(q) >> k;                    // N flags of the bases behind the first k-mer
+            const int free_n = nn ? __ffsll((long long)nn) : 64;   // positions q .. q+free_n-1 have an N-free k-mer
+            gmax = gmax < free_n ? gmax : free_n;
+        }
+        uint32_t bw[kBloomBatch][3], bs[kBloomBatch][3];
+#pragma unroll
+        for (int g = 0; g < kBloomBatch; ++g) {
+            if (g < gmax) {
+                const uint64_t vg = R.get2(q + g) & mask;
+                const uint64_t fg = grouprev(vg) >> (64 - 2 * k), rg = ~vg & mask;
+                uint32_t bp[3];
+                qm_bloom_pos(fg < rg ? fg : rg, V.bloom_bits, bp);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) { bw[g][t] = __ldg(&bloom[bp[t] >> 5]); bs[g][t] = bp[t] & 31; }
+            }
+        }
+        unsigned hitmask = 0;
+#pragma unroll
+        for (int g = 0; g < kBloomBatch; ++g)
+            if (g < gmax) hitmask |= ((bw[g][0] >> bs[g][0]) & (bw[g][1] >> bs[g][1]) & (bw[g][2] >> bs[g][2]) & 1u) << g;
+        const int lead = hitmask ? __ffs((int)hitmask) - 1 : gmax;             // positions in a row that miss
+        W.miss_run = lead == gmax;
+        if (lead > 0) {
+            trk_p = -1; trk_p2 = -1; nt = 0;
+            q += lead;
+            if (lead == gmax) return;
+        }
+        // position q passed the filter (and its k-mer holds no N)
+    }
+    const uint64_t v = R.get2(q) & mask;            // first base in the lowest bits
+    const uint64_t fw = grouprev(v) >> (64 - 2 * k);  // first base in the highest bits: the table's key order
+    const uint64_t rc = ~v & mask;                  // reverse complement in the same order
+    // the first table slot of both strands, fetched together (two dependent L2 round trips become one)
+    const uint64_t slot0[2] = {(fw * 0x9E3779B97F4A7C15ull) >> V.shift, (rc * 0x9E3779B97F4A7C15ull) >> V.shift};
+    const uint4 ent0[2] = {__ldg(&V.table[slot0[0]]), __ldg(&V.table[slot0[1]])};
+    int n_hits = 0, one_pass = 0, n_pass[2] = {0, 0};
+    int64_t one_p = -1, p_of[2] = {-1, -1};
+    bool ignored = false;
+    nt = 0; tpass = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        uint32_t first, cnt;
+        if (!qm_idx_lookup_from(V, pass ? rc : fw, pass ? slot0[1] : slot0[0], pass ? ent0[1] : ent0[0], first, cnt)) continue;
+        if (cnt > occ_cap) { n_hits += 2; ignored = true; continue; }          // ignored k-mer: nothing of this position is tracked
+        for (uint32_t t = 0; t < cnt; ++t) {
+            const int64_t p = V.pos[first + t];
+            add_hit(pass, p, q, cnt == 1);
+            one_p = p; one_pass = pass; p_of[pass] = p;
+            if (nt < 4) { if (nt == 0) tp[0] = p; else if (nt == 1) tp[1] = p; else if (nt == 2) tp[2] = p; else tp[3] = p; tpass |= (unsigned)pass << nt; }
+            ++nt;
+        }
+        n_hits += (int)cnt; n_pass[pass] = (int)cnt;
+    }
+    trk_p = -1; trk_p2 = -1;
+    if (n_hits == 1) { trk_p = one_p; trk_pass = one_pass; nt = 0; }
+    else if (n_hits == 2 && n_pass[0] == 1 && n_pass[1] == 1) { trk_p = p_of[0]; trk_p2 = p_of[1]; trk_pass = 0; nt = 0; }
+    else if (ignored || nt < 2 || nt > 4) nt = 0;                  // (otherwise: 2..4 hits, all tracked)
+    ++q;
+}
+
+// the end of a read's walk: the growing seeds' lengths handed back, seeds ordered by (qbeg, rbeg); returns their number
+__device__ __forceinline__ int seed_walk_finish(SeedWalk &W)
+{
+    qm_seed *S = W.S;
+    if (W.cur0.idx >= 0) S[W.cur0.idx].len = W.cur0.len;
+    if (W.cur1.idx >= 0) S[W.cur1.idx].len = W.cur1.len;
+    const int n = W.n;
+    for (int i = 1; i < n; ++i) {
         const qm_seed x = S[i];
         int j = i - 1;
         while (j >= 0 && (S[j].qbeg > x.qbeg || (S[j].qbeg == x.qbeg && S[j].rbeg > x.rbeg))) { S[j + 1] = S[j]; --j; }
         S[j + 1] = x;
     }
     return n;
+}
+
+__device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
+                             const uint32_t *__restrict__ bloom /* V.bloom, or NULL */, PackedRead &R, int n_words, int n_nwords,
+                             int bloom_batch = kBloomBatch)
+{
+    pack_read(rd, len, n_words, n_nwords, R);
+    SeedWalk W;
+    seed_walk_init(W, S, len, V.k);
+    while (W.q <= W.q_last) seed_walk_step(V, o, W, bloom, R, bloom_batch);
+    return seed_walk_finish(W);
 }
 
 __device__ __forceinline__ int seed_rid(const IndexView &V, const qm_seed &s)
@@ -540,16 +599,111 @@ seed_chain_kernel(IndexView V, qm_opt o, const uint8_t *__restrict__ codes, int 
     st[r] = s;
 }
 
+// ---- the seeding stage as three kernels (the default): pack, walk, plan ----
+// pack_reads_kernel   the block's rows staged by one bulk copy, every thread packs its read (2 bits per base + N flags) and the
+//                     block writes the packed words out coalesced: [read][n_words + n_nwords] 64-bit words.
+// seed_walk_kernel    PERSISTENT: a lane walks one read's k-mer positions (seed_walk_step) and takes the next read off a global
+//                     cursor when it is done.  Reads differ ~30x in work (mismatches, repeats); with one read per thread a warp
+//                     lived as long as its slowest read with, on average, 15 of 32 lanes still walking.  Finished lanes wait until
+//                     `refill` of them are idle (or nobody works) and fetch together: the refill is a short uniform burst of loads.
+// plan_kernel         one thread per read: chains + filter -> plan (build_plan), the state machine's start state.
+__global__ void __launch_bounds__(kSeedThreads)
+pack_reads_kernel(const uint8_t *__restrict__ codes, int stride, const int32_t *__restrict__ lens, int64_t n, uint64_t *__restrict__ packed,
+                  int n_words, int n_nwords, bool staged)
+{
+    extern __shared__ __align__(16) uint64_t s_read[];
+    __shared__ uint64_t s_bar;
+    const int64_t r0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t r = r0 + threadIdx.x;
+    const int pw = n_words + n_nwords;
+    const int n_rows = n - r0 < (int64_t)blockDim.x ? (int)(n - r0) : (int)blockDim.x;
+    const uint8_t *rd = codes + r * stride;
+    if (staged) rd = stage_block_reads(codes, stride, r0, n_rows, (uint8_t *)(s_read + (size_t)pw * blockDim.x), &s_bar) + (size_t)threadIdx.x * stride;
+    if (r < n) {
+        PackedRead R;
+        R.bits = s_read + threadIdx.x;
+        R.nmask = s_read + (size_t)n_words * blockDim.x + threadIdx.x;
+        R.ts = (int)blockDim.x;
+        pack_read(rd, lens[r], n_words, n_nwords, R);
+    }
+    __syncthreads();
+    uint64_t *out = packed + r0 * pw;
+    for (int i = threadIdx.x; i < n_rows * pw; i += blockDim.x) {
+        const int t = i / pw, w = i - t * pw;
+        out[i] = s_read[(size_t)w * blockDim.x + t];
+    }
+}
+
+template <int MINB>                                     // resident blocks of 64 threads asked of the compiler (register budget 65536 / 64 / MINB)
+__global__ void __launch_bounds__(64, MINB)
+seed_walk_kernel(IndexView V, qm_opt o, const uint64_t *__restrict__ packed, const int32_t *__restrict__ lens, int64_t n,
+                 qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds, int *__restrict__ cursor, int n_words, int n_nwords,
+                 int bloom_batch, int refill)
+{
+    extern __shared__ __align__(16) uint64_t s_read[];   // [n_words + n_nwords][threads]: the lane's current read
+    PackedRead R;
+    R.bits = s_read + threadIdx.x;
+    R.nmask = s_read + (size_t)n_words * blockDim.x + threadIdx.x;
+    R.ts = (int)blockDim.x;
+    const int pw = n_words + n_nwords;
+    const uint32_t *bloom = V.bloom_bits ? V.bloom : nullptr;
+    SeedWalk W;
+    seed_walk_init(W, nullptr, 0, V.k);
+    int64_t r = -1;                                      // the lane's read, -1 = none
+    bool exhausted = false;
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        const bool idle = r < 0;
+        const unsigned idle_m = __ballot_sync(0xffffffffu, idle);
+        const unsigned want_m = __ballot_sync(0xffffffffu, idle && !exhausted);
+        if (idle_m == 0xffffffffu && want_m == 0u) break;
+        if (idle && !exhausted && (__popc(want_m) >= refill || idle_m == 0xffffffffu)) {
+            // the lanes in here are exactly want_m: one atomic for all of them
+            const int leader = __ffs((int)want_m) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, __popc(want_m));
+            base = __shfl_sync(want_m, base, leader);
+            const int64_t idx = base + __popc(want_m & ((1u << lane) - 1u));
+            if (idx >= n) exhausted = true;
+            else {
+                r = idx;
+                const uint64_t *src = packed + r * pw;
+                for (int w = 0; w < pw; ++w) s_read[(size_t)w * blockDim.x + threadIdx.x] = __ldg(src + w);
+                seed_walk_init(W, seeds + r * QM_MAX_SEEDS, lens[r], V.k);
+            }
+        }
+        if (r >= 0) {
+            if (W.q <= W.q_last) seed_walk_step(V, o, W, bloom, R, bloom_batch);
+            if (W.q > W.q_last) { n_seeds[r] = seed_walk_finish(W); r = -1; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+plan_kernel(IndexView V, qm_opt o, int64_t n, const qm_seed *__restrict__ seeds, const int32_t *__restrict__ n_seeds,
+            uint16_t *__restrict__ plan, uint8_t *__restrict__ n_plan, ReadState *__restrict__ st)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int np = build_plan(V, o, seeds + r * QM_MAX_SEEDS, n_seeds[r], plan + r * QM_MAX_SEEDS);
+    n_plan[r] = (uint8_t)np;
+    ReadState s;
+    s.cursor = 0; s.phase = PH_NEXT; s.n_av = 0; s.task = -1;
+    st[r] = s;
+}
+
+// packed (n * (n_words + n_nwords) words of scratch) and cursor (one int of scratch) select the three-kernel form; without them
+// (or with QM_SEED_PERSIST=0, for A/B measurements) the one-read-per-thread kernel runs
 static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_opt &o, const uint8_t *codes, int stride, const int32_t *lens,
                                      int64_t n, qm_seed *seeds, int32_t *n_seeds, uint16_t *plan, uint8_t *n_plan, ReadState *st,
-                                     bool seeds_only, cudaStream_t stream)
+                                     bool seeds_only, cudaStream_t stream, uint64_t *packed = nullptr, int *cursor = nullptr)
 {
-    (void)ctx;
     // packed read: one word per 32 bases + one spare (windows may start at the last base), N flags per 64 bases + one spare
     const int n_words = (stride + 31) / 32 + 2, n_nwords = (stride + 63) / 64 + 2;
     static const int threads = getenv("QM_SEED_THREADS") ? std::max(32, std::min(kSeedThreads, atoi(getenv("QM_SEED_THREADS")) & ~31)) : 64;   // tuning knob; 64: a block
     // lives as long as its slowest read (repeats), and smaller blocks give their slots back sooner (7.47 -> 7.13 ms per 4 M reads; 32: 7.35)
-    size_t smem = (size_t)(n_words + n_nwords) * threads * sizeof(uint64_t);
+    const size_t smem_packed = (size_t)(n_words + n_nwords) * threads * sizeof(uint64_t);
+    size_t smem = smem_packed;
     // the block's rows staged by one bulk copy (QM_SEED_STAGE=0: per-thread loads, for A/B measurements); very long rows stay
     // with the per-thread loads (the default 48 KB of dynamic shared memory)
     static const bool want_stage = !(getenv("QM_SEED_STAGE") && atoi(getenv("QM_SEED_STAGE")) == 0);
@@ -557,7 +711,31 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
     const bool staged = want_stage && smem + stage_bytes <= 40 * 1024;
     if (staged) smem += stage_bytes;
     static const int bloom_batch = getenv("QM_BLOOM_BATCH") ? std::max(1, std::min(kBloomBatch, atoi(getenv("QM_BLOOM_BATCH")))) : kBloomBatch;   // tuning knob
-    seed_chain_kernel<<<(unsigned)((n + threads - 1) / threads), threads, smem, stream>>>(
+    static const bool want_persist = !(getenv("QM_SEED_PERSIST") && atoi(getenv("QM_SEED_PERSIST")) == 0);
+    static const int refill = getenv("QM_SEED_REFILL") ? std::max(1, std::min(32, atoi(getenv("QM_SEED_REFILL")))) : 8;                           // tuning knob
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (packed && cursor && want_persist && smem_packed <= 40 * 1024 && n <= 0x7fffffff - 4096) {
+        cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        pack_reads_kernel<<<blocks, threads, smem, stream>>>(codes, stride, lens, n, packed, n_words, n_nwords, staged);
+        // the walk is bound by the latency of dependent L2 look-ups: resident warps matter more than registers per thread
+        static const int minb = getenv("QM_SEED_MINB") ? atoi(getenv("QM_SEED_MINB")) : 8;                                                        // tuning knob: 8 / 12 / 16
+        auto walk = minb >= 16 ? seed_walk_kernel<16> : minb >= 12 ? seed_walk_kernel<12> : seed_walk_kernel<8>;
+        const int wt = 64;                             // (its launch bounds)
+        const size_t smem_walk = (size_t)(n_words + n_nwords) * wt * sizeof(uint64_t);
+        static int per_sm[64] = {};                    // resident blocks of the walk kernel per SM, per device
+        int &ps = per_sm[ctx->device & 63];
+        if (ps == 0) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, walk, wt, smem_walk);
+            if (e != cudaSuccess) return e;
+            if (ps < 1) ps = 1;
+        }
+        const unsigned walk_blocks = std::min<unsigned>((unsigned)((n + wt - 1) / wt), (unsigned)(ctx->sm_count * ps));
+        walk<<<walk_blocks, wt, smem_walk, stream>>>(V, o, packed, lens, n, seeds, n_seeds, cursor, n_words, n_nwords, bloom_batch, refill);
+        if (!seeds_only) plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(V, o, n, seeds, n_seeds, plan, n_plan, st);
+        return cudaGetLastError();
+    }
+    seed_chain_kernel<<<blocks, threads, smem, stream>>>(
         V, o, codes, stride, lens, n, seeds, n_seeds, plan, n_plan, st, seeds_only, n_words, n_nwords, staged, bloom_batch);
     return cudaGetLastError();
 }
@@ -1086,9 +1264,10 @@ constexpr int64_t kSeBatch = 1 << 22;         // a round with fewer tasks hands 
 struct SeScratch {
     qm_seed *seeds; int32_t *n_seeds; uint16_t *plan; uint8_t *n_plan; ReadState *st;
     ExtTaskI *tasks; qm_ext_result *res; int *lists; uint64_t *keys; RoundCounters *ctr; RoundCounters *h_ctr;
+    uint64_t *packed; size_t packed_words; int *cursors;        // the seeding stage's packed reads (per read: packed_words) and read cursors
 };
 
-int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
+int se_scratch(qm_ctx *ctx, int64_t nb, int stride, SeScratch *sc)
 {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -1102,6 +1281,8 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     const size_t o_lists = take((size_t)nb * (1 + kExtClasses) * 4);   // the round's sorted task list, then the fallback lists
     const size_t o_keys = take((size_t)nb * 8);
     const size_t o_ctr = take(sizeof(RoundCounters));
+    const size_t pw = (size_t)((stride + 31) / 32 + 2 + (stride + 63) / 64 + 2);
+    const size_t o_packed = take((size_t)nb * pw * 8), o_cursors = take(64 * sizeof(int));
     void *p = nullptr;
     int rc = qm_scratch_reserve(ctx, 3, off, &p);
     if (rc) return rc;
@@ -1109,6 +1290,7 @@ int se_scratch(qm_ctx *ctx, int64_t nb, SeScratch *sc)
     sc->seeds = (qm_seed *)(b + o_seeds); sc->n_seeds = (int32_t *)(b + o_ns); sc->plan = (uint16_t *)(b + o_plan);
     sc->n_plan = (uint8_t *)(b + o_np); sc->st = (ReadState *)(b + o_st); sc->tasks = (ExtTaskI *)(b + o_tasks);
     sc->res = (qm_ext_result *)(b + o_res); sc->lists = (int *)(b + o_lists); sc->keys = (uint64_t *)(b + o_keys); sc->ctr = (RoundCounters *)(b + o_ctr);
+    sc->packed = (uint64_t *)(b + o_packed); sc->packed_words = pw; sc->cursors = (int *)(b + o_cursors);
     return QM_OK;
 }
 
@@ -1224,8 +1406,13 @@ int qm_collect_seeds(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const 
         QM_CUDA(ctx, launch_fm_seed(idx, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true, (cudaStream_t)stream));
         return QM_OK;
     }
+    // scratch of the three-kernel form: the packed reads and the read cursor
+    const size_t pw = (size_t)((stride + 31) / 32 + 2 + (stride + 63) / 64 + 2);
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(ctx, 3, (size_t)n_reads * pw * 8 + 256, &p);
+    if (rc) return rc;
     QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, d_codes, stride, d_lens, n_reads, d_seeds, d_n_seeds, nullptr, nullptr, nullptr, true,
-                                   (cudaStream_t)stream));
+                                   (cudaStream_t)stream, (uint64_t *)((char *)p + 256), (int *)p));
     return QM_OK;
 }
 
@@ -1241,7 +1428,7 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nbmax = n_reads < kSeBatch ? n_reads : kSeBatch;
     SeScratch sc;
-    int rc = se_scratch(ctx, nbmax, &sc);
+    int rc = se_scratch(ctx, nbmax, stride, &sc);
     if (rc) return rc;
     static_assert(kRoundHeader <= 8192, "round header must fit the context's pinned buffer");
     RoundCounters *h_ctr = (RoundCounters *)ctx->h_pinned;          // only the first kRoundHeader bytes are ever read back
@@ -1275,7 +1462,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                     if (ctx->se_pk) QM_CUDA(ctx, qm_unpack_reads_launch(ctx->se_pk + r0 * ctx->se_sp, ctx->se_mk + r0 * ctx->se_sm, stride, ctx->se_sp, ctx->se_sm,
                                                                         r1 - r0, (uint8_t *)codes + r0 * stride, ss));
                     QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes + r0 * stride, stride, lens + r0, r1 - r0, sc.seeds + r0 * QM_MAX_SEEDS,
-                                                   sc.n_seeds + r0, sc.plan + r0 * QM_MAX_SEEDS, sc.n_plan + r0, sc.st + r0, false, ss));
+                                                   sc.n_seeds + r0, sc.plan + r0 * QM_MAX_SEEDS, sc.n_plan + r0, sc.st + r0, false, ss,
+                                                   sc.packed + r0 * sc.packed_words, sc.cursors + 1 + pt % 32));
                     QM_CUDA(ctx, cudaEventRecord(ctx->ev_join[pt % 12], ss));
                     QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[pt % 12], 0));
                     ++n_seed_launches;
@@ -1289,7 +1477,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             // (a chunk whose pieces have all landed already -- every chunk of a host call but the first -- is seeded in one launch)
             for (int pt = 0; pt < ctx->se_n_parts; ++pt) QM_CUDA(ctx, cudaStreamWaitEvent(st, ctx->se_part_ev[pt], 0));
             if (ctx->se_pk && b0 == 0) QM_CUDA(ctx, qm_unpack_reads_launch(ctx->se_pk, ctx->se_mk, stride, ctx->se_sp, ctx->se_sm, n_reads, (uint8_t *)d_codes, st));
-            QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st));
+            QM_CUDA(ctx, launch_seed_chain(ctx, idx->v, *opt, codes, stride, lens, nb, sc.seeds, sc.n_seeds, sc.plan, sc.n_plan, sc.st, false, st,
+                                           sc.packed, sc.cursors));
             n_seed_launches = 1;
         }
         ctx->se_n_parts = 0; ctx->se_pk = ctx->se_mk = nullptr;

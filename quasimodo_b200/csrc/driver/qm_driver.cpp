@@ -5,7 +5,7 @@
 //   qm_driver sample   --ref REF.fa[,MORE.fa...] --r1 R1.fq[.gz] --r2 R2.fq[.gz] [--sample NAME]
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf [--vcf-gz 0]] [--gpu I | --gpus A,B,..|A-B] [-t THREADS] [-w BAND]
 //                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
-//                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0] [--max-depth N]
+//                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0] [--max-depth N] [--baq 1]
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
 //        semantics, formatted on the device (with --rmdup 1: of the duplicate-free records, as the reference's rule reads them)
 //        --no-rescue 1 = bwa mem -S (mate rescue off; on by default as in the reference's command line)
@@ -869,6 +869,10 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     if (max_depth < 0) die(1, "--max-depth must be >= 0");
     if (max_depth > 0 && n_gpu > 1) die(1, "--max-depth needs the records of the whole sample on one device: run it with one GPU");
     if (max_depth > 0) L.check(qm_sample_set_max_depth(smp, max_depth), "qm_sample_set_max_depth");
+    // --baq 1: base alignment quality on, as both mpileups of the reference flow run (no -B at rules/vcfcall.smk:39,115): extended BAQ
+    // caps the base qualities the counts, the calls and the text pileup see.  Off by default (the parity configuration is -B).
+    const int baq = atoi(a.get("baq", "0").c_str()) ? 3 : 0;
+    if (baq) for (int d = 0; d < n_gpu; ++d) Ls[d].check(qm_sample_set_baq(smps[d], baq), "qm_sample_set_baq");
     const std::string mpileup = a.get("mpileup");
     const bool want_bam = !bam.empty() || !rmdup_bam.empty();
     const bool want_batches = want_bam || !mpileup.empty();
@@ -1051,6 +1055,12 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         }
         std::vector<const char *> nm;
         for (auto &s : g.names) nm.push_back(s.c_str());
+        if (baq) {                                   // samtools mpileup without -B: the text shows the capped qualities
+            std::vector<uint8_t> capped(quals.size());
+            L.check(qm_baq_apply_host(L.ctx, idx, &popt, alns.data(), codes.data(), quals.data(), stride, lens.data(), 2 * n_pairs, baq, capped.data()),
+                    "qm_baq_apply_host");
+            quals.swap(capped);
+        }
         int64_t bytes = 0;
         L.check(qm_mpileup_text_host(L.ctx, idx, &popt, alns.data(), codes.data(), quals.data(), stride, lens.data(), n_pairs, nm.data(), &bytes),
                 "qm_mpileup_text_host");

@@ -42,6 +42,7 @@ struct qm_sample {
     // qm_sample_rmdup_finish
     bool rmdup = false;
     int max_depth = 0;                            // > 0: `bcftools mpileup -d` depth cap (qm_sample_set_max_depth): deferred counting too
+    int baq = 0;                                  // 1 / 3: base alignment quality (plain / extended) caps the qualities the pileup sees (qm_sample_set_baq)
     bool rmdup_finished = false;                  // qm_sample_rmdup_finish has run: no more pairs, no second finish until a reset
     struct Kept { uint8_t *codes, *quals; int32_t *lens; qm_aln *alns; int64_t n; int32_t stride; };
     std::vector<Kept> kept;
@@ -82,6 +83,21 @@ cudaError_t qm_unpack_reads_launch(const uint8_t *d_bases2, const uint8_t *d_nma
 }
 
 namespace {
+
+// the qualities the pileup sees: the reads' own, or (qm_sample_set_baq) capped by their base alignment quality
+int sample_pileup_quals(qm_sample *s, const qm_aln *alns, const uint8_t *d_codes, const uint8_t *d_quals, int32_t stride, const int32_t *d_lens,
+                        int64_t n_reads, cudaStream_t st, const uint8_t **out)
+{
+    *out = d_quals;
+    if (!s->baq || n_reads == 0) return QM_OK;
+    void *p = nullptr;
+    int rc = qm_scratch_reserve(s->ctx, 30, (size_t)n_reads * stride, &p);
+    if (rc) return rc;
+    rc = qm_baq_apply(s->ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n_reads, s->baq, (uint8_t *)p, st);
+    if (rc) return rc;
+    *out = (const uint8_t *)p;
+    return QM_OK;
+}
 
 // quals_ready (may be NULL): event after which d_quals is valid; only the pileup reads the qualities, so their copy
 // may still be in flight while the reads are being aligned
@@ -130,7 +146,10 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
         return QM_OK;
     }
     if (quals_ready) QM_CUDA(ctx, cudaStreamWaitEvent(st, quals_ready, 0));
-    rc = qm_pileup_accumulate_indels(ctx, s->idx, &s->popt, alns, d_codes, d_quals, stride, d_lens, n, s->d_counts, s->indels, st);
+    const uint8_t *pq = nullptr;
+    rc = sample_pileup_quals(s, alns, d_codes, d_quals, stride, d_lens, 2 * n, st, &pq);
+    if (rc) return rc;
+    rc = qm_pileup_accumulate_indels(ctx, s->idx, &s->popt, alns, d_codes, pq, stride, d_lens, n, s->d_counts, s->indels, st);
     if (rc) return rc;
     s->n_pairs += n;
     return QM_OK;
@@ -226,6 +245,17 @@ int qm_sample_set_max_depth(qm_sample *s, int max_depth)
     return QM_OK;
 }
 
+// Base alignment quality for the sample's pileup: 0 = off (the default: `mpileup -B`, the parity configuration), 3 = extended BAQ as
+// `bcftools mpileup` / `samtools mpileup` run it without -B (rules/vcfcall.smk:39,115), 1 = plain BAQ.  Duplicate marking keeps
+// using the reads' own qualities (picard runs before the pileup).
+int qm_sample_set_baq(qm_sample *s, int flag)
+{
+    if (!s || (flag != 0 && flag != 1 && flag != 3)) return QM_EINVAL;
+    if (s->n_pairs != 0) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_set_baq: pairs were already added; reset the sample first");
+    s->baq = flag;
+    return QM_OK;
+}
+
 // Deferred counting: marks the duplicates among everything added since the last reset (rmdup mode), replays htslib's depth
 // cap over the records that are left (max_depth mode), then counts what survives both.
 int qm_sample_finish(qm_sample *s, int64_t *n_dup_pairs, int64_t *n_capped_reads, void *stream)
@@ -258,7 +288,9 @@ int qm_sample_finish(qm_sample *s, int64_t *n_dup_pairs, int64_t *n_capped_reads
     }
     for (int c = 0; c < nc; ++c) {
         const auto &k = s->kept[c];
-        rc = qm_pileup_accumulate_masked(ctx, s->idx, &s->popt, k.alns, k.codes, k.quals, k.stride, k.lens, k.n, s->d_counts, s->indels, drop[c], stream);
+        const uint8_t *pq = nullptr;
+        rc = sample_pileup_quals(s, k.alns, k.codes, k.quals, k.stride, k.lens, 2 * k.n, (cudaStream_t)stream, &pq);
+        if (!rc) rc = qm_pileup_accumulate_masked(ctx, s->idx, &s->popt, k.alns, k.codes, pq, k.stride, k.lens, k.n, s->d_counts, s->indels, drop[c], stream);
         if (rc) { for (auto d : drop) cudaFree(d); return rc; }
     }
     QM_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));

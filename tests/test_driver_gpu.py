@@ -106,6 +106,24 @@ def test_driver_text_pileup_matches_oracle(sample_case):
     assert len(want) > 100000 and got == want
 
 
+def test_driver_baq_caps_counts_and_text_pileup(sample_case):
+    """--baq 1 (both mpileups of the reference flow run without -B): count TSV and text pileup equal the oracle's on the qualities its
+    BAQ restatement caps; without the flag the outputs above are the -B ones"""
+    from oracle import qmo_py
+    from tests import drvutil
+    c = sample_case
+    d = c["dir"]
+    tsv, txt = str(d / "baq.tsv"), str(d / "baq.text.mpileup")
+    drvutil.run_driver(["sample", "--ref", c["fa"], "--r1", c["r1"], "--r2", c["r2"], "--counts", tsv, "--mpileup", txt, "--baq", 1, "-t", 2])
+    capped = qmo_py.baq(c["ref"], c["alns"], c["codes"], c["quals"], c["lens"], flag=3)
+    want = qmo_py.pileup(c["ref"], c["alns"], c["codes"], capped, c["lens"])
+    assert not np.array_equal(want, c["counts"])
+    got = np.array([[int(x) for x in ln.rstrip("\n").split("\t")[4:]] for ln in list(open(tsv))[1:]], dtype=np.int32)
+    assert np.array_equal(got, want)
+    want_txt = qmo_py.mpileup_text(c["ref"], c["alns"], c["codes"], capped, c["lens"], list(c["W"].ref.names))
+    assert open(txt, "rb").read() == want_txt != open(c["txt"], "rb").read()
+
+
 def test_driver_count_tsv_matches_oracle(sample_case):
     W, counts = sample_case["W"], sample_case["counts"]
     rows = [ln.rstrip("\n").split("\t") for ln in open(sample_case["tsv"])]

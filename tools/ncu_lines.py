@@ -19,6 +19,8 @@ for r in rows:
     d = {}
     for k, v in zip(hdr, r):
         d.setdefault(k, v)
+    if not d["Line No"].strip():
+        continue                      # the SASS rows under a source line: counted with the line already
     try:
         ie = int(d["Instructions Executed"] or 0); ns = int(d["# Samples"] or 0); te = int(d["Thread Instructions Executed"] or 0)
     except ValueError:
