@@ -53,6 +53,7 @@ __device__ __forceinline__ int max_gap_for(const qm_opt &o, int qlen)
 //  * a k-mer whose canonical form misses the Bloom filter occurs on neither strand.
 // The read is packed once into shared memory (2 bits per base + an N bitmap); k-mers are cut out of the packed words,
 // so no rolling state ties one position to the next and whole runs can be skipped.
+constexpr int kWalkRange = 64;             // reads a warp of the walk kernel takes off the global cursor at a time
 constexpr int kBloomBatch = 8;             // filter look-ups in flight per thread behind a mismatch (collect_seeds)
 constexpr int kSeedThreads = 128;          // most a block may have (launch bounds); launched with kSeedThreadsDefault
 
@@ -147,6 +148,8 @@ struct SeedWalk {
     // S[] in global memory is only touched when a seed is created, looked for, or handed back
     // (two named copies, one per strand, picked with selects: an array indexed by the strand would live in local memory)
     struct Cur { int64_t diag; int idx, len, qnext; } cur0, cur1;
+    int last_ext;                   // start of the last k-mer that created or extended ANY seed (-2 = none yet): a hit at q can only
+                                    // continue a seed when last_ext == q - 1, otherwise the seed list need not be searched
     int miss_run;                   // the last filter look-up missed (or a tracked match just broke): the next look-ups come in batches
 };
 
@@ -173,7 +176,7 @@ __device__ __forceinline__ void seed_walk_init(SeedWalk &W, qm_seed *S, int len,
     W.tp[0] = W.tp[1] = W.tp[2] = W.tp[3] = 0;
     W.cur0.diag = W.cur1.diag = 0;
     W.cur0.idx = W.cur1.idx = -1; W.cur0.len = W.cur1.len = 0; W.cur0.qnext = W.cur1.qnext = 0;
-    W.miss_run = 0;
+    W.miss_run = 0; W.last_ext = -2;
 }
 
 // one trip: positions q .. of the read are decided (at least one), W.q moves on
@@ -210,9 +213,10 @@ __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt 
     auto add_hit = [&](int pass, int64_t p, int q, bool single) {
         const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
         const int64_t diag = rpos - q;
-        if (single && cur_is(pass, diag, q)) { cur_grow(pass, 1); return; }
+        if (single && cur_is(pass, diag, q)) { cur_grow(pass, 1); W.last_ext = q; return; }
         flush();
-        const int m = seed_find(S, n, diag, q, k);
+        const int m = W.last_ext >= q - 1 ? seed_find(S, n, diag, q, k) : -1;
+        W.last_ext = q;
         if (m >= 0) { const int len = S[m].len + 1; S[m].len = len; cur_set(pass, m, len, diag, q + 1); }
         else if (n < QM_MAX_SEEDS) {
             S[n].rbeg = rpos; S[n].qbeg = q; S[n].len = k;
@@ -244,6 +248,7 @@ __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt 
             m = m < m_b ? m : m_b; m = (int64_t)m > lim ? (int)lim : m;
         }
         if (m > 0) {
+            W.last_ext = q + m - 1;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 if (t >= nt) break;
@@ -300,6 +305,7 @@ __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt 
                 const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;                 // of the hit at q-1
                 if (cur_is(pass, rpos - (q - 1), q)) cur_grow(pass, m);
             };
+            W.last_ext = q + m - 1;
             if (two) { grow(0, trk_p); grow(1, trk_p2); trk_p += m; trk_p2 -= m; }
             else { grow(trk_pass, trk_p); trk_p = trk_pass ? trk_p - m : trk_p + m; }
             q += m;
@@ -370,7 +376,7 @@ __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt 
         if (!qm_idx_lookup_from(V, pass ? rc : fw, pass ? slot0[1] : slot0[0], pass ? ent0[1] : ent0[0], first, cnt)) continue;
         if (cnt > occ_cap) { n_hits += 2; ignored = true; continue; }          // ignored k-mer: nothing of this position is tracked
         for (uint32_t t = 0; t < cnt; ++t) {
-            const int64_t p = V.pos[first + t];
+            const int64_t p = cnt == 1 ? (int64_t)first : (int64_t)V.pos[first + t];
             add_hit(pass, p, q, cnt == 1);
             one_p = p; one_pass = pass; p_of[pass] = p;
             if (nt < 4) { if (nt == 0) tp[0] = p; else if (nt == 1) tp[1] = p; else if (nt == 2) tp[2] = p; else tp[3] = p; tpass |= (unsigned)pass << nt; }
@@ -385,20 +391,26 @@ __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt 
     ++q;
 }
 
-// the end of a read's walk: the growing seeds' lengths handed back, seeds ordered by (qbeg, rbeg); returns their number
-__device__ __forceinline__ int seed_walk_finish(SeedWalk &W)
+// seeds ordered by (qbeg, rbeg)
+__device__ __forceinline__ void seed_sort(qm_seed *S, int n)
 {
-    qm_seed *S = W.S;
-    if (W.cur0.idx >= 0) S[W.cur0.idx].len = W.cur0.len;
-    if (W.cur1.idx >= 0) S[W.cur1.idx].len = W.cur1.len;
-    const int n = W.n;
     for (int i = 1; i < n; ++i) {
         const qm_seed x = S[i];
         int j = i - 1;
         while (j >= 0 && (S[j].qbeg > x.qbeg || (S[j].qbeg == x.qbeg && S[j].rbeg > x.rbeg))) { S[j + 1] = S[j]; --j; }
         S[j + 1] = x;
     }
-    return n;
+}
+
+// the end of a read's walk: the growing seeds' lengths handed back; returns the number of seeds (in order of creation when
+// `sorted` is false: the persistent kernel leaves the ordering to plan_kernel, where all lanes of a warp sort at the same time)
+__device__ __forceinline__ int seed_walk_finish(SeedWalk &W, bool sorted = true)
+{
+    qm_seed *S = W.S;
+    if (W.cur0.idx >= 0) S[W.cur0.idx].len = W.cur0.len;
+    if (W.cur1.idx >= 0) S[W.cur1.idx].len = W.cur1.len;
+    if (sorted) seed_sort(S, W.n);
+    return W.n;
 }
 
 __device__ int collect_seeds(const IndexView &V, const qm_opt &o, const uint8_t *__restrict__ rd, int len, qm_seed *S,
@@ -638,9 +650,11 @@ template <int MINB>                                     // resident blocks of 64
 __global__ void __launch_bounds__(64, MINB)
 seed_walk_kernel(IndexView V, qm_opt o, const uint64_t *__restrict__ packed, const int32_t *__restrict__ lens, int64_t n,
                  qm_seed *__restrict__ seeds, int32_t *__restrict__ n_seeds, int *__restrict__ cursor, int n_words, int n_nwords,
-                 int bloom_batch, int refill)
+                 int bloom_batch, int refill, unsigned long long *__restrict__ dbg /* QM_SEED_DEBUG: per-read cycle / trip histograms, else NULL */)
 {
     extern __shared__ __align__(16) uint64_t s_read[];   // [n_words + n_nwords][threads]: the lane's current read
+    long long t_start = 0;
+    int n_steps = 0;
     PackedRead R;
     R.bits = s_read + threadIdx.x;
     R.nmask = s_read + (size_t)n_words * blockDim.x + threadIdx.x;
@@ -651,40 +665,63 @@ seed_walk_kernel(IndexView V, qm_opt o, const uint64_t *__restrict__ packed, con
     seed_walk_init(W, nullptr, 0, V.k);
     int64_t r = -1;                                      // the lane's read, -1 = none
     bool exhausted = false;
+    int w_next = 0, w_end = 0;                           // the warp's range of reads (the same in every lane)
+    bool w_dry = false;                                  // the global cursor has run past the last read
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
         const bool idle = r < 0;
         const unsigned idle_m = __ballot_sync(0xffffffffu, idle);
         const unsigned want_m = __ballot_sync(0xffffffffu, idle && !exhausted);
         if (idle_m == 0xffffffffu && want_m == 0u) break;
-        if (idle && !exhausted && (__popc(want_m) >= refill || idle_m == 0xffffffffu)) {
-            // the lanes in here are exactly want_m: one atomic for all of them
-            const int leader = __ffs((int)want_m) - 1;
-            int base = 0;
-            if ((int)lane == leader) base = atomicAdd(cursor, __popc(want_m));
-            base = __shfl_sync(want_m, base, leader);
-            const int64_t idx = base + __popc(want_m & ((1u << lane) - 1u));
-            if (idx >= n) exhausted = true;
-            else {
+        if (want_m != 0u && (__popc(want_m) >= refill || idle_m == 0xffffffffu)) {
+            // (Uniform branch: every lane keeps the same copy of the warp's range.)  The warp owns a range of reads [w_next, w_end)
+            // taken off the global cursor kWalkRange at a time: most refills are served without the round trip of a global atomic.
+            // When the range holds fewer reads than lanes want, the rest of the lanes are served on the next trip.
+            if (w_next >= w_end && !w_dry) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cursor, kWalkRange);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                w_next = base; w_end = base + kWalkRange;
+                if ((int64_t)w_next >= n) { w_dry = true; w_end = w_next; }
+                else if ((int64_t)w_end > n) w_end = (int)n;
+            }
+            const int need = __popc(want_m), have = w_end - w_next;
+            const int rank = __popc(want_m & ((1u << lane) - 1u));
+            const bool mine = idle && !exhausted;
+            const int64_t idx = (int64_t)w_next + rank;
+            w_next += need < have ? need : have;
+            if (mine && rank >= have) { if (w_dry) exhausted = true; }
+            else if (mine) {
                 r = idx;
                 const uint64_t *src = packed + r * pw;
                 for (int w = 0; w < pw; ++w) s_read[(size_t)w * blockDim.x + threadIdx.x] = __ldg(src + w);
                 seed_walk_init(W, seeds + r * QM_MAX_SEEDS, lens[r], V.k);
+                if (dbg) { t_start = clock64(); n_steps = 0; }
             }
         }
         if (r >= 0) {
-            if (W.q <= W.q_last) seed_walk_step(V, o, W, bloom, R, bloom_batch);
-            if (W.q > W.q_last) { n_seeds[r] = seed_walk_finish(W); r = -1; }
+            if (W.q <= W.q_last) { seed_walk_step(V, o, W, bloom, R, bloom_batch); ++n_steps; }
+            if (W.q > W.q_last) {
+                n_seeds[r] = seed_walk_finish(W, false); r = -1;
+                if (dbg) {
+                    const unsigned long long c = (unsigned long long)(clock64() - t_start);
+                    const int bc = 63 - __clzll((long long)(c | 1ull)), bs = 31 - __clz(n_steps | 1);
+                    atomicAdd(&dbg[bc & 31], 1ull); atomicAdd(&dbg[32 + (bc & 31)], c);
+                    atomicAdd(&dbg[64 + bs], 1ull); atomicAdd(&dbg[96 + bs], c);
+                }
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(128)
-plan_kernel(IndexView V, qm_opt o, int64_t n, const qm_seed *__restrict__ seeds, const int32_t *__restrict__ n_seeds,
-            uint16_t *__restrict__ plan, uint8_t *__restrict__ n_plan, ReadState *__restrict__ st)
+plan_kernel(IndexView V, qm_opt o, int64_t n, qm_seed *__restrict__ seeds, const int32_t *__restrict__ n_seeds,
+            uint16_t *__restrict__ plan, uint8_t *__restrict__ n_plan, ReadState *__restrict__ st, bool seeds_only)
 {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n) return;
+    seed_sort(seeds + r * QM_MAX_SEEDS, n_seeds[r]);
+    if (seeds_only) return;
     const int np = build_plan(V, o, seeds + r * QM_MAX_SEEDS, n_seeds[r], plan + r * QM_MAX_SEEDS);
     n_plan[r] = (uint8_t)np;
     ReadState s;
@@ -714,7 +751,7 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
     static const bool want_persist = !(getenv("QM_SEED_PERSIST") && atoi(getenv("QM_SEED_PERSIST")) == 0);
     static const int refill = getenv("QM_SEED_REFILL") ? std::max(1, std::min(32, atoi(getenv("QM_SEED_REFILL")))) : 8;                           // tuning knob
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    if (packed && cursor && want_persist && smem_packed <= 40 * 1024 && n <= 0x7fffffff - 4096) {
+    if (packed && cursor && want_persist && smem_packed <= 40 * 1024 && n <= 0x7fffffff - (1 << 22)) {
         cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int), stream);
         if (e != cudaSuccess) return e;
         pack_reads_kernel<<<blocks, threads, smem, stream>>>(codes, stride, lens, n, packed, n_words, n_nwords, staged);
@@ -731,8 +768,22 @@ static cudaError_t launch_seed_chain(qm_ctx *ctx, const IndexView &V, const qm_o
             if (ps < 1) ps = 1;
         }
         const unsigned walk_blocks = std::min<unsigned>((unsigned)((n + wt - 1) / wt), (unsigned)(ctx->sm_count * ps));
-        walk<<<walk_blocks, wt, smem_walk, stream>>>(V, o, packed, lens, n, seeds, n_seeds, cursor, n_words, n_nwords, bloom_batch, refill);
-        if (!seeds_only) plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(V, o, n, seeds, n_seeds, plan, n_plan, st);
+        static const bool debug = getenv("QM_SEED_DEBUG") != nullptr;       // diagnostics: where the walk's time goes, read by read
+        unsigned long long *dbg = nullptr;
+        if (debug) { cudaMalloc(&dbg, 128 * 8); cudaMemsetAsync(dbg, 0, 128 * 8, stream); }
+        walk<<<walk_blocks, wt, smem_walk, stream>>>(V, o, packed, lens, n, seeds, n_seeds, cursor, n_words, n_nwords, bloom_batch, refill, dbg);
+        if (debug) {
+            unsigned long long h[128];
+            cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream); cudaFree(dbg);
+            fprintf(stderr, "[qm seed walk] %lld reads, %u blocks; per read: log2(cycles) bucket: reads, share of all cycles | log2(trips) bucket: reads, mean cycles\n", (long long)n, walk_blocks);
+            unsigned long long tot = 0;
+            for (int b = 0; b < 32; ++b) tot += h[32 + b];
+            for (int b = 0; b < 32; ++b)
+                if (h[b] || h[64 + b])
+                    fprintf(stderr, "[qm seed walk]  2^%-2d cycles: %9llu reads %5.1f %% | 2^%-2d trips: %9llu reads, mean %10.0f cycles, %5.1f %%\n", b, h[b],
+                            tot ? 100.0 * h[32 + b] / tot : 0.0, b, h[64 + b], h[64 + b] ? (double)h[96 + b] / h[64 + b] : 0.0, tot ? 100.0 * h[96 + b] / tot : 0.0);
+        }
+        plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(V, o, n, seeds, n_seeds, plan, n_plan, st, seeds_only);
         return cudaGetLastError();
     }
     seed_chain_kernel<<<blocks, threads, smem, stream>>>(

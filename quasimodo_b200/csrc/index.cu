@@ -62,7 +62,8 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         const uint64_t key = km[i].first;
         uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> v.shift;
         while (table[h].x != 0xffffffffu || table[h].y != 0xffffffffu) h = (h + 1) & v.mask;
-        table[h] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)i, (uint32_t)(j - i));
+        // (a k-mer with ONE occurrence carries the position itself instead of its slot in pos[]: the seeding walk saves a dependent look-up)
+        table[h] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)(j - i == 1 ? km[i].second : i), (uint32_t)(j - i));
         i = j;
     }
     // uniqueness bitmap: k-mer occurs once and its reverse complement never (see IndexView::uniq)

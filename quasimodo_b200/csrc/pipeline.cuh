@@ -6,7 +6,8 @@
 // ---- reference index as kernels see it (passed by value) ----
 struct IndexView {
     const uint8_t *refb;      // forward strand, one base code (0..3) per byte, contigs concatenated
-    const uint4 *table;       // open addressing: {key lo, key hi, first, count}; empty = key all-ones
+    const uint4 *table;       // open addressing: {key lo, key hi, first, count}; empty = key all-ones; first = slot of the k-mer's
+                              // occurrences in pos[], or, when count == 1, the position itself
     const uint32_t *pos;      // occurrence lists (ascending forward positions)
     const uint32_t *uniq;     // bit p: the k-mer starting at forward position p occurs exactly once in the reference
                               // and its reverse complement does not occur at all (both look-ups of a read k-mer equal
