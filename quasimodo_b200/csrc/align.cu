@@ -179,6 +179,49 @@ __device__ __forceinline__ void seed_walk_init(SeedWalk &W, qm_seed *S, int len,
     W.miss_run = 0; W.last_ext = -2;
 }
 
+// the read's seed list and the two growing seeds (one per strand)
+struct SeedList {
+    const IndexView &V;
+    SeedWalk &W;
+    __device__ __forceinline__ void flush() const
+    {
+        if (W.cur0.idx >= 0) W.S[W.cur0.idx].len = W.cur0.len;
+        if (W.cur1.idx >= 0) W.S[W.cur1.idx].len = W.cur1.len;
+    }
+    // is strand `pass` growing a seed on `diag` whose next k-mer starts at qq?
+    __device__ __forceinline__ bool cur_is(int pass, int64_t diag, int qq) const
+    {
+        const int idx = pass ? W.cur1.idx : W.cur0.idx, qn = pass ? W.cur1.qnext : W.cur0.qnext;
+        const int64_t d = pass ? W.cur1.diag : W.cur0.diag;
+        return idx >= 0 && d == diag && qn == qq;
+    }
+    __device__ __forceinline__ void cur_grow(int pass, int m) const
+    {
+        if (pass) { W.cur1.len += m; W.cur1.qnext += m; } else { W.cur0.len += m; W.cur0.qnext += m; }
+    }
+    __device__ __forceinline__ void cur_set(int pass, int idx, int len, int64_t diag, int qnext) const
+    {
+        if (pass) { W.cur1.idx = idx; W.cur1.len = len; W.cur1.diag = diag; W.cur1.qnext = qnext; }
+        else { W.cur0.idx = idx; W.cur0.len = len; W.cur0.diag = diag; W.cur0.qnext = qnext; }
+    }
+    __device__ __forceinline__ void add_hit(int pass, int64_t p, int q, bool single) const
+    {
+        const int k = V.k;
+        qm_seed *S = W.S;
+        const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
+        const int64_t diag = rpos - q;
+        if (single && cur_is(pass, diag, q)) { cur_grow(pass, 1); W.last_ext = q; return; }
+        flush();
+        const int m = W.last_ext >= q - 1 ? seed_find(S, W.n, diag, q, k) : -1;
+        W.last_ext = q;
+        if (m >= 0) { const int len = S[m].len + 1; S[m].len = len; cur_set(pass, m, len, diag, q + 1); }
+        else if (W.n < QM_MAX_SEEDS) {
+            S[W.n].rbeg = rpos; S[W.n].qbeg = q; S[W.n].len = k;
+            cur_set(pass, W.n++, k, diag, q + 1);
+        }
+    }
+};
+
 // one trip: positions q .. of the read are decided (at least one), W.q moves on
 __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt &o, SeedWalk &W, const uint32_t *__restrict__ bloom /* V.bloom, or NULL */,
                                                const PackedRead &R, int bloom_batch)
@@ -193,36 +236,12 @@ __device__ __forceinline__ void seed_walk_step(const IndexView &V, const qm_opt 
     int64_t &trk_p = W.trk_p, &trk_p2 = W.trk_p2;
     int64_t (&tp)[4] = W.tp;
     unsigned &tpass = W.tpass;
-    auto flush = [&]() {
-        if (W.cur0.idx >= 0) S[W.cur0.idx].len = W.cur0.len;
-        if (W.cur1.idx >= 0) S[W.cur1.idx].len = W.cur1.len;
-    };
-    // is strand `pass` growing a seed on `diag` whose next k-mer starts at qq?
-    auto cur_is = [&](int pass, int64_t diag, int qq) {
-        const int idx = pass ? W.cur1.idx : W.cur0.idx, qn = pass ? W.cur1.qnext : W.cur0.qnext;
-        const int64_t d = pass ? W.cur1.diag : W.cur0.diag;
-        return idx >= 0 && d == diag && qn == qq;
-    };
-    auto cur_grow = [&](int pass, int m) {
-        if (pass) { W.cur1.len += m; W.cur1.qnext += m; } else { W.cur0.len += m; W.cur0.qnext += m; }
-    };
-    auto cur_set = [&](int pass, int idx, int len, int64_t diag, int qnext) {
-        if (pass) { W.cur1.idx = idx; W.cur1.len = len; W.cur1.diag = diag; W.cur1.qnext = qnext; }
-        else { W.cur0.idx = idx; W.cur0.len = len; W.cur0.diag = diag; W.cur0.qnext = qnext; }
-    };
-    auto add_hit = [&](int pass, int64_t p, int q, bool single) {
-        const int64_t rpos = pass ? 2 * V.l_pac - p - k : p;
-        const int64_t diag = rpos - q;
-        if (single && cur_is(pass, diag, q)) { cur_grow(pass, 1); W.last_ext = q; return; }
-        flush();
-        const int m = W.last_ext >= q - 1 ? seed_find(S, n, diag, q, k) : -1;
-        W.last_ext = q;
-        if (m >= 0) { const int len = S[m].len + 1; S[m].len = len; cur_set(pass, m, len, diag, q + 1); }
-        else if (n < QM_MAX_SEEDS) {
-            S[n].rbeg = rpos; S[n].qbeg = q; S[n].len = k;
-            cur_set(pass, n++, k, diag, q + 1);
-        }
-    };
+    const SeedList SL = {V, W};
+    auto flush = [&]() { SL.flush(); };
+    auto cur_is = [&](int pass, int64_t diag, int qq) { return SL.cur_is(pass, diag, qq); };
+    auto cur_grow = [&](int pass, int m) { SL.cur_grow(pass, m); };
+    auto cur_set = [&](int pass, int idx, int len, int64_t diag, int qnext) { SL.cur_set(pass, idx, len, diag, qnext); };
+    auto add_hit = [&](int pass, int64_t p, int q, bool single) { SL.add_hit(pass, p, q, single); };
     if (nt >= 2) {
         // every hit of position q-1 is tracked: position q+j has exactly these hits, one step further, as long as the new
         // read base continues ALL of them and the index says the reference k-mer there occurs nt times in total

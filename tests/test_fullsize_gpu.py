@@ -185,3 +185,91 @@ def test_call_larger_than_one_internal_chunk(ctx, full):
         s.close()
     assert np.array_equal(total, whole)
     assert torch.equal(torch.cat(parts), whole_alns)
+
+
+def _run_whole(ctx, W, n_pairs, L, opt, calls=1, records=True):
+    """simulate n_pairs on the device and run them through one qm_sample in `calls` library calls -> (counts, alns or None, stats, pes, tensors)"""
+    import torch
+    from quasimodo_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.from_numpy(W.src_codes).to(dev)
+    c = torch.empty((2 * n_pairs, L), dtype=torch.uint8, device=dev)
+    q = torch.empty_like(c)
+    step = 1 << 21
+    for o in range(0, n_pairs, step):
+        m = min(step, n_pairs - o)
+        ctx.simulate_pairs(W, o, m, g, c[2 * o:2 * (o + m)], q[2 * o:2 * (o + m)], 0)
+    lens = torch.full((2 * n_pairs,), L, dtype=torch.int32, device=dev)
+    idx = ctx.index(W.ref, 31)
+    s = ctx.sample(idx, opt)
+    d_alns = torch.zeros(2 * n_pairs * 128, dtype=torch.uint8, device=dev) if records else None
+    per = (n_pairs + calls - 1) // calls
+    for k in range(calls):
+        lo, hi = k * per, min(n_pairs, (k + 1) * per)
+        s.add_pairs(c[2 * lo:2 * hi], q[2 * lo:2 * hi], lens[2 * lo:2 * hi], pair_id0=lo,
+                    d_alns=None if d_alns is None else d_alns[2 * lo * 128:2 * hi * 128])
+    counts, stats, pes = s.counts_host(), s.stats(), s.get_pestat()
+    s.close()
+    alns = None if d_alns is None else d_alns.cpu().numpy().view(_lib.ALN_DTYPE)
+    return counts, alns, stats, pes, (idx, c, q, lens)
+
+
+def test_full_size_config5_long_reads_with_indels(ctx):
+    """BASELINE configs[4] at size: 2 M pairs of 2 x 250 bp with indels, band 200.  Conservation between records and tensor,
+    deletion / insertion events between CIGARs and channels 12 / 13 / 5 / 11, two shards add up to the whole."""
+    from quasimodo_b200 import _lib, workloads
+    n = 2_000_000
+    W = workloads.config5(n)
+    opt = _lib.default_opt()
+    opt.w = 200
+    counts, alns, stats, pes, (idx, c, q, lens) = _run_whole(ctx, W, n, 250, opt)
+    a, b = conservation(alns, counts)
+    assert a == b and a[0] > 3_000_000
+    assert stats[0] == n and stats[1] > 40_000_000_000             # ~29 k extension cells per pair
+    f = alns["flag"].astype(np.int64)
+    nc = alns["n_cigar"].astype(np.int64)
+    ok = ((f & (0x4 | 0x100 | 0x200 | 0x400)) == 0) & (nc != 0) & (nc != 255) & ~(((f & 1) != 0) & ((f & 2) == 0))
+    cig = alns["cigar"].astype(np.int64)[ok]
+    live = np.arange(cig.shape[1])[None, :] < nc[ok][:, None]
+    after_m = np.cumsum(((cig & 0xf) == 0) & live, axis=1) > 0           # the event channels need an aligned base in front
+    n_ins, n_del = int((((cig & 0xf) == 1) & live & after_m).sum()), int((((cig & 0xf) == 2) & live & after_m).sum())
+    del_bases = int(((cig >> 4) * (((cig & 0xf) == 2) & live)).sum())
+    assert n_ins > 50_000 and n_del > 50_000
+    assert int(counts[:, 12].sum()) == n_ins and int(counts[:, 13].sum()) == n_del
+    assert int(counts[:, 5].sum() + counts[:, 11].sum()) == del_bases
+    # two shards, the second primed with the sample's insert-size prefix
+    total = np.zeros_like(counts)
+    npre = _lib.PESTAT_PAIRS
+    for k in range(2):
+        s = ctx.sample(idx, opt)
+        lo, hi = k * n // 2, (k + 1) * n // 2
+        if k:
+            s.estimate_pestat(c[:2 * npre], lens[:2 * npre])
+        s.add_pairs(c[2 * lo:2 * hi], q[2 * lo:2 * hi], lens[2 * lo:2 * hi], pair_id0=lo)
+        assert s.get_pestat().tobytes() == pes.tobytes()
+        total += s.counts_host()
+        s.close()
+    assert np.array_equal(total, counts)
+    idx.close()
+
+
+def test_config4_deep_sample_in_several_calls(ctx):
+    """BASELINE configs[3]'s sample (TM-1-50, one reference, 60,000x when whole) at 6 M pairs: three library calls of 2 M pairs give
+    the tensor of one call of 6 M (the batching of a 50 M-pair sample does not show in the result), conservation holds, and the depth
+    is what the pair count implies"""
+    from quasimodo_b200 import _lib, workloads
+    n = 6_000_000
+    W = workloads.config4(50_000_000)
+    opt = _lib.default_opt()
+    c3, alns, stats3, pes3, (idx, c, q, lens) = _run_whole(ctx, W, n, 150, opt, calls=3)
+    a, b = conservation(alns, c3)
+    assert a == b and a[0] > 10_000_000
+    del alns
+    s = ctx.sample(idx, opt)
+    s.add_pairs(c, q, lens)
+    assert np.array_equal(s.counts_host(), c3)
+    assert s.stats() == stats3 and s.get_pestat().tobytes() == pes3.tobytes()
+    s.close()
+    depth = c3[:, 14].sum() / W.ref.total
+    assert 0.8 * 2 * n * 150 / W.ref.total < depth <= 2 * n * 150 / W.ref.total
+    idx.close()
