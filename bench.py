@@ -468,7 +468,7 @@ def run_ours(args):
     gcups_peak = dpx_gops * 2.0 / 9.0                   # 2 packed cells per lane-instr, 9 DPX-class instr per cell
     traffic = None
     try:                                                   # per-launch DRAM bytes of the extension kernel from the committed ncu capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ext2_traffic.json")))["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ext3_traffic.json")))["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
     ext_ms = stage_ms["extend"]
@@ -479,7 +479,7 @@ def run_ours(args):
                 "bound": "int-issue (DPX), not hbm/tensor",
                 "achieved": gcups, "peak": gcups_peak, "unit": "GCUPS", "frac": gcups / gcups_peak if gcups_peak else None,
                 "traffic": traffic, "traffic_how": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per extension-kernel launch "
-                                               "(profiles/ext2_traffic.json); the kernel is issue-bound, not DRAM-bound",
+                                               "(profiles/ext3_traffic.json: the class 65-80 launch of a sample's first round); the kernel is issue-bound, not DRAM-bound",
                 "avg_launch_ms": ext_ms / max(1, stage_launch["extend"]),
                 "work": f"{cells_total} executed ksw_extend2 cells in {K} steps ({cells_total / max(1, Pk):.0f} cells/pair)",
                 "cells_per_pair": cells_total / max(1, Pk),
@@ -499,9 +499,15 @@ def run_ours(args):
     seed_ms = stage_ms["seed_chain"]
     seed_b = 2 * ((L + 3) // 4)                         # packed read bytes read once (seed records are reported apart)
     seed_gbs = seed_b * Pk / seed_ms / 1e6 if seed_ms > 0 else 0.0
-    roofline_seed = {"kernel": "seed_chain_kernel", "bound": "hbm (algorithmic); in practice L2 probe latency + integer issue",
-                     "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": seed_gbs / hbm_peak, "traffic": None,
-                     "work": f"{seed_b} B/pair of 2-bit packed read bases x {Pk} pairs; reads arrive 1 B/base ({2 * L} B/pair actually read)"}
+    seed_traffic = None
+    try:
+        seed_traffic = json.load(open(os.path.join(ROOT, "profiles", "seed_traffic.json")))["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline_seed = {"kernel": "pack_reads_kernel + seed_walk_kernel + plan_kernel", "bound": "hbm (algorithmic); in practice the latency of dependent L2 look-ups at ~11 of 32 lanes",
+                     "achieved": seed_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": seed_gbs / hbm_peak, "traffic": seed_traffic,
+                     "work": f"{seed_b} B/pair of 2-bit packed read bases x {Pk} pairs; the reads arrive 1 B/base ({2 * L} B/pair), are packed once by "
+                             f"pack_reads_kernel and walked from the packed copy"}
     launches = int(sum(stage_launch.values()))
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if plan.strong else "weak", "vs_baseline": None,
