@@ -397,6 +397,8 @@ def run_ours(args):
                 h_nm[o:o + cp.shape[0]].copy_((isn.view(cp.shape[0], Lp // 8, 8).to(torch.uint8) * w8).sum(-1, dtype=torch.uint8))
         e2e_times, d2h = [], 0
 
+        h_alns = [None]                                 # set for the e2e_records pass: the 128-byte records come back too
+
         def step_host(i):
             j = i % n_used
             W = wl[j]
@@ -409,7 +411,7 @@ def run_ours(args):
             for o in range(0, P, 4 * CHUNK):            # the library chunks and double-buffers its copies itself
                 n = min(4 * CHUNK, P - o)
                 s.add_pairs_host_packed(h_b2[2 * o:2 * (o + n)], h_nm[2 * o:2 * (o + n)], h_quals[2 * o:2 * (o + n)], h_lens[2 * o:2 * (o + n)],
-                                        pair_id0=lo + o)
+                                        pair_id0=lo + o, h_alns=None if h_alns[0] is None else h_alns[0][2 * o * 128:2 * (o + n) * 128])
             r = finish_sample(j, s, key)
             nb = 0
             if r is not None:
@@ -440,14 +442,38 @@ def run_ours(args):
             step_host(i if i % n_used == last else last)
         e2e_stage_ms, _ = ctx.profile_collect()
         ctx.profile_enable(False)
-        te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
+        # the same step with the alignment records (128 B per read: what the BAM writer needs) returned to pinned host memory inside the
+        # timed region; 3 steps on the buffers the last step left in place
+        rec_times = []
+        try:
+            if P > 8_000_000:
+                raise RuntimeError("records pass skipped: more than 2 GB of records per step")
+            h_alns[0] = torch.empty(2 * P * 128, dtype=torch.uint8).pin_memory()
+            for i in range(4):
+                barrier()
+                t0 = time.perf_counter()
+                step_host(last)
+                barrier()
+                if i:
+                    rec_times.append(time.perf_counter() - t0)
+        except RuntimeError:
+            rec_times = []
+        h_alns[0] = None
+        te = torch.tensor([sum(e2e_times), sum(rec_times)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        t_rec = float(te[1].item())
+        te = te[:1]
         e2e = {"value": plan.total * K / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * P * (h_b2.shape[1] + h_nm.shape[1] + L) + 4 * 2 * P), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(te.item()) / K * 1e3, "step_ms": [round(x * 1e3, 3) for x in e2e_times],
                "stages_ms_per_step": {k: v / 2 for k, v in e2e_stage_ms.items()},
-               "api": "qm_sample_add_pairs_host_packed (2-bit bases + N mask + 1 B/base qualities; + qm_call_snps, qm_eval_calls), pinned host buffers"}
+               "api": "qm_sample_add_pairs_host_packed (2-bit bases + N mask + 1 B/base qualities; + qm_call_snps, qm_eval_calls), pinned host buffers",
+               "with_records": None if not rec_times else {
+                   "value": plan.total * len(rec_times) / t_rec, "unit": UNIT, "ms_per_step": t_rec / len(rec_times) * 1e3,
+                   "d2h_bytes_per_step": int(d2h + 2 * P * 128),
+                   "what": "the same call with h_alns: every read's 128-byte alignment record (position, flag, MAPQ, CIGAR, mate fields) copied back to "
+                           "pinned host memory inside the timed region, as the BAM writer of qm_driver needs them"}}
 
     if rank != 0:
         for x in smp.values():

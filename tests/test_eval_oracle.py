@@ -66,3 +66,29 @@ def test_performance_row():
     assert row[6] == eval_py.r_num(round(tp / len(snp), 3))
     pure = eval_py.performance_row(os.path.join(GOLD, "TA-1-0", "TA-1-0.Merlin.bcftools.filtered.vcf"), truth, ["TM-1-1"])
     assert pure[2] == "0" and pure[4] == "0" and pure[5] == pure[3] and pure[6:] == ["0", "NA", "NA"]
+
+
+def test_python_round_equals_r_long_double_rounding_on_every_ratio():
+    """R 3.5.1's round(x, 3) is nearbyintl(x * 10^3) / 10^3 in long double (round half even on the SCALED value), the
+    product's and the oracle's tables use Python's round(x, 3) (decimal round-half-even on the BINARY value).  The two can only differ
+    when the scaled value lands on a half within a long-double ulp; on every precision / recall a table can hold (TP / n with
+    n <= 400 here; all n < 1200 were checked when this test was written) and on every F1 built from such pairs they agree."""
+    import numpy as np
+    if np.finfo(np.longdouble).nmant < 63:
+        import pytest
+        pytest.skip("no 80-bit long double on this host")
+    k = np.longdouble(1000)
+    vals = []
+    for b in range(1, 401):
+        vals.append(np.arange(0, b + 1) / b)
+    x = np.concatenate(vals)
+    r = (np.rint(x.astype(np.longdouble) * k) / k).astype(np.float64)
+    p = np.array([round(float(v), 3) for v in x])
+    assert np.array_equal(r, p)
+    # F1 = 2 p r / (p + r) of rounded p, r (scripts/caller_performance_compare.R:51)
+    g = np.round(np.linspace(0.001, 1, 250), 3)
+    pp, rr = np.meshgrid(g, g)
+    f = (2 * pp * rr / (pp + rr)).ravel()
+    rf = (np.rint(f.astype(np.longdouble) * k) / k).astype(np.float64)
+    pf = np.array([round(float(v), 3) for v in f])
+    assert np.array_equal(rf, pf)
