@@ -1570,7 +1570,10 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
                 for (int c = 0; c < kExtClasses; ++c) fprintf(stderr, " %d", h_ctr->class_count[c]);
                 fprintf(stderr, "\n");
             }
-            static const int tail_min = getenv("QM_TAIL_MIN") ? atoi(getenv("QM_TAIL_MIN")) : kTailMinTasks;       // tuning knob
+            // (both thresholds follow the batch: they were tuned on 4 M reads, and a 200 k-read batch that switched modes at the same task
+            // counts spent its whole first round in the speculative finish: 9.2 against 7.6 ms per 100 k pairs)
+            static const int tail_env = getenv("QM_TAIL_MIN") ? atoi(getenv("QM_TAIL_MIN")) : -1;       // tuning knob
+            const int tail_min = tail_env >= 0 ? tail_env : (int)std::min<int64_t>(kTailMinTasks, std::max<int64_t>(2048, nb / 64));
             if (h_ctr->n_tasks < tail_min) {
                 // few reads left: finish them on the device, one warp per read, no more round trips
                 sp = qm_prof_begin(ctx, QM_ST_EXTEND, st);
@@ -1591,7 +1594,8 @@ int qm_align_se(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const uint8
             // between the two thresholds: every remaining seed ahead of the state machine (spec_finish_batch).  Below tail_min the
             // serial warp-per-read tail above is quicker: two launch groups of the throughput kernels cost ~1 ms whatever they hold.
             static const bool spec_on = !(getenv("QM_SPEC") && atoi(getenv("QM_SPEC")) == 0);       // QM_SPEC=0: the serial tail of round 1
-            static const int spec_min = getenv("QM_SPEC_MIN") ? std::min(atoi(getenv("QM_SPEC_MIN")), kSpecMinTasks) : kSpecMinTasks;   // tuning knob
+            static const int spec_env = getenv("QM_SPEC_MIN") ? std::min(atoi(getenv("QM_SPEC_MIN")), kSpecMinTasks) : -1;   // tuning knob
+            const int spec_min = spec_env >= 0 ? spec_env : (int)std::min<int64_t>(kSpecMinTasks, std::max<int64_t>(8192, nb / 8));
             if (spec_on && h_ctr->n_tasks < spec_min) {
                 rc = spec_finish_batch(ctx, idx, opt, P, codes, stride, lens, sc, d_regs + b0 * QM_MAX_REGS, d_n_regs + b0, d_cells, h_ctr,
                                        h_ctr->n_tasks, st);
