@@ -11,6 +11,8 @@
 // pair stream is split into batches or across GPUs.
 #include <stdlib.h>
 #include <vector>
+#include <thread>
+#include <algorithm>
 #include "pipeline.cuh"
 
 namespace {
@@ -587,14 +589,25 @@ int qm_pack_reads_host(const uint8_t *h_codes, int32_t stride, int64_t n_reads, 
 {
     if (stride <= 0 || n_reads < 0 || (n_reads > 0 && (!h_codes || !h_bases2 || !h_nmask))) return QM_EINVAL;
     const int sp = (stride + 3) >> 2, sm = (stride + 7) >> 3;
-    for (int64_t r = 0; r < n_reads; ++r) {
-        const uint8_t *c = h_codes + r * stride;
-        uint8_t *b = h_bases2 + r * sp, *m = h_nmask + r * sm;
-        memset(b, 0, (size_t)sp); memset(m, 0, (size_t)sm);
-        for (int j = 0; j < stride; ++j) {
-            if (c[j] > 3) m[j >> 3] |= (uint8_t)(1u << (j & 7));
-            else b[j >> 2] |= (uint8_t)(c[j] << (2 * (j & 3)));
+    auto rows = [=](int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; ++r) {
+            const uint8_t *c = h_codes + r * stride;
+            uint8_t *b = h_bases2 + r * sp, *m = h_nmask + r * sm;
+            memset(b, 0, (size_t)sp); memset(m, 0, (size_t)sm);
+            for (int j = 0; j < stride; ++j) {
+                if (c[j] > 3) m[j >> 3] |= (uint8_t)(1u << (j & 7));
+                else b[j >> 2] |= (uint8_t)(c[j] << (2 * (j & 3)));
+            }
         }
+    };
+    // (the FASTQ side of a host entry: rows are independent, a few threads keep the packing out of the file-level time)
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int64_t nt = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hw ? hw : 4, 16), n_reads / 65536));
+    if (nt == 1) rows(0, n_reads);
+    else {
+        std::vector<std::thread> pool;
+        for (int64_t t = 0; t < nt; ++t) pool.emplace_back(rows, n_reads * t / nt, n_reads * (t + 1) / nt);
+        for (auto &th : pool) th.join();
     }
     return QM_OK;
 }
