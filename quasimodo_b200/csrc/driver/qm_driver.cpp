@@ -165,17 +165,20 @@ struct FastqPairReader {
         if (s.size() != q.size()) die(2, "%s: sequence and quality lengths differ in %s", r.path.c_str(), h.c_str());
         return true;
     }
-    static std::string clean_name(const std::string &h)
-    {   // bwa: up to the first whitespace, a trailing /1 or /2 dropped
-        size_t e = 1;
-        while (e < h.size() && !isspace((unsigned char)h[e])) ++e;
-        std::string n = h.substr(1, e - 1);
-        if (n.size() > 2 && n[n.size() - 2] == '/' && (n.back() == '1' || n.back() == '2')) n.resize(n.size() - 2);
-        return n;
-    }
 };
 
-struct RawPair { std::string name, s[2], q[2]; };
+// one mate file's share of a batch, flat: record i's bases are seq[soff[i] .. soff[i+1]), its qualities the same range of qual, its
+// cleaned name names + noff[i] (NUL-terminated).  No allocation per record: the line buffers are reused, the arrays grow amortised.
+struct Side {
+    std::vector<char> names, seq, qual;
+    std::vector<uint64_t> soff;
+    std::vector<uint32_t> noff;
+    size_t n = 0;
+    void clear() { names.clear(); seq.clear(); qual.clear(); soff.assign(1, 0); noff.clear(); n = 0; }
+    size_t len(size_t i) const { return (size_t)(soff[i + 1] - soff[i]); }
+};
+
+struct RawBatch { Side a, b; size_t size() const { return a.n; } };
 
 int g_threads = 8;                                  // -t: host threads for parsing, packing, record encoding, BGZF
 
@@ -191,31 +194,31 @@ template <class F> void parallel_ranges(size_t n, F fn)
 
 // reads up to max_pairs pairs; mates are matched by file order (bwa's rule), not by name.  The two files are read (and
 // inflated) side by side: the second mate's file has a thread of its own.
-bool read_batch(FastqPairReader &fr, int64_t max_pairs, std::vector<RawPair> &out)
+bool read_batch(FastqPairReader &fr, int64_t max_pairs, RawBatch &out)
 {
-    struct Rec { std::string h, s, q; };
-    auto side = [max_pairs](LineReader &r, std::vector<Rec> &v) {
-        std::string p;
-        Rec rec;
-        while ((int64_t)v.size() < max_pairs && FastqPairReader::record(r, rec.h, rec.s, p, rec.q)) { v.push_back(std::move(rec)); rec = Rec(); }
-    };
-    std::vector<Rec> a, b;
-    std::thread t2([&]() { side(fr.r2, b); });
-    side(fr.r1, a);
-    t2.join();
-    if (a.size() < b.size()) die(2, "%s has more records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
-    if (a.size() > b.size()) die(2, "%s has fewer records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
-    out.clear();
-    out.resize(a.size());
-    parallel_ranges(a.size(), [&](size_t i0, size_t i1) {
-        for (size_t i = i0; i < i1; ++i) {
-            RawPair &rp = out[i];
-            rp.name = FastqPairReader::clean_name(a[i].h);
-            rp.s[0] = std::move(a[i].s); rp.q[0] = std::move(a[i].q);
-            rp.s[1] = std::move(b[i].s); rp.q[1] = std::move(b[i].q);
+    auto side = [max_pairs](LineReader &r, Side &v) {
+        std::string h, s, p, q;
+        v.clear();
+        while ((int64_t)v.n < max_pairs && FastqPairReader::record(r, h, s, p, q)) {
+            // bwa: the name up to the first whitespace, a trailing /1 or /2 dropped
+            size_t e = 1;
+            while (e < h.size() && !isspace((unsigned char)h[e])) ++e;
+            if (e > 3 && h[e - 2] == '/' && (h[e - 1] == '1' || h[e - 1] == '2')) e -= 2;
+            v.noff.push_back((uint32_t)v.names.size());
+            v.names.insert(v.names.end(), h.begin() + 1, h.begin() + (ptrdiff_t)e);
+            v.names.push_back('\0');
+            v.seq.insert(v.seq.end(), s.begin(), s.end());
+            v.qual.insert(v.qual.end(), q.begin(), q.end());
+            v.soff.push_back((uint64_t)v.seq.size());
+            ++v.n;
         }
-    });
-    return !out.empty();
+    };
+    std::thread t2([&]() { side(fr.r2, out.b); });
+    side(fr.r1, out.a);
+    t2.join();
+    if (out.a.n < out.b.n) die(2, "%s has more records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
+    if (out.a.n > out.b.n) die(2, "%s has fewer records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
+    return out.a.n > 0;
 }
 
 struct Lib {
@@ -226,7 +229,7 @@ struct Lib {
     }
 };
 
-void pack_batch(Lib &L, const std::vector<RawPair> &raw, bool want_alns, Batch &b)
+void pack_batch(Lib &L, const RawBatch &raw, bool want_alns, Batch &b)
 {
     static uint8_t lut[256];
     static bool init = false;
@@ -235,9 +238,11 @@ void pack_batch(Lib &L, const std::vector<RawPair> &raw, bool want_alns, Batch &
         lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
         init = true;
     }
+    const Side *sd[2] = {&raw.a, &raw.b};
     b.n_pairs = (int64_t)raw.size();
     size_t mx = 1;
-    for (auto &r : raw) mx = std::max(mx, std::max(r.s[0].size(), r.s[1].size()));
+    for (int m = 0; m < 2; ++m)
+        for (size_t i = 0; i < sd[m]->n; ++i) mx = std::max(mx, sd[m]->len(i));
     if (mx > 500) die(2, "read of %zu bases: reads longer than 500 bp are not supported", mx);
     b.stride = (int32_t)((mx + 15) & ~(size_t)15);
     const size_t nb = (size_t)2 * b.n_pairs * b.stride;
@@ -246,18 +251,15 @@ void pack_batch(Lib &L, const std::vector<RawPair> &raw, bool want_alns, Batch &
     L.check(qm_host_alloc(L.ctx, nb, &p), "qm_host_alloc"); b.quals = (uint8_t *)p;
     L.check(qm_host_alloc(L.ctx, (size_t)2 * b.n_pairs * sizeof(int32_t), &p), "qm_host_alloc"); b.lens = (int32_t *)p;
     if (want_alns) { L.check(qm_host_alloc(L.ctx, (size_t)2 * b.n_pairs * sizeof(qm_aln), &p), "qm_host_alloc"); b.alns = (qm_aln *)p; }
-    b.name_off.reserve(raw.size());
-    for (size_t i = 0; i < raw.size(); ++i) {
-        b.name_off.push_back((uint32_t)b.names.size());
-        b.names.append(raw[i].name);
-        b.names.push_back('\0');
-    }
+    // the pair's name is the first mate's (bwa prints one name for both records)
+    b.names.assign(raw.a.names.begin(), raw.a.names.end());
+    b.name_off = raw.a.noff;
     parallel_ranges(raw.size(), [&](size_t i0, size_t i1) {
         for (size_t i = i0; i < i1; ++i) {
             for (int m = 0; m < 2; ++m) {
-                const std::string &s = raw[i].s[m], &q = raw[i].q[m];
+                const char *s = sd[m]->seq.data() + sd[m]->soff[i], *q = sd[m]->qual.data() + sd[m]->soff[i];
                 uint8_t *c = b.codes + (2 * i + m) * b.stride, *qq = b.quals + (2 * i + m) * b.stride;
-                const size_t n = s.size();
+                const size_t n = sd[m]->len(i);
                 for (size_t j = 0; j < n; ++j) {
                     c[j] = lut[(unsigned char)s[j]];
                     const int v = (int)(unsigned char)q[j] - 33;
@@ -938,7 +940,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     FastqPairReader fr(a.get("r1"), a.get("r2"));
     std::deque<Batch> batches;                        // (a deque: the workers hold references while more batches arrive)
     std::vector<int64_t> first_read;
-    std::vector<RawPair> raw;
+    RawBatch raw;
     int64_t n_pairs = 0, kept = 0;
     FILE *f1 = nullptr, *f2 = nullptr;
     if (decontam) {
@@ -961,7 +963,6 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         batches.emplace_back();
         Batch &b = batches.back();
         pack_batch(Ls[d], raw, keep, b);
-        raw.clear();
         const int64_t pair0 = n_pairs;
         if (n_batches == 0 || decontam) {
             // (later batches go to a worker thread, also with one GPU: the next batch is read and packed while this one is on the device)
@@ -1182,27 +1183,30 @@ int cmd_bam_from_records(const Args &a, const std::string &cmdline)
     load_refs(a.get("ref"), g);
     std::vector<qm_aln> alns = read_binary<qm_aln>(a.get("alns"));
     FastqPairReader fr(a.get("r1"), a.get("r2"));
-    std::vector<RawPair> raw;
+    RawBatch raw;
     read_batch(fr, (int64_t)1 << 40, raw);
     if (raw.size() * 2 != alns.size()) die(2, "%zu records for %zu pairs", alns.size(), raw.size());
     // host-only path: plain memory instead of page-locked buffers, no context
     Batch b;
     b.n_pairs = (int64_t)raw.size();
+    const Side *sd[2] = {&raw.a, &raw.b};
     size_t mx = 1;
-    for (auto &r : raw) mx = std::max(mx, std::max(r.s[0].size(), r.s[1].size()));
+    for (int m = 0; m < 2; ++m)
+        for (size_t i = 0; i < sd[m]->n; ++i) mx = std::max(mx, sd[m]->len(i));
     b.stride = (int32_t)mx;
     std::vector<uint8_t> codes(2 * raw.size() * mx, 4), quals(2 * raw.size() * mx, 0);
     std::vector<int32_t> lens(2 * raw.size());
     static uint8_t lut[256];
     memset(lut, 4, sizeof lut);
     lut['A'] = lut['a'] = 0; lut['C'] = lut['c'] = 1; lut['G'] = lut['g'] = 2; lut['T'] = lut['t'] = 3;
+    b.names.assign(raw.a.names.begin(), raw.a.names.end());
+    b.name_off = raw.a.noff;
     for (size_t i = 0; i < raw.size(); ++i) {
-        b.name_off.push_back((uint32_t)b.names.size());
-        b.names.append(raw[i].name); b.names.push_back('\0');
         for (int m = 0; m < 2; ++m) {
-            const std::string &s = raw[i].s[m], &q = raw[i].q[m];
-            for (size_t j = 0; j < s.size(); ++j) { codes[(2 * i + m) * mx + j] = lut[(unsigned char)s[j]]; quals[(2 * i + m) * mx + j] = (uint8_t)(q[j] - 33); }
-            lens[2 * i + m] = (int32_t)s.size();
+            const char *s = sd[m]->seq.data() + sd[m]->soff[i], *q = sd[m]->qual.data() + sd[m]->soff[i];
+            const size_t n = sd[m]->len(i);
+            for (size_t j = 0; j < n; ++j) { codes[(2 * i + m) * mx + j] = lut[(unsigned char)s[j]]; quals[(2 * i + m) * mx + j] = (uint8_t)(q[j] - 33); }
+            lens[2 * i + m] = (int32_t)n;
         }
     }
     b.codes = codes.data(); b.quals = quals.data(); b.lens = lens.data(); b.alns = alns.data();
