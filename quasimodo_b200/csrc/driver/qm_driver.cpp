@@ -858,8 +858,27 @@ int sort_key_bits(const Genome &g, int &pos_bits)
 
 template <class T> std::vector<T> read_binary(const std::string &path);
 
+// wall clock of the run's phases, one line on stderr at the end (where a sample's file-level time goes)
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    std::string line;
+    void mark(const char *name)
+    {
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof buf, "%s%s %.2f", line.empty() ? "" : ", ", name, std::chrono::duration<double>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    void report()
+    {
+        fprintf(stderr, "[qm_driver] phases (s): %s; total %.2f\n", line.c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
 {
+    PhaseClock pc;
     if (!a.has("ref") || !a.has("r1") || !a.has("r2")) die(1, "--ref, --r1 and --r2 are required");
     const std::string bam = a.get("bam"), counts = a.get("counts"), vcf = a.get("vcf"), o1 = a.get("out-r1"), o2 = a.get("out-r2");
     if (decontam && (o1.empty() || o2.empty())) die(1, "decontam needs --out-r1 and --out-r2");
@@ -917,6 +936,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         Ls[d].check(qm_sample_begin(Ls[d].ctx, idxs[d], &opt, &popt, &smps[d]), "qm_sample_begin");
     }
     qm_index *idx = idxs[0];
+    pc.mark("context + reference + index");
     qm_sample *smp = smps[0];
 
     const bool rmdup = !decontam && atoi(a.get("rmdup", "0").c_str()) != 0;
@@ -999,6 +1019,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     }
     for (int d = 0; d < n_gpu; ++d) join_worker(d);
     const double loop_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_loop).count();
+    pc.mark("FASTQ -> records + counts");
     if (decontam) {
         if (fclose(f1) != 0 || fclose(f2) != 0) die(2, "write error on the cleaned FASTQ files");
         fprintf(stderr, "[qm_driver] decontam: %lld of %lld pairs kept\n", (long long)kept, (long long)n_pairs);
@@ -1056,6 +1077,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         }
     }
 
+    pc.mark("merge / deferred counting");
     if (!counts.empty()) {
         std::vector<int32_t> rows(g.codes.size() * QM_NCH);
         L.check(qm_sample_counts_host(smp, rows.data()), "qm_sample_counts_host");
@@ -1130,6 +1152,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         if (!fp || (bytes && fwrite(text.data(), 1, (size_t)bytes, fp) != (size_t)bytes) || fclose(fp) != 0) die(2, "cannot write %s", mpileup.c_str());
         fprintf(stderr, "[qm_driver] text pileup: %lld bytes\n", (long long)bytes);
     }
+    pc.mark("count TSV + calls + VCF + text pileup");
     if (want_bam) {
         // coordinate sort on the device: keys from the records, stable radix sort, gather through the permutation
         int pos_bits = 0;
@@ -1141,7 +1164,9 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
                 keys[k] = qm_sort_key(b.alns[r].rid, b.alns[r].pos, (b.alns[r].flag & 0x10) != 0, (int)g.names.size(), pos_bits);
         std::vector<uint32_t> perm(keys.size());
         L.check(qm_sort_keys_host(L.ctx, keys.data(), (int64_t)keys.size(), key_bits, perm.data()), "qm_sort_keys_host");
+        pc.mark("coordinate sort");
         if (!bam.empty()) write_bam(bam, g, batches, perm, first_read, cmdline, threads);
+        pc.mark("BAM + BAI");
         if (!rmdup_bam.empty()) {                      // REMOVE_DUPLICATES=true: the same order without the flagged records
             std::vector<uint32_t> kept_perm;
             kept_perm.reserve(perm.size());
@@ -1158,6 +1183,8 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         qm_index_destroy(Ls[d].ctx, idxs[d]);
         qm_ctx_destroy(Ls[d].ctx);
     }
+    pc.mark("release");
+    pc.report();
     return 0;
 }
 

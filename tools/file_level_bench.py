@@ -55,4 +55,5 @@ with tempfile.TemporaryDirectory() as d:
         line = [ln for ln in p.stderr.split("\n") if "from the first read to the last record" in ln]
         print(json.dumps({"metric": "file_level_read_pairs_per_s", "outputs": what, "pairs": n, "wall_s": round(dt, 2), "value": round(n / dt),
                           "unit": "pairs/s", "threads": threads, "fastq_mb": round(fq_bytes / 1e6), "output_bytes": sizes,
-                          "driver_log": line[0].strip() if line else None, "workload": W.name}))
+                          "driver_log": line[0].strip() if line else None,
+                          "phases": next((ln.strip() for ln in p.stderr.split("\n") if "phases (s)" in ln), None), "workload": W.name}))
