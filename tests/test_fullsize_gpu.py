@@ -273,3 +273,28 @@ def test_config4_deep_sample_in_several_calls(ctx):
     depth = c3[:, 14].sum() / W.ref.total
     assert 0.8 * 2 * n * 150 / W.ref.total < depth <= 2 * n * 150 / W.ref.total
     idx.close()
+
+
+def test_full_size_config3_contaminated_sample(ctx):
+    """BASELINE configs[2] at size: 1 M pairs of AD169:Merlin 1:10 + 5 % PhiX + 5 % E. coli against the 4.89 Mb three-contig index.
+    Conservation between records and tensor; the reads of each source land on its contig (the decontamination rule's premise);
+    two library calls give the tensor of one."""
+    from quasimodo_b200 import _lib, workloads
+    n = 1_000_000
+    W = workloads.config3(n)
+    opt = _lib.default_opt()
+    counts, alns, stats, pes, (idx, c, q, lens) = _run_whole(ctx, W, n, 150, opt)
+    a, b = conservation(alns, counts)
+    assert a == b and a[0] > 1_800_000
+    m = (alns["flag"] & 4) == 0
+    share = np.bincount(alns["rid"][m], minlength=3) / m.sum()
+    assert 0.86 < share[0] < 0.93 and 0.03 < share[1] < 0.07 and 0.03 < share[2] < 0.07, share
+    assert (alns["pos"][m] < np.array(W.ref.lens)[alns["rid"][m]]).all()
+    # depth per contig follows the read shares: channel 14 summed inside each contig
+    off = np.concatenate([[0], np.cumsum(W.ref.lens)])
+    per = np.array([counts[off[k]:off[k + 1], 14].sum() for k in range(3)], dtype=np.float64)
+    assert abs(per[0] / per.sum() - share[0]) < 0.03
+    c2, _, stats2, pes2, t2 = _run_whole(ctx, W, n, 150, opt, calls=2, records=False)
+    assert np.array_equal(c2, counts) and stats2 == stats and pes2.tobytes() == pes.tobytes()
+    t2[0].close()
+    idx.close()
