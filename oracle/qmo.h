@@ -46,6 +46,7 @@ typedef struct {
     int32_t reserved[2];
 } qmo_opt_t;
 #define QMO_F_NO_RESCUE 1         /* bwa mem -S: skip mate rescue                       */
+#define QMO_F_PATCH     4         /* mem_patch_reg: two collinear hits merged when one global alignment explains them */
 #define QMO_F_FM_SEEDS  2         /* seeds from bwa's FM-index (qmo_ref_set_fm) instead of the k-mer hash index */
 
 void qmo_opt_default(qmo_opt_t *o);

@@ -389,8 +389,49 @@ static void chain_to_regs(const qmo_ref_t *R, const qmo_opt_t *o, int l_query, c
     free(qs); free(rs);
 }
 
-/* ---- mem_sort_dedup_patch without mem_patch_reg; stable sorts ---- */
-static int sort_dedup(const qmo_opt_t *o, int n, qmo_reg_t *a)
+/* ---- mem_sort_dedup_patch; stable sorts.  Patching (bwamem.c mem_patch_reg: two collinear hits of a read that one banded global
+ * alignment explains at >= 90 % of the score their lengths predict become one) runs when the caller hands in the read (R, query):
+ * mem_align1_core does, mem_matesw does not.  Off unless o->flags & QMO_F_PATCH (a deviation the product shares by default). ---- */
+#define PATCH_MAX_R_BW 0.05f
+#define PATCH_MIN_SC_RATIO 0.90f
+#define QMO_PATCH_MAX_QUERY 256      /* longer spans are not patched (limit shared with the product's scalar DP) */
+static int gen_cigar(const qmo_ref_t *R, const qmo_opt_t *o, int w_, int l_query, const uint8_t *query,
+                     int64_t rb, int64_t re, int *n_cigar, uint32_t *cigar, int *nm);
+long long g_qmo_patch_tried = 0, g_qmo_patch_done = 0;      /* diagnostics */
+
+static int patch_reg(const qmo_ref_t *R, const qmo_opt_t *o, const uint8_t *query, const qmo_reg_t *a, const qmo_reg_t *b, int *_w)
+{
+    int w, score, q_s, r_s, n_cigar = 0, nm;
+    uint32_t cig[QMO_MAX_CIGAR];
+    double r;
+    if (a->rb < R->l_pac && b->rb >= R->l_pac) return 0;                          /* on different strands */
+    if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;             /* not collinear */
+    w = (int)((a->re - b->rb) - (a->qe - b->qb));                                 /* required bandwidth */
+    w = w > 0 ? w : -w;
+    r = (double)(a->re - b->rb) / (b->re - a->rb) - (double)(a->qe - b->qb) / (b->qe - a->qb);   /* relative bandwidth */
+    r = r > 0. ? r : -r;
+    if (a->re < b->rb || a->qe < b->qb) {                                         /* no overlap on query or on reference */
+        if (w > o->w << 1 || r >= PATCH_MAX_R_BW) return 0;
+    } else if (w > o->w << 2 || r >= PATCH_MAX_R_BW * 2) return 0;                /* more permissive if overlapping on both */
+    if (b->qe - a->qb > QMO_PATCH_MAX_QUERY || b->re - a->rb > 2 * QMO_PATCH_MAX_QUERY) return 0;
+    w += a->w + b->w;
+    w = w < o->w << 2 ? w : o->w << 2;
+#pragma omp atomic
+    ++g_qmo_patch_tried;
+    score = gen_cigar(R, o, w, b->qe - a->qb, query + a->qb, a->rb, b->re, &n_cigar, cig, &nm);
+    q_s = (int)((double)(b->qe - a->qb) / ((b->qe - b->qb) + (a->qe - a->qb)) * (b->score + a->score) + .499);
+    r_s = (int)((double)(b->re - a->rb) / ((b->re - b->rb) + (a->re - a->rb)) * (b->score + a->score) + .499);
+    if ((double)score / (q_s > r_s ? q_s : r_s) < PATCH_MIN_SC_RATIO) return 0;
+    *_w = w;
+#pragma omp atomic
+    ++g_qmo_patch_done;
+    return score;
+}
+
+static int sort_dedup_patch(const qmo_ref_t *R, const qmo_opt_t *o, const uint8_t *query, int n, qmo_reg_t *a);
+static int sort_dedup(const qmo_opt_t *o, int n, qmo_reg_t *a) { return sort_dedup_patch(0, o, 0, n, a); }
+
+static int sort_dedup_patch(const qmo_ref_t *R, const qmo_opt_t *o, const uint8_t *query, int n, qmo_reg_t *a)
 {
     int i, j, m;
     if (n <= 1) return n;
@@ -409,6 +450,17 @@ static int sort_dedup(const qmo_opt_t *o, int n, qmo_reg_t *a)
             if (orr > o->mask_level_redun * mr && oq > o->mask_level_redun * mq) {
                 if (p->score < q->score) { p->qe = p->qb; break; }
                 else q->qe = q->qb;
+            } else if (query && (o->flags & QMO_F_PATCH) && q->rb < p->rb) {
+                int w, score = patch_reg(R, o, query, q, p, &w);
+                if (score > 0) {                                  /* merge q into p (n_comp is not kept here) */
+                    p->seedcov = p->seedcov > q->seedcov ? p->seedcov : q->seedcov;
+                    p->sub = p->sub > q->sub ? p->sub : q->sub;
+                    p->csub = p->csub > q->csub ? p->csub : q->csub;
+                    p->qb = q->qb; p->rb = q->rb;
+                    p->truesc = p->score = score;
+                    p->w = w;
+                    q->qe = q->qb;
+                }
             }
         }
     }
@@ -455,7 +507,7 @@ void qmo_align_se(const qmo_ref_t *R, const qmo_opt_t *o, int64_t n, const uint8
         int nc = build_chains(R, o, S, ns, chn), c, nav = 0;
         int64_t mycells = 0;
         for (c = 0; c < nc; ++c) chain_to_regs(R, o, lens[r], q, S, &chn[c], av, &nav, log, &mycells);
-        nav = sort_dedup(o, nav, av);
+        nav = sort_dedup_patch(R, o, q, nav, av);
         if (seeds) { memcpy(seeds + r * QMO_MAX_SEEDS, S, sizeof(qmo_seed_t) * ns); n_seeds[r] = ns; }
         if (regs) { memcpy(regs + r * QMO_MAX_REGS, av, sizeof(qmo_reg_t) * nav); n_regs[r] = nav; }
         cells += mycells;

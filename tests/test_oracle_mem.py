@@ -143,3 +143,28 @@ def test_text_pileup_agrees_with_the_count_tensor(run):
     # a column has a line iff an admitted read covers it (raw depth or a deletion)
     assert np.array_equal(seen, (cnt[:, 14] + cnt[:, 5] + cnt[:, 11]) > 0)
     assert n_zero > 0
+
+
+def test_mem_patch_reg_has_nothing_to_patch_on_baseline_data():
+    """the product has no mem_patch_reg (bwamem.c: two collinear hits of a read become one when a banded global
+    alignment explains them at >= 90 % of the predicted score).  The oracle restates the rule behind QMO_F_PATCH; on reads of the
+    BASELINE configs it finds nothing to do: short reads' collinear hit pairs are rare and fail the relative-bandwidth test, so the
+    regions with and without the flag are identical."""
+    import ctypes as C
+    from quasimodo_b200 import workloads
+    L = qmo_py.lib()
+    tried0 = C.c_longlong.in_dll(L, "g_qmo_patch_tried").value
+    for W, rl, w in ((workloads.config2(4, 6000), 150, 100), (workloads.config2(1, 6000), 150, 100), (workloads.config5(4000), 250, 200)):
+        n = 6000 if rl == 150 else 4000
+        codes, _, _, _ = W.simulate_host(0, n)
+        lens = np.full(2 * n, rl, np.int32)
+        ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+        o0, o1 = qmo_py.default_opt(), qmo_py.default_opt()
+        o0.w = o1.w = w
+        o1.flags |= 4                                  # QMO_F_PATCH
+        a0 = qmo_py.align_se(ref, codes, lens, opt=o0)
+        a1 = qmo_py.align_se(ref, codes, lens, opt=o1)
+        assert np.array_equal(a0["n_regs"], a1["n_regs"]) and a0["regs"].tobytes() == a1["regs"].tobytes()
+        assert (a0["n_regs"] > 1).sum() > 50           # there ARE reads with several hits: repeats, other strands -- not collinear pairs
+    done = C.c_longlong.in_dll(L, "g_qmo_patch_done").value
+    assert done == 0 and C.c_longlong.in_dll(L, "g_qmo_patch_tried").value - tried0 <= 5
