@@ -16,6 +16,8 @@ W = workloads.config2(i, P)
 opt = _lib.default_opt()
 idx = ctx.index(W.ref, 31)
 s = ctx.sample(idx, opt)
+if os.environ.get("QM_AB_BAQ"):
+    s.set_baq(int(os.environ["QM_AB_BAQ"]))          # base alignment quality on (3 = as both mpileups run it)
 st = torch.cuda.current_stream().cuda_stream
 g = torch.from_numpy(W.src_codes).to(dev)
 c = torch.empty((2 * P, L), dtype=torch.uint8, device=dev); q = torch.empty_like(c)
