@@ -157,14 +157,17 @@ struct SeedWalk {
 __device__ __forceinline__ int seed_find(const qm_seed *S, int n, int64_t diag, int q, int k)
 {
     for (int m0 = 0; m0 < n; m0 += 4) {
-        int4 e[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) e[i] = *(const int4 *)&S[m0 + i < QM_MAX_SEEDS ? m0 + i : QM_MAX_SEEDS - 1];
+        // (8-byte loads: a caller's seed array is only as aligned as the struct)
+        int64_t rb[4];
+        int2 ql[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int64_t rbeg = (int64_t)(((uint64_t)(uint32_t)e[i].y << 32) | (uint32_t)e[i].x);
-            if (m0 + i < n && rbeg - e[i].z == diag && e[i].z + e[i].w - k + 1 == q) return m0 + i;
+            const qm_seed *e = &S[m0 + i < QM_MAX_SEEDS ? m0 + i : QM_MAX_SEEDS - 1];
+            rb[i] = e->rbeg; ql[i] = *(const int2 *)&e->qbeg;
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (m0 + i < n && rb[i] - ql[i].x == diag && ql[i].x + ql[i].y - k + 1 == q) return m0 + i;
     }
     return -1;
 }
