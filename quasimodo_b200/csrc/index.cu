@@ -116,13 +116,15 @@ int qm_index_build(qm_ctx *ctx, const uint8_t *h_codes, int n_contigs, const int
         if ((uniq[x >> 5] >> (x & 31)) & 1u) uniqp[(size_t)(x + 32) >> 5] |= 1u << ((x + 32) & 31);
         if ((uniq2[x >> 5] >> (x & 31)) & 1u) uniq2p[(size_t)(x + 32) >> 5] |= 1u << ((x + 32) & 31);
     }
-    // Bloom filter over canonical k-mers: a read k-mer whose canonical form is not in the filter occurs on neither strand,
-    // and the seeding kernel answers that from shared memory instead of probing the table twice through L2.  Sized at
-    // >= 7 bits per distinct k-mer (3 hashes: ~4 % false positives) within the shared-memory budget, else no filter.
+    // Bloom filter over canonical k-mers: a read k-mer whose canonical form is not in the filter occurs on neither strand, and
+    // the seeding walk answers that from three filter words instead of probing the table twice.  The filter lives in L2 (it
+    // was sized for shared memory once: 208 KB whatever the genome, ~7 bits per k-mer of a herpesvirus and NO filter at all for the
+    // 4.9 Mb index of config 3): 16 bits per distinct k-mer (3 hashes: ~0.5 % false positives), at least 208 KB, at most 256 MB.
     std::vector<uint32_t> bloom;
     v.bloom_bits = 0;
-    if (n_unique * 7 <= (int64_t)kBloomMaxBytes * 8) {
-        const uint32_t bbits = kBloomMaxBytes * 8;
+    const int64_t want_bits = std::max<int64_t>((int64_t)kBloomMinBytes * 8, ((n_unique * 16 + 8191) / 8192) * 8192);
+    if (want_bits <= (int64_t)kBloomMaxBytes * 8) {
+        const uint32_t bbits = (uint32_t)want_bits;
         bloom.assign(bbits / 32, 0u);
         for (size_t i = 0; i < km.size(); ++i) {
             if (i && km[i].first == km[i - 1].first) continue;

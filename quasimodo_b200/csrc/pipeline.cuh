@@ -20,7 +20,7 @@ struct IndexView {
     const uint32_t *cnteqp[3];// same layout: the k-mer starting at x and its reverse complement occur 2 / 3 / 4 times in total
                               // (repeats in a few copies): a read k-mer equal to it has exactly that many hits
     const uint32_t *bloom;    // Bloom filter over the canonical (min of k-mer and its reverse complement) reference k-mers,
-    uint32_t bloom_bits;      // 3 hash functions; 0 bits = no filter (reference too large for a shared-memory filter)
+    uint32_t bloom_bits;      // 3 hash functions; 0 bits = no filter (a reference of more than 128 M distinct k-mers)
     uint64_t mask;            // table size - 1
     int shift;                // 64 - log2(table size)
     int k, n_contigs;
@@ -60,7 +60,7 @@ static __host__ __device__ __forceinline__ void qm_bloom_pos(uint64_t canon, uin
     p[1] = (uint32_t)(((uint64_t)b * bits) >> 32);
     p[2] = (uint32_t)(((uint64_t)c * bits) >> 32);
 }
-constexpr uint32_t kBloomMaxBytes = 208 * 1024;          // shared-memory budget of the seeding kernel's filter
+constexpr uint32_t kBloomMinBytes = 208 * 1024, kBloomMaxBytes = 256u << 20;      // the seeding filter: 16 bits per k-mer between these
 static __device__ __forceinline__ bool qm_idx_lookup(const IndexView &V, uint64_t key, uint32_t &first, uint32_t &cnt)
 {
     uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> V.shift;
