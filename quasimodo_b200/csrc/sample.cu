@@ -461,6 +461,7 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         s->stage_cap = need;
     }
     cudaStream_t cs = ctx->copy_stream, ks = ctx->own_stream;
+    static const int n_parts = getenv("QM_COPY_PARTS") ? std::max(1, std::min(kCopyParts, atoi(getenv("QM_COPY_PARTS")))) : kCopyParts;   // tuning knob
     // Full-size chunks (large batches: fewer extension rounds, shorter tails).  A chunk's bases are copied in kCopyParts
     // pieces and seeded piece by piece, so only the first piece's copy is exposed; qualities travel behind the bases
     // (only the pileup at the end of a chunk reads them); the next chunk's copies run under this chunk's kernels.
@@ -505,8 +506,8 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         if ((e = cudaMemcpyAsync(s->d_stage[b] + 2 * seq_al, h_lens + 2 * p0, (size_t)2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
         if ((e = cudaEventRecord(s->ev_copied[b], cs)) != cudaSuccess) return e;
         // the bases in kCopyParts pieces, an event behind each: seeding starts on piece 0 while the others are in flight
-        for (int pt = 0; pt < kCopyParts; ++pt) {
-            const int64_t r0 = 2 * n * pt / kCopyParts, r1 = 2 * n * (pt + 1) / kCopyParts;
+        for (int pt = 0; pt < n_parts; ++pt) {
+            const int64_t r0 = 2 * n * pt / n_parts, r1 = 2 * n * (pt + 1) / n_parts;
             if (r1 > r0 && !packed && (e = cudaMemcpyAsync(s->d_stage[b] + r0 * stride, h_codes + (2 * p0 + r0) * stride, (size_t)(r1 - r0) * stride,
                                                            cudaMemcpyHostToDevice, cs)) != cudaSuccess) return e;
             if (r1 > r0 && packed) {
@@ -534,9 +535,9 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
         const int64_t p0 = starts[c], n = sizes[c];
         if (c + 1 < n_chunks) QM_CUDA(ctx, enqueue_copy(c + 1));
         QM_CUDA(ctx, cudaStreamWaitEvent(ks, s->ev_copied[b], 0));
-        ctx->se_n_parts = kCopyParts;
+        ctx->se_n_parts = n_parts;
         if (packed) { ctx->se_pk = s->d_stage[b] + o_pk; ctx->se_mk = s->d_stage[b] + o_mk; ctx->se_sp = stride_p; ctx->se_sm = stride_m; }
-        for (int pt = 0; pt < kCopyParts; ++pt) { ctx->se_part_end[pt] = 2 * n * (pt + 1) / kCopyParts; ctx->se_part_ev[pt] = s->ev_part[b][pt]; }
+        for (int pt = 0; pt < n_parts; ++pt) { ctx->se_part_end[pt] = 2 * n * (pt + 1) / n_parts; ctx->se_part_ev[pt] = s->ev_part[b][pt]; }
         int rc = sample_chunk(s, s->d_stage[b], s->d_stage[b] + seq_al, stride, (const int32_t *)(s->d_stage[b] + 2 * seq_al), n,
                               pair_id0 + p0, nullptr, ks, s->ev_quals[b]);
         ctx->se_n_parts = 0; ctx->se_pk = ctx->se_mk = nullptr;
@@ -550,7 +551,7 @@ static int add_pairs_host_impl(qm_sample *s, const uint8_t *h_codes, const uint8
     if (trace) {
         float ms = 0;
         fprintf(stderr, "[qm host trace] pairs %lld pieces", (long long)sizes[0]);
-        for (int i = 0; i < kCopyParts; ++i) { cudaEventElapsedTime(&ms, tr0, tr_part[i]); fprintf(stderr, " %.2f", ms); cudaEventDestroy(tr_part[i]); }
+        for (int i = 0; i < kCopyParts; ++i) { if (i < n_parts) { cudaEventElapsedTime(&ms, tr0, tr_part[i]); fprintf(stderr, " %.2f", ms); } cudaEventDestroy(tr_part[i]); }
         cudaEventElapsedTime(&ms, tr0, tr_quals); fprintf(stderr, " quals %.2f", ms);
         cudaEventElapsedTime(&ms, tr0, tr_done); fprintf(stderr, " chunk done %.2f ms", ms);
         if (n_chunks > 1) {
