@@ -22,10 +22,15 @@
 //          a pair is dropped iff a mate maps to a later (contaminant) contig: one pass instead of three.
 //   qm_driver bam-from-records --ref .. --r1 .. --r2 .. --alns ALNS.bin [--perm PERM.bin] --bam OUT.bam
 //        = the BAM/BAI writer alone on given qm_aln records (test entry; with --perm no GPU is touched)
+//   qm_driver fastq-check --r1 .. --r2 .. [-t THREADS]
+//        = the FASTQ side alone (host only): the two mate files parsed and validated as `sample` would, pairs / bases / parse rate
 //
 // Exit status: 0 ok, 1 usage, 2 I/O or format error, 3 library/CUDA error (message on stderr), so a failing job
 // fails its Snakemake rule exactly like a failing `bwa`.
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <cerrno>
 
 #include <algorithm>
 #include <atomic>
@@ -60,23 +65,53 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // line reader over zlib (reads plain and gzip files alike)
 struct LineReader {
-    gzFile f = nullptr;
+    gzFile f = nullptr;                   // gzip input
+    int fd = -1;                          // plain input: read(2) straight into the buffer (zlib's transparent mode copies every byte twice)
     std::string path;
     std::vector<char> buf;
     size_t pos = 0, len = 0;
-    explicit LineReader(const std::string &p) : path(p), buf(1 << 20)
+    explicit LineReader(const std::string &p) : path(p), buf(4 << 20)
     {
-        f = gzopen(p.c_str(), "rb");
-        if (!f) die(2, "cannot open %s", p.c_str());
-        gzbuffer(f, 1 << 20);
+        fd = open(p.c_str(), O_RDONLY);
+        if (fd < 0) die(2, "cannot open %s", p.c_str());
+        unsigned char magic[2] = {0, 0};
+        const ssize_t got = pread(fd, magic, 2, 0);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            close(fd); fd = -1;
+            f = gzopen(p.c_str(), "rb");
+            if (!f) die(2, "cannot open %s", p.c_str());
+            gzbuffer(f, 1 << 20);
+        }
     }
-    ~LineReader() { if (f) gzclose(f); }
+    ~LineReader() { if (f) gzclose(f); if (fd >= 0) close(fd); }
+    LineReader(const LineReader &) = delete;
+    LineReader &operator=(const LineReader &) = delete;
     bool fill()
     {
-        const int n = gzread(f, buf.data(), (unsigned)buf.size());
+        long n;
+        if (f) n = gzread(f, buf.data(), (unsigned)buf.size());
+        else do { n = (long)read(fd, buf.data(), buf.size()); } while (n < 0 && errno == EINTR);
         if (n < 0) die(2, "read error in %s", path.c_str());
         pos = 0; len = (size_t)n;
         return n > 0;
+    }
+    // next line as a view into the buffer (valid until the next call), without the terminator; false at end of file.  A line that
+    // crosses the end of the buffer is assembled in `spill`.
+    std::string spill;
+    bool next_view(const char *&p, size_t &n)
+    {
+        if (pos == len && !fill()) return false;
+        const char *s = buf.data() + pos;
+        const char *nl = (const char *)memchr(s, '\n', len - pos);
+        if (nl) {
+            p = s; n = (size_t)(nl - s);
+            pos += n + 1;
+            if (n && p[n - 1] == '\r') --n;
+            return true;
+        }
+        if (!next(spill)) return false;
+        p = spill.data(); n = spill.size();
+        return true;
     }
     // next line without the terminator; false at end of file
     bool next(std::string &out)
@@ -196,21 +231,38 @@ template <class F> void parallel_ranges(size_t n, F fn)
 // inflated) side by side: the second mate's file has a thread of its own.
 bool read_batch(FastqPairReader &fr, int64_t max_pairs, RawBatch &out)
 {
+    // a record's four lines are consumed as they are read (a view dies with the next read): one copy from the file buffer into the
+    // side's arrays, no string per line
     auto side = [max_pairs](LineReader &r, Side &v) {
-        std::string h, s, p, q;
         v.clear();
-        while ((int64_t)v.n < max_pairs && FastqPairReader::record(r, h, s, p, q)) {
+        const char *p = nullptr;
+        size_t n = 0;
+        while ((int64_t)v.n < max_pairs) {
+            if (!r.next_view(p, n)) return;
+            while (n == 0) if (!r.next_view(p, n)) return;              // blank lines between records
+            if (p[0] != '@') die(2, "%s: FASTQ header expected, got '%.*s'", r.path.c_str(), (int)std::min<size_t>(n, 40), p);
             // bwa: the name up to the first whitespace, a trailing /1 or /2 dropped
             size_t e = 1;
-            while (e < h.size() && !isspace((unsigned char)h[e])) ++e;
-            if (e > 3 && h[e - 2] == '/' && (h[e - 1] == '1' || h[e - 1] == '2')) e -= 2;
+            while (e < n && !isspace((unsigned char)p[e])) ++e;
+            if (e > 3 && p[e - 2] == '/' && (p[e - 1] == '1' || p[e - 1] == '2')) e -= 2;
             v.noff.push_back((uint32_t)v.names.size());
-            v.names.insert(v.names.end(), h.begin() + 1, h.begin() + (ptrdiff_t)e);
+            v.names.insert(v.names.end(), p + 1, p + e);
             v.names.push_back('\0');
-            v.seq.insert(v.seq.end(), s.begin(), s.end());
-            v.qual.insert(v.qual.end(), q.begin(), q.end());
+            if (!r.next_view(p, n)) die(2, "%s: truncated FASTQ record", r.path.c_str());
+            const size_t sl = n;
+            v.seq.insert(v.seq.end(), p, p + n);
+            if (!r.next_view(p, n)) die(2, "%s: truncated FASTQ record", r.path.c_str());
+            if (n == 0 || p[0] != '+') die(2, "%s: '+' line expected", r.path.c_str());
+            if (!r.next_view(p, n)) die(2, "%s: truncated FASTQ record", r.path.c_str());
+            if (n != sl) die(2, "%s: sequence and quality lengths differ in @%s", r.path.c_str(), v.names.data() + v.noff.back());
+            v.qual.insert(v.qual.end(), p, p + n);
             v.soff.push_back((uint64_t)v.seq.size());
-            ++v.n;
+            if (++v.n == 1 && max_pairs <= ((int64_t)1 << 23)) {
+                // the first record sizes the batch's arrays (address space only: no growth by doubling, no copies of what was read)
+                const size_t m = (size_t)max_pairs;
+                v.seq.reserve(m * (sl + 1)); v.qual.reserve(m * (sl + 1));
+                v.names.reserve(m * (v.names.size() + 2)); v.soff.reserve(m + 1); v.noff.reserve(m);
+            }
         }
     };
     std::thread t2([&]() { side(fr.r2, out.b); });
@@ -1262,7 +1314,7 @@ int cmd_bam_from_records(const Args &a, const std::string &cmdline)
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records|vcf-index [options]   (%s)", qm_version());
+    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records|vcf-index|fastq-check [options]   (%s)", qm_version());
     std::string cmdline;
     for (int i = 0; i < argc; ++i) { if (i) cmdline += ' '; cmdline += argv[i]; }
     const std::string cmd = argv[1];
@@ -1270,6 +1322,24 @@ int main(int argc, char **argv)
     if (cmd == "sample") return cmd_sample(a, cmdline, false);
     if (cmd == "decontam") return cmd_sample(a, cmdline, true);
     if (cmd == "bam-from-records") return cmd_bam_from_records(a, cmdline);
+    if (cmd == "fastq-check") {                        // host only: parse the two mate files as `sample` would, report what is there
+        if (!a.has("r1") || !a.has("r2")) die(1, "--r1 --r2 are required");
+        g_threads = std::max(1, atoi(a.get("t", a.get("threads", "4")).c_str()));
+        FastqPairReader fr(a.get("r1"), a.get("r2"));
+        RawBatch raw;
+        int64_t n_pairs = 0, bases = 0;
+        size_t mx = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (read_batch(fr, 2000000, raw)) {
+            n_pairs += (int64_t)raw.size();
+            bases += (int64_t)raw.a.seq.size() + (int64_t)raw.b.seq.size();
+            for (const Side *sd : {&raw.a, &raw.b}) for (size_t i = 0; i < sd->n; ++i) mx = std::max(mx, sd->len(i));
+        }
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("%lld pairs, %lld bases, longest read %zu, parsed in %.2f s (%.3f M pairs/s)\n", (long long)n_pairs, (long long)bases, mx, dt,
+               dt > 0 ? (double)n_pairs / dt / 1e6 : 0.0);
+        return 0;
+    }
     if (cmd == "vcf-index") {                          // bgzip -c X > X.gz; tabix -p vcf X.gz  (host only: rules/vcfcall.smk:118-119, rules/genome_diff.smk:24-25)
         if (!a.has("vcf")) die(1, "--vcf is required");
         write_vcf_gz_tbi(a.get("vcf"), a.get("out", a.get("vcf") + ".gz"), std::max(1, atoi(a.get("t", "2").c_str())));
