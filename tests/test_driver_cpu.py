@@ -172,3 +172,42 @@ def test_vcf_gz_and_tabix_index(tmp_path):
     bad = tmp_path / "bad.vcf"
     bad.write_text("#CHROM\tPOS\tID\tREF\tALT\nMerlin\t500\t.\tA\tG\nMerlin\t20\t.\tA\tG\n")
     assert drvutil.run_driver(["vcf-index", "--vcf", bad], check=False).returncode == 2
+
+
+def test_fastq_side_parses_what_bwa_would(tmp_path):
+    """`qm_driver fastq-check` (host only) runs the FASTQ side of `sample`: plain and gzip input, CRLF line ends, blank lines between
+    records, a last line without a newline, records longer than the file buffer's remainder; and it fails loudly (exit 2) on what
+    bwa would reject: a truncated record, a quality line of another length, mate files of different length."""
+    import gzip
+    rng = np.random.default_rng(3)
+    n = 30_000                                              # ~5 MB per file: several refills of the 4 MB buffer
+    seqs = ["".join("ACGTN"[c] for c in rng.integers(0, 5, int(l))) for l in rng.integers(30, 151, n)]
+    def records(mate, eol="\n", blank_every=0):
+        out = []
+        for i, s in enumerate(seqs):
+            out.append(f"@r{i}/{mate} extra words{eol}{s}{eol}+{eol}{'I' * len(s)}{eol}")
+            if blank_every and i % blank_every == 0:
+                out.append(eol)
+        return "".join(out)
+    p1, p2 = tmp_path / "a_1.fq", tmp_path / "a_2.fq.gz"
+    p1.write_text(records(1, "\r\n", blank_every=997).rstrip("\r\n"))          # CRLF, blank lines, no final newline
+    with gzip.open(p2, "wt") as fh:
+        fh.write(records(2))
+    ok = drvutil.run_driver(["fastq-check", "--r1", p1, "--r2", p2])
+    total = 2 * sum(len(s) for s in seqs)
+    assert ok.stdout.startswith(f"{n} pairs, {total} bases, longest read {max(len(s) for s in seqs)},")
+    # malformed inputs
+    bad = tmp_path / "bad.fq"
+    good = records(1)
+    cases = {"truncated": good[:good.rindex("+")], "lengths": good.replace("I" * len(seqs[5]) + "\n", "I" * (len(seqs[5]) + 1) + "\n", 1) if len(seqs[5]) != len(seqs[4]) else None,
+             "header": good.replace("@r7/1", "r7/1", 1)}
+    for name, text in cases.items():
+        if text is None:
+            continue
+        bad.write_text(text)
+        p = drvutil.run_driver(["fastq-check", "--r1", bad, "--r2", p2], check=False)
+        assert p.returncode == 2 and str(bad) in p.stderr, (name, p.returncode, p.stderr[-200:])
+    short = tmp_path / "short.fq"
+    short.write_text("".join(records(1).split("@r29999/1")[:1]))
+    p = drvutil.run_driver(["fastq-check", "--r1", short, "--r2", p2], check=False)
+    assert p.returncode == 2 and "more records" in p.stderr
