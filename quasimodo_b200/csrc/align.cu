@@ -4,15 +4,22 @@
 // rules/bwa.smk:15; semantics SURVEY.md A.2, A.5).
 //
 // Layout of the work on the GPU:
-//   seed_chain_kernel   one thread per read: rolling 2-bit k-mers of both strands probe the L2-resident
-//                       hash index; consecutive hits on one diagonal are merged into maximal exact
-//                       matches; seeds are chained and chains filtered exactly as bwa does; the result
-//                       is a per-read "plan" = the order in which mem_chain2aln visits the seeds.
+//   pack_reads_kernel   a block's rows staged by one cp.async.bulk copy, every read packed to 2 bits per base + N flags.
+//   seed_walk_kernel    PERSISTENT, one lane per read at a time: 2-bit k-mers of both strands probe the L2-resident hash
+//                       index behind a Bloom filter; a hit that is the k-mer's only one is followed 32 bases per step
+//                       against the packed reference; consecutive hits on one diagonal are merged into maximal exact
+//                       matches; a lane that finishes its read takes the next one off a cursor.
+//   plan_kernel         one thread per read: seeds sorted, chained and the chains filtered exactly as bwa does; the
+//                       result is a per-read "plan" = the order in which mem_chain2aln visits the seeds.
+//   (seed_chain_kernel  the three in one, one read per thread: the form of round 1, kept for A/B runs and very long rows.)
 //   advance_kernel      one thread per read: a small state machine that walks the plan, applies
 //                       mem_chain2aln's "already covered" test against the read's regions so far and
 //                       emits at most one extension task (left or right) per round; it consumes the
 //                       previous task's result first (right depends on left).
-//   ext_kernel<C>       extend.cu: all tasks of a round, one warp per task, DPX cell updates.
+//   ext3_kernel / ext_kernel<C>   extend3.cu / extend.cu: all tasks of a round, sorted; a thread per PAIR of tasks (packed
+//                       s16x2 DPX cells) for the big classes, a warp per task for small rounds and long queries.
+//   spec_* / tail_kernel   the last reads of a batch: every remaining seed's extensions ahead of the state machine, or one warp
+//                       per read without further host round trips.
 //   The host loops advance -> extend until no read emits a task (one 24-byte read-back per round).
 // Tasks reference the read batch and the reference in place (ExtTaskI, QM_EXTI_INDIRECT); no sequence
 // bytes are materialised.
