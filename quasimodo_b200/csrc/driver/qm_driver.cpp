@@ -6,6 +6,9 @@
 //                      [--bam OUT.bam] [--counts OUT.tsv] [--vcf OUT.vcf [--vcf-gz 0]] [--gpu I | --gpus A,B,..|A-B] [-t THREADS] [-w BAND]
 //                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
 //                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0] [--max-depth N] [--baq 1]
+//                      [-A -B -O -E -L -U -T -d -c -D -W: bwa mem's options of the same letters, -A scaling the others as bwa does]
+//                      [--print-options 1: print the alignment options the command line resolves to and exit (host only)]
+//        an option the command does not know is a usage error
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
 //        semantics, formatted on the device (with --rmdup 1: of the duplicate-free records, as the reference's rule reads them)
 //        --no-rescue 1 = bwa mem -S (mate rescue off; on by default as in the reference's command line)
@@ -881,6 +884,73 @@ Args parse_args(int argc, char **argv, int first)
     return a;
 }
 
+// an option the command does not know is a usage error (a typo such as --min-qual must not silently run with the default)
+void require_known(const Args &a, const char *cmd, std::initializer_list<const char *> known)
+{
+    for (auto &kv : a.kv) {
+        bool ok = false;
+        for (const char *k : known) ok = ok || kv.first == k;
+        if (!ok) die(1, "%s: unknown option '%s%s'", cmd, kv.first.size() > 1 ? "--" : "-", kv.first.c_str());
+    }
+}
+
+// a whole non-negative decimal number or a usage error (atoi would read "6x" as 6 and "x" as 0)
+int32_t parse_int(const std::string &opt, const std::string &v)
+{
+    if (v.empty() || v.size() > 9 || v.find_first_not_of("0123456789") != std::string::npos)
+        die(1, "option -%s: '%s' is not a non-negative integer", opt.c_str(), v.c_str());
+    return (int32_t)atol(v.c_str());
+}
+
+std::vector<std::string> split(const std::string &s, char sep);
+
+// bwa mem's scoring and filtering options on top of the defaults of `bwa mem -k 31` (rules/bwa.smk:15), with bwa's own letters
+// and bwa's rule for -A (fastmap.c main_mem): the match score scales -T -d -B -O -E -L -U unless they are given themselves;
+// -O / -E / -L take "INT[,INT]" (deletion,insertion; 5',3').
+void apply_bwa_options(const Args &a, qm_opt &o)
+{
+    auto one = [&](const char *k, int32_t &x) { if (a.has(k)) x = parse_int(k, a.get(k)); return a.has(k); };
+    auto two = [&](const char *k, int32_t &x, int32_t &y) {
+        if (!a.has(k)) return false;
+        const auto v = split(a.get(k), ',');
+        if (v.size() > 2) die(1, "option -%s takes INT[,INT]", k);
+        x = y = parse_int(k, v[0]);
+        if (v.size() == 2) y = parse_int(k, v[1]);
+        return true;
+    };
+    one("w", o.w);
+    one("k", o.min_seed_len);
+    one("c", o.max_occ);
+    one("W", o.min_chain_weight);
+    if (a.has("D")) {
+        char *end = nullptr;
+        const std::string v = a.get("D");
+        o.drop_ratio = strtof(v.c_str(), &end);
+        if (v.empty() || *end || !(o.drop_ratio >= 0.f && o.drop_ratio <= 1.f)) die(1, "option -D: '%s' is not a fraction in [0, 1]", v.c_str());
+    }
+    const bool hB = one("B", o.b), hT = one("T", o.T), hd = one("d", o.zdrop), hU = one("U", o.pen_unpaired);
+    const bool hO = two("O", o.o_del, o.o_ins), hE = two("E", o.e_del, o.e_ins), hL = two("L", o.pen_clip5, o.pen_clip3);
+    if (one("A", o.a)) {
+        if (!hB) o.b *= o.a;
+        if (!hT) o.T *= o.a;
+        if (!hO) { o.o_del *= o.a; o.o_ins *= o.a; }
+        if (!hE) { o.e_del *= o.a; o.e_ins *= o.a; }
+        if (!hd) o.zdrop *= o.a;
+        if (!hL) { o.pen_clip5 *= o.a; o.pen_clip3 *= o.a; }
+        if (!hU) o.pen_unpaired *= o.a;
+    }
+    if (o.a < 1) die(1, "option -A: the match score must be at least 1");
+    if (o.w < 1) die(1, "option -w: the band width must be at least 1");
+    if (o.max_occ < 1) die(1, "option -c: at least 1");
+    if (o.min_seed_len < 8 || o.min_seed_len > 31) die(1, "option -k: 8 <= k <= 31 (the k-mer index packs a seed into 62 bits)");
+}
+
+void print_options(const qm_opt &o)
+{
+    printf("A=%d B=%d O=%d,%d E=%d,%d L=%d,%d U=%d T=%d d=%d w=%d k=%d c=%d D=%g W=%d flags=%d\n", o.a, o.b, o.o_del, o.o_ins, o.e_del, o.e_ins,
+           o.pen_clip5, o.pen_clip3, o.pen_unpaired, o.T, o.zdrop, o.w, o.min_seed_len, o.max_occ, (double)o.drop_ratio, o.min_chain_weight, o.flags);
+}
+
 std::vector<std::string> split(const std::string &s, char sep)
 {
     std::vector<std::string> out;
@@ -931,6 +1001,19 @@ struct PhaseClock {
 int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
 {
     PhaseClock pc;
+    require_known(a, decontam ? "decontam" : "sample",
+                  {"ref", "r1", "r2", "sample", "bam", "counts", "vcf", "vcf-gz", "out-r1", "out-r2", "keep-contigs", "gpu", "gpus", "t", "threads",
+                   "batch-pairs", "rmdup", "rmdup-bam", "metrics", "no-rescue", "mpileup", "bwa-index", "fm-seeds", "indels", "max-depth", "baq",
+                   "min-mapq", "min-bq", "min-dp", "min-alt", "min-af", "print-options",
+                   "w", "k", "c", "W", "D", "A", "B", "O", "E", "L", "U", "T", "d"});
+    if (atoi(a.get("print-options", "0").c_str())) {   // host only: the alignment options this command line resolves to
+        qm_opt o; qm_opt_default(&o);
+        apply_bwa_options(a, o);
+        if (atoi(a.get("no-rescue", "0").c_str())) o.flags |= QM_F_NO_RESCUE;
+        if (a.has("bwa-index") || atoi(a.get("fm-seeds", "0").c_str())) o.flags |= QM_F_FM_SEEDS;
+        print_options(o);
+        return 0;
+    }
     if (!a.has("ref") || !a.has("r1") || !a.has("r2")) die(1, "--ref, --r1 and --r2 are required");
     const std::string bam = a.get("bam"), counts = a.get("counts"), vcf = a.get("vcf"), o1 = a.get("out-r1"), o2 = a.get("out-r2");
     if (decontam && (o1.empty() || o2.empty())) die(1, "decontam needs --out-r1 and --out-r2");
@@ -962,8 +1045,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     }
     Lib &L = Ls[0];
     qm_opt opt; qm_opt_default(&opt);
-    if (a.has("w")) opt.w = atoi(a.get("w").c_str());
-    if (a.has("k")) opt.min_seed_len = atoi(a.get("k").c_str());
+    apply_bwa_options(a, opt);
     if (atoi(a.get("no-rescue", "0").c_str())) opt.flags |= QM_F_NO_RESCUE;          // bwa mem -S
     qm_pileup_opt popt; qm_pileup_opt_default(&popt);
     if (a.has("min-mapq")) popt.min_mapq = atoi(a.get("min-mapq").c_str());
@@ -1257,6 +1339,7 @@ template <class T> std::vector<T> read_binary(const std::string &path)
 // the BAM/BAI writer alone: records given as a binary file of qm_aln (2 per pair, input order)
 int cmd_bam_from_records(const Args &a, const std::string &cmdline)
 {
+    require_known(a, "bam-from-records", {"ref", "r1", "r2", "alns", "perm", "bam", "gpu", "t"});
     if (!a.has("ref") || !a.has("r1") || !a.has("r2") || !a.has("alns") || !a.has("bam")) die(1, "--ref --r1 --r2 --alns --bam are required");
     Genome g;
     load_refs(a.get("ref"), g);
@@ -1323,6 +1406,7 @@ int main(int argc, char **argv)
     if (cmd == "decontam") return cmd_sample(a, cmdline, true);
     if (cmd == "bam-from-records") return cmd_bam_from_records(a, cmdline);
     if (cmd == "fastq-check") {                        // host only: parse the two mate files as `sample` would, report what is there
+        require_known(a, "fastq-check", {"r1", "r2", "t", "threads"});
         if (!a.has("r1") || !a.has("r2")) die(1, "--r1 --r2 are required");
         g_threads = std::max(1, atoi(a.get("t", a.get("threads", "4")).c_str()));
         FastqPairReader fr(a.get("r1"), a.get("r2"));
@@ -1341,6 +1425,7 @@ int main(int argc, char **argv)
         return 0;
     }
     if (cmd == "vcf-index") {                          // bgzip -c X > X.gz; tabix -p vcf X.gz  (host only: rules/vcfcall.smk:118-119, rules/genome_diff.smk:24-25)
+        require_known(a, "vcf-index", {"vcf", "out", "t"});
         if (!a.has("vcf")) die(1, "--vcf is required");
         write_vcf_gz_tbi(a.get("vcf"), a.get("out", a.get("vcf") + ".gz"), std::max(1, atoi(a.get("t", "2").c_str())));
         return 0;

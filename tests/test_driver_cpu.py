@@ -133,6 +133,28 @@ def test_driver_rejects_bad_input(case):
     assert p.returncode == 2 and "only A/C/G/T" in p.stderr
     p = drvutil.run_driver(["frobnicate"], check=False)
     assert p.returncode == 1
+    # an option the command does not know is a usage error, not a silent run with the default
+    p = drvutil.run_driver(["sample", "--ref", case["fa"], "--r1", case["r1"], "--r2", case["r2"], "--min-qual", "3"], check=False)
+    assert p.returncode == 1 and "unknown option '--min-qual'" in p.stderr
+    p = drvutil.run_driver(["vcf-index", "--vcf", d / "x.vcf", "--gpu", "0"], check=False)
+    assert p.returncode == 1 and "unknown option" in p.stderr
+
+
+def test_driver_takes_bwa_mems_scoring_options():
+    """-A -B -O -E -L -U -T -d -c -D -W mean what they mean to `bwa mem` (rules/bwa.smk:15 passes only -k 31, the defaults below);
+    bwa's fastmap.c scales -T -d -B -O -E -L -U by -A unless they are given themselves"""
+    def resolved(*args):
+        p = drvutil.run_driver(["sample", "--print-options", "1", *args])
+        return dict(kv.split("=") for kv in p.stdout.split())
+    assert resolved() == dict(A="1", B="4", O="6,6", E="1,1", L="5,5", U="17", T="30", d="100", w="100", k="31", c="500", D="0.5", W="0", flags="0")
+    r = resolved("-A", "2")
+    assert (r["B"], r["O"], r["E"], r["L"], r["U"], r["T"], r["d"]) == ("8", "12,12", "2,2", "10,10", "34", "60", "200")
+    r = resolved("-A", "2", "-B", "5", "-O", "5,7", "-E", "2", "-L", "0,9", "-T", "50", "-U", "25", "-d", "20", "-w", "8", "-c", "50", "-D", "0.3", "-W", "3")
+    assert r == dict(A="2", B="5", O="5,7", E="2,2", L="0,9", U="25", T="50", d="20", w="8", k="31", c="50", D="0.3", W="3", flags="0")
+    assert resolved("--no-rescue", "1")["flags"] == "1" and resolved("--fm-seeds", "1")["flags"] == "2"
+    for bad in (["-O", "6x"], ["-O", "1,2,3"], ["-B", "-4"], ["-A", "0"], ["-w", "0"], ["-k", "32"], ["-D", "1.5"], ["-E", ""]):
+        p = drvutil.run_driver(["sample", "--print-options", "1", *bad], check=False)
+        assert p.returncode == 1 and "option -" in p.stderr, bad
 
 
 def test_vcf_gz_and_tabix_index(tmp_path):

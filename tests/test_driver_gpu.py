@@ -192,6 +192,34 @@ def test_driver_batches_do_not_change_the_outputs(tmp_path):
     assert len(outs[0][0]) > 2 * n * 200
 
 
+def test_driver_scoring_options_reach_the_aligner(tmp_path):
+    """bwa mem's -A -B -O -E -L -U -T -d on the driver's command line: the records in the BAM are the oracle's under the same options
+    (the scheme of test_pipeline_nondefault_scoring; -A 2 alone would also double -d and -L, so they are given)"""
+    from oracle import qmo_py, sort_py
+    from quasimodo_b200 import workloads
+    from tests import bamio, drvutil
+    n = 1200
+    W = workloads.config1(n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    opt = qmo_py.default_opt()
+    for name, v in dict(a=2, b=5, o_del=5, e_del=2, o_ins=7, e_ins=1, T=50, pen_unpaired=25).items():
+        setattr(opt, name, v)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns, _, cells, _ = qmo_py.run_sample(ref, codes, quals, lens, opt=opt)
+    base = qmo_py.run_sample(ref, codes, quals, lens)[0]
+    assert (alns["score"] != base["score"]).mean() > 0.5            # the options matter
+    names = drvutil.pair_names("sc", n)
+    fa, r1, r2, bam = str(tmp_path / "ref.fa"), str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq"), str(tmp_path / "s.bam")
+    drvutil.write_fasta(W.ref, fa)
+    drvutil.write_fastq(codes, quals, lens, names, r1, r2)
+    p = drvutil.run_driver(["sample", "--ref", fa, "--r1", r1, "--r2", r2, "--bam", bam, "-A", 2, "-B", 5, "-O", "5,7", "-E", "2,1", "-T", 50,
+                            "-U", 25, "-d", 100, "-L", 5])
+    assert f"{n} pairs aligned, {cells} extension cells" in p.stderr
+    case = dict(W=W, codes=codes, quals=quals, lens=lens, alns=alns, names=names, perm=sort_py.sort_perm(alns), bam=bamio.Bam(bam))
+    assert drvutil.check_bam_records(case) > n
+
+
 def test_driver_decontam(sample_case):
     """rules/decontamination.smk:15-17: pairs with both records unmapped against the contaminant survive, in input order"""
     from oracle import qmo_py
