@@ -7,6 +7,7 @@
 //                      [--rmdup 1 [--rmdup-bam OUT.rmdup.bam] [--metrics FILE]] [--no-rescue 1] [--mpileup OUT.mpileup]
 //                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0] [--max-depth N] [--baq 1]
 //                      [-A -B -O -E -L -U -T -d -c -D -W: bwa mem's options of the same letters, -A scaling the others as bwa does]
+//                      [-q / --min-mapq N] [-Q / --min-bq N] [--count-orphans 1] [--ignore-overlaps 1]: the mpileups' -q -Q -A -x
 //                      [--print-options 1: print the alignment options the command line resolves to and exit (host only)]
 //        an option the command does not know is a usage error
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
@@ -945,8 +946,20 @@ void apply_bwa_options(const Args &a, qm_opt &o)
     if (o.min_seed_len < 8 || o.min_seed_len > 31) die(1, "option -k: 8 <= k <= 31 (the k-mer index packs a seed into 62 bits)");
 }
 
-void print_options(const qm_opt &o)
+// the admission options of both mpileups (rules/vcfcall.smk:39,115 pass none: the defaults), under the tools' names:
+// -q / --min-mapq, -Q / --min-bq, --count-orphans 1 (-A), --ignore-overlaps 1 (-x)
+void apply_mpileup_options(const Args &a, qm_pileup_opt &p)
 {
+    for (const char *k : {"min-mapq", "q"}) if (a.has(k)) p.min_mapq = parse_int(k, a.get(k));
+    for (const char *k : {"min-bq", "Q"}) if (a.has(k)) p.min_bq = parse_int(k, a.get(k));
+    if (a.has("count-orphans")) p.count_orphans = parse_int("count-orphans", a.get("count-orphans")) != 0;
+    if (a.has("ignore-overlaps")) p.ignore_overlaps = parse_int("ignore-overlaps", a.get("ignore-overlaps")) != 0;
+    if (p.min_mapq > 255 || p.min_bq > 93) die(1, "option -q is at most 255 and option -Q at most 93");
+}
+
+void print_options(const qm_opt &o, const qm_pileup_opt &p)
+{
+    printf("q=%d Q=%d count-orphans=%d ignore-overlaps=%d ", p.min_mapq, p.min_bq, p.count_orphans, p.ignore_overlaps);
     printf("A=%d B=%d O=%d,%d E=%d,%d L=%d,%d U=%d T=%d d=%d w=%d k=%d c=%d D=%g W=%d flags=%d\n", o.a, o.b, o.o_del, o.o_ins, o.e_del, o.e_ins,
            o.pen_clip5, o.pen_clip3, o.pen_unpaired, o.T, o.zdrop, o.w, o.min_seed_len, o.max_occ, (double)o.drop_ratio, o.min_chain_weight, o.flags);
 }
@@ -1004,14 +1017,16 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     require_known(a, decontam ? "decontam" : "sample",
                   {"ref", "r1", "r2", "sample", "bam", "counts", "vcf", "vcf-gz", "out-r1", "out-r2", "keep-contigs", "gpu", "gpus", "t", "threads",
                    "batch-pairs", "rmdup", "rmdup-bam", "metrics", "no-rescue", "mpileup", "bwa-index", "fm-seeds", "indels", "max-depth", "baq",
-                   "min-mapq", "min-bq", "min-dp", "min-alt", "min-af", "print-options",
+                   "min-mapq", "q", "min-bq", "Q", "count-orphans", "ignore-overlaps", "min-dp", "min-alt", "min-af", "print-options",
                    "w", "k", "c", "W", "D", "A", "B", "O", "E", "L", "U", "T", "d"});
     if (atoi(a.get("print-options", "0").c_str())) {   // host only: the alignment options this command line resolves to
         qm_opt o; qm_opt_default(&o);
         apply_bwa_options(a, o);
         if (atoi(a.get("no-rescue", "0").c_str())) o.flags |= QM_F_NO_RESCUE;
         if (a.has("bwa-index") || atoi(a.get("fm-seeds", "0").c_str())) o.flags |= QM_F_FM_SEEDS;
-        print_options(o);
+        qm_pileup_opt po; qm_pileup_opt_default(&po);
+        apply_mpileup_options(a, po);
+        print_options(o, po);
         return 0;
     }
     if (!a.has("ref") || !a.has("r1") || !a.has("r2")) die(1, "--ref, --r1 and --r2 are required");
@@ -1048,8 +1063,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     apply_bwa_options(a, opt);
     if (atoi(a.get("no-rescue", "0").c_str())) opt.flags |= QM_F_NO_RESCUE;          // bwa mem -S
     qm_pileup_opt popt; qm_pileup_opt_default(&popt);
-    if (a.has("min-mapq")) popt.min_mapq = atoi(a.get("min-mapq").c_str());
-    if (a.has("min-bq")) popt.min_bq = atoi(a.get("min-bq").c_str());
+    apply_mpileup_options(a, popt);
     // --bwa-index PREFIX: seeds through bwa's own index files PREFIX.bwt + PREFIX.sa (what `bwa index` left next to the genome,
     // rules/index.smk:13) -- bwa-mem's seeds (SMEMs, re-seeding, third round) instead of the k-mer hash index's exact matches;
     // --fm-seeds 1 rebuilds the same index from the FASTA when the files are not at hand

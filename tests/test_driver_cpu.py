@@ -146,13 +146,16 @@ def test_driver_takes_bwa_mems_scoring_options():
     def resolved(*args):
         p = drvutil.run_driver(["sample", "--print-options", "1", *args])
         return dict(kv.split("=") for kv in p.stdout.split())
-    assert resolved() == dict(A="1", B="4", O="6,6", E="1,1", L="5,5", U="17", T="30", d="100", w="100", k="31", c="500", D="0.5", W="0", flags="0")
+    assert resolved() == dict(q="0", Q="13", **{"count-orphans": "0", "ignore-overlaps": "0"}, A="1", B="4", O="6,6", E="1,1", L="5,5", U="17", T="30", d="100", w="100", k="31", c="500", D="0.5", W="0", flags="0")
     r = resolved("-A", "2")
     assert (r["B"], r["O"], r["E"], r["L"], r["U"], r["T"], r["d"]) == ("8", "12,12", "2,2", "10,10", "34", "60", "200")
     r = resolved("-A", "2", "-B", "5", "-O", "5,7", "-E", "2", "-L", "0,9", "-T", "50", "-U", "25", "-d", "20", "-w", "8", "-c", "50", "-D", "0.3", "-W", "3")
-    assert r == dict(A="2", B="5", O="5,7", E="2,2", L="0,9", U="25", T="50", d="20", w="8", k="31", c="50", D="0.3", W="3", flags="0")
+    assert r == dict(q="0", Q="13", **{"count-orphans": "0", "ignore-overlaps": "0"}, A="2", B="5", O="5,7", E="2,2", L="0,9", U="25", T="50", d="20", w="8", k="31", c="50", D="0.3", W="3", flags="0")
     assert resolved("--no-rescue", "1")["flags"] == "1" and resolved("--fm-seeds", "1")["flags"] == "2"
-    for bad in (["-O", "6x"], ["-O", "1,2,3"], ["-B", "-4"], ["-A", "0"], ["-w", "0"], ["-k", "32"], ["-D", "1.5"], ["-E", ""]):
+    r = resolved("-q", "20", "-Q", "25", "--count-orphans", "1", "--ignore-overlaps", "1")       # the mpileups' -q -Q -A -x
+    assert (r["q"], r["Q"], r["count-orphans"], r["ignore-overlaps"]) == ("20", "25", "1", "1")
+    assert resolved("--min-mapq", "7", "--min-bq", "0")["q"] == "7"
+    for bad in (["-Q", "94"], ["-O", "6x"], ["-O", "1,2,3"], ["-B", "-4"], ["-A", "0"], ["-w", "0"], ["-k", "32"], ["-D", "1.5"], ["-E", ""]):
         p = drvutil.run_driver(["sample", "--print-options", "1", *bad], check=False)
         assert p.returncode == 1 and "option -" in p.stderr, bad
 
