@@ -8,6 +8,7 @@
 //                      [--bwa-index PREFIX | --fm-seeds 1] [--indels 0] [--max-depth N] [--baq 1]
 //                      [-A -B -O -E -L -U -T -d -c -D -W: bwa mem's options of the same letters, -A scaling the others as bwa does]
 //                      [-q / --min-mapq N] [-Q / --min-bq N] [--count-orphans 1] [--ignore-overlaps 1]: the mpileups' -q -Q -A -x
+//                      [--stage-ms 1: per-stage device time (CUDA events) of every GPU in the log]
 //                      [--print-options 1: print the alignment options the command line resolves to and exit (host only)]
 //        an option the command does not know is a usage error
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
@@ -1017,7 +1018,7 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     require_known(a, decontam ? "decontam" : "sample",
                   {"ref", "r1", "r2", "sample", "bam", "counts", "vcf", "vcf-gz", "out-r1", "out-r2", "keep-contigs", "gpu", "gpus", "t", "threads",
                    "batch-pairs", "rmdup", "rmdup-bam", "metrics", "no-rescue", "mpileup", "bwa-index", "fm-seeds", "indels", "max-depth", "baq",
-                   "min-mapq", "q", "min-bq", "Q", "count-orphans", "ignore-overlaps", "min-dp", "min-alt", "min-af", "print-options",
+                   "min-mapq", "q", "min-bq", "Q", "count-orphans", "ignore-overlaps", "min-dp", "min-alt", "min-af", "print-options", "stage-ms",
                    "w", "k", "c", "W", "D", "A", "B", "O", "E", "L", "U", "T", "d"});
     if (atoi(a.get("print-options", "0").c_str())) {   // host only: the alignment options this command line resolves to
         qm_opt o; qm_opt_default(&o);
@@ -1058,6 +1059,10 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         const int rc = qm_ctx_create(devs[d], &Ls[d].ctx);
         if (rc != QM_OK) die(3, "qm_ctx_create(%d) failed (%d): no usable B200 (there is no CPU fallback)", devs[d], rc);
     }
+    // --stage-ms 1: the library's CUDA-event stage timers on, one line per GPU in the log at the end (what a Snakemake
+    // `benchmark:` file cannot show: where inside the job the device time went)
+    const bool stage_ms = atoi(a.get("stage-ms", "0").c_str()) != 0;
+    if (stage_ms) for (int d = 0; d < n_gpu; ++d) Ls[d].check(qm_profile_enable(Ls[d].ctx, 1), "qm_profile_enable");
     Lib &L = Ls[0];
     qm_opt opt; qm_opt_default(&opt);
     apply_bwa_options(a, opt);
@@ -1182,6 +1187,25 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
     fprintf(stderr, "[qm_driver] %d GPU(s), %lld batch(es): %.2f s from the first read to the last record, %.3f M pairs/s, %.1f G extension cells/s "
                     "(FASTQ parsing included)\n", n_gpu, (long long)n_batches, loop_s, loop_s > 0 ? n_pairs / loop_s / 1e6 : 0.0,
             loop_s > 0 ? cells / loop_s / 1e9 : 0.0);
+    if (stage_ms) {
+        static const char *const kStage[QM_N_STAGES] = {"seed+chain", "advance", "extend", "pair+cigar", "pileup", "h2d", "d2h", "other", "rescue"};
+        for (int d = 0; d < n_gpu; ++d) {
+            double ms[QM_N_STAGES];
+            int64_t launches[QM_N_STAGES];
+            Ls[d].check(qm_profile_collect(Ls[d].ctx, ms, launches), "qm_profile_collect");
+            std::string line;
+            double tot = 0;
+            int64_t nl = 0;
+            for (int i = 0; i < QM_N_STAGES; ++i) {
+                char buf[64];
+                snprintf(buf, sizeof buf, "%s%s %.1f", i ? ", " : "", kStage[i], ms[i]);
+                line += buf;
+                tot += ms[i];
+                nl += launches[i];
+            }
+            fprintf(stderr, "[qm_driver] GPU %d stages (ms of device time): %s; total %.1f in %lld launches\n", devs[d], line.c_str(), tot, (long long)nl);
+        }
+    }
     if (n_gpu > 1) {
         // per-GPU int32 count tensors -> one NCCL all-reduce over NVLink; every GPU ends up with the sample's totals
         std::vector<qm_ctx *> ctxs;
