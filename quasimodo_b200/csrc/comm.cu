@@ -8,6 +8,7 @@
 // ranks by whatever the host has -- torch.distributed, MPI, a file -- then qm_comm_init_rank), or one process driving N GPUs
 // (qm_comm_init_all, what `qm_driver sample --gpus` uses).  qm_counts_allreduce_nccl takes a caller-owned ncclComm_t.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include "common.cuh"
@@ -35,29 +36,42 @@ struct Nccl {
     std::string why;
 };
 
+Nccl g_nccl;
+
 Nccl *nccl()
 {
-    static Nccl N;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char *names[] = {"libnccl.so.2", "libnccl.so"};
-        for (const char *nm : names) { N.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (N.h) break; }
-        if (!N.h) { N.why = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return; }
-        auto sym = [&](const char *s) { void *p = dlsym(N.h, s); if (!p && N.why.empty()) N.why = std::string("libnccl lacks ") + s; return p; };
-        N.GetUniqueId = (int (*)(ncclUniqueId *))sym("ncclGetUniqueId");
-        N.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))sym("ncclCommInitRank");
-        N.CommInitAll = (int (*)(ncclComm_t *, int, const int *))sym("ncclCommInitAll");
-        N.CommDestroy = (int (*)(ncclComm_t))sym("ncclCommDestroy");
-        N.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclAllReduce");
-        N.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclBroadcast");
-        N.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))sym("ncclAllGather");
-        N.GetVersion = (int (*)(int *))sym("ncclGetVersion");
-        N.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+        // QM_NCCL_LIB=/path/to/libnccl.so.2 names the library when it is not on the loader's path (and nothing else is tried)
+        const char *env = getenv("QM_NCCL_LIB");
+        const char *names[] = {env && *env ? env : "libnccl.so.2", env && *env ? nullptr : "libnccl.so"};
+        for (const char *nm : names) { if (nm) g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+        if (!g_nccl.h) {
+            const char *err = dlerror();               // one call: dlerror() clears the message it returns
+            g_nccl.why = std::string("dlopen(") + names[0] + "): " + (err ? err : "not found");
+            return;
+        }
+        auto sym = [&](const char *s) { void *p = dlsym(g_nccl.h, s); if (!p && g_nccl.why.empty()) g_nccl.why = std::string("libnccl lacks ") + s; return p; };
+        g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))sym("ncclGetUniqueId");
+        g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))sym("ncclCommInitRank");
+        g_nccl.CommInitAll = (int (*)(ncclComm_t *, int, const int *))sym("ncclCommInitAll");
+        g_nccl.CommDestroy = (int (*)(ncclComm_t))sym("ncclCommDestroy");
+        g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclAllReduce");
+        g_nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))sym("ncclBroadcast");
+        g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t))sym("ncclAllGather");
+        g_nccl.GetVersion = (int (*)(int *))sym("ncclGetVersion");
+        g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
     });
-    return (N.h && N.why.empty()) ? &N : nullptr;
+    return (g_nccl.h && g_nccl.why.empty()) ? &g_nccl : nullptr;
 }
 
-const char *nccl_why() { return "NCCL is not available (libnccl.so.2 could not be loaded or lacks a symbol)"; }
+// why nccl() answered null (call it after nccl())
+const char *nccl_why()
+{
+    static std::string msg;
+    msg = "NCCL is not available: " + (g_nccl.why.empty() ? std::string("libnccl.so.2 could not be loaded") : g_nccl.why);
+    return msg.c_str();
+}
 
 }  // namespace
 

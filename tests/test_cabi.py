@@ -51,3 +51,20 @@ def test_no_cpu_fallback(so):
     from quasimodo_b200 import Context, QmError
     with pytest.raises(QmError):
         Context(0)
+
+
+def test_missing_nccl_is_an_error_code_not_a_crash(so):
+    """NCCL is bound at run time (csrc/comm.cu): on a host without it the library still loads, qm_comm_available() says 0 and the
+    communicator entry points answer QM_ENODEV; with the library at hand the same process finds it (fresh processes: the binding
+    happens once)"""
+    import subprocess
+    import sys
+    prog = ("import ctypes, sys; L = ctypes.CDLL(sys.argv[1]); buf = (ctypes.c_uint8 * 128)(); "
+            "print(L.qm_comm_available(), L.qm_comm_unique_id(buf))")
+    env = dict(os.environ, QM_NCCL_LIB="/nonexistent/libnccl.so.2")
+    p = subprocess.run([sys.executable, "-c", prog, so], capture_output=True, text=True, env=env)
+    assert p.returncode == 0 and p.stdout.split() == ["0", "-2"], (p.stdout, p.stderr)      # QM_ENODEV
+    env.pop("QM_NCCL_LIB")
+    p = subprocess.run([sys.executable, "-c", "import ctypes, sys; print(ctypes.CDLL(sys.argv[1]).qm_comm_available())", so],
+                       capture_output=True, text=True, env=env)
+    assert p.returncode == 0 and p.stdout.strip() in ("0", "1")
