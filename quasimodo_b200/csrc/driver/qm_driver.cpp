@@ -724,6 +724,26 @@ std::string trim_float3(double x)
 // program/mummer2vcf.py for the truth set and of bcftools).
 struct IndelCall { qm_indel a; int dp; double af, qual; };
 
+// two allele tables sorted by key -> one sorted table, the counts of an allele both hold added up
+std::vector<qm_indel> merge_indel_tables(const std::vector<qm_indel> &a, const qm_indel *b, int64_t nb)
+{
+    std::vector<qm_indel> out;
+    out.reserve(a.size() + (size_t)nb);
+    size_t i = 0;
+    int64_t j = 0;
+    while (i < a.size() || j < nb) {
+        if (j >= nb || (i < a.size() && a[i].key < b[j].key)) out.push_back(a[i++]);
+        else if (i >= a.size() || b[j].key < a[i].key) out.push_back(b[j++]);
+        else {
+            qm_indel x = a[i++];
+            x.n_fwd += b[j].n_fwd; x.n_rev += b[j].n_rev;
+            ++j;
+            out.push_back(x);
+        }
+    }
+    return out;
+}
+
 void write_vcf(const std::string &path, const Genome &g, const std::string &sample, const std::string &ref_path,
                const std::vector<qm_call> &calls, const std::vector<IndelCall> &indels)
 {
@@ -1215,7 +1235,6 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
         std::vector<std::thread> team;
         for (int d = 0; d < n_gpu; ++d)
             team.emplace_back([&, d]() {
-                Ls[d].check(qm_sample_set_comm(smps[d], nullptr), "qm_sample_set_comm");
                 Ls[d].check(qm_counts_allreduce(Ls[d].ctx, comms[d], qm_sample_counts(smps[d]), (int64_t)QM_NCH * (int64_t)g.codes.size(), nullptr),
                             "qm_counts_allreduce");
                 Ls[d].check(qm_sample_stats_sync(smps[d], nullptr, nullptr, nullptr), "qm_sample_stats_sync");
@@ -1270,6 +1289,18 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
             std::vector<qm_indel> tab((size_t)1 << 18);
             int64_t nt = 0;
             L.check(qm_indel_table_fetch_host(qm_sample_indel_table(smp), idx, tab.data(), (int64_t)tab.size(), &nt), "qm_indel_table_fetch_host");
+            if (n_gpu > 1) {
+                // the sparse part of the merge ("host merge of the sparse indel-allele table"): every GPU tallied the
+                // alleles of its own batches; the tables (a few thousand records, sorted by key) are added up by key here
+                tab.resize((size_t)nt);
+                std::vector<qm_indel> other((size_t)1 << 18);
+                for (int d = 1; d < n_gpu; ++d) {
+                    int64_t no = 0;
+                    Ls[d].check(qm_indel_table_fetch_host(qm_sample_indel_table(smps[d]), idxs[d], other.data(), (int64_t)other.size(), &no), "qm_indel_table_fetch_host");
+                    tab = merge_indel_tables(tab, other.data(), no);
+                }
+                nt = (int64_t)tab.size();
+            }
             std::vector<int32_t> rows(g.codes.size() * QM_NCH);
             L.check(qm_sample_counts_host(smp, rows.data()), "qm_sample_counts_host");
             for (int64_t i = 0; i < nt; ++i) {

@@ -479,6 +479,7 @@ int qm_pileup_accumulate_masked(qm_ctx *ctx, const qm_index *idx, const qm_pileu
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t L = idx->v.l_pac;
+    if (2 * (L + 1) > 0x7fffffffll) return qm_fail(ctx, QM_ELIMIT, "qm_pileup_accumulate: a reference of %lld bases is beyond the 2^30 the coverage scan indexes", (long long)L);
     // scratch 25: difference arrays [2][L + 1] | minus [2][L] | cub temp
     const size_t cov_bytes = (size_t)2 * (L + 1) * 4, minus_bytes = (size_t)2 * L * 4;
     const size_t o_minus = (cov_bytes + 255) & ~(size_t)255, o_cub = (o_minus + minus_bytes + 255) & ~(size_t)255;

@@ -331,7 +331,8 @@ int qm_sample_kept_alns_host(qm_sample *s, qm_aln *h_alns, int64_t max_records)
 int qm_sample_set_comm(qm_sample *s, qm_comm *comm)
 {
     if (!s) return QM_EINVAL;
-    if (s->n_pairs != 0) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_set_comm: pairs were already added; reset the sample first");
+    // clearing is always allowed; a communicator has to be there before the first pairs (it decides whose insert-size model is used)
+    if (comm && s->n_pairs != 0) return qm_fail(s->ctx, QM_EINVAL, "qm_sample_set_comm: pairs were already added; reset the sample first");
     s->comm = comm;
     return QM_OK;
 }
