@@ -1466,7 +1466,7 @@ int cmd_bam_from_records(const Args &a, const std::string &cmdline)
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records|vcf-index|fastq-check [options]   (%s)", qm_version());
+    if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records|vcf-index|fastq-check|selftest [options]   (%s)", qm_version());
     std::string cmdline;
     for (int i = 0; i < argc; ++i) { if (i) cmdline += ' '; cmdline += argv[i]; }
     const std::string cmd = argv[1];
@@ -1497,6 +1497,18 @@ int main(int argc, char **argv)
         require_known(a, "vcf-index", {"vcf", "out", "t"});
         if (!a.has("vcf")) die(1, "--vcf is required");
         write_vcf_gz_tbi(a.get("vcf"), a.get("out", a.get("vcf") + ".gz"), std::max(1, atoi(a.get("t", "2").c_str())));
+        return 0;
+    }
+    if (cmd == "selftest") {                           // host-only checks of the driver's own helpers (tests/test_driver_cpu.py)
+        auto rec = [](uint64_t key, int f, int r) { qm_indel x; memset(&x, 0, sizeof x); x.key = key; x.n_fwd = f; x.n_rev = r; return x; };
+        const std::vector<qm_indel> A = {rec(3, 1, 0), rec(7, 2, 2), rec(9, 0, 1)}, B = {rec(1, 1, 1), rec(7, 0, 3), rec(9, 4, 0), rec(12, 1, 0)};
+        const std::vector<qm_indel> M = merge_indel_tables(A, B.data(), (int64_t)B.size());
+        const int64_t want[5][3] = {{1, 1, 1}, {3, 1, 0}, {7, 2, 5}, {9, 4, 1}, {12, 1, 0}};
+        bool ok = M.size() == 5;
+        for (size_t i = 0; ok && i < 5; ++i) ok = (int64_t)M[i].key == want[i][0] && M[i].n_fwd == want[i][1] && M[i].n_rev == want[i][2];
+        ok = ok && merge_indel_tables(A, nullptr, 0).size() == 3 && merge_indel_tables({}, B.data(), 4).size() == 4 && merge_indel_tables({}, nullptr, 0).empty();
+        if (!ok) die(2, "selftest: merge_indel_tables is wrong");
+        printf("selftest ok\n");
         return 0;
     }
     die(1, "unknown command '%s'", cmd.c_str());

@@ -236,3 +236,8 @@ def test_fastq_side_parses_what_bwa_would(tmp_path):
     short.write_text("".join(records(1).split("@r29999/1")[:1]))
     p = drvutil.run_driver(["fastq-check", "--r1", short, "--r2", p2], check=False)
     assert p.returncode == 2 and "more records" in p.stderr
+
+
+def test_driver_selftest():
+    """host-only checks of helpers that otherwise only run with several GPUs (the by-key merge of the per-GPU indel allele tables)"""
+    assert drvutil.run_driver(["selftest"]).stdout.strip() == "selftest ok"
