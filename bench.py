@@ -177,6 +177,61 @@ def cpu_arm(plan, steps, warmup, sample_pairs):
     return sample_pairs * len(times) / tot, tot / len(times) * 1e3
 
 
+def upstream_tools():
+    """the reference's own CPU path is `bwa mem | samtools view | samtools sort` + `bcftools mpileup | call`; the image
+    has none of them (checked at run time: if they ever appear, the CPU arms run them instead of the port).  -> {name: path or None}"""
+    import shutil
+    return {t: shutil.which(t) for t in ("bwa", "samtools", "bcftools")}
+
+
+def upstream_arm(plan, steps, warmup, sample_pairs, threads):
+    """the reference's own command lines (rules/bwa.smk:15-18, rules/vcfcall.smk:115-117) on FASTQ files of the same simulated
+    pairs; `bwa index` and the FASTQ / FASTA writing are outside the timed region (the index is a one-off rule, rules/index.smk:13).
+    Only reachable when bwa, samtools and bcftools are on PATH.  -> (pairs/s, ms/step)"""
+    import subprocess
+    import tempfile
+    import numpy as np
+    from oracle import qmo_py
+    lut = np.frombuffer(b"ACGTN", np.uint8)
+    times = []
+    with tempfile.TemporaryDirectory(prefix="qm_upstream_") as d:
+        indexed = {}
+        for i in range(warmup + steps):
+            W = plan.make(i % plan.n_inputs)
+            key = "|".join(W.ref_stems)
+            if key not in indexed:
+                fa = os.path.join(d, f"ref{len(indexed)}.fa")
+                with open(fa, "wb") as fh:
+                    off = 0
+                    for name, ln in zip(W.ref.names, W.ref.lens):
+                        fh.write(b">" + str(name).encode() + b"\n")
+                        seq = lut[W.ref.codes[off:off + ln]].tobytes()
+                        fh.write(b"\n".join(seq[j:j + 70] for j in range(0, ln, 70)) + b"\n")
+                        off += ln
+                subprocess.run(["bwa", "index", fa], check=True, capture_output=True)
+                indexed[key] = fa
+            fa = indexed[key]
+            codes, quals = qmo_py.simulate_pairs(W, plan.window(i % plan.n_inputs), sample_pairs)
+            fq = [os.path.join(d, f"r{m + 1}.fq") for m in (0, 1)]
+            for m in (0, 1):
+                seq, q = lut[np.minimum(codes[m::2, :plan.L], 4)], (quals[m::2, :plan.L] + 33).astype(np.uint8)
+                with open(fq[m], "wb") as fh:
+                    for r in range(sample_pairs):
+                        fh.write(b"@sim.%d/%d\n" % (r, m + 1) + seq[r].tobytes() + b"\n+\n" + q[r].tobytes() + b"\n")
+            bam, vcf = os.path.join(d, "s.bam"), os.path.join(d, "s.vcf")
+            cmd = (f"set -e -o pipefail; bwa mem -k 31 -w {plan.w} -t {threads} {fa} {fq[0]} {fq[1]} 2>/dev/null | samtools view -Shb - | "
+                   f"samtools sort -@ {threads} - -o {bam}; samtools index {bam}; "
+                   f"bcftools mpileup --threads {threads} -Ou -f {fa} {bam} 2>/dev/null | bcftools call --threads {threads} -p 0.01 --ploidy 1 -mv -Ob | "
+                   f"bcftools view -i 'INFO/DP>=10' - > {vcf}")
+            t0 = time.perf_counter()
+            subprocess.run(["bash", "-c", cmd], check=True, capture_output=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    tot = sum(times)
+    return sample_pairs * len(times) / tot, tot / len(times) * 1e3
+
+
 def calibrated_cpu_sample(plan, seconds, cap):
     """pick a sample size that costs about `seconds` of CPU wall time"""
     rate, _ = cpu_arm(plan, 1, 0, 20_000)
@@ -194,15 +249,25 @@ def run_reference(args):
     cores = qmo_py.n_threads()
     per_step = max(20_000, int(calibrated_cpu_sample(plan, args.cpu_seconds, per_rank) / max(1, args.steps + args.warmup) * 4))
     per_step = min(per_step - per_step % 1000, plan.total)
-    value, ms = cpu_arm(plan, args.steps, args.warmup, per_step)
-    sample = (f"{per_step} pairs per step (prefix of each step's sample), oracle port: seeding+extension+mate rescue+pairing+CIGAR+pileup; "
-              f"build {qmo_py.BUILD_KIND}")
+    tools, kind, note = upstream_tools(), "port", CPU_NOTE
+    value = None
+    if all(tools.values()):                           # the reference's own binaries, if the image ever has them
+        try:
+            value, ms = upstream_arm(plan, args.steps, args.warmup, per_step, cores)
+            kind, note = "reference", "upstream bwa + samtools + bcftools found on PATH: the reference's own command lines (rules/bwa.smk:15-18, rules/vcfcall.smk:115-117)"
+            sample = f"{per_step} pairs per step (prefix of each step's sample) as FASTQ through bwa mem | samtools view | sort | index + bcftools mpileup | call | view"
+        except Exception as e:                         # a broken install must not take the arm down: fall back to the port and say so
+            value, note = None, CPU_NOTE + f" (upstream binaries on PATH failed: {type(e).__name__}: {str(e)[:200]})"
+    if value is None:
+        value, ms = cpu_arm(plan, args.steps, args.warmup, per_step)
+        sample = (f"{per_step} pairs per step (prefix of each step's sample), oracle port: seeding+extension+mate rescue+pairing+CIGAR+pileup; "
+                  f"build {qmo_py.BUILD_KIND}")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if plan.strong else "weak",
            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": plan.config_dict(args.gpus, per_rank),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0, "note": CPU_NOTE}
+           "gpu_launches": 0, "note": note, "upstream_tools": tools}
     print(json.dumps(out), file=_json_out, flush=True)
 
 
