@@ -246,10 +246,10 @@ bool read_batch(FastqPairReader &fr, int64_t max_pairs, RawBatch &out)
             if (!r.next_view(p, n)) return;
             while (n == 0) if (!r.next_view(p, n)) return;              // blank lines between records
             if (p[0] != '@') die(2, "%s: FASTQ header expected, got '%.*s'", r.path.c_str(), (int)std::min<size_t>(n, 40), p);
-            // bwa: the name up to the first whitespace, a trailing /1 or /2 dropped
+            // bwa: the name up to the first whitespace, a trailing /<digit> dropped (bwa.c trim_readno)
             size_t e = 1;
             while (e < n && !isspace((unsigned char)p[e])) ++e;
-            if (e > 3 && p[e - 2] == '/' && (p[e - 1] == '1' || p[e - 1] == '2')) e -= 2;
+            if (e > 3 && p[e - 2] == '/' && isdigit((unsigned char)p[e - 1])) e -= 2;
             v.noff.push_back((uint32_t)v.names.size());
             v.names.insert(v.names.end(), p + 1, p + e);
             v.names.push_back('\0');
@@ -275,6 +275,22 @@ bool read_batch(FastqPairReader &fr, int64_t max_pairs, RawBatch &out)
     t2.join();
     if (out.a.n < out.b.n) die(2, "%s has more records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
     if (out.a.n > out.b.n) die(2, "%s has fewer records than %s", fr.r2.path.c_str(), fr.r1.path.c_str());
+    // bwa refuses mates whose names differ once /1 and /2 are dropped (bwamem_pair.c mem_sam_pe: "paired reads have different
+    // names"): files that went out of step pair every read with a stranger and still align -- fail like bwa instead
+    std::atomic<size_t> first_bad{out.a.n};
+    parallel_ranges(out.a.n, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i)
+            if (strcmp(out.a.names.data() + out.a.noff[i], out.b.names.data() + out.b.noff[i]) != 0) {
+                size_t cur = first_bad.load();
+                while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {}
+                return;
+            }
+    });
+    if (first_bad.load() < out.a.n) {
+        const size_t i = first_bad.load();
+        die(2, "paired reads have different names: \"%s\" (%s), \"%s\" (%s)", out.a.names.data() + out.a.noff[i], fr.r1.path.c_str(),
+            out.b.names.data() + out.b.noff[i], fr.r2.path.c_str());
+    }
     return out.a.n > 0;
 }
 

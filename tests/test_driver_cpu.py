@@ -236,6 +236,11 @@ def test_fastq_side_parses_what_bwa_would(tmp_path):
     short.write_text("".join(records(1).split("@r29999/1")[:1]))
     p = drvutil.run_driver(["fastq-check", "--r1", short, "--r2", p2], check=False)
     assert p.returncode == 2 and "more records" in p.stderr
+    # mate files out of step (a record lost in one of them): bwa's "paired reads have different names", not a silent mis-pairing
+    shifted = tmp_path / "shifted.fq"
+    shifted.write_text(records(1).replace(f"@r100/1 extra words\n{seqs[100]}\n+\n{'I' * len(seqs[100])}\n", "", 1) + f"@tail/1\nACGT\n+\nIIII\n")
+    p = drvutil.run_driver(["fastq-check", "--r1", shifted, "--r2", p2], check=False)
+    assert p.returncode == 2 and 'paired reads have different names: "r101"' in p.stderr and '"r100"' in p.stderr, p.stderr[-300:]
 
 
 def test_driver_selftest():
