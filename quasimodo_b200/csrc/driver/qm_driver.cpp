@@ -1018,6 +1018,12 @@ void load_refs(const std::string &spec, Genome &g)
 {
     for (auto &p : split(spec, ',')) read_fasta(p, g);
     if (g.names.size() > QM_MAX_CONTIGS) die(2, "%zu contigs: at most %d are supported", g.names.size(), QM_MAX_CONTIGS);
+    for (size_t i = 0; i < g.names.size(); ++i) {
+        if (g.lens[i] <= 0) die(2, "contig %s is empty", g.names[i].c_str());
+        // the BAI / TBI binning scheme (and with it `samtools index`, `tabix -p vcf`) ends at 2^29 bases per contig
+        if (g.lens[i] > ((int64_t)1 << 29)) die(2, "contig %s has %lld bases: BAI / TBI indexes address at most 2^29 per contig", g.names[i].c_str(), (long long)g.lens[i]);
+        for (size_t j = 0; j < i; ++j) if (g.names[j] == g.names[i]) die(2, "contig name %s occurs twice in the reference", g.names[i].c_str());
+    }
 }
 
 int sort_key_bits(const Genome &g, int &pos_bits)

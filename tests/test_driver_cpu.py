@@ -131,6 +131,11 @@ def test_driver_rejects_bad_input(case):
     p = drvutil.run_driver(["bam-from-records", "--ref", bad, "--r1", case["r1"], "--r2", case["r2"], "--alns", d / "alns.bin",
                             "--perm", d / "perm.bin", "--bam", d / "x.bam"], check=False)
     assert p.returncode == 2 and "only A/C/G/T" in p.stderr
+    for text, msg in ((">c1\nACGT\n>c2\n>c3\nAC\n", "contig c2 is empty"), (">c1 x\nACGT\n>c1 y\nAC\n", "occurs twice")):
+        open(bad, "w").write(text)
+        p = drvutil.run_driver(["bam-from-records", "--ref", bad, "--r1", case["r1"], "--r2", case["r2"], "--alns", d / "alns.bin",
+                                "--perm", d / "perm.bin", "--bam", d / "x.bam"], check=False)
+        assert p.returncode == 2 and msg in p.stderr, p.stderr
     p = drvutil.run_driver(["frobnicate"], check=False)
     assert p.returncode == 1
     # an option the command does not know is a usage error, not a silent run with the default
