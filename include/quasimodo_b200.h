@@ -247,7 +247,10 @@ int qm_counts_to_rows(qm_ctx *ctx, const qm_index *idx, const int32_t *d_planes,
  * the first min(n, QM_PESTAT_PAIRS) pairs handed in, or from that prefix of the sample given explicitly
  * (qm_sample_estimate_pestat: a shard that does not start at pair 0 passes the sample's first pairs; every
  * GPU derives the same model, no collective), or set directly, so that the records do not depend on batching
- * or sharding. */
+ * or sharding.
+ * Contract of the read arrays (every entry below): read r occupies row r of `stride` bytes, its length lens[r] lies in
+ * [0, stride], stride <= 512 (QM_ELIMIT otherwise); the lengths are the caller's word -- the device entry cannot check them
+ * without a pass over the data, the driver checks them while it parses FASTQ. */
 #define QM_PESTAT_PAIRS 65536
 typedef struct qm_sample qm_sample;
 int  qm_sample_begin(qm_ctx *ctx, const qm_index *idx, const qm_opt *opt, const qm_pileup_opt *popt, qm_sample **out);

@@ -107,6 +107,8 @@ int sample_chunk(qm_sample *s, const uint8_t *d_codes, const uint8_t *d_quals, i
                  int64_t n, int64_t pair_id0, qm_aln *d_alns_out, cudaStream_t st, cudaEvent_t quals_ready = nullptr)
 {
     qm_ctx *ctx = s->ctx;
+    // the pileup stages a pair's reads in 512-byte rows and would leave longer reads out of the counts without a word
+    if (stride > 512) return qm_fail(ctx, QM_ELIMIT, "rows of %d bases: reads longer than 512 bases are not supported", stride);
     if ((s->rmdup || s->max_depth > 0) && s->rmdup_finished)
         return qm_fail(ctx, QM_EINVAL, "pairs added after qm_sample_rmdup_finish: reset the sample first");
     int rc = qm_align_se(ctx, s->idx, &s->opt, d_codes, stride, d_lens, 2 * n, s->d_regs, s->d_n_regs, s->d_cells, st);
