@@ -101,7 +101,7 @@ int qm_extend_batch_host(qm_ctx *ctx, const qm_opt *opt, const uint8_t *h_seq, s
                          const qm_ext_task *h_tasks, int64_t n_tasks, qm_ext_result *h_out);
 
 /* ---- reference index (replaces `bwa index`, rules/index.smk:13) ----
- * k-mer hash index (k = opt->min_seed_len <= 32) over the forward strands of the concatenated contigs
+ * k-mer hash index (k = opt->min_seed_len, 8 <= k <= 31) over the forward strands of the concatenated contigs
  * plus the 2-bit packed reference; both live in device memory owned by the index object. */
 typedef struct qm_index qm_index;
 #define QM_MAX_CONTIGS 16
