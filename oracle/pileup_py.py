@@ -1,0 +1,114 @@
+"""ORACLE (test infrastructure) -- a SECOND, independently formulated restatement of the per-column counting of
+`bcftools mpileup -B` (reference call site rules/vcfcall.smk:115; spec SURVEY.md A.8-A.9), written to be diffed against
+oracle/qmo_pileup.c ("write two independent restatements and diff them" -- neither can be pinned to
+bcftools, which is absent from the image).
+
+Where qmo_pileup.c walks a pair's two CIGARs side by side with two cursors, this one goes the way htslib does: every read
+becomes a list of pileup entries (reference position -> query position / deleted), the mate-overlap rewrite looks the second
+mate's positions up in a hash of the first's (htslib overlap_push / tweak_overlap_quality), and the tensor is tallied from the
+entries at the end.  Pure Python: for a few thousand pairs."""
+import numpy as np
+
+NCH = 16
+M, I, D, N_, S = 0, 1, 2, 3, 4
+
+
+def _entries(aln, L):
+    """-> (cols, ins_after, del_after, first_col): cols = [(ref_pos, query_pos or None when the base is deleted)] in SEQ
+    orientation; ins_after / del_after = reference positions of the aligned base in front of an insertion / a deletion"""
+    cols, ins_after, del_after = [], [], []
+    q, r, last = 0, int(aln["pos"]), None
+    for c in aln["cigar"][:int(aln["n_cigar"])]:
+        op, ln = int(c) & 15, int(c) >> 4
+        if op == M:
+            cols.extend((r + j, q + j) for j in range(ln))
+            q += ln
+            r += ln
+            last = r - 1
+        elif op == I:
+            if last is not None:
+                ins_after.append(last)
+            q += ln
+        elif op == S:
+            q += ln
+        elif op == D:
+            if last is not None:
+                del_after.append(last)
+            cols.extend((r + j, None) for j in range(ln))
+            r += ln
+        elif op == N_:
+            r += ln
+    assert q == L, (q, L)
+    aligned = [p for p, x in cols if x is not None]
+    return cols, ins_after, del_after, (aligned[0] if aligned else None)
+
+
+def _admitted(aln, min_mapq, count_orphans):
+    f = int(aln["flag"])
+    if f & (0x4 | 0x100 | 0x200 | 0x400):
+        return False
+    if int(aln["n_cigar"]) in (0, 255):                    # no alignment stored / CIGAR beyond the record's room
+        return False
+    if int(aln["mapq"]) < min_mapq:
+        return False
+    if (f & 0x1) and not (f & 0x2) and not count_orphans:
+        return False
+    return True
+
+
+def count_tensor(ref_offs, l_pac, alns, codes, quals, lens, min_mapq=0, min_bq=13, count_orphans=False, ignore_overlaps=False):
+    """-> int32 [l_pac, 16], channels as include/quasimodo_b200.h documents them"""
+    counts = np.zeros((l_pac, NCH), dtype=np.int64)
+    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+    for pi in range(len(alns) // 2):
+        reads = []
+        for e in (0, 1):
+            a, L = alns[2 * pi + e], int(lens[2 * pi + e])
+            if not _admitted(a, min_mapq, count_orphans):
+                reads.append(None)
+                continue
+            seq, ql = np.minimum(codes[2 * pi + e, :L], 4), quals[2 * pi + e, :L].astype(np.int64)
+            if int(a["flag"]) & 0x10:                      # BAM stores the reverse strand's read reverse-complemented
+                seq, ql = comp[seq[::-1]], ql[::-1]
+            cols, ia, da, first = _entries(a, L)
+            reads.append(dict(a=a, L=L, seq=seq, q=ql.copy(), cols=cols, ia=ia, da=da, first=first, rev=bool(int(a["flag"]) & 0x10)))
+        x, y = reads
+        if (not ignore_overlaps and x is not None and y is not None and int(x["a"]["rid"]) == int(y["a"]["rid"])
+                and (int(x["a"]["flag"]) & 0x2) and not (int(x["a"]["flag"]) & 0x8)
+                and abs(int(x["a"]["tlen"])) < 2 * x["L"] and abs(int(y["a"]["tlen"])) < 2 * y["L"]):
+            # the mate the sorted BAM delivers first is hashed, the other one is matched against it
+            kx, ky = (int(x["a"]["pos"]), x["rev"]), (int(y["a"]["pos"]), y["rev"])
+            first, second = (x, y) if kx <= ky else (y, x)
+            where = {p: qp for p, qp in first["cols"] if qp is not None}
+            for p, qb in second["cols"]:
+                if qb is None or p not in where:
+                    continue
+                qa = where[p]
+                if first["seq"][qa] == second["seq"][qb]:
+                    first["q"][qa] = min(200, first["q"][qa] + second["q"][qb])
+                    second["q"][qb] = 0
+                elif first["q"][qa] >= second["q"][qb]:
+                    first["q"][qa] = int(0.8 * first["q"][qa])
+                    second["q"][qb] = 0
+                else:
+                    second["q"][qb] = int(0.8 * second["q"][qb])
+                    first["q"][qa] = 0
+        for rd in reads:
+            if rd is None:
+                continue
+            base = int(ref_offs[int(rd["a"]["rid"])])
+            strand = 6 if rd["rev"] else 0
+            if rd["first"] is not None:
+                counts[base + rd["first"], 15] += 1
+            for p, qp in rd["cols"]:
+                if qp is None:
+                    counts[base + p, 11 if rd["rev"] else 5] += 1
+                    continue
+                counts[base + p, 14] += 1
+                if rd["q"][qp] >= min_bq:
+                    counts[base + p, strand + int(rd["seq"][qp])] += 1
+            for p in rd["ia"]:
+                counts[base + p, 12] += 1
+            for p in rd["da"]:
+                counts[base + p, 13] += 1
+    return counts.astype(np.int32)

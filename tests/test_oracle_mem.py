@@ -168,3 +168,36 @@ def test_mem_patch_reg_has_nothing_to_patch_on_baseline_data():
         assert (a0["n_regs"] > 1).sum() > 50           # there ARE reads with several hits: repeats, other strands -- not collinear pairs
     done = C.c_longlong.in_dll(L, "g_qmo_patch_done").value
     assert done == 0 and C.c_longlong.in_dll(L, "g_qmo_patch_tried").value - tried0 <= 5
+
+
+@pytest.mark.parametrize("cfg, n, popt", [
+    ("cfg1", 1200, {}),                                                          # 2 x 150, substitutions only, mates overlap often
+    ("cfg5", 600, {}),                                                           # 2 x 250 with simulated indels
+    ("cfg3", 800, {}),                                                           # three contigs, unmapped contaminant reads
+    ("cfg1", 600, dict(min_bq=25, min_mapq=30)),
+    ("cfg5", 400, dict(count_orphans=1, ignore_overlaps=1)),
+])
+def test_count_tensor_equals_an_independent_restatement(cfg, n, popt):
+    """bcftools is not in the image, so the counting oracle cannot be pinned; SURVEY.md Appendix A asks for two independent
+    restatements diffed against each other instead.  oracle/pileup_py.py goes htslib's way (pileup entries per read, the second
+    mate looked up in a hash of the first), oracle/qmo_pileup.c walks the pair's CIGARs with two cursors: same tensor, every channel."""
+    from oracle import pileup_py
+    W = {"cfg1": workloads.config1, "cfg5": workloads.config5, "cfg3": workloads.config3}[cfg](n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    L = W.params.read_len
+    lens = np.full(2 * n, L, np.int32)
+    lens[[3, 10]] = [L - 30, L // 2]                                             # ragged reads
+    codes[3, L - 30:] = 4
+    codes[10, L // 2:] = 4
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    alns = qmo_py.run_sample(ref, codes, quals, lens, opt=opt)[0]
+    po = qmo_py.PileupOpt(0, 13, 0, 0)
+    for k, v in popt.items():
+        setattr(po, k, v)
+    want = qmo_py.pileup(ref, alns, codes, quals, lens, po)
+    offs = np.concatenate([[0], np.cumsum(W.ref.lens)])
+    got = pileup_py.count_tensor(offs, ref.l_pac, alns, codes, quals, lens, po.min_mapq, po.min_bq, bool(po.count_orphans), bool(po.ignore_overlaps))
+    assert np.array_equal(got, want), np.argwhere(got != want)[:5]
+    assert want[:, 14].sum() > n * L and (cfg != "cfg5" or (want[:, 12].sum() > 0 and want[:, 13].sum() > 0 and want[:, 5].sum() > 0))
