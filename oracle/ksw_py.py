@@ -121,3 +121,87 @@ def ksw_align2(query, target, minsc, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=
         if s2 == sc:
             tb, qb = te - t2, qe - q2
     return sc, te, qe, score2, te2, tb, qb
+
+
+NEG_INF = -0x40000000
+
+
+def ksw_global2(query, target, w, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1):
+    """Banded global alignment with traceback, written as WHOLE MATRICES and a traceback that
+    re-derives every decision from the matrix values -- oracle/qmo_ksw.c keeps one rolling row and a byte of decision bits per
+    cell.  M[i][j] = "arrive diagonally" (bwa's m), E[i][j] / F[i][j] = the best score ending in a deletion / insertion when
+    cell (i, j) is entered (gaps open from m, not from h); cells outside the band are minus infinity.
+    -> (score, [(op, len)...]) with op 0 = M, 1 = I, 2 = D"""
+    qlen, tlen = len(query), len(target)
+    oe_del, oe_ins = o_del + e_del, o_ins + e_ins
+
+    def band(i):
+        return max(0, i - w), min(qlen, i + w + 1)
+
+    def h_above(i, j):                  # H[i][j] for i = -1 or j = -1 (the borders), minus infinity outside the band
+        if i == -1 and j == -1:
+            return 0
+        if i == -1:
+            return -(o_ins + e_ins * (j + 1)) if j + 1 <= w else NEG_INF
+        return -(o_del + e_del * (i + 1)) if band(i)[0] == 0 else NEG_INF
+
+    H, M, E, F = {}, {}, {}, {}
+    for i in range(tlen):
+        lo, hi = band(i)
+        for j in range(lo, hi):
+            if i > 0 and j > 0:
+                diag = H.get((i - 1, j - 1), NEG_INF)
+            elif i == 0:
+                diag = h_above(-1, j - 1)
+            else:
+                diag = h_above(i - 1, -1)
+            M[i, j] = diag + score(a, b, target[i], query[j])
+            # deletion: extend the one that ended at (i-1, j), or open from the diagonal arrival there
+            E[i, j] = max(E[i - 1, j] - e_del, M[i - 1, j] - oe_del) if (i - 1, j) in M else NEG_INF
+            # insertion: likewise along the row; the first cell of a row's band has none
+            F[i, j] = max(F[i, j - 1] - e_ins, M[i, j - 1] - oe_ins) if j > lo else NEG_INF
+            H[i, j] = max(M[i, j], E[i, j], F[i, j])
+    if tlen == 0:
+        final = h_above(-1, qlen - 1)
+    elif band(tlen - 1)[1] == qlen and qlen > 0:
+        final = H[tlen - 1, qlen - 1]
+    elif qlen == 0:
+        final = h_above(tlen - 1, -1)
+    else:
+        final = NEG_INF                  # the band never reaches the last column (the rolling row's cell holds minus infinity)
+    ops = []
+
+    def push(op, n=1):
+        if ops and ops[-1][0] == op:
+            ops[-1][1] += n
+        else:
+            ops.append([op, n])
+
+    i = tlen - 1
+    k = min(i + w + 1, qlen) - 1
+    state = 0
+    while i >= 0 and k >= 0:
+        m, e, f = M[i, k], E[i, k], F[i, k]
+        if state == 0:                  # how was H[i][k] reached: diagonal wins ties over deletion, both over insertion
+            state = 0 if m >= e else 1
+            if max(m, e) < f:
+                state = 2
+        elif state == 1:                # we came up a deletion column: was E[i+1][k] an extension of E[i][k] or opened from m?
+            state = 1 if e - e_del > m - oe_del else 0
+        else:
+            state = 2 if f - e_ins > m - oe_ins else 0
+        if state == 0:
+            push(0)
+            i -= 1
+            k -= 1
+        elif state == 1:
+            push(2)
+            i -= 1
+        else:
+            push(1)
+            k -= 1
+    if i >= 0:
+        push(2, i + 1)
+    if k >= 0:
+        push(1, k + 1)
+    return final, [(op, n) for op, n in reversed(ops)]

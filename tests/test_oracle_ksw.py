@@ -124,3 +124,40 @@ def test_align2_known_answers():
     t2 = q + [3] * 20 + q
     r = qmo_py.ksw_align2(q, t2, 5)[0]
     assert r[0] == 12 and r[1] == 11 and r[3] == 12 and r[4] == 43 and (r[5], r[6]) == (0, 0)
+
+
+# ---- ksw_global2 (CIGAR generation): the rolling-row C restatement vs the whole-matrix Python one ----
+@pytest.mark.parametrize("scoring", [{}, dict(a=2, b=5, o_del=5, e_del=2, o_ins=7, e_ins=1), dict(a=1, b=1, o_del=1, e_del=1, o_ins=1, e_ins=1),
+                                     dict(a=1, b=9, o_del=0, e_del=1, o_ins=0, e_ins=3)])
+def test_global_c_vs_python_random(scoring):
+    """score and CIGAR, op for op: the tie rules of the traceback (diagonal over deletion over insertion; a gap continues only if
+    extending beat opening strictly) decide where an indel inside a repeat lands, which is what downstream tools see"""
+    rng = np.random.default_rng(42)
+    opt = qmo_py.default_opt()
+    for k, v in scoring.items():
+        setattr(opt, k, v)
+    kw = {k: getattr(opt, k) for k in ("a", "b", "o_del", "e_del", "o_ins", "e_ins")}
+    n_gapped = 0
+    for it in range(400):
+        qlen = int(rng.integers(1, 70))
+        kind = it % 4
+        if kind == 0:                   # low-complexity: many equally good placements of a gap
+            unit = rng.integers(0, 4, int(rng.integers(1, 4))).astype(np.uint8)
+            q = np.resize(unit, qlen)
+        else:
+            q = rng.integers(0, 4, qlen).astype(np.uint8)
+        t = mutate(rng, q, [0.0, 0.03, 0.10, 0.05][kind], [0.08, 0.0, 0.04, 0.10][kind])
+        if kind == 3 and rng.random() < 0.5:
+            t = np.concatenate([t, rng.integers(0, 4, int(rng.integers(1, 6))).astype(np.uint8)])
+        if rng.random() < 0.1:
+            q = q.copy()
+            q[rng.integers(0, qlen)] = 4
+        if len(t) == 0:
+            continue
+        w = abs(len(t) - qlen) + int(rng.choice([3, 5, 12, 100]))
+        got = qmo_py.ksw_global2(q, t, w, opt)
+        want = ksw_py.ksw_global2(list(q), list(t), w, **kw)
+        assert got == want, (it, list(q), list(t), w, got, want)
+        assert sum(l for op, l in got[1] if op in (0, 1)) == qlen and sum(l for op, l in got[1] if op in (0, 2)) == len(t)
+        n_gapped += any(op != 0 for op, _ in got[1])
+    assert n_gapped > 100
