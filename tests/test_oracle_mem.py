@@ -201,3 +201,72 @@ def test_count_tensor_equals_an_independent_restatement(cfg, n, popt):
     got = pileup_py.count_tensor(offs, ref.l_pac, alns, codes, quals, lens, po.min_mapq, po.min_bq, bool(po.count_orphans), bool(po.ignore_overlaps))
     assert np.array_equal(got, want), np.argwhere(got != want)[:5]
     assert want[:, 14].sum() > n * L and (cfg != "cfg5" or (want[:, 12].sum() > 0 and want[:, 13].sum() > 0 and want[:, 5].sum() > 0))
+
+
+@pytest.mark.parametrize("cfg, n", [("cfg1", 3000), ("cfg5", 1500), ("cfg3", 2500)])
+def test_insert_size_model_equals_an_independent_restatement(cfg, n):
+    """mem_pestat twice: oracle/qmo_mem.c against oracle/pestat_py.py (written separately from SURVEY.md A.6) on the same
+    region lists -- windows, failed flags and the double-precision mean / deviation, bit for bit"""
+    from oracle import pestat_py
+    W = {"cfg1": workloads.config1, "cfg5": workloads.config5, "cfg3": workloads.config3}[cfg](n)
+    codes, _, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    o = qmo_py.align_se(ref, codes, lens, opt=opt)
+    want = qmo_py.pestat(ref, o["regs"], o["n_regs"], opt=opt)
+    got, n_obs = pestat_py.pestat(ref.l_pac, o["regs"], o["n_regs"])
+    assert n_obs[1] > 0.8 * n * (0.85 if cfg == "cfg3" else 1)          # FR pairs dominate
+    for d in range(4):
+        assert bool(want[d]["failed"]) == bool(got[d]["failed"]), d
+        if not got[d]["failed"]:
+            assert (int(want[d]["low"]), int(want[d]["high"])) == (got[d]["low"], got[d]["high"]), d
+            assert float(want[d]["avg"]) == got[d]["avg"] and float(want[d]["std"]) == got[d]["std"], d
+    assert not got[1]["failed"]
+
+
+def test_insert_size_model_all_orientations_synthetic():
+    """hand-made region lists: all four orientation bins filled (one below the 5 % rule, one below ten samples), outliers,
+    second-best regions that do and do not disqualify a pair, mates on different contigs"""
+    from oracle import pestat_py
+    W = workloads.config3(10)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    l_pac = ref.l_pac
+    rng = np.random.default_rng(9)
+    n = 6000
+    regs = np.zeros((2 * n, qmo_py.MAX_REGS), dtype=qmo_py.REG_DTYPE)
+    n_regs = np.ones(2 * n, dtype=np.int32)
+    for p in range(n):
+        u = rng.random()
+        d = 1 if u < 0.80 else 0 if u < 0.93 else 3 if u < 0.998 else 2       # FR 80 %, FF 13 %, RR 6.8 % , RF ~0.2 % (< 10 samples)
+        ins = int(rng.normal(300, 30)) if rng.random() > 0.03 else int(rng.integers(1, 12000))
+        b1 = int(rng.integers(20000, 200000))
+        if rng.random() < 0.5:
+            b1 = 2 * l_pac - 1 - b1                                               # read 1 on the reverse strand
+        r1 = b1 >= l_pac
+        # invert mem_infer_dir: pick p2 on read 1's strand, then map it back to read 2's own strand
+        same = d in (0, 3)
+        p2 = b1 + ins if d in (0, 1) else b1 - ins
+        b2 = p2 if same else 2 * l_pac - 1 - p2
+        for e, b in ((0, b1), (1, b2)):
+            r = regs[2 * p + e]
+            r[0]["rb"], r[0]["re"], r[0]["qb"], r[0]["qe"], r[0]["score"], r[0]["rid"] = b, b + 150, 0, 150, 140, 0
+            if rng.random() < 0.2:                                                # a second region: overlapping or not, strong or weak
+                n_regs[2 * p + e] = 2
+                qb = int(rng.choice([0, 100]))
+                r[1]["rb"], r[1]["re"], r[1]["qb"], r[1]["qe"], r[1]["rid"] = b + 5000, b + 5100, qb, qb + 50 + int(rng.integers(0, 60)), 0
+                r[1]["score"] = int(rng.choice([40, 111, 112, 113, 130]))
+        if rng.random() < 0.02:
+            regs[2 * p + 1][0]["rid"] = 1
+        if rng.random() < 0.02:
+            n_regs[2 * p] = 0
+    want = qmo_py.pestat(ref, regs, n_regs)
+    got, n_obs = pestat_py.pestat(l_pac, regs, n_regs)
+    assert min(n_obs[0], n_obs[1], n_obs[3]) > 200 and 0 < n_obs[2]
+    assert [bool(x["failed"]) for x in got] == [False, False, True, False] or n_obs[2] >= 10
+    for d in range(4):
+        assert bool(want[d]["failed"]) == bool(got[d]["failed"]), (d, n_obs)
+        if not got[d]["failed"]:
+            assert (int(want[d]["low"]), int(want[d]["high"])) == (got[d]["low"], got[d]["high"]), d
+            assert float(want[d]["avg"]) == got[d]["avg"] and float(want[d]["std"]) == got[d]["std"], d
