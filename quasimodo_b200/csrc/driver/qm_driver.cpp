@@ -9,6 +9,7 @@
 //                      [-A -B -O -E -L -U -T -d -c -D -W: bwa mem's options of the same letters, -A scaling the others as bwa does]
 //                      [-q / --min-mapq N] [-Q / --min-bq N] [--count-orphans 1] [--ignore-overlaps 1]: the mpileups' -q -Q -A -x
 //                      [--stage-ms 1: per-stage device time (CUDA events) of every GPU in the log]
+//                      [--benchmark FILE (every command): wall time, peak memory, I/O and CPU load as a Snakemake benchmark TSV]
 //                      [--print-options 1: print the alignment options the command line resolves to and exit (host only)]
 //        an option the command does not know is a usage error
 //        --mpileup: the text pileup of `samtools mpileup -f ref bam` (rules/vcfcall.smk:39, input of the VarScan rule) with -B
@@ -41,6 +42,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
+#include <ctime>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -1486,13 +1488,56 @@ int cmd_bam_from_records(const Args &a, const std::string &cmdline)
 
 }  // namespace
 
+// --benchmark FILE (any command): the job's resources in the shape of a Snakemake `benchmark:` file (one header line, one row:
+// s, h:m:s, max_rss, max_vms, max_uss, max_pss, io_in, io_out in MB, mean_load in percent), the format
+// scripts/resource_benchmark.R reads -- the rule `bwa` this driver replaces has no `benchmark:` of its own (rules/bwa.smk:1-19),
+// rules `mpileup` and `bcftools` do (rules/vcfcall.smk:32-33,108-109).  Written when the process ends, whatever its exit status.
+std::string g_benchmark_path;
+std::chrono::steady_clock::time_point g_benchmark_t0;
+clock_t g_benchmark_cpu0;
+
+void write_benchmark()
+{
+    if (g_benchmark_path.empty()) return;
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - g_benchmark_t0).count();
+    auto proc_kb = [](const char *file, const char *key) {           // "Key:   12345 kB" lines of /proc/self/{status,smaps_rollup}
+        double v = 0;
+        if (FILE *fh = fopen(file, "r")) {
+            char ln[256];
+            const size_t kl = strlen(key);
+            while (fgets(ln, sizeof ln, fh)) if (!strncmp(ln, key, kl) && ln[kl] == ':') v += atof(ln + kl + 1);
+            fclose(fh);
+        }
+        return v;
+    };
+    const double rss = proc_kb("/proc/self/status", "VmHWM") / 1024, vms = proc_kb("/proc/self/status", "VmPeak") / 1024;
+    const double pss = proc_kb("/proc/self/smaps_rollup", "Pss") / 1024;
+    const double uss = (proc_kb("/proc/self/smaps_rollup", "Private_Clean") + proc_kb("/proc/self/smaps_rollup", "Private_Dirty")) / 1024;
+    const double io_in = proc_kb("/proc/self/io", "rchar") / (1024.0 * 1024.0), io_out = proc_kb("/proc/self/io", "wchar") / (1024.0 * 1024.0);
+    const double cpu = (double)(clock() - g_benchmark_cpu0) / CLOCKS_PER_SEC;      // process CPU time since main(), every thread
+    FILE *fh = fopen(g_benchmark_path.c_str(), "w");
+    if (!fh) { fprintf(stderr, "qm_driver: cannot create %s\n", g_benchmark_path.c_str()); return; }
+    const long ws = (long)wall;
+    fprintf(fh, "s\th:m:s\tmax_rss\tmax_vms\tmax_uss\tmax_pss\tio_in\tio_out\tmean_load\n");
+    fprintf(fh, "%.4f\t%ld:%02ld:%02ld\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\n", wall, ws / 3600, ws / 60 % 60, ws % 60, rss, vms, uss, pss, io_in, io_out,
+            wall > 0 ? 100.0 * cpu / wall : 0.0);
+    fclose(fh);
+}
+
 int main(int argc, char **argv)
 {
+    g_benchmark_t0 = std::chrono::steady_clock::now();
+    g_benchmark_cpu0 = clock();
     if (argc < 2) die(1, "usage: qm_driver sample|decontam|bam-from-records|vcf-index|fastq-check|selftest [options]   (%s)", qm_version());
     std::string cmdline;
     for (int i = 0; i < argc; ++i) { if (i) cmdline += ' '; cmdline += argv[i]; }
     const std::string cmd = argv[1];
-    const Args a = parse_args(argc, argv, 2);
+    Args a = parse_args(argc, argv, 2);
+    if (a.has("benchmark")) {
+        g_benchmark_path = a.get("benchmark");
+        a.kv.erase("benchmark");
+        atexit(write_benchmark);
+    }
     if (cmd == "sample") return cmd_sample(a, cmdline, false);
     if (cmd == "decontam") return cmd_sample(a, cmdline, true);
     if (cmd == "bam-from-records") return cmd_bam_from_records(a, cmdline);

@@ -1,6 +1,8 @@
 """CPU tests of the C++ host driver's file formats: the BAM + BAI writer is run on alignment
 records produced by the CPU oracle (`qm_driver bam-from-records --perm`, which touches no GPU) and read back with the
 test-side BAM reader; record order is checked against the restated samtools comparator (oracle/sort_py.py)."""
+import re
+
 import numpy as np
 import pytest
 
@@ -251,3 +253,19 @@ def test_fastq_side_parses_what_bwa_would(tmp_path):
 def test_driver_selftest():
     """host-only checks of helpers that otherwise only run with several GPUs (the by-key merge of the per-GPU indel allele tables)"""
     assert drvutil.run_driver(["selftest"]).stdout.strip() == "selftest ok"
+
+
+def test_driver_benchmark_file_has_snakemakes_shape(tmp_path):
+    """--benchmark FILE: one header line + one row in the column order of a Snakemake `benchmark:` file, which is what
+    scripts/resource_benchmark.R reads (read_tsv(..., skip = 1) with nine column names; it uses s, max_rss and io_out)"""
+    vcf = tmp_path / "x.vcf"
+    vcf.write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\nc1\t5\t.\tA\tC\t50\t.\tDP=20\n")
+    bench = tmp_path / "x.benchmark.txt"
+    drvutil.run_driver(["vcf-index", "--vcf", vcf, "--benchmark", bench])
+    head, row = bench.read_text().splitlines()
+    assert head.split("\t") == ["s", "h:m:s", "max_rss", "max_vms", "max_uss", "max_pss", "io_in", "io_out", "mean_load"]
+    f = row.split("\t")
+    assert len(f) == 9 and re.fullmatch(r"\d+:\d\d:\d\d", f[1])
+    v = [float(x) for x in f[:1] + f[2:]]
+    assert 0 <= v[0] < 60 and 1 < v[1] < 4096 and v[2] >= v[1] and v[5] > 0 and all(x >= 0 for x in v) and v[7] < 100 * 64
+    assert (tmp_path / "x.vcf.gz.tbi").exists()
