@@ -17,6 +17,12 @@ RULE_LOGS = {
     "bwa": ("report_dir", "/bwa/{sample}.{ref_name}.log"),
     "rmdup": ("report_dir", "/picard/{sample}.{ref_name}.rmdup.metrics.txt"),
 }
+# `benchmark:` files of the replaced rules (rules/vcfcall.smk:32-33,108-109; `bwa` and `rmdup` declare none): one driver job stands
+# for all four rules, its `--benchmark` file goes to the last rule's path
+RULE_BENCHMARKS = {
+    "mpileup": ("report_dir", "/benchmarks/{sample}.{ref_name}.mpileup.benchmark.txt"),
+    "bcftools": ("report_dir", "/benchmarks/{sample}.{ref_name}.bcftools.benchmark.txt"),
+}
 # files the rules' shell lines leave next to a declared output (`samtools index`, `tabix -p vcf`)
 SIDE_FILES = {("bwa", "sortedbam"): ".bai", ("rmdup", "rmdupbam"): ".bai", ("bcftools", "vcf_bgz"): ".tbi"}
 # which driver option writes which declared path
@@ -30,8 +36,15 @@ def expand(dirs, rule, name, sample, ref_name):
     return dirs[var] + pat.format(sample=sample, ref_name=ref_name)
 
 
-def sample_command(driver, dirs, sample, ref_name, ref_fa, r1, r2, threads=4, extra=()):
-    """-> (argv, [every path the four reference rules declare or leave behind]) for one {sample}.{ref_name}"""
+def benchmark_path(dirs, rule, sample, ref_name):
+    var, pat = RULE_BENCHMARKS[rule]
+    return dirs[var] + pat.format(sample=sample, ref_name=ref_name)
+
+
+def sample_command(driver, dirs, sample, ref_name, ref_fa, r1, r2, threads=4, extra=(), benchmark=False):
+    """-> (argv, [every path the four reference rules declare or leave behind]) for one {sample}.{ref_name};
+    benchmark=True adds `--benchmark` at rule bcftools' benchmark path (not part of the returned list: Snakemake does not
+    fail a job over it)"""
     argv = [driver, "sample", "--ref", ref_fa, "--r1", r1, "--r2", r2, "--sample", sample, "-t", str(threads), "--rmdup", "1"]
     paths = []
     for key, opt in DRIVER_OPTION.items():
@@ -43,4 +56,8 @@ def sample_command(driver, dirs, sample, ref_name, ref_fa, r1, r2, threads=4, ex
         if key in SIDE_FILES:
             paths.append(p + SIDE_FILES[key])
     os.makedirs(os.path.dirname(expand(dirs, "bwa", "log", sample, ref_name)), exist_ok=True)
+    if benchmark:
+        b = benchmark_path(dirs, "bcftools", sample, ref_name)
+        os.makedirs(os.path.dirname(b), exist_ok=True)
+        argv += ["--benchmark", b]
     return argv + list(extra), paths

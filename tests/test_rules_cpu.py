@@ -35,16 +35,18 @@ def parse_rule(path, rule):
 
     outs = entries(section("output"))
     log = entries(section("log"))
-    return outs, (log.get("") if log else None)
+    bench = entries(section("benchmark"))
+    return outs, (log.get("") if log else None), (bench.get("") if bench else None)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is not on this machine")
 def test_declared_outputs_of_the_replaced_rules_are_all_produced():
     where = {"bwa": "bwa.smk", "rmdup": "rmdup.smk", "mpileup": "vcfcall.smk", "bcftools": "vcfcall.smk"}
     for rule, f in where.items():
-        outs, log = parse_rule(os.path.join(REF, f), rule)
+        outs, log, bench = parse_rule(os.path.join(REF, f), rule)
         assert outs == rules.RULE_OUTPUTS[rule], (rule, outs)
         assert log == rules.RULE_LOGS.get(rule), (rule, log)
+        assert bench == rules.RULE_BENCHMARKS.get(rule), (rule, bench)
         for name in outs:
             assert (rule, name) in rules.DRIVER_OPTION, f"output {name!r} of rule {rule} has no driver option"
     # the shell lines' side files: `samtools index` after bwa and rmdup, `tabix -p vcf` after bcftools
@@ -61,3 +63,6 @@ def test_sample_command_names_every_path(tmp_path):
         assert argv[argv.index(opt) + 1] in paths
     assert str(tmp_path / "seq_dir" / "bam" / "TM-1-1.Merlin.bam") in paths
     assert str(tmp_path / "snpcall_dir" / "bcftools" / "TM-1-1.Merlin.bcftools.vcf.gz.tbi") in paths
+    argv_b, paths_b = rules.sample_command("qm_driver", dirs, "TM-1-1", "Merlin", "ref.fa", "a.fq", "b.fq", benchmark=True)
+    assert paths_b == paths and argv_b[:len(argv)] == argv
+    assert argv_b[-2:] == ["--benchmark", str(tmp_path / "report_dir" / "benchmarks" / "TM-1-1.Merlin.bcftools.benchmark.txt")]
