@@ -270,3 +270,22 @@ def test_insert_size_model_all_orientations_synthetic():
         if not got[d]["failed"]:
             assert (int(want[d]["low"]), int(want[d]["high"])) == (got[d]["low"], got[d]["high"]), d
             assert float(want[d]["avg"]) == got[d]["avg"] and float(want[d]["std"]) == got[d]["std"], d
+
+
+@pytest.mark.parametrize("cfg, n, depth", [("cfg1", 3000, 3), ("cfg1", 3000, 8), ("cfg3", 2500, 2), ("cfg5", 1500, 5), ("cfg1", 1500, 250)])
+def test_depth_cap_equals_a_literal_replay_of_the_iterator(cfg, n, depth):
+    """`bcftools mpileup -d N`: which reads htslib's pileup iterator keeps is order dependent; oracle/qmo_pileup.c restates it with a
+    heap of read ends, oracle/depthcap_py.py replays the linked list literally -- the same reads survive"""
+    from oracle import depthcap_py
+    W = {"cfg1": workloads.config1, "cfg5": workloads.config5, "cfg3": workloads.config3}[cfg](n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    alns = qmo_py.run_sample(ref, codes, quals, lens, opt=opt)[0]
+    want = qmo_py.depth_cap(ref, alns, depth)
+    got = depthcap_py.depth_cap(alns, depth)
+    assert np.array_equal(got, want), (int(got.sum()), int(want.sum()), np.flatnonzero(got != want)[:10])
+    everyone = qmo_py.depth_cap(ref, alns, 1 << 30)
+    assert (want <= everyone).all() and (depth >= 250 or want.sum() < everyone.sum())
