@@ -112,3 +112,40 @@ def count_tensor(ref_offs, l_pac, alns, codes, quals, lens, min_mapq=0, min_bq=1
             for p in rd["da"]:
                 counts[base + p, 13] += 1
     return counts.astype(np.int32)
+
+
+def indel_alleles(ref_offs, alns, codes, lens, min_mapq=0, count_orphans=False, seq_bases=11):
+    """The indel allele tally (include/quasimodo_b200.h: anchor = the aligned base in front of the event; an insertion is told
+    apart by its first `seq_bases` bases on the forward strand of the reference, an N among them flagged and stored as A; lengths
+    above 255 clamped) from the BAM view of every admitted read.
+    -> {(rid, anchor pos, type 0 ins / 1 del, length, bases packed 2 bits each, has_n): [forward reads, reverse reads]}"""
+    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+    table = {}
+    for r in range(len(alns)):
+        a, L = alns[r], int(lens[r])
+        if not _admitted(a, min_mapq, count_orphans):
+            continue
+        rev = bool(int(a["flag"]) & 0x10)
+        seq = np.minimum(codes[r, :L], 4)
+        if rev:
+            seq = comp[seq[::-1]]
+        q, ref_pos, anchor = 0, int(a["pos"]), None
+        for c in a["cigar"][:int(a["n_cigar"])]:
+            op, ln = int(c) & 15, int(c) >> 4
+            if op == M:
+                q += ln
+                ref_pos += ln
+                anchor = ref_pos - 1
+            elif op == S:
+                q += ln
+            elif op in (I, D):
+                if anchor is not None:
+                    ins = [int(b) for b in seq[q:q + min(ln, seq_bases)]] if op == I else []
+                    packed = sum((b if b < 4 else 0) << (2 * j) for j, b in enumerate(ins))
+                    key = (int(a["rid"]), anchor, int(op == D), min(ln, 255), packed, int(any(b > 3 for b in ins)))
+                    table.setdefault(key, [0, 0])[1 if rev else 0] += 1
+                if op == I:
+                    q += ln
+                else:
+                    ref_pos += ln
+    return table

@@ -289,3 +289,23 @@ def test_depth_cap_equals_a_literal_replay_of_the_iterator(cfg, n, depth):
     assert np.array_equal(got, want), (int(got.sum()), int(want.sum()), np.flatnonzero(got != want)[:10])
     everyone = qmo_py.depth_cap(ref, alns, 1 << 30)
     assert (want <= everyone).all() and (depth >= 250 or want.sum() < everyone.sum())
+
+
+def test_indel_allele_table_equals_an_independent_restatement():
+    """config 5 (simulated indels): every allele (anchor, type, length, inserted bases) and its forward / reverse support, from
+    oracle/qmo_pileup.c and from oracle/pileup_py.py"""
+    from oracle import pileup_py
+    n = 1500
+    W = workloads.config5(n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    codes[7, 40:44] = 4                                                          # Ns, possibly inside an insertion
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    alns = qmo_py.run_sample(ref, codes, quals, lens, opt=opt)[0]
+    rows = qmo_py.indels(ref, alns, codes, lens)
+    want = {(int(r[0]), int(r[1]), int(r[3]), int(r[2]), int(r[5]), int(r[4])): [int(r[6]), int(r[7])] for r in rows}
+    got = pileup_py.indel_alleles(np.concatenate([[0], np.cumsum(W.ref.lens)]), alns, codes, lens)
+    assert got == want
+    assert len(want) > 100 and any(k[2] == 0 for k in want) and any(k[2] == 1 for k in want) and any(sum(v) > 1 for v in want.values())
