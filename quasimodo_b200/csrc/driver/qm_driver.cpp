@@ -1095,6 +1095,10 @@ int cmd_sample(const Args &a, const std::string &cmdline, bool decontam)
             else if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
         }
         if (devs.empty()) die(1, "--gpus: no device given");
+        for (size_t i = 0; i < devs.size(); ++i) {
+            if (devs[i] < 0 || devs[i] > 1023) die(1, "--gpus: '%s' names no device list (A,B,.. or A-B)", a.get("gpus").c_str());
+            for (size_t j = 0; j < i; ++j) if (devs[j] == devs[i]) die(1, "--gpus: device %d is listed twice", devs[i]);
+        }
         if (decontam && devs.size() > 1) die(1, "decontam runs on one GPU (--gpu I)");
     } else devs.push_back(atoi(a.get("gpu", "0").c_str()));
     const int n_gpu = (int)devs.size();

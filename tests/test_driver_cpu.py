@@ -143,6 +143,9 @@ def test_driver_rejects_bad_input(case):
     # an option the command does not know is a usage error, not a silent run with the default
     p = drvutil.run_driver(["sample", "--ref", case["fa"], "--r1", case["r1"], "--r2", case["r2"], "--min-qual", "3"], check=False)
     assert p.returncode == 1 and "unknown option '--min-qual'" in p.stderr
+    for spec, msg in (("0,0", "listed twice"), ("1-0", "no device given"), ("0,-3", "names no device list")):
+        p = drvutil.run_driver(["sample", "--ref", case["fa"], "--r1", case["r1"], "--r2", case["r2"], "--gpus", spec], check=False)
+        assert p.returncode == 1 and msg in p.stderr, (spec, p.stderr)
     p = drvutil.run_driver(["vcf-index", "--vcf", d / "x.vcf", "--gpu", "0"], check=False)
     assert p.returncode == 1 and "unknown option" in p.stderr
 
