@@ -309,3 +309,62 @@ def test_indel_allele_table_equals_an_independent_restatement():
     got = pileup_py.indel_alleles(np.concatenate([[0], np.cumsum(W.ref.lens)]), alns, codes, lens)
     assert got == want
     assert len(want) > 100 and any(k[2] == 0 for k in want) and any(k[2] == 1 for k in want) and any(sum(v) > 1 for v in want.values())
+
+
+def test_hash_seeds_against_brute_force():
+    """the default seeder's contract: on every diagonal, the maximal runs of read positions whose k-mer equals the
+    reference's there, counting only k-mers that occur 1..32 times on that strand and lie inside one contig.  Brute force over a
+    small two-contig genome with a 3-copy repeat and a 40-copy repeat (above the cap), reads from both strands with errors."""
+    rng = np.random.default_rng(17)
+    k, cap = 31, 32
+    unit200, unit40 = rng.integers(0, 4, 200), rng.integers(0, 4, 40)
+    c0 = np.concatenate([rng.integers(0, 4, 900), unit200, rng.integers(0, 4, 500), unit200, rng.integers(0, 4, 300)] +
+                        [np.concatenate([unit40, rng.integers(0, 4, 3)]) for _ in range(40)])
+    c1 = np.concatenate([rng.integers(0, 4, 700), unit200, rng.integers(0, 4, 600)])
+    fwd = np.concatenate([c0, c1]).astype(np.uint8)
+    lens_ref = np.array([len(c0), len(c1)], np.int64)
+    l_pac = len(fwd)
+    D = np.concatenate([fwd, (3 - fwd[::-1]).astype(np.uint8)])
+    # contig interval of every doubled position (mirrored for the reverse half): a k-mer must not leave it
+    bounds = [(0, len(c0)), (len(c0), l_pac), (l_pac, l_pac + len(c1)), (l_pac + len(c1), 2 * l_pac)]
+    where = {}
+    for lo, hi in bounds:
+        for x in range(lo, hi - k + 1):
+            where.setdefault((lo >= l_pac, D[x:x + k].tobytes()), []).append(x)
+    n = 60
+    L = 150
+    reads = np.full((n, L), 4, np.uint8)
+    for r in range(n):
+        x = int(rng.integers(0, 2 * l_pac - L))
+        rd = D[x:x + L].copy()
+        for j in np.flatnonzero(rng.random(L) < 0.02):
+            rd[j] = (rd[j] + 1 + rng.integers(0, 3)) % 4
+        if r % 7 == 0:
+            rd[int(rng.integers(0, L))] = 4
+        reads[r] = rd
+    ref = qmo_py.Ref(fwd, lens_ref, k=k)
+    o = qmo_py.align_se(ref, reads, np.full(n, L, np.int32))
+    n_multi = 0
+    for r in range(n):
+        hits = set()
+        for q in range(L - k + 1):
+            km = reads[r, q:q + k]
+            if (km > 3).any():
+                continue
+            for half in (False, True):
+                occ = where.get((half, km.tobytes()), [])
+                if 1 <= len(occ) <= cap:
+                    hits.update((q, x) for x in occ)
+        want = []
+        for q, x in sorted(hits):
+            if (q - 1, x - 1) in hits:
+                continue                                                    # not the start of a run
+            run = 1
+            while (q + run, x + run) in hits:
+                run += 1
+            want.append((q, x, k + run - 1))
+        got = sorted((int(s["qbeg"]), int(s["rbeg"]), int(s["len"])) for s in o["seeds"][r][:o["n_seeds"][r]])
+        assert len(want) < qmo_py.MAX_SEEDS
+        assert got == sorted(want), (r, got, want)
+        n_multi += len(want) > 1
+    assert n_multi > 10
