@@ -149,3 +149,102 @@ def indel_alleles(ref_offs, alns, codes, lens, min_mapq=0, count_orphans=False, 
                 else:
                     ref_pos += ln
     return table
+
+
+def mpileup_text(ref_codes, ref_offs, ref_lens, contig_names, alns, codes, quals, lens, min_mapq=0, min_bq=13, count_orphans=False,
+                 ignore_overlaps=False):
+    """The text pileup of `samtools mpileup` (rules/vcfcall.smk:39) with -B semantics, assembled column by column
+    from per-read pileup entries -- a second formulation next to oracle/qmo_pileup.c qmo_mpileup_text.  -> bytes"""
+    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+    n = len(alns)
+    view = [None] * n
+    for r in range(n):
+        a, L = alns[r], int(lens[r])
+        if not _admitted(a, min_mapq, count_orphans):
+            continue
+        rev = bool(int(a["flag"]) & 0x10)
+        seq, ql = np.minimum(codes[r, :L], 4), quals[r, :L].astype(np.int64)
+        if rev:
+            seq, ql = comp[seq[::-1]], ql[::-1]
+        cols, _, _, _ = _entries(a, L)
+        view[r] = dict(a=a, L=L, rev=rev, seq=seq, q=ql.copy(), cols=cols)
+    if not ignore_overlaps:
+        for p in range(n // 2):
+            x, y = view[2 * p], view[2 * p + 1]
+            if x is None or y is None or int(x["a"]["rid"]) != int(y["a"]["rid"]):
+                continue
+            if not (int(x["a"]["flag"]) & 0x2) or (int(x["a"]["flag"]) & 0x8):
+                continue
+            if abs(int(x["a"]["tlen"])) >= 2 * x["L"] or abs(int(y["a"]["tlen"])) >= 2 * y["L"]:
+                continue
+            first, second = (x, y) if (int(x["a"]["pos"]), x["rev"]) <= (int(y["a"]["pos"]), y["rev"]) else (y, x)
+            at = {pos: qp for pos, qp in first["cols"] if qp is not None}
+            for pos, qb in second["cols"]:
+                if qb is None or pos not in at:
+                    continue
+                qa = at[pos]
+                if first["seq"][qa] == second["seq"][qb]:
+                    first["q"][qa], second["q"][qb] = min(200, first["q"][qa] + second["q"][qb]), 0
+                elif first["q"][qa] >= second["q"][qb]:
+                    first["q"][qa], second["q"][qb] = int(0.8 * first["q"][qa]), 0
+                else:
+                    first["q"][qa], second["q"][qb] = 0, int(0.8 * second["q"][qb])
+    # reads reach a column in the order of the sorted BAM: (contig, position, strand), input order on ties
+    order = sorted((r for r in range(n) if view[r] is not None),
+                   key=lambda r: (int(view[r]["a"]["rid"]), int(view[r]["a"]["pos"]), view[r]["rev"], r))
+    columns = {}                                           # (rid, pos) -> [bases string parts, quality chars]; every covered column has an entry
+    for r in order:
+        v = view[r]
+        a, L, rid = v["a"], v["L"], int(v["a"]["rid"])
+        ops = [(int(c) & 15, int(c) >> 4) for c in a["cigar"][:int(a["n_cigar"])]]
+        follows = {}                                       # reference position of the last base of an M / D run -> the indel right after it
+        q, pos = 0, int(a["pos"])
+        for i, (op, ln) in enumerate(ops):
+            if op in (M, D):
+                pos += ln
+                if i + 1 < len(ops) and ops[i + 1][0] in (I, D):
+                    follows[pos - 1] = (ops[i + 1][0], ops[i + 1][1], q + (ln if op == M else 0))
+            if op in (M, I, S):
+                q += ln
+        last = pos - 1
+        letters = "acgtn" if v["rev"] else "ACGTN"
+        nxt = {}                                           # a deleted base borrows the quality of the query base after the deletion
+        pending = []
+        for cpos, qp in v["cols"]:
+            if qp is None:
+                pending.append(cpos)
+            else:
+                for d in pending:
+                    nxt[d] = qp
+                pending = []
+        for cpos, qp in v["cols"]:
+            col = columns.setdefault((rid, cpos), [[], []])
+            qq = qp if qp is not None else nxt.get(cpos, L)
+            qual = int(v["q"][qq]) if qq < L else 0
+            if qual < min_bq:
+                continue
+            s = ""
+            if cpos == int(a["pos"]):
+                s += "^" + chr(126 if int(a["mapq"]) > 93 else int(a["mapq"]) + 33)
+            if qp is None:
+                s += "*"
+            else:
+                b = int(v["seq"][qp])
+                s += ("," if v["rev"] else ".") if b < 4 and b == int(ref_codes[int(ref_offs[rid]) + cpos]) else letters[b]
+            if cpos in follows:
+                kind, ln, q_after = follows[cpos]
+                if kind == I:
+                    s += "+%d" % ln + "".join(letters[int(v["seq"][q_after + j])] if q_after + j < L else letters[4] for j in range(ln))
+                else:
+                    s += "-%d" % ln + "".join(letters[int(ref_codes[int(ref_offs[rid]) + cpos + 1 + j])] if cpos + 1 + j < int(ref_lens[rid]) else letters[4]
+                                              for j in range(ln))
+            if cpos == last:
+                s += "$"
+            col[0].append(s)
+            col[1].append(chr(min(qual + 33, 126)))
+    out = []
+    for (rid, cpos) in sorted(columns):
+        bases, qs = columns[(rid, cpos)]
+        out.append("%s\t%d\t%s\t%d\t%s\t%s\n" % (contig_names[rid], cpos + 1, "ACGT"[int(ref_codes[int(ref_offs[rid]) + cpos])], len(qs),
+                                               "".join(bases) or "*", "".join(qs) or "*"))
+    return "".join(out).encode()

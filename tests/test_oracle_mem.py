@@ -368,3 +368,30 @@ def test_hash_seeds_against_brute_force():
         assert got == sorted(want), (r, got, want)
         n_multi += len(want) > 1
     assert n_multi > 10
+
+
+@pytest.mark.parametrize("cfg, n, popt", [("cfg1", 800, {}), ("cfg5", 500, {}), ("cfg3", 700, {}), ("cfg5", 300, dict(min_bq=30, ignore_overlaps=1))])
+def test_text_pileup_equals_an_independent_restatement(cfg, n, popt):
+    """samtools-mpileup text twice (oracle/qmo_pileup.c and oracle/pileup_py.py): byte-identical, indel strings, read starts and
+    ends, deleted bases and all-filtered columns included"""
+    from oracle import pileup_py
+    W = {"cfg1": workloads.config1, "cfg5": workloads.config5, "cfg3": workloads.config3}[cfg](n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    alns = qmo_py.run_sample(ref, codes, quals, lens, opt=opt)[0]
+    po = qmo_py.PileupOpt(0, 13, 0, 0)
+    for k, v in popt.items():
+        setattr(po, k, v)
+    names = [f"contig{i}" for i in range(len(W.ref.lens))]
+    want = qmo_py.mpileup_text(ref, alns, codes, quals, lens, names, po)
+    offs = np.concatenate([[0], np.cumsum(W.ref.lens)])
+    got = pileup_py.mpileup_text(W.ref.codes, offs, W.ref.lens, names, alns, codes, quals, lens, po.min_mapq, po.min_bq,
+                                 bool(po.count_orphans), bool(po.ignore_overlaps))
+    if got != want:
+        gl, wl = got.split(b"\n"), want.split(b"\n")
+        bad = next(i for i in range(min(len(gl), len(wl))) if gl[i] != wl[i])
+        raise AssertionError((len(gl), len(wl), gl[bad][:300], wl[bad][:300]))
+    assert want.count(b"\n") > 10000 and (cfg != "cfg5" or (b"+1" in want and b"-1" in want and b"*" in want))
