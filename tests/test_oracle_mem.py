@@ -395,3 +395,43 @@ def test_text_pileup_equals_an_independent_restatement(cfg, n, popt):
         bad = next(i for i in range(min(len(gl), len(wl))) if gl[i] != wl[i])
         raise AssertionError((len(gl), len(wl), gl[bad][:300], wl[bad][:300]))
     assert want.count(b"\n") > 10000 and (cfg != "cfg5" or (b"+1" in want and b"-1" in want and b"*" in want))
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg5"])
+def test_single_end_finish_equals_an_independent_restatement(cfg):
+    """batches of 8 pairs have no insert-size model (mem_pestat wants 10 per orientation): no rescue, no pairing, every record is
+    the read's best hit with mem_approx_mapq_se's quality.  Order of the hits (score, then bwa's hash of the read id), primary,
+    sub-optimal score, rivals and MAPQ from oracle/mapq_py.py against the records of oracle/qmo_mem.c -- on a sample whose
+    references share long repeats, so that ties and sub-optimal hits are common"""
+    from oracle import mapq_py
+    n, step = (1600, 8) if cfg == "cfg2" else (800, 8)
+    W = workloads.config2(4, n) if cfg == "cfg2" else workloads.config5(n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    se = qmo_py.align_se(ref, codes, lens, opt=opt)
+    l_pac = ref.l_pac
+    seen = dict(mapped=0, unmapped=0, with_sub=0, mapq0=0, mapq60=0, mid=0)
+    for p0 in range(0, n, step):
+        sl = slice(2 * p0, 2 * (p0 + step))
+        alns, _, _, pes = qmo_py.run_sample(ref, codes[sl], quals[sl], lens[sl], pair_id0=p0, opt=opt)
+        assert all(pes[d]["failed"] for d in range(4))
+        for j in range(2 * step):
+            r = 2 * p0 + j
+            want = mapq_py.finish_single_end(se["regs"][r], int(se["n_regs"][r]), r)
+            a = alns[j]
+            if want is None:
+                assert a["flag"] & 4, r
+                seen["unmapped"] += 1
+                continue
+            assert not (a["flag"] & 4) or a["n_cigar"] == 255, r
+            assert (int(a["score"]), int(a["sub"]), int(a["mapq"])) == (want["score"], want["sub"], want["mapq"]), (r, a, want)
+            assert bool(a["flag"] & 0x10) == (want["rb"] >= l_pac), r
+            seen["mapped"] += 1
+            seen["with_sub"] += want["sub"] > 0
+            seen["mapq0"] += want["mapq"] == 0
+            seen["mapq60"] += want["mapq"] == 60
+            seen["mid"] += 0 < want["mapq"] < 60
+    assert seen["mapped"] > 0.9 * 2 * n and seen["with_sub"] > 30 and seen["mapq0"] > 20 and seen["mid"] > 5, seen
