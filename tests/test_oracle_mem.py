@@ -435,3 +435,43 @@ def test_single_end_finish_equals_an_independent_restatement(cfg):
             seen["mapq60"] += want["mapq"] == 60
             seen["mid"] += 0 < want["mapq"] < 60
     assert seen["mapped"] > 0.9 * 2 * n and seen["with_sub"] > 30 and seen["mapq0"] > 20 and seen["mid"] > 5, seen
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg5", "cfg3"])
+def test_pairing_decision_equals_an_independent_restatement(cfg):
+    """mem_pair + the MAPQ logic of mem_sam_pe twice (mate rescue off, so both see the same hit lists): which hits are reported, the
+    proper-pair flag, AS / XS and the mapping quality of every record"""
+    from oracle import pair_py
+    n = 1500
+    W = {"cfg2": lambda: workloads.config2(4, n), "cfg5": lambda: workloads.config5(n), "cfg3": lambda: workloads.config3(n)}[cfg]()
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    opt.flags = qmo_py.F_NO_RESCUE
+    se = qmo_py.align_se(ref, codes, lens, opt=opt)
+    pes = qmo_py.pestat(ref, se["regs"], se["n_regs"], opt=opt)
+    alns = qmo_py.pair_and_finish(ref, codes, lens, se["regs"].copy(), se["n_regs"].copy(), pes, opt=opt)
+    offs = np.concatenate([[0], np.cumsum(W.ref.lens)])
+    seen = dict(proper=0, improper=0, unmapped=0, lifted=0)
+    for p in range(n):
+        proper, recs = pair_py.finish_pair(ref.l_pac, offs, pes, se["regs"][2 * p], int(se["n_regs"][2 * p]), se["regs"][2 * p + 1],
+                                           int(se["n_regs"][2 * p + 1]), p)
+        for m in (0, 1):
+            a, want = alns[2 * p + m], recs[m]
+            if want is None:
+                assert a["flag"] & 4, (p, m)
+                seen["unmapped"] += 1
+                continue
+            if a["n_cigar"] == 255:
+                continue                                   # CIGAR too long for the record: reported unmapped by both implementations
+            assert not (a["flag"] & 4), (p, m)
+            assert (int(a["score"]), int(a["sub"]), int(a["mapq"]), bool(a["flag"] & 0x10)) == \
+                (want["score"], want["sub"], want["mapq"], want["rb"] >= ref.l_pac), (p, m, a, want)
+            assert bool(a["flag"] & 2) == bool(proper), (p, m)
+        seen["proper" if proper else "improper"] += 1
+        if proper and recs[0] and recs[1]:
+            hs = pair_py.order_and_mark(se["regs"][2 * p], int(se["n_regs"][2 * p]), 2 * p)
+            seen["lifted"] += recs[0]["mapq"] > pair_py.approx_mapq(hs[0]) if hs and hs[0]["rb"] == recs[0]["rb"] else 0
+    assert seen["proper"] > 0.8 * n * (0.85 if cfg == "cfg3" else 1) and seen["improper"] > 3 and seen["lifted"] > 0, seen
