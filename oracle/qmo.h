@@ -13,8 +13,12 @@
  *   - alignment (ksw_extend2 / ksw_global2 / bwa-mem glue), pileup counting: PARITY UNPINNED.
  *     bwa / samtools / bcftools are absent from the image and from /root/reference; the reference
  *     holds no test, fixture or golden vector for them.  The restatement
- *     follows the published algorithms and is cross-checked against an
- *     independent Python restatement (oracle/ksw_py.py).
+ *     follows the published algorithms and is held against second, separately
+ *     written restatements, stage by stage (tests/test_oracle_ksw.py, tests/test_oracle_mem.py):
+ *     oracle/ksw_py.py (ksw_extend2, ksw_align2, ksw_global2), pileup_py.py (counting, indel tally,
+ *     text pileup), pestat_py.py (mem_pestat), mapq_py.py + pair_py.py (primary marking, MAPQ,
+ *     mem_pair and mem_sam_pe's decision), depthcap_py.py (htslib's depth cap), a brute-force seed
+ *     enumeration; FM-index construction is PINNED to bwa's own ref/X.bwt and ref/X.sa bytes.
  *   - evaluation (TP/FP split, caller_performance table): PINNED against the reference's own
  *     program/extract_TP_FP_SNPs.py run in the build container (tests/golden/eval_*).
  *   - truth VCF: produced by the reference's own program/mummer2vcf.py (tests/golden/make_truth.py).
