@@ -25,7 +25,7 @@ def order_and_mark(regs, n, read_id, a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=
     by a better one is secondary to it (`parent` = its index), the better one notes the first such score (`sub`) and counts the
     rivals within one edit's worth of score"""
     hits = [dict(score=int(r["score"]), qb=int(r["qb"]), qe=int(r["qe"]), rb=int(r["rb"]), re=int(r["re"]), csub=int(r["csub"]),
-                 rid=int(r["rid"]), tie=hash_64((read_id + i) & M64), sub=0, rivals=0, parent=-1) for i, r in enumerate(regs[:n])]
+                 rid=int(r["rid"]), truesc=int(r["truesc"]), w=int(r["w"]), tie=hash_64((read_id + i) & M64), sub=0, rivals=0, parent=-1) for i, r in enumerate(regs[:n])]
     hits.sort(key=lambda h: (-h["score"], h["tie"]))
     near = max(a + b, o_del + e_del, o_ins + e_ins)
     heads = [0] if hits else []
@@ -68,4 +68,4 @@ def finish_single_end(regs, n, read_id, T=30, **scoring):
     if not hits or hits[0]["score"] < T:
         return None
     best = hits[0]
-    return dict(score=best["score"], sub=max(best["sub"], best["csub"]), mapq=approx_mapq(best), rb=best["rb"])
+    return dict(score=best["score"], sub=max(best["sub"], best["csub"]), mapq=approx_mapq(best), rb=best["rb"], hit=best)

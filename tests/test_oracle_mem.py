@@ -475,3 +475,42 @@ def test_pairing_decision_equals_an_independent_restatement(cfg):
             hs = pair_py.order_and_mark(se["regs"][2 * p], int(se["n_regs"][2 * p]), 2 * p)
             seen["lifted"] += recs[0]["mapq"] > pair_py.approx_mapq(hs[0]) if hs and hs[0]["rb"] == recs[0]["rb"] else 0
     assert seen["proper"] > 0.8 * n * (0.85 if cfg == "cfg3" else 1) and seen["improper"] > 3 and seen["lifted"] > 0, seen
+
+
+@pytest.mark.parametrize("cfg", ["cfg5", "cfg2"])
+def test_record_generation_equals_an_independent_restatement(cfg):
+    """mem_reg2aln + bwa_gen_cigar2 twice: the hit the single-end finish reports (batches without an insert-size model, so the hit is
+    known) turned into position, strand, CIGAR and NM by oracle/cigar_py.py over oracle/ksw_py.py's whole-matrix global alignment,
+    against the records of oracle/qmo_mem.c.  Config 5 has indels (gapped paths, leftmost placement on the forward strand)."""
+    from oracle import cigar_py, mapq_py
+    n, step = (320, 8) if cfg == "cfg5" else (480, 8)
+    W = workloads.config5(n) if cfg == "cfg5" else workloads.config2(4, n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    L = W.params.read_len
+    lens = np.full(2 * n, L, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    se = qmo_py.align_se(ref, codes, lens, opt=opt)
+    fwd = np.asarray(W.ref.codes, dtype=np.uint8)
+    doubled = np.concatenate([fwd, (3 - fwd[::-1]).astype(np.uint8)])
+    offs = [int(x) for x in np.concatenate([[0], np.cumsum(W.ref.lens)])]
+    n_gapped = n_clipped = n_rev_gapped = 0
+    for p0 in range(0, n, step):
+        sl = slice(2 * p0, 2 * (p0 + step))
+        alns = qmo_py.run_sample(ref, codes[sl], quals[sl], lens[sl], pair_id0=p0, opt=opt)[0]
+        for j in range(2 * step):
+            r = 2 * p0 + j
+            fin = mapq_py.finish_single_end(se["regs"][r], int(se["n_regs"][r]), r)
+            a = alns[j]
+            if fin is None or a["n_cigar"] == 255:
+                continue
+            rec = cigar_py.hit_to_record(doubled, ref.l_pac, offs, codes[r, :L], fin["hit"], w=W.w)
+            got = [(int(c) & 15, int(c) >> 4) for c in a["cigar"][:int(a["n_cigar"])]]
+            assert (int(a["rid"]), int(a["pos"]), bool(a["flag"] & 0x10), got, int(a["nm"])) == \
+                (rec["rid"], rec["pos"], rec["rev"], rec["cigar"], rec["nm"]), (r, a, rec)
+            gapped = any(op in (1, 2) for op, _ in got)
+            n_gapped += gapped
+            n_rev_gapped += gapped and rec["rev"]
+            n_clipped += any(op == 4 for op, _ in got)
+    assert n_clipped > 5 and (cfg != "cfg5" or (n_gapped > 20 and n_rev_gapped > 5)), (n_gapped, n_rev_gapped, n_clipped)
