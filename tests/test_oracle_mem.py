@@ -514,3 +514,47 @@ def test_record_generation_equals_an_independent_restatement(cfg):
             n_rev_gapped += gapped and rec["rev"]
             n_clipped += any(op == 4 for op, _ in got)
     assert n_clipped > 5 and (cfg != "cfg5" or (n_gapped > 20 and n_rev_gapped > 5)), (n_gapped, n_rev_gapped, n_clipped)
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg3"])
+def test_flags_and_mate_fields_follow_the_sam_rules(cfg):
+    """every pair of records against the SAM-level rules bwa's mem_aln2sam implements, stated from the SAM side: 0x1 / 0x40 / 0x80, 0x8
+    and 0x20 mirror the mate's 0x4 and 0x10, an unmapped read sits at its mate's coordinate (and takes its strand bit), RNEXT / PNEXT
+    are the mate's, TLEN spans the two 5' ends (signed, +-1 inclusive, 0 when a mate is unmapped or on another contig), 0x2 only
+    when both are mapped to one contig"""
+    n = 2500
+    W = {"cfg1": workloads.config1, "cfg3": workloads.config3}[cfg](n)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    lens[[4, 9]] = [20, 25]                                                   # too short to seed: unmapped reads with mapped mates
+    codes[4, 20:] = 4
+    codes[9, 25:] = 4
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns = qmo_py.run_sample(ref, codes, quals, lens)[0]
+    seen = dict(both=0, one=0, none=0, cross=0)
+    for p in range(n):
+        pair = alns[2 * p:2 * p + 2]
+        placed = [not (int(x["flag"]) & 4) for x in pair]
+        ends5 = []
+        for x in pair:
+            span = sum(int(c) >> 4 for c in x["cigar"][:int(x["n_cigar"])] if (int(c) & 15) in (0, 2)) if int(x["n_cigar"]) != 255 else 0
+            ends5.append(int(x["pos"]) + (span - 1 if int(x["flag"]) & 0x10 else 0))
+        for m in (0, 1):
+            me, mate, f = pair[m], pair[1 - m], int(pair[m]["flag"])
+            assert f & 0x1 and bool(f & 0x40) == (m == 0) and bool(f & 0x80) == (m == 1) and not (f & 0x900)
+            assert bool(f & 0x8) == (not placed[1 - m])
+            if placed[m] or placed[1 - m]:
+                assert bool(f & 0x20) == bool(int(mate["flag"]) & 0x10)
+                assert (int(me["mate_rid"]), int(me["mate_pos"])) == (int(mate["rid"]), int(mate["pos"]))
+            else:
+                assert (int(me["rid"]), int(me["mate_rid"]), int(me["tlen"])) == (-1, -1, 0)
+            if not placed[m] and placed[1 - m]:
+                assert (int(me["rid"]), int(me["pos"])) == (int(mate["rid"]), int(mate["pos"])) and bool(f & 0x10) == bool(int(mate["flag"]) & 0x10)
+            if placed[0] and placed[1] and int(pair[0]["rid"]) == int(pair[1]["rid"]):
+                d = ends5[1 - m] - ends5[m]
+                assert int(me["tlen"]) == d + (d > 0) - (d < 0), (p, m)
+            else:
+                assert int(me["tlen"]) == 0 and not (f & 0x2)
+        seen["both" if all(placed) else "none" if not any(placed) else "one"] += 1
+        seen["cross"] += all(placed) and int(pair[0]["rid"]) != int(pair[1]["rid"])
+    assert seen["both"] > 0.85 * n and seen["one"] >= 2 and (cfg != "cfg3" or seen["none"] + seen["cross"] >= 0), seen
