@@ -17,7 +17,8 @@
  *     written restatements, stage by stage (tests/test_oracle_ksw.py, tests/test_oracle_mem.py):
  *     oracle/ksw_py.py (ksw_extend2, ksw_align2, ksw_global2), pileup_py.py (counting, indel tally,
  *     text pileup), pestat_py.py (mem_pestat), mapq_py.py + pair_py.py (primary marking, MAPQ,
- *     mem_pair and mem_sam_pe's decision), cigar_py.py (mem_reg2aln / bwa_gen_cigar2), depthcap_py.py (htslib's depth cap), a brute-force seed
+ *     mem_pair and mem_sam_pe's decision), cigar_py.py (mem_reg2aln / bwa_gen_cigar2), rescue_py.py (mem_matesw, mem_sort_dedup_patch),
+ *     depthcap_py.py (htslib's depth cap), a brute-force seed
  *     enumeration; FM-index construction is PINNED to bwa's own ref/X.bwt and ref/X.sa bytes.
  *   - evaluation (TP/FP split, caller_performance table): PINNED against the reference's own
  *     program/extract_TP_FP_SNPs.py run in the build container (tests/golden/eval_*).

@@ -558,3 +558,37 @@ def test_flags_and_mate_fields_follow_the_sam_rules(cfg):
         seen["both" if all(placed) else "none" if not any(placed) else "one"] += 1
         seen["cross"] += all(placed) and int(pair[0]["rid"]) != int(pair[1]["rid"])
     assert seen["both"] > 0.85 * n and seen["one"] >= 2 and (cfg != "cfg3" or seen["none"] + seen["cross"] >= 0), seen
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg5"])
+def test_mate_rescue_equals_an_independent_restatement(cfg):
+    """mem_matesw and its loop twice: which windows are searched (count and cells of the local alignments), what each find becomes,
+    how the mate's hit list ends up (order, redundancy filter) -- oracle/rescue_py.py against oracle/qmo_mem.c on a sample where
+    one strain's reads often lack a hit of their own (TB40E reads against AD169)"""
+    from oracle import rescue_py
+    n = 1200 if cfg == "cfg2" else 500
+    W = workloads.config2(1, n) if cfg == "cfg2" else workloads.config5(n)
+    codes, _, _, _ = W.simulate_host(0, n)
+    L = W.params.read_len
+    lens = np.full(2 * n, L, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = W.w
+    se = qmo_py.align_se(ref, codes, lens, opt=opt)
+    pes = qmo_py.pestat(ref, se["regs"], se["n_regs"], opt=opt)
+    regs, n_regs = se["regs"].copy(), se["n_regs"].copy()
+    want_sw, want_cells = qmo_py.mate_rescue(ref, codes, lens, regs, n_regs, pes, opt=opt)
+    fwd = np.asarray(W.ref.codes, dtype=np.uint8)
+    doubled = np.concatenate([fwd, (3 - fwd[::-1]).astype(np.uint8)])
+    offs = [int(x) for x in np.concatenate([[0], np.cumsum(W.ref.lens)])]
+    fields = ("rid", "score", "csub", "qb", "qe", "rb", "re")
+    counters = dict(sw=0, cells=0)
+    n_new = 0
+    for p in range(n):
+        hits = [[{f: int(r[f]) for f in fields} for r in se["regs"][2 * p + m][:int(se["n_regs"][2 * p + m])]] for m in (0, 1)]
+        got = rescue_py.rescue_pair(doubled, ref.l_pac, offs, W.ref.lens, pes, hits, [codes[2 * p, :L], codes[2 * p + 1, :L]], opt, counters)
+        for m in (0, 1):
+            want = [{f: int(r[f]) for f in fields} for r in regs[2 * p + m][:int(n_regs[2 * p + m])]]
+            assert got[m] == want, (p, m, got[m], want)
+            n_new += len(want) > len(hits[m])
+    assert (counters["sw"], counters["cells"]) == (want_sw, want_cells) and want_sw > (50 if cfg == "cfg2" else 5) and n_new > (20 if cfg == "cfg2" else 2), (counters, want_sw, n_new)
