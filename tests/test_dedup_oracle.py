@@ -38,3 +38,23 @@ def test_pairs_fragments_and_clips():
     quals[0, :50] = 14                                                               # qualities below 15 do not count
     dup = dedup_py.mark_duplicates(alns, quals, lens)
     assert dup.tolist()[:3] == [True, False, True]
+
+
+def test_dictionary_and_sorted_table_formulations_agree():
+    """oracle/dedup_py.py (groups in dictionaries) against oracle/dedup_sort_py.py (one sorted table of read ends, runs of equal keys,
+    as picard works) on a deep sample of a small genome -- thousands of positional duplicates, fragments whose mate is unplaced,
+    soft-clipped ends -- and on the hand-made cases above"""
+    from oracle import dedup_sort_py
+    from quasimodo_b200 import workloads
+    n = 12_000
+    W = workloads.Workload("phix-deep", [("Phix", 1)], ["Phix"], n, 901)
+    codes, quals, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, 150, np.int32)
+    codes[1:800:2] = 4                                       # 400 unplaced second mates
+    codes[1001:1400:2, 120:] = (codes[1001:1400:2, 120:] + 1) % 4          # ruined tails: soft clips at 3' ends
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    alns = qmo_py.run_sample(ref, codes, quals, lens)[0]
+    a, b = dedup_py.mark_duplicates(alns, quals, lens), dedup_sort_py.mark_duplicates(alns, quals, lens)
+    assert np.array_equal(a, b), np.flatnonzero(a != b)[:10]
+    clipped = sum(1 for x in alns if x["n_cigar"] not in (0, 255) and any((int(c) & 15) == 4 for c in x["cigar"][:x["n_cigar"]]))
+    assert 0.02 < a.mean() < 0.9 and a[:400].any() and clipped > 50
