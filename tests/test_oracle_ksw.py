@@ -161,3 +161,39 @@ def test_global_c_vs_python_random(scoring):
         assert sum(l for op, l in got[1] if op in (0, 1)) == qlen and sum(l for op, l in got[1] if op in (0, 2)) == len(t)
         n_gapped += any(op != 0 for op, _ in got[1])
     assert n_gapped > 100
+
+
+def test_band_retry_of_the_extension_tasks_against_python():
+    """the extension calls mem_chain2aln makes (the oracle's task log on reads with indels, band 2 so that retries happen): each task
+    replayed through the independent ksw_py.ksw_extend2 with bwa's retry rule -- twice the band while the score still moves and the
+    path came within a quarter of the band's edge, at most two tries -- gives the logged result, last band and cell count"""
+    from quasimodo_b200 import workloads
+    n = 150
+    W = workloads.config5(n)
+    codes, _, _, _ = W.simulate_host(0, n)
+    lens = np.full(2 * n, W.params.read_len, np.int32)
+    ref = qmo_py.Ref(W.ref.codes, W.ref.lens, k=31)
+    opt = qmo_py.default_opt()
+    opt.w = 2
+    lg = qmo_py.align_se(ref, codes, lens, opt=opt, want_log=True)["log"]
+    seq = lg["seq"]
+    n_retried = 0
+    pick = np.random.default_rng(1).permutation(len(lg["tasks"]))[:160]
+    for i in pick:
+        t = lg["tasks"][i]
+        q = [int(x) for x in seq[t["q_off"]:t["q_off"] + t["qlen"]]]
+        tg = [int(x) for x in seq[t["t_off"]:t["t_off"] + t["tlen"]]]
+        assert int(t["flags"]) & 1
+        prev = int(t["h0"]) if int(t["flags"]) & 2 else -1
+        cells = 0
+        for attempt in range(2):
+            w = int(t["w"]) << attempt
+            res, c = ksw_py.ksw_extend2(q, tg, int(t["h0"]), w, int(t["end_bonus"]))
+            cells += c
+            if res[0] == prev or res[5] < (w >> 1) + (w >> 2):
+                break
+            prev = res[0]
+        assert tuple(int(x) for x in lg["results"][i]) == res, (i, t)
+        assert (int(lg["w_used"][i]), int(lg["cells"][i])) == (w, cells), (i, t)
+        n_retried += w != int(t["w"])
+    assert n_retried > 3, n_retried
